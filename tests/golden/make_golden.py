@@ -1,0 +1,203 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures in this directory from the REFERENCE's own model code.
+
+Runs only in the build container (needs /root/reference; the GPU box never runs this).  It imports
+``experiments/models_gnn.py`` and ``experiments/models_gnn2D.py`` unchanged from /root/reference and
+executes their classes (GNN_Layer, GNN_LayerLin, MP_PDE_Solver, MP_PDE_SolverLEMLinGated,
+MP_PDE_Solver2DLEMLinGated) in float64 -- the reference's native dtype -- on seeded inputs.  The
+third-party packages those files import are not installed, so they are stubbed with
+the restated semantics of ``oracle/pyg_semantics.py`` / ``oracle.models.lem_forward``: the fixtures
+pin everything the reference's own files compute (feature order, quirks, decoder, gating, time
+stepping) while the third-party boundary stays "parity unpinned".
+
+    python tests/golden/make_golden.py          # rewrites tests/golden/*.npz
+"""
+from __future__ import annotations
+
+import inspect
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+REF = "/root/reference"
+
+from oracle import pyg_semantics as pg            # noqa: E402
+from oracle.models import lem_forward             # noqa: E402
+from tests.util import formula_weights_, grads_digest, random_directed_graph  # noqa: E402
+from msmp_pde_b200 import synth                   # noqa: E402  (input generators only; no kernels)
+from msmp_pde_b200.compat.torch_geometric.data import Data  # noqa: E402
+
+
+# ------------------------------------------------------------------ third-party stubs
+def _install_reference_stubs():
+    tg = types.ModuleType("torch_geometric")
+    tg_data = types.ModuleType("torch_geometric.data")
+    tg_data.Data = Data
+    tg_nn = types.ModuleType("torch_geometric.nn")
+    tg_utils = types.ModuleType("torch_geometric.utils")
+    tg_rand = types.ModuleType("torch_geometric.utils.random")
+    tg_rand.erdos_renyi_graph = lambda *a, **k: (_ for _ in ()).throw(NotImplementedError())
+
+    class MessagePassing(torch.nn.Module):
+        def __init__(self, aggr="add", flow="source_to_target", node_dim=-2):
+            super().__init__()
+            assert aggr == "mean" and flow == "source_to_target" and node_dim == -2
+            self._msg_args = list(inspect.signature(self.message).parameters)
+            self._upd_args = list(inspect.signature(self.update).parameters)[1:]
+
+        def propagate(self, edge_index, **kwargs):
+            j, i = edge_index[0], edge_index[1]
+            margs = []
+            for a in self._msg_args:
+                base, side = a[:-2], a[-2:]
+                margs.append(kwargs[base][i if side == "_i" else j])
+            msg = self.message(*margs)
+            n = kwargs["x"].shape[0]
+            aggr = pg.scatter_mean(msg, i, n)
+            return self.update(aggr, *[kwargs[a] for a in self._upd_args])
+
+    class InstanceNorm(torch.nn.Module):
+        def __init__(self, in_channels, eps=1e-5, affine=False, track_running_stats=False):
+            super().__init__()
+            assert not affine and not track_running_stats
+            self.eps = eps
+
+        def forward(self, x, batch=None):
+            return pg.instance_norm(x, batch, self.eps)
+
+    for n in ("BatchNorm", "GCNConv", "GATConv", "SAGEConv", "TransformerConv", "RGATConv"):
+        setattr(tg_nn, n, type(n, (), {}))
+    tg_nn.MessagePassing, tg_nn.InstanceNorm = MessagePassing, InstanceNorm
+    tg_nn.global_mean_pool = tg_nn.avg_pool_x = None
+    tg.data, tg.nn, tg.utils = tg_data, tg_nn, tg_utils
+    tg_utils.random = tg_rand
+
+    tc = types.ModuleType("torch_cluster")
+    tc.radius_graph, tc.knn_graph = pg.radius_graph, pg.knn_graph
+    ts = types.ModuleType("torch_scatter")
+    ts.scatter = lambda src, index, dim=0, dim_size=None, reduce="sum": (
+        pg.scatter_mean(src, index, dim_size) if reduce == "mean" else pg.scatter_sum(src, index, dim_size))
+
+    lem = types.ModuleType("lem_cuda")
+
+    def lem_fwd(inputs, weights, weights_lin_z, bias, bias_lin_z, y0, z0, dt):
+        with torch.no_grad():
+            ys, zs = lem_forward(inputs, weights, weights_lin_z, bias, bias_lin_z, y0, z0, dt)
+        e = torch.empty(0)
+        return ys, zs, inputs, e, e, e          # all_X slot carries the inputs for the stub backward
+
+    def lem_bwd(gy, gz, all_X, all_X2, all_ms, all_lin, weights, weights_lin_z, bias, bias_lin_z, y0, z0, dt):
+        with torch.enable_grad():
+            leaves = [t.detach().requires_grad_(True) for t in (weights, weights_lin_z, bias, bias_lin_z, y0, z0)]
+            ys, zs = lem_forward(all_X, *leaves[:4], leaves[4], leaves[5], dt)
+            gs = torch.autograd.grad([ys, zs], leaves, [gy, gz], allow_unused=True)
+        return (None,) + tuple(gs)
+
+    lem.forward, lem.backward = lem_fwd, lem_bwd
+
+    plt = types.ModuleType("matplotlib.pyplot")
+    mpl = types.ModuleType("matplotlib")
+    mpl.pyplot = plt
+    h5 = types.ModuleType("h5py")
+    for name, mod in {"torch_geometric": tg, "torch_geometric.data": tg_data, "torch_geometric.nn": tg_nn,
+                      "torch_geometric.utils": tg_utils, "torch_geometric.utils.random": tg_rand,
+                      "torch_cluster": tc, "torch_scatter": ts, "lem_cuda": lem, "matplotlib": mpl,
+                      "matplotlib.pyplot": plt, "h5py": h5}.items():
+        sys.modules[name] = mod
+
+
+def _load_reference():
+    _install_reference_stubs()
+    sys.path.insert(0, REF)
+    torch.Tensor.cuda = lambda self, *a, **k: self          # LEMcuda.__init__ calls .cuda() (models_gnn.py:314)
+    import experiments.models_gnn as mg
+    import experiments.models_gnn2D as mg2
+    assert torch.get_default_dtype() == torch.float64        # temporal/solvers.py:10 side effect
+    return mg, mg2
+
+
+def _np(d):
+    return {k: (v.detach().cpu().numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in d.items()}
+
+
+def _data_arrays(data):
+    return {"in_" + k: getattr(data, k) for k in data.keys()}
+
+
+def layer_case(mg, cls_name, seed, F_u, V, fname):
+    torch.manual_seed(seed)
+    ei, batch = random_directed_graph([23, 40, 9], avg_deg=4.0, seed=seed)
+    n = batch.numel()
+    g = torch.Generator().manual_seed(seed + 1)
+    x = torch.randn(n, 128, generator=g, dtype=torch.float64, requires_grad=True)
+    u = torch.randn(n, F_u, generator=g, dtype=torch.float64)
+    pos = torch.rand(n, 1, generator=g, dtype=torch.float64)
+    var = torch.rand(n, V, generator=g, dtype=torch.float64)
+    wout = torch.randn(n, 128, generator=g, dtype=torch.float64)
+    layer = getattr(mg, cls_name)(128, 128, 128, F_u, V)
+    formula_weights_(layer)
+    out = layer(x, u, pos, var, ei, batch)
+    (out * wout).sum().backward()
+    arrs = dict(in_x=x, in_u=u, in_pos=pos, in_variables=var, in_edge_index=ei, in_batch=batch, in_wout=wout,
+                out=out, grad_x=x.grad)
+    arrs.update({"gdig_" + k: v for k, v in grads_digest(layer).items()})
+    np.savez_compressed(os.path.join(os.path.dirname(__file__), fname), **_np(arrs))
+    print(fname, "out", tuple(out.shape), "E", ei.shape[1])
+
+
+def model_case(cls, cfg_fn, cfg_kwargs, fname, extra_params=None, model_kwargs=None):
+    pde, data, meta = cfg_fn(**cfg_kwargs)
+    if extra_params:
+        g = torch.Generator().manual_seed(7)
+        B = meta["B"]
+        for k in extra_params:
+            vals = 0.2 + torch.rand(B, generator=g, dtype=torch.float64)
+            setattr(data, k, vals.repeat_interleave(meta["nx"])[:, None])
+    eq = meta["eq_variables"] if extra_params is None else extra_params
+    model = cls(pde, time_window=meta["tw"], hidden_features=128, hidden_layer=6, eq_variables=eq,
+                **(model_kwargs or {}))
+    formula_weights_(model)
+    out = model(data)
+    loss = torch.sqrt(torch.nn.functional.mse_loss(out, data.y, reduction="sum"))   # train_helper.py:126,138
+    loss.backward()
+    arrs = _data_arrays(data)
+    arrs.update(out=out, loss=loss, pde_L=pde.L, pde_tmax=pde.tmax, pde_dt=pde.dt)
+    arrs.update({"gdig_" + k: v for k, v in grads_digest(model).items()})
+    np.savez_compressed(os.path.join(os.path.dirname(__file__), fname), **_np(arrs))
+    print(fname, "N", data.x.shape[0], "E", data.edge_index.shape[1], "loss", float(loss),
+          "params", sum(p.numel() for p in model.parameters()))
+
+
+def main():
+    mg, mg2 = _load_reference()
+    layer_case(mg, "GNN_Layer", 11, 25, 1, "layer_gnn.npz")
+    layer_case(mg, "GNN_LayerLin", 12, 50, 3, "layer_gnnlin.npz")
+    model_case(mg.MP_PDE_Solver, synth.config_c1, dict(B=3, nx=40), "mp_pde_c1.npz")
+    model_case(mg.MP_PDE_SolverLEMLinGated, synth.config_c1, dict(B=2, nx=40, seed=3), "msmp_pde_1f.npz",
+               extra_params={"alpha": 3.0, "beta": 0.4, "gamma": 1.0})
+    model_case(mg2.MP_PDE_Solver2DLEMLinGated, synth.config_c2, dict(B=3, nx=40, seed=4), "msmp_pde2d_c2.npz")
+    model_case(mg2.MP_PDE_Solver2DLEMLinGated, synth.config_c3, dict(B=2, nx=100, seed=5, neighbors=3),
+               "msmp_pde2d_c3.npz")
+    # structural fixtures: state_dict key/shape tables
+    import json
+    tables = {}
+    pde1, _, m1 = synth.config_c1(B=1, nx=10)
+    pde2, _, m2 = synth.config_c2(B=1, nx=10)
+    for name, model in {
+        "MP_PDE_Solver": mg.MP_PDE_Solver(pde1, 25, 128, 6, {}),
+        "MP_PDE_SolverLEMLinGated": mg.MP_PDE_SolverLEMLinGated(pde1, 25, 128, 6, {}),
+        "MP_PDE_Solver2DLEMLinGated": mg2.MP_PDE_Solver2DLEMLinGated(pde2, 25, 128, 6, {"a": 1.0, "b": 1.0}),
+    }.items():
+        tables[name] = {k: list(v.shape) for k, v in model.state_dict().items()}
+    with open(os.path.join(os.path.dirname(__file__), "state_dict_tables.json"), "w") as f:
+        json.dump(tables, f, indent=0, sort_keys=True)
+    print({k: len(v) for k, v in tables.items()})
+
+
+if __name__ == "__main__":
+    main()

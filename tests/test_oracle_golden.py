@@ -1,0 +1,80 @@
+"""The oracle against the fixtures produced by the reference's own model code (CPU only)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import models as om
+from tests import golden_io
+from tests.util import formula_weights_, grads_digest, rel_err
+
+TOL = 1e-11      # float64 restatement vs float64 reference: summation-order noise only
+
+
+def _check_digests(model, gold):
+    mine = grads_digest(model)
+    want = golden_io.grad_digests(gold)
+    assert set(mine) == set(want)
+    scale = max(float(np.abs(v[0])) for v in want.values())
+    for k in want:
+        # update_net_2 bias of a GNN_LayerLin has a structurally zero gradient
+        assert np.allclose(mine[k], want[k], rtol=1e-8, atol=1e-10 * max(scale, 1.0)), k
+
+
+@pytest.mark.parametrize("cls,fname,F_u,V", [("GNN_Layer", "layer_gnn.npz", 25, 1),
+                                             ("GNN_LayerLin", "layer_gnnlin.npz", 50, 3)])
+def test_layer_matches_reference(cls, fname, F_u, V):
+    torch.set_default_dtype(torch.float64)
+    g = golden_io.load(fname)
+    layer = getattr(om, cls)(128, 128, 128, F_u, V)
+    formula_weights_(layer)
+    x = torch.from_numpy(g["in_x"]).requires_grad_(True)
+    out = layer(x, torch.from_numpy(g["in_u"]), torch.from_numpy(g["in_pos"]), torch.from_numpy(g["in_variables"]),
+                torch.from_numpy(g["in_edge_index"]), torch.from_numpy(g["in_batch"]))
+    (out * torch.from_numpy(g["in_wout"])).sum().backward()
+    assert rel_err(out, torch.from_numpy(g["out"])) < TOL
+    assert rel_err(x.grad, torch.from_numpy(g["grad_x"])) < TOL
+    _check_digests(layer, g)
+
+
+CASES = [
+    ("MP_PDE_Solver", "mp_pde_c1.npz", "CE", {}, {}),
+    ("MP_PDE_SolverLEMLinGated", "msmp_pde_1f.npz", "CE", {"alpha": 3.0, "beta": 0.4, "gamma": 1.0}, {}),
+    ("MP_PDE_Solver2DLEMLinGated", "msmp_pde2d_c2.npz", "AD", {"a": 1.0, "b": 1.0}, {}),
+    ("MP_PDE_Solver2DLEMLinGated", "msmp_pde2d_c3.npz", "AD", {"a": 1.0, "b": 1.0}, {}),
+]
+
+
+@pytest.mark.parametrize("cls,fname,pde_name,eq,kw", CASES)
+def test_model_matches_reference(cls, fname, pde_name, eq, kw):
+    torch.set_default_dtype(torch.float64)
+    g = golden_io.load(fname)
+    pde, data = golden_io.model_inputs(g, pde_name)
+    model = getattr(om, cls)(pde, time_window=25, hidden_features=128, hidden_layer=6, eq_variables=eq, **kw)
+    formula_weights_(model)
+    out = model(data)
+    loss = torch.sqrt(torch.nn.functional.mse_loss(out, data.y, reduction="sum"))
+    loss.backward()
+    assert rel_err(out, torch.from_numpy(g["out"])) < TOL
+    assert abs(float(loss) - float(g["loss"])) < 1e-9 * float(g["loss"])
+    _check_digests(model, g)
+
+
+def test_state_dict_tables():
+    torch.set_default_dtype(torch.float64)
+    with open(os.path.join(golden_io.GOLDEN_DIR, "state_dict_tables.json")) as f:
+        tables = json.load(f)
+    from msmp_pde_b200.synth import config_c1, config_c2
+    pde1 = config_c1(B=1, nx=10)[0]
+    pde2 = config_c2(B=1, nx=10)[0]
+    models = {
+        "MP_PDE_Solver": om.MP_PDE_Solver(pde1, 25, 128, 6, {}),
+        "MP_PDE_SolverLEMLinGated": om.MP_PDE_SolverLEMLinGated(pde1, 25, 128, 6, {}),
+        "MP_PDE_Solver2DLEMLinGated": om.MP_PDE_Solver2DLEMLinGated(pde2, 25, 128, 6, {"a": 1.0, "b": 1.0}),
+    }
+    for name, m in models.items():
+        got = {k: list(v.shape) for k, v in m.state_dict().items()}
+        assert got == tables[name], name
+        assert repr(m) == "GNN"
