@@ -1,0 +1,118 @@
+/* msmp_b200 -- C ABI of the B200-native MP-PDE / MSMP-PDE message-passing hot path.
+ *
+ * Plain pointers and sizes only (no torch types).  Every entry point
+ *   - works on DEVICE pointers (fp32 / int32 unless stated), row-major, 16-byte aligned rows,
+ *   - enqueues on the caller's stream and returns immediately (0 = MSMP_OK, negative = error;
+ *     -1 bad argument, -2 CUDA launch/runtime error, -3 workspace too small),
+ *   - never allocates and keeps no mutable global state (re-entrant per stream); scratch memory is
+ *     passed in, sized by the matching *_workspace() query.
+ *
+ * What each one replaces in the reference (Leqr/MSMP-PDE; the reference has a single native FFI
+ * boundary, `lem_cuda.forward/backward`, experiments/models_gnn.py:287-302 -- everything else below
+ * replaces Python-level torch / PyG / torch_scatter calls on the same path):
+ *
+ *   msmp_linear_fwd / _wgrad     nn.Linear(+Swish) blocks: message_net_1 in per-node factorised form,
+ *                                update_net_1/2, embedding / lemoutput / double MLPs, LEM gate GEMMs
+ *                                (models_gnn.py:47-58,77-86,201-206,290; models_gnn2D.py:375-379)
+ *   msmp_edge_fwd / _bwd         MessagePassing.propagate: gather + message() + aggr='mean'
+ *                                (models_gnn.py:42,65,69-75,107,128,132-138; torch_scatter atomics)
+ *   msmp_segment_reduce          torch_scatter.scatter(reduce='mean'|'sum') (models_gnn2D.py:600-601)
+ *                                and the by-source gradient scatter of the backward pass
+ *   msmp_instnorm_fwd / _bwd     PyG InstanceNorm (models_gnn.py:59,66,122,129) fused with the MSMP gate
+ *                                blend  h = (1-tau) h + tau sw(.)  (models_gnn.py:1365-1368)
+ *   msmp_lem_*                   lem_cuda.forward / lem_cuda.backward (models_gnn.py:290-292,300)
+ *   msmp_decoder_*               output_mlp Conv1d -> Swish -> Conv1d + time stepping
+ *                                (models_gnn.py:215-219,275-279; models_gnn2D.py:382-386,448-458)
+ */
+#ifndef MSMP_B200_H_
+#define MSMP_B200_H_
+
+#include <stddef.h>
+#include <cuda_runtime_api.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSMP_B200_ABI_VERSION 1
+int msmp_abi_version(void);
+
+/* ---- dense node-level layers ------------------------------------------------------------------
+ * Y[M, Nout] = epilogue( [A0 | A1 | A2] (K = sum ka) * Wt[K, ldw] + bias + side[M, 0:r] * Wside[r, ldw] )
+ *   epilogue(z): z *= swish'(Zmul) if Zmul;  Ypre = z if Ypre;  z = swish(z) if act;  z += R if R;  Y = z.
+ * ka[s] % 32 == 0, lda % 4 == 0, Nout % 4 == 0, ldw >= roundup(Nout,128), r <= 8.
+ * aswish[s] != 0 applies swish to segment s while loading (a3 = swish(z3) is never materialised). */
+int msmp_linear_fwd(const float* const* A, const int* lda, const int* ka, const int* aswish, int nseg,
+                    const float* Wt, int ldw, const float* bias, const float* side, int lds, int r,
+                    const float* Wside, const float* Zmul, int ldz, float* Ypre, int ldpre, int act,
+                    const float* R, int ldr, float* Y, int ldy, int M, int Nout, cudaStream_t stream);
+
+/* dWt[K, Nout] (+)= X[M, K]^T (swish(X) if xswish) * dY[M, Nout];
+ * dWside[r (+1), Nout] (+)= [side | 1]^T * dY  (bias gradient = the implicit ones column when has_bias).
+ * Deterministic: per-CTA partials over row ranges + fixed-order reduction. */
+int msmp_linear_wgrad_splits(int M, int K, int Nout);
+size_t msmp_linear_wgrad_workspace(int M, int K, int Nout, int nside);
+int msmp_linear_wgrad(const float* X, int ldx, int K, int xswish, const float* dY, int lddy, int Nout,
+                      const float* side, int lds, int r, int has_bias, float* dWt, float* dWside,
+                      int accumulate, int M, void* workspace, size_t ws_bytes, cudaStream_t stream);
+
+/* ---- edge kernels (edges sorted by destination; rowptr = CSR offsets by destination) ------------
+ * forward : agg[i] = inv_deg[i] * sum_{e -> i} sw( sw(P[dst e] + Q[src e]) W2^T + b2 );  z2 (optional) keeps
+ *           the second pre-activation for the backward pass.  W2t[k][n] = W2[n][k]. */
+int msmp_edge_tiles(int E);
+int msmp_edge_grid(int E);
+size_t msmp_edge_fwd_workspace(int E);
+int msmp_edge_fwd(const float* P, const float* Q, int ldpq, const int* src, const int* dst, const int* rowptr,
+                  const float* inv_deg, const float* W2t, const float* b2, float* z2, float* agg, int E, int N,
+                  void* workspace, size_t ws_bytes, cudaStream_t stream);
+/* backward: given dagg -> dz1[E,128] (gradient at the first pre-activation), dP[i] = sum_{e->i} dz1[e],
+ *           dW2[n][k], db2[n].  (dQ[j] = sum_{e from j} dz1[e] is msmp_segment_reduce over the CSC order.) */
+size_t msmp_edge_bwd_workspace(int E);
+int msmp_edge_bwd(const float* P, const float* Q, int ldpq, const int* src, const int* dst, const int* rowptr,
+                  const float* inv_deg, const float* W2, const float* z2, const float* dagg, int lddagg,
+                  float* dz1, float* dP, int lddp, float* dW2, float* db2, int E, int N, void* workspace,
+                  size_t ws_bytes, cudaStream_t stream);
+
+/* out[n, 0:128] = scale[n] * sum_{k in [ptr[n], ptr[n+1])} src[perm ? perm[k] : k, 0:128]
+ * (scale == NULL -> sum; scale = 1/max(count,1) -> mean).  One warp per segment, fixed order, no atomics. */
+int msmp_segment_reduce(const float* src, int lds, const int* perm, const int* ptr, const float* scale,
+                        float* out, int ldo, int N, cudaStream_t stream);
+
+/* ---- InstanceNorm (+ gate blend) ------------------------------------------------------------------
+ * mode 0: out = IN(y0).   mode 1: out = (1 - s) h + s * swish(IN(y1)),  s = sigmoid(IN(y0)).
+ * chunk_begin/end: graph-aligned node ranges; graph_chunk_ptr[B+1]: chunks of each graph; node_graph[N].
+ * stat: [mode+1][B][2][128] (mean, rstd) -- written by fwd, read by bwd. */
+size_t msmp_instnorm_workspace(int nchunks, int B);
+int msmp_instnorm_fwd(const float* y0, const float* y1, int ld, const float* h, const int* chunk_begin,
+                      const int* chunk_end, const int* graph_chunk_ptr, const int* node_graph, int nchunks, int B,
+                      int N, int mode, float eps, float* stat, float* out, void* workspace, size_t ws_bytes,
+                      cudaStream_t stream);
+int msmp_instnorm_bwd(const float* dout, const float* y0, const float* y1, int ld, const float* h,
+                      const float* stat, const int* chunk_begin, const int* chunk_end, const int* graph_chunk_ptr,
+                      const int* node_graph, int nchunks, int B, int N, int mode, float* dy0, float* dy1, int lddy,
+                      float* dh, void* workspace, size_t ws_bytes, cudaStream_t stream);
+
+/* ---- LEM recurrence (replaces lem_cuda.forward / .backward, models_gnn.py:290-292,300) -------------
+ * One step t:  G[N,384] = [y_{t-1} | I_t] W^T + b         (msmp_linear_fwd)
+ *              msmp_lem_gate_z: a = dt*sig(G0), b = dt*sig(G1), zc = tanh(G2), z_t = (1-b) z_{t-1} + b zc
+ *              L[N,128] = [z_t | I_t] Wz^T + bz            (msmp_linear_fwd)
+ *              msmp_lem_gate_y: tL = tanh(L), y_t = (1-a) y_{t-1} + a tL
+ * gates[4][N][128] = (a, b, zc, tL) is the per-step state kept for the backward pass.
+ * Backward step (reverse t): msmp_lem_bwd_y (dy in/out, gy external grad or NULL) -> dL, dG[:,0:128];
+ * dz_tot = dz + dL Wz[:, :128] (msmp_linear_fwd); msmp_lem_bwd_z -> dG[:,128:384], dz;
+ * dy += dG W[:, :128] (msmp_linear_fwd); weight gradients by msmp_linear_wgrad over all T*N rows. */
+int msmp_lem_gate_z(const float* G, const float* z_prev, float dt, float* gates, float* z_new, int N,
+                    cudaStream_t stream);
+int msmp_lem_gate_y(const float* L, const float* y_prev, float* gates, float* y_new, int N, cudaStream_t stream);
+int msmp_lem_bwd_y(float* dy, const float* gy, const float* y_prev, const float* gates, float dt, float* dL,
+                   float* dG, int N, cudaStream_t stream);
+int msmp_lem_bwd_z(const float* dz_tot, const float* gz, const float* z_prev, const float* gates, float dt,
+                   float* dG, float* dz, int N, cudaStream_t stream);
+
+/* out[i] = g[i] * swish'(z[i])  (n % 4 == 0) */
+int msmp_mul_dswish(const float* g, const float* z, float* out, size_t n, cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSMP_B200_H_ */

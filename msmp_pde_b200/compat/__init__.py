@@ -46,9 +46,14 @@ def install_shims(stub_io: bool = True) -> list[str]:
                 m = types.ModuleType(name)
                 m.__dict__["__shim__"] = True
 
-                def _fail(*a, __n=name, **k):
-                    raise ImportError(f"{__n} is not installed; msmp_pde_b200 only provides an import stub")
-                m.__getattr__ = lambda attr, __f=_fail: __f     # any attribute is a callable that raises
+                def _getattr(attr, __n=name):
+                    if attr.startswith("__"):
+                        raise AttributeError(attr)
+
+                    def _fail(*a, **k):
+                        raise ImportError(f"{__n}.{attr}: {__n} is not installed; msmp_pde_b200 only provides an import stub")
+                    return _fail
+                m.__getattr__ = _getattr
                 sys.modules[name] = m
                 done.append(name)
         if "matplotlib" in done and "matplotlib.pyplot" in done:

@@ -1,0 +1,247 @@
+// InstanceNorm (PyG semantics, affine=False; models_gnn.py:59,66,122,129) and the MSMP-PDE gate blend
+// (models_gnn.py:1365-1368 / models_gnn2D.py:438-441), forward and backward, fp32 (sm_100a).
+//
+// Per graph g and channel c:  mu = mean_n y,  var = mean_n (y - mu)^2 (biased),  o = (y - mu) * rsqrt(var + eps).
+// Statistics are computed per graph-aligned node chunk with a two-pass (centred) sum, chunks are merged with
+// Chan's formula in a fixed order (bit-stable; no E[x^2]-mu^2 cancellation; no atomics).
+//   mode 0 (plain):  out = o                                           (MP_PDE_Solver stack)
+//   mode 1 (gated):  out = (1 - tau) * h + tau * sw(o_main), tau = sigmoid(o_gate)
+#include "common.cuh"
+#include "msmp_b200.h"
+
+namespace msmp {
+
+// stats layout per tensor: stat[g][0][c] = mu, stat[g][1][c] = rstd
+__global__ void __launch_bounds__(256) k_in_chunk_stats(const float* __restrict__ y0, const float* __restrict__ y1,
+                                                        int ld, const int* __restrict__ chunk_begin,
+                                                        const int* __restrict__ chunk_end, float* __restrict__ cstat,
+                                                        int nchunks) {
+  __shared__ float red[2][128];
+  const float* y = blockIdx.y == 0 ? y0 : y1;
+  const int chunk = blockIdx.x;
+  const int c = threadIdx.x & 127, g = threadIdx.x >> 7;
+  const int b = chunk_begin[chunk], e = chunk_end[chunk];
+  const float n = (float)(e - b);
+  float s = 0.f;
+  for (int r = b + g; r < e; r += 2) s += __ldg(y + (size_t)r * ld + c);
+  red[g][c] = s;
+  __syncthreads();
+  const float mean = (red[0][c] + red[1][c]) / fmaxf(n, 1.f);
+  __syncthreads();
+  float q = 0.f;
+  for (int r = b + g; r < e; r += 2) {
+    float d = __ldg(y + (size_t)r * ld + c) - mean;
+    q = fmaf(d, d, q);
+  }
+  red[g][c] = q;
+  __syncthreads();
+  if (g == 0) {
+    float* o = cstat + ((size_t)blockIdx.y * nchunks + chunk) * 256;
+    o[c] = mean;
+    o[128 + c] = red[0][c] + red[1][c];
+  }
+}
+
+__global__ void __launch_bounds__(128) k_in_finalize(const float* __restrict__ cstat, const int* __restrict__ chunk_begin,
+                                                     const int* __restrict__ chunk_end,
+                                                     const int* __restrict__ graph_chunk_ptr, float* __restrict__ stat,
+                                                     int nchunks, int B, float eps) {
+  const int g = blockIdx.x, c = threadIdx.x;
+  const float* cs = cstat + (size_t)blockIdx.y * nchunks * 256;
+  float n = 0.f, mean = 0.f, m2 = 0.f;
+  for (int k = graph_chunk_ptr[g]; k < graph_chunk_ptr[g + 1]; ++k) {
+    const float nb = (float)(chunk_end[k] - chunk_begin[k]);
+    if (nb <= 0.f) continue;
+    const float mb = cs[(size_t)k * 256 + c], qb = cs[(size_t)k * 256 + 128 + c];
+    const float nt = n + nb;
+    const float d = mb - mean;
+    mean += d * (nb / nt);
+    m2 += qb + d * d * (n * nb / nt);
+    n = nt;
+  }
+  float* o = stat + ((size_t)blockIdx.y * B + g) * 256;
+  o[c] = mean;
+  o[128 + c] = rsqrtf(m2 / fmaxf(n, 1.f) + eps);
+}
+
+// forward apply. y1/stat1/h only used in gated mode.
+__global__ void __launch_bounds__(256) k_in_apply(const float* __restrict__ y0, const float* __restrict__ y1, int ld,
+                                                  const float* __restrict__ stat, const int* __restrict__ node_graph,
+                                                  const float* __restrict__ h, float* __restrict__ out, int N, int B,
+                                                  int mode) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * 32) return;
+  const int row = idx >> 5, c4 = (idx & 31) * 4;
+  const int g = __ldg(node_graph + row);
+  const float* st0 = stat + (size_t)g * 256;
+  float4 mu = ldg4(st0 + c4), rs = ldg4(st0 + 128 + c4);
+  float4 y = ldg4(y0 + (size_t)row * ld + c4);
+  float4 o = make_float4((y.x - mu.x) * rs.x, (y.y - mu.y) * rs.y, (y.z - mu.z) * rs.z, (y.w - mu.w) * rs.w);
+  if (mode == 0) {
+    st4(out + (size_t)row * 128 + c4, o);
+    return;
+  }
+  const float* st1 = stat + ((size_t)B + g) * 256;
+  float4 mu1 = ldg4(st1 + c4), rs1 = ldg4(st1 + 128 + c4);
+  float4 ym = ldg4(y1 + (size_t)row * ld + c4);
+  float4 om = make_float4((ym.x - mu1.x) * rs1.x, (ym.y - mu1.y) * rs1.y, (ym.z - mu1.z) * rs1.z, (ym.w - mu1.w) * rs1.w);
+  float4 hh = ldg4(h + (size_t)row * 128 + c4);
+  float4 r;
+  {
+    float t;
+    t = sigmoidf_(o.x); r.x = (1.f - t) * hh.x + t * swish(om.x);
+    t = sigmoidf_(o.y); r.y = (1.f - t) * hh.y + t * swish(om.y);
+    t = sigmoidf_(o.z); r.z = (1.f - t) * hh.z + t * swish(om.z);
+    t = sigmoidf_(o.w); r.w = (1.f - t) * hh.w + t * swish(om.w);
+  }
+  st4(out + (size_t)row * 128 + c4, r);
+}
+
+// ---- backward -------------------------------------------------------------------------------------
+// d(out)/d(o_gate), d(out)/d(o_main) for one element of the gated blend
+__device__ __forceinline__ void blend_grads(float dout, float og, float om, float h, float& dog, float& dom, float& dh) {
+  const float t = sigmoidf_(og);
+  dog = dout * (swish(om) - h) * t * (1.f - t);
+  dom = dout * t * dswish(om);
+  dh = dout * (1.f - t);
+}
+
+// per chunk: part[chunk][q][c], q = 0: sum do0, 1: sum do0*o0, 2: sum do1, 3: sum do1*o1
+__global__ void __launch_bounds__(256) k_in_bwd_chunk(const float* __restrict__ dout, const float* __restrict__ y0,
+                                                      const float* __restrict__ y1, int ld,
+                                                      const float* __restrict__ stat, const float* __restrict__ h,
+                                                      const int* __restrict__ chunk_begin,
+                                                      const int* __restrict__ chunk_end,
+                                                      const int* __restrict__ node_graph, float* __restrict__ part,
+                                                      int B, int mode) {
+  __shared__ float red[4][128];
+  const int chunk = blockIdx.x;
+  const int c = threadIdx.x & 127, half = threadIdx.x >> 7;
+  const int b = chunk_begin[chunk], e = chunk_end[chunk];
+  float s[4] = {0.f, 0.f, 0.f, 0.f};
+  if (e > b) {
+    const int g = node_graph[b];
+    const float mu0 = stat[(size_t)g * 256 + c], rs0 = stat[(size_t)g * 256 + 128 + c];
+    float mu1 = 0.f, rs1 = 0.f;
+    if (mode == 1) {
+      mu1 = stat[((size_t)B + g) * 256 + c];
+      rs1 = stat[((size_t)B + g) * 256 + 128 + c];
+    }
+    for (int r = b + half; r < e; r += 2) {
+      const float d = __ldg(dout + (size_t)r * 128 + c);
+      const float o0 = (__ldg(y0 + (size_t)r * ld + c) - mu0) * rs0;
+      if (mode == 0) {
+        s[0] += d;
+        s[1] = fmaf(d, o0, s[1]);
+      } else {
+        const float o1 = (__ldg(y1 + (size_t)r * ld + c) - mu1) * rs1;
+        float dog, dom, dh;
+        blend_grads(d, o0, o1, __ldg(h + (size_t)r * 128 + c), dog, dom, dh);
+        s[0] += dog;
+        s[1] = fmaf(dog, o0, s[1]);
+        s[2] += dom;
+        s[3] = fmaf(dom, o1, s[3]);
+      }
+    }
+  }
+  if (half == 1) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) red[q][c] = s[q];
+  }
+  __syncthreads();
+  if (half == 0) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) part[((size_t)chunk * 4 + q) * 128 + c] = s[q] + red[q][c];
+  }
+}
+
+// gm[g][q][c] = (sum over the graph's chunks, fixed order) / n_g
+__global__ void __launch_bounds__(512) k_in_bwd_finalize(const float* __restrict__ part,
+                                                         const int* __restrict__ chunk_begin,
+                                                         const int* __restrict__ chunk_end,
+                                                         const int* __restrict__ graph_chunk_ptr,
+                                                         float* __restrict__ gm) {
+  const int g = blockIdx.x, q = threadIdx.x >> 7, c = threadIdx.x & 127;
+  float s = 0.f, n = 0.f;
+  for (int k = graph_chunk_ptr[g]; k < graph_chunk_ptr[g + 1]; ++k) {
+    s += part[((size_t)k * 4 + q) * 128 + c];
+    n += (float)(chunk_end[k] - chunk_begin[k]);
+  }
+  gm[((size_t)g * 4 + q) * 128 + c] = s / fmaxf(n, 1.f);
+}
+
+// dy = rstd * (do - mean(do) - o * mean(do * o))
+__global__ void __launch_bounds__(256) k_in_bwd_apply(const float* __restrict__ dout, const float* __restrict__ y0,
+                                                      const float* __restrict__ y1, int ld,
+                                                      const float* __restrict__ stat, const float* __restrict__ h,
+                                                      const float* __restrict__ gm,
+                                                      const int* __restrict__ node_graph, float* __restrict__ dy0,
+                                                      float* __restrict__ dy1, int lddy, float* __restrict__ dh, int N,
+                                                      int B, int mode) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * 128) return;
+  const int row = idx >> 7, c = idx & 127;
+  const int g = __ldg(node_graph + row);
+  const float mu0 = stat[(size_t)g * 256 + c], rs0 = stat[(size_t)g * 256 + 128 + c];
+  const float d = dout[idx];
+  const float o0 = (y0[(size_t)row * ld + c] - mu0) * rs0;
+  const float* m = gm + (size_t)g * 4 * 128;
+  if (mode == 0) {
+    dy0[(size_t)row * lddy + c] = rs0 * (d - m[c] - o0 * m[128 + c]);
+    return;
+  }
+  const float mu1 = stat[((size_t)B + g) * 256 + c], rs1 = stat[((size_t)B + g) * 256 + 128 + c];
+  const float o1 = (y1[(size_t)row * ld + c] - mu1) * rs1;
+  float dog, dom, dhv;
+  blend_grads(d, o0, o1, h[idx], dog, dom, dhv);
+  dy0[(size_t)row * lddy + c] = rs0 * (dog - m[c] - o0 * m[128 + c]);
+  dy1[(size_t)row * lddy + c] = rs1 * (dom - m[256 + c] - o1 * m[384 + c]);
+  dh[idx] = dhv;
+}
+
+}  // namespace msmp
+
+using namespace msmp;
+
+extern "C" size_t msmp_instnorm_workspace(int nchunks, int B) {
+  // chunk stats [2][nchunks][256] (fwd) or chunk partials [nchunks][4][128] (bwd) + per-graph means [B][4][128]
+  return ((size_t)nchunks * 512 + (size_t)B * 512) * sizeof(float);
+}
+
+extern "C" int msmp_instnorm_fwd(const float* y0, const float* y1, int ld, const float* h, const int* chunk_begin,
+                                 const int* chunk_end, const int* graph_chunk_ptr, const int* node_graph, int nchunks,
+                                 int B, int N, int mode, float eps, float* stat, float* out, void* workspace,
+                                 size_t ws_bytes, cudaStream_t stream) {
+  if (N < 0 || B < 0 || (mode != 0 && mode != 1) || (ld & 3)) return MSMP_ERR_ARG;
+  if (N == 0) return MSMP_OK;
+  if (ws_bytes < msmp_instnorm_workspace(nchunks, B)) return MSMP_ERR_WORKSPACE;
+  float* cstat = reinterpret_cast<float*>(workspace);
+  const int nt = mode + 1;
+  k_in_chunk_stats<<<dim3(nchunks, nt), 256, 0, stream>>>(y0, y1, ld, chunk_begin, chunk_end, cstat, nchunks);
+  MSMP_CHECK_LAUNCH();
+  k_in_finalize<<<dim3(B, nt), 128, 0, stream>>>(cstat, chunk_begin, chunk_end, graph_chunk_ptr, stat, nchunks, B, eps);
+  MSMP_CHECK_LAUNCH();
+  k_in_apply<<<(N * 32 + 255) / 256, 256, 0, stream>>>(y0, y1, ld, stat, node_graph, h, out, N, B, mode);
+  MSMP_CHECK_LAUNCH();
+  return MSMP_OK;
+}
+
+extern "C" int msmp_instnorm_bwd(const float* dout, const float* y0, const float* y1, int ld, const float* h,
+                                 const float* stat, const int* chunk_begin, const int* chunk_end,
+                                 const int* graph_chunk_ptr, const int* node_graph, int nchunks, int B, int N, int mode,
+                                 float* dy0, float* dy1, int lddy, float* dh, void* workspace, size_t ws_bytes,
+                                 cudaStream_t stream) {
+  if (N < 0 || B < 0 || (mode != 0 && mode != 1)) return MSMP_ERR_ARG;
+  if (N == 0) return MSMP_OK;
+  if (ws_bytes < msmp_instnorm_workspace(nchunks, B)) return MSMP_ERR_WORKSPACE;
+  float* part = reinterpret_cast<float*>(workspace);
+  float* gm = part + (size_t)nchunks * 512;
+  k_in_bwd_chunk<<<nchunks, 256, 0, stream>>>(dout, y0, y1, ld, stat, h, chunk_begin, chunk_end, node_graph, part, B, mode);
+  MSMP_CHECK_LAUNCH();
+  k_in_bwd_finalize<<<B, 512, 0, stream>>>(part, chunk_begin, chunk_end, graph_chunk_ptr, gm);
+  MSMP_CHECK_LAUNCH();
+  k_in_bwd_apply<<<(N * 128 + 255) / 256, 256, 0, stream>>>(dout, y0, y1, ld, stat, h, gm, node_graph, dy0, dy1, lddy, dh,
+                                                            N, B, mode);
+  MSMP_CHECK_LAUNCH();
+  return MSMP_OK;
+}

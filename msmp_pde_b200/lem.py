@@ -1,0 +1,157 @@
+"""LEM (Long Expressive Memory) recurrent encoder -- replaces the absent native extension ``lem_cuda``.
+
+Reference boundary: ``LEMFunction`` / ``LEMcuda`` / ``LEM`` / ``LEMS`` (experiments/models_gnn.py:285-361)
+call ``lem_cuda.forward(inputs, weights, weights_lin_z, bias, bias_lin_z, y0, z0, dt)`` and
+``lem_cuda.backward`` (upstream tk-rusch/LEM ``src/lem_cuda``; source not in the reference tree).
+
+Equations, per step t with X = [y_{t-1} | I_t]:
+    G = X W^T + b -> (G0, G1, G2);  dt_bar = dt*sigmoid(G0);  dt_z = dt*sigmoid(G1)
+    z_t = (1 - dt_z) z_{t-1} + dt_z tanh(G2)
+    y_t = (1 - dt_bar) y_{t-1} + dt_bar tanh([z_t | I_t] Wz^T + bz)
+Column order of ``weights`` / ``weights_lin_z`` is [state(H) | input(ninp)]; this (and the chunk-to-gate
+assignment) cannot be verified without the lem_cuda source and is documented in DESIGN.md.
+No gradient flows to the inputs (LEMFunction.backward returns None for them, models_gnn.py:302).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+from torch import nn
+
+from . import ops
+from .layers import H, pad32
+
+
+class _LEMFn(torch.autograd.Function):
+    """All T steps through msmp_linear_fwd (gate GEMMs) + msmp_lem_gate_* (fused gate math)."""
+
+    @staticmethod
+    def forward(ctx, inputs, weights, weights_lin_z, bias, bias_lin_z, y0, z0, dt):
+        T, N, ninp = inputs.shape
+        dev = inputs.device
+        ip = pad32(ninp)
+        inp = torch.zeros(T, N, ip, dtype=torch.float32, device=dev)
+        inp[:, :, :ninp] = inputs
+        # k-major packs: rows [state(128) | input(ip)]
+        Wt = torch.zeros(H + ip, 3 * H, dtype=torch.float32, device=dev)
+        Wt[:H] = weights[:, :H].t()
+        Wt[H:H + ninp] = weights[:, H:].t()
+        Wzt = torch.zeros(H + ip, H, dtype=torch.float32, device=dev)
+        Wzt[:H] = weights_lin_z[:, :H].t()
+        Wzt[H:H + ninp] = weights_lin_z[:, H:].t()
+        Y = torch.empty(T + 1, N, H, dtype=torch.float32, device=dev)
+        Z = torch.empty(T + 1, N, H, dtype=torch.float32, device=dev)
+        Y[0], Z[0] = y0, z0
+        gates = torch.empty(T, 4, N, H, dtype=torch.float32, device=dev)   # dt_bar, dt_z, tanh(G2), tanh(L)
+        G = torch.empty(N, 3 * H, dtype=torch.float32, device=dev)
+        L = torch.empty(N, H, dtype=torch.float32, device=dev)
+        for t in range(T):
+            ops.linear_fwd([Y[t], inp[t]], Wt, bias=bias, out=G)
+            ops.lem_gate_z(G, Z[t], dt, gates[t], Z[t + 1])
+            ops.linear_fwd([Z[t + 1], inp[t]], Wzt, bias=bias_lin_z, out=L)
+            ops.lem_gate_y(L, Y[t], gates[t], Y[t + 1])
+        ctx.save_for_backward(inp, Y, Z, gates, weights, weights_lin_z)
+        ctx.dt, ctx.ninp = dt, ninp
+        return Y[1:], Z[1:]
+
+    @staticmethod
+    def backward(ctx, gY, gZ):
+        inp, Y, Z, gates, weights, weights_lin_z = ctx.saved_tensors
+        dt, ninp = ctx.dt, ctx.ninp
+        T, N, ip = inp.shape
+        dev = inp.device
+        gY, gZ = gY.contiguous(), gZ.contiguous()
+        Wh = weights[:, :H].contiguous()            # [384][128]: dgrad operand  (dG -> dy_prev)
+        Wzh = weights_lin_z[:, :H].contiguous()     # [128][128]: dgrad operand  (dL -> dz_t)
+        dG = torch.empty(T, N, 3 * H, dtype=torch.float32, device=dev)
+        dL = torch.empty(T, N, H, dtype=torch.float32, device=dev)
+        dy = torch.zeros(N, H, dtype=torch.float32, device=dev)      # carried d/dy_t
+        dz = torch.zeros(N, H, dtype=torch.float32, device=dev)      # carried d/dz_t
+        dz_tot = torch.empty(N, H, dtype=torch.float32, device=dev)
+        for t in range(T - 1, -1, -1):
+            # through y_t = (1-a) y_{t-1} + a tanh(L):  dL, dG0, dy <- dy*(1-a)
+            ops.lem_bwd_y(dy, gY[t], Y[t], gates[t], dt, dL[t], dG[t])
+            # dz_t total = carried + dL Wz[:, :H]  (+ external gZ[t], added inside lem_bwd_z)
+            ops.linear_fwd([dL[t]], Wzh, R=dz, out=dz_tot)
+            # through z_t = (1-b) z_{t-1} + b tanh(G2): dG1, dG2, dz <- d*(1-b)
+            ops.lem_bwd_z(dz_tot, gZ[t], Z[t], gates[t], dt, dG[t], dz)
+            # dy_{t-1} += dG W[:, :H]
+            ops.linear_fwd([dG[t]], Wh, R=dy, out=dy)
+        # weight gradients over all steps at once (M = T*N rows)
+        Kp = H + ip
+        dWt = torch.empty(Kp, 3 * H, dtype=torch.float32, device=dev)
+        dGf, dLf = dG.view(T * N, 3 * H), dL.view(T * N, H)
+        inpf = inp.view(T * N, ip)
+        _, dbias = ops.linear_wgrad(Y[:T].view(T * N, H), dGf, has_bias=True, dWt=dWt[:H])
+        ops.linear_wgrad(inpf, dGf, dWt=dWt[H:])
+        dWzt = torch.empty(Kp, H, dtype=torch.float32, device=dev)
+        _, dbz = ops.linear_wgrad(Z[1:].reshape(T * N, H), dLf, has_bias=True, dWt=dWzt[:H])
+        ops.linear_wgrad(inpf, dLf, dWt=dWzt[H:])
+        dW = torch.cat([dWt[:H].t(), dWt[H:H + ninp].t()], 1)
+        dWz = torch.cat([dWzt[:H].t(), dWzt[H:H + ninp].t()], 1)
+        return None, dW, dWz, dbias[0], dbz[0], dy, dz, None
+
+
+class LEMcuda(nn.Module):
+    """models_gnn.py:305-330 -- same parameter names/shapes/init; fp32 parameters; device follows .to()."""
+
+    def __init__(self, ninp, nhid, dt):
+        super().__init__()
+        if nhid != H:
+            raise ValueError("msmp_b200 LEM kernels are specialised for nhid = 128")
+        self.ninp, self.nhid = ninp, nhid
+        f32 = dict(dtype=torch.float32)
+        self.weights = nn.Parameter(torch.empty(3 * nhid, ninp + nhid, **f32))
+        self.weights_lin_z = nn.Parameter(torch.empty(nhid, ninp + nhid, **f32))
+        self.bias = nn.Parameter(torch.empty(3 * nhid, **f32))
+        self.bias_lin_z = nn.Parameter(torch.empty(nhid, **f32))
+        self.dt = float(dt)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        stdv = 1.0 / math.sqrt(self.nhid)
+        for w in self.parameters():
+            w.data.uniform_(-stdv, +stdv)
+
+    def forward(self, input, states=None):
+        if not input.is_cuda:
+            raise RuntimeError("msmp_pde_b200 LEM runs on CUDA only (no CPU fallback)")
+        x = input.detach().float().contiguous()
+        if states is None:
+            y = x.new_zeros(x.size(1), self.nhid)
+            z = x.new_zeros(x.size(1), self.nhid)
+        else:
+            y, z = states[0].float().contiguous(), states[1].float().contiguous()
+        return _LEMFn.apply(x, self.weights, self.weights_lin_z, self.bias, self.bias_lin_z, y, z, self.dt)
+
+
+class LEM(nn.Module):
+    """models_gnn.py:333-342"""
+
+    def __init__(self, ninp, nhid, dt=1.):
+        super().__init__()
+        self.ninp, self.nhid = ninp, nhid
+        self.rnn = LEMcuda(ninp, nhid, dt)
+
+    def forward(self, input):
+        all_y, all_z = self.rnn(input)
+        return all_y[-1]
+
+
+class LEMS(nn.Module):
+    """models_gnn.py:345-361 -- carries (y_T, z_T) into the next call until reset_states()."""
+
+    def __init__(self, ninp, nhid, dt=1.):
+        super().__init__()
+        self.ninp, self.nhid = ninp, nhid
+        self.rnn = LEMcuda(ninp, nhid, dt)
+        self.states = None
+
+    def forward(self, input):
+        all_y, all_z = self.rnn(input, self.states)
+        self.states = (all_y[-1], all_z[-1])
+        return all_y[-1]
+
+    def reset_states(self):
+        self.states = None

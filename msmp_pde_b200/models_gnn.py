@@ -1,0 +1,123 @@
+"""Drop-in replacements for the classes of ``experiments/models_gnn.py`` (1-field models).
+
+Same class names, constructor arguments, ``forward(data)`` contract, ``__repr__`` and state_dict layout as
+the reference, computed by the msmp_b200 CUDA kernels.  Parameters are fp32 (the
+reference's are float64 because of ``temporal/solvers.py:10``); inputs of any float dtype are cast once at
+entry and the result is returned in ``data.x.dtype`` so ``criterion(pred, graph.y)`` (train_helper.py:126)
+and ``torch.cat((graph.x, pred), 1)`` (common/utils.py:448) behave as before.
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from .graph import get_topology
+from .layers import GNN_Layer, GNN_LayerLin, H, NodeFeatures, Swish, gate_blend  # noqa: F401 (re-exported)
+from .lem import LEM, LEMS, LEMcuda  # noqa: F401 (re-exported)
+from .solver import (cumulative_dt, linear_act, make_decoder, mlp2, pad_cols, require_cuda, variables_1field)
+
+
+class LSTM(nn.Module):
+    """models_gnn.py:758-767 (cuDNN LSTM encoder of the LSTM variants; not on the BASELINE path)."""
+
+    def __init__(self, ninp, nhid):
+        super().__init__()
+        self.ninp, self.nhid = ninp, nhid
+        self.rnn = nn.LSTM(ninp, nhid, dtype=torch.float32)
+
+    def forward(self, input):
+        output, _ = self.rnn(input.float())
+        return output[-1]
+
+
+class _Solver1F(nn.Module):
+    """Shared skeleton of the 1-field solvers: encoder -> (gated) message passing stack -> Conv1d decoder."""
+    layer_cls = GNN_Layer
+    gated = False
+    encoder = "mlp"            # 'mlp' | 'lem'
+    lem_mlp = False            # lemoutput_mlp after the LEM encoder
+
+    def __init__(self, pde, time_window: int = 25, hidden_features: int = 128, hidden_layer: int = 6,
+                 eq_variables: dict = {}):
+        super().__init__()
+        assert time_window in (20, 25, 50)           # models_gnn.py:176
+        if hidden_features != H:
+            raise ValueError("msmp_pde_b200 supports hidden_features = 128 (the reference's only value)")
+        self.pde = pde
+        self.out_features = time_window
+        self.hidden_features, self.hidden_layer = hidden_features, hidden_layer
+        self.time_window, self.eq_variables = time_window, eq_variables
+        nv = len(eq_variables) + 1
+        mk = lambda: self.layer_cls(hidden_features, hidden_features, hidden_features, time_window, nv)
+        self.gnn_layers = nn.ModuleList(mk() for _ in range(hidden_layer))
+        if self.gated:
+            self.gnn_layers_gate = nn.ModuleList(mk() for _ in range(hidden_layer))
+        f32 = dict(dtype=torch.float32)
+        if self.encoder == "mlp":
+            self.embedding_mlp = nn.Sequential(nn.Linear(time_window + 2 + len(eq_variables), hidden_features, **f32),
+                                               Swish(), nn.Linear(hidden_features, hidden_features, **f32), Swish())
+        else:
+            self.embedding_lem = LEM(2 + len(eq_variables) + 1, hidden_features)
+            if self.lem_mlp:
+                self.lemoutput_mlp = nn.Sequential(nn.Linear(hidden_features, hidden_features, **f32), Swish(),
+                                                   nn.Linear(hidden_features, hidden_features, **f32), Swish())
+        if self.gated:
+            self.swish = Swish()
+        self.output_mlp = make_decoder(time_window, 1)
+
+    def __repr__(self):
+        return 'GNN'
+
+    def forward(self, data) -> torch.Tensor:
+        u_in = data.x
+        require_cuda(u_in)
+        pos = data.pos
+        pos_x = pos[:, 1][:, None] / self.pde.L
+        pos_t = pos[:, 0][:, None] / self.pde.tmax
+        variables = variables_1field(data, pos_t, self.eq_variables)
+        u = u_in.float()
+        feat = NodeFeatures(u, pos_x.float(), variables.float())
+        topo = get_topology(data.edge_index, data.batch, u.shape[0])
+
+        if self.encoder == "mlp":
+            node_input = pad_cols(torch.cat((u_in, pos_x, variables), -1))
+            h = mlp2(node_input, self.embedding_mlp)
+        else:
+            # I_t = [pos_x, u[:, t], variables]  (models_gnn.py:1357-1360)
+            T = u.shape[1]
+            static = torch.cat((pos_x, variables), -1).float()
+            lem_in = torch.empty(T, u.shape[0], 2 + variables.shape[1], dtype=torch.float32, device=u.device)
+            lem_in[:, :, 0] = static[:, 0]
+            lem_in[:, :, 1] = u.t()
+            lem_in[:, :, 2:] = static[:, 1:]
+            h = self.embedding_lem(lem_in)
+            if self.lem_mlp:
+                h = mlp2(h, self.lemoutput_mlp)
+
+        for i in range(self.hidden_layer):
+            if self.gated:
+                yg = self.gnn_layers_gate[i].core(h, feat, topo)
+                ym = self.gnn_layers[i].core(h, feat, topo)
+                h = gate_blend(yg, ym, h, topo)
+            else:
+                h = self.gnn_layers[i].forward_prepared(h, feat, topo)
+
+        dt = cumulative_dt(self.pde, self.time_window, h.device)
+        diff = self.output_mlp(h[:, None]).squeeze(1)
+        out = u[:, -1:].expand(-1, self.time_window) + dt * diff          # models_gnn.py:279
+        return out.to(u_in.dtype)
+
+
+class MP_PDE_Solver(_Solver1F):
+    """models_gnn.py:151-281 (`--model MP-PDE`)."""
+    layer_cls, gated, encoder = GNN_Layer, False, "mlp"
+
+
+class MP_PDE_SolverLEM(_Solver1F):
+    """models_gnn.py:365-497 (LEM encoder, plain GNN_Layer stack)."""
+    layer_cls, gated, encoder, lem_mlp = GNN_Layer, False, "lem", False
+
+
+class MP_PDE_SolverLEMLinGated(_Solver1F):
+    """models_gnn.py:1220-1377 (`--model MSMP-PDE`)."""
+    layer_cls, gated, encoder, lem_mlp = GNN_LayerLin, True, "lem", True

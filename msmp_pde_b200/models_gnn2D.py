@@ -1,0 +1,111 @@
+"""Drop-in replacements for the classes of ``experiments/models_gnn2D.py`` (two-field models).
+
+"2D" is a two-field 1-D system: node features are [N, 2*time_window] with the two fields in
+consecutive column blocks (common/utils.py:350-354).
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from .graph import get_topology
+from .layers import GNN_Layer, GNN_LayerLin, H, NodeFeatures, Swish, gate_blend  # noqa: F401
+from .lem import LEM, LEMS  # noqa: F401
+from .models_gnn import LSTM  # noqa: F401
+from .solver import linear_act, make_decoder, mlp2, pad_cols, require_cuda
+
+
+def unflatten_u(u: torch.Tensor, time_window: int):
+    """models_gnn2D.py:9-14: [*, n*time_window] -> [*, n, time_window]"""
+    return u.unflatten(1, (u.size(1) // time_window, time_window))
+
+
+class _Solver2F(nn.Module):
+    layer_cls = GNN_LayerLin
+    gated = True
+    encoder = "lem"
+
+    def __init__(self, pde, time_window: int = 25, hidden_features: int = 128, hidden_layer: int = 6,
+                 eq_variables: dict = {}, save_state=None):
+        super().__init__()
+        assert time_window in (25, 50)               # models_gnn2D.py:322
+        if hidden_features != H:
+            raise ValueError("msmp_pde_b200 supports hidden_features = 128 (the reference's only value)")
+        self.pde = pde
+        self.out_features = time_window
+        self.hidden_features, self.hidden_layer = hidden_features, hidden_layer
+        self.time_window, self.eq_variables = time_window, eq_variables
+        self.save_state = save_state
+        nv = len(eq_variables) + 1
+        mk = lambda: self.layer_cls(hidden_features, hidden_features, hidden_features, 2 * time_window, nv)
+        self.gnn_layers = nn.ModuleList(mk() for _ in range(hidden_layer))
+        if self.gated:
+            self.gnn_layers_gate = nn.ModuleList(mk() for _ in range(hidden_layer))
+        f32 = dict(dtype=torch.float32)
+        if self.encoder == "lem":
+            lem_cls = LEM if save_state is None else LEMS          # models_gnn2D.py:358-363
+            self.embedding_lem = lem_cls(2 + len(eq_variables) + 2, hidden_features)
+            self.lemoutput_mlp = nn.Sequential(nn.Linear(hidden_features, hidden_features, **f32), Swish(),
+                                               nn.Linear(hidden_features, hidden_features, **f32), Swish())
+        else:
+            self.embedding_mlp = nn.Sequential(nn.Linear(2 * time_window + 2 + len(eq_variables), hidden_features, **f32),
+                                               Swish(), nn.Linear(hidden_features, hidden_features, **f32), Swish())
+        if self.gated:
+            self.swish = Swish()
+        self.double_mlp = nn.Sequential(nn.Linear(hidden_features, 2 * hidden_features, **f32), Swish(),
+                                        nn.Unflatten(1, (2, hidden_features)))
+        self.output_mlp = make_decoder(time_window, 2)
+
+    def __repr__(self):
+        return 'GNN'
+
+    def forward(self, data) -> torch.Tensor:
+        tw = self.time_window
+        u_in = data.x
+        require_cuda(u_in)
+        pos = data.pos
+        pos_x = pos[:, 1][:, None] / self.pde.L
+        pos_t = pos[:, 0][:, None] / self.pde.tmax
+        variables = pos_t
+        if "a" in self.eq_variables:
+            variables = torch.cat((variables, data.a / self.eq_variables["a"]), -1)
+        if "b" in self.eq_variables:          # sic: data.a also feeds the 'b' column (models_gnn2D.py:419)
+            variables = torch.cat((variables, data.a / self.eq_variables["b"]), -1)
+        u = u_in.float()
+        N = u.shape[0]
+        feat = NodeFeatures(u, pos_x.float(), variables.float())
+        topo = get_topology(data.edge_index, data.batch, N)
+        dt64 = torch.cumsum(torch.ones(1, tw, dtype=torch.float64, device=u.device) * float(self.pde.dt), dim=1)
+        dt = dt64.float()
+
+        if self.encoder == "lem":
+            # I_t = [pos_x, u1[:, t], u2[:, t], cumsum(dt)_t + pos_t, variables[:, 1:]]  (models_gnn2D.py:421-433)
+            nvar = variables.shape[1] - 1
+            lem_in = torch.empty(tw, N, 4 + nvar, dtype=torch.float32, device=u.device)
+            lem_in[:, :, 0] = pos_x.float()[:, 0]
+            lem_in[:, :, 1] = u[:, :tw].t()
+            lem_in[:, :, 2] = u[:, tw:].t()
+            lem_in[:, :, 3] = (dt64 + pos_t.double()).float().t()
+            if nvar:
+                lem_in[:, :, 4:] = variables[:, 1:].float()
+            h = mlp2(self.embedding_lem(lem_in), self.lemoutput_mlp)
+        else:
+            h = mlp2(pad_cols(torch.cat((u_in, pos_x, variables), -1)), self.embedding_mlp)
+
+        for i in range(self.hidden_layer):
+            if self.gated:
+                yg = self.gnn_layers_gate[i].core(h, feat, topo)
+                ym = self.gnn_layers[i].core(h, feat, topo)
+                h = gate_blend(yg, ym, h, topo)
+            else:
+                h = self.gnn_layers[i].forward_prepared(h, feat, topo)
+
+        h2 = linear_act(h, self.double_mlp[0]).view(N, 2, H)              # models_gnn2D.py:444
+        diff = self.output_mlp(h2)                                        # [N, 2, tw]
+        out = unflatten_u(u, tw) + dt.view(1, 1, tw) * diff               # models_gnn2D.py:451-455
+        return torch.flatten(out, 1, 2).to(u_in.dtype)
+
+
+class MP_PDE_Solver2DLEMLinGated(_Solver2F):
+    """models_gnn2D.py:290-458 (`--model MSMP-PDE2D`; BASELINE configs 2-4)."""
+    layer_cls, gated, encoder = GNN_LayerLin, True, "lem"

@@ -1,0 +1,189 @@
+"""Thin Python wrappers over the C ABI (one call each, tensors in, tensors out, current CUDA stream).
+
+These do no math of their own; they validate layout, size the shared scratch buffer and forward raw
+device pointers to ``libmsmp_b200.so``.  CPU tensors are rejected: there is no fallback path.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from ._lib import check, lib
+
+H = 128
+_ws: dict = {}
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor:
+    key = (device.type, device.index)
+    buf = _ws.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 22), dtype=torch.uint8, device=device)
+        _ws[key] = buf
+    return buf
+
+
+def _req(t: torch.Tensor, name: str, dtype=torch.float32):
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: msmp_pde_b200 ops need CUDA tensors (no CPU fallback)")
+    if t.dtype != dtype:
+        raise TypeError(f"{name}: expected {dtype}, got {t.dtype}")
+    if t.dim() >= 1 and t.stride(-1) != 1 and t.numel() > 1:
+        raise ValueError(f"{name}: innermost dimension must be contiguous")
+    return t
+
+
+def _ld(t: torch.Tensor) -> int:
+    return t.stride(0) if t.dim() == 2 else t.shape[-1]
+
+
+def _p(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def linear_fwd(segs, Wt, bias=None, side=None, r=0, Wside=None, Zmul=None, Ypre=None, act=False, R=None,
+               out=None, Nout=None, aswish=None):
+    """Y = epi([A0|A1|A2] @ Wt + bias + side[:, :r] @ Wside); see include/msmp_b200.h."""
+    n = len(segs)
+    M = segs[0].shape[0]
+    Nout = Wt.shape[1] if Nout is None else Nout
+    for i, a in enumerate(segs):
+        _req(a, f"A{i}")
+    _req(Wt, "Wt")
+    if out is None:
+        out = torch.empty(M, Nout, dtype=torch.float32, device=Wt.device)
+    A = (ctypes.c_void_p * 3)(*[a.data_ptr() for a in segs], *([0] * (3 - n)))
+    lda = (ctypes.c_int * 3)(*[_ld(a) for a in segs], *([0] * (3 - n)))
+    ka = (ctypes.c_int * 3)(*[a.shape[1] for a in segs], *([0] * (3 - n)))
+    asw = (ctypes.c_int * 3)(*([int(bool(x)) for x in aswish] if aswish else [0] * n), *([0] * (3 - n)))
+    check(lib.msmp_linear_fwd(A, lda, ka, asw, n, Wt.data_ptr(), _ld(Wt), _p(bias), _p(side),
+                              _ld(side) if side is not None else 0, r if side is not None else 0, _p(Wside),
+                              _p(Zmul), _ld(Zmul) if Zmul is not None else 0, _p(Ypre),
+                              _ld(Ypre) if Ypre is not None else 0, int(act), _p(R), _ld(R) if R is not None else 0,
+                              out.data_ptr(), _ld(out), M, Nout, _stream()), "msmp_linear_fwd")
+    return out
+
+
+def linear_wgrad(X, dY, K=None, xswish=False, side=None, r=0, has_bias=False, dWt=None, dWside=None,
+                 accumulate=False):
+    """dWt[K, Nout] = X^T dY ; dWside[r(+1), Nout] = [side|1]^T dY."""
+    _req(X, "X")
+    _req(dY, "dY")
+    M, Nout = dY.shape
+    K = X.shape[1] if K is None else K
+    nside = (r if side is not None else 0) + int(has_bias)
+    dev = dY.device
+    if dWt is None:
+        dWt = torch.empty(K, Nout, dtype=torch.float32, device=dev)
+    if nside and dWside is None:
+        dWside = torch.empty(nside, Nout, dtype=torch.float32, device=dev)
+    nbytes = lib.msmp_linear_wgrad_workspace(M, K, Nout, nside)
+    ws = _workspace(nbytes, dev)
+    check(lib.msmp_linear_wgrad(X.data_ptr(), _ld(X), K, int(xswish), dY.data_ptr(), _ld(dY), Nout, _p(side),
+                                _ld(side) if side is not None else 0, r if side is not None else 0, int(has_bias),
+                                dWt.data_ptr(), _p(dWside), int(accumulate), M, ws.data_ptr(), ws.numel(), _stream()),
+          "msmp_linear_wgrad")
+    return dWt, dWside
+
+
+def edge_fwd(P, Q, topo, W2t, b2, save_z2=True):
+    _req(P, "P")
+    _req(Q, "Q")
+    dev = P.device
+    agg = torch.empty(topo.N, H, dtype=torch.float32, device=dev)
+    z2 = torch.empty(topo.E, H, dtype=torch.float32, device=dev) if save_z2 else None
+    ws = _workspace(lib.msmp_edge_fwd_workspace(topo.E), dev)
+    check(lib.msmp_edge_fwd(P.data_ptr(), Q.data_ptr(), _ld(P), topo.src.data_ptr(), topo.dst.data_ptr(),
+                            topo.rowptr.data_ptr(), topo.inv_deg.data_ptr(), W2t.data_ptr(), b2.data_ptr(), _p(z2),
+                            agg.data_ptr(), topo.E, topo.N, ws.data_ptr(), ws.numel(), _stream()), "msmp_edge_fwd")
+    return agg, z2
+
+
+def edge_bwd(P, Q, topo, W2, z2, dagg, dP):
+    """Returns dz1 [E,128], dW2 [128,128] ([n][k] = parameter layout), db2 [128]; writes dP in place."""
+    dev = P.device
+    dz1 = torch.empty(topo.E, H, dtype=torch.float32, device=dev)
+    dW2 = torch.empty(H, H, dtype=torch.float32, device=dev)
+    db2 = torch.empty(H, dtype=torch.float32, device=dev)
+    ws = _workspace(lib.msmp_edge_bwd_workspace(topo.E), dev)
+    check(lib.msmp_edge_bwd(P.data_ptr(), Q.data_ptr(), _ld(P), topo.src.data_ptr(), topo.dst.data_ptr(),
+                            topo.rowptr.data_ptr(), topo.inv_deg.data_ptr(), W2.data_ptr(), z2.data_ptr(),
+                            dagg.data_ptr(), _ld(dagg), dz1.data_ptr(), dP.data_ptr(), _ld(dP), dW2.data_ptr(),
+                            db2.data_ptr(), topo.E, topo.N, ws.data_ptr(), ws.numel(), _stream()), "msmp_edge_bwd")
+    return dz1, dW2, db2
+
+
+def segment_reduce(src, ptr, perm=None, scale=None, out=None, N=None):
+    """out[n] = scale[n] * sum_{k in [ptr[n], ptr[n+1])} src[perm[k] or k]  (rows of 128 floats)."""
+    _req(src, "src")
+    N = ptr.numel() - 1 if N is None else N
+    if out is None:
+        out = torch.empty(N, H, dtype=torch.float32, device=src.device)
+    check(lib.msmp_segment_reduce(src.data_ptr(), _ld(src), _p(perm), ptr.data_ptr(), _p(scale), out.data_ptr(),
+                                  _ld(out), N, _stream()), "msmp_segment_reduce")
+    return out
+
+
+def instnorm_fwd(y0, topo, y1=None, h=None, eps=1e-5):
+    """mode 0: IN(y0);  mode 1 (y1, h given): (1-s) h + s*swish(IN(y1)), s = sigmoid(IN(y0)).
+    Returns (out, stat)."""
+    mode = 0 if y1 is None else 1
+    dev = y0.device
+    out = torch.empty(topo.N, H, dtype=torch.float32, device=dev)
+    stat = torch.empty(mode + 1, topo.B, 2, H, dtype=torch.float32, device=dev)
+    ws = _workspace(lib.msmp_instnorm_workspace(topo.nchunks, topo.B), dev)
+    check(lib.msmp_instnorm_fwd(y0.data_ptr(), _p(y1), _ld(y0), _p(h), topo.chunk_begin.data_ptr(),
+                                topo.chunk_end.data_ptr(), topo.graph_chunk_ptr.data_ptr(), topo.node_graph.data_ptr(),
+                                topo.nchunks, topo.B, topo.N, mode, eps, stat.data_ptr(), out.data_ptr(),
+                                ws.data_ptr(), ws.numel(), _stream()), "msmp_instnorm_fwd")
+    return out, stat
+
+
+def instnorm_bwd(dout, y0, topo, stat, y1=None, h=None):
+    """Returns dy0 (mode 0) or (dy0, dy1, dh) (mode 1)."""
+    mode = 0 if y1 is None else 1
+    dev = y0.device
+    dout = dout.contiguous()
+    dy0 = torch.empty(topo.N, H, dtype=torch.float32, device=dev)
+    dy1 = torch.empty(topo.N, H, dtype=torch.float32, device=dev) if mode else None
+    dh = torch.empty(topo.N, H, dtype=torch.float32, device=dev) if mode else None
+    ws = _workspace(lib.msmp_instnorm_workspace(topo.nchunks, topo.B), dev)
+    check(lib.msmp_instnorm_bwd(dout.data_ptr(), y0.data_ptr(), _p(y1), _ld(y0), _p(h), stat.data_ptr(),
+                                topo.chunk_begin.data_ptr(), topo.chunk_end.data_ptr(),
+                                topo.graph_chunk_ptr.data_ptr(), topo.node_graph.data_ptr(), topo.nchunks, topo.B,
+                                topo.N, mode, dy0.data_ptr(), _p(dy1), H, _p(dh), ws.data_ptr(), ws.numel(),
+                                _stream()), "msmp_instnorm_bwd")
+    return dy0 if mode == 0 else (dy0, dy1, dh)
+
+
+def mul_dswish(g, z):
+    g = g.contiguous()
+    out = torch.empty_like(z)
+    check(lib.msmp_mul_dswish(g.data_ptr(), z.data_ptr(), out.data_ptr(), z.numel(), _stream()), "msmp_mul_dswish")
+    return out
+
+
+# ---- LEM gate kernels (tensors are contiguous [N,128] slices of the step buffers) -----------------
+def lem_gate_z(G, z_prev, dt, gates_t, z_new):
+    check(lib.msmp_lem_gate_z(G.data_ptr(), z_prev.data_ptr(), float(dt), gates_t.data_ptr(), z_new.data_ptr(),
+                              z_prev.shape[0], _stream()), "msmp_lem_gate_z")
+
+
+def lem_gate_y(L, y_prev, gates_t, y_new):
+    check(lib.msmp_lem_gate_y(L.data_ptr(), y_prev.data_ptr(), gates_t.data_ptr(), y_new.data_ptr(),
+                              y_prev.shape[0], _stream()), "msmp_lem_gate_y")
+
+
+def lem_bwd_y(dy, gy_t, y_prev, gates_t, dt, dL_t, dG_t):
+    check(lib.msmp_lem_bwd_y(dy.data_ptr(), _p(gy_t), y_prev.data_ptr(), gates_t.data_ptr(), float(dt),
+                             dL_t.data_ptr(), dG_t.data_ptr(), y_prev.shape[0], _stream()), "msmp_lem_bwd_y")
+
+
+def lem_bwd_z(dz_tot, gz_t, z_prev, gates_t, dt, dG_t, dz):
+    check(lib.msmp_lem_bwd_z(dz_tot.data_ptr(), _p(gz_t), z_prev.data_ptr(), gates_t.data_ptr(), float(dt),
+                             dG_t.data_ptr(), dz.data_ptr(), z_prev.shape[0], _stream()), "msmp_lem_bwd_z")

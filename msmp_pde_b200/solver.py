@@ -1,0 +1,96 @@
+"""Building blocks shared by the drop-in solver classes (encoder MLPs, decoder, input prep)."""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from . import ops
+from .layers import H, NodeFeatures, Swish, pad32
+
+_EQ_ORDER_1F = ("alpha", "beta", "gamma", "bc_left", "bc_right", "c", "D", "r")
+
+
+def variables_1field(data, pos_t, eq_variables):
+    """models_gnn.py:250-266: [t/tmax, then parameters in this fixed order]; bc_left / bc_right are
+    not divided by their maximum."""
+    v = pos_t
+    for k in _EQ_ORDER_1F:
+        if k in eq_variables:
+            col = getattr(data, k)
+            if k not in ("bc_left", "bc_right"):
+                col = col / eq_variables[k]
+            v = torch.cat((v, col), -1)
+    return v
+
+
+class _LinearActFn(torch.autograd.Function):
+    """y = act(x W^T + b) on msmp_linear_fwd / msmp_linear_wgrad.  x is [M, Kp] with Kp % 32 == 0 (zero padded)."""
+
+    @staticmethod
+    def forward(ctx, x, W, b, act: bool):
+        Nout, K = W.shape
+        Kp = x.shape[1]
+        x = x.contiguous()
+        Wt = torch.zeros(Kp, Nout, dtype=torch.float32, device=x.device)
+        Wt[:K] = W.t()
+        z = torch.empty(x.shape[0], Nout, dtype=torch.float32, device=x.device) if act else None
+        y = ops.linear_fwd([x], Wt, bias=b, Ypre=z, act=act)
+        ctx.act, ctx.K = act, K
+        ctx.save_for_backward(x, z, W)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, z, W = ctx.saved_tensors
+        dy = dy.contiguous()
+        dz = ops.mul_dswish(dy, z) if ctx.act else dy
+        dWt, dbs = ops.linear_wgrad(x, dz, has_bias=True)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            if ctx.K != x.shape[1]:
+                raise RuntimeError("input gradient of a zero-padded linear layer is not needed on this path")
+            dx = ops.linear_fwd([dz], W)            # W [Nout][K] is the reduction-major dgrad operand
+        return dx, dWt[:ctx.K].t(), dbs[0], None
+
+
+def linear_act(x, linear: nn.Linear, act: bool = True):
+    return _LinearActFn.apply(x, linear.weight, linear.bias, act)
+
+
+def pad_cols(x: torch.Tensor) -> torch.Tensor:
+    """Zero-pad the feature dimension to a multiple of 32 (fp32)."""
+    n, k = x.shape
+    kp = pad32(k)
+    if kp == k and x.dtype == torch.float32:
+        return x.contiguous()
+    out = torch.zeros(n, kp, dtype=torch.float32, device=x.device)
+    out[:, :k] = x
+    return out
+
+
+def mlp2(x, seq: nn.Sequential):
+    """Sequential(Linear, Swish, Linear, Swish) -- embedding_mlp / lemoutput_mlp (models_gnn.py:201-206,1288-1292)."""
+    return linear_act(linear_act(x, seq[0]), seq[2])
+
+
+def make_decoder(time_window: int, channels: int):
+    """Conv1d decoder geometry of models_gnn.py:208-224 (1 field) / models_gnn2D.py:382-391 (2 fields)."""
+    f32 = dict(dtype=torch.float32)
+    if time_window == 20 and channels == 1:
+        return nn.Sequential(nn.Conv1d(channels, 8, 15, stride=4, **f32), Swish(), nn.Conv1d(8, channels, 10, stride=1, **f32))
+    if time_window == 25:
+        return nn.Sequential(nn.Conv1d(channels, 8, 16, stride=3, **f32), Swish(), nn.Conv1d(8, channels, 14, stride=1, **f32))
+    if time_window == 50:
+        return nn.Sequential(nn.Conv1d(channels, 8, 12, stride=2, **f32), Swish(), nn.Conv1d(8, channels, 10, stride=1, **f32))
+    raise AssertionError("unsupported time_window")
+
+
+def cumulative_dt(pde, time_window, device):
+    # cumulated in float64 like the reference (models_gnn.py:275-276), then rounded once to fp32
+    return torch.cumsum(torch.ones(1, time_window, dtype=torch.float64, device=device) * float(pde.dt), dim=1).float()
+
+
+def require_cuda(t: torch.Tensor):
+    if not t.is_cuda:
+        raise RuntimeError("msmp_pde_b200 models run on CUDA only: move the model and the Data object to a GPU "
+                           "(there is no CPU fallback)")

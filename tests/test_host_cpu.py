@@ -1,0 +1,117 @@
+"""CPU-side checks: the C-ABI library loads and exports every declared symbol, graph construction and
+topology indexing are bit-exact against independent restatements, the host glue fails loudly without CUDA."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import pyg_semantics as pg
+
+
+def test_library_exports_every_declared_symbol():
+    from msmp_pde_b200 import _lib
+    syms = _lib.declared_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(_lib.lib, s), s
+    assert set(syms) == set(_lib._SIGS), set(syms) ^ set(_lib._SIGS)
+    assert _lib.lib.msmp_abi_version() == 1          # pure host call, no GPU needed
+
+
+def test_workspace_queries_are_host_only():
+    from msmp_pde_b200 import _lib
+    assert _lib.lib.msmp_edge_tiles(9408) == 74
+    assert _lib.lib.msmp_edge_fwd_workspace(9408) == 74 * 2 * 128 * 4
+    assert _lib.lib.msmp_linear_wgrad_splits(100000, 128, 128) >= 148
+
+
+def test_radius_graph_matches_bruteforce_and_closed_form():
+    from msmp_pde_b200.compat.torch_cluster import radius_graph
+    B, nx = 4, 100
+    x = torch.linspace(0, 16, nx, dtype=torch.float64).repeat(B)
+    batch = torch.arange(B).repeat_interleave(nx)
+    r = 3 * (x[1] - x[0]) + 1e-4                       # common/utils.py:366-367
+    e1 = radius_graph(x, r=r, batch=batch, loop=False)
+    e2 = pg.radius_graph(x, r=float(r), batch=batch)
+    assert torch.equal(e1, e2)
+    assert e1.shape[1] == B * 588                      # 588 directed edges per graph
+    assert bool((e1[1][1:] >= e1[1][:-1]).all())       # destination-sorted => CSR for free
+    deg = torch.bincount(e1[1], minlength=B * nx)[:nx]
+    assert deg[:3].tolist() == [3, 4, 5] and int(deg[50]) == 6
+
+
+def test_knn_graph_on_pseudo_random_grid():
+    from msmp_pde_b200.compat.torch_cluster import knn_graph
+    from msmp_pde_b200.synth import pseudo_random_grid
+    g = pseudo_random_grid(0, 16, 100)
+    assert np.array_equal(g, pg.pseudo_random_grid(0, 16, 100))
+    assert g[0] == 0 and g[-1] == 16 and np.all(np.diff(g) > 0)
+    xg = torch.tensor(g)
+    X = 2 * np.pi * xg / (xg.max() - 1e-3)
+    xp = torch.stack([torch.cos(X), torch.sin(X)], 1).repeat(2, 1)
+    batch = torch.arange(2).repeat_interleave(100)
+    for k in (3, 6):
+        e1 = knn_graph(xp, k, batch=batch)
+        assert torch.equal(e1, pg.knn_graph(xp, k, batch=batch))
+        assert e1.shape[1] == 2 * 100 * k
+    # periodic seam: nodes 0 and 99 are neighbours on the circle
+    e = knn_graph(xp[:100], 3)
+    assert 99 in e[0][e[1] == 0].tolist()
+
+
+def test_topology_bit_exact_vs_numpy():
+    from msmp_pde_b200.graph import build_topology
+    from tests.util import random_directed_graph
+    ei, batch = random_directed_graph([23, 300, 9, 129], 4.0, seed=3)
+    perm = torch.randperm(ei.shape[1], generator=torch.Generator().manual_seed(0))
+    for edges in (ei, ei[:, perm]):                    # sorted and unsorted input
+        N = batch.numel()
+        t = build_topology(edges, batch, N)
+        src, dst = edges[0].numpy(), edges[1].numpy()
+        order = np.argsort(dst, kind="stable")
+        s_sorted, d_sorted = src[order], dst[order]
+        assert np.array_equal(t.src.numpy(), s_sorted) and np.array_equal(t.dst.numpy(), d_sorted)
+        rowptr = np.concatenate([[0], np.cumsum(np.bincount(dst, minlength=N))])
+        assert np.array_equal(t.rowptr.numpy(), rowptr)
+        colptr = np.concatenate([[0], np.cumsum(np.bincount(src, minlength=N))])
+        assert np.array_equal(t.colptr.numpy(), colptr)
+        assert np.array_equal(t.csc_perm.numpy(), np.argsort(s_sorted, kind="stable"))
+        deg = np.maximum(np.bincount(dst, minlength=N), 1)
+        assert np.array_equal(t.inv_deg.numpy(), (1.0 / deg).astype(np.float32))
+        # chunks: graph aligned, <= 128 rows, cover every node exactly once
+        cb, ce = t.chunk_begin.numpy(), t.chunk_end.numpy()
+        assert np.all(ce - cb <= 128) and np.all(ce > cb)
+        covered = np.concatenate([np.arange(a, b) for a, b in zip(cb, ce)])
+        assert np.array_equal(covered, np.arange(N))
+        for c0, c1 in zip(cb, ce):
+            assert len(set(batch[c0:c1].tolist())) == 1
+        assert t.graph_chunk_ptr.tolist() == [0, 1, 4, 5, 7]
+
+
+def test_no_cpu_fallback():
+    from msmp_pde_b200 import models_gnn, synth
+    pde, data, meta = synth.config_c1(B=1, nx=20)
+    model = models_gnn.MP_PDE_Solver(pde, 25, 128, 6, {})
+    with pytest.raises(RuntimeError, match="CUDA"):
+        model(data)
+
+
+def test_install_makes_reference_imports_resolve():
+    import sys
+    import msmp_pde_b200
+    saved = {k: sys.modules.get(k) for k in list(sys.modules) if k.startswith(("experiments", "torch_geometric", "torch_cluster", "torch_scatter"))}
+    try:
+        msmp_pde_b200.install()
+        from experiments.models_gnn import MP_PDE_Solver, MP_PDE_SolverLEMLinGated, GNN_Layer, LEM, LEMS, LSTM, Swish  # noqa: F401
+        from experiments.models_gnn2D import MP_PDE_Solver2DLEMLinGated, unflatten_u  # noqa: F401
+        from torch_geometric.data import Data
+        from torch_cluster import radius_graph, knn_graph  # noqa: F401
+        from torch_scatter import scatter
+        d = Data(x=torch.zeros(3, 2), edge_index=torch.zeros(2, 0, dtype=torch.long))
+        d.y = torch.ones(3)
+        assert d.to("cpu").y.sum() == 3
+        out = scatter(torch.ones(4, 2), torch.tensor([0, 0, 2, 2]), dim=0, dim_size=3, reduce="mean")
+        assert out.tolist() == [[1, 1], [0, 0], [1, 1]]
+    finally:
+        for k in list(sys.modules):
+            if k.startswith(("experiments", "torch_geometric", "torch_cluster", "torch_scatter")) and k not in saved:
+                del sys.modules[k]

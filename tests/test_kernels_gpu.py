@@ -1,0 +1,226 @@
+"""Per-entry-point parity of the C ABI against float64 torch math on the same inputs (B200 only)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from tests.util import random_directed_graph, rel_err  # noqa: E402
+
+TOL = 1e-5          # max|delta| <= TOL * max|ref|  (north_star: rtol 1e-5 in fp32, SURVEY section 4 metric)
+
+
+def _sw(x):
+    return x * torch.sigmoid(x)
+
+
+def _dsw(x):
+    s = torch.sigmoid(x)
+    return s * (1 + x * (1 - s))
+
+
+def _graph(sizes, deg, seed, hub=None):
+    ei, batch = random_directed_graph(sizes, deg, seed)
+    if hub is not None:      # one destination with > 128 in-edges: segment cut by several tile boundaries
+        n = int(batch.numel())
+        extra_src = torch.arange(0, min(n, hub))
+        extra = torch.stack([extra_src, torch.full_like(extra_src, 5)])
+        extra = extra[:, extra[0] != 5]
+        ei = torch.unique(torch.cat([ei, extra], 1), dim=1)
+        order = torch.argsort(ei[1] * n + ei[0], stable=True)
+        ei = ei[:, order]
+    return ei, batch
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+def test_abi_loaded():
+    from msmp_pde_b200 import _lib
+    assert _lib.lib.msmp_abi_version() == 1
+
+
+@pytest.mark.parametrize("M", [1, 300, 1024])
+def test_linear_fwd(dev, M):
+    from msmp_pde_b200 import ops
+    g = torch.Generator().manual_seed(M)
+    A0 = torch.randn(M, 128, generator=g)
+    A1 = torch.randn(M, 64, generator=g)
+    Wt = torch.randn(192, 256, generator=g) / 14
+    bias = torch.randn(256, generator=g)
+    side = torch.randn(M, 8, generator=g)
+    Ws = torch.randn(8, 256, generator=g)
+    R = torch.randn(M, 256, generator=g)
+    Z = torch.randn(M, 256, generator=g)
+    c = lambda t: t.to(dev)
+    ypre = torch.empty(M, 256, device=dev)
+    y = ops.linear_fwd([c(A0), c(A1)], c(Wt), bias=c(bias), side=c(side), r=3, Wside=c(Ws), Zmul=c(Z), Ypre=ypre,
+                       act=True, R=c(R), aswish=[0, 1])
+    d = lambda t: t.double()
+    z = torch.cat([d(A0), _sw(d(A1))], 1) @ d(Wt) + d(bias) + d(side)[:, :3] @ d(Ws)[:3]
+    z = z * _dsw(d(Z))
+    ref = _sw(z) + d(R)
+    assert rel_err(ypre, z) < TOL
+    assert rel_err(y, ref) < TOL
+
+
+def test_linear_fwd_plain_and_strided(dev):
+    from msmp_pde_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    M = 777
+    big = torch.randn(M, 256, generator=g).to(dev)
+    W = (torch.randn(128, 128, generator=g) / 11).to(dev)
+    y = ops.linear_fwd([big[:, 128:]], W)             # strided view as A; W[n][k] used as Wt[k=n][n=k]
+    ref = big[:, 128:].double() @ W.double()
+    assert rel_err(y, ref) < TOL
+
+
+@pytest.mark.parametrize("M,K,Nout", [(1000, 192, 256), (130, 128, 128), (5000, 160, 384)])
+def test_linear_wgrad(dev, M, K, Nout):
+    from msmp_pde_b200 import ops
+    g = torch.Generator().manual_seed(K)
+    X = torch.randn(M, K, generator=g)
+    dY = torch.randn(M, Nout, generator=g)
+    side = torch.randn(M, 8, generator=g)
+    dWt, dWs = ops.linear_wgrad(X.to(dev), dY.to(dev), xswish=True, side=side.to(dev), r=2, has_bias=True)
+    refW = _sw(X.double()).t() @ dY.double()
+    refS = torch.cat([side.double()[:, :2], torch.ones(M, 1, dtype=torch.float64)], 1).t() @ dY.double()
+    assert rel_err(dWt, refW) < TOL
+    assert rel_err(dWs, refS) < TOL
+    # deterministic
+    dWt2, _ = ops.linear_wgrad(X.to(dev), dY.to(dev), xswish=True, side=side.to(dev), r=2, has_bias=True)
+    assert torch.equal(dWt, dWt2)
+
+
+def _edge_inputs(sizes, deg, seed, hub, dev):
+    from msmp_pde_b200.graph import build_topology
+    ei, batch = _graph(sizes, deg, seed, hub)
+    N = batch.numel()
+    g = torch.Generator().manual_seed(seed + 100)
+    PQ = torch.randn(N, 256, generator=g)
+    W2 = torch.randn(128, 128, generator=g) / 11
+    b2 = torch.randn(128, generator=g) * 0.1
+    topo = build_topology(ei.to(dev), batch.to(dev), N)
+    return ei, batch, N, PQ, W2, b2, topo
+
+
+def _edge_ref(ei, N, PQ, W2, b2):
+    j, i = ei[0], ei[1]
+    P, Q = PQ[:, :128].double(), PQ[:, 128:].double()
+    z1 = P[i] + Q[j]
+    a1 = _sw(z1)
+    z2 = a1 @ W2.double().t() + b2.double()
+    m = _sw(z2)
+    agg = torch.zeros(N, 128, dtype=torch.float64).index_add_(0, i, m)
+    deg = torch.bincount(i, minlength=N).clamp(min=1).double()
+    return z1, a1, z2, agg / deg[:, None], deg
+
+
+@pytest.mark.parametrize("sizes,deg,hub", [([50, 37, 64], 5.0, None), ([300, 500], 7.0, 450), ([20], 1.5, None),
+                                           ([2000, 1000], 16.0, None)])
+def test_edge_fwd(dev, sizes, deg, hub):
+    from msmp_pde_b200 import ops
+    ei, batch, N, PQ, W2, b2, topo = _edge_inputs(sizes, deg, 1, hub, dev)
+    PQd = PQ.to(dev)
+    agg, z2 = ops.edge_fwd(PQd[:, :128], PQd[:, 128:], topo, W2.t().contiguous().to(dev), b2.to(dev))
+    _, _, z2_ref, agg_ref, _ = _edge_ref(ei, N, PQ, W2, b2)
+    assert rel_err(z2, z2_ref) < TOL
+    assert rel_err(agg, agg_ref) < TOL
+    agg2, _ = ops.edge_fwd(PQd[:, :128], PQd[:, 128:], topo, W2.t().contiguous().to(dev), b2.to(dev))
+    assert torch.equal(agg, agg2)
+
+
+@pytest.mark.parametrize("sizes,deg,hub", [([50, 37, 64], 5.0, None), ([300, 500], 7.0, 450), ([2000, 1000], 16.0, None)])
+def test_edge_bwd(dev, sizes, deg, hub):
+    from msmp_pde_b200 import ops
+    ei, batch, N, PQ, W2, b2, topo = _edge_inputs(sizes, deg, 2, hub, dev)
+    g = torch.Generator().manual_seed(9)
+    dagg = torch.randn(N, 128, generator=g)
+    z1, a1, z2, _, degc = _edge_ref(ei, N, PQ, W2, b2)
+    j, i = ei[0], ei[1]
+    dm = dagg.double()[i] / degc[i][:, None]
+    dz2 = dm * _dsw(z2)
+    dW2_ref = dz2.t() @ a1
+    db2_ref = dz2.sum(0)
+    dz1_ref = (dz2 @ W2.double()) * _dsw(z1)
+    dP_ref = torch.zeros(N, 128, dtype=torch.float64).index_add_(0, i, dz1_ref)
+    dQ_ref = torch.zeros(N, 128, dtype=torch.float64).index_add_(0, j, dz1_ref)
+    PQd = PQ.to(dev)
+    dPQ = torch.full((N, 256), float("nan"), device=dev)
+    dz1, dW2, db2 = ops.edge_bwd(PQd[:, :128], PQd[:, 128:], topo, W2.to(dev), z2.float().to(dev), dagg.to(dev), dPQ[:, :128])
+    ops.segment_reduce(dz1, topo.colptr, perm=topo.csc_perm, out=dPQ[:, 128:], N=N)
+    assert rel_err(dz1, dz1_ref) < TOL
+    assert rel_err(dPQ[:, :128], dP_ref) < TOL
+    assert rel_err(dPQ[:, 128:], dQ_ref) < TOL
+    assert rel_err(dW2, dW2_ref) < TOL
+    assert rel_err(db2, db2_ref) < TOL
+
+
+def test_segment_mean_standalone(dev):
+    """torch_scatter.scatter(reduce='mean') semantics, keyed on the SOURCE index (models_gnn2D.py:600-601)."""
+    from msmp_pde_b200 import ops
+    from msmp_pde_b200.graph import build_topology
+    ei, batch = _graph([200, 100], 6.0, 5)
+    N = batch.numel()
+    src = torch.randn(ei.shape[1], 128, generator=torch.Generator().manual_seed(1))
+    topo = build_topology(ei.to(dev), batch.to(dev), N)
+    outdeg = torch.bincount(ei[0], minlength=N).clamp(min=1)
+    out = ops.segment_reduce(src.to(dev), topo.colptr, perm=topo.csc_perm, scale=(1.0 / outdeg.float()).to(dev))
+    ref = torch.zeros(N, 128, dtype=torch.float64).index_add_(0, ei[0], src.double()) / outdeg[:, None]
+    assert rel_err(out, ref) < TOL
+
+
+@pytest.mark.parametrize("sizes", [[100, 100, 100], [37, 300, 1, 129]])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_instnorm(dev, sizes, mode):
+    from oracle.pyg_semantics import instance_norm
+    from msmp_pde_b200 import ops
+    from msmp_pde_b200.graph import build_topology
+    batch = torch.cat([torch.full((n,), b) for b, n in enumerate(sizes)])
+    N = batch.numel()
+    ei = torch.stack([torch.arange(N), torch.arange(N)])       # topology irrelevant here
+    topo = build_topology(ei.to(dev), batch.to(dev), N)
+    g = torch.Generator().manual_seed(4)
+    y0 = (torch.randn(N, 128, generator=g) * 3 + 50).double().requires_grad_(True)     # |mean| >> sigma
+    y1 = torch.randn(N, 128, generator=g).double().requires_grad_(True)
+    h = torch.randn(N, 128, generator=g).double().requires_grad_(True)
+    w = torch.randn(N, 128, generator=g).double()
+    if mode == 0:
+        ref = instance_norm(y0, batch)
+    else:
+        tau = torch.sigmoid(instance_norm(y0, batch))
+        ref = (1 - tau) * h + tau * _sw(instance_norm(y1, batch))
+    (ref * w).sum().backward()
+    f = lambda t: t.detach().float().to(dev)
+    if mode == 0:
+        out, stat = ops.instnorm_fwd(f(y0), topo)
+        dy0 = ops.instnorm_bwd(f(w), f(y0), topo, stat)
+    else:
+        out, stat = ops.instnorm_fwd(f(y0), topo, y1=f(y1), h=f(h))
+        dy0, dy1, dh = ops.instnorm_bwd(f(w), f(y0), topo, stat, y1=f(y1), h=f(h))
+        assert rel_err(dy1, y1.grad) < TOL
+        assert rel_err(dh, h.grad) < TOL
+    # y0 ~ 50 +- 3 in fp32: the input itself carries 4e-6 relative rounding, amplified by 1/sigma
+    assert rel_err(out, ref) < 5e-5
+    assert rel_err(dy0, y0.grad) < 2e-4
+
+
+def test_lem_matches_oracle(dev):
+    from oracle.models import lem_forward
+    from msmp_pde_b200.lem import LEMcuda
+    torch.manual_seed(0)
+    T, N, ninp = 7, 333, 6
+    rnn = LEMcuda(ninp, 128, 1.0).to(dev)
+    x = torch.randn(T, N, ninp)
+    wy, wz = torch.randn(T, N, 128), torch.randn(T, N, 128)
+    ys, zs = rnn(x.to(dev))
+    ((ys * wy.to(dev)).sum() + (zs * wz.to(dev)).sum()).backward()
+    ps = [p.detach().double().cpu().requires_grad_(True) for p in (rnn.weights, rnn.weights_lin_z, rnn.bias, rnn.bias_lin_z)]
+    z0 = torch.zeros(N, 128, dtype=torch.float64)
+    yr, zr = lem_forward(x.double(), *ps, z0, z0, 1.0)
+    ((yr * wy.double()).sum() + (zr * wz.double()).sum()).backward()
+    assert rel_err(ys, yr) < TOL
+    assert rel_err(zs, zr) < TOL
+    for p, q in zip((rnn.weights, rnn.weights_lin_z, rnn.bias, rnn.bias_lin_z), ps):
+        assert rel_err(p.grad, q.grad) < TOL

@@ -1,0 +1,125 @@
+"""Parity of the CUDA drop-in modules against the oracle and the reference-generated golden fixtures (B200)."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from tests import golden_io  # noqa: E402
+from tests.util import formula_weights_, rel_err, tensor_digest  # noqa: E402
+
+OUT_TOL = 1e-5       # north_star: outputs/gradients to rtol 1e-5 in fp32, measured as max|d| / max|ref|
+GRAD_TOL = 1e-5
+
+
+def _grad_errs(model, ref_model):
+    """Per-parameter max|d| / max|ref| ; structurally-zero gradients are compared on the global scale."""
+    refs = dict(ref_model.named_parameters())
+    gscale = max(float(p.grad.abs().max()) for p in refs.values() if p.grad is not None)
+    errs = {}
+    for name, p in model.named_parameters():
+        ref = refs[name].grad.double()
+        got = (p.grad if p.grad is not None else torch.zeros_like(p)).double().cpu()
+        denom = float(ref.abs().max())
+        if denom < 1e-9 * gscale:          # e.g. update_net_2 bias of GNN_LayerLin
+            denom = gscale
+        errs[name] = float((got - ref).abs().max()) / denom
+    return errs
+
+
+@pytest.mark.parametrize("cls,fname,F_u,V", [("GNN_Layer", "layer_gnn.npz", 25, 1), ("GNN_LayerLin", "layer_gnnlin.npz", 50, 3)])
+def test_layer_vs_golden(cls, fname, F_u, V):
+    from msmp_pde_b200 import layers
+    from oracle import models as om
+    dev = torch.device("cuda:0")
+    g = golden_io.load(fname)
+    layer = getattr(layers, cls)(128, 128, 128, F_u, V)
+    formula_weights_(layer)
+    layer = layer.to(dev)
+    t = lambda k: torch.from_numpy(g[k]).to(dev)
+    x = t("in_x").requires_grad_(True)
+    out = layer(x, t("in_u"), t("in_pos"), t("in_variables"), t("in_edge_index"), t("in_batch"))
+    assert out.dtype == torch.float64               # returned in the caller's dtype
+    (out * t("in_wout")).sum().backward()
+    assert rel_err(out, torch.from_numpy(g["out"])) < OUT_TOL
+    assert rel_err(x.grad, torch.from_numpy(g["grad_x"])) < GRAD_TOL
+    # parameter gradients against the float64 oracle with the same weights
+    torch.set_default_dtype(torch.float64)
+    ref = getattr(om, cls)(128, 128, 128, F_u, V)
+    formula_weights_(ref)
+    c = lambda k: torch.from_numpy(g[k])
+    xr = c("in_x").requires_grad_(True)
+    outr = ref(xr, c("in_u"), c("in_pos"), c("in_variables"), c("in_edge_index"), c("in_batch"))
+    (outr * c("in_wout")).sum().backward()
+    errs = _grad_errs(layer, ref)
+    assert max(errs.values()) < GRAD_TOL, errs
+    # and the reference-made digests of those gradients
+    for name, p in layer.named_parameters():
+        want = g["gdig_" + name]
+        got = tensor_digest(p.grad)
+        scale = max(abs(want[0]), 1e-12)
+        if want[0] > 1e-9:
+            assert abs(got[0] - want[0]) < 1e-4 * scale, name
+
+
+CASES = [
+    ("models_gnn", "MP_PDE_Solver", "mp_pde_c1.npz", "CE", {}),
+    ("models_gnn", "MP_PDE_SolverLEMLinGated", "msmp_pde_1f.npz", "CE", {"alpha": 3.0, "beta": 0.4, "gamma": 1.0}),
+    ("models_gnn2D", "MP_PDE_Solver2DLEMLinGated", "msmp_pde2d_c2.npz", "AD", {"a": 1.0, "b": 1.0}),
+    ("models_gnn2D", "MP_PDE_Solver2DLEMLinGated", "msmp_pde2d_c3.npz", "AD", {"a": 1.0, "b": 1.0}),
+]
+
+
+@pytest.mark.parametrize("mod,cls,fname,pde_name,eq", CASES)
+def test_model_vs_golden_and_oracle(mod, cls, fname, pde_name, eq):
+    import importlib
+    from oracle import models as om
+    dev = torch.device("cuda:0")
+    g = golden_io.load(fname)
+    pde, data = golden_io.model_inputs(g, pde_name)
+    m = importlib.import_module("msmp_pde_b200." + mod)
+    torch.set_default_dtype(torch.float64)          # the reference constructs everything under float64 (F1)
+    model = getattr(m, cls)(pde, time_window=25, hidden_features=128, hidden_layer=6, eq_variables=eq)
+    assert all(p.dtype == torch.float32 for p in model.parameters())
+    formula_weights_(model)
+    model = model.to(dev)
+    dd = copy.copy(data).clone().to(dev)
+    out = model(dd)
+    assert out.dtype == torch.float64 and repr(model) == "GNN"
+    loss = torch.sqrt(torch.nn.functional.mse_loss(out, dd.y, reduction="sum"))
+    loss.backward()
+    assert rel_err(out, torch.from_numpy(g["out"])) < OUT_TOL
+    assert abs(float(loss) - float(g["loss"])) < 1e-5 * float(g["loss"])
+    ref = getattr(om, cls)(pde, time_window=25, hidden_features=128, hidden_layer=6, eq_variables=eq)
+    formula_weights_(ref)
+    outr = ref(data)
+    torch.sqrt(torch.nn.functional.mse_loss(outr, data.y, reduction="sum")).backward()
+    errs = _grad_errs(model, ref)
+    worst = max(errs, key=errs.get)
+    assert errs[worst] < GRAD_TOL, (worst, errs[worst])
+
+
+def test_determinism_and_state_dict_roundtrip():
+    """Bit-identical outputs/gradients across runs (no atomics); fp64 reference checkpoints load."""
+    from msmp_pde_b200 import models_gnn2D, synth
+    from oracle import models as om
+    dev = torch.device("cuda:0")
+    pde, data, meta = synth.config_c2(B=4, nx=100, seed=1)
+    torch.manual_seed(0)
+    model = models_gnn2D.MP_PDE_Solver2DLEMLinGated(pde, 25, 128, 6, meta["eq_variables"]).to(dev)
+    torch.set_default_dtype(torch.float64)
+    ref = om.MP_PDE_Solver2DLEMLinGated(pde, 25, 128, 6, meta["eq_variables"])
+    model.load_state_dict(ref.state_dict())          # float64 checkpoint -> fp32 parameters
+    dd = data.clone().to(dev)
+    outs, grads = [], []
+    for _ in range(3):
+        model.zero_grad()
+        out = model(dd)
+        torch.sqrt(((out - dd.y) ** 2).sum()).backward()
+        outs.append(out.detach().clone())
+        grads.append(torch.cat([p.grad.reshape(-1) for p in model.parameters()]).clone())
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    assert torch.equal(grads[0], grads[1]) and torch.equal(grads[0], grads[2])
+    assert rel_err(outs[0], ref(data)) < OUT_TOL
