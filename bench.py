@@ -1,0 +1,291 @@
+#!/usr/bin/env python
+"""Benchmark of the MSMP-PDE hot path (contract: see the task statement / DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1]): MSMP-PDE2D training step on the RP shape -- 64 trajectories per GPU,
+100 nodes each, time_window 25, 6-neighbour radius graph (N = 6400 nodes, E = 37632 edges per GPU),
+MP_PDE_Solver2DLEMLinGated (LEM encoder + 6 gated layer pairs + Conv1d decoder, 1 409 002 parameters),
+synthetic data, random-init weights.  One step = forward + loss (sqrt of the batch-global summed squared
+error, train_helper.py:126,138) + backward + (N > 1: gradient all-reduce over NCCL) + AdamW update.
+Metric: graph-nodes per second, whole job.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "GNN fwd+bwd graph-nodes/sec"
+UNIT = "nodes/s"
+B_PER_GPU, NX, TW = 64, 100, 25
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return dict(hbm_gbs=float(d["hbm_gbs"]), tensor_tflops=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])),
+                    source="measured (MEASURED_PEAKS.json: copy GB/s, cuBLAS bf16 sustained TFLOP/s)")
+    return dict(hbm_gbs=6650.0, tensor_tflops=1590.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (profiling recipe's clocks line)."""
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i] == "Active" for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def _workload(rank: int):
+    import torch
+    from msmp_pde_b200 import synth
+    pde, data, meta = synth.config_c2(B=B_PER_GPU, nx=NX, tw=TW, seed=rank)     # float64 host tensors (F1)
+    return pde, data, meta
+
+
+def _loss(pred, y):
+    import torch
+    return torch.sqrt(torch.nn.functional.mse_loss(pred, y, reduction="sum"))
+
+
+# ----------------------------------------------------------------------------------------------- ours
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from msmp_pde_b200 import models_gnn2D, ops
+    from msmp_pde_b200.graph import get_topology
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    pde, data, meta = _workload(rank)
+    torch.manual_seed(0)
+    model = models_gnn2D.MP_PDE_Solver2DLEMLinGated(pde, TW, 128, 6, meta["eq_variables"]).to(dev)
+    params = [p for p in model.parameters()]
+    opt = torch.optim.AdamW(params, lr=1e-4, fused=True)           # train.py:410
+    N, E = data.x.shape[0], data.edge_index.shape[1]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def allreduce_grads():
+        if world > 1:
+            flat = torch.cat([p.grad.reshape(-1) for p in params])
+            dist.all_reduce(flat)                                   # SUM (loss is sqrt of a batch-global sum)
+            off = 0
+            for p in params:
+                n = p.numel()
+                p.grad.copy_(flat[off:off + n].view_as(p))
+                off += n
+
+    def step(graph):
+        opt.zero_grad(set_to_none=True)
+        pred = model(graph)
+        loss = _loss(pred, graph.y)
+        loss.backward()
+        allreduce_grads()
+        opt.step()
+        return loss
+
+    def timed(K, make_graph, read_loss):
+        evs = []
+        for _ in range(K):
+            flush.zero_()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            g = make_graph()
+            loss = step(g)
+            if read_loss:
+                loss.item()
+            e.record()
+            evs.append((s, e))
+        torch.cuda.synchronize()
+        return [s.elapsed_time(e) for s, e in evs]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    resident = data.clone().to(dev)
+    pinned = data.clone().apply(lambda t: t.pin_memory())
+    h2d = sum(t.numel() * t.element_size() for t in (getattr(pinned, k) for k in pinned.keys()) if torch.is_tensor(t))
+
+    for _ in range(max(3, args.warmup)):
+        step(resident)
+    barrier()
+    # ---- device-resident timing (value) with per-kernel events on the edge kernels (roofline)
+    ops.PROFILE_EVENTS = {}
+    ops.LAUNCHES = 0
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    times = timed(args.steps, lambda: resident, False)
+    barrier()
+    launches = ops.LAUNCHES
+    kern = {k: [s.elapsed_time(e) for s, e in v] for k, v in ops.PROFILE_EVENTS.items()}
+    ops.PROFILE_EVENTS = None
+    # ---- end-to-end timing: host (pinned, float64) inputs -> device every step, loss read back
+    for _ in range(2):
+        step(pinned.clone().to(dev, non_blocking=True))
+    barrier()
+    e2e_times = timed(args.steps, lambda: pinned.clone().to(dev, non_blocking=True), True)
+    barrier()
+    clocks = sampler.stop()
+
+    ms = sum(times) / len(times)
+    ms_e2e = sum(e2e_times) / len(e2e_times)
+    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+
+    out = None
+    if rank == 0:
+        peaks = _peaks()
+        # dominant kernel: the edge kernels (message MLP layer 2 + aggregation; backward incl. dW2)
+        flops = {"edge_fwd": E * 2 * 128 * 128, "edge_bwd": E * 2 * 2 * 128 * 128}
+        tot = {k: sum(v) for k, v in kern.items()}
+        dom = max(tot, key=tot.get) if tot else None
+        roof = None
+        if dom:
+            avg_ms = tot[dom] / len(kern[dom])
+            ach = flops[dom] / (avg_ms * 1e-3) / 1e12
+            roof = {"kernel": "k_" + dom, "bound": "tensor", "achieved": round(ach, 3),
+                    "peak": peaks["tensor_tflops"], "unit": "TFLOP/s", "frac": round(ach / peaks["tensor_tflops"], 5),
+                    "traffic": None, "avg_launch_ms": round(avg_ms, 5),
+                    "share_of_step": round(tot[dom] / (ms * args.steps), 4), "peak_source": peaks["source"],
+                    "note": "fp32 FFMA path (round 1): executed FLOPs of the factorised message MLP per launch; "
+                            "tensor peak = cuBLAS bf16 sustained"}
+        out = {
+            "metric": METRIC, "value": round(world * N / (ms * 1e-3), 1), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": round(ms, 4), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "C2: MSMP-PDE2D (MP_PDE_Solver2DLEMLinGated) RP shape, 64 graphs x 100 nodes per GPU, "
+                                   "tw=25, 588 edges/graph, fwd+loss+bwd+AdamW",
+                       "nodes_per_gpu": N, "edges_per_gpu": E, "global_batch": world * B_PER_GPU,
+                       "parallelism": f"dp{world}", "l2": "flushed (256 MiB write) between timed steps"},
+            "e2e": {"value": round(world * N / (ms_e2e * 1e-3), 1), "unit": UNIT, "ms_per_step": round(ms_e2e, 4),
+                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 8},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
+            "kernel_ms_per_step": {k: round(v / args.steps, 4) for k, v in tot.items()},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(sample_graphs=8, steps=2)
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return out
+
+
+# ------------------------------------------------------------------------------------------ reference
+def _oracle_step_time(B, steps, warmup, dtype_name="float64"):
+    """The reference's CPU path (oracle port, float64 = reference-native dtype) on all host cores."""
+    import torch
+    from msmp_pde_b200 import synth
+    from oracle import models as om
+    torch.set_num_threads(os.cpu_count())
+    prev = torch.get_default_dtype()
+    torch.set_default_dtype(getattr(torch, dtype_name))
+    try:
+        pde, data, meta = synth.config_c2(B=B, nx=NX, tw=TW, seed=0, dtype=getattr(torch, dtype_name))
+        torch.manual_seed(0)
+        model = om.MP_PDE_Solver2DLEMLinGated(pde, TW, 128, 6, meta["eq_variables"])
+        opt = torch.optim.AdamW(model.parameters(), lr=1e-4)
+        ts = []
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            opt.zero_grad()
+            loss = _loss(model(data), data.y)
+            loss.backward()
+            opt.step()
+            if i >= warmup:
+                ts.append(time.perf_counter() - t0)
+    finally:
+        torch.set_default_dtype(prev)
+    return sum(ts) / len(ts), data.x.shape[0]
+
+
+def cpu_baseline(sample_graphs=8, steps=2):
+    sec, n = _oracle_step_time(sample_graphs, steps, 1)
+    return {"value": round(n / sec, 1), "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+            "sample": f"{sample_graphs} of the 64 graphs of the C2 batch ({n} nodes), {steps} steps after 1 warm-up, "
+                      f"float64 (reference-native), torch CPU with {os.cpu_count()} threads", "ms_per_step": round(sec * 1e3, 2)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    B = 16          # bounded sample of the 64-graph batch: keeps --steps K --warmup W within minutes
+    steps, warmup = min(args.steps, 5), min(max(args.warmup, 1), 2)
+    sec, n = _oracle_step_time(B, steps, warmup)
+    v = round(n / sec, 1)
+    out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
+           "steps": steps, "warmup": warmup, "ms_per_step": round(sec * 1e3, 3), "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": "C2: MSMP-PDE2D RP shape (bounded sample: 16 of 64 graphs x 100 nodes), fwd+loss+bwd+AdamW, "
+                                  "oracle port of the reference CPU path (reference not importable: torch_geometric, "
+                                  "torch_scatter, torch_cluster, lem_cuda absent)"},
+           "cpu_baseline": {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                            "sample": f"16 of 64 graphs ({n} nodes) x {steps} steps, float64, {os.cpu_count()} threads"},
+           "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -109,6 +109,20 @@ int msmp_lem_bwd_y(float* dy, const float* gy, const float* y_prev, const float*
 int msmp_lem_bwd_z(const float* dz_tot, const float* gz, const float* z_prev, const float* gates, float dt,
                    float* dG, float* dz, int N, cudaStream_t stream);
 
+/* ---- decoder: Conv1d(C,8,K1,stride S1) -> Swish -> Conv1d(8,C,K2) + time stepping -------------------
+ * (models_gnn.py:208-224,275-279 with C = 1; models_gnn2D.py:382-391,448-458 with C = 2)
+ * h[N, C*128]; out[n, c*TW + k] = base + dt[k] * diff[n, c, k], base = u[n, TW-1] (C = 1) or u[n, c*TW + k].
+ * za[N, 8*L1] keeps the first pre-activation.  L1 = (128 - K1)/S1 + 1, TW = L1 - K2 + 1.
+ * bwd: dh[N, C*128], dW = [w1 | b1 | w2 | b2] gradients in the parameters' own layouts (fixed-order reduce). */
+int msmp_decoder_nweights(int C, int K1, int K2);
+size_t msmp_decoder_bwd_workspace(int N, int C, int K1, int K2);
+int msmp_decoder_fwd(const float* h, const float* w1, const float* b1, const float* w2, const float* b2,
+                     const float* u, int ldu, const float* dt, float* za, float* out, int N, int C, int K1, int S1,
+                     int L1, int K2, int TW, cudaStream_t stream);
+int msmp_decoder_bwd(const float* dout, const float* h, const float* za, const float* w1, const float* w2,
+                     const float* dt, float* dh, float* dW, int N, int C, int K1, int S1, int L1, int K2, int TW,
+                     void* workspace, size_t ws_bytes, cudaStream_t stream);
+
 /* out[i] = g[i] * swish'(z[i])  (n % 4 == 0) */
 int msmp_mul_dswish(const float* g, const float* z, float* out, size_t n, cudaStream_t stream);
 

@@ -145,7 +145,10 @@ class _LayerCoreFn(torch.autograd.Function):
         db1 = dWs[1 + V, :H]
         dW3 = torch.cat([dW3t.t(), dW3s[:V].t()], 1)
         db3 = dW3s[V]
-        return dh, dW1, db1, dW2, db2, dW3, db3, dW4t.t(), dW4s[0], None
+        # GNN_LayerLin: b4 sits directly in front of a non-affine InstanceNorm, its gradient is identically
+        # zero (SURVEY.md appendix A "structural zero"); return exact zeros instead of rounding noise.
+        db4 = dW4s[0] if aux.final else torch.zeros_like(dW4s[0])
+        return dh, dW1, db1, dW2, db2, dW3, db3, dW4t.t(), db4, None
 
 
 class _InstNormFn(torch.autograd.Function):

@@ -14,7 +14,7 @@ from torch import nn
 from .graph import get_topology
 from .layers import GNN_Layer, GNN_LayerLin, H, NodeFeatures, Swish, gate_blend  # noqa: F401 (re-exported)
 from .lem import LEM, LEMS, LEMcuda  # noqa: F401 (re-exported)
-from .solver import (cumulative_dt, linear_act, make_decoder, mlp2, pad_cols, require_cuda, variables_1field)
+from .solver import (cumulative_dt, decode, linear_act, make_decoder, mlp2, pad_cols, require_cuda, variables_1field)
 
 
 class LSTM(nn.Module):
@@ -103,8 +103,7 @@ class _Solver1F(nn.Module):
                 h = self.gnn_layers[i].forward_prepared(h, feat, topo)
 
         dt = cumulative_dt(self.pde, self.time_window, h.device)
-        diff = self.output_mlp(h[:, None]).squeeze(1)
-        out = u[:, -1:].expand(-1, self.time_window) + dt * diff          # models_gnn.py:279
+        out = decode(h, self.output_mlp, u, dt, 1, self.time_window)     # models_gnn.py:278-279
         return out.to(u_in.dtype)
 
 

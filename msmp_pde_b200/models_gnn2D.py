@@ -12,7 +12,7 @@ from .graph import get_topology
 from .layers import GNN_Layer, GNN_LayerLin, H, NodeFeatures, Swish, gate_blend  # noqa: F401
 from .lem import LEM, LEMS  # noqa: F401
 from .models_gnn import LSTM  # noqa: F401
-from .solver import linear_act, make_decoder, mlp2, pad_cols, require_cuda
+from .solver import decode, linear_act, make_decoder, mlp2, pad_cols, require_cuda
 
 
 def unflatten_u(u: torch.Tensor, time_window: int):
@@ -100,10 +100,9 @@ class _Solver2F(nn.Module):
             else:
                 h = self.gnn_layers[i].forward_prepared(h, feat, topo)
 
-        h2 = linear_act(h, self.double_mlp[0]).view(N, 2, H)              # models_gnn2D.py:444
-        diff = self.output_mlp(h2)                                        # [N, 2, tw]
-        out = unflatten_u(u, tw) + dt.view(1, 1, tw) * diff               # models_gnn2D.py:451-455
-        return torch.flatten(out, 1, 2).to(u_in.dtype)
+        h2 = linear_act(h, self.double_mlp[0])                            # [N, 2*128] (models_gnn2D.py:444)
+        out = decode(h2, self.output_mlp, u, dt, 2, tw)                   # models_gnn2D.py:448-458
+        return out.to(u_in.dtype)
 
 
 class MP_PDE_Solver2DLEMLinGated(_Solver2F):

@@ -14,6 +14,35 @@ from ._lib import check, lib
 H = 128
 _ws: dict = {}
 
+# bench.py instrumentation: number of msmp kernels launched, and (when a dict) CUDA events around the edge ops
+LAUNCHES = 0
+PROFILE_EVENTS = None
+
+
+def _count(n: int) -> None:
+    global LAUNCHES
+    LAUNCHES += n
+
+
+class _timed:
+    """Records start/stop CUDA events on the current stream around one op when PROFILE_EVENTS is a dict."""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if PROFILE_EVENTS is not None:
+            self.s = torch.cuda.Event(enable_timing=True)
+            self.e = torch.cuda.Event(enable_timing=True)
+            self.s.record()
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE_EVENTS is not None:
+            self.e.record()
+            PROFILE_EVENTS.setdefault(self.name, []).append((self.s, self.e))
+        return False
+
 
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
@@ -66,6 +95,7 @@ def linear_fwd(segs, Wt, bias=None, side=None, r=0, Wside=None, Zmul=None, Ypre=
                               _p(Zmul), _ld(Zmul) if Zmul is not None else 0, _p(Ypre),
                               _ld(Ypre) if Ypre is not None else 0, int(act), _p(R), _ld(R) if R is not None else 0,
                               out.data_ptr(), _ld(out), M, Nout, _stream()), "msmp_linear_fwd")
+    _count(1)
     return out
 
 
@@ -88,6 +118,7 @@ def linear_wgrad(X, dY, K=None, xswish=False, side=None, r=0, has_bias=False, dW
                                 _ld(side) if side is not None else 0, r if side is not None else 0, int(has_bias),
                                 dWt.data_ptr(), _p(dWside), int(accumulate), M, ws.data_ptr(), ws.numel(), _stream()),
           "msmp_linear_wgrad")
+    _count(3 if nside else 2)
     return dWt, dWside
 
 
@@ -98,9 +129,12 @@ def edge_fwd(P, Q, topo, W2t, b2, save_z2=True):
     agg = torch.empty(topo.N, H, dtype=torch.float32, device=dev)
     z2 = torch.empty(topo.E, H, dtype=torch.float32, device=dev) if save_z2 else None
     ws = _workspace(lib.msmp_edge_fwd_workspace(topo.E), dev)
-    check(lib.msmp_edge_fwd(P.data_ptr(), Q.data_ptr(), _ld(P), topo.src.data_ptr(), topo.dst.data_ptr(),
-                            topo.rowptr.data_ptr(), topo.inv_deg.data_ptr(), W2t.data_ptr(), b2.data_ptr(), _p(z2),
-                            agg.data_ptr(), topo.E, topo.N, ws.data_ptr(), ws.numel(), _stream()), "msmp_edge_fwd")
+    with _timed("edge_fwd"):
+        check(lib.msmp_edge_fwd(P.data_ptr(), Q.data_ptr(), _ld(P), topo.src.data_ptr(), topo.dst.data_ptr(),
+                                topo.rowptr.data_ptr(), topo.inv_deg.data_ptr(), W2t.data_ptr(), b2.data_ptr(),
+                                _p(z2), agg.data_ptr(), topo.E, topo.N, ws.data_ptr(), ws.numel(), _stream()),
+              "msmp_edge_fwd")
+    _count(2)
     return agg, z2
 
 
@@ -111,10 +145,13 @@ def edge_bwd(P, Q, topo, W2, z2, dagg, dP):
     dW2 = torch.empty(H, H, dtype=torch.float32, device=dev)
     db2 = torch.empty(H, dtype=torch.float32, device=dev)
     ws = _workspace(lib.msmp_edge_bwd_workspace(topo.E), dev)
-    check(lib.msmp_edge_bwd(P.data_ptr(), Q.data_ptr(), _ld(P), topo.src.data_ptr(), topo.dst.data_ptr(),
-                            topo.rowptr.data_ptr(), topo.inv_deg.data_ptr(), W2.data_ptr(), z2.data_ptr(),
-                            dagg.data_ptr(), _ld(dagg), dz1.data_ptr(), dP.data_ptr(), _ld(dP), dW2.data_ptr(),
-                            db2.data_ptr(), topo.E, topo.N, ws.data_ptr(), ws.numel(), _stream()), "msmp_edge_bwd")
+    with _timed("edge_bwd"):
+        check(lib.msmp_edge_bwd(P.data_ptr(), Q.data_ptr(), _ld(P), topo.src.data_ptr(), topo.dst.data_ptr(),
+                                topo.rowptr.data_ptr(), topo.inv_deg.data_ptr(), W2.data_ptr(), z2.data_ptr(),
+                                dagg.data_ptr(), _ld(dagg), dz1.data_ptr(), dP.data_ptr(), _ld(dP), dW2.data_ptr(),
+                                db2.data_ptr(), topo.E, topo.N, ws.data_ptr(), ws.numel(), _stream()),
+              "msmp_edge_bwd")
+    _count(4)
     return dz1, dW2, db2
 
 
@@ -126,6 +163,7 @@ def segment_reduce(src, ptr, perm=None, scale=None, out=None, N=None):
         out = torch.empty(N, H, dtype=torch.float32, device=src.device)
     check(lib.msmp_segment_reduce(src.data_ptr(), _ld(src), _p(perm), ptr.data_ptr(), _p(scale), out.data_ptr(),
                                   _ld(out), N, _stream()), "msmp_segment_reduce")
+    _count(1)
     return out
 
 
@@ -141,6 +179,7 @@ def instnorm_fwd(y0, topo, y1=None, h=None, eps=1e-5):
                                 topo.chunk_end.data_ptr(), topo.graph_chunk_ptr.data_ptr(), topo.node_graph.data_ptr(),
                                 topo.nchunks, topo.B, topo.N, mode, eps, stat.data_ptr(), out.data_ptr(),
                                 ws.data_ptr(), ws.numel(), _stream()), "msmp_instnorm_fwd")
+    _count(3)
     return out, stat
 
 
@@ -158,6 +197,7 @@ def instnorm_bwd(dout, y0, topo, stat, y1=None, h=None):
                                 topo.graph_chunk_ptr.data_ptr(), topo.node_graph.data_ptr(), topo.nchunks, topo.B,
                                 topo.N, mode, dy0.data_ptr(), _p(dy1), H, _p(dh), ws.data_ptr(), ws.numel(),
                                 _stream()), "msmp_instnorm_bwd")
+    _count(3)
     return dy0 if mode == 0 else (dy0, dy1, dh)
 
 
@@ -165,6 +205,7 @@ def mul_dswish(g, z):
     g = g.contiguous()
     out = torch.empty_like(z)
     check(lib.msmp_mul_dswish(g.data_ptr(), z.data_ptr(), out.data_ptr(), z.numel(), _stream()), "msmp_mul_dswish")
+    _count(1)
     return out
 
 
@@ -172,18 +213,51 @@ def mul_dswish(g, z):
 def lem_gate_z(G, z_prev, dt, gates_t, z_new):
     check(lib.msmp_lem_gate_z(G.data_ptr(), z_prev.data_ptr(), float(dt), gates_t.data_ptr(), z_new.data_ptr(),
                               z_prev.shape[0], _stream()), "msmp_lem_gate_z")
+    _count(1)
 
 
 def lem_gate_y(L, y_prev, gates_t, y_new):
     check(lib.msmp_lem_gate_y(L.data_ptr(), y_prev.data_ptr(), gates_t.data_ptr(), y_new.data_ptr(),
                               y_prev.shape[0], _stream()), "msmp_lem_gate_y")
+    _count(1)
 
 
 def lem_bwd_y(dy, gy_t, y_prev, gates_t, dt, dL_t, dG_t):
     check(lib.msmp_lem_bwd_y(dy.data_ptr(), _p(gy_t), y_prev.data_ptr(), gates_t.data_ptr(), float(dt),
                              dL_t.data_ptr(), dG_t.data_ptr(), y_prev.shape[0], _stream()), "msmp_lem_bwd_y")
+    _count(1)
 
 
 def lem_bwd_z(dz_tot, gz_t, z_prev, gates_t, dt, dG_t, dz):
     check(lib.msmp_lem_bwd_z(dz_tot.data_ptr(), _p(gz_t), z_prev.data_ptr(), gates_t.data_ptr(), float(dt),
                              dG_t.data_ptr(), dz.data_ptr(), z_prev.shape[0], _stream()), "msmp_lem_bwd_z")
+    _count(1)
+
+
+# ---- decoder ----------------------------------------------------------------------------------------
+def decoder_fwd(h, w1, b1, w2, b2, u, dt, geom):
+    """geom = (C, K1, S1, L1, K2, TW).  Returns (out [N, C*TW], za [N, 8*L1])."""
+    C, K1, S1, L1, K2, TW = geom
+    N = h.shape[0]
+    out = torch.empty(N, C * TW, dtype=torch.float32, device=h.device)
+    za = torch.empty(N, 8 * L1, dtype=torch.float32, device=h.device)
+    check(lib.msmp_decoder_fwd(h.data_ptr(), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(),
+                               u.data_ptr(), _ld(u), dt.data_ptr(), za.data_ptr(), out.data_ptr(), N, C, K1, S1, L1,
+                               K2, TW, _stream()), "msmp_decoder_fwd")
+    _count(1)
+    return out, za
+
+
+def decoder_bwd(dout, h, za, w1, w2, dt, geom):
+    """Returns (dh [N, C*128], dW flat [w1 | b1 | w2 | b2])."""
+    C, K1, S1, L1, K2, TW = geom
+    N = h.shape[0]
+    dev = h.device
+    dh = torch.empty_like(h)
+    dW = torch.empty(lib.msmp_decoder_nweights(C, K1, K2), dtype=torch.float32, device=dev)
+    ws = _workspace(lib.msmp_decoder_bwd_workspace(N, C, K1, K2), dev)
+    check(lib.msmp_decoder_bwd(dout.data_ptr(), h.data_ptr(), za.data_ptr(), w1.data_ptr(), w2.data_ptr(),
+                               dt.data_ptr(), dh.data_ptr(), dW.data_ptr(), N, C, K1, S1, L1, K2, TW, ws.data_ptr(),
+                               ws.numel(), _stream()), "msmp_decoder_bwd")
+    _count(2)
+    return dh, dW

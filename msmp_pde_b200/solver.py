@@ -85,6 +85,37 @@ def make_decoder(time_window: int, channels: int):
     raise AssertionError("unsupported time_window")
 
 
+class _DecoderFn(torch.autograd.Function):
+    """out = base(u) + dt * Conv1d(Swish(Conv1d(h)))  on msmp_decoder_fwd / msmp_decoder_bwd."""
+
+    @staticmethod
+    def forward(ctx, h, w1, b1, w2, b2, u, dt, geom):
+        h = h.contiguous()
+        out, za = ops.decoder_fwd(h, w1, b1, w2, b2, u, dt, geom)
+        ctx.geom = geom
+        ctx.save_for_backward(h, za, w1, w2, dt)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        h, za, w1, w2, dt = ctx.saved_tensors
+        C, K1, S1, L1, K2, TW = ctx.geom
+        dh, dW = ops.decoder_bwd(dout.contiguous(), h, za, w1, w2, dt, ctx.geom)
+        n1 = 8 * C * K1
+        n2 = C * 8 * K2
+        return (dh, dW[:n1].view(8, C, K1), dW[n1:n1 + 8], dW[n1 + 8:n1 + 8 + n2].view(C, 8, K2),
+                dW[n1 + 8 + n2:], None, None, None)
+
+
+def decode(h, output_mlp: nn.Sequential, u, dt, channels: int, time_window: int):
+    """h [N, channels*128] -> out [N, channels*time_window] (formula 10 of the paper + time stepping)."""
+    c1, c2 = output_mlp[0], output_mlp[2]
+    K1, S1, K2 = c1.kernel_size[0], c1.stride[0], c2.kernel_size[0]
+    L1 = (H - K1) // S1 + 1
+    geom = (channels, K1, S1, L1, K2, time_window)
+    return _DecoderFn.apply(h, c1.weight, c1.bias, c2.weight, c2.bias, u, dt.reshape(-1).contiguous(), geom)
+
+
 def cumulative_dt(pde, time_window, device):
     # cumulated in float64 like the reference (models_gnn.py:275-276), then rounded once to fp32
     return torch.cumsum(torch.ones(1, time_window, dtype=torch.float64, device=device) * float(pde.dt), dim=1).float()

@@ -218,7 +218,7 @@ class MP_PDE_Solver(nn.Module):
         h = self.embedding_mlp(torch.cat((u, pos_x, variables), -1))
         for layer in self.gnn_layers:
             h = layer(h, u, pos_x, variables, data.edge_index, data.batch)
-        dt = torch.cumsum(torch.ones(1, self.time_window, dtype=h.dtype) * self.pde.dt, dim=1)
+        dt = torch.cumsum(torch.ones(1, self.time_window, dtype=h.dtype, device=h.device) * self.pde.dt, dim=1)
         diff = self.output_mlp(h[:, None]).squeeze(1)
         return u[:, -1].repeat(self.time_window, 1).transpose(0, 1) + dt * diff
 
@@ -257,7 +257,7 @@ class MP_PDE_SolverLEMLinGated(nn.Module):
         for i in range(self.hidden_layer):
             tau = torch.sigmoid(self.gnn_layers_gate[i](h, u, pos_x, variables, data.edge_index, data.batch))
             h = (1 - tau) * h + tau * self.swish(self.gnn_layers[i](h, u, pos_x, variables, data.edge_index, data.batch))
-        dt = torch.cumsum(torch.ones(1, self.time_window, dtype=h.dtype) * self.pde.dt, dim=1)
+        dt = torch.cumsum(torch.ones(1, self.time_window, dtype=h.dtype, device=h.device) * self.pde.dt, dim=1)
         diff = self.output_mlp(h[:, None]).squeeze(1)
         return u[:, -1].repeat(self.time_window, 1).transpose(0, 1) + dt * diff
 
@@ -306,7 +306,7 @@ class MP_PDE_Solver2DLEMLinGated(nn.Module):
             variables = torch.cat((variables, data.a / self.eq_variables["a"]), -1)
         if "b" in self.eq_variables:      # sic: data.a is used for 'b' (models_gnn2D.py:419)
             variables = torch.cat((variables, data.a / self.eq_variables["b"]), -1)
-        dt = torch.cumsum(torch.ones(1, 1, tw, dtype=u.dtype) * self.pde.dt, dim=2)
+        dt = torch.cumsum(torch.ones(1, 1, tw, dtype=u.dtype, device=u.device) * self.pde.dt, dim=2)
         ts = (dt + pos_t).squeeze(0)                                   # [N, tw] (un-normalised dt + normalised t)
         lem_in = torch.stack([
             torch.cat((pos_x, u[:, t:t + 1], u[:, t + tw:t + tw + 1], ts[:, t:t + 1], variables[:, 1:]), -1)

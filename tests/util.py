@@ -7,15 +7,30 @@ import numpy as np
 import torch
 
 
+def _hash_uniform(n: int, t: int) -> torch.Tensor:
+    """Exact integer hash (int64 arithmetic mod 2^32) of (index, tensor id) -> float64 uniform in [-1, 1)."""
+    M = 0xFFFFFFFF
+    x = (torch.arange(1, n + 1, dtype=torch.int64) * 2654435761 + (t + 1) * 40503) & M
+    x = ((x ^ (x >> 16)) * 0x45D9F3B) & M
+    x = ((x ^ (x >> 16)) * 0x45D9F3B) & M
+    x = x ^ (x >> 16)
+    return x.double() / 2.0 ** 31 - 1.0
+
+
 def formula_weights_(module: torch.nn.Module) -> None:
-    """Fill every parameter with a closed-form, RNG-independent pattern (so fixtures need not store
-    weights): w[i] = s * sin(0.7 i (1 + 0.013 t) + t), s = 1/sqrt(fan_in) for matrices, 0.1 for vectors."""
+    """Fill every parameter with a closed-form, RNG-independent pattern (so fixtures need not store weights):
+    w = U(-1, 1) / sqrt(fan_in) from an exact integer hash -- the scale of torch's default Linear/Conv init."""
     with torch.no_grad():
+        fan = {}
+        for name, p in module.state_dict().items():
+            if p.dim() > 1:
+                fan[name.rsplit(".", 1)[0]] = max(1, p[0].numel())
         for t, (name, p) in enumerate(module.state_dict().items()):
-            n = p.numel()
-            i = torch.arange(n, dtype=torch.float64)
-            s = 0.1 if p.dim() == 1 else 1.0 / math.sqrt(max(1, p[0].numel()))
-            vals = s * torch.sin(0.7 * i * (1 + 0.013 * t) + t)
+            owner = name.rsplit(".", 1)[0]
+            f = fan.get(owner, p.numel())
+            if "rnn" in name:                 # LEMcuda: every tensor is U(-1/sqrt(nhid), 1/sqrt(nhid))
+                f = 128
+            vals = _hash_uniform(p.numel(), t) / math.sqrt(f)
             p.copy_(vals.view(p.shape).to(p.dtype))
 
 
