@@ -47,6 +47,16 @@ int msmp_linear_fwd(const float* const* A, const int* lda, const int* ka, const 
                     const float* Wside, const float* Zmul, int ldz, float* Ypre, int ldpre, int act,
                     const float* R, int ldr, float* Y, int ldy, int M, int Nout, cudaStream_t stream);
 
+/* Tensor-core variant (tcgen05.mma kind::tf32, error-compensated 3xTF32, accumulators in TMEM): same contract,
+ * the weight is passed as pre-split, pre-swizzled tile images Bimg[ntile][K/32][2 (hi,lo)][128 x 32 fp32]:
+ * element (n, k) of a tile sits at float offset ((n>>3)*1024 + (n&7)*128 + ((((k>>2)^n)&7)<<4))/4 + (k&3);
+ * hi = value rounded to tf32, lo = value - hi.  Wside has row stride ldws. */
+size_t msmp_linear_tc_image_floats(int K, int Nout);
+int msmp_linear_tc_fwd(const float* const* A, const int* lda, const int* ka, const int* aswish, int nseg,
+                       const float* Bimg, const float* bias, const float* side, int lds, int r, const float* Wside,
+                       int ldws, const float* Zmul, int ldz, float* Ypre, int ldpre, int act, const float* R,
+                       int ldr, float* Y, int ldy, int M, int Nout, cudaStream_t stream);
+
 /* dWt[K, Nout] (+)= X[M, K]^T (swish(X) if xswish) * dY[M, Nout];
  * dWside[r (+1), Nout] (+)= [side | 1]^T * dY  (bias gradient = the implicit ones column when has_bias).
  * Deterministic: per-CTA partials over row ranges + fixed-order reduction. */

@@ -1,0 +1,205 @@
+// Node-level dense layers on the 5th-gen tensor cores (tcgen05.mma kind::tf32, accumulators in TMEM).
+//
+//   msmp_linear_tc_fwd : same contract as msmp_linear_fwd (Y = epilogue([A0|A1|A2] W^T + bias + side Wside))
+//                        with the weight given as pre-split (hi | lo), pre-swizzled tile images:
+//                        Bimg[ntile][kchunk][2][128 x 32 fp32]  (row n of tile, column k of chunk).
+// Per CTA: one 128 x 128 output tile.  K is consumed in 32-wide chunks through a 2-stage ring:
+//   weights  : one 32 KiB cp.async.bulk (TMA engine, 1-D) per chunk, completion on an mbarrier
+//   A operand: threads load fp32 rows (coalesced), apply the optional swish, split into tf32 hi/lo and
+//              store both in the UMMA 128B-swizzled layout (generic proxy -> fence.proxy.async)
+//   MMA      : one thread issues 4 k-steps x 3 products (hi*hi, lo*hi, hi*lo) per chunk, tcgen05.commit
+//              releases the stage; production of chunk c+1 overlaps the MMAs of chunk c
+//   epilogue : tcgen05.ld (32 lanes x 32 columns per warp) -> bias / side / swish / residual -> global
+#include "umma.cuh"
+#include "msmp_b200.h"
+
+namespace msmp {
+
+constexpr int TC_STAGE_BYTES = 4 * IMG_BYTES;                 // A_hi, A_lo, B_hi, B_lo
+constexpr int TC_STAGES = 2;
+constexpr int TC_SMEM = TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+
+struct LinTcParams {
+  const float* A[3];
+  int lda[3];
+  int ka[3];
+  int aswish[3];
+  int nseg;
+  const float* Bimg;
+  const float* bias;
+  const float* side;
+  int lds;
+  int r;
+  const float* Wside;
+  int ldws;
+  const float* Zmul;
+  int ldz;
+  float* Ypre;
+  int ldpre;
+  int act;
+  const float* R;
+  int ldr;
+  float* Y;
+  int ldy;
+  int M;
+  int Nout;
+};
+
+__global__ void __launch_bounds__(256, 1) k_linear_tc(const LinTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES);   // full[2], free[2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row0 = blockIdx.x * 128;
+  const int ntile = blockIdx.y;
+
+  int ktot = 0;
+  for (int s = 0; s < p.nseg; ++s) ktot += p.ka[s];
+  const int nchunks = ktot >> 5;
+
+  if (warp == 0) tmem_alloc(tmem_slot, 128);
+  if (tid == 32) {
+    for (int s = 0; s < TC_STAGES; ++s) {
+      mbar_init(&bars[s], 1);
+      mbar_init(&bars[2 + s], 1);
+    }
+    fence_barrier_init();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  constexpr uint32_t IDESC = umma_idesc_tf32(128, 128, 0, 0);
+
+  for (int c = 0; c < nchunks; ++c) {
+    const int s = c & 1, use = c >> 1;
+    uint8_t* st = smem + s * TC_STAGE_BYTES;
+    if (c >= TC_STAGES) mbar_wait(&bars[2 + s], (use - 1) & 1);      // MMAs that read this stage are done
+    if (tid == 0) {
+      mbar_expect_tx(&bars[s], 2 * IMG_BYTES);
+      bulk_g2s(st + 2 * IMG_BYTES, p.Bimg + ((size_t)ntile * nchunks + c) * (2 * IMG_BYTES / 4), 2 * IMG_BYTES, &bars[s]);
+    }
+    // locate the chunk inside the concatenated A segments
+    int seg = 0, koff = c * 32;
+    while (seg < p.nseg - 1 && koff >= p.ka[seg]) {
+      koff -= p.ka[seg];
+      ++seg;
+    }
+    const float* A = p.A[seg];
+    const int lda = p.lda[seg];
+    const bool sw = p.aswish[seg] != 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = tid + 256 * i;
+      const int r = idx >> 3, c16 = idx & 7;
+      const int grow = row0 + r;
+      float4 v = zero4();
+      if (grow < p.M) v = ldg4(A + (size_t)grow * lda + koff + 4 * c16);
+      if (sw) v = swish4(v);
+      store_split4(st, st + IMG_BYTES, img_off(r, c16), v);
+    }
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+      mbar_wait(&bars[s], use & 1);                                  // weights of this chunk have landed
+      tc_fence_after();
+      const uint32_t a_hi = smem_u32(st), a_lo = a_hi + IMG_BYTES, b_hi = a_hi + 2 * IMG_BYTES, b_lo = a_hi + 3 * IMG_BYTES;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint64_t dah = umma_desc(a_hi + 32 * k, 16, 1024), dal = umma_desc(a_lo + 32 * k, 16, 1024);
+        const uint64_t dbh = umma_desc(b_hi + 32 * k, 16, 1024), dbl = umma_desc(b_lo + 32 * k, 16, 1024);
+        umma_tf32(tmem, dah, dbh, IDESC, (c | k) ? 1u : 0u);
+        umma_tf32(tmem, dal, dbh, IDESC, 1u);
+        umma_tf32(tmem, dah, dbl, IDESC, 1u);
+      }
+      umma_commit(&bars[2 + s]);
+    }
+  }
+  // accumulator complete when the last commit arrives
+  {
+    const int last = nchunks - 1;
+    mbar_wait(&bars[2 + (last & 1)], (last >> 1) & 1);
+    tc_fence_after();
+  }
+  // ---- epilogue: warp w reads lanes 32*(w&3).., columns 64*(w>>2)..
+  const int row = row0 + 32 * (warp & 3) + lane;
+  const int n0 = ntile * 128;
+  float sv[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) sv[q] = (q < p.r && row < p.M) ? __ldg(p.side + (size_t)row * p.lds + q) : 0.f;
+#pragma unroll 1
+  for (int cb = 0; cb < 2; ++cb) {
+    const int colbase = 64 * (warp >> 2) + 32 * cb;
+    float v[32];
+    __syncwarp();
+    tmem_ld32(tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)colbase, v);
+    if (row < p.M) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const int col = n0 + colbase + j;
+        if (col >= p.Nout) continue;
+        float4 z = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        if (p.bias) z = add4(z, ldg4(p.bias + col));
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          if (q >= p.r) break;
+          float4 w = ldg4(p.Wside + (size_t)q * p.ldws + col);
+          z.x = fmaf(sv[q], w.x, z.x);
+          z.y = fmaf(sv[q], w.y, z.y);
+          z.z = fmaf(sv[q], w.z, z.z);
+          z.w = fmaf(sv[q], w.w, z.w);
+        }
+        if (p.Zmul) {
+          float4 zz = ldg4(p.Zmul + (size_t)row * p.ldz + col);
+          z = mul4(z, make_float4(dswish(zz.x), dswish(zz.y), dswish(zz.z), dswish(zz.w)));
+        }
+        if (p.Ypre) st4(p.Ypre + (size_t)row * p.ldpre + col, z);
+        if (p.act) z = swish4(z);
+        if (p.R) z = add4(z, ldg4(p.R + (size_t)row * p.ldr + col));
+        st4(p.Y + (size_t)row * p.ldy + col, z);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 128);
+}
+
+}  // namespace msmp
+
+using namespace msmp;
+
+extern "C" size_t msmp_linear_tc_image_floats(int K, int Nout) {
+  return (size_t)((Nout + 127) / 128) * (size_t)(K / 32) * 2 * (IMG_BYTES / 4);
+}
+
+extern "C" int msmp_linear_tc_fwd(const float* const* A, const int* lda, const int* ka, const int* aswish, int nseg,
+                                  const float* Bimg, const float* bias, const float* side, int lds, int r,
+                                  const float* Wside, int ldws, const float* Zmul, int ldz, float* Ypre, int ldpre,
+                                  int act, const float* R, int ldr, float* Y, int ldy, int M, int Nout,
+                                  cudaStream_t stream) {
+  if (nseg < 1 || nseg > 3 || M < 0 || Nout <= 0 || (Nout & 3) || r < 0 || r > 8) return MSMP_ERR_ARG;
+  if (M == 0) return MSMP_OK;
+  LinTcParams p{};
+  for (int s = 0; s < nseg; ++s) {
+    if (ka[s] <= 0 || (ka[s] & 31) || (lda[s] & 3)) return MSMP_ERR_ARG;
+    p.A[s] = A[s];
+    p.lda[s] = lda[s];
+    p.ka[s] = ka[s];
+    p.aswish[s] = aswish ? aswish[s] : 0;
+  }
+  p.nseg = nseg; p.Bimg = Bimg; p.bias = bias; p.side = side; p.lds = lds; p.r = side ? r : 0; p.Wside = Wside;
+  p.ldws = ldws; p.Zmul = Zmul; p.ldz = ldz; p.Ypre = Ypre; p.ldpre = ldpre; p.act = act; p.R = R; p.ldr = ldr;
+  p.Y = Y; p.ldy = ldy; p.M = M; p.Nout = Nout;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(k_linear_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM) != cudaSuccess)
+      return MSMP_ERR_CUDA;
+    attr_set = true;
+  }
+  dim3 grid((M + 127) / 128, (Nout + 127) / 128);
+  k_linear_tc<<<grid, 256, TC_SMEM, stream>>>(p);
+  MSMP_CHECK_LAUNCH();
+  return MSMP_OK;
+}

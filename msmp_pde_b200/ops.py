@@ -99,6 +99,61 @@ def linear_fwd(segs, Wt, bias=None, side=None, r=0, Wside=None, Zmul=None, Ypre=
     return out
 
 
+_IMG_IDX = {}
+
+
+def _img_index(device):
+    """float offset of element (n, k) inside a [128 x 32] UMMA 128B-swizzled tile image (see msmp_b200.h)."""
+    idx = _IMG_IDX.get(device)
+    if idx is None:
+        n = torch.arange(128, device=device).view(128, 1)
+        k = torch.arange(32, device=device).view(1, 32)
+        idx = ((n >> 3) * 1024 + (n & 7) * 128 + ((((k >> 2) ^ n) & 7) << 4)) // 4 + (k & 3)
+        idx = idx.reshape(-1)
+        _IMG_IDX[device] = idx
+    return idx
+
+
+def tc_images(Wt: torch.Tensor) -> torch.Tensor:
+    """Pre-split (tf32 hi | lo), pre-swizzled weight images for msmp_linear_tc_fwd from the k-major weight
+    Wt[K, N] (K % 32 == 0): returns [ceil(N/128), K/32, 2, 4096] fp32."""
+    K, N = Wt.shape
+    nt, nc = (N + 127) // 128, K // 32
+    Wp = Wt.new_zeros(K, nt * 128)
+    Wp[:, :N] = Wt
+    B = Wp.t().reshape(nt, 128, nc, 32).permute(0, 2, 1, 3).contiguous()          # [nt, nc, n, k]
+    hi = ((B.view(torch.int32) + 0x1000) & -8192).view(torch.float32)
+    lo = B - hi
+    img = Wt.new_empty(nt, nc, 2, 4096)
+    idx = _img_index(Wt.device)
+    img[:, :, 0, idx] = hi.reshape(nt, nc, 4096)
+    img[:, :, 1, idx] = lo.reshape(nt, nc, 4096)
+    return img
+
+
+def linear_tc_fwd(segs, img, Nout, bias=None, side=None, r=0, Wside=None, Zmul=None, Ypre=None, act=False, R=None,
+                  out=None, aswish=None):
+    """Tensor-core (3xTF32) version of linear_fwd; ``img`` = tc_images(Wt)."""
+    n = len(segs)
+    M = segs[0].shape[0]
+    for i, a in enumerate(segs):
+        _req(a, f"A{i}")
+    if out is None:
+        out = torch.empty(M, Nout, dtype=torch.float32, device=img.device)
+    A = (ctypes.c_void_p * 3)(*[a.data_ptr() for a in segs], *([0] * (3 - n)))
+    lda = (ctypes.c_int * 3)(*[_ld(a) for a in segs], *([0] * (3 - n)))
+    ka = (ctypes.c_int * 3)(*[a.shape[1] for a in segs], *([0] * (3 - n)))
+    asw = (ctypes.c_int * 3)(*([int(bool(x)) for x in aswish] if aswish else [0] * n), *([0] * (3 - n)))
+    check(lib.msmp_linear_tc_fwd(A, lda, ka, asw, n, img.data_ptr(), _p(bias), _p(side),
+                                 _ld(side) if side is not None else 0, r if side is not None else 0, _p(Wside),
+                                 _ld(Wside) if Wside is not None else 0, _p(Zmul),
+                                 _ld(Zmul) if Zmul is not None else 0, _p(Ypre), _ld(Ypre) if Ypre is not None else 0,
+                                 int(act), _p(R), _ld(R) if R is not None else 0, out.data_ptr(), _ld(out), M, Nout,
+                                 _stream()), "msmp_linear_tc_fwd")
+    _count(1)
+    return out
+
+
 def linear_wgrad(X, dY, K=None, xswish=False, side=None, r=0, has_bias=False, dWt=None, dWside=None,
                  accumulate=False):
     """dWt[K, Nout] = X^T dY ; dWside[r(+1), Nout] = [side|1]^T dY."""

@@ -65,6 +65,38 @@ def test_linear_fwd(dev, M):
     assert rel_err(y, ref) < TOL
 
 
+@pytest.mark.parametrize("M,Nout", [(1, 128), (300, 256), (1024, 384), (6400, 128)])
+def test_linear_tc_fwd(dev, M, Nout):
+    """tcgen05 3xTF32 path: same contract and the same 1e-5 bar as the FFMA path."""
+    from msmp_pde_b200 import ops
+    g = torch.Generator().manual_seed(M + Nout)
+    A0 = torch.randn(M, 128, generator=g)
+    A1 = torch.randn(M, 64, generator=g)
+    Wt = torch.randn(192, Nout, generator=g) / 14
+    bias = torch.randn(Nout, generator=g)
+    side = torch.randn(M, 8, generator=g)
+    Ws = torch.randn(8, Nout, generator=g)
+    R = torch.randn(M, Nout, generator=g)
+    Z = torch.randn(M, Nout, generator=g)
+    c = lambda t: t.to(dev)
+    img = ops.tc_images(c(Wt))
+    ypre = torch.empty(M, Nout, device=dev)
+    y = ops.linear_tc_fwd([c(A0), c(A1)], img, Nout, bias=c(bias), side=c(side), r=3, Wside=c(Ws), Zmul=c(Z),
+                          Ypre=ypre, act=True, R=c(R), aswish=[0, 1])
+    d = lambda t: t.double()
+    z = torch.cat([d(A0), _sw(d(A1))], 1) @ d(Wt) + d(bias) + d(side)[:, :3] @ d(Ws)[:3]
+    z = z * _dsw(d(Z))
+    ref = _sw(z) + d(R)
+    e1, e2 = rel_err(ypre, z), rel_err(y, ref)
+    print(f"linear_tc M={M} Nout={Nout}: pre {e1:.2e} out {e2:.2e}")
+    assert e1 < TOL and e2 < TOL
+    # plain single-segment use, bit-stable
+    y1 = ops.linear_tc_fwd([c(A0)], ops.tc_images(c(Wt[:128].contiguous())), Nout)
+    y2 = ops.linear_tc_fwd([c(A0)], ops.tc_images(c(Wt[:128].contiguous())), Nout)
+    assert torch.equal(y1, y2)
+    assert rel_err(y1, d(A0) @ d(Wt[:128])) < TOL
+
+
 def test_linear_fwd_plain_and_strided(dev):
     from msmp_pde_b200 import ops
     g = torch.Generator().manual_seed(3)
