@@ -66,6 +66,12 @@ int msmp_linear_wgrad(const float* X, int ldx, int K, int xswish, const float* d
                       const float* side, int lds, int r, int has_bias, float* dWt, float* dWside,
                       int accumulate, int M, void* workspace, size_t ws_bytes, cudaStream_t stream);
 
+/* Tensor-core variant (both operands MN-major, 3xTF32, split-M partials in TMEM -> fixed-order reduce);
+ * same contract as msmp_linear_wgrad, r + has_bias <= 8. */
+int msmp_linear_wgrad_tc(const float* X, int ldx, int K, int xswish, const float* dY, int lddy, int Nout,
+                         const float* side, int lds, int r, int has_bias, float* dWt, float* dWside, int accumulate,
+                         int M, void* workspace, size_t ws_bytes, cudaStream_t stream);
+
 /* ---- edge kernels (edges sorted by destination; rowptr = CSR offsets by destination) ------------
  * forward : agg[i] = inv_deg[i] * sum_{e -> i} sw( sw(P[dst e] + Q[src e]) W2^T + b2 );  z2 (optional) keeps
  *           the second pre-activation for the backward pass.  W2t[k][n] = W2[n][k]. */

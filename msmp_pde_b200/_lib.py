@@ -41,6 +41,7 @@ _SIGS = {
     "msmp_linear_wgrad_splits": (I, [I, I, I]),
     "msmp_linear_wgrad_workspace": (S, [I, I, I, I]),
     "msmp_linear_wgrad": (I, [P, I, I, I, P, I, I, P, I, I, I, P, P, I, I, P, S, P]),
+    "msmp_linear_wgrad_tc": (I, [P, I, I, I, P, I, I, P, I, I, I, P, P, I, I, P, S, P]),
     "msmp_edge_tiles": (I, [I]),
     "msmp_edge_grid": (I, [I]),
     "msmp_edge_fwd_workspace": (S, [I]),

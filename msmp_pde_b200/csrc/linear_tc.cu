@@ -72,6 +72,34 @@ __global__ void __launch_bounds__(256, 1) k_linear_tc(const LinTcParams p) {
   const uint32_t tmem = *tmem_slot;
   constexpr uint32_t IDESC = umma_idesc_tf32(128, 128, 0, 0);
 
+  // chunk c -> (segment pointer, row stride, column offset, swish flag)
+  auto locate = [&](int c, const float*& A, int& lda, int& koff, bool& sw) {
+    int seg = 0;
+    koff = c * 32;
+    while (seg < p.nseg - 1 && koff >= p.ka[seg]) {
+      koff -= p.ka[seg];
+      ++seg;
+    }
+    A = p.A[seg];
+    lda = p.lda[seg];
+    sw = p.aswish[seg] != 0;
+  };
+  // software pipeline: the fp32 rows of chunk c+1 are in flight (registers) while chunk c is split/stored and
+  // its MMAs run; weights of chunk c arrive by bulk copy while the A operand is being staged.
+  float4 pre[4];
+  bool pre_sw;
+  auto prefetch = [&](int c) {
+    const float* A;
+    int lda, koff;
+    locate(c, A, lda, koff, pre_sw);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = tid + 256 * i;
+      const int grow = row0 + (idx >> 3);
+      pre[i] = (grow < p.M) ? ldg4(A + (size_t)grow * lda + koff + 4 * (idx & 7)) : zero4();
+    }
+  };
+  prefetch(0);
   for (int c = 0; c < nchunks; ++c) {
     const int s = c & 1, use = c >> 1;
     uint8_t* st = smem + s * TC_STAGE_BYTES;
@@ -80,25 +108,14 @@ __global__ void __launch_bounds__(256, 1) k_linear_tc(const LinTcParams p) {
       mbar_expect_tx(&bars[s], 2 * IMG_BYTES);
       bulk_g2s(st + 2 * IMG_BYTES, p.Bimg + ((size_t)ntile * nchunks + c) * (2 * IMG_BYTES / 4), 2 * IMG_BYTES, &bars[s]);
     }
-    // locate the chunk inside the concatenated A segments
-    int seg = 0, koff = c * 32;
-    while (seg < p.nseg - 1 && koff >= p.ka[seg]) {
-      koff -= p.ka[seg];
-      ++seg;
-    }
-    const float* A = p.A[seg];
-    const int lda = p.lda[seg];
-    const bool sw = p.aswish[seg] != 0;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int idx = tid + 256 * i;
-      const int r = idx >> 3, c16 = idx & 7;
-      const int grow = row0 + r;
-      float4 v = zero4();
-      if (grow < p.M) v = ldg4(A + (size_t)grow * lda + koff + 4 * c16);
-      if (sw) v = swish4(v);
-      store_split4(st, st + IMG_BYTES, img_off(r, c16), v);
+      float4 v = pre[i];
+      if (pre_sw) v = swish4(v);
+      store_split4(st, st + IMG_BYTES, img_off(idx >> 3, idx & 7), v);
     }
+    if (c + 1 < nchunks) prefetch(c + 1);
     fence_proxy_async();
     __syncthreads();
     if (tid == 0) {

@@ -1,0 +1,220 @@
+// Weight gradients on the tensor cores: dWt[k][n] = sum_m X[m][k] * dY[m][n]  (tcgen05 kind::tf32, 3xTF32).
+//
+// The reduction index m is the MMA K dimension, so BOTH operands are MN-major.  For 32-bit MN-major operands the
+// only shared-memory layout the tensor core accepts is SWIZZLE_128B_BASE32B (CUTLASS sm100_common.inl:92): an atom
+// is 4 K-rows x 128 B (32 MN-contiguous floats per row) and the four 32-byte units of a row are XOR-permuted with
+// (row & 3) (Swizzle<2,5,2> on byte addresses; verified on hardware by scripts/diag history).  A chunk of 32 rows of X
+// ([32 x 128] fp32, rows = MMA-K, columns = MMA-M) is stored as four column blocks of [32 rows x 128 B]:
+//     descriptor start = base + kstep * 1024 (8 rows),  LBO = 4096 (next 32 columns),  SBO = 512 (next 4 rows).
+// Per CTA: one 128 (k) x 128 (n) tile of dWt over a contiguous range of rows (split-M), accumulated in TMEM;
+// the per-split partials are summed in a fixed order afterwards (deterministic, no atomics).  Side / bias
+// gradients ([side | 1]^T dY) are accumulated on the CUDA cores by the threads that stage the dY operand.
+#include "umma.cuh"
+#include "msmp_b200.h"
+
+namespace msmp {
+
+constexpr int WT_CHUNK = 32;                               // rows (MMA-K) per stage
+constexpr int WT_OP_BYTES = WT_CHUNK * 128 * 4;            // one [32 x 128] operand image = 16 KiB
+constexpr int WT_STAGE_BYTES = 4 * WT_OP_BYTES;            // X_hi, X_lo, dY_hi, dY_lo
+constexpr int WT_SMEM = 2 * WT_STAGE_BYTES + 1024 + 256 + 8 * 8 * 128 * 4;
+
+struct WgradTcParams {
+  const float* X; int ldx; int K; int xswish;
+  const float* dY; int lddy; int Nout;
+  const float* side; int lds; int r; int has_bias;
+  float* part;         // [S][K][Nout]
+  float* part_side;    // [S][nside][Nout]
+  int M; int rows_per_split;
+};
+
+// byte offset of (row m in 0..31, 16-byte chunk c4 in 0..31) of a [32 x 128] MN-major (BASE32B) operand image:
+// column block (c4 >> 3), row m, and inside the 128-byte row the 32-byte unit index is XORed with (m & 3).
+__device__ __forceinline__ uint32_t mn_off(int m, int c4) {
+  const int c = c4 & 7;
+  const int cs = ((((c >> 1) ^ m) & 3) << 1) | (c & 1);
+  return (uint32_t)((c4 >> 3) * 4096 + m * 128 + cs * 16);
+}
+
+__global__ void __launch_bounds__(256, 1) k_wgrad_tc(const WgradTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * WT_STAGE_BYTES);     // free[2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  float* sred = reinterpret_cast<float*>(smem + 2 * WT_STAGE_BYTES + 256);     // [8 warps][8 side rows][128]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int split = blockIdx.x;
+  const int k0 = blockIdx.y * 128, n0 = blockIdx.z * 128;
+  const int m_begin = split * p.rows_per_split;
+  const int m_end = min(p.M, m_begin + p.rows_per_split);
+  const int nchunks = (m_end > m_begin) ? (m_end - m_begin + WT_CHUNK - 1) / WT_CHUNK : 0;
+  const int nside = p.r + p.has_bias;
+  const bool do_side = (blockIdx.y == 0) && nside > 0;
+
+  if (warp == 0) tmem_alloc(tmem_slot, 128);
+  if (tid == 32) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    fence_barrier_init();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  constexpr uint32_t IDESC = umma_idesc_tf32(128, 128, 1, 1);      // both operands MN-major
+
+  // each thread stages 4 float4 of X and 4 of dY per chunk: element idx -> (row mm = idx >> 5, chunk c4 = idx & 31)
+  float4 px[4], py[4];
+  float sacc[8][4];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) sacc[q][0] = sacc[q][1] = sacc[q][2] = sacc[q][3] = 0.f;
+  auto prefetch = [&](int c) {
+    const int mb = m_begin + c * WT_CHUNK;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = tid + 256 * i;
+      const int m = mb + (idx >> 5), c4 = idx & 31;
+      const bool okm = m < m_end;
+      px[i] = (okm && k0 + 4 * c4 < p.K) ? ldg4(p.X + (size_t)m * p.ldx + k0 + 4 * c4) : zero4();
+      py[i] = (okm && n0 + 4 * c4 < p.Nout) ? ldg4(p.dY + (size_t)m * p.lddy + n0 + 4 * c4) : zero4();
+    }
+  };
+  if (nchunks > 0) prefetch(0);
+  for (int c = 0; c < nchunks; ++c) {
+    const int s = c & 1, use = c >> 1;
+    uint8_t* st = smem + s * WT_STAGE_BYTES;
+    if (c >= 2) mbar_wait(&bars[s], (use - 1) & 1);
+    const int mb = m_begin + c * WT_CHUNK;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = tid + 256 * i;
+      const int mm = idx >> 5, c4 = idx & 31;
+      float4 x = px[i];
+      if (p.xswish) x = swish4(x);
+      const uint32_t off = mn_off(mm, c4);
+      store_split4(st, st + WT_OP_BYTES, off, x);
+      store_split4(st + 2 * WT_OP_BYTES, st + 3 * WT_OP_BYTES, off, py[i]);
+      if (do_side) {
+        const int m = mb + mm;
+        if (m < m_end) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            if (q >= nside) break;
+            const float sv = (q < p.r) ? __ldg(p.side + (size_t)m * p.lds + q) : 1.0f;
+            sacc[q][0] = fmaf(sv, py[i].x, sacc[q][0]);
+            sacc[q][1] = fmaf(sv, py[i].y, sacc[q][1]);
+            sacc[q][2] = fmaf(sv, py[i].z, sacc[q][2]);
+            sacc[q][3] = fmaf(sv, py[i].w, sacc[q][3]);
+          }
+        }
+      }
+    }
+    if (c + 1 < nchunks) prefetch(c + 1);
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t xh = smem_u32(st), xl = xh + WT_OP_BYTES, yh = xh + 2 * WT_OP_BYTES, yl = xh + 3 * WT_OP_BYTES;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t ko = 1024 * k;      // 8 rows per k-step; LBO = 4096 (next 32 columns), SBO = 512 (next 4 rows)
+        const uint64_t dxh = umma_desc(xh + ko, 4096, 512, 1), dxl = umma_desc(xl + ko, 4096, 512, 1);
+        const uint64_t dyh = umma_desc(yh + ko, 4096, 512, 1), dyl = umma_desc(yl + ko, 4096, 512, 1);
+        umma_tf32(tmem, dxh, dyh, IDESC, (c | k) ? 1u : 0u);
+        umma_tf32(tmem, dxl, dyh, IDESC, 1u);
+        umma_tf32(tmem, dxh, dyl, IDESC, 1u);
+      }
+      umma_commit(&bars[s]);
+    }
+  }
+  float* out = p.part + (size_t)split * p.K * p.Nout;
+  if (nchunks > 0) {
+    const int last = nchunks - 1;
+    mbar_wait(&bars[last & 1], (last >> 1) & 1);
+    tc_fence_after();
+  }
+  // epilogue: warp w -> TMEM lanes 32*(w&3).. (= k rows), columns 64*(w>>2)..
+  {
+    const int krow = k0 + 32 * (warp & 3) + lane;
+#pragma unroll 1
+    for (int cb = 0; cb < 2; ++cb) {
+      const int colbase = 64 * (warp >> 2) + 32 * cb;
+      float v[32];
+      if (nchunks > 0) {
+        __syncwarp();
+        tmem_ld32(tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)colbase, v);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+      }
+      if (krow < p.K) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const int n = n0 + colbase + j;
+          if (n < p.Nout) st4(out + (size_t)krow * p.Nout + n, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+        }
+      }
+    }
+  }
+  // side / bias partials: fixed-order reduction over the 8 warps (thread lane owns columns 4*lane..4*lane+3)
+  if (do_side) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      if (q < nside) st4(sred + (warp * 8 + q) * 128 + 4 * lane, make_float4(sacc[q][0], sacc[q][1], sacc[q][2], sacc[q][3]));
+    __syncthreads();
+    for (int i = tid; i < nside * 128; i += 256) {
+      const int q = i >> 7, col = i & 127;
+      float s = 0.f;
+      for (int w = 0; w < 8; ++w) s += sred[(w * 8 + q) * 128 + col];
+      if (n0 + col < p.Nout) p.part_side[((size_t)split * nside + q) * p.Nout + n0 + col] = s;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 128);
+}
+
+}  // namespace msmp
+
+using namespace msmp;
+
+extern "C" int msmp_linear_wgrad_tc(const float* X, int ldx, int K, int xswish, const float* dY, int lddy, int Nout,
+                                    const float* side, int lds, int r, int has_bias, float* dWt, float* dWside,
+                                    int accumulate, int M, void* workspace, size_t ws_bytes, cudaStream_t stream) {
+  if (K <= 0 || (K & 3) || Nout <= 0 || (Nout & 3) || (ldx & 3) || (lddy & 3) || r < 0 || r + has_bias > 8)
+    return MSMP_ERR_ARG;
+  const int nside = (side ? r : 0) + (has_bias ? 1 : 0);
+  if (ws_bytes < msmp_linear_wgrad_workspace(M, K, Nout, nside)) return MSMP_ERR_WORKSPACE;
+  const int S = msmp_linear_wgrad_splits(M, K, Nout);
+  WgradTcParams p{};
+  p.X = X; p.ldx = ldx; p.K = K; p.xswish = xswish; p.dY = dY; p.lddy = lddy; p.Nout = Nout;
+  p.side = side; p.lds = lds; p.r = side ? r : 0; p.has_bias = has_bias ? 1 : 0;
+  p.part = reinterpret_cast<float*>(workspace);
+  p.part_side = p.part + (size_t)S * K * Nout;
+  p.M = M;
+  int rps = (M + S - 1) / S;
+  rps = ((rps + WT_CHUNK - 1) / WT_CHUNK) * WT_CHUNK;
+  if (rps < WT_CHUNK) rps = WT_CHUNK;
+  p.rows_per_split = rps;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM) != cudaSuccess)
+      return MSMP_ERR_CUDA;
+    attr_set = true;
+  }
+  dim3 grid(S, (K + 127) / 128, (Nout + 127) / 128);
+  k_wgrad_tc<<<grid, 256, WT_SMEM, stream>>>(p);
+  MSMP_CHECK_LAUNCH();
+  {
+    int count = K * Nout;
+    k_reduce_partials<<<(count + 255) / 256, 256, 0, stream>>>(p.part, dWt, count, S, (size_t)K * Nout, accumulate);
+    MSMP_CHECK_LAUNCH();
+  }
+  if (nside > 0) {
+    int count = nside * Nout;
+    k_reduce_partials<<<(count + 255) / 256, 256, 0, stream>>>(p.part_side, dWside, count, S, (size_t)nside * Nout,
+                                                              accumulate);
+    MSMP_CHECK_LAUNCH();
+  }
+  return MSMP_OK;
+}

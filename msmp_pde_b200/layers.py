@@ -79,6 +79,7 @@ class LayerPack:
         w3s[:V] = W3[:, 2 * H:].t()
         self.W3side = w3s
         self.W4t = W4.t().contiguous()
+        self.W4d = W4                                                  # [n][k]: dgrad operand (alias)
 
 
 class _Aux:
@@ -121,7 +122,7 @@ class _LayerCoreFn(torch.autograd.Function):
         dz4 = ops.mul_dswish(dy, z4) if aux.final else dy
         # update_net_2
         dW4t, dW4s = ops.linear_wgrad(z3, dz4, xswish=True, has_bias=True)
-        dz3 = ops.linear_fwd([dz4], W4, Zmul=z3)
+        dz3 = ops.linear_fwd([dz4], pk.W4d, Zmul=z3)
         # update_net_1
         dW3t = torch.empty(2 * H, H, dtype=torch.float32, device=dev)
         _, dW3s = ops.linear_wgrad(h, dz3, side=ft.side[:, 1:], r=V, has_bias=True, dWt=dW3t[:H])

@@ -27,19 +27,13 @@ class _LEMFn(torch.autograd.Function):
     """All T steps through msmp_linear_fwd (gate GEMMs) + msmp_lem_gate_* (fused gate math)."""
 
     @staticmethod
-    def forward(ctx, inputs, weights, weights_lin_z, bias, bias_lin_z, y0, z0, dt):
+    def forward(ctx, inputs, weights, weights_lin_z, bias, bias_lin_z, y0, z0, dt, packs):
         T, N, ninp = inputs.shape
         dev = inputs.device
         ip = pad32(ninp)
         inp = torch.zeros(T, N, ip, dtype=torch.float32, device=dev)
         inp[:, :, :ninp] = inputs
-        # k-major packs: rows [state(128) | input(ip)]
-        Wt = torch.zeros(H + ip, 3 * H, dtype=torch.float32, device=dev)
-        Wt[:H] = weights[:, :H].t()
-        Wt[H:H + ninp] = weights[:, H:].t()
-        Wzt = torch.zeros(H + ip, H, dtype=torch.float32, device=dev)
-        Wzt[:H] = weights_lin_z[:, :H].t()
-        Wzt[H:H + ninp] = weights_lin_z[:, H:].t()
+        Wt, Wzt, Wh, Wzh = packs          # k-major packs, rows [state(128) | input(ip)]; dgrad operands
         Y = torch.empty(T + 1, N, H, dtype=torch.float32, device=dev)
         Z = torch.empty(T + 1, N, H, dtype=torch.float32, device=dev)
         Y[0], Z[0] = y0, z0
@@ -51,19 +45,18 @@ class _LEMFn(torch.autograd.Function):
             ops.lem_gate_z(G, Z[t], dt, gates[t], Z[t + 1])
             ops.linear_fwd([Z[t + 1], inp[t]], Wzt, bias=bias_lin_z, out=L)
             ops.lem_gate_y(L, Y[t], gates[t], Y[t + 1])
-        ctx.save_for_backward(inp, Y, Z, gates, weights, weights_lin_z)
-        ctx.dt, ctx.ninp = dt, ninp
+        ctx.save_for_backward(inp, Y, Z, gates)
+        ctx.dt, ctx.ninp, ctx.packs = dt, ninp, packs
         return Y[1:], Z[1:]
 
     @staticmethod
     def backward(ctx, gY, gZ):
-        inp, Y, Z, gates, weights, weights_lin_z = ctx.saved_tensors
+        inp, Y, Z, gates = ctx.saved_tensors
         dt, ninp = ctx.dt, ctx.ninp
+        _, _, Wh, Wzh = ctx.packs
         T, N, ip = inp.shape
         dev = inp.device
         gY, gZ = gY.contiguous(), gZ.contiguous()
-        Wh = weights[:, :H].contiguous()            # [384][128]: dgrad operand  (dG -> dy_prev)
-        Wzh = weights_lin_z[:, :H].contiguous()     # [128][128]: dgrad operand  (dL -> dz_t)
         dG = torch.empty(T, N, 3 * H, dtype=torch.float32, device=dev)
         dL = torch.empty(T, N, H, dtype=torch.float32, device=dev)
         dy = torch.zeros(N, H, dtype=torch.float32, device=dev)      # carried d/dy_t
@@ -90,7 +83,7 @@ class _LEMFn(torch.autograd.Function):
         ops.linear_wgrad(inpf, dLf, dWt=dWzt[H:])
         dW = torch.cat([dWt[:H].t(), dWt[H:H + ninp].t()], 1)
         dWz = torch.cat([dWzt[:H].t(), dWzt[H:H + ninp].t()], 1)
-        return None, dW, dWz, dbias[0], dbz[0], dy, dz, None
+        return None, dW, dWz, dbias[0], dbz[0], dy, dz, None, None
 
 
 class LEMcuda(nn.Module):
@@ -107,7 +100,25 @@ class LEMcuda(nn.Module):
         self.bias = nn.Parameter(torch.empty(3 * nhid, **f32))
         self.bias_lin_z = nn.Parameter(torch.empty(nhid, **f32))
         self.dt = float(dt)
+        self._packs, self._pack_key = None, None
         self.reset_parameters()
+
+    def packs(self):
+        """Kernel-side weight layouts, rebuilt only when a parameter changed (once per optimizer step)."""
+        key = tuple((p.data_ptr(), p._version) for p in (self.weights, self.weights_lin_z))
+        if self._packs is None or key != self._pack_key:
+            with torch.no_grad():
+                W, Wz = self.weights.detach(), self.weights_lin_z.detach()
+                ninp, ip = self.ninp, pad32(self.ninp)
+                Wt = W.new_zeros(H + ip, 3 * H)
+                Wt[:H] = W[:, :H].t()
+                Wt[H:H + ninp] = W[:, H:].t()
+                Wzt = W.new_zeros(H + ip, H)
+                Wzt[:H] = Wz[:, :H].t()
+                Wzt[H:H + ninp] = Wz[:, H:].t()
+                self._packs = (Wt, Wzt, W[:, :H].contiguous(), Wz[:, :H].contiguous())
+            self._pack_key = key
+        return self._packs
 
     def reset_parameters(self):
         stdv = 1.0 / math.sqrt(self.nhid)
@@ -123,7 +134,8 @@ class LEMcuda(nn.Module):
             z = x.new_zeros(x.size(1), self.nhid)
         else:
             y, z = states[0].float().contiguous(), states[1].float().contiguous()
-        return _LEMFn.apply(x, self.weights, self.weights_lin_z, self.bias, self.bias_lin_z, y, z, self.dt)
+        return _LEMFn.apply(x, self.weights, self.weights_lin_z, self.bias, self.bias_lin_z, y, z, self.dt,
+                            self.packs())
 
 
 class LEM(nn.Module):

@@ -75,9 +75,34 @@ def _p(t):
     return 0 if t is None else t.data_ptr()
 
 
+# Tensor-core (tcgen05 3xTF32) execution of the dense layers.  "ffma" keeps the exact-fp32 CUDA-core kernels.
+GEMM_MODE = "tc"
+_IMG_CACHE: dict = {}
+
+
+def _cached_images(Wt: torch.Tensor) -> torch.Tensor:
+    """tc_images(Wt), cached on the identity + version of the weight tensor (weights change once per step)."""
+    key = id(Wt)
+    ent = _IMG_CACHE.get(key)
+    if ent is not None:
+        ref, ver, ptr, img = ent
+        if ref() is Wt and ver == Wt._version and ptr == Wt.data_ptr():
+            return img
+    img = tc_images(Wt if Wt.is_contiguous() else Wt.contiguous())
+    import weakref
+
+    def _drop(_, key=key):
+        _IMG_CACHE.pop(key, None)
+    _IMG_CACHE[key] = (weakref.ref(Wt, _drop), Wt._version, Wt.data_ptr(), img)
+    return img
+
+
 def linear_fwd(segs, Wt, bias=None, side=None, r=0, Wside=None, Zmul=None, Ypre=None, act=False, R=None,
                out=None, Nout=None, aswish=None):
     """Y = epi([A0|A1|A2] @ Wt + bias + side[:, :r] @ Wside); see include/msmp_b200.h."""
+    if GEMM_MODE == "tc":
+        return linear_tc_fwd(segs, _cached_images(Wt), Wt.shape[1] if Nout is None else Nout, bias=bias, side=side,
+                             r=r, Wside=Wside, Zmul=Zmul, Ypre=Ypre, act=act, R=R, out=out, aswish=aswish)
     n = len(segs)
     M = segs[0].shape[0]
     Nout = Wt.shape[1] if Nout is None else Nout
@@ -169,7 +194,8 @@ def linear_wgrad(X, dY, K=None, xswish=False, side=None, r=0, has_bias=False, dW
         dWside = torch.empty(nside, Nout, dtype=torch.float32, device=dev)
     nbytes = lib.msmp_linear_wgrad_workspace(M, K, Nout, nside)
     ws = _workspace(nbytes, dev)
-    check(lib.msmp_linear_wgrad(X.data_ptr(), _ld(X), K, int(xswish), dY.data_ptr(), _ld(dY), Nout, _p(side),
+    fn = lib.msmp_linear_wgrad_tc if GEMM_MODE == "tc" else lib.msmp_linear_wgrad
+    check(fn(X.data_ptr(), _ld(X), K, int(xswish), dY.data_ptr(), _ld(dY), Nout, _p(side),
                                 _ld(side) if side is not None else 0, r if side is not None else 0, int(has_bias),
                                 dWt.data_ptr(), _p(dWside), int(accumulate), M, ws.data_ptr(), ws.numel(), _stream()),
           "msmp_linear_wgrad")

@@ -27,21 +27,19 @@ class _LinearActFn(torch.autograd.Function):
     """y = act(x W^T + b) on msmp_linear_fwd / msmp_linear_wgrad.  x is [M, Kp] with Kp % 32 == 0 (zero padded)."""
 
     @staticmethod
-    def forward(ctx, x, W, b, act: bool):
+    def forward(ctx, x, W, b, act: bool, packs):
         Nout, K = W.shape
-        Kp = x.shape[1]
         x = x.contiguous()
-        Wt = torch.zeros(Kp, Nout, dtype=torch.float32, device=x.device)
-        Wt[:K] = W.t()
+        Wt, Wd = packs
         z = torch.empty(x.shape[0], Nout, dtype=torch.float32, device=x.device) if act else None
         y = ops.linear_fwd([x], Wt, bias=b, Ypre=z, act=act)
-        ctx.act, ctx.K = act, K
-        ctx.save_for_backward(x, z, W)
+        ctx.act, ctx.K, ctx.Wd = act, K, Wd
+        ctx.save_for_backward(x, z)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, z, W = ctx.saved_tensors
+        x, z = ctx.saved_tensors
         dy = dy.contiguous()
         dz = ops.mul_dswish(dy, z) if ctx.act else dy
         dWt, dbs = ops.linear_wgrad(x, dz, has_bias=True)
@@ -49,12 +47,27 @@ class _LinearActFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             if ctx.K != x.shape[1]:
                 raise RuntimeError("input gradient of a zero-padded linear layer is not needed on this path")
-            dx = ops.linear_fwd([dz], W)            # W [Nout][K] is the reduction-major dgrad operand
-        return dx, dWt[:ctx.K].t(), dbs[0], None
+            dx = ops.linear_fwd([dz], ctx.Wd)       # W [Nout][K] is the reduction-major dgrad operand
+        return dx, dWt[:ctx.K].t(), dbs[0], None, None
+
+
+def _linear_packs(linear: nn.Linear, Kp: int):
+    """(k-major zero-padded W^T [Kp, Nout], detached W [Nout, K]) cached on the module per parameter version."""
+    W = linear.weight
+    key = (W.data_ptr(), W._version, Kp)
+    cache = linear.__dict__.get("_msmp_packs")
+    if cache is None or cache[0] != key:
+        with torch.no_grad():
+            Wd = W.detach()
+            Wt = Wd.new_zeros(Kp, Wd.shape[0])
+            Wt[:Wd.shape[1]] = Wd.t()
+            cache = (key, (Wt, Wd.clone()))
+        linear.__dict__["_msmp_packs"] = cache
+    return cache[1]
 
 
 def linear_act(x, linear: nn.Linear, act: bool = True):
-    return _LinearActFn.apply(x, linear.weight, linear.bias, act)
+    return _LinearActFn.apply(x, linear.weight, linear.bias, act, _linear_packs(linear, x.shape[1]))
 
 
 def pad_cols(x: torch.Tensor) -> torch.Tensor:

@@ -42,7 +42,7 @@ def test_abi_loaded():
 
 
 @pytest.mark.parametrize("M", [1, 300, 1024])
-def test_linear_fwd(dev, M):
+def test_linear_fwd(dev, gemm_mode, M):
     from msmp_pde_b200 import ops
     g = torch.Generator().manual_seed(M)
     A0 = torch.randn(M, 128, generator=g)
@@ -108,8 +108,17 @@ def test_linear_fwd_plain_and_strided(dev):
     assert rel_err(y, ref) < TOL
 
 
-@pytest.mark.parametrize("M,K,Nout", [(1000, 192, 256), (130, 128, 128), (5000, 160, 384)])
-def test_linear_wgrad(dev, M, K, Nout):
+@pytest.fixture(params=["tc", "ffma"])
+def gemm_mode(request):
+    from msmp_pde_b200 import ops
+    prev = ops.GEMM_MODE
+    ops.GEMM_MODE = request.param
+    yield request.param
+    ops.GEMM_MODE = prev
+
+
+@pytest.mark.parametrize("M,K,Nout", [(1000, 192, 256), (130, 128, 128), (5000, 160, 384), (40, 64, 128)])
+def test_linear_wgrad(dev, gemm_mode, M, K, Nout):
     from msmp_pde_b200 import ops
     g = torch.Generator().manual_seed(K)
     X = torch.randn(M, K, generator=g)
