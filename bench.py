@@ -95,6 +95,13 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    def say(msg):
+        if args.verbose:
+            print(f"[bench rank {rank}] {msg}", file=sys.stderr, flush=True)
+    if world > 1:
+        # CUDA-graph capture of NCCL collectives: the watchdog thread must not touch the capturing context
+        os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -110,7 +117,9 @@ def run_ours(args):
     h2d = sum(t.numel() * t.element_size() for t in (getattr(pinned, k) for k in pinned.keys())
               if torch.is_tensor(t) and t.is_floating_point())
     # public API: the whole training step (fwd + loss + bwd + DP all-reduce + AdamW) as one CUDA graph
+    say("model built")
     step = GraphedTrainStep(model, opt, resident, warmup=max(3, args.warmup), use_graph=not args.eager)
+    say("step captured")
 
     def timed(K, graph, read_loss):
         evs = []
@@ -144,6 +153,7 @@ def run_ours(args):
     launches_per_step = ops.LAUNCHES // 3
     kern = {k: [s.elapsed_time(e) for s, e in v] for k, v in ops.PROFILE_EVENTS.items()}
     ops.PROFILE_EVENTS = None
+    say("eager profiling pass done")
     # ---- device-resident timing (value)
     sampler = ClockSampler(local)
     sampler.start()
@@ -157,6 +167,7 @@ def run_ours(args):
     e2e_times = timed(args.steps, pinned, True)
     barrier()
     clocks = sampler.stop()
+    say("timing done")
     launches = launches_per_step * args.steps
 
     ms = sum(times) / len(times)
@@ -269,6 +280,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--verbose", action="store_true")
     ap.add_argument("--eager", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -46,14 +46,14 @@ def global_rmse_loss(pred, y, group=None):
 
 
 class FlatGradBucket:
-    """One contiguous fp32 buffer holding every parameter gradient (``p.grad`` are views into it), so the
+    """One contiguous buffer (the parameters' dtype; fp32 for the msmp modules) holding every parameter gradient (``p.grad`` are views into it), so the
     data-parallel reduction is a single NCCL all-reduce on a fixed address."""
 
     def __init__(self, params):
         self.params = [p for p in params if p.requires_grad]
         n = sum(p.numel() for p in self.params)
         dev = self.params[0].device
-        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.flat = torch.zeros(n, dtype=self.params[0].dtype, device=dev)
         off = 0
         for p in self.params:
             p.grad = self.flat[off:off + p.numel()].view_as(p)
@@ -67,13 +67,17 @@ class FlatGradBucket:
 
 
 class GraphedTrainStep:
-    """Captures ``model(graph) -> loss -> backward -> (all-reduce) -> optimizer.step()`` into a CUDA graph.
+    """Captures ``model(graph) -> loss -> backward -> (all-reduce) -> optimizer.step()`` into CUDA graphs.
 
     >>> step = GraphedTrainStep(model, optimizer, example_graph_on_device)
-    >>> loss = step(host_or_device_graph)        # copies the tensor fields into the static graph and replays
+    >>> loss = step(host_or_device_graph)        # copies the float fields into the static graph and replays
 
-    ``optimizer`` must be capturable (e.g. ``torch.optim.AdamW(..., capturable=True)`` or ``fused=True`` with
-    ``capturable=True``).  The topology of later graphs must equal the example's (checked by shape)."""
+    Single GPU: ONE graph for the whole step.  Data parallel (world > 1): three graphs -- forward (+ local
+    squared error), backward (seeded with 1 / (2 sqrt(global SSE))), optimizer -- with the two NCCL all-reduces
+    (one scalar, one flat gradient bucket) launched eagerly between them on the same stream.
+
+    ``optimizer`` must be capturable (``torch.optim.AdamW(..., capturable=True)``).  The topology of later
+    graphs must equal the example's (only floating-point fields are refreshed)."""
 
     def __init__(self, model, optimizer, example, group=None, warmup: int = 3, use_graph: bool = True):
         self.model, self.opt, self.group = model, optimizer, group
@@ -85,7 +89,11 @@ class GraphedTrainStep:
         self.bucket = FlatGradBucket(model.parameters())
         self.use_graph = use_graph
         self.graph = None
+        self.graphs = None
         self.loss = None
+        dev = self.bucket.flat.device
+        self._sse_total = torch.zeros((), dtype=torch.float64, device=dev)
+        self._seed = torch.zeros((), dtype=torch.float64, device=dev)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -93,24 +101,52 @@ class GraphedTrainStep:
                 self._eager_step()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        if use_graph:
+        if not use_graph:
+            return
+        if self.world == 1:
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph):
                 self._eager_step()
-            torch.cuda.synchronize()
+        else:
+            g_fwd, g_bwd, g_opt = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_fwd):
+                self._fwd()
+            self._reduce_loss()
+            with torch.cuda.graph(g_bwd, pool=g_fwd.pool()):
+                self._bwd()
+            self.bucket.all_reduce(self.group)
+            with torch.cuda.graph(g_opt, pool=g_fwd.pool()):
+                self.opt.step()
+            self.graphs = (g_fwd, g_bwd, g_opt)
+        torch.cuda.synchronize()
 
-    def _eager_step(self):
+    # ---- pieces of one step -------------------------------------------------------------------------
+    def _fwd(self):
         self.bucket.zero_()
         pred = self.model(self.static)
-        loss = global_rmse_loss(pred, self.static.y, self.group if self.world > 1 else None)
-        loss.backward()
+        self._sse_local = ((pred - self.static.y) ** 2).sum()          # train_helper.py:126 (reduction='sum')
+
+    def _reduce_loss(self):
+        """global SSE (all ranks) -> loss and the backward seed d loss / d sse_local = 1 / (2 loss)."""
+        self._sse_total.copy_(self._sse_local.detach())
+        if self.world > 1:
+            dist.all_reduce(self._sse_total, group=self.group)
+        self.loss = torch.sqrt(self._sse_total)
+        self._seed.copy_(0.5 / self.loss)
+
+    def _bwd(self):
+        self._sse_local.backward(self._seed.to(self._sse_local.dtype))
+
+    def _eager_step(self):
+        self._fwd()
+        self._reduce_loss()
+        self._bwd()
         if self.world > 1:
             self.bucket.all_reduce(self.group)
         self.opt.step()
-        self.loss = loss.detach()
 
     def load(self, graph):
-        """Copy the tensor fields of ``graph`` (host or device) into the static device buffers."""
+        """Copy the floating-point fields of ``graph`` (host or device) into the static device buffers."""
         for k in self.fields:
             src = getattr(graph, k)
             dst = getattr(self.static, k)
@@ -125,6 +161,12 @@ class GraphedTrainStep:
             self.load(graph)
         if self.graph is not None:
             self.graph.replay()
+        elif self.graphs is not None:
+            self.graphs[0].replay()
+            self._reduce_loss()
+            self.graphs[1].replay()
+            self.bucket.all_reduce(self.group)
+            self.graphs[2].replay()
         else:
             self._eager_step()
         return self.loss
