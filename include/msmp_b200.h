@@ -89,6 +89,17 @@ int msmp_edge_bwd(const float* P, const float* Q, int ldpq, const int* src, cons
                   float* dz1, float* dP, int lddp, float* dW2, float* db2, int E, int N, void* workspace,
                   size_t ws_bytes, cudaStream_t stream);
 
+/* Tensor-core variants (tcgen05 3xTF32).  W2t_img / W2_img = tile images (msmp_linear_tc_fwd format, K = N = 128)
+ * of the k-major W2^T (forward) and of W2 itself (backward).  The backward materialises dz2 and a1 [E,128];
+ * dW2^T / db2 = msmp_linear_wgrad_tc(X = a1, dY = dz2, has_bias).  Workspace: msmp_edge_fwd_workspace(E). */
+int msmp_edge_tc_fwd(const float* P, const float* Q, int ldpq, const int* src, const int* dst, const int* rowptr,
+                     const float* inv_deg, const float* W2t_img, const float* b2, float* z2, float* agg, int E,
+                     int N, void* workspace, size_t ws_bytes, cudaStream_t stream);
+int msmp_edge_tc_bwd(const float* P, const float* Q, int ldpq, const int* src, const int* dst, const int* rowptr,
+                     const float* inv_deg, const float* W2_img, const float* z2, const float* dagg, int lddagg,
+                     float* dz2, float* a1, float* dz1, float* dP, int lddp, int E, int N, void* workspace,
+                     size_t ws_bytes, cudaStream_t stream);
+
 /* out[n, 0:128] = scale[n] * sum_{k in [ptr[n], ptr[n+1])} src[perm ? perm[k] : k, 0:128]
  * (scale == NULL -> sum; scale = 1/max(count,1) -> mean).  One warp per segment, fixed order, no atomics. */
 int msmp_segment_reduce(const float* src, int lds, const int* perm, const int* ptr, const float* scale,
@@ -138,6 +149,18 @@ int msmp_decoder_fwd(const float* h, const float* w1, const float* b1, const flo
 int msmp_decoder_bwd(const float* dout, const float* h, const float* za, const float* w1, const float* w2,
                      const float* dt, float* dh, float* dW, int N, int C, int K1, int S1, int L1, int K2, int TW,
                      void* workspace, size_t ws_bytes, cudaStream_t stream);
+
+/* Persistent tensor-core LEM: ALL T steps in one launch, one CTA per 128 nodes (the recurrence is per node).
+ * inp [T][N][32] zero-padded inputs; Wimg / Wzimg = tile images (msmp_linear_tc_fwd format) of the k-major
+ * W^T [160 x 384] and Wz^T [160 x 128] (rows: 128 state + 32 input); Y, Z [T+1][N][128] with Y[0], Z[0] the initial
+ * state; gates [T][4][N][128].  Backward: Wzh_img / Wh_img = images of Wz[:, :128] ([128 x 128]) and W[:, :128]
+ * ([384 x 128]) read as k-major; dy / dz [N][128] zero on entry, gradient wrt the initial state on exit;
+ * dG [T][N][384], dL [T][N][128] feed the weight-gradient GEMMs. */
+int msmp_lem_tc_fwd(const float* inp, const float* Wimg, const float* Wzimg, const float* bias, const float* bias_z,
+                    float* Y, float* Z, float* gates, float dt, int T, int N, cudaStream_t stream);
+int msmp_lem_tc_bwd(const float* Wzh_img, const float* Wh_img, const float* Y, const float* Z, const float* gates,
+                    const float* gY, const float* gZ, float* dG, float* dL, float* dy, float* dz, float dt, int T,
+                    int N, cudaStream_t stream);
 
 /* out[i] = g[i] * swish'(z[i])  (n % 4 == 0) */
 int msmp_mul_dswish(const float* g, const float* z, float* out, size_t n, cudaStream_t stream);

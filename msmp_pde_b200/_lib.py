@@ -48,6 +48,8 @@ _SIGS = {
     "msmp_edge_fwd": (I, [P, P, I, P, P, P, P, P, P, P, P, I, I, P, S, P]),
     "msmp_edge_bwd_workspace": (S, [I]),
     "msmp_edge_bwd": (I, [P, P, I, P, P, P, P, P, P, P, I, P, P, I, P, P, I, I, P, S, P]),
+    "msmp_edge_tc_fwd": (I, [P, P, I, P, P, P, P, P, P, P, P, I, I, P, S, P]),
+    "msmp_edge_tc_bwd": (I, [P, P, I, P, P, P, P, P, P, P, I, P, P, P, P, I, I, I, P, S, P]),
     "msmp_segment_reduce": (I, [P, I, P, P, P, P, I, I, P]),
     "msmp_instnorm_workspace": (S, [I, I]),
     "msmp_instnorm_fwd": (I, [P, P, I, P, P, P, P, P, I, I, I, I, F, P, P, P, S, P]),
@@ -57,6 +59,8 @@ _SIGS = {
     "msmp_decoder_bwd_workspace": (S, [I, I, I, I]),
     "msmp_decoder_fwd": (I, [P, P, P, P, P, P, I, P, P, P, I, I, I, I, I, I, I, P]),
     "msmp_decoder_bwd": (I, [P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, P, S, P]),
+    "msmp_lem_tc_fwd": (I, [P, P, P, P, P, P, P, P, F, I, I, P]),
+    "msmp_lem_tc_bwd": (I, [P, P, P, P, P, P, P, P, P, P, P, F, I, I, P]),
     "msmp_lem_gate_z": (I, [P, P, F, P, P, I, P]),
     "msmp_lem_gate_y": (I, [P, P, P, P, I, P]),
     "msmp_lem_bwd_y": (I, [P, P, P, P, F, P, P, I, P]),

@@ -118,4 +118,24 @@ static __global__ void k_reduce_partials(const float* __restrict__ part, float* 
   out[i] = accumulate ? out[i] + s : s;
 }
 
+// Two partial sets in one launch (main weight tile + side/bias rows of a weight-gradient call).
+static __global__ void k_reduce_partials2(const float* __restrict__ part0, float* __restrict__ out0, int count0,
+                                          size_t stride0, const float* __restrict__ part1, float* __restrict__ out1,
+                                          int count1, size_t stride1, int S, int accumulate) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const float* part;
+  float* out;
+  size_t stride;
+  if (i < count0) {
+    part = part0; out = out0; stride = stride0;
+  } else {
+    i -= count0;
+    if (i >= count1) return;
+    part = part1; out = out1; stride = stride1;
+  }
+  float s = 0.f;
+  for (int q = 0; q < S; ++q) s += part[(size_t)q * stride + i];
+  out[i] = accumulate ? out[i] + s : s;
+}
+
 }  // namespace msmp

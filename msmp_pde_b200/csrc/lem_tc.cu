@@ -1,0 +1,447 @@
+// Persistent LEM recurrence on the tensor cores (replaces lem_cuda.forward / lem_cuda.backward,
+// experiments/models_gnn.py:290-292,300).  The recurrence is independent per node, so one CTA owns 128 nodes and
+// walks all T time steps inside ONE launch: no inter-CTA synchronisation, the state tiles never leave the SM.
+//
+// forward, per step t:
+//   G[128 x 384] = [y_{t-1} | I_t] W^T          15 weight chunks (3 n-tiles x 5 k-chunks), TMEM columns 0..383
+//   gate_z      : a = dt sig(G0 + b), b = dt sig(G1 + b), zc = tanh(G2 + b), z_t = (1-b) z_{t-1} + b zc
+//   L[128 x 128] = [z_t | I_t] Wz^T             5 weight chunks, TMEM columns 384..511
+//   gate_y      : tL = tanh(L + bz), y_t = (1-a) y_{t-1} + a tL
+// The state operand (y, then z, then y again) lives in shared memory as a tf32 hi/lo tile image written by the
+// gate epilogues; the weights (pre-split, pre-swizzled images, 640 KiB per step) are streamed from L2 through a
+// 2-stage ring of 32 KiB bulk copies; one thread issues copies and MMAs, all threads run the epilogues.
+//
+// backward, per step t = T-1..0 (dy, dz carried in global scratch, owned row-wise by the same thread):
+//   bwd_y : d = dy + gY[t]; dL = d a (1-tL^2); dG0 = d (tL - y_{t-1}) a (1 - a/dt); dy = d (1-a)
+//   acc1  = dL Wz[:, :128]                        4 chunks
+//   bwd_z : d = dz + gZ[t] + acc1; dG1 = d (zc - z_{t-1}) b (1 - b/dt); dG2 = d b (1-zc^2); dz = d (1-b)
+//   acc2  = [dG0 | dG1 | dG2] W[:, :128]          3 x 4 chunks (the A tile is restaged per 128-column block)
+//   dy   += acc2
+// dG [T,N,384] and dL [T,N,128] are written for the four weight-gradient GEMMs (msmp_linear_wgrad_tc).
+#include "umma.cuh"
+#include "msmp_b200.h"
+
+namespace msmp {
+
+constexpr int LT_A_BYTES = 4 * 2 * IMG_BYTES;      // state tile: 4 k-chunks x (hi | lo) = 128 KiB
+constexpr int LT_I_BYTES = 2 * IMG_BYTES;          // input chunk image (hi | lo) = 32 KiB
+constexpr int LT_B_BYTES = 2 * IMG_BYTES;          // one weight chunk (hi | lo) = 32 KiB
+constexpr int LT_SMEM_FWD = LT_A_BYTES + LT_I_BYTES + 2 * LT_B_BYTES + 1024 + 256;
+constexpr int LT_SMEM_BWD = LT_A_BYTES + 2 * LT_B_BYTES + 1024 + 256;
+
+// Weight streaming + MMA issue, executed by ONE thread.  `nb` chunks: chunk i uses A image chunk a_of(i),
+// weight image #w_of(i), TMEM column offset d_of(i), accumulate flag acc_of(i).
+struct Ring {
+  uint8_t* smB;        // 2 stages
+  uint64_t* bfull;     // [2]
+  uint64_t* bfree;     // [2]
+  uint32_t n;          // running chunk counter (parity bookkeeping across the whole kernel)
+};
+
+__device__ __forceinline__ void ring_issue_copy(Ring& rg, uint32_t i, const float* src) {
+  const uint32_t s = i & 1;
+  if (i >= 2) mbar_wait(&rg.bfree[s], ((i >> 1) - 1) & 1);        // MMAs that read this stage are complete
+  mbar_expect_tx(&rg.bfull[s], LT_B_BYTES);
+  bulk_g2s(rg.smB + s * LT_B_BYTES, src, LT_B_BYTES, &rg.bfull[s]);
+}
+
+__device__ __forceinline__ void ring_mma(Ring& rg, uint32_t i, uint32_t a_img /* smem addr of (hi|lo) A chunk */,
+                                         uint32_t tmem_d, bool accumulate) {
+  const uint32_t s = i & 1;
+  mbar_wait(&rg.bfull[s], (i >> 1) & 1);
+  tc_fence_after();
+  constexpr uint32_t IDESC = umma_idesc_tf32(128, 128, 0, 0);
+  const uint32_t a_hi = a_img, a_lo = a_img + IMG_BYTES;
+  const uint32_t b_hi = smem_u32(rg.smB + s * LT_B_BYTES), b_lo = b_hi + IMG_BYTES;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const uint64_t dah = umma_desc(a_hi + 32 * k, 16, 1024), dal = umma_desc(a_lo + 32 * k, 16, 1024);
+    const uint64_t dbh = umma_desc(b_hi + 32 * k, 16, 1024), dbl = umma_desc(b_lo + 32 * k, 16, 1024);
+    umma_tf32(tmem_d, dah, dbh, IDESC, (accumulate || k) ? 1u : 0u);
+    umma_tf32(tmem_d, dal, dbh, IDESC, 1u);
+    umma_tf32(tmem_d, dah, dbl, IDESC, 1u);
+  }
+  umma_commit(&rg.bfree[s]);
+}
+
+// write 4 consecutive values of row r, columns col..col+3 (col % 4 == 0, col < 128) into the state tile image
+__device__ __forceinline__ void state_store4(uint8_t* smA, int r, int col, float4 v) {
+  uint8_t* chunk = smA + (col >> 5) * (2 * IMG_BYTES);
+  store_split4(chunk, chunk + IMG_BYTES, img_off(r, (col & 31) >> 2), v);
+}
+
+struct LemFwdParams {
+  const float* inp;      // [T][N][32]   zero-padded inputs
+  const float* Wimg;     // images of Wt  [160 x 384]: [3 ntiles][5 chunks][2][4096]
+  const float* Wzimg;    // images of Wzt [160 x 128]: [1][5][2][4096]
+  const float* bias;     // [384]
+  const float* bias_z;   // [128]
+  float* Y;              // [T+1][N][128]  (Y[0] = y0 on entry)
+  float* Z;              // [T+1][N][128]  (Z[0] = z0 on entry)
+  float* gates;          // [T][4][N][128]  a, b, zc, tL
+  float dt;
+  int T; int N;
+};
+
+__global__ void __launch_bounds__(256, 1) k_lem_fwd_tc(const LemFwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smA = smem;
+  uint8_t* smI = smem + LT_A_BYTES;
+  uint8_t* smB = smI + LT_I_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smB + 2 * LT_B_BYTES);    // bfull[2], bfree[2], accG, accL
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row0 = blockIdx.x * 128;
+  const size_t plane = (size_t)p.N * 128;
+
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  if (tid == 32) {
+    for (int i = 0; i < 6; ++i) mbar_init(&bars[i], 1);
+    fence_barrier_init();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  Ring rg{smB, &bars[0], &bars[2], 0};
+  uint64_t* accG = &bars[4];
+  uint64_t* accL = &bars[5];
+
+  // epilogue ownership: thread = row r, 64 channels [c0, c0+64)
+  const int r = 32 * (warp & 3) + lane;
+  const int grow = row0 + r;
+  const bool live = grow < p.N;
+  const int c0 = 64 * (warp >> 2);
+  const uint32_t tlane = (uint32_t)(32 * (warp & 3)) << 16;
+
+  // y_{-1} tile from Y[0]
+  for (int i = 0; i < 16; ++i) {
+    const int idx = tid + 256 * i;
+    const int rr = idx >> 5, c4 = idx & 31;
+    const int g = row0 + rr;
+    float4 v = (g < p.N) ? ldg4(p.Y + (size_t)g * 128 + 4 * c4) : zero4();
+    state_store4(smA, rr, 4 * c4, v);
+  }
+
+  for (int t = 0; t < p.T; ++t) {
+    // ---- input chunk image for this step
+    {
+      const float* it = p.inp + (size_t)t * p.N * 32;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int idx = tid + 256 * i;
+        const int rr = idx >> 3, c16 = idx & 7;
+        const int g = row0 + rr;
+        float4 v = (g < p.N) ? ldg4(it + (size_t)g * 32 + 4 * c16) : zero4();
+        store_split4(smI, smI + IMG_BYTES, img_off(rr, c16), v);
+      }
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    // ---- G = [y | I] W^T : 3 n-tiles x 5 chunks
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t base = rg.n;
+      auto src_of = [&](uint32_t j) { return p.Wimg + (size_t)j * (LT_B_BYTES / 4); };   // j = ntile*5 + chunk
+      ring_issue_copy(rg, base + 0, src_of(0));
+      ring_issue_copy(rg, base + 1, src_of(1));
+      for (uint32_t j = 0; j < 15; ++j) {
+        const uint32_t nt = j / 5, c = j % 5;
+        const uint32_t a_img = (c < 4) ? smem_u32(smA + c * 2 * IMG_BYTES) : smem_u32(smI);
+        ring_mma(rg, base + j, a_img, tmem + nt * 128, c != 0);
+        if (j + 2 < 15) ring_issue_copy(rg, base + j + 2, src_of(j + 2));
+      }
+      rg.n = base + 15;
+      umma_commit(accG);
+    }
+    mbar_wait(accG, t & 1);
+    tc_fence_after();
+    // ---- gate_z: thread (row r, channels c0..c0+63)
+    float* g_t = p.gates + (size_t)t * 4 * plane;
+#pragma unroll 1
+    for (int cb = 0; cb < 2; ++cb) {
+      const int cc = c0 + 32 * cb;
+      float v0[32], v1[32], v2[32];
+      __syncwarp();
+      tmem_ld32(tmem + tlane + (uint32_t)cc, v0);
+      tmem_ld32(tmem + tlane + (uint32_t)(128 + cc), v1);
+      tmem_ld32(tmem + tlane + (uint32_t)(256 + cc), v2);
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const int col = cc + j;
+        float4 zn = zero4();
+        if (live) {
+          const float4 b0 = ldg4(p.bias + col), b1 = ldg4(p.bias + 128 + col), b2 = ldg4(p.bias + 256 + col);
+          const float4 zp = ldcg4(p.Z + (size_t)t * plane + (size_t)grow * 128 + col);
+          float4 a, b, zc;
+          a.x = p.dt * sigmoidf_(v0[j] + b0.x); a.y = p.dt * sigmoidf_(v0[j + 1] + b0.y);
+          a.z = p.dt * sigmoidf_(v0[j + 2] + b0.z); a.w = p.dt * sigmoidf_(v0[j + 3] + b0.w);
+          b.x = p.dt * sigmoidf_(v1[j] + b1.x); b.y = p.dt * sigmoidf_(v1[j + 1] + b1.y);
+          b.z = p.dt * sigmoidf_(v1[j + 2] + b1.z); b.w = p.dt * sigmoidf_(v1[j + 3] + b1.w);
+          zc.x = tanhf(v2[j] + b2.x); zc.y = tanhf(v2[j + 1] + b2.y);
+          zc.z = tanhf(v2[j + 2] + b2.z); zc.w = tanhf(v2[j + 3] + b2.w);
+          zn = make_float4((1.f - b.x) * zp.x + b.x * zc.x, (1.f - b.y) * zp.y + b.y * zc.y,
+                           (1.f - b.z) * zp.z + b.z * zc.z, (1.f - b.w) * zp.w + b.w * zc.w);
+          const size_t o = (size_t)grow * 128 + col;
+          st4(g_t + o, a);
+          st4(g_t + plane + o, b);
+          st4(g_t + 2 * plane + o, zc);
+          st4(p.Z + (size_t)(t + 1) * plane + o, zn);
+        }
+        state_store4(smA, r, col, zn);          // z_t becomes the A operand of the L GEMM
+      }
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    // ---- L = [z | I] Wz^T : 5 chunks
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t base = rg.n;
+      auto src_of = [&](uint32_t j) { return p.Wzimg + (size_t)j * (LT_B_BYTES / 4); };
+      ring_issue_copy(rg, base + 0, src_of(0));
+      ring_issue_copy(rg, base + 1, src_of(1));
+      for (uint32_t j = 0; j < 5; ++j) {
+        const uint32_t a_img = (j < 4) ? smem_u32(smA + j * 2 * IMG_BYTES) : smem_u32(smI);
+        ring_mma(rg, base + j, a_img, tmem + 384, j != 0);
+        if (j + 2 < 5) ring_issue_copy(rg, base + j + 2, src_of(j + 2));
+      }
+      rg.n = base + 5;
+      umma_commit(accL);
+    }
+    mbar_wait(accL, t & 1);
+    tc_fence_after();
+    // ---- gate_y
+#pragma unroll 1
+    for (int cb = 0; cb < 2; ++cb) {
+      const int cc = c0 + 32 * cb;
+      float v[32];
+      __syncwarp();
+      tmem_ld32(tmem + tlane + (uint32_t)(384 + cc), v);
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const int col = cc + j;
+        float4 yn = zero4();
+        if (live) {
+          const size_t o = (size_t)grow * 128 + col;
+          const float4 bz = ldg4(p.bias_z + col);
+          const float4 a = ldcg4(g_t + o);
+          const float4 yp = ldcg4(p.Y + (size_t)t * plane + o);
+          float4 tl = make_float4(tanhf(v[j] + bz.x), tanhf(v[j + 1] + bz.y), tanhf(v[j + 2] + bz.z), tanhf(v[j + 3] + bz.w));
+          yn = make_float4((1.f - a.x) * yp.x + a.x * tl.x, (1.f - a.y) * yp.y + a.y * tl.y,
+                           (1.f - a.z) * yp.z + a.z * tl.z, (1.f - a.w) * yp.w + a.w * tl.w);
+          st4(g_t + 3 * plane + o, tl);
+          st4(p.Y + (size_t)(t + 1) * plane + o, yn);
+        }
+        state_store4(smA, r, col, yn);          // y_t is the A operand of the next step's G GEMM
+      }
+    }
+    // the loop head fences + syncs before the next MMAs read the state tile / overwrite TMEM
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------------------ backward
+struct LemBwdParams {
+  const float* Wzh_img;  // images of Wt := Wz[:, :128]  ([K = n][N = k]) : [1][4][2][4096]
+  const float* Wh_img;   // images of Wt := W[:, :128]   ([K = 384][N = 128]) : [1][12][2][4096]
+  const float* Y;        // [T+1][N][128]
+  const float* Z;        // [T+1][N][128]
+  const float* gates;    // [T][4][N][128]
+  const float* gY;       // [T][N][128] external gradients (nullable)
+  const float* gZ;       // [T][N][128] (nullable)
+  float* dG;             // [T][N][384]
+  float* dL;             // [T][N][128]
+  float* dy;             // [N][128] carried gradient (zero on entry; d/dy0 on exit)
+  float* dz;             // [N][128]
+  float dt;
+  int T; int N;
+};
+
+__global__ void __launch_bounds__(256, 1) k_lem_bwd_tc(const LemBwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smA = smem;
+  uint8_t* smB = smem + LT_A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smB + 2 * LT_B_BYTES);    // bfull[2], bfree[2], acc
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row0 = blockIdx.x * 128;
+  const size_t plane = (size_t)p.N * 128;
+
+  if (warp == 0) tmem_alloc(tmem_slot, 256);
+  if (tid == 32) {
+    for (int i = 0; i < 5; ++i) mbar_init(&bars[i], 1);
+    fence_barrier_init();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  Ring rg{smB, &bars[0], &bars[2], 0};
+  uint64_t* acc = &bars[4];
+  uint32_t nacc = 0;                        // completed accumulator waits (parity)
+
+  const int r = 32 * (warp & 3) + lane;
+  const int grow = row0 + r;
+  const bool live = grow < p.N;
+  const int c0 = 64 * (warp >> 2);
+  const uint32_t tlane = (uint32_t)(32 * (warp & 3)) << 16;
+
+  // runs `nchunk` (4) weight chunks starting at image index w0 against the state tile, D at tmem + dcol
+  auto gemm4 = [&](const float* wimg, uint32_t w0, uint32_t dcol, bool accumulate_first) {
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t base = rg.n;
+      auto src_of = [&](uint32_t j) { return wimg + (size_t)(w0 + j) * (LT_B_BYTES / 4); };
+      ring_issue_copy(rg, base + 0, src_of(0));
+      ring_issue_copy(rg, base + 1, src_of(1));
+      for (uint32_t j = 0; j < 4; ++j) {
+        ring_mma(rg, base + j, smem_u32(smA + j * 2 * IMG_BYTES), tmem + dcol, accumulate_first || j != 0);
+        if (j + 2 < 4) ring_issue_copy(rg, base + j + 2, src_of(j + 2));
+      }
+      rg.n = base + 4;
+      umma_commit(acc);
+    }
+    mbar_wait(acc, nacc & 1);
+    ++nacc;
+    tc_fence_after();
+  };
+
+  for (int t = p.T - 1; t >= 0; --t) {
+    const float* g_t = p.gates + (size_t)t * 4 * plane;
+    float* dG_t = p.dG + (size_t)t * p.N * 384;
+    // ---- bwd_y (thread = row r, channels c0..c0+63)
+#pragma unroll 1
+    for (int j = 0; j < 64; j += 4) {
+      const int col = c0 + j;
+      float4 dl = zero4();
+      if (live) {
+        const size_t o = (size_t)grow * 128 + col;
+        float4 d = ldcg4(p.dy + o);
+        if (p.gY) d = add4(d, ldg4(p.gY + (size_t)t * plane + o));
+        const float4 a = ldg4(g_t + o), tl = ldg4(g_t + 3 * plane + o);
+        const float4 yp = ldg4(p.Y + (size_t)t * plane + o);
+        dl = make_float4(d.x * a.x * (1.f - tl.x * tl.x), d.y * a.y * (1.f - tl.y * tl.y),
+                         d.z * a.z * (1.f - tl.z * tl.z), d.w * a.w * (1.f - tl.w * tl.w));
+        const float4 dg0 = make_float4(d.x * (tl.x - yp.x) * a.x * (1.f - a.x / p.dt), d.y * (tl.y - yp.y) * a.y * (1.f - a.y / p.dt),
+                                       d.z * (tl.z - yp.z) * a.z * (1.f - a.z / p.dt), d.w * (tl.w - yp.w) * a.w * (1.f - a.w / p.dt));
+        st4(p.dL + (size_t)t * plane + o, dl);
+        st4(dG_t + (size_t)grow * 384 + col, dg0);
+        st4(p.dy + o, make_float4(d.x * (1.f - a.x), d.y * (1.f - a.y), d.z * (1.f - a.z), d.w * (1.f - a.w)));
+      }
+      state_store4(smA, r, col, dl);
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    // ---- acc1 = dL Wz[:, :128]   -> TMEM columns 0..127
+    gemm4(p.Wzh_img, 0, 0, false);
+    // ---- bwd_z, and stage dG0 for the first block of the dy GEMM
+#pragma unroll 1
+    for (int cb = 0; cb < 2; ++cb) {
+      const int cc = c0 + 32 * cb;
+      float v[32];
+      __syncwarp();
+      tmem_ld32(tmem + tlane + (uint32_t)cc, v);
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const int col = cc + j;
+        float4 g0 = zero4();
+        if (live) {
+          const size_t o = (size_t)grow * 128 + col;
+          float4 d = add4(ldcg4(p.dz + o), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+          if (p.gZ) d = add4(d, ldg4(p.gZ + (size_t)t * plane + o));
+          const float4 b = ldg4(g_t + plane + o), zc = ldg4(g_t + 2 * plane + o);
+          const float4 zp = ldg4(p.Z + (size_t)t * plane + o);
+          st4(dG_t + (size_t)grow * 384 + 128 + col,
+              make_float4(d.x * (zc.x - zp.x) * b.x * (1.f - b.x / p.dt), d.y * (zc.y - zp.y) * b.y * (1.f - b.y / p.dt),
+                          d.z * (zc.z - zp.z) * b.z * (1.f - b.z / p.dt), d.w * (zc.w - zp.w) * b.w * (1.f - b.w / p.dt)));
+          st4(dG_t + (size_t)grow * 384 + 256 + col,
+              make_float4(d.x * b.x * (1.f - zc.x * zc.x), d.y * b.y * (1.f - zc.y * zc.y), d.z * b.z * (1.f - zc.z * zc.z),
+                          d.w * b.w * (1.f - zc.w * zc.w)));
+          st4(p.dz + o, make_float4(d.x * (1.f - b.x), d.y * (1.f - b.y), d.z * (1.f - b.z), d.w * (1.f - b.w)));
+          g0 = ldcg4(dG_t + (size_t)grow * 384 + col);      // written by this thread in bwd_y
+        }
+        state_store4(smA, r, col, g0);
+      }
+    }
+    // ---- acc2 = [dG0 | dG1 | dG2] W[:, :128]  -> TMEM columns 128..255, A tile restaged per block
+    for (int blk = 0; blk < 3; ++blk) {
+      if (blk > 0) {
+#pragma unroll 1
+        for (int j = 0; j < 64; j += 4) {
+          const int col = c0 + j;
+          float4 g = live ? ldcg4(dG_t + (size_t)grow * 384 + 128 * blk + col) : zero4();
+          state_store4(smA, r, col, g);
+        }
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      __syncthreads();
+      gemm4(p.Wh_img, 4 * blk, 128, blk != 0);
+    }
+    // ---- dy += acc2
+#pragma unroll 1
+    for (int cb = 0; cb < 2; ++cb) {
+      const int cc = c0 + 32 * cb;
+      float v[32];
+      __syncwarp();
+      tmem_ld32(tmem + tlane + (uint32_t)(128 + cc), v);
+      if (live) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const size_t o = (size_t)grow * 128 + cc + j;
+          st4(p.dy + o, add4(ldcg4(p.dy + o), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3])));
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
+}  // namespace msmp
+
+using namespace msmp;
+
+extern "C" int msmp_lem_tc_fwd(const float* inp, const float* Wimg, const float* Wzimg, const float* bias,
+                               const float* bias_z, float* Y, float* Z, float* gates, float dt, int T, int N,
+                               cudaStream_t stream) {
+  if (T < 0 || N < 0) return MSMP_ERR_ARG;
+  if (T == 0 || N == 0) return MSMP_OK;
+  LemFwdParams p{inp, Wimg, Wzimg, bias, bias_z, Y, Z, gates, dt, T, N};
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(k_lem_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_SMEM_FWD) != cudaSuccess)
+      return MSMP_ERR_CUDA;
+    attr_set = true;
+  }
+  k_lem_fwd_tc<<<(N + 127) / 128, 256, LT_SMEM_FWD, stream>>>(p);
+  MSMP_CHECK_LAUNCH();
+  return MSMP_OK;
+}
+
+extern "C" int msmp_lem_tc_bwd(const float* Wzh_img, const float* Wh_img, const float* Y, const float* Z,
+                               const float* gates, const float* gY, const float* gZ, float* dG, float* dL, float* dy,
+                               float* dz, float dt, int T, int N, cudaStream_t stream) {
+  if (T < 0 || N < 0) return MSMP_ERR_ARG;
+  if (T == 0 || N == 0) return MSMP_OK;
+  LemBwdParams p{Wzh_img, Wh_img, Y, Z, gates, gY, gZ, dG, dL, dy, dz, dt, T, N};
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(k_lem_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_SMEM_BWD) != cudaSuccess)
+      return MSMP_ERR_CUDA;
+    attr_set = true;
+  }
+  k_lem_bwd_tc<<<(N + 127) / 128, 256, LT_SMEM_BWD, stream>>>(p);
+  MSMP_CHECK_LAUNCH();
+  return MSMP_OK;
+}

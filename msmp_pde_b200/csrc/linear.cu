@@ -383,14 +383,9 @@ extern "C" int msmp_linear_wgrad(const float* X, int ldx, int K, int xswish, con
   k_wgrad<<<grid, 256, WG_SMEM, stream>>>(p);
   MSMP_CHECK_LAUNCH();
   {
-    int count = K * Nout;
-    k_reduce_partials<<<(count + 255) / 256, 256, 0, stream>>>(p.part, dWt, count, S, (size_t)K * Nout, accumulate);
-    MSMP_CHECK_LAUNCH();
-  }
-  if (nside > 0) {
-    int count = nside * Nout;
-    k_reduce_partials<<<(count + 255) / 256, 256, 0, stream>>>(p.part_side, dWside, count, S, (size_t)nside * Nout,
-                                                              accumulate);
+    const int c0 = K * Nout, c1 = nside * Nout;
+    k_reduce_partials2<<<(c0 + c1 + 255) / 256, 256, 0, stream>>>(p.part, dWt, c0, (size_t)K * Nout, p.part_side, dWside,
+                                                                 c1, (size_t)nside * Nout, S, accumulate);
     MSMP_CHECK_LAUNCH();
   }
   return MSMP_OK;

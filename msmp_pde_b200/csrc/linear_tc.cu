@@ -15,9 +15,10 @@
 
 namespace msmp {
 
-constexpr int TC_STAGE_BYTES = 4 * IMG_BYTES;                 // A_hi, A_lo, B_hi, B_lo
-constexpr int TC_STAGES = 2;
-constexpr int TC_SMEM = TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int TC_A_STAGES = 2;                                // A_hi, A_lo per stage (32 KiB)
+constexpr int TC_B_STAGES = 4;                                // B_hi, B_lo per stage (32 KiB), prefetched ahead
+constexpr int TC_A_BYTES = 2 * IMG_BYTES, TC_B_BYTES = 2 * IMG_BYTES;
+constexpr int TC_SMEM = TC_A_STAGES * TC_A_BYTES + TC_B_STAGES * TC_B_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 
 struct LinTcParams {
   const float* A[3];
@@ -48,7 +49,8 @@ struct LinTcParams {
 __global__ void __launch_bounds__(256, 1) k_linear_tc(const LinTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES);   // full[2], free[2]
+  uint8_t* smemB = smem + TC_A_STAGES * TC_A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smemB + TC_B_STAGES * TC_B_BYTES);     // bfull[4], done[2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row0 = blockIdx.x * 128;
@@ -60,10 +62,7 @@ __global__ void __launch_bounds__(256, 1) k_linear_tc(const LinTcParams p) {
 
   if (warp == 0) tmem_alloc(tmem_slot, 128);
   if (tid == 32) {
-    for (int s = 0; s < TC_STAGES; ++s) {
-      mbar_init(&bars[s], 1);
-      mbar_init(&bars[2 + s], 1);
-    }
+    for (int s = 0; s < 6; ++s) mbar_init(&bars[s], 1);
     fence_barrier_init();
   }
   tc_fence_before();
@@ -100,13 +99,20 @@ __global__ void __launch_bounds__(256, 1) k_linear_tc(const LinTcParams p) {
     }
   };
   prefetch(0);
+  const float* bsrc = p.Bimg + (size_t)ntile * nchunks * (TC_B_BYTES / 4);
+  auto issue_b = [&](int c) {      // thread 0: bulk copy of the (hi | lo) weight images of chunk c
+    uint64_t* bar = &bars[c & 3];
+    mbar_expect_tx(bar, TC_B_BYTES);
+    bulk_g2s(smemB + (c & 3) * TC_B_BYTES, bsrc + (size_t)c * (TC_B_BYTES / 4), TC_B_BYTES, bar);
+  };
+  if (tid == 0)
+    for (int c = 0; c < nchunks && c < TC_B_STAGES; ++c) issue_b(c);
   for (int c = 0; c < nchunks; ++c) {
     const int s = c & 1, use = c >> 1;
-    uint8_t* st = smem + s * TC_STAGE_BYTES;
-    if (c >= TC_STAGES) mbar_wait(&bars[2 + s], (use - 1) & 1);      // MMAs that read this stage are done
-    if (tid == 0) {
-      mbar_expect_tx(&bars[s], 2 * IMG_BYTES);
-      bulk_g2s(st + 2 * IMG_BYTES, p.Bimg + ((size_t)ntile * nchunks + c) * (2 * IMG_BYTES / 4), 2 * IMG_BYTES, &bars[s]);
+    uint8_t* st = smem + s * TC_A_BYTES;
+    if (c >= 2) {
+      mbar_wait(&bars[4 + s], (use - 1) & 1);        // MMAs of chunk c-2 done: A stage s and B stage (c-2)&3 free
+      if (tid == 0 && c + 2 < nchunks) issue_b(c + 2);
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -119,9 +125,10 @@ __global__ void __launch_bounds__(256, 1) k_linear_tc(const LinTcParams p) {
     fence_proxy_async();
     __syncthreads();
     if (tid == 0) {
-      mbar_wait(&bars[s], use & 1);                                  // weights of this chunk have landed
+      mbar_wait(&bars[c & 3], (c >> 2) & 1);                         // weights of this chunk have landed
       tc_fence_after();
-      const uint32_t a_hi = smem_u32(st), a_lo = a_hi + IMG_BYTES, b_hi = a_hi + 2 * IMG_BYTES, b_lo = a_hi + 3 * IMG_BYTES;
+      const uint32_t a_hi = smem_u32(st), a_lo = a_hi + IMG_BYTES;
+      const uint32_t b_hi = smem_u32(smemB + (c & 3) * TC_B_BYTES), b_lo = b_hi + IMG_BYTES;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const uint64_t dah = umma_desc(a_hi + 32 * k, 16, 1024), dal = umma_desc(a_lo + 32 * k, 16, 1024);
@@ -130,13 +137,13 @@ __global__ void __launch_bounds__(256, 1) k_linear_tc(const LinTcParams p) {
         umma_tf32(tmem, dal, dbh, IDESC, 1u);
         umma_tf32(tmem, dah, dbl, IDESC, 1u);
       }
-      umma_commit(&bars[2 + s]);
+      umma_commit(&bars[4 + s]);
     }
   }
   // accumulator complete when the last commit arrives
   {
     const int last = nchunks - 1;
-    mbar_wait(&bars[2 + (last & 1)], (last >> 1) & 1);
+    mbar_wait(&bars[4 + (last & 1)], (last >> 1) & 1);
     tc_fence_after();
   }
   // ---- epilogue: warp w reads lanes 32*(w&3).., columns 64*(w>>2)..

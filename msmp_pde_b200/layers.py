@@ -80,6 +80,7 @@ class LayerPack:
         self.W3side = w3s
         self.W4t = W4.t().contiguous()
         self.W4d = W4                                                  # [n][k]: dgrad operand (alias)
+        self.W2d = W2                                                  # [n][k]: edge-backward operand (alias)
 
 
 class _Aux:
@@ -130,7 +131,7 @@ class _LayerCoreFn(torch.autograd.Function):
         dcat = ops.linear_fwd([dz3], pk.W3hx)                          # [N,256] = [dh (via x) | dagg]
         # message path
         dPQ = torch.empty(N, 2 * H, dtype=torch.float32, device=dev)
-        dz1, dW2, db2 = ops.edge_bwd(PQ[:, :H], PQ[:, H:], topo, W2, z2, dcat[:, H:], dPQ[:, :H])
+        dz1, dW2, db2 = ops.edge_bwd(PQ[:, :H], PQ[:, H:], topo, pk.W2d, z2, dcat[:, H:], dPQ[:, :H])
         ops.segment_reduce(dz1, topo.colptr, perm=topo.csc_perm, out=dPQ[:, H:], N=N)
         Kp = pk.Wpq_t.shape[0]
         dWpq_t = torch.empty(Kp, 2 * H, dtype=torch.float32, device=dev)

@@ -40,6 +40,11 @@ class _LEMFn(torch.autograd.Function):
         gates = torch.empty(T, 4, N, H, dtype=torch.float32, device=dev)   # dt_bar, dt_z, tanh(G2), tanh(L)
         G = torch.empty(N, 3 * H, dtype=torch.float32, device=dev)
         L = torch.empty(N, H, dtype=torch.float32, device=dev)
+        if ops.GEMM_MODE == "tc" and ip == 32:
+            ops.lem_tc_fwd(inp, Wt, Wzt, bias, bias_lin_z, Y, Z, gates, dt)
+            ctx.save_for_backward(inp, Y, Z, gates)
+            ctx.dt, ctx.ninp, ctx.packs = dt, ninp, packs
+            return Y[1:], Z[1:]
         for t in range(T):
             ops.linear_fwd([Y[t], inp[t]], Wt, bias=bias, out=G)
             ops.lem_gate_z(G, Z[t], dt, gates[t], Z[t + 1])
@@ -62,7 +67,10 @@ class _LEMFn(torch.autograd.Function):
         dy = torch.zeros(N, H, dtype=torch.float32, device=dev)      # carried d/dy_t
         dz = torch.zeros(N, H, dtype=torch.float32, device=dev)      # carried d/dz_t
         dz_tot = torch.empty(N, H, dtype=torch.float32, device=dev)
-        for t in range(T - 1, -1, -1):
+        fused = ops.GEMM_MODE == "tc" and ip == 32
+        if fused:
+            ops.lem_tc_bwd(Wzh, Wh, Y, Z, gates, gY, gZ, dG, dL, dy, dz, dt)
+        for t in (range(T - 1, -1, -1) if not fused else ()):
             # through y_t = (1-a) y_{t-1} + a tanh(L):  dL, dG0, dy <- dy*(1-a)
             ops.lem_bwd_y(dy, gY[t], Y[t], gates[t], dt, dL[t], dG[t])
             # dz_t total = carried + dL Wz[:, :H]  (+ external gZ[t], added inside lem_bwd_z)

@@ -199,7 +199,7 @@ def linear_wgrad(X, dY, K=None, xswish=False, side=None, r=0, has_bias=False, dW
                                 _ld(side) if side is not None else 0, r if side is not None else 0, int(has_bias),
                                 dWt.data_ptr(), _p(dWside), int(accumulate), M, ws.data_ptr(), ws.numel(), _stream()),
           "msmp_linear_wgrad")
-    _count(3 if nside else 2)
+    _count(2)
     return dWt, dWside
 
 
@@ -210,6 +210,15 @@ def edge_fwd(P, Q, topo, W2t, b2, save_z2=True):
     agg = torch.empty(topo.N, H, dtype=torch.float32, device=dev)
     z2 = torch.empty(topo.E, H, dtype=torch.float32, device=dev) if save_z2 else None
     ws = _workspace(lib.msmp_edge_fwd_workspace(topo.E), dev)
+    if GEMM_MODE == "tc":
+        img = _cached_images(W2t)
+        with _timed("edge_fwd"):
+            check(lib.msmp_edge_tc_fwd(P.data_ptr(), Q.data_ptr(), _ld(P), topo.src.data_ptr(), topo.dst.data_ptr(),
+                                       topo.rowptr.data_ptr(), topo.inv_deg.data_ptr(), img.data_ptr(), b2.data_ptr(),
+                                       _p(z2), agg.data_ptr(), topo.E, topo.N, ws.data_ptr(), ws.numel(), _stream()),
+                  "msmp_edge_tc_fwd")
+        _count(2)
+        return agg, z2
     with _timed("edge_fwd"):
         check(lib.msmp_edge_fwd(P.data_ptr(), Q.data_ptr(), _ld(P), topo.src.data_ptr(), topo.dst.data_ptr(),
                                 topo.rowptr.data_ptr(), topo.inv_deg.data_ptr(), W2t.data_ptr(), b2.data_ptr(),
@@ -223,6 +232,23 @@ def edge_bwd(P, Q, topo, W2, z2, dagg, dP):
     """Returns dz1 [E,128], dW2 [128,128] ([n][k] = parameter layout), db2 [128]; writes dP in place."""
     dev = P.device
     dz1 = torch.empty(topo.E, H, dtype=torch.float32, device=dev)
+    if GEMM_MODE == "tc":
+        dz2 = torch.empty(topo.E, H, dtype=torch.float32, device=dev)
+        a1 = torch.empty(topo.E, H, dtype=torch.float32, device=dev)
+        img = _cached_images(W2)
+        ws = _workspace(lib.msmp_edge_fwd_workspace(topo.E), dev)
+        with _timed("edge_bwd"):
+            check(lib.msmp_edge_tc_bwd(P.data_ptr(), Q.data_ptr(), _ld(P), topo.src.data_ptr(), topo.dst.data_ptr(),
+                                       topo.rowptr.data_ptr(), topo.inv_deg.data_ptr(), img.data_ptr(), z2.data_ptr(),
+                                       dagg.data_ptr(), _ld(dagg), dz2.data_ptr(), a1.data_ptr(), dz1.data_ptr(),
+                                       dP.data_ptr(), _ld(dP), topo.E, topo.N, ws.data_ptr(), ws.numel(), _stream()),
+                  "msmp_edge_tc_bwd")
+            _count(2)
+            if topo.E > 0:
+                dW2t, dbs = linear_wgrad(a1, dz2, has_bias=True)       # dW2t[k][n] = sum_e a1[e][k] dz2[e][n]
+            else:
+                dW2t, dbs = torch.zeros(H, H, device=dev), torch.zeros(1, H, device=dev)
+        return dz1, dW2t.t(), dbs[0]
     dW2 = torch.empty(H, H, dtype=torch.float32, device=dev)
     db2 = torch.empty(H, dtype=torch.float32, device=dev)
     ws = _workspace(lib.msmp_edge_bwd_workspace(topo.E), dev)
@@ -342,3 +368,20 @@ def decoder_bwd(dout, h, za, w1, w2, dt, geom):
                                ws.numel(), _stream()), "msmp_decoder_bwd")
     _count(2)
     return dh, dW
+
+
+def lem_tc_fwd(inp, Wt, Wzt, bias, bias_z, Y, Z, gates, dt):
+    """Persistent tensor-core LEM forward (all T steps, one launch)."""
+    T, N = inp.shape[0], inp.shape[1]
+    check(lib.msmp_lem_tc_fwd(inp.data_ptr(), _cached_images(Wt).data_ptr(), _cached_images(Wzt).data_ptr(),
+                              bias.data_ptr(), bias_z.data_ptr(), Y.data_ptr(), Z.data_ptr(), gates.data_ptr(),
+                              float(dt), T, N, _stream()), "msmp_lem_tc_fwd")
+    _count(1)
+
+
+def lem_tc_bwd(Wzh, Wh, Y, Z, gates, gY, gZ, dG, dL, dy, dz, dt):
+    T, N = gates.shape[0], gates.shape[2]
+    check(lib.msmp_lem_tc_bwd(_cached_images(Wzh).data_ptr(), _cached_images(Wh).data_ptr(), Y.data_ptr(),
+                              Z.data_ptr(), gates.data_ptr(), _p(gY), _p(gZ), dG.data_ptr(), dL.data_ptr(),
+                              dy.data_ptr(), dz.data_ptr(), float(dt), T, N, _stream()), "msmp_lem_tc_bwd")
+    _count(1)

@@ -36,6 +36,15 @@ def dev():
     return torch.device("cuda:0")
 
 
+@pytest.fixture(params=["tc", "ffma"])
+def gemm_mode(request):
+    from msmp_pde_b200 import ops
+    prev = ops.GEMM_MODE
+    ops.GEMM_MODE = request.param
+    yield request.param
+    ops.GEMM_MODE = prev
+
+
 def test_abi_loaded():
     from msmp_pde_b200 import _lib
     assert _lib.lib.msmp_abi_version() == 1
@@ -108,15 +117,6 @@ def test_linear_fwd_plain_and_strided(dev):
     assert rel_err(y, ref) < TOL
 
 
-@pytest.fixture(params=["tc", "ffma"])
-def gemm_mode(request):
-    from msmp_pde_b200 import ops
-    prev = ops.GEMM_MODE
-    ops.GEMM_MODE = request.param
-    yield request.param
-    ops.GEMM_MODE = prev
-
-
 @pytest.mark.parametrize("M,K,Nout", [(1000, 192, 256), (130, 128, 128), (5000, 160, 384), (40, 64, 128)])
 def test_linear_wgrad(dev, gemm_mode, M, K, Nout):
     from msmp_pde_b200 import ops
@@ -160,7 +160,7 @@ def _edge_ref(ei, N, PQ, W2, b2):
 
 @pytest.mark.parametrize("sizes,deg,hub", [([50, 37, 64], 5.0, None), ([300, 500], 7.0, 450), ([20], 1.5, None),
                                            ([2000, 1000], 16.0, None)])
-def test_edge_fwd(dev, sizes, deg, hub):
+def test_edge_fwd(dev, gemm_mode, sizes, deg, hub):
     from msmp_pde_b200 import ops
     ei, batch, N, PQ, W2, b2, topo = _edge_inputs(sizes, deg, 1, hub, dev)
     PQd = PQ.to(dev)
@@ -173,7 +173,7 @@ def test_edge_fwd(dev, sizes, deg, hub):
 
 
 @pytest.mark.parametrize("sizes,deg,hub", [([50, 37, 64], 5.0, None), ([300, 500], 7.0, 450), ([2000, 1000], 16.0, None)])
-def test_edge_bwd(dev, sizes, deg, hub):
+def test_edge_bwd(dev, gemm_mode, sizes, deg, hub):
     from msmp_pde_b200 import ops
     ei, batch, N, PQ, W2, b2, topo = _edge_inputs(sizes, deg, 2, hub, dev)
     g = torch.Generator().manual_seed(9)
@@ -247,7 +247,7 @@ def test_instnorm(dev, sizes, mode):
     assert rel_err(dy0, y0.grad) < 2e-4
 
 
-def test_lem_matches_oracle(dev):
+def test_lem_matches_oracle(dev, gemm_mode):
     from oracle.models import lem_forward
     from msmp_pde_b200.lem import LEMcuda
     torch.manual_seed(0)
