@@ -151,13 +151,16 @@ int msmp_decoder_bwd(const float* dout, const float* h, const float* za, const f
                      void* workspace, size_t ws_bytes, cudaStream_t stream);
 
 /* Persistent tensor-core LEM: ALL T steps in one launch, one CTA per 128 nodes (the recurrence is per node).
- * inp [T][N][32] zero-padded inputs; Wimg / Wzimg = tile images (msmp_linear_tc_fwd format) of the k-major
- * W^T [160 x 384] and Wz^T [160 x 128] (rows: 128 state + 32 input); Y, Z [T+1][N][128] with Y[0], Z[0] the initial
- * state; gates [T][4][N][128].  Backward: Wzh_img / Wh_img = images of Wz[:, :128] ([128 x 128]) and W[:, :128]
- * ([384 x 128]) read as k-major; dy / dz [N][128] zero on entry, gradient wrt the initial state on exit;
- * dG [T][N][384], dL [T][N][128] feed the weight-gradient GEMMs. */
-int msmp_lem_tc_fwd(const float* inp, const float* Wimg, const float* Wzimg, const float* bias, const float* bias_z,
-                    float* Y, float* Z, float* gates, float dt, int T, int N, cudaStream_t stream);
+ * inp [T][N][32] zero-padded inputs (ninp real columns).  The input part of both affine maps is hoisted:
+ * pre [T][N][512] (scratch) = [bias | bias_z] + inp [Wt_in | Wzt_in] with Wt_in / Wzt_in = rows 128.. of the k-major
+ * packs W^T [160 x 384] / Wz^T [160 x 128].  Wimg / Wzimg = tile images (msmp_linear_tc_fwd format) of the STATE
+ * rows W^T[:128] / Wz^T[:128].  Y, Z [T+1][N][128] with Y[0], Z[0] the initial state; gates [T][4][N][128].
+ * Backward: Wzh_img / Wh_img = images of Wz[:, :128] ([128 x 128]) and W[:, :128] ([384 x 128]) read as k-major;
+ * dy / dz [N][128] zero on entry, gradient wrt the initial state on exit; dG [T][N][384], dL [T][N][128] feed the
+ * weight-gradient GEMMs. */
+int msmp_lem_tc_fwd(const float* inp, int ninp, const float* Wt_in, const float* Wzt_in, const float* Wimg,
+                    const float* Wzimg, const float* bias, const float* bias_z, float* pre, float* Y, float* Z,
+                    float* gates, float dt, int T, int N, cudaStream_t stream);
 int msmp_lem_tc_bwd(const float* Wzh_img, const float* Wh_img, const float* Y, const float* Z, const float* gates,
                     const float* gY, const float* gZ, float* dG, float* dL, float* dy, float* dz, float dt, int T,
                     int N, cudaStream_t stream);

@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(256, 1) k_edge_tc(const EdgeTcParams p) {
     for (int c = 0; c < 4; ++c, ++nchunk) {
       const int s = nchunk & 1;
       uint8_t* st = smA + s * ETC_A_BYTES;
-      if (nchunk >= 2) mbar_wait(&bars[1 + s], ((nchunk >> 1) - 1) & 1);
+      if (nchunk >= 2) mbar_wait_warp(&bars[1 + s], ((nchunk >> 1) - 1) & 1);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int idx = tid + 256 * i;
@@ -147,8 +147,8 @@ __global__ void __launch_bounds__(256, 1) k_edge_tc(const EdgeTcParams p) {
     // ---- wait for the accumulator: both stages' last commits (also frees the A ring for the tile below)
     {
       const uint32_t l1 = nchunk - 1, l0 = nchunk - 2;
-      mbar_wait(&bars[1 + (l0 & 1)], (l0 >> 1) & 1);
-      mbar_wait(&bars[1 + (l1 & 1)], (l1 >> 1) & 1);
+      mbar_wait_warp(&bars[1 + (l0 & 1)], (l0 >> 1) & 1);
+      mbar_wait_warp(&bars[1 + (l1 & 1)], (l1 >> 1) & 1);
       tc_fence_after();
     }
     // ---- epilogue: thread = edge row r, 64 columns (two TMEM loads of 32)

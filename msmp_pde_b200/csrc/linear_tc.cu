@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(256, 1) k_linear_tc(const LinTcParams p) {
     const int s = c & 1, use = c >> 1;
     uint8_t* st = smem + s * TC_A_BYTES;
     if (c >= 2) {
-      mbar_wait(&bars[4 + s], (use - 1) & 1);        // MMAs of chunk c-2 done: A stage s and B stage (c-2)&3 free
+      mbar_wait_warp(&bars[4 + s], (use - 1) & 1);   // MMAs of chunk c-2 done: A stage s and B stage (c-2)&3 free
       if (tid == 0 && c + 2 < nchunks) issue_b(c + 2);
     }
 #pragma unroll
@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(256, 1) k_linear_tc(const LinTcParams p) {
   // accumulator complete when the last commit arrives
   {
     const int last = nchunks - 1;
-    mbar_wait(&bars[4 + (last & 1)], (last >> 1) & 1);
+    mbar_wait_warp(&bars[4 + (last & 1)], (last >> 1) & 1);
     tc_fence_after();
   }
   // ---- epilogue: warp w reads lanes 32*(w&3).., columns 64*(w>>2)..

@@ -40,8 +40,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(20);
     if (clock64() - t0 > 4000000000LL) __trap();
   }
+}
+// Warp-collective wait: one lane polls (256 threads spinning on one mbarrier starve the producer / MMA-issuing
+// threads of issue slots), the rest of the warp parks at the warp barrier.
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
+  if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity);
+  __syncwarp();
 }
 
 // ---- async-proxy plumbing -----------------------------------------------------------------------

@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(256, 1) k_wgrad_tc(const WgradTcParams p) {
   for (int c = 0; c < nchunks; ++c) {
     const int s = c & 1, use = c >> 1;
     uint8_t* st = smem + s * WT_STAGE_BYTES;
-    if (c >= 2) mbar_wait(&bars[s], (use - 1) & 1);
+    if (c >= 2) mbar_wait_warp(&bars[s], (use - 1) & 1);
     const int mb = m_begin + c * WT_CHUNK;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(256, 1) k_wgrad_tc(const WgradTcParams p) {
   float* out = p.part + (size_t)split * p.K * p.Nout;
   if (nchunks > 0) {
     const int last = nchunks - 1;
-    mbar_wait(&bars[last & 1], (last >> 1) & 1);
+    mbar_wait_warp(&bars[last & 1], (last >> 1) & 1);
     tc_fence_after();
   }
   // epilogue: warp w -> TMEM lanes 32*(w&3).. (= k rows), columns 64*(w>>2)..

@@ -33,15 +33,15 @@ class _LEMFn(torch.autograd.Function):
         ip = pad32(ninp)
         inp = torch.zeros(T, N, ip, dtype=torch.float32, device=dev)
         inp[:, :, :ninp] = inputs
-        Wt, Wzt, Wh, Wzh = packs          # k-major packs, rows [state(128) | input(ip)]; dgrad operands
+        Wt, Wzt, Wh, Wzh, Wt_h, Wzt_h = packs    # k-major packs, rows [state(128) | input(ip)]; dgrad operands
         Y = torch.empty(T + 1, N, H, dtype=torch.float32, device=dev)
         Z = torch.empty(T + 1, N, H, dtype=torch.float32, device=dev)
         Y[0], Z[0] = y0, z0
         gates = torch.empty(T, 4, N, H, dtype=torch.float32, device=dev)   # dt_bar, dt_z, tanh(G2), tanh(L)
         G = torch.empty(N, 3 * H, dtype=torch.float32, device=dev)
         L = torch.empty(N, H, dtype=torch.float32, device=dev)
-        if ops.GEMM_MODE == "tc" and ip == 32:
-            ops.lem_tc_fwd(inp, Wt, Wzt, bias, bias_lin_z, Y, Z, gates, dt)
+        if ops.GEMM_MODE == "tc" and ops.LEM_PERSISTENT and ip == 32:
+            ops.lem_tc_fwd(inp, ninp, Wt, Wzt, Wt_h, Wzt_h, bias, bias_lin_z, Y, Z, gates, dt)
             ctx.save_for_backward(inp, Y, Z, gates)
             ctx.dt, ctx.ninp, ctx.packs = dt, ninp, packs
             return Y[1:], Z[1:]
@@ -58,7 +58,7 @@ class _LEMFn(torch.autograd.Function):
     def backward(ctx, gY, gZ):
         inp, Y, Z, gates = ctx.saved_tensors
         dt, ninp = ctx.dt, ctx.ninp
-        _, _, Wh, Wzh = ctx.packs
+        _, _, Wh, Wzh, _, _ = ctx.packs
         T, N, ip = inp.shape
         dev = inp.device
         gY, gZ = gY.contiguous(), gZ.contiguous()
@@ -67,7 +67,7 @@ class _LEMFn(torch.autograd.Function):
         dy = torch.zeros(N, H, dtype=torch.float32, device=dev)      # carried d/dy_t
         dz = torch.zeros(N, H, dtype=torch.float32, device=dev)      # carried d/dz_t
         dz_tot = torch.empty(N, H, dtype=torch.float32, device=dev)
-        fused = ops.GEMM_MODE == "tc" and ip == 32
+        fused = ops.GEMM_MODE == "tc" and ops.LEM_PERSISTENT and ip == 32
         if fused:
             ops.lem_tc_bwd(Wzh, Wh, Y, Z, gates, gY, gZ, dG, dL, dy, dz, dt)
         for t in (range(T - 1, -1, -1) if not fused else ()):
@@ -124,7 +124,8 @@ class LEMcuda(nn.Module):
                 Wzt = W.new_zeros(H + ip, H)
                 Wzt[:H] = Wz[:, :H].t()
                 Wzt[H:H + ninp] = Wz[:, H:].t()
-                self._packs = (Wt, Wzt, W[:, :H].contiguous(), Wz[:, :H].contiguous())
+                self._packs = (Wt, Wzt, W[:, :H].contiguous(), Wz[:, :H].contiguous(), Wt[:H].contiguous(),
+                               Wzt[:H].contiguous())
             self._pack_key = key
         return self._packs
 

@@ -77,6 +77,8 @@ def _p(t):
 
 # Tensor-core (tcgen05 3xTF32) execution of the dense layers.  "ffma" keeps the exact-fp32 CUDA-core kernels.
 GEMM_MODE = "tc"
+# Persistent (all-T-steps-in-one-launch) LEM kernels; False = one GEMM + one gate kernel per step.
+LEM_PERSISTENT = False
 _IMG_CACHE: dict = {}
 
 
@@ -370,13 +372,16 @@ def decoder_bwd(dout, h, za, w1, w2, dt, geom):
     return dh, dW
 
 
-def lem_tc_fwd(inp, Wt, Wzt, bias, bias_z, Y, Z, gates, dt):
-    """Persistent tensor-core LEM forward (all T steps, one launch)."""
+def lem_tc_fwd(inp, ninp, Wt, Wzt, Wt_h, Wzt_h, bias, bias_z, Y, Z, gates, dt):
+    """Persistent tensor-core LEM forward (input projection + all T steps, two launches).
+    Wt / Wzt: k-major packs [160, 384] / [160, 128]; Wt_h / Wzt_h: their state rows (stable tensors, for the images)."""
     T, N = inp.shape[0], inp.shape[1]
-    check(lib.msmp_lem_tc_fwd(inp.data_ptr(), _cached_images(Wt).data_ptr(), _cached_images(Wzt).data_ptr(),
-                              bias.data_ptr(), bias_z.data_ptr(), Y.data_ptr(), Z.data_ptr(), gates.data_ptr(),
+    pre = torch.empty(T, N, 512, dtype=torch.float32, device=inp.device)
+    check(lib.msmp_lem_tc_fwd(inp.data_ptr(), int(ninp), Wt[H:].data_ptr(), Wzt[H:].data_ptr(),
+                              _cached_images(Wt_h).data_ptr(), _cached_images(Wzt_h).data_ptr(), bias.data_ptr(),
+                              bias_z.data_ptr(), pre.data_ptr(), Y.data_ptr(), Z.data_ptr(), gates.data_ptr(),
                               float(dt), T, N, _stream()), "msmp_lem_tc_fwd")
-    _count(1)
+    _count(2)
 
 
 def lem_tc_bwd(Wzh, Wh, Y, Z, gates, gY, gZ, dG, dL, dy, dz, dt):

@@ -247,9 +247,22 @@ def test_instnorm(dev, sizes, mode):
     assert rel_err(dy0, y0.grad) < 2e-4
 
 
-def test_lem_matches_oracle(dev, gemm_mode):
+@pytest.mark.parametrize("persistent", [False, True])
+def test_lem_matches_oracle(dev, gemm_mode, persistent):
     from oracle.models import lem_forward
+    from msmp_pde_b200 import ops
     from msmp_pde_b200.lem import LEMcuda
+    if persistent and gemm_mode != "tc":
+        pytest.skip("persistent LEM kernels are tensor-core only")
+    prev = ops.LEM_PERSISTENT
+    ops.LEM_PERSISTENT = persistent
+    try:
+        _lem_check(dev, lem_forward, LEMcuda)
+    finally:
+        ops.LEM_PERSISTENT = prev
+
+
+def _lem_check(dev, lem_forward, LEMcuda):
     torch.manual_seed(0)
     T, N, ninp = 7, 333, 6
     rnn = LEMcuda(ninp, 128, 1.0).to(dev)
