@@ -193,8 +193,9 @@ def run_ours(args):
                     "peak": peaks["tensor_tflops"], "unit": "TFLOP/s", "frac": round(ach / peaks["tensor_tflops"], 5),
                     "traffic": None, "avg_launch_ms": round(avg_ms, 5),
                     "share_of_step": round((tot[dom] / 3) / ms, 4), "peak_source": peaks["source"],
-                    "note": "fp32 FFMA path (round 1): executed FLOPs of the factorised message MLP per launch; "
-                            "tensor peak = cuBLAS bf16 sustained"}
+                    "note": "tcgen05 kind::tf32, error-compensated 3xTF32 (fp32 parity): executed useful FLOPs of the "
+                            "factorised message MLP per launch (the 3x MMA work is not counted); op = gather + GEMM + "
+                            "segmented reduce (+ carry fix-up, wgrad for bwd); tensor peak = cuBLAS bf16 sustained"}
         out = {
             "metric": METRIC, "value": round(world * N / (ms * 1e-3), 1), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": round(ms, 4), "higher_is_better": True,

@@ -72,6 +72,12 @@ int msmp_linear_wgrad_tc(const float* X, int ldx, int K, int xswish, const float
                          const float* side, int lds, int r, int has_bias, float* dWt, float* dWside, int accumulate,
                          int M, void* workspace, size_t ws_bytes, cudaStream_t stream);
 
+/* dWt[K0 + K1, Nout] = [X | X1]^T dY with the two column blocks in different tensors (K0 % 128 == 0). */
+int msmp_linear_wgrad_tc2(const float* X, int ldx, int K0, const float* X1, int ldx1, int K1, int xswish,
+                          const float* dY, int lddy, int Nout, const float* side, int lds, int r, int has_bias,
+                          float* dWt, float* dWside, int accumulate, int M, void* workspace, size_t ws_bytes,
+                          cudaStream_t stream);
+
 /* ---- edge kernels (edges sorted by destination; rowptr = CSR offsets by destination) ------------
  * forward : agg[i] = inv_deg[i] * sum_{e -> i} sw( sw(P[dst e] + Q[src e]) W2^T + b2 );  z2 (optional) keeps
  *           the second pre-activation for the backward pass.  W2t[k][n] = W2[n][k]. */
@@ -151,19 +157,23 @@ int msmp_decoder_bwd(const float* dout, const float* h, const float* za, const f
                      void* workspace, size_t ws_bytes, cudaStream_t stream);
 
 /* Persistent tensor-core LEM: ALL T steps in one launch, one CTA per 128 nodes (the recurrence is per node).
- * inp [T][N][32] zero-padded inputs (ninp real columns).  The input part of both affine maps is hoisted:
- * pre [T][N][512] (scratch) = [bias | bias_z] + inp [Wt_in | Wzt_in] with Wt_in / Wzt_in = rows 128.. of the k-major
- * packs W^T [160 x 384] / Wz^T [160 x 128].  Wimg / Wzimg = tile images (msmp_linear_tc_fwd format) of the STATE
- * rows W^T[:128] / Wz^T[:128].  Y, Z [T+1][N][128] with Y[0], Z[0] the initial state; gates [T][4][N][128].
+ * inp [T][N][32] zero-padded inputs (ninp <= 8 real columns).  Npad = N rounded up to 128.  Arrays private to the
+ * recurrence are LANE-MAJOR: element (row n, channel c) of a C-channel array at ((n/32)*C + c)*32 + n%32.
+ *   pre   lane-major [T][Npad/32][512][32] scratch: [bias | bias_z] + inp [Wt_in | Wzt_in], Wt_in / Wzt_in = rows
+ *         128.. of the k-major packs W^T [160 x 384] / Wz^T [160 x 128]
+ *   Wimg / Wzimg: tile images (msmp_linear_tc_fwd format) of the STATE rows W^T[:128] / Wz^T[:128]
+ *   Y, Z  row-major [T+1][N][128] (Y[0], Z[0] = initial state);  Yt, Zt lane-major copies (slab 0 initialised)
+ *   gates lane-major [T][Npad/32][512][32] = a | b | zc | tL
  * Backward: Wzh_img / Wh_img = images of Wz[:, :128] ([128 x 128]) and W[:, :128] ([384 x 128]) read as k-major;
- * dy / dz [N][128] zero on entry, gradient wrt the initial state on exit; dG [T][N][384], dL [T][N][128] feed the
- * weight-gradient GEMMs. */
+ * gYt / gZt lane-major external gradients ([T] slabs, or one slab for t = T-1 when g_last_only; may be NULL);
+ * dyt / dzt lane-major [Npad/32][128][32], zero on entry, gradient wrt the initial state on exit; s0 / s2 scratch
+ * of the same shape; dG [T][N][384], dL [T][N][128] row-major feed the weight-gradient GEMMs. */
 int msmp_lem_tc_fwd(const float* inp, int ninp, const float* Wt_in, const float* Wzt_in, const float* Wimg,
                     const float* Wzimg, const float* bias, const float* bias_z, float* pre, float* Y, float* Z,
-                    float* gates, float dt, int T, int N, cudaStream_t stream);
-int msmp_lem_tc_bwd(const float* Wzh_img, const float* Wh_img, const float* Y, const float* Z, const float* gates,
-                    const float* gY, const float* gZ, float* dG, float* dL, float* dy, float* dz, float dt, int T,
-                    int N, cudaStream_t stream);
+                    float* Yt, float* Zt, float* gates, float dt, int T, int N, int Npad, cudaStream_t stream);
+int msmp_lem_tc_bwd(const float* Wzh_img, const float* Wh_img, const float* Yt, const float* Zt, const float* gates,
+                    const float* gYt, const float* gZt, int g_last_only, float* dG, float* dL, float* dyt, float* dzt,
+                    float* s0, float* s2, float dt, int T, int N, int Npad, cudaStream_t stream);
 
 /* out[i] = g[i] * swish'(z[i])  (n % 4 == 0) */
 int msmp_mul_dswish(const float* g, const float* z, float* out, size_t n, cudaStream_t stream);

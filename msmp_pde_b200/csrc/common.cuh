@@ -20,6 +20,19 @@ namespace msmp {
 
 // accurate expf (not __expf): fp32 parity against the fp64 oracle is held to 1e-5 of max|ref|
 __device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.0f, 1.0f + expf(-x)); }
+// MUFU-based variants (ex2.approx + rcp.approx): ~1e-6 absolute error, ~6x fewer instructions than expf/tanhf.
+// Used where the transcendental count makes a kernel ALU bound (LEM gate epilogues: 3 per channel per step).
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float tanh_fast(float x) {
+  const float e = __expf(-2.0f * fabsf(x));                 // in (0, 1]: no overflow
+  return copysignf(__fdividef(1.0f - e, 1.0f + e), x);
+}
+// tanh from the accurate expf (2 ulp) and one fast division: ~1e-7 absolute error, about a third of tanhf's cost.
+// (the __expf variants above were measured to push a few small bias gradients 3% over the 1e-5 parity allowance)
+__device__ __forceinline__ float tanh_acc(float x) {
+  const float e = expf(-2.0f * fabsf(x));
+  return copysignf(__fdividef(1.0f - e, 1.0f + e), x);
+}
 // swish(x) = x * sigmoid(x)          (models_gnn.py:12-21, beta = 1)
 __device__ __forceinline__ float swish(float x) { return x * sigmoidf_(x); }
 // d/dx swish = s * (1 + x * (1 - s))

@@ -161,6 +161,17 @@ __global__ void __launch_bounds__(256, 1) k_edge_tc(const EdgeTcParams p) {
       float v[32];
       __syncwarp();
       tmem_ld32(tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)colbase, v);
+      float4 pz[8];          // bwd: z1 = P[dst] + Q[src] of this 32-column block, loaded up front
+      if (BWD && live) {
+        float4 pa[8], qa[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          pa[j] = ldg4(p.P + (size_t)my_dst * p.ldpq + colbase + 4 * j);
+          qa[j] = ldg4(p.Q + (size_t)my_src * p.ldpq + colbase + 4 * j);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) pz[j] = add4(pa[j], qa[j]);
+      }
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
         const int col = colbase + j;
@@ -172,7 +183,7 @@ __global__ void __launch_bounds__(256, 1) k_edge_tc(const EdgeTcParams p) {
             if (p.z2) st4(p.z2 + (size_t)(e0 + r) * 128 + col, z);
             o = swish4(z);
           } else {
-            float4 z1 = add4(ldg4(p.P + (size_t)my_dst * p.ldpq + col), ldg4(p.Q + (size_t)my_src * p.ldpq + col));
+            const float4 z1 = pz[j >> 2];
             st4(p.a1 + (size_t)(e0 + r) * 128 + col, swish4(z1));
             o = make_float4(acc.x * dswish(z1.x), acc.y * dswish(z1.y), acc.z * dswish(z1.z), acc.w * dswish(z1.w));
             st4(p.dz1 + (size_t)(e0 + r) * 128 + col, o);

@@ -21,6 +21,15 @@
 //   acc2  = [dG0 | dG1 | dG2] W[:, :128]          3 x 4 chunks (the A tile is restaged per 128-column block)
 //   dy   += acc2
 // dG [T,N,384] and dL [T,N,128] are written for the four weight-gradient GEMMs (msmp_linear_wgrad_tc).
+//
+// Memory access.  The gate epilogues own one node row per thread (a TMEM lane), so row-major global arrays would be
+// touched 16 bytes per thread at a 512-byte stride (32 lines per warp request; measured: 77 us per step).  Every array
+// private to the recurrence (pre, gates, the y/z history used for y_{t-1}/z_{t-1}, the carried dy/dz, the dG0/dG2
+// scratch) is therefore kept LANE-MAJOR: element (row n, channel c) of a C-channel array lives at
+//     ((n / 32) * C + c) * 32 + n % 32
+// so the 32 lanes of a warp (32 consecutive rows) read/write one contiguous 128-byte line per channel.  Arrays
+// that other kernels consume row-major (Y, Z, dL, dG) are written by a cooperative, fully coalesced copy-out of the
+// state tile image (hi + lo reconstructs the fp32 value exactly).
 #include "umma.cuh"
 #include "msmp_b200.h"
 
@@ -108,40 +117,76 @@ __device__ __forceinline__ void state_store4(uint8_t* smA, int r, int col, float
   store_split4(chunk, chunk + IMG_BYTES, img_off(r, (col & 31) >> 2), v);
 }
 
-// pre[m][0:512] = [bias | bias_z] + inp[m][0:ninp] * [Wt_in | Wzt_in]   (m over T*N rows; exact fp32, memory bound)
+__device__ long long g_lem_dbg[64];
+#define LEM_TICK(i) do { if (blockIdx.x == 0 && tid == 0 && t == 2) g_lem_dbg[i] = clock64(); } while (0)
+
+// L2 prefetch of `nch` consecutive lane-major channel lines (128 B each) of row-tile gt, starting at channel c_begin
+__device__ __forceinline__ void prefetch_lm(const float* base, size_t gt, int C, int c_begin, int nch, int lane) {
+  for (int c = c_begin + lane; c < c_begin + nch; c += 32)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (gt * C + c) * 32));
+}
+
+// lane-major address of (row-tile gt, channel c, lane l) in a C-channel array
+__device__ __forceinline__ size_t lm(size_t gt, int C, int c, int l) { return (gt * C + c) * 32 + l; }
+
+// pre (lane-major, 512 channels) = [bias | bias_z] + inp[:, 0:ninp] * [Wt_in | Wzt_in]; rows = T * Npad
 __global__ void __launch_bounds__(256) k_lem_inproj(const float* __restrict__ inp, const float* __restrict__ Wt_in,
                                                     const float* __restrict__ Wzt_in, const float* __restrict__ bias,
-                                                    const float* __restrict__ bias_z, float* __restrict__ pre,
-                                                    size_t rows, int ninp) {
-  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;      // one float4 of one row
-  if (idx >= rows * 128) return;
-  const size_t m = idx >> 7;
-  const int c = (int)(idx & 127) * 4;                                    // column 0..508
-  const bool g = c < 384;
-  const float* W = g ? Wt_in + c : Wzt_in + (c - 384);
+                                                    const float* __restrict__ bias_z, float* __restrict__ pre, int T,
+                                                    int N, int Npad, int ninp) {
+  // one warp = a quarter (128 channels) of one 32-row tile; x values live in registers
+  const int lane = threadIdx.x & 31;
+  const size_t wid = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);      // over 4 * T * Npad / 32
+  const size_t ntiles = (size_t)T * (Npad / 32);
+  const size_t tile = wid >> 2;
+  const int cq = (int)(wid & 3) * 128;
+  if (tile >= ntiles) return;
+  const int t = (int)(tile / (Npad / 32));
+  const int n = (int)(tile % (Npad / 32)) * 32 + lane;
+  float x[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) x[q] = (q < ninp && n < N) ? __ldg(inp + ((size_t)t * N + n) * 32 + q) : 0.f;
+  float* o = pre + tile * 512 * 32 + lane;
+  const bool g = cq < 384;
+  const float* Wb = g ? Wt_in + cq : Wzt_in;
+  const float* bb = g ? bias + cq : bias_z;
   const int ldw = g ? 384 : 128;
-  float4 acc = g ? ldg4(bias + c) : ldg4(bias_z + (c - 384));
-  const float* x = inp + m * 32;
-  for (int q = 0; q < ninp; ++q) {
-    const float xv = __ldg(x + q);
-    const float4 w = ldg4(W + (size_t)q * ldw);
-    acc.x = fmaf(xv, w.x, acc.x);
-    acc.y = fmaf(xv, w.y, acc.y);
-    acc.z = fmaf(xv, w.z, acc.z);
-    acc.w = fmaf(xv, w.w, acc.w);
+#pragma unroll 4
+  for (int c = 0; c < 128; ++c) {
+    float acc = __ldg(bb + c);
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      if (q < ninp) acc = fmaf(x[q], __ldg(Wb + (size_t)q * ldw + c), acc);
+    o[(size_t)(cq + c) * 32] = acc;
   }
-  st4(pre + m * 512 + c, acc);
+}
+
+// cooperative coalesced copy of the state tile (hi + lo) to a row-major array: dst[(row0 + r) * ld + c], c < 128
+__device__ __forceinline__ void image_to_global(const uint8_t* smA, float* dst, int ld, int row0, int N) {
+  const int tid = threadIdx.x;
+#pragma unroll 4
+  for (int i = 0; i < 16; ++i) {
+    const int idx = tid + 256 * i;
+    const int rr = idx >> 5, c4 = idx & 31;
+    const uint8_t* chunk = smA + (c4 >> 3) * (2 * IMG_BYTES);
+    const uint32_t off = img_off(rr, c4 & 7);
+    const float4 h = *reinterpret_cast<const float4*>(chunk + off);
+    const float4 l = *reinterpret_cast<const float4*>(chunk + IMG_BYTES + off);
+    if (row0 + rr < N) st4(dst + (size_t)(row0 + rr) * ld + 4 * c4, add4(h, l));
+  }
 }
 
 struct LemFwdParams {
-  const float* pre;      // [T][N][512]  bias + input projection (G0 | G1 | G2 | L)
+  const float* pre;      // lane-major [T][Npad/32][512][32]
   const float* Wimg;     // images of Wt[:128]  [128 x 384]: [3 ntiles][4 chunks][2][4096]
   const float* Wzimg;    // images of Wzt[:128] [128 x 128]: [1][4][2][4096]
-  float* Y;              // [T+1][N][128]  (Y[0] = y0 on entry)
-  float* Z;              // [T+1][N][128]  (Z[0] = z0 on entry)
-  float* gates;          // [T][4][N][128]  a, b, zc, tL
+  float* Y;              // row-major [T+1][N][128]  (Y[0] = y0 on entry)
+  float* Z;              // row-major [T+1][N][128]  (Z[0] = z0 on entry)
+  float* Yt;             // lane-major [T+1][Npad/32][128][32]  (Yt[0] = y0 on entry)
+  float* Zt;             // lane-major [T+1][Npad/32][128][32]
+  float* gates;          // lane-major [T][Npad/32][512][32]  a | b | zc | tL
   float dt;
-  int T; int N;
+  int T; int N; int Npad;
 };
 
 __global__ void __launch_bounds__(256, 1) k_lem_fwd_tc(const LemFwdParams p) {
@@ -154,6 +199,7 @@ __global__ void __launch_bounds__(256, 1) k_lem_fwd_tc(const LemFwdParams p) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row0 = blockIdx.x * 128;
   const size_t plane = (size_t)p.N * 128;
+  const size_t ntile = p.Npad / 32;
 
   if (warp == 0) tmem_alloc(tmem_slot, 512);
   if (tid == 32) {
@@ -172,14 +218,13 @@ __global__ void __launch_bounds__(256, 1) k_lem_fwd_tc(const LemFwdParams p) {
   uint64_t* acc = &bars[2 * LT_STAGES];
   uint32_t nacc = 0;
 
-  // epilogue ownership: thread = row r, 64 channels [c0, c0+64)
+  // epilogue ownership: thread = row r (TMEM lane), 64 channels [c0, c0+64); gt = its 32-row tile
   const int r = 32 * (warp & 3) + lane;
-  const int grow = row0 + r;
-  const bool live = grow < p.N;
   const int c0 = 64 * (warp >> 2);
+  const size_t gt = (size_t)blockIdx.x * 4 + (warp & 3);
   const uint32_t tlane = (uint32_t)(32 * (warp & 3)) << 16;
 
-  // y_{-1} tile from Y[0]
+  // y_{-1} tile from the row-major Y[0]
   for (int i = 0; i < 16; ++i) {
     const int idx = tid + 256 * i;
     const int rr = idx >> 5, c4 = idx & 31;
@@ -192,11 +237,21 @@ __global__ void __launch_bounds__(256, 1) k_lem_fwd_tc(const LemFwdParams p) {
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
+    // pull this step's input-projection lines (HBM) into L2 while the G GEMM runs
+    {
+      const float* pre_pf = p.pre + ((size_t)t * ntile) * 512 * 32;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) prefetch_lm(pre_pf, gt, 512, 128 * q + c0, 64, lane);
+    }
     // ---- G = y W_h^T : 3 n-tiles x 4 chunks -> TMEM columns 0..383
+    LEM_TICK(0);
     gemm_phase(rg, p.Wimg, 0, 12, smA, tmem, 0, false, acc, nacc);
-    // ---- gate_z: thread (row r, channels c0..c0+63)
-    float* g_t = p.gates + (size_t)t * 4 * plane;
-    const float* pre_t = p.pre + ((size_t)t * p.N + (live ? grow : 0)) * 512;
+    LEM_TICK(1);
+    // ---- gate_z
+    const float* pre_t = p.pre + ((size_t)t * ntile) * 512 * 32;
+    float* g_t = p.gates + ((size_t)t * ntile) * 512 * 32;
+    const float* zprev = p.Zt + ((size_t)t * ntile) * 128 * 32;
+    float* znext = p.Zt + ((size_t)(t + 1) * ntile) * 128 * 32;
 #pragma unroll 1
     for (int cb = 0; cb < 2; ++cb) {
       const int cc = c0 + 32 * cb;
@@ -206,36 +261,45 @@ __global__ void __launch_bounds__(256, 1) k_lem_fwd_tc(const LemFwdParams p) {
       tmem_ld32(tmem + tlane + (uint32_t)(128 + cc), v1);
       tmem_ld32(tmem + tlane + (uint32_t)(256 + cc), v2);
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const int col = cc + j;
-        float4 zn = zero4();
-        if (live) {
-          const float4 b0 = ldg4(pre_t + col), b1 = ldg4(pre_t + 128 + col), b2 = ldg4(pre_t + 256 + col);
-          const float4 zp = ldcg4(p.Z + (size_t)t * plane + (size_t)grow * 128 + col);
-          float4 a, b, zc;
-          a.x = p.dt * sigmoidf_(v0[j] + b0.x); a.y = p.dt * sigmoidf_(v0[j + 1] + b0.y);
-          a.z = p.dt * sigmoidf_(v0[j + 2] + b0.z); a.w = p.dt * sigmoidf_(v0[j + 3] + b0.w);
-          b.x = p.dt * sigmoidf_(v1[j] + b1.x); b.y = p.dt * sigmoidf_(v1[j + 1] + b1.y);
-          b.z = p.dt * sigmoidf_(v1[j + 2] + b1.z); b.w = p.dt * sigmoidf_(v1[j + 3] + b1.w);
-          zc.x = tanhf(v2[j] + b2.x); zc.y = tanhf(v2[j + 1] + b2.y);
-          zc.z = tanhf(v2[j + 2] + b2.z); zc.w = tanhf(v2[j + 3] + b2.w);
-          zn = make_float4((1.f - b.x) * zp.x + b.x * zc.x, (1.f - b.y) * zp.y + b.y * zc.y,
-                           (1.f - b.z) * zp.z + b.z * zc.z, (1.f - b.w) * zp.w + b.w * zc.w);
-          const size_t o = (size_t)grow * 128 + col;
-          st4(g_t + o, a);
-          st4(g_t + plane + o, b);
-          st4(g_t + 2 * plane + o, zc);
-          st4(p.Z + (size_t)(t + 1) * plane + o, zn);
+      for (int j = 0; j < 32; j += 8) {
+        // batch the 32 loads of 8 channels before any dependent math (the epilogue is latency bound otherwise)
+        float p0[8], p1[8], p2[8], zp[8], zn[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int c = cc + j + e;
+          p0[e] = __ldg(pre_t + lm(gt, 512, c, lane));
+          p1[e] = __ldg(pre_t + lm(gt, 512, 128 + c, lane));
+          p2[e] = __ldg(pre_t + lm(gt, 512, 256 + c, lane));
+          zp[e] = __ldcg(zprev + lm(gt, 128, c, lane));
         }
-        state_store4(smA, r, col, zn);          // z_t becomes the A operand of the L GEMM
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int c = cc + j + e;
+          const float a = p.dt * sigmoidf_(v0[j + e] + p0[e]);
+          const float b = p.dt * sigmoidf_(v1[j + e] + p1[e]);
+          const float zc = tanh_acc(v2[j + e] + p2[e]);
+          zn[e] = (1.f - b) * zp[e] + b * zc;
+          g_t[lm(gt, 512, c, lane)] = a;
+          g_t[lm(gt, 512, 128 + c, lane)] = b;
+          g_t[lm(gt, 512, 256 + c, lane)] = zc;
+          znext[lm(gt, 128, c, lane)] = zn[e];
+        }
+        state_store4(smA, r, cc + j, make_float4(zn[0], zn[1], zn[2], zn[3]));    // z_t: A operand of the L GEMM
+        state_store4(smA, r, cc + j + 4, make_float4(zn[4], zn[5], zn[6], zn[7]));
       }
     }
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
+    LEM_TICK(2);
+    image_to_global(smA, p.Z + (size_t)(t + 1) * plane, 128, row0, p.N);
+    LEM_TICK(3);
     // ---- L = z Wz_h^T : 4 chunks -> TMEM columns 384..511
     gemm_phase(rg, p.Wzimg, 0, 4, smA, tmem, 384, false, acc, nacc);
+    LEM_TICK(4);
     // ---- gate_y
+    const float* yprev = p.Yt + ((size_t)t * ntile) * 128 * 32;
+    float* ynext = p.Yt + ((size_t)(t + 1) * ntile) * 128 * 32;
 #pragma unroll 1
     for (int cb = 0; cb < 2; ++cb) {
       const int cc = c0 + 32 * cb;
@@ -243,24 +307,33 @@ __global__ void __launch_bounds__(256, 1) k_lem_fwd_tc(const LemFwdParams p) {
       __syncwarp();
       tmem_ld32(tmem + tlane + (uint32_t)(384 + cc), v);
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const int col = cc + j;
-        float4 yn = zero4();
-        if (live) {
-          const size_t o = (size_t)grow * 128 + col;
-          const float4 bz = ldg4(pre_t + 384 + col);
-          const float4 a = ldcg4(g_t + o);
-          const float4 yp = ldcg4(p.Y + (size_t)t * plane + o);
-          float4 tl = make_float4(tanhf(v[j] + bz.x), tanhf(v[j + 1] + bz.y), tanhf(v[j + 2] + bz.z), tanhf(v[j + 3] + bz.w));
-          yn = make_float4((1.f - a.x) * yp.x + a.x * tl.x, (1.f - a.y) * yp.y + a.y * tl.y,
-                           (1.f - a.z) * yp.z + a.z * tl.z, (1.f - a.w) * yp.w + a.w * tl.w);
-          st4(g_t + 3 * plane + o, tl);
-          st4(p.Y + (size_t)(t + 1) * plane + o, yn);
+      for (int j = 0; j < 32; j += 8) {
+        float pz[8], av[8], yp[8], yn[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int c = cc + j + e;
+          pz[e] = __ldg(pre_t + lm(gt, 512, 384 + c, lane));
+          av[e] = __ldcg(g_t + lm(gt, 512, c, lane));
+          yp[e] = __ldcg(yprev + lm(gt, 128, c, lane));
         }
-        state_store4(smA, r, col, yn);          // y_t is the A operand of the next step's G GEMM
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int c = cc + j + e;
+          const float tl = tanh_acc(v[j + e] + pz[e]);
+          yn[e] = (1.f - av[e]) * yp[e] + av[e] * tl;
+          g_t[lm(gt, 512, 384 + c, lane)] = tl;
+          ynext[lm(gt, 128, c, lane)] = yn[e];
+        }
+        state_store4(smA, r, cc + j, make_float4(yn[0], yn[1], yn[2], yn[3]));    // y_t: A operand of the next G GEMM
+        state_store4(smA, r, cc + j + 4, make_float4(yn[4], yn[5], yn[6], yn[7]));
       }
     }
-    // the loop head fences + syncs before the next MMAs read the state tile / overwrite TMEM
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    LEM_TICK(5);
+    image_to_global(smA, p.Y + (size_t)(t + 1) * plane, 128, row0, p.N);
+    LEM_TICK(6);
   }
   tc_fence_before();
   __syncthreads();
@@ -271,17 +344,20 @@ __global__ void __launch_bounds__(256, 1) k_lem_fwd_tc(const LemFwdParams p) {
 struct LemBwdParams {
   const float* Wzh_img;  // images of Wt := Wz[:, :128]  ([K = n][N = k]) : [1][4][2][4096]
   const float* Wh_img;   // images of Wt := W[:, :128]   ([K = 384][N = 128]) : [1][12][2][4096]
-  const float* Y;        // [T+1][N][128]
-  const float* Z;        // [T+1][N][128]
-  const float* gates;    // [T][4][N][128]
-  const float* gY;       // [T][N][128] external gradients (nullable)
-  const float* gZ;       // [T][N][128] (nullable)
-  float* dG;             // [T][N][384]
-  float* dL;             // [T][N][128]
-  float* dy;             // [N][128] carried gradient (zero on entry; d/dy0 on exit)
-  float* dz;             // [N][128]
+  const float* Yt;       // lane-major [T+1][Npad/32][128][32]
+  const float* Zt;       // lane-major [T+1][Npad/32][128][32]
+  const float* gates;    // lane-major [T][Npad/32][512][32]
+  const float* gYt;      // lane-major external gradients: [T][..] or, if g_last_only, one slab applied at t = T-1
+  const float* gZt;      // (either may be NULL)
+  int g_last_only;
+  float* dG;             // row-major [T][N][384]
+  float* dL;             // row-major [T][N][128]
+  float* dyt;            // lane-major [Npad/32][128][32] carried gradient (zero on entry; d/dy0 on exit)
+  float* dzt;            // lane-major
+  float* s0;             // lane-major scratch [Npad/32][128][32]  (dG0 of the current step)
+  float* s2;             // lane-major scratch                      (dG2 of the current step)
   float dt;
-  int T; int N;
+  int T; int N; int Npad;
 };
 
 __global__ void __launch_bounds__(256, 1) k_lem_bwd_tc(const LemBwdParams p) {
@@ -293,7 +369,7 @@ __global__ void __launch_bounds__(256, 1) k_lem_bwd_tc(const LemBwdParams p) {
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row0 = blockIdx.x * 128;
-  const size_t plane = (size_t)p.N * 128;
+  const size_t ntile = p.Npad / 32;
 
   if (warp == 0) tmem_alloc(tmem_slot, 256);
   if (tid == 32) {
@@ -313,41 +389,72 @@ __global__ void __launch_bounds__(256, 1) k_lem_bwd_tc(const LemBwdParams p) {
   uint32_t nacc = 0;
 
   const int r = 32 * (warp & 3) + lane;
-  const int grow = row0 + r;
-  const bool live = grow < p.N;
   const int c0 = 64 * (warp >> 2);
+  const size_t gt = (size_t)blockIdx.x * 4 + (warp & 3);
   const uint32_t tlane = (uint32_t)(32 * (warp & 3)) << 16;
+  const float inv_dt = 1.0f / p.dt;
 
-  for (int t = p.T - 1; t >= 0; --t) {
-    const float* g_t = p.gates + (size_t)t * 4 * plane;
-    float* dG_t = p.dG + (size_t)t * p.N * 384;
-    // ---- bwd_y (thread = row r, channels c0..c0+63)
+  // stage a lane-major 128-channel scratch slab (this thread's row, its 64 channels) into the state tile
+  auto stage_lm = [&](const float* slab) {
 #pragma unroll 1
-    for (int j = 0; j < 64; j += 4) {
-      const int col = c0 + j;
-      float4 dl = zero4();
-      if (live) {
-        const size_t o = (size_t)grow * 128 + col;
-        float4 d = ldcg4(p.dy + o);
-        if (p.gY) d = add4(d, ldg4(p.gY + (size_t)t * plane + o));
-        const float4 a = ldg4(g_t + o), tl = ldg4(g_t + 3 * plane + o);
-        const float4 yp = ldg4(p.Y + (size_t)t * plane + o);
-        dl = make_float4(d.x * a.x * (1.f - tl.x * tl.x), d.y * a.y * (1.f - tl.y * tl.y),
-                         d.z * a.z * (1.f - tl.z * tl.z), d.w * a.w * (1.f - tl.w * tl.w));
-        const float4 dg0 = make_float4(d.x * (tl.x - yp.x) * a.x * (1.f - a.x / p.dt), d.y * (tl.y - yp.y) * a.y * (1.f - a.y / p.dt),
-                                       d.z * (tl.z - yp.z) * a.z * (1.f - a.z / p.dt), d.w * (tl.w - yp.w) * a.w * (1.f - a.w / p.dt));
-        st4(p.dL + (size_t)t * plane + o, dl);
-        st4(dG_t + (size_t)grow * 384 + col, dg0);
-        st4(p.dy + o, make_float4(d.x * (1.f - a.x), d.y * (1.f - a.y), d.z * (1.f - a.z), d.w * (1.f - a.w)));
-      }
-      state_store4(smA, r, col, dl);
+    for (int j = 0; j < 64; j += 16) {
+      float g[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) g[e] = __ldcg(slab + lm(gt, 128, c0 + j + e, lane));
+#pragma unroll
+      for (int e = 0; e < 16; e += 4) state_store4(smA, r, c0 + j + e, make_float4(g[e], g[e + 1], g[e + 2], g[e + 3]));
     }
+  };
+  auto publish = [&]() {       // make the freshly written state tile visible to the async proxy / other threads
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
+  };
+
+  for (int t = p.T - 1; t >= 0; --t) {
+    const float* g_t = p.gates + ((size_t)t * ntile) * 512 * 32;
+    const float* yprev = p.Yt + ((size_t)t * ntile) * 128 * 32;
+    const float* zprev = p.Zt + ((size_t)t * ntile) * 128 * 32;
+    const bool ext = !p.g_last_only || t == p.T - 1;
+    const float* gy = (p.gYt && ext) ? p.gYt + (p.g_last_only ? 0 : (size_t)t * ntile * 128 * 32) : nullptr;
+    const float* gz = (p.gZt && ext) ? p.gZt + (p.g_last_only ? 0 : (size_t)t * ntile * 128 * 32) : nullptr;
+    float* dG_t = p.dG + (size_t)t * p.N * 384;
+    if (t > 0) {      // next step's saved activations (written by the forward pass, now in HBM) -> L2
+      const float* g_n = p.gates + ((size_t)(t - 1) * ntile) * 512 * 32;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) prefetch_lm(g_n, gt, 512, 128 * q + c0, 64, lane);
+      prefetch_lm(p.Yt + ((size_t)(t - 1) * ntile) * 128 * 32, gt, 128, c0, 64, lane);
+      prefetch_lm(p.Zt + ((size_t)(t - 1) * ntile) * 128 * 32, gt, 128, c0, 64, lane);
+    }
+    // ---- bwd_y : dL -> state tile, dG0 -> s0, dy <- d (1 - a)
+#pragma unroll 1
+    for (int j = 0; j < 64; j += 8) {
+      float dv[8], av[8], tv[8], yv[8], dl[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int c = c0 + j + e;
+        dv[e] = __ldcg(p.dyt + lm(gt, 128, c, lane));
+        if (gy) dv[e] += __ldg(gy + lm(gt, 128, c, lane));
+        av[e] = __ldg(g_t + lm(gt, 512, c, lane));
+        tv[e] = __ldg(g_t + lm(gt, 512, 384 + c, lane));
+        yv[e] = __ldg(yprev + lm(gt, 128, c, lane));
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int c = c0 + j + e;
+        const float d = dv[e], a = av[e], tl = tv[e];
+        dl[e] = d * a * (1.f - tl * tl);
+        p.s0[lm(gt, 128, c, lane)] = d * (tl - yv[e]) * a * (1.f - a * inv_dt);
+        p.dyt[lm(gt, 128, c, lane)] = d * (1.f - a);
+      }
+      state_store4(smA, r, c0 + j, make_float4(dl[0], dl[1], dl[2], dl[3]));
+      state_store4(smA, r, c0 + j + 4, make_float4(dl[4], dl[5], dl[6], dl[7]));
+    }
+    publish();
+    image_to_global(smA, p.dL + (size_t)t * p.N * 128, 128, row0, p.N);
     // ---- acc1 = dL Wz[:, :128]   -> TMEM columns 0..127
     gemm_phase(rg, p.Wzh_img, 0, 4, smA, tmem, 0, false, acc, nacc);
-    // ---- bwd_z, and stage dG0 for the first block of the dy GEMM
+    // ---- bwd_z : dG1 -> state tile, dG2 -> s2, dz <- d (1 - b)
 #pragma unroll 1
     for (int cb = 0; cb < 2; ++cb) {
       const int cc = c0 + 32 * cb;
@@ -355,42 +462,41 @@ __global__ void __launch_bounds__(256, 1) k_lem_bwd_tc(const LemBwdParams p) {
       __syncwarp();
       tmem_ld32(tmem + tlane + (uint32_t)cc, v);
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const int col = cc + j;
-        float4 g0 = zero4();
-        if (live) {
-          const size_t o = (size_t)grow * 128 + col;
-          float4 d = add4(ldcg4(p.dz + o), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
-          if (p.gZ) d = add4(d, ldg4(p.gZ + (size_t)t * plane + o));
-          const float4 b = ldg4(g_t + plane + o), zc = ldg4(g_t + 2 * plane + o);
-          const float4 zp = ldg4(p.Z + (size_t)t * plane + o);
-          st4(dG_t + (size_t)grow * 384 + 128 + col,
-              make_float4(d.x * (zc.x - zp.x) * b.x * (1.f - b.x / p.dt), d.y * (zc.y - zp.y) * b.y * (1.f - b.y / p.dt),
-                          d.z * (zc.z - zp.z) * b.z * (1.f - b.z / p.dt), d.w * (zc.w - zp.w) * b.w * (1.f - b.w / p.dt)));
-          st4(dG_t + (size_t)grow * 384 + 256 + col,
-              make_float4(d.x * b.x * (1.f - zc.x * zc.x), d.y * b.y * (1.f - zc.y * zc.y), d.z * b.z * (1.f - zc.z * zc.z),
-                          d.w * b.w * (1.f - zc.w * zc.w)));
-          st4(p.dz + o, make_float4(d.x * (1.f - b.x), d.y * (1.f - b.y), d.z * (1.f - b.z), d.w * (1.f - b.w)));
-          g0 = ldcg4(dG_t + (size_t)grow * 384 + col);      // written by this thread in bwd_y
+      for (int j = 0; j < 32; j += 8) {
+        float dv[8], bv[8], zcv[8], zpv[8], g1[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int c = cc + j + e;
+          dv[e] = __ldcg(p.dzt + lm(gt, 128, c, lane)) + v[j + e];
+          if (gz) dv[e] += __ldg(gz + lm(gt, 128, c, lane));
+          bv[e] = __ldg(g_t + lm(gt, 512, 128 + c, lane));
+          zcv[e] = __ldg(g_t + lm(gt, 512, 256 + c, lane));
+          zpv[e] = __ldg(zprev + lm(gt, 128, c, lane));
         }
-        state_store4(smA, r, col, g0);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int c = cc + j + e;
+          const float d = dv[e], b = bv[e], zc = zcv[e];
+          g1[e] = d * (zc - zpv[e]) * b * (1.f - b * inv_dt);
+          p.s2[lm(gt, 128, c, lane)] = d * b * (1.f - zc * zc);
+          p.dzt[lm(gt, 128, c, lane)] = d * (1.f - b);
+        }
+        state_store4(smA, r, cc + j, make_float4(g1[0], g1[1], g1[2], g1[3]));
+        state_store4(smA, r, cc + j + 4, make_float4(g1[4], g1[5], g1[6], g1[7]));
       }
     }
-    // ---- acc2 = [dG0 | dG1 | dG2] W[:, :128]  -> TMEM columns 128..255, A tile restaged per block
-    for (int blk = 0; blk < 3; ++blk) {
-      if (blk > 0) {
-#pragma unroll 1
-        for (int j = 0; j < 64; j += 4) {
-          const int col = c0 + j;
-          float4 g = live ? ldcg4(dG_t + (size_t)grow * 384 + 128 * blk + col) : zero4();
-          state_store4(smA, r, col, g);
-        }
-      }
-      fence_proxy_async();
-      tc_fence_before();
-      __syncthreads();
-      gemm_phase(rg, p.Wh_img, 4 * blk, 4, smA, tmem, 128, blk != 0, acc, nacc);
-    }
+    // ---- acc2 = [dG1 | dG2 | dG0] W[:, :128]  -> TMEM columns 128..255 (weight chunks 4..7, 8..11, 0..3)
+    publish();
+    image_to_global(smA, dG_t + 128, 384, row0, p.N);
+    gemm_phase(rg, p.Wh_img, 4, 4, smA, tmem, 128, false, acc, nacc);
+    stage_lm(p.s2);
+    publish();
+    image_to_global(smA, dG_t + 256, 384, row0, p.N);
+    gemm_phase(rg, p.Wh_img, 8, 4, smA, tmem, 128, true, acc, nacc);
+    stage_lm(p.s0);
+    publish();
+    image_to_global(smA, dG_t, 384, row0, p.N);
+    gemm_phase(rg, p.Wh_img, 0, 4, smA, tmem, 128, true, acc, nacc);
     // ---- dy += acc2
 #pragma unroll 1
     for (int cb = 0; cb < 2; ++cb) {
@@ -398,13 +504,11 @@ __global__ void __launch_bounds__(256, 1) k_lem_bwd_tc(const LemBwdParams p) {
       float v[32];
       __syncwarp();
       tmem_ld32(tmem + tlane + (uint32_t)(128 + cc), v);
-      if (live) {
+      float cur[32];
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const size_t o = (size_t)grow * 128 + cc + j;
-          st4(p.dy + o, add4(ldcg4(p.dy + o), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3])));
-        }
-      }
+      for (int j = 0; j < 32; ++j) cur[j] = __ldcg(p.dyt + lm(gt, 128, cc + j, lane));
+#pragma unroll
+      for (int j = 0; j < 32; ++j) p.dyt[lm(gt, 128, cc + j, lane)] = cur[j] + v[j];
     }
     tc_fence_before();
     __syncthreads();
@@ -418,41 +522,45 @@ __global__ void __launch_bounds__(256, 1) k_lem_bwd_tc(const LemBwdParams p) {
 
 using namespace msmp;
 
-// inp [T][N][32]; Wt_in = rows 128.. of the k-major W^T pack ([ninp..][384]); Wzt_in likewise ([..][128]);
-// pre [T][N][512] scratch; Wimg / Wzimg = images of the STATE rows only (Wt[:128], Wzt[:128]).
+extern "C" int msmp_lem_debug_ticks(long long* host_out) {
+  return cudaMemcpyFromSymbol(host_out, g_lem_dbg, sizeof(long long) * 64) == cudaSuccess ? 0 : -2;
+}
+
 extern "C" int msmp_lem_tc_fwd(const float* inp, int ninp, const float* Wt_in, const float* Wzt_in, const float* Wimg,
                                const float* Wzimg, const float* bias, const float* bias_z, float* pre, float* Y,
-                               float* Z, float* gates, float dt, int T, int N, cudaStream_t stream) {
-  if (T < 0 || N < 0 || ninp < 0 || ninp > 32) return MSMP_ERR_ARG;
+                               float* Z, float* Yt, float* Zt, float* gates, float dt, int T, int N, int Npad,
+                               cudaStream_t stream) {
+  if (T < 0 || N < 0 || ninp < 0 || ninp > 8 || Npad < N || (Npad & 127)) return MSMP_ERR_ARG;
   if (T == 0 || N == 0) return MSMP_OK;
-  const size_t rows = (size_t)T * N;
-  k_lem_inproj<<<(unsigned)((rows * 128 + 255) / 256), 256, 0, stream>>>(inp, Wt_in, Wzt_in, bias, bias_z, pre, rows, ninp);
+  const size_t tiles = (size_t)T * (Npad / 32);
+  k_lem_inproj<<<(unsigned)((4 * tiles + 7) / 8), 256, 0, stream>>>(inp, Wt_in, Wzt_in, bias, bias_z, pre, T, N, Npad, ninp);
   MSMP_CHECK_LAUNCH();
-  LemFwdParams p{pre, Wimg, Wzimg, Y, Z, gates, dt, T, N};
+  LemFwdParams p{pre, Wimg, Wzimg, Y, Z, Yt, Zt, gates, dt, T, N, Npad};
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(k_lem_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_SMEM) != cudaSuccess)
       return MSMP_ERR_CUDA;
     attr_set = true;
   }
-  k_lem_fwd_tc<<<(N + 127) / 128, 256, LT_SMEM, stream>>>(p);
+  k_lem_fwd_tc<<<Npad / 128, 256, LT_SMEM, stream>>>(p);
   MSMP_CHECK_LAUNCH();
   return MSMP_OK;
 }
 
-extern "C" int msmp_lem_tc_bwd(const float* Wzh_img, const float* Wh_img, const float* Y, const float* Z,
-                               const float* gates, const float* gY, const float* gZ, float* dG, float* dL, float* dy,
-                               float* dz, float dt, int T, int N, cudaStream_t stream) {
-  if (T < 0 || N < 0) return MSMP_ERR_ARG;
+extern "C" int msmp_lem_tc_bwd(const float* Wzh_img, const float* Wh_img, const float* Yt, const float* Zt,
+                               const float* gates, const float* gYt, const float* gZt, int g_last_only, float* dG,
+                               float* dL, float* dyt, float* dzt, float* s0, float* s2, float dt, int T, int N, int Npad,
+                               cudaStream_t stream) {
+  if (T < 0 || N < 0 || Npad < N || (Npad & 127)) return MSMP_ERR_ARG;
   if (T == 0 || N == 0) return MSMP_OK;
-  LemBwdParams p{Wzh_img, Wh_img, Y, Z, gates, gY, gZ, dG, dL, dy, dz, dt, T, N};
+  LemBwdParams p{Wzh_img, Wh_img, Yt, Zt, gates, gYt, gZt, g_last_only, dG, dL, dyt, dzt, s0, s2, dt, T, N, Npad};
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(k_lem_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_SMEM) != cudaSuccess)
       return MSMP_ERR_CUDA;
     attr_set = true;
   }
-  k_lem_bwd_tc<<<(N + 127) / 128, 256, LT_SMEM, stream>>>(p);
+  k_lem_bwd_tc<<<Npad / 128, 256, LT_SMEM, stream>>>(p);
   MSMP_CHECK_LAUNCH();
   return MSMP_OK;
 }

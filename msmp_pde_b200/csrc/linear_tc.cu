@@ -159,9 +159,20 @@ __global__ void __launch_bounds__(256, 1) k_linear_tc(const LinTcParams p) {
     __syncwarp();
     tmem_ld32(tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)colbase, v);
     if (row < p.M) {
+      const int colb = n0 + colbase;
+      // issue every global load of this 32-column block first (the epilogue is latency bound otherwise)
+      float4 zm[8], rr[8];
+      if (p.Zmul) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) zm[j] = (colb + 4 * j < p.Nout) ? ldg4(p.Zmul + (size_t)row * p.ldz + colb + 4 * j) : zero4();
+      }
+      if (p.R) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) rr[j] = (colb + 4 * j < p.Nout) ? ldg4(p.R + (size_t)row * p.ldr + colb + 4 * j) : zero4();
+      }
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
-        const int col = n0 + colbase + j;
+        const int col = colb + j;
         if (col >= p.Nout) continue;
         float4 z = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
         if (p.bias) z = add4(z, ldg4(p.bias + col));
@@ -175,12 +186,12 @@ __global__ void __launch_bounds__(256, 1) k_linear_tc(const LinTcParams p) {
           z.w = fmaf(sv[q], w.w, z.w);
         }
         if (p.Zmul) {
-          float4 zz = ldg4(p.Zmul + (size_t)row * p.ldz + col);
+          const float4 zz = zm[j >> 2];
           z = mul4(z, make_float4(dswish(zz.x), dswish(zz.y), dswish(zz.z), dswish(zz.w)));
         }
         if (p.Ypre) st4(p.Ypre + (size_t)row * p.ldpre + col, z);
         if (p.act) z = swish4(z);
-        if (p.R) z = add4(z, ldg4(p.R + (size_t)row * p.ldr + col));
+        if (p.R) z = add4(z, rr[j >> 2]);
         st4(p.Y + (size_t)row * p.ldy + col, z);
       }
     }

@@ -20,7 +20,8 @@ constexpr int WT_STAGE_BYTES = 4 * WT_OP_BYTES;            // X_hi, X_lo, dY_hi,
 constexpr int WT_SMEM = 2 * WT_STAGE_BYTES + 1024 + 256 + 8 * 8 * 128 * 4;
 
 struct WgradTcParams {
-  const float* X; int ldx; int K; int xswish;
+  const float* X; int ldx; int K; int xswish;     // K = rows of dWt in total
+  const float* X1; int ldx1; int K0;              // optional second column block of X: columns K0.. come from X1
   const float* dY; int lddy; int Nout;
   const float* side; int lds; int r; int has_bias;
   float* part;         // [S][K][Nout]
@@ -45,6 +46,12 @@ __global__ void __launch_bounds__(256, 1) k_wgrad_tc(const WgradTcParams p) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int split = blockIdx.x;
   const int k0 = blockIdx.y * 128, n0 = blockIdx.z * 128;
+  // column block of X handled by this CTA: [X | X1] concatenated at K0 (K0 % 128 == 0 when X1 is given)
+  const bool second = p.X1 != nullptr && k0 >= p.K0;
+  const float* Xb = second ? p.X1 : p.X;
+  const int ldxb = second ? p.ldx1 : p.ldx;
+  const int kloc = second ? k0 - p.K0 : k0;                 // first column inside the selected block
+  const int kvalid = (second ? p.K - p.K0 : (p.X1 ? p.K0 : p.K)) - kloc;   // valid columns from kloc on
   const int m_begin = split * p.rows_per_split;
   const int m_end = min(p.M, m_begin + p.rows_per_split);
   const int nchunks = (m_end > m_begin) ? (m_end - m_begin + WT_CHUNK - 1) / WT_CHUNK : 0;
@@ -75,7 +82,7 @@ __global__ void __launch_bounds__(256, 1) k_wgrad_tc(const WgradTcParams p) {
       const int idx = tid + 256 * i;
       const int m = mb + (idx >> 5), c4 = idx & 31;
       const bool okm = m < m_end;
-      px[i] = (okm && k0 + 4 * c4 < p.K) ? ldg4(p.X + (size_t)m * p.ldx + k0 + 4 * c4) : zero4();
+      px[i] = (okm && 4 * c4 < kvalid) ? ldg4(Xb + (size_t)m * ldxb + kloc + 4 * c4) : zero4();
       py[i] = (okm && n0 + 4 * c4 < p.Nout) ? ldg4(p.dY + (size_t)m * p.lddy + n0 + 4 * c4) : zero4();
     }
   };
@@ -178,16 +185,34 @@ __global__ void __launch_bounds__(256, 1) k_wgrad_tc(const WgradTcParams p) {
 
 using namespace msmp;
 
+extern "C" int msmp_linear_wgrad_tc2(const float* X, int ldx, int K0, const float* X1, int ldx1, int K1, int xswish,
+                                     const float* dY, int lddy, int Nout, const float* side, int lds, int r,
+                                     int has_bias, float* dWt, float* dWside, int accumulate, int M, void* workspace,
+                                     size_t ws_bytes, cudaStream_t stream);
+
 extern "C" int msmp_linear_wgrad_tc(const float* X, int ldx, int K, int xswish, const float* dY, int lddy, int Nout,
                                     const float* side, int lds, int r, int has_bias, float* dWt, float* dWside,
                                     int accumulate, int M, void* workspace, size_t ws_bytes, cudaStream_t stream) {
+  return msmp_linear_wgrad_tc2(X, ldx, K, nullptr, 0, 0, xswish, dY, lddy, Nout, side, lds, r, has_bias, dWt, dWside,
+                               accumulate, M, workspace, ws_bytes, stream);
+}
+
+// dWt[K0 + K1, Nout] = [X | X1]^T dY : the two column blocks of the (virtual) concatenation come from different
+// tensors (e.g. [h | agg] for update_net_1, [h | u] for the P|Q projection); K0 % 128 == 0 when X1 is given.
+extern "C" int msmp_linear_wgrad_tc2(const float* X, int ldx, int K0, const float* X1, int ldx1, int K1, int xswish,
+                                     const float* dY, int lddy, int Nout, const float* side, int lds, int r,
+                                     int has_bias, float* dWt, float* dWside, int accumulate, int M, void* workspace,
+                                     size_t ws_bytes, cudaStream_t stream) {
+  const int K = K0 + (X1 ? K1 : 0);
   if (K <= 0 || (K & 3) || Nout <= 0 || (Nout & 3) || (ldx & 3) || (lddy & 3) || r < 0 || r + has_bias > 8)
     return MSMP_ERR_ARG;
+  if (X1 && ((K0 & 127) || (K1 & 3) || (ldx1 & 3) || K1 <= 0)) return MSMP_ERR_ARG;
   const int nside = (side ? r : 0) + (has_bias ? 1 : 0);
   if (ws_bytes < msmp_linear_wgrad_workspace(M, K, Nout, nside)) return MSMP_ERR_WORKSPACE;
   const int S = msmp_linear_wgrad_splits(M, K, Nout);
   WgradTcParams p{};
   p.X = X; p.ldx = ldx; p.K = K; p.xswish = xswish; p.dY = dY; p.lddy = lddy; p.Nout = Nout;
+  p.X1 = X1; p.ldx1 = ldx1; p.K0 = K0;
   p.side = side; p.lds = lds; p.r = side ? r : 0; p.has_bias = has_bias ? 1 : 0;
   p.part = reinterpret_cast<float*>(workspace);
   p.part_side = p.part + (size_t)S * K * Nout;

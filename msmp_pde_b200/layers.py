@@ -126,8 +126,7 @@ class _LayerCoreFn(torch.autograd.Function):
         dz3 = ops.linear_fwd([dz4], pk.W4d, Zmul=z3)
         # update_net_1
         dW3t = torch.empty(2 * H, H, dtype=torch.float32, device=dev)
-        _, dW3s = ops.linear_wgrad(h, dz3, side=ft.side[:, 1:], r=V, has_bias=True, dWt=dW3t[:H])
-        ops.linear_wgrad(agg, dz3, dWt=dW3t[H:])
+        _, dW3s = ops.linear_wgrad(h, dz3, X1=agg, side=ft.side[:, 1:], r=V, has_bias=True, dWt=dW3t)
         dcat = ops.linear_fwd([dz3], pk.W3hx)                          # [N,256] = [dh (via x) | dagg]
         # message path
         dPQ = torch.empty(N, 2 * H, dtype=torch.float32, device=dev)
@@ -135,8 +134,7 @@ class _LayerCoreFn(torch.autograd.Function):
         ops.segment_reduce(dz1, topo.colptr, perm=topo.csc_perm, out=dPQ[:, H:], N=N)
         Kp = pk.Wpq_t.shape[0]
         dWpq_t = torch.empty(Kp, 2 * H, dtype=torch.float32, device=dev)
-        _, dWs = ops.linear_wgrad(h, dPQ, side=ft.side, r=1 + V, has_bias=True, dWt=dWpq_t[:H])
-        ops.linear_wgrad(ft.upad, dPQ, dWt=dWpq_t[H:])
+        _, dWs = ops.linear_wgrad(h, dPQ, X1=ft.upad, side=ft.side, r=1 + V, has_bias=True, dWt=dWpq_t)
         dh = ops.linear_fwd([dPQ], pk.W1hq, R=dcat[:, :H])
         if aux.final:
             dh = dh + dy

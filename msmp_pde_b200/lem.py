@@ -24,10 +24,12 @@ from .layers import H, pad32
 
 
 class _LEMFn(torch.autograd.Function):
-    """All T steps through msmp_linear_fwd (gate GEMMs) + msmp_lem_gate_* (fused gate math)."""
+    """All T steps.  tensor-core mode: one persistent kernel per direction (msmp_lem_tc_*); otherwise one
+    msmp_linear_fwd + one fused gate kernel per GEMM and step.  ``last_only`` returns (y_T, z_T) instead of the
+    whole history (what LEM / LEMS consume, models_gnn.py:340-342,354-357)."""
 
     @staticmethod
-    def forward(ctx, inputs, weights, weights_lin_z, bias, bias_lin_z, y0, z0, dt, packs):
+    def forward(ctx, inputs, weights, weights_lin_z, bias, bias_lin_z, y0, z0, dt, packs, last_only):
         T, N, ninp = inputs.shape
         dev = inputs.device
         ip = pad32(ninp)
@@ -37,26 +39,29 @@ class _LEMFn(torch.autograd.Function):
         Y = torch.empty(T + 1, N, H, dtype=torch.float32, device=dev)
         Z = torch.empty(T + 1, N, H, dtype=torch.float32, device=dev)
         Y[0], Z[0] = y0, z0
-        gates = torch.empty(T, 4, N, H, dtype=torch.float32, device=dev)   # dt_bar, dt_z, tanh(G2), tanh(L)
-        G = torch.empty(N, 3 * H, dtype=torch.float32, device=dev)
-        L = torch.empty(N, H, dtype=torch.float32, device=dev)
-        if ops.GEMM_MODE == "tc" and ops.LEM_PERSISTENT and ip == 32:
-            ops.lem_tc_fwd(inp, ninp, Wt, Wzt, Wt_h, Wzt_h, bias, bias_lin_z, Y, Z, gates, dt)
+        persistent = ops.GEMM_MODE == "tc" and ops.LEM_PERSISTENT and ip == 32 and ninp <= 8
+        if persistent:
+            Yt, Zt, gates = ops.lem_tc_fwd(inp, ninp, Wt, Wzt, Wt_h, Wzt_h, bias, bias_lin_z, Y, Z, dt)
+            ctx.save_for_backward(inp, Y, Z, gates, Yt, Zt)
+        else:
+            gates = torch.empty(T, 4, N, H, dtype=torch.float32, device=dev)   # dt_bar, dt_z, tanh(G2), tanh(L)
+            G = torch.empty(N, 3 * H, dtype=torch.float32, device=dev)
+            L = torch.empty(N, H, dtype=torch.float32, device=dev)
+            for t in range(T):
+                ops.linear_fwd([Y[t], inp[t]], Wt, bias=bias, out=G)
+                ops.lem_gate_z(G, Z[t], dt, gates[t], Z[t + 1])
+                ops.linear_fwd([Z[t + 1], inp[t]], Wzt, bias=bias_lin_z, out=L)
+                ops.lem_gate_y(L, Y[t], gates[t], Y[t + 1])
             ctx.save_for_backward(inp, Y, Z, gates)
-            ctx.dt, ctx.ninp, ctx.packs = dt, ninp, packs
-            return Y[1:], Z[1:]
-        for t in range(T):
-            ops.linear_fwd([Y[t], inp[t]], Wt, bias=bias, out=G)
-            ops.lem_gate_z(G, Z[t], dt, gates[t], Z[t + 1])
-            ops.linear_fwd([Z[t + 1], inp[t]], Wzt, bias=bias_lin_z, out=L)
-            ops.lem_gate_y(L, Y[t], gates[t], Y[t + 1])
-        ctx.save_for_backward(inp, Y, Z, gates)
-        ctx.dt, ctx.ninp, ctx.packs = dt, ninp, packs
+        ctx.dt, ctx.ninp, ctx.packs, ctx.persistent, ctx.last_only = dt, ninp, packs, persistent, last_only
+        if last_only:
+            return Y[T], Z[T]
         return Y[1:], Z[1:]
 
     @staticmethod
     def backward(ctx, gY, gZ):
-        inp, Y, Z, gates = ctx.saved_tensors
+        saved = ctx.saved_tensors
+        inp, Y, Z, gates = saved[:4]
         dt, ninp = ctx.dt, ctx.ninp
         _, _, Wh, Wzh, _, _ = ctx.packs
         T, N, ip = inp.shape
@@ -64,34 +69,41 @@ class _LEMFn(torch.autograd.Function):
         gY, gZ = gY.contiguous(), gZ.contiguous()
         dG = torch.empty(T, N, 3 * H, dtype=torch.float32, device=dev)
         dL = torch.empty(T, N, H, dtype=torch.float32, device=dev)
-        dy = torch.zeros(N, H, dtype=torch.float32, device=dev)      # carried d/dy_t
-        dz = torch.zeros(N, H, dtype=torch.float32, device=dev)      # carried d/dz_t
-        dz_tot = torch.empty(N, H, dtype=torch.float32, device=dev)
-        fused = ops.GEMM_MODE == "tc" and ops.LEM_PERSISTENT and ip == 32
-        if fused:
-            ops.lem_tc_bwd(Wzh, Wh, Y, Z, gates, gY, gZ, dG, dL, dy, dz, dt)
-        for t in (range(T - 1, -1, -1) if not fused else ()):
-            # through y_t = (1-a) y_{t-1} + a tanh(L):  dL, dG0, dy <- dy*(1-a)
-            ops.lem_bwd_y(dy, gY[t], Y[t], gates[t], dt, dL[t], dG[t])
-            # dz_t total = carried + dL Wz[:, :H]  (+ external gZ[t], added inside lem_bwd_z)
-            ops.linear_fwd([dL[t]], Wzh, R=dz, out=dz_tot)
-            # through z_t = (1-b) z_{t-1} + b tanh(G2): dG1, dG2, dz <- d*(1-b)
-            ops.lem_bwd_z(dz_tot, gZ[t], Z[t], gates[t], dt, dG[t], dz)
-            # dy_{t-1} += dG W[:, :H]
-            ops.linear_fwd([dG[t]], Wh, R=dy, out=dy)
+        if ctx.persistent:
+            Yt, Zt = saved[4], saved[5]
+            Npad = Yt.shape[1] * 32
+            dyt, dzt = ops.lem_tc_bwd(Wzh, Wh, Yt, Zt, gates, ops.to_lane_major(gY, Npad), ops.to_lane_major(gZ, Npad),
+                                      ctx.last_only, dG, dL, dt, N)
+            dy, dz = ops.from_lane_major(dyt, N), ops.from_lane_major(dzt, N)
+        else:
+            if ctx.last_only:
+                gy_full = torch.zeros(T, N, H, dtype=torch.float32, device=dev)
+                gz_full = torch.zeros(T, N, H, dtype=torch.float32, device=dev)
+                gy_full[T - 1], gz_full[T - 1] = gY, gZ
+                gY, gZ = gy_full, gz_full
+            dy = torch.zeros(N, H, dtype=torch.float32, device=dev)      # carried d/dy_t
+            dz = torch.zeros(N, H, dtype=torch.float32, device=dev)      # carried d/dz_t
+            dz_tot = torch.empty(N, H, dtype=torch.float32, device=dev)
+            for t in range(T - 1, -1, -1):
+                # through y_t = (1-a) y_{t-1} + a tanh(L):  dL, dG0, dy <- dy*(1-a)
+                ops.lem_bwd_y(dy, gY[t], Y[t], gates[t], dt, dL[t], dG[t])
+                # dz_t total = carried + dL Wz[:, :H]  (+ external gZ[t], added inside lem_bwd_z)
+                ops.linear_fwd([dL[t]], Wzh, R=dz, out=dz_tot)
+                # through z_t = (1-b) z_{t-1} + b tanh(G2): dG1, dG2, dz <- d*(1-b)
+                ops.lem_bwd_z(dz_tot, gZ[t], Z[t], gates[t], dt, dG[t], dz)
+                # dy_{t-1} += dG W[:, :H]
+                ops.linear_fwd([dG[t]], Wh, R=dy, out=dy)
         # weight gradients over all steps at once (M = T*N rows)
         Kp = H + ip
         dWt = torch.empty(Kp, 3 * H, dtype=torch.float32, device=dev)
         dGf, dLf = dG.view(T * N, 3 * H), dL.view(T * N, H)
         inpf = inp.view(T * N, ip)
-        _, dbias = ops.linear_wgrad(Y[:T].view(T * N, H), dGf, has_bias=True, dWt=dWt[:H])
-        ops.linear_wgrad(inpf, dGf, dWt=dWt[H:])
+        _, dbias = ops.linear_wgrad(Y[:T].view(T * N, H), dGf, X1=inpf, has_bias=True, dWt=dWt)
         dWzt = torch.empty(Kp, H, dtype=torch.float32, device=dev)
-        _, dbz = ops.linear_wgrad(Z[1:].reshape(T * N, H), dLf, has_bias=True, dWt=dWzt[:H])
-        ops.linear_wgrad(inpf, dLf, dWt=dWzt[H:])
+        _, dbz = ops.linear_wgrad(Z[1:].reshape(T * N, H), dLf, X1=inpf, has_bias=True, dWt=dWzt)
         dW = torch.cat([dWt[:H].t(), dWt[H:H + ninp].t()], 1)
         dWz = torch.cat([dWzt[:H].t(), dWzt[H:H + ninp].t()], 1)
-        return None, dW, dWz, dbias[0], dbz[0], dy, dz, None, None
+        return None, dW, dWz, dbias[0], dbz[0], dy, dz, None, None, None
 
 
 class LEMcuda(nn.Module):
@@ -134,7 +146,7 @@ class LEMcuda(nn.Module):
         for w in self.parameters():
             w.data.uniform_(-stdv, +stdv)
 
-    def forward(self, input, states=None):
+    def forward(self, input, states=None, last_only=False):
         if not input.is_cuda:
             raise RuntimeError("msmp_pde_b200 LEM runs on CUDA only (no CPU fallback)")
         x = input.detach().float().contiguous()
@@ -144,7 +156,7 @@ class LEMcuda(nn.Module):
         else:
             y, z = states[0].float().contiguous(), states[1].float().contiguous()
         return _LEMFn.apply(x, self.weights, self.weights_lin_z, self.bias, self.bias_lin_z, y, z, self.dt,
-                            self.packs())
+                            self.packs(), last_only)
 
 
 class LEM(nn.Module):
@@ -156,8 +168,8 @@ class LEM(nn.Module):
         self.rnn = LEMcuda(ninp, nhid, dt)
 
     def forward(self, input):
-        all_y, all_z = self.rnn(input)
-        return all_y[-1]
+        y_last, _ = self.rnn(input, last_only=True)
+        return y_last
 
 
 class LEMS(nn.Module):
@@ -170,9 +182,9 @@ class LEMS(nn.Module):
         self.states = None
 
     def forward(self, input):
-        all_y, all_z = self.rnn(input, self.states)
-        self.states = (all_y[-1], all_z[-1])
-        return all_y[-1]
+        y_last, z_last = self.rnn(input, self.states, last_only=True)
+        self.states = (y_last, z_last)
+        return y_last
 
     def reset_states(self):
         self.states = None

@@ -78,7 +78,7 @@ def _p(t):
 # Tensor-core (tcgen05 3xTF32) execution of the dense layers.  "ffma" keeps the exact-fp32 CUDA-core kernels.
 GEMM_MODE = "tc"
 # Persistent (all-T-steps-in-one-launch) LEM kernels; False = one GEMM + one gate kernel per step.
-LEM_PERSISTENT = False
+LEM_PERSISTENT = True
 _IMG_CACHE: dict = {}
 
 
@@ -182,26 +182,40 @@ def linear_tc_fwd(segs, img, Nout, bias=None, side=None, r=0, Wside=None, Zmul=N
 
 
 def linear_wgrad(X, dY, K=None, xswish=False, side=None, r=0, has_bias=False, dWt=None, dWside=None,
-                 accumulate=False):
-    """dWt[K, Nout] = X^T dY ; dWside[r(+1), Nout] = [side|1]^T dY."""
+                 accumulate=False, X1=None):
+    """dWt[K, Nout] = [X | X1]^T dY ; dWside[r(+1), Nout] = [side|1]^T dY.  X1 (optional) supplies the columns
+    after X's (X.shape[1] % 128 == 0), e.g. [h | agg] or [h | u_padded], without materialising the concatenation."""
     _req(X, "X")
     _req(dY, "dY")
     M, Nout = dY.shape
-    K = X.shape[1] if K is None else K
+    K0 = X.shape[1] if K is None else K
+    K1 = X1.shape[1] if X1 is not None else 0
+    Kt = K0 + K1
     nside = (r if side is not None else 0) + int(has_bias)
     dev = dY.device
     if dWt is None:
-        dWt = torch.empty(K, Nout, dtype=torch.float32, device=dev)
+        dWt = torch.empty(Kt, Nout, dtype=torch.float32, device=dev)
     if nside and dWside is None:
         dWside = torch.empty(nside, Nout, dtype=torch.float32, device=dev)
-    nbytes = lib.msmp_linear_wgrad_workspace(M, K, Nout, nside)
-    ws = _workspace(nbytes, dev)
-    fn = lib.msmp_linear_wgrad_tc if GEMM_MODE == "tc" else lib.msmp_linear_wgrad
-    check(fn(X.data_ptr(), _ld(X), K, int(xswish), dY.data_ptr(), _ld(dY), Nout, _p(side),
-                                _ld(side) if side is not None else 0, r if side is not None else 0, int(has_bias),
+    sargs = (_p(side), _ld(side) if side is not None else 0, r if side is not None else 0, int(has_bias))
+    if GEMM_MODE == "tc":
+        ws = _workspace(lib.msmp_linear_wgrad_workspace(M, Kt, Nout, nside), dev)
+        check(lib.msmp_linear_wgrad_tc2(X.data_ptr(), _ld(X), K0, _p(X1), _ld(X1) if X1 is not None else 0, K1,
+                                        int(xswish), dY.data_ptr(), _ld(dY), Nout, *sargs, dWt.data_ptr(), _p(dWside),
+                                        int(accumulate), M, ws.data_ptr(), ws.numel(), _stream()),
+              "msmp_linear_wgrad_tc2")
+        _count(2)
+        return dWt, dWside
+    ws = _workspace(lib.msmp_linear_wgrad_workspace(M, max(K0, K1), Nout, nside), dev)
+    check(lib.msmp_linear_wgrad(X.data_ptr(), _ld(X), K0, int(xswish), dY.data_ptr(), _ld(dY), Nout, *sargs,
                                 dWt.data_ptr(), _p(dWside), int(accumulate), M, ws.data_ptr(), ws.numel(), _stream()),
           "msmp_linear_wgrad")
     _count(2)
+    if X1 is not None:
+        check(lib.msmp_linear_wgrad(X1.data_ptr(), _ld(X1), K1, int(xswish), dY.data_ptr(), _ld(dY), Nout, 0, 0, 0, 0,
+                                    dWt[K0:].data_ptr(), 0, int(accumulate), M, ws.data_ptr(), ws.numel(), _stream()),
+              "msmp_linear_wgrad")
+        _count(2)
     return dWt, dWside
 
 
@@ -372,21 +386,55 @@ def decoder_bwd(dout, h, za, w1, w2, dt, geom):
     return dh, dW
 
 
-def lem_tc_fwd(inp, ninp, Wt, Wzt, Wt_h, Wzt_h, bias, bias_z, Y, Z, gates, dt):
+def to_lane_major(x: torch.Tensor, Npad: int) -> torch.Tensor:
+    """[..., N, C] row-major -> [..., Npad/32, C, 32] lane-major (rows zero-padded to Npad)."""
+    *lead, N, C = x.shape
+    if N != Npad:
+        xp = x.new_zeros(*lead, Npad, C)
+        xp[..., :N, :] = x
+        x = xp
+    return x.reshape(*lead, Npad // 32, 32, C).transpose(-1, -2).contiguous()
+
+
+def from_lane_major(x: torch.Tensor, N: int) -> torch.Tensor:
+    """[..., Npad/32, C, 32] lane-major -> [..., N, C] row-major."""
+    *lead, nt, C, _ = x.shape
+    return x.transpose(-1, -2).reshape(*lead, nt * 32, C)[..., :N, :].contiguous()
+
+
+def lem_tc_fwd(inp, ninp, Wt, Wzt, Wt_h, Wzt_h, bias, bias_z, Y, Z, dt):
     """Persistent tensor-core LEM forward (input projection + all T steps, two launches).
-    Wt / Wzt: k-major packs [160, 384] / [160, 128]; Wt_h / Wzt_h: their state rows (stable tensors, for the images)."""
+    Wt / Wzt: k-major packs [160, 384] / [160, 128]; Wt_h / Wzt_h: their state rows (stable tensors, for the images).
+    Y, Z: row-major [T+1, N, 128] with slab 0 set.  Returns the lane-major (Yt, Zt, gates) kept for the backward."""
     T, N = inp.shape[0], inp.shape[1]
-    pre = torch.empty(T, N, 512, dtype=torch.float32, device=inp.device)
+    Npad = (N + 127) // 128 * 128
+    dev = inp.device
+    pre = torch.empty(T, Npad // 32, 512, 32, dtype=torch.float32, device=dev)
+    gates = torch.empty(T, Npad // 32, 512, 32, dtype=torch.float32, device=dev)
+    Yt = torch.empty(T + 1, Npad // 32, H, 32, dtype=torch.float32, device=dev)
+    Zt = torch.empty(T + 1, Npad // 32, H, 32, dtype=torch.float32, device=dev)
+    Yt[0] = to_lane_major(Y[0], Npad)
+    Zt[0] = to_lane_major(Z[0], Npad)
     check(lib.msmp_lem_tc_fwd(inp.data_ptr(), int(ninp), Wt[H:].data_ptr(), Wzt[H:].data_ptr(),
                               _cached_images(Wt_h).data_ptr(), _cached_images(Wzt_h).data_ptr(), bias.data_ptr(),
-                              bias_z.data_ptr(), pre.data_ptr(), Y.data_ptr(), Z.data_ptr(), gates.data_ptr(),
-                              float(dt), T, N, _stream()), "msmp_lem_tc_fwd")
+                              bias_z.data_ptr(), pre.data_ptr(), Y.data_ptr(), Z.data_ptr(), Yt.data_ptr(),
+                              Zt.data_ptr(), gates.data_ptr(), float(dt), T, N, Npad, _stream()), "msmp_lem_tc_fwd")
     _count(2)
+    return Yt, Zt, gates
 
 
-def lem_tc_bwd(Wzh, Wh, Y, Z, gates, gY, gZ, dG, dL, dy, dz, dt):
-    T, N = gates.shape[0], gates.shape[2]
-    check(lib.msmp_lem_tc_bwd(_cached_images(Wzh).data_ptr(), _cached_images(Wh).data_ptr(), Y.data_ptr(),
-                              Z.data_ptr(), gates.data_ptr(), _p(gY), _p(gZ), dG.data_ptr(), dL.data_ptr(),
-                              dy.data_ptr(), dz.data_ptr(), float(dt), T, N, _stream()), "msmp_lem_tc_bwd")
+def lem_tc_bwd(Wzh, Wh, Yt, Zt, gates, gYt, gZt, last_only, dG, dL, dt, N):
+    """Returns the lane-major gradients (dyt, dzt) wrt the initial state; fills dG [T,N,384], dL [T,N,128]."""
+    T, nt = gates.shape[0], gates.shape[1]
+    Npad = nt * 32
+    dev = gates.device
+    dyt = torch.zeros(nt, H, 32, dtype=torch.float32, device=dev)
+    dzt = torch.zeros(nt, H, 32, dtype=torch.float32, device=dev)
+    s0 = torch.empty(nt, H, 32, dtype=torch.float32, device=dev)
+    s2 = torch.empty(nt, H, 32, dtype=torch.float32, device=dev)
+    check(lib.msmp_lem_tc_bwd(_cached_images(Wzh).data_ptr(), _cached_images(Wh).data_ptr(), Yt.data_ptr(),
+                              Zt.data_ptr(), gates.data_ptr(), _p(gYt), _p(gZt), int(bool(last_only)), dG.data_ptr(),
+                              dL.data_ptr(), dyt.data_ptr(), dzt.data_ptr(), s0.data_ptr(), s2.data_ptr(), float(dt),
+                              T, N, Npad, _stream()), "msmp_lem_tc_bwd")
     _count(1)
+    return dyt, dzt

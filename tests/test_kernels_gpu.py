@@ -134,6 +134,20 @@ def test_linear_wgrad(dev, gemm_mode, M, K, Nout):
     assert torch.equal(dWt, dWt2)
 
 
+def test_linear_wgrad_two_blocks(dev, gemm_mode):
+    """[X | X1]^T dY without materialising the concatenation (update_net_1: [h | agg]; P|Q projection: [h | u])."""
+    from msmp_pde_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    M = 3000
+    X, X1, dY = torch.randn(M, 128, generator=g), torch.randn(M, 64, generator=g), torch.randn(M, 256, generator=g)
+    side = torch.randn(M, 8, generator=g)
+    dWt, dWs = ops.linear_wgrad(X.to(dev), dY.to(dev), X1=X1.to(dev), side=side.to(dev), r=4, has_bias=True)
+    ref = torch.cat([X, X1], 1).double().t() @ dY.double()
+    refS = torch.cat([side.double()[:, :4], torch.ones(M, 1, dtype=torch.float64)], 1).t() @ dY.double()
+    assert dWt.shape == (192, 256)
+    assert rel_err(dWt, ref) < TOL and rel_err(dWs, refS) < TOL
+
+
 def _edge_inputs(sizes, deg, seed, hub, dev):
     from msmp_pde_b200.graph import build_topology
     ei, batch = _graph(sizes, deg, seed, hub)
@@ -278,3 +292,35 @@ def _lem_check(dev, lem_forward, LEMcuda):
     assert rel_err(zs, zr) < TOL
     for p, q in zip((rnn.weights, rnn.weights_lin_z, rnn.bias, rnn.bias_lin_z), ps):
         assert rel_err(p.grad, q.grad) < TOL
+
+
+@pytest.mark.parametrize("persistent", [False, True])
+def test_lem_module_last_state(dev, persistent):
+    """LEM / LEMS path (only y_T, z_T leave the op) incl. a carried initial state, vs the float64 oracle."""
+    from oracle import models as om
+    from msmp_pde_b200 import ops
+    from msmp_pde_b200.lem import LEMS
+    prev = ops.LEM_PERSISTENT
+    ops.LEM_PERSISTENT = persistent
+    try:
+        torch.manual_seed(1)
+        T, N, ninp = 5, 300, 4
+        mod = LEMS(ninp, 128).to(dev)
+        torch.set_default_dtype(torch.float64)
+        ref = om.LEMS(ninp, 128)
+        ref.load_state_dict({k: v.double().cpu() for k, v in mod.state_dict().items()})
+        x1, x2 = torch.randn(T, N, ninp), torch.randn(T, N, ninp)
+        w = torch.randn(N, 128)
+        out = mod(x2.float().to(dev)) if False else None
+        mod.reset_states()
+        h1 = mod(x1.float().to(dev))
+        h2 = mod(x2.float().to(dev))          # second call starts from the carried (y, z)
+        ((h1 + h2) * w.float().to(dev)).sum().backward()
+        r1 = ref(x1)
+        r2 = ref(x2)
+        ((r1 + r2) * w).sum().backward()
+        assert rel_err(h2, r2) < TOL
+        for (n, p_), (_, q) in zip(mod.named_parameters(), ref.named_parameters()):
+            assert rel_err(p_.grad, q.grad) < TOL, n
+    finally:
+        ops.LEM_PERSISTENT = prev
