@@ -57,6 +57,13 @@ int msmp_linear_tc_fwd(const float* const* A, const int* lda, const int* ka, con
                        int ldws, const float* Zmul, int ldz, float* Ypre, int ldpre, int act, const float* R,
                        int ldr, float* Y, int ldy, int M, int Nout, cudaStream_t stream);
 
+/* One launch packs any number of weight blocks into tile images / plain side arrays.  jobs_dev: device array of
+ * records {const float* src; float* dst; int ld, transpose; float sign; int kvalid, nvalid, nchunks, kind, ldd}
+ * (msmp_pack_job_bytes() bytes each).  kind 0: dst[chunk][hi|lo][4096] images of Wt[k][n] = sign * (transpose ?
+ * src[n*ld + k] : src[k*ld + n]) (zero outside kvalid x nvalid);  kind 1: dst[q*ldd + n] = sign * src[n*ld + q]. */
+int msmp_pack_job_bytes(void);
+int msmp_pack_run(const void* jobs_dev, int njobs, int max_chunks, cudaStream_t stream);
+
 /* dWt[K, Nout] (+)= X[M, K]^T (swish(X) if xswish) * dY[M, Nout];
  * dWside[r (+1), Nout] (+)= [side | 1]^T * dY  (bias gradient = the implicit ones column when has_bias).
  * Deterministic: per-CTA partials over row ranges + fixed-order reduction. */

@@ -38,6 +38,8 @@ _SIGS = {
     "msmp_linear_fwd": (I, [P, P, P, P, I, P, I, P, P, I, I, P, P, I, P, I, I, P, I, P, I, I, I, P]),
     "msmp_linear_tc_image_floats": (S, [I, I]),
     "msmp_linear_tc_fwd": (I, [P, P, P, P, I, P, P, P, I, I, P, I, P, I, P, I, I, P, I, P, I, I, I, P]),
+    "msmp_pack_job_bytes": (I, []),
+    "msmp_pack_run": (I, [P, I, I, P]),
     "msmp_linear_wgrad_splits": (I, [I, I, I]),
     "msmp_linear_wgrad_workspace": (S, [I, I, I, I]),
     "msmp_linear_wgrad": (I, [P, I, I, I, P, I, I, P, I, I, I, P, P, I, I, P, S, P]),

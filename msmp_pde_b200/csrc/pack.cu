@@ -1,0 +1,71 @@
+// Weight packing for the tensor-core kernels: ONE launch converts every parameter of the model into the layouts
+// the kernels consume (pre-split tf32 hi | lo, UMMA 128B-swizzled tile images; small plain side / bias arrays).
+// Parameters keep the reference's layout and names (state_dict compatibility); they change once per optimizer
+// step, so this runs once per step -- it replaces several hundred tiny framework ops per step.
+//
+// A job describes one tile-image block  dst[chunk][hi|lo][4096]  of the k-major weight  Wt[k][n]:
+//     Wt[k][n] = sign * (transpose ? src[n * ld + k] : src[k * ld + n])   for k < kvalid, n < nvalid, else 0
+// (kind 0), or a plain row block  dst[q * ldd + n] = sign * src[n * ld + q]  (q < kvalid rows, n < nvalid; kind 1).
+#include "umma.cuh"
+#include "msmp_b200.h"
+
+namespace msmp {
+
+struct PackJob {
+  const float* src;
+  float* dst;
+  int ld;
+  int transpose;
+  float sign;
+  int kvalid;
+  int nvalid;
+  int nchunks;     // kind 0: number of 32-row k-chunks;  kind 1: unused
+  int kind;
+  int ldd;
+};
+
+__global__ void __launch_bounds__(256) k_pack(const PackJob* __restrict__ jobs) {
+  const PackJob j = jobs[blockIdx.y];
+  const int tid = threadIdx.x;
+  if (j.kind == 1) {
+    if (blockIdx.x != 0) return;
+    for (int i = tid; i < j.kvalid * j.nvalid; i += 256) {
+      const int q = i / j.nvalid, n = i - q * j.nvalid;
+      j.dst[(size_t)q * j.ldd + n] = j.sign * j.src[(size_t)n * j.ld + q];
+    }
+    return;
+  }
+  const int chunk = blockIdx.x;
+  if (chunk >= j.nchunks) return;
+  uint8_t* hi = reinterpret_cast<uint8_t*>(j.dst + (size_t)chunk * 2 * (IMG_BYTES / 4));
+  uint8_t* lo = hi + IMG_BYTES;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int idx = tid + 256 * i;
+    const int n = idx >> 3, c16 = idx & 7;
+    const int k0 = chunk * 32 + 4 * c16;
+    float v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int k = k0 + e;
+      float x = 0.f;
+      if (n < j.nvalid && k < j.kvalid) x = j.sign * (j.transpose ? j.src[(size_t)n * j.ld + k] : j.src[(size_t)k * j.ld + n]);
+      v[e] = x;
+    }
+    store_split4(hi, lo, img_off(n, c16), make_float4(v[0], v[1], v[2], v[3]));
+  }
+}
+
+}  // namespace msmp
+
+extern "C" int msmp_pack_job_bytes(void) { return (int)sizeof(msmp::PackJob); }
+
+// jobs_dev: device array of `njobs` PackJob records (layout above; see msmp_pde_b200/packing.py)
+extern "C" int msmp_pack_run(const void* jobs_dev, int njobs, int max_chunks, cudaStream_t stream) {
+  if (njobs < 0 || max_chunks < 1) return MSMP_ERR_ARG;
+  if (njobs == 0) return MSMP_OK;
+  dim3 grid(max_chunks, njobs);
+  msmp::k_pack<<<grid, 256, 0, stream>>>(reinterpret_cast<const msmp::PackJob*>(jobs_dev));
+  MSMP_CHECK_LAUNCH();
+  return MSMP_OK;
+}

@@ -79,8 +79,8 @@ class LayerPack:
         w3s[:V] = W3[:, 2 * H:].t()
         self.W3side = w3s
         self.W4t = W4.t().contiguous()
-        self.W4d = W4                                                  # [n][k]: dgrad operand (alias)
-        self.W2d = W2                                                  # [n][k]: edge-backward operand (alias)
+        self.W4d = W4.clone()                                          # [n][k]: dgrad operand
+        self.W2d = W2.clone()                                          # [n][k]: edge-backward operand
 
 
 class _Aux:
@@ -132,7 +132,7 @@ class _LayerCoreFn(torch.autograd.Function):
         dPQ = torch.empty(N, 2 * H, dtype=torch.float32, device=dev)
         dz1, dW2, db2 = ops.edge_bwd(PQ[:, :H], PQ[:, H:], topo, pk.W2d, z2, dcat[:, H:], dPQ[:, :H])
         ops.segment_reduce(dz1, topo.colptr, perm=topo.csc_perm, out=dPQ[:, H:], N=N)
-        Kp = pk.Wpq_t.shape[0]
+        Kp = H + ft.upad.shape[1]
         dWpq_t = torch.empty(Kp, 2 * H, dtype=torch.float32, device=dev)
         _, dWs = ops.linear_wgrad(h, dPQ, X1=ft.upad, side=ft.side, r=1 + V, has_bias=True, dWt=dWpq_t)
         dh = ops.linear_fwd([dPQ], pk.W1hq, R=dcat[:, :H])
@@ -211,23 +211,22 @@ class _LayerBase(nn.Module):
             self.update_net_2 = nn.Sequential(nn.Linear(hidden_features, out_features, **f32), Swish())
         else:
             self.update_net_2 = nn.Sequential(nn.Linear(hidden_features, out_features, **f32))
-        self._pack = None
-        self._pack_key = None
+        self._plan_pack = None
 
     def _params(self):
         return (self.message_net_1[0].weight, self.message_net_1[0].bias, self.message_net_2[0].weight,
                 self.message_net_2[0].bias, self.update_net_1[0].weight, self.update_net_1[0].bias,
                 self.update_net_2[0].weight, self.update_net_2[0].bias)
 
-    def pack(self) -> LayerPack:
-        ps = self._params()
-        key = tuple((p.data_ptr(), p._version) for p in ps)
-        if self._pack is None or key != self._pack_key:
-            with torch.no_grad():
-                W1, b1, W2, b2, W3, b3, W4, b4 = [p.detach() for p in ps]
-                self._pack = LayerPack(W1, b1, W3, W2, W4, self.time_window, self.n_variables)
-            self._pack_key = key
-        return self._pack
+    def pack(self):
+        """Kernel-side weight layouts.  Tensor-core mode inside a solver: views into the model-wide PackPlan (re-packed
+        by one launch per forward).  Otherwise built here with framework ops on every call -- parameter ``_version``
+        counters cannot be used to cache them (fused optimizers and CUDA-graph replays do not move them)."""
+        if self._plan_pack is not None and ops.GEMM_MODE == "tc":
+            return self._plan_pack
+        with torch.no_grad():
+            W1, b1, W2, b2, W3, b3, W4, b4 = [p.detach() for p in self._params()]
+            return LayerPack(W1, b1, W3, W2, W4, self.time_window, self.n_variables)
 
     def core(self, h, feat: NodeFeatures, topo: Topology):
         """h -> propagate(h) (before the norm)."""
@@ -257,3 +256,23 @@ class GNN_Layer(_LayerBase):
 class GNN_LayerLin(_LayerBase):
     """models_gnn.py:88-149 (no final Swish, no residual)"""
     final_swish = False
+
+
+def prepare_packs(model, layers, lem=None, linears=()) -> None:
+    """Tensor-core mode: (re)build the model-wide PackPlan when parameters moved and re-pack every weight of the model
+    with ONE launch (called at the start of each forward pass)."""
+    if ops.GEMM_MODE != "tc":
+        return
+    from .packing import PackPlan
+    plan = model.__dict__.get("_msmp_pack_plan")
+    if plan is None or not plan.valid():
+        plan = PackPlan(layers[0].message_net_1[0].weight.device)
+        for l in layers:
+            l._plan_pack = plan.add_layer(l)
+        if lem is not None:
+            lem.__dict__["_plan_pack"] = plan.add_lem(lem)
+        for lin in linears:
+            lin.__dict__["_msmp_tcw"] = plan.add_linear(lin)
+        plan.finalize()
+        model.__dict__["_msmp_pack_plan"] = plan
+    plan.refresh()

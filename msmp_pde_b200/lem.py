@@ -35,13 +35,13 @@ class _LEMFn(torch.autograd.Function):
         ip = pad32(ninp)
         inp = torch.zeros(T, N, ip, dtype=torch.float32, device=dev)
         inp[:, :, :ninp] = inputs
-        Wt, Wzt, Wh, Wzh, Wt_h, Wzt_h = packs    # k-major packs, rows [state(128) | input(ip)]; dgrad operands
+        Wt, Wzt, Wh, Wzh, Wt_h, Wzt_h, Wt_in, Wzt_in = packs    # see LEMcuda.packs()
         Y = torch.empty(T + 1, N, H, dtype=torch.float32, device=dev)
         Z = torch.empty(T + 1, N, H, dtype=torch.float32, device=dev)
         Y[0], Z[0] = y0, z0
         persistent = ops.GEMM_MODE == "tc" and ops.LEM_PERSISTENT and ip == 32 and ninp <= 8
         if persistent:
-            Yt, Zt, gates = ops.lem_tc_fwd(inp, ninp, Wt, Wzt, Wt_h, Wzt_h, bias, bias_lin_z, Y, Z, dt)
+            Yt, Zt, gates = ops.lem_tc_fwd(inp, ninp, Wt_in, Wzt_in, Wt_h, Wzt_h, bias, bias_lin_z, Y, Z, dt)
             ctx.save_for_backward(inp, Y, Z, gates, Yt, Zt)
         else:
             gates = torch.empty(T, 4, N, H, dtype=torch.float32, device=dev)   # dt_bar, dt_z, tanh(G2), tanh(L)
@@ -63,7 +63,7 @@ class _LEMFn(torch.autograd.Function):
         saved = ctx.saved_tensors
         inp, Y, Z, gates = saved[:4]
         dt, ninp = ctx.dt, ctx.ninp
-        _, _, Wh, Wzh, _, _ = ctx.packs
+        Wh, Wzh = ctx.packs[2], ctx.packs[3]
         T, N, ip = inp.shape
         dev = inp.device
         gY, gZ = gY.contiguous(), gZ.contiguous()
@@ -120,26 +120,27 @@ class LEMcuda(nn.Module):
         self.bias = nn.Parameter(torch.empty(3 * nhid, **f32))
         self.bias_lin_z = nn.Parameter(torch.empty(nhid, **f32))
         self.dt = float(dt)
-        self._packs, self._pack_key = None, None
         self.reset_parameters()
 
     def packs(self):
-        """Kernel-side weight layouts, rebuilt only when a parameter changed (once per optimizer step)."""
-        key = tuple((p.data_ptr(), p._version) for p in (self.weights, self.weights_lin_z))
-        if self._packs is None or key != self._pack_key:
-            with torch.no_grad():
-                W, Wz = self.weights.detach(), self.weights_lin_z.detach()
-                ninp, ip = self.ninp, pad32(self.ninp)
-                Wt = W.new_zeros(H + ip, 3 * H)
-                Wt[:H] = W[:, :H].t()
-                Wt[H:H + ninp] = W[:, H:].t()
-                Wzt = W.new_zeros(H + ip, H)
-                Wzt[:H] = Wz[:, :H].t()
-                Wzt[H:H + ninp] = Wz[:, H:].t()
-                self._packs = (Wt, Wzt, W[:, :H].contiguous(), Wz[:, :H].contiguous(), Wt[:H].contiguous(),
-                               Wzt[:H].contiguous())
-            self._pack_key = key
-        return self._packs
+        """(Wt, Wzt, Wh, Wzh, Wt_h, Wzt_h, Wt_in, Wzt_in): k-major packs W^T / Wz^T (rows [state | input]), dgrad
+        operands W[:, :H] / Wz[:, :H], state rows and input rows of the k-major packs.  Tensor-core mode inside a
+        solver: images from the model-wide PackPlan; otherwise rebuilt here on every call."""
+        persistent = ops.GEMM_MODE == "tc" and ops.LEM_PERSISTENT and pad32(self.ninp) == 32 and self.ninp <= 8
+        pk = self.__dict__.get("_plan_pack")
+        if pk is not None and persistent:
+            return (None, None, pk.Wh, pk.Wzh, pk.Wt_h, pk.Wzt_h, pk.Wt_in, pk.Wzt_in)
+        with torch.no_grad():
+            W, Wz = self.weights.detach(), self.weights_lin_z.detach()
+            ninp, ip = self.ninp, pad32(self.ninp)
+            Wt = W.new_zeros(H + ip, 3 * H)
+            Wt[:H] = W[:, :H].t()
+            Wt[H:H + ninp] = W[:, H:].t()
+            Wzt = W.new_zeros(H + ip, H)
+            Wzt[:H] = Wz[:, :H].t()
+            Wzt[H:H + ninp] = Wz[:, H:].t()
+            return (Wt, Wzt, W[:, :H].contiguous(), Wz[:, :H].contiguous(), Wt[:H].contiguous(), Wzt[:H].contiguous(),
+                    Wt[H:], Wzt[H:])
 
     def reset_parameters(self):
         stdv = 1.0 / math.sqrt(self.nhid)

@@ -12,7 +12,7 @@ import torch
 from torch import nn
 
 from .graph import get_topology
-from .layers import GNN_Layer, GNN_LayerLin, H, NodeFeatures, Swish, gate_blend  # noqa: F401 (re-exported)
+from .layers import GNN_Layer, GNN_LayerLin, H, NodeFeatures, Swish, gate_blend, prepare_packs  # noqa: F401 (re-exported)
 from .lem import LEM, LEMS, LEMcuda  # noqa: F401 (re-exported)
 from .solver import (cumulative_dt, decode, linear_act, make_decoder, mlp2, pad_cols, require_cuda, variables_1field)
 
@@ -68,9 +68,19 @@ class _Solver1F(nn.Module):
     def __repr__(self):
         return 'GNN'
 
+    def _prepare_packs(self):
+        layers = list(self.gnn_layers) + (list(self.gnn_layers_gate) if self.gated else [])
+        if self.encoder == "mlp":
+            lem, linears = None, [self.embedding_mlp[0], self.embedding_mlp[2]]
+        else:
+            lem = self.embedding_lem.rnn
+            linears = [self.lemoutput_mlp[0], self.lemoutput_mlp[2]] if self.lem_mlp else []
+        prepare_packs(self, layers, lem, linears)
+
     def forward(self, data) -> torch.Tensor:
         u_in = data.x
         require_cuda(u_in)
+        self._prepare_packs()
         pos = data.pos
         pos_x = pos[:, 1][:, None] / self.pde.L
         pos_t = pos[:, 0][:, None] / self.pde.tmax

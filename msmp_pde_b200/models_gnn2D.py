@@ -9,7 +9,7 @@ import torch
 from torch import nn
 
 from .graph import get_topology
-from .layers import GNN_Layer, GNN_LayerLin, H, NodeFeatures, Swish, gate_blend  # noqa: F401
+from .layers import GNN_Layer, GNN_LayerLin, H, NodeFeatures, Swish, gate_blend, prepare_packs  # noqa: F401
 from .lem import LEM, LEMS  # noqa: F401
 from .models_gnn import LSTM  # noqa: F401
 from .solver import decode, linear_act, make_decoder, mlp2, pad_cols, require_cuda
@@ -59,10 +59,19 @@ class _Solver2F(nn.Module):
     def __repr__(self):
         return 'GNN'
 
+    def _prepare_packs(self):
+        layers = list(self.gnn_layers) + (list(self.gnn_layers_gate) if self.gated else [])
+        if self.encoder == "lem":
+            lem, linears = self.embedding_lem.rnn, [self.lemoutput_mlp[0], self.lemoutput_mlp[2]]
+        else:
+            lem, linears = None, [self.embedding_mlp[0], self.embedding_mlp[2]]
+        prepare_packs(self, layers, lem, linears + [self.double_mlp[0]])
+
     def forward(self, data) -> torch.Tensor:
         tw = self.time_window
         u_in = data.x
         require_cuda(u_in)
+        self._prepare_packs()
         pos = data.pos
         pos_x = pos[:, 1][:, None] / self.pde.L
         pos_t = pos[:, 0][:, None] / self.pde.tmax

@@ -10,6 +10,7 @@ import ctypes
 import torch
 
 from ._lib import check, lib
+from .packing import TcW
 
 H = 128
 _ws: dict = {}
@@ -25,10 +26,11 @@ def _count(n: int) -> None:
 
 
 class _timed:
-    """Records start/stop CUDA events on the current stream around one op when PROFILE_EVENTS is a dict."""
+    """Records (start, stop, flops, bytes) with CUDA events on the current stream around one op when
+    PROFILE_EVENTS is a dict (bench.py's per-kernel roofline pass)."""
 
-    def __init__(self, name):
-        self.name = name
+    def __init__(self, name, flops=0.0, nbytes=0.0):
+        self.name, self.flops, self.nbytes = name, flops, nbytes
 
     def __enter__(self):
         if PROFILE_EVENTS is not None:
@@ -40,7 +42,7 @@ class _timed:
     def __exit__(self, *exc):
         if PROFILE_EVENTS is not None:
             self.e.record()
-            PROFILE_EVENTS.setdefault(self.name, []).append((self.s, self.e))
+            PROFILE_EVENTS.setdefault(self.name, []).append((self.s, self.e, self.flops, self.nbytes))
         return False
 
 
@@ -102,6 +104,9 @@ def _cached_images(Wt: torch.Tensor) -> torch.Tensor:
 def linear_fwd(segs, Wt, bias=None, side=None, r=0, Wside=None, Zmul=None, Ypre=None, act=False, R=None,
                out=None, Nout=None, aswish=None):
     """Y = epi([A0|A1|A2] @ Wt + bias + side[:, :r] @ Wside); see include/msmp_b200.h."""
+    if isinstance(Wt, TcW):          # pre-packed by packing.PackPlan (tensor-core mode only)
+        return linear_tc_fwd(segs, Wt.img, Wt.N if Nout is None else Nout, bias=bias, side=side, r=r, Wside=Wside,
+                             Zmul=Zmul, Ypre=Ypre, act=act, R=R, out=out, aswish=aswish)
     if GEMM_MODE == "tc":
         return linear_tc_fwd(segs, _cached_images(Wt), Wt.shape[1] if Nout is None else Nout, bias=bias, side=side,
                              r=r, Wside=Wside, Zmul=Zmul, Ypre=Ypre, act=act, R=R, out=out, aswish=aswish)
@@ -171,7 +176,9 @@ def linear_tc_fwd(segs, img, Nout, bias=None, side=None, r=0, Wside=None, Zmul=N
     lda = (ctypes.c_int * 3)(*[_ld(a) for a in segs], *([0] * (3 - n)))
     ka = (ctypes.c_int * 3)(*[a.shape[1] for a in segs], *([0] * (3 - n)))
     asw = (ctypes.c_int * 3)(*([int(bool(x)) for x in aswish] if aswish else [0] * n), *([0] * (3 - n)))
-    check(lib.msmp_linear_tc_fwd(A, lda, ka, asw, n, img.data_ptr(), _p(bias), _p(side),
+    Ktot = sum(a.shape[1] for a in segs)
+    with _timed("linear_tc", 2.0 * M * Ktot * Nout, 4.0 * (M * Ktot + M * Nout)):
+      check(lib.msmp_linear_tc_fwd(A, lda, ka, asw, n, img.data_ptr(), _p(bias), _p(side),
                                  _ld(side) if side is not None else 0, r if side is not None else 0, _p(Wside),
                                  _ld(Wside) if Wside is not None else 0, _p(Zmul),
                                  _ld(Zmul) if Zmul is not None else 0, _p(Ypre), _ld(Ypre) if Ypre is not None else 0,
@@ -200,7 +207,8 @@ def linear_wgrad(X, dY, K=None, xswish=False, side=None, r=0, has_bias=False, dW
     sargs = (_p(side), _ld(side) if side is not None else 0, r if side is not None else 0, int(has_bias))
     if GEMM_MODE == "tc":
         ws = _workspace(lib.msmp_linear_wgrad_workspace(M, Kt, Nout, nside), dev)
-        check(lib.msmp_linear_wgrad_tc2(X.data_ptr(), _ld(X), K0, _p(X1), _ld(X1) if X1 is not None else 0, K1,
+        with _timed("wgrad_tc", 2.0 * M * Kt * Nout, 4.0 * (M * Kt + M * Nout)):
+          check(lib.msmp_linear_wgrad_tc2(X.data_ptr(), _ld(X), K0, _p(X1), _ld(X1) if X1 is not None else 0, K1,
                                         int(xswish), dY.data_ptr(), _ld(dY), Nout, *sargs, dWt.data_ptr(), _p(dWside),
                                         int(accumulate), M, ws.data_ptr(), ws.numel(), _stream()),
               "msmp_linear_wgrad_tc2")
@@ -226,9 +234,9 @@ def edge_fwd(P, Q, topo, W2t, b2, save_z2=True):
     agg = torch.empty(topo.N, H, dtype=torch.float32, device=dev)
     z2 = torch.empty(topo.E, H, dtype=torch.float32, device=dev) if save_z2 else None
     ws = _workspace(lib.msmp_edge_fwd_workspace(topo.E), dev)
-    if GEMM_MODE == "tc":
-        img = _cached_images(W2t)
-        with _timed("edge_fwd"):
+    if GEMM_MODE == "tc" or isinstance(W2t, TcW):
+        img = W2t.img if isinstance(W2t, TcW) else _cached_images(W2t)
+        with _timed("edge_tc_fwd", 2.0 * topo.E * H * H, 4.0 * H * (3 * topo.E + topo.N)):
             check(lib.msmp_edge_tc_fwd(P.data_ptr(), Q.data_ptr(), _ld(P), topo.src.data_ptr(), topo.dst.data_ptr(),
                                        topo.rowptr.data_ptr(), topo.inv_deg.data_ptr(), img.data_ptr(), b2.data_ptr(),
                                        _p(z2), agg.data_ptr(), topo.E, topo.N, ws.data_ptr(), ws.numel(), _stream()),
@@ -248,22 +256,22 @@ def edge_bwd(P, Q, topo, W2, z2, dagg, dP):
     """Returns dz1 [E,128], dW2 [128,128] ([n][k] = parameter layout), db2 [128]; writes dP in place."""
     dev = P.device
     dz1 = torch.empty(topo.E, H, dtype=torch.float32, device=dev)
-    if GEMM_MODE == "tc":
+    if GEMM_MODE == "tc" or isinstance(W2, TcW):
         dz2 = torch.empty(topo.E, H, dtype=torch.float32, device=dev)
         a1 = torch.empty(topo.E, H, dtype=torch.float32, device=dev)
-        img = _cached_images(W2)
+        img = W2.img if isinstance(W2, TcW) else _cached_images(W2)
         ws = _workspace(lib.msmp_edge_fwd_workspace(topo.E), dev)
-        with _timed("edge_bwd"):
+        with _timed("edge_tc_bwd", 2.0 * topo.E * H * H, 4.0 * H * (6 * topo.E + topo.N)):
             check(lib.msmp_edge_tc_bwd(P.data_ptr(), Q.data_ptr(), _ld(P), topo.src.data_ptr(), topo.dst.data_ptr(),
                                        topo.rowptr.data_ptr(), topo.inv_deg.data_ptr(), img.data_ptr(), z2.data_ptr(),
                                        dagg.data_ptr(), _ld(dagg), dz2.data_ptr(), a1.data_ptr(), dz1.data_ptr(),
                                        dP.data_ptr(), _ld(dP), topo.E, topo.N, ws.data_ptr(), ws.numel(), _stream()),
                   "msmp_edge_tc_bwd")
-            _count(2)
-            if topo.E > 0:
-                dW2t, dbs = linear_wgrad(a1, dz2, has_bias=True)       # dW2t[k][n] = sum_e a1[e][k] dz2[e][n]
-            else:
-                dW2t, dbs = torch.zeros(H, H, device=dev), torch.zeros(1, H, device=dev)
+        _count(2)
+        if topo.E > 0:
+            dW2t, dbs = linear_wgrad(a1, dz2, has_bias=True)       # dW2t[k][n] = sum_e a1[e][k] dz2[e][n]
+        else:
+            dW2t, dbs = torch.zeros(H, H, device=dev), torch.zeros(1, H, device=dev)
         return dz1, dW2t.t(), dbs[0]
     dW2 = torch.empty(H, H, dtype=torch.float32, device=dev)
     db2 = torch.empty(H, dtype=torch.float32, device=dev)
@@ -284,8 +292,9 @@ def segment_reduce(src, ptr, perm=None, scale=None, out=None, N=None):
     N = ptr.numel() - 1 if N is None else N
     if out is None:
         out = torch.empty(N, H, dtype=torch.float32, device=src.device)
-    check(lib.msmp_segment_reduce(src.data_ptr(), _ld(src), _p(perm), ptr.data_ptr(), _p(scale), out.data_ptr(),
-                                  _ld(out), N, _stream()), "msmp_segment_reduce")
+    with _timed("segment_reduce", 0.0, 4.0 * (src.shape[0] * H + N * H + N + 1)):
+        check(lib.msmp_segment_reduce(src.data_ptr(), _ld(src), _p(perm), ptr.data_ptr(), _p(scale), out.data_ptr(),
+                                      _ld(out), N, _stream()), "msmp_segment_reduce")
     _count(1)
     return out
 
@@ -402,10 +411,15 @@ def from_lane_major(x: torch.Tensor, N: int) -> torch.Tensor:
     return x.transpose(-1, -2).reshape(*lead, nt * 32, C)[..., :N, :].contiguous()
 
 
-def lem_tc_fwd(inp, ninp, Wt, Wzt, Wt_h, Wzt_h, bias, bias_z, Y, Z, dt):
+def _img_of(w):
+    return w.img if isinstance(w, TcW) else _cached_images(w)
+
+
+def lem_tc_fwd(inp, ninp, Wt_in, Wzt_in, Wt_h, Wzt_h, bias, bias_z, Y, Z, dt):
     """Persistent tensor-core LEM forward (input projection + all T steps, two launches).
-    Wt / Wzt: k-major packs [160, 384] / [160, 128]; Wt_h / Wzt_h: their state rows (stable tensors, for the images).
-    Y, Z: row-major [T+1, N, 128] with slab 0 set.  Returns the lane-major (Yt, Zt, gates) kept for the backward."""
+    Wt_in [>= ninp, 384] / Wzt_in [>= ninp, 128]: input rows of the k-major W^T / Wz^T; Wt_h / Wzt_h: their state rows
+    (TcW images or k-major tensors).  Y, Z: row-major [T+1, N, 128] with slab 0 set.
+    Returns the lane-major (Yt, Zt, gates) kept for the backward."""
     T, N = inp.shape[0], inp.shape[1]
     Npad = (N + 127) // 128 * 128
     dev = inp.device
@@ -415,10 +429,11 @@ def lem_tc_fwd(inp, ninp, Wt, Wzt, Wt_h, Wzt_h, bias, bias_z, Y, Z, dt):
     Zt = torch.empty(T + 1, Npad // 32, H, 32, dtype=torch.float32, device=dev)
     Yt[0] = to_lane_major(Y[0], Npad)
     Zt[0] = to_lane_major(Z[0], Npad)
-    check(lib.msmp_lem_tc_fwd(inp.data_ptr(), int(ninp), Wt[H:].data_ptr(), Wzt[H:].data_ptr(),
-                              _cached_images(Wt_h).data_ptr(), _cached_images(Wzt_h).data_ptr(), bias.data_ptr(),
-                              bias_z.data_ptr(), pre.data_ptr(), Y.data_ptr(), Z.data_ptr(), Yt.data_ptr(),
-                              Zt.data_ptr(), gates.data_ptr(), float(dt), T, N, Npad, _stream()), "msmp_lem_tc_fwd")
+    with _timed("lem_tc_fwd", 2.0 * T * N * H * 4 * H, 4.0 * T * N * (512 * 2 + 4 * H)):
+      check(lib.msmp_lem_tc_fwd(inp.data_ptr(), int(ninp), Wt_in.data_ptr(), Wzt_in.data_ptr(), _img_of(Wt_h).data_ptr(),
+                              _img_of(Wzt_h).data_ptr(), bias.data_ptr(), bias_z.data_ptr(), pre.data_ptr(),
+                              Y.data_ptr(), Z.data_ptr(), Yt.data_ptr(), Zt.data_ptr(), gates.data_ptr(), float(dt), T,
+                              N, Npad, _stream()), "msmp_lem_tc_fwd")
     _count(2)
     return Yt, Zt, gates
 
@@ -432,7 +447,8 @@ def lem_tc_bwd(Wzh, Wh, Yt, Zt, gates, gYt, gZt, last_only, dG, dL, dt, N):
     dzt = torch.zeros(nt, H, 32, dtype=torch.float32, device=dev)
     s0 = torch.empty(nt, H, 32, dtype=torch.float32, device=dev)
     s2 = torch.empty(nt, H, 32, dtype=torch.float32, device=dev)
-    check(lib.msmp_lem_tc_bwd(_cached_images(Wzh).data_ptr(), _cached_images(Wh).data_ptr(), Yt.data_ptr(),
+    with _timed("lem_tc_bwd", 2.0 * T * N * H * 4 * H, 4.0 * T * N * (512 + 512 + 6 * H)):
+      check(lib.msmp_lem_tc_bwd(_img_of(Wzh).data_ptr(), _img_of(Wh).data_ptr(), Yt.data_ptr(),
                               Zt.data_ptr(), gates.data_ptr(), _p(gYt), _p(gZt), int(bool(last_only)), dG.data_ptr(),
                               dL.data_ptr(), dyt.data_ptr(), dzt.data_ptr(), s0.data_ptr(), s2.data_ptr(), float(dt),
                               T, N, Npad, _stream()), "msmp_lem_tc_bwd")

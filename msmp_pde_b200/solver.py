@@ -52,18 +52,16 @@ class _LinearActFn(torch.autograd.Function):
 
 
 def _linear_packs(linear: nn.Linear, Kp: int):
-    """(k-major zero-padded W^T [Kp, Nout], detached W [Nout, K]) cached on the module per parameter version."""
-    W = linear.weight
-    key = (W.data_ptr(), W._version, Kp)
-    cache = linear.__dict__.get("_msmp_packs")
-    if cache is None or cache[0] != key:
-        with torch.no_grad():
-            Wd = W.detach()
-            Wt = Wd.new_zeros(Kp, Wd.shape[0])
-            Wt[:Wd.shape[1]] = Wd.t()
-            cache = (key, (Wt, Wd.clone()))
-        linear.__dict__["_msmp_packs"] = cache
-    return cache[1]
+    """(forward operand, dgrad operand): PackPlan images in tensor-core mode inside a solver, else k-major tensors
+    rebuilt on every call (parameter versions cannot be trusted as a cache key, see packing.py)."""
+    tcw = linear.__dict__.get("_msmp_tcw")
+    if tcw is not None and ops.GEMM_MODE == "tc":
+        return tcw.fwd, tcw.dgrad
+    with torch.no_grad():
+        Wd = linear.weight.detach()
+        Wt = Wd.new_zeros(Kp, Wd.shape[0])
+        Wt[:Wd.shape[1]] = Wd.t()
+        return Wt, Wd.clone()
 
 
 def linear_act(x, linear: nn.Linear, act: bool = True):

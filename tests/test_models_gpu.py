@@ -125,3 +125,29 @@ def test_determinism_and_state_dict_roundtrip():
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
     assert torch.equal(grads[0], grads[1]) and torch.equal(grads[0], grads[2])
     assert rel_err(outs[0], ref(data)) < OUT_TOL
+
+
+@pytest.mark.parametrize("graphed", [False, True])
+def test_packed_weights_follow_optimizer_updates(graphed):
+    """Fused optimizers and CUDA-graph replays update parameters without moving ``_version``: the kernel-side
+    weight packs must still track them (they are rebuilt on every forward)."""
+    from msmp_pde_b200 import models_gnn2D, synth
+    from msmp_pde_b200.train_step import GraphedTrainStep
+    from oracle import models as om
+    dev = torch.device("cuda:0")
+    pde, data, meta = synth.config_c2(B=2, nx=40, seed=3)
+    torch.manual_seed(0)
+    model = models_gnn2D.MP_PDE_Solver2DLEMLinGated(pde, 25, 128, 6, meta["eq_variables"]).to(dev)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-2, fused=True, capturable=True)
+    dd = data.clone().to(dev)
+    before = model(dd).detach().clone()
+    step = GraphedTrainStep(model, opt, dd, warmup=1, use_graph=graphed)
+    for _ in range(3):
+        step(dd)
+    torch.cuda.synchronize()
+    after = model(dd).detach()
+    assert rel_err(after, before) > 1e-3                      # the weights really moved
+    torch.set_default_dtype(torch.float64)
+    ref = om.MP_PDE_Solver2DLEMLinGated(pde, 25, 128, 6, meta["eq_variables"])
+    ref.load_state_dict({k: v.double().cpu() for k, v in model.state_dict().items()})
+    assert rel_err(after, ref(data)) < OUT_TOL                # forward uses the CURRENT parameters
