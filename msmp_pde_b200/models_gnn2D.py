@@ -9,7 +9,7 @@ import torch
 from torch import nn
 
 from .graph import get_topology
-from .layers import GNN_Layer, GNN_LayerLin, H, NodeFeatures, Swish, gate_blend, prepare_packs  # noqa: F401
+from .layers import GNN_Layer, GNN_LayerLin, H, NodeFeatures, Swish, gate_blend, gated_pair, prepare_packs  # noqa: F401
 from .lem import LEM, LEMS  # noqa: F401
 from .models_gnn import LSTM  # noqa: F401
 from .solver import decode, linear_act, make_decoder, mlp2, pad_cols, require_cuda
@@ -103,9 +103,7 @@ class _Solver2F(nn.Module):
 
         for i in range(self.hidden_layer):
             if self.gated:
-                yg = self.gnn_layers_gate[i].core(h, feat, topo)
-                ym = self.gnn_layers[i].core(h, feat, topo)
-                h = gate_blend(yg, ym, h, topo)
+                h = gated_pair(self.gnn_layers_gate[i], self.gnn_layers[i], h, feat, topo)
             else:
                 h = self.gnn_layers[i].forward_prepared(h, feat, topo)
 

@@ -51,7 +51,8 @@ def _stream() -> int:
 
 
 def _workspace(nbytes: int, device) -> torch.Tensor:
-    key = (device.type, device.index)
+    # one scratch buffer per (device, stream): ops issued on different streams may run concurrently
+    key = (device.type, device.index, torch.cuda.current_stream().cuda_stream)
     buf = _ws.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(max(nbytes, 1 << 22), dtype=torch.uint8, device=device)
@@ -252,8 +253,10 @@ def edge_fwd(P, Q, topo, W2t, b2, save_z2=True):
     return agg, z2
 
 
-def edge_bwd(P, Q, topo, W2, z2, dagg, dP):
-    """Returns dz1 [E,128], dW2 [128,128] ([n][k] = parameter layout), db2 [128]; writes dP in place."""
+def edge_bwd(P, Q, topo, W2, z2, dagg, dP, defer_wgrad=False):
+    """Returns dz1 [E,128], dW2 [128,128] ([n][k] = parameter layout), db2 [128]; writes dP in place.
+    defer_wgrad (tensor-core path): returns (dz1, a1, dz2) instead; the caller runs
+    ``linear_wgrad(a1, dz2, has_bias=True)`` itself (e.g. on a side stream)."""
     dev = P.device
     dz1 = torch.empty(topo.E, H, dtype=torch.float32, device=dev)
     if GEMM_MODE == "tc" or isinstance(W2, TcW):
@@ -268,6 +271,8 @@ def edge_bwd(P, Q, topo, W2, z2, dagg, dP):
                                        dP.data_ptr(), _ld(dP), topo.E, topo.N, ws.data_ptr(), ws.numel(), _stream()),
                   "msmp_edge_tc_bwd")
         _count(2)
+        if defer_wgrad:
+            return dz1, a1, dz2
         if topo.E > 0:
             dW2t, dbs = linear_wgrad(a1, dz2, has_bias=True)       # dW2t[k][n] = sum_e a1[e][k] dz2[e][n]
         else:
