@@ -174,6 +174,7 @@ def run_ours(args):
     say("timing done")
     launches = launches_per_step * args.steps
 
+    scatter = scatter_bandwidth(dev) if rank == 0 else None
     ms = sum(times) / len(times)
     ms_e2e = sum(e2e_times) / len(e2e_times)
     t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
@@ -214,7 +215,7 @@ def run_ours(args):
             "e2e": {"value": round(world * N / (ms_e2e * 1e-3), 1), "unit": UNIT, "ms_per_step": round(ms_e2e, 4),
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 8},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
-            "ops": table,
+            "ops": table, "scatter_hbm": scatter,
             "execution": "eager launches" if args.eager else "whole step captured as one CUDA graph (GraphedTrainStep)",
         }
         if world == 1 and not args.no_cpu_baseline:
@@ -224,6 +225,38 @@ def run_ours(args):
         dist.barrier()
         dist.destroy_process_group()
     return out
+
+
+def scatter_bandwidth(dev, n_nodes=1 << 20, degree=6, reps=10):
+    """Second half of the metric: standalone deterministic scatter-mean (msmp_segment_reduce) HBM GB/s on a 1 Mi-node,
+    6-neighbour graph (config 5 shape): algorithmic bytes E*512 + N*512 + (N+1)*4 / CUDA-event time.
+    Inputs (3.2 GB) exceed L2, so every repetition streams from HBM."""
+    import torch
+    from msmp_pde_b200 import ops
+    E = n_nodes * degree
+    src = torch.randn(E, 128, device=dev)
+    ptr = (torch.arange(n_nodes + 1, device=dev, dtype=torch.int32) * degree).contiguous()
+    inv = torch.full((n_nodes,), 1.0 / degree, device=dev)
+    out = torch.empty(n_nodes, 128, device=dev)
+    perm = torch.randperm(E, device=dev, dtype=torch.int32)            # gather-hostile order (by-source scatter)
+    res = {}
+    for name, pm in (("contiguous", None), ("permuted", perm)):
+        for _ in range(3):
+            ops.segment_reduce(src, ptr, perm=pm, scale=inv, out=out, N=n_nodes)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(reps):
+            ops.segment_reduce(src, ptr, perm=pm, scale=inv, out=out, N=n_nodes)
+        e.record()
+        torch.cuda.synchronize()
+        ms = s.elapsed_time(e) / reps
+        nbytes = E * 512 + n_nodes * 512 + (n_nodes + 1) * 4 + (E * 4 if pm is not None else 0)
+        res[name] = {"ms": round(ms, 4), "gbs": round(nbytes / ms / 1e6, 1)}
+    peak = _peaks()["hbm_gbs"]
+    return {"kernel": "k_segment_reduce", "nodes": n_nodes, "edges": E, "bytes": E * 512 + n_nodes * 512 + (n_nodes + 1) * 4,
+            "contiguous_gbs": res["contiguous"]["gbs"], "contiguous_frac": round(res["contiguous"]["gbs"] / peak, 4),
+            "permuted_gbs": res["permuted"]["gbs"], "permuted_frac": round(res["permuted"]["gbs"] / peak, 4),
+            "peak_gbs": peak}
 
 
 # ------------------------------------------------------------------------------------------ reference

@@ -151,3 +151,49 @@ def test_packed_weights_follow_optimizer_updates(graphed):
     ref = om.MP_PDE_Solver2DLEMLinGated(pde, 25, 128, 6, meta["eq_variables"])
     ref.load_state_dict({k: v.double().cpu() for k, v in model.state_dict().items()})
     assert rel_err(after, ref(data)) < OUT_TOL                # forward uses the CURRENT parameters
+
+
+def test_c4_lattice_multichunk_graphs():
+    """BASELINE config 4 shape (reduced): two-field model on 2-D lattice graphs whose graphs span many InstanceNorm
+    chunks (4096 nodes per graph, 4-neighbour lattice, irregular boundary degree), outputs + gradients vs the oracle."""
+    from msmp_pde_b200 import models_gnn2D, synth
+    from oracle import models as om
+    dev = torch.device("cuda:0")
+    pde, data, meta = synth.config_c4(B=2, side=64, seed=2)
+    torch.manual_seed(0)
+    model = models_gnn2D.MP_PDE_Solver2DLEMLinGated(pde, 25, 128, 6, meta["eq_variables"]).to(dev)
+    torch.set_default_dtype(torch.float64)
+    ref = om.MP_PDE_Solver2DLEMLinGated(pde, 25, 128, 6, meta["eq_variables"])
+    ref.load_state_dict({k: v.double().cpu() for k, v in model.state_dict().items()})
+    dd = data.clone().to(dev)
+    out = model(dd)
+    torch.sqrt(((out - dd.y) ** 2).sum()).backward()
+    outr = ref(data)
+    torch.sqrt(((outr - data.y) ** 2).sum()).backward()
+    assert rel_err(out, outr) < OUT_TOL
+    errs = _grad_errs(model, ref)
+    worst = max(errs, key=errs.get)
+    assert errs[worst] <= 1.0, (worst, errs[worst])
+
+
+def test_rollout_reuses_topology_and_no_grad():
+    """Autoregressive rollout as in train_helper.py:255-261 / common/utils.py:448-471: x is replaced by the prediction,
+    pos[:, 0] advances; the cached topology is reused; no_grad forward equals the grad-mode forward."""
+    from msmp_pde_b200 import graph as G
+    from msmp_pde_b200 import models_gnn, synth
+    dev = torch.device("cuda:0")
+    pde, data, meta = synth.config_c1(B=4, nx=100, seed=5)
+    torch.manual_seed(0)
+    model = models_gnn.MP_PDE_Solver(pde, 25, 128, 6, {}).to(dev)
+    dd = data.clone().to(dev)
+    ref1 = model(dd).detach()
+    G._CACHE.clear()
+    with torch.no_grad():
+        p1 = model(dd)
+        n_topo = len(G._CACHE)
+        dd.x = torch.cat((dd.x, p1), 1)[:, 25:]                  # create_next_graph for non-AD equations
+        dd.pos[:, 0] += 25 * pde.dt
+        p2 = model(dd)
+    assert torch.equal(p1, ref1)
+    assert len(G._CACHE) == n_topo == 1                          # edge_index identity unchanged => one topology
+    assert p2.shape == p1.shape and bool(torch.isfinite(p2).all())
