@@ -117,8 +117,13 @@ __device__ __forceinline__ void state_store4(uint8_t* smA, int r, int col, float
   store_split4(chunk, chunk + IMG_BYTES, img_off(r, (col & 31) >> 2), v);
 }
 
+// clock64() phase stamps of CTA 0 at step 2 (scripts/lem_ticks.py); compiled in only with -DMSMP_LEM_TICKS.
+#ifdef MSMP_LEM_TICKS
 __device__ long long g_lem_dbg[64];
 #define LEM_TICK(i) do { if (blockIdx.x == 0 && tid == 0 && t == 2) g_lem_dbg[i] = clock64(); } while (0)
+#else
+#define LEM_TICK(i) do { } while (0)
+#endif
 
 // L2 prefetch of `nch` consecutive lane-major channel lines (128 B each) of row-tile gt, starting at channel c_begin
 __device__ __forceinline__ void prefetch_lm(const float* base, size_t gt, int C, int c_begin, int nch, int lane) {
@@ -522,9 +527,11 @@ __global__ void __launch_bounds__(256, 1) k_lem_bwd_tc(const LemBwdParams p) {
 
 using namespace msmp;
 
+#ifdef MSMP_LEM_TICKS
 extern "C" int msmp_lem_debug_ticks(long long* host_out) {
   return cudaMemcpyFromSymbol(host_out, g_lem_dbg, sizeof(long long) * 64) == cudaSuccess ? 0 : -2;
 }
+#endif
 
 extern "C" int msmp_lem_tc_fwd(const float* inp, int ninp, const float* Wt_in, const float* Wzt_in, const float* Wimg,
                                const float* Wzimg, const float* bias, const float* bias_z, float* pre, float* Y,

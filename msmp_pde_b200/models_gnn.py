@@ -26,6 +26,9 @@ class LSTM(nn.Module):
         self.rnn = nn.LSTM(ninp, nhid, dtype=torch.float32)
 
     def forward(self, input):
+        # fp32 parity: cuDNN's RNN kernels default to TF32 (forward here, backward later from autograd), so the flag
+        # is cleared process-wide rather than in a context manager that would have closed before backward runs.
+        torch.backends.cudnn.allow_tf32 = False
         output, _ = self.rnn(input.float())
         return output[-1]
 
@@ -34,8 +37,9 @@ class _Solver1F(nn.Module):
     """Shared skeleton of the 1-field solvers: encoder -> (gated) message passing stack -> Conv1d decoder."""
     layer_cls = GNN_Layer
     gated = False
-    encoder = "mlp"            # 'mlp' | 'lem'
-    lem_mlp = False            # lemoutput_mlp after the LEM encoder
+    encoder = "mlp"            # 'mlp' | 'lem' | 'lems' (state kept across calls) | 'lstm'
+    lem_mlp = False            # lemoutput_mlp / lstmoutput_mlp after the recurrent encoder
+    diff_only = False          # MSSMP sub-network: return the decoder output without the time stepping
 
     def __init__(self, pde, time_window: int = 25, hidden_features: int = 128, hidden_layer: int = 6,
                  eq_variables: dict = {}):
@@ -57,10 +61,17 @@ class _Solver1F(nn.Module):
             self.embedding_mlp = nn.Sequential(nn.Linear(time_window + 2 + len(eq_variables), hidden_features, **f32),
                                                Swish(), nn.Linear(hidden_features, hidden_features, **f32), Swish())
         else:
-            self.embedding_lem = LEM(2 + len(eq_variables) + 1, hidden_features)
-            if self.lem_mlp:
-                self.lemoutput_mlp = nn.Sequential(nn.Linear(hidden_features, hidden_features, **f32), Swish(),
-                                                   nn.Linear(hidden_features, hidden_features, **f32), Swish())
+            ninp = 2 + len(eq_variables) + 1
+            mlp = lambda: nn.Sequential(nn.Linear(hidden_features, hidden_features, **f32), Swish(),
+                                        nn.Linear(hidden_features, hidden_features, **f32), Swish())
+            if self.encoder == "lstm":
+                self.embedding_lstm = LSTM(ninp, hidden_features)
+                if self.lem_mlp:
+                    self.lstmoutput_mlp = mlp()
+            else:
+                self.embedding_lem = (LEMS if self.encoder == "lems" else LEM)(ninp, hidden_features)
+                if self.lem_mlp:
+                    self.lemoutput_mlp = mlp()
         if self.gated:
             self.swish = Swish()
         self.output_mlp = make_decoder(time_window, 1)
@@ -72,6 +83,9 @@ class _Solver1F(nn.Module):
         layers = list(self.gnn_layers) + (list(self.gnn_layers_gate) if self.gated else [])
         if self.encoder == "mlp":
             lem, linears = None, [self.embedding_mlp[0], self.embedding_mlp[2]]
+        elif self.encoder == "lstm":
+            lem = None
+            linears = [self.lstmoutput_mlp[0], self.lstmoutput_mlp[2]] if self.lem_mlp else []
         else:
             lem = self.embedding_lem.rnn
             linears = [self.lemoutput_mlp[0], self.lemoutput_mlp[2]] if self.lem_mlp else []
@@ -100,9 +114,14 @@ class _Solver1F(nn.Module):
             lem_in[:, :, 0] = static[:, 0]
             lem_in[:, :, 1] = u.t()
             lem_in[:, :, 2:] = static[:, 1:]
-            h = self.embedding_lem(lem_in)
-            if self.lem_mlp:
-                h = mlp2(h, self.lemoutput_mlp)
+            if self.encoder == "lstm":
+                h = self.embedding_lstm(lem_in).contiguous()
+                if self.lem_mlp:
+                    h = mlp2(h, self.lstmoutput_mlp)
+            else:
+                h = self.embedding_lem(lem_in)
+                if self.lem_mlp:
+                    h = mlp2(h, self.lemoutput_mlp)
 
         for i in range(self.hidden_layer):
             if self.gated:
@@ -110,6 +129,10 @@ class _Solver1F(nn.Module):
             else:
                 h = self.gnn_layers[i].forward_prepared(h, feat, topo)
 
+        if self.diff_only:             # MSSMP_PDE_Solver_sub returns diff (models_gnn.py:1676-1680)
+            out = decode(h, self.output_mlp, torch.zeros_like(u), torch.ones(self.time_window, dtype=torch.float32, device=h.device), 1,
+                         self.time_window)
+            return out.to(u_in.dtype)
         dt = cumulative_dt(self.pde, self.time_window, h.device)
         out = decode(h, self.output_mlp, u, dt, 1, self.time_window)     # models_gnn.py:278-279
         return out.to(u_in.dtype)
@@ -128,3 +151,64 @@ class MP_PDE_SolverLEM(_Solver1F):
 class MP_PDE_SolverLEMLinGated(_Solver1F):
     """models_gnn.py:1220-1377 (`--model MSMP-PDE`)."""
     layer_cls, gated, encoder, lem_mlp = GNN_LayerLin, True, "lem", True
+
+
+class MP_PDE_SolverLEMLin(_Solver1F):
+    """models_gnn.py:619-756 (LEM + lemoutput_mlp, plain GNN_Layer stack)."""
+    layer_cls, gated, encoder, lem_mlp = GNN_Layer, False, "lem", True
+
+
+class MP_PDE_SolverLSTMLin(_Solver1F):
+    """models_gnn.py:770-907 (cuDNN LSTM encoder + lstmoutput_mlp, plain stack)."""
+    layer_cls, gated, encoder, lem_mlp = GNN_Layer, False, "lstm", True
+
+
+class MP_PDE_SolverLSTMLinGated(_Solver1F):
+    """models_gnn.py:909-1065"""
+    layer_cls, gated, encoder, lem_mlp = GNN_LayerLin, True, "lstm", True
+
+
+class MP_PDE_SolverGated(_Solver1F):
+    """models_gnn.py:1067-1218 (MLP encoder, gated GNN_LayerLin stack)."""
+    layer_cls, gated, encoder = GNN_LayerLin, True, "mlp"
+
+
+class MP_PDE_SolverLEMLinGatedSave(_Solver1F):
+    """models_gnn.py:1747-1904 (LEMS keeps (y, z) across calls; train_helper.py:144-145 resets it)."""
+    layer_cls, gated, encoder, lem_mlp = GNN_LayerLin, True, "lems", True
+
+
+class MSSMP_PDE_Solver_sub(_Solver1F):
+    """models_gnn.py:1525-1682 (returns the decoder output only)."""
+    layer_cls, gated, encoder, lem_mlp, diff_only = GNN_LayerLin, True, "lem", True, True
+
+
+class MSSMP_PDE_Solver(nn.Module):
+    """models_gnn.py:1684-1745: out = (1 - scale) * u_last + cumsum(dt) * scale * diff with two sub-networks."""
+
+    def __init__(self, pde, time_window: int = 25, hidden_features: int = 128, hidden_layer: int = 6,
+                 eq_variables: dict = {}):
+        super().__init__()
+        assert time_window in (20, 25, 50)
+        self.pde, self.out_features = pde, time_window
+        self.hidden_features, self.hidden_layer = hidden_features, hidden_layer
+        self.time_window, self.eq_variables = time_window, eq_variables
+        self.diff = MSSMP_PDE_Solver_sub(pde, time_window, hidden_features, hidden_layer, eq_variables)
+        self.scale = MSSMP_PDE_Solver_sub(pde, time_window, hidden_features, hidden_layer, eq_variables)
+
+    def __repr__(self):
+        return 'GNN'
+
+    def forward(self, data) -> torch.Tensor:
+        scale = self.scale(data)
+        diff = self.diff(data)
+        u = data.x
+        dt = torch.cumsum(torch.ones(1, self.time_window, dtype=u.dtype, device=u.device) * self.pde.dt, dim=1)
+        return (1 - scale) * u[:, -1:].expand(-1, self.time_window) + dt * (scale * diff)
+
+
+class MP_PDE_SolverLEMLinGatedGLU(nn.Module):
+    """models_gnn.py:1379-1523 uses hidden_features = 164; the msmp_b200 kernels are specialised for 128."""
+
+    def __init__(self, *a, **k):
+        raise NotImplementedError("MP_PDE_SolverLEMLinGatedGLU (hidden_features=164) is outside the 128-wide hot path")

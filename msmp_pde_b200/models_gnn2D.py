@@ -23,7 +23,8 @@ def unflatten_u(u: torch.Tensor, time_window: int):
 class _Solver2F(nn.Module):
     layer_cls = GNN_LayerLin
     gated = True
-    encoder = "lem"
+    encoder = "lem"            # 'lem' (LEM, or LEMS when save_state) | 'lstm' | 'mlp'
+    g2 = False                 # G^2-style gate (models_gnn2D.py:598-603)
 
     def __init__(self, pde, time_window: int = 25, hidden_features: int = 128, hidden_layer: int = 6,
                  eq_variables: dict = {}, save_state=None):
@@ -47,6 +48,10 @@ class _Solver2F(nn.Module):
             self.embedding_lem = lem_cls(2 + len(eq_variables) + 2, hidden_features)
             self.lemoutput_mlp = nn.Sequential(nn.Linear(hidden_features, hidden_features, **f32), Swish(),
                                                nn.Linear(hidden_features, hidden_features, **f32), Swish())
+        elif self.encoder == "lstm":
+            self.embedding_lstm = LSTM(2 + len(eq_variables) + 2, hidden_features)
+            self.lstmoutput_mlp = nn.Sequential(nn.Linear(hidden_features, hidden_features, **f32), Swish(),
+                                                nn.Linear(hidden_features, hidden_features, **f32), Swish())
         else:
             self.embedding_mlp = nn.Sequential(nn.Linear(2 * time_window + 2 + len(eq_variables), hidden_features, **f32),
                                                Swish(), nn.Linear(hidden_features, hidden_features, **f32), Swish())
@@ -63,6 +68,8 @@ class _Solver2F(nn.Module):
         layers = list(self.gnn_layers) + (list(self.gnn_layers_gate) if self.gated else [])
         if self.encoder == "lem":
             lem, linears = self.embedding_lem.rnn, [self.lemoutput_mlp[0], self.lemoutput_mlp[2]]
+        elif self.encoder == "lstm":
+            lem, linears = None, [self.lstmoutput_mlp[0], self.lstmoutput_mlp[2]]
         else:
             lem, linears = None, [self.embedding_mlp[0], self.embedding_mlp[2]]
         prepare_packs(self, layers, lem, linears + [self.double_mlp[0]])
@@ -87,7 +94,7 @@ class _Solver2F(nn.Module):
         dt64 = torch.cumsum(torch.ones(1, tw, dtype=torch.float64, device=u.device) * float(self.pde.dt), dim=1)
         dt = dt64.float()
 
-        if self.encoder == "lem":
+        if self.encoder in ("lem", "lstm"):
             # I_t = [pos_x, u1[:, t], u2[:, t], cumsum(dt)_t + pos_t, variables[:, 1:]]  (models_gnn2D.py:421-433)
             nvar = variables.shape[1] - 1
             lem_in = torch.empty(tw, N, 4 + nvar, dtype=torch.float32, device=u.device)
@@ -97,12 +104,17 @@ class _Solver2F(nn.Module):
             lem_in[:, :, 3] = (dt64 + pos_t.double()).float().t()
             if nvar:
                 lem_in[:, :, 4:] = variables[:, 1:].float()
-            h = mlp2(self.embedding_lem(lem_in), self.lemoutput_mlp)
+            if self.encoder == "lem":
+                h = mlp2(self.embedding_lem(lem_in), self.lemoutput_mlp)
+            else:
+                h = mlp2(self.embedding_lstm(lem_in).contiguous(), self.lstmoutput_mlp)
         else:
             h = mlp2(pad_cols(torch.cat((u_in, pos_x, variables), -1)), self.embedding_mlp)
 
         for i in range(self.hidden_layer):
-            if self.gated:
+            if self.g2:
+                h = _g2_pair(self.gnn_layers_gate[i], self.gnn_layers[i], h, feat, topo)
+            elif self.gated:
                 h = gated_pair(self.gnn_layers_gate[i], self.gnn_layers[i], h, feat, topo)
             else:
                 h = self.gnn_layers[i].forward_prepared(h, feat, topo)
@@ -115,3 +127,76 @@ class _Solver2F(nn.Module):
 class MP_PDE_Solver2DLEMLinGated(_Solver2F):
     """models_gnn2D.py:290-458 (`--model MSMP-PDE2D`; BASELINE configs 2-4)."""
     layer_cls, gated, encoder = GNN_LayerLin, True, "lem"
+
+
+class _SourceMeanFn(torch.autograd.Function):
+    """torch_scatter.scatter(src, edge_index[0], reduce='mean') on the deterministic segmented kernel
+    (msmp_segment_reduce over the CSC permutation); backward is the matching gather."""
+
+    @staticmethod
+    def forward(ctx, src, topo):
+        from . import ops
+        outdeg = (topo.colptr[1:] - topo.colptr[:-1]).clamp(min=1).float()
+        inv = 1.0 / outdeg
+        ctx.topo, ctx.inv = topo, inv
+        return ops.segment_reduce(src.contiguous(), topo.colptr, perm=topo.csc_perm, scale=inv, N=topo.N)
+
+    @staticmethod
+    def backward(ctx, g):
+        topo = ctx.topo
+        return (g * ctx.inv[:, None])[topo.src.long()], None
+
+
+def _g2_pair(gate_layer, main_layer, h, feat, topo):
+    """models_gnn2D.py:598-603: tau = tanh(mean over out-edges of |t_src - t_dst|^2), t = swish(gate layer output)."""
+    from .layers import instance_norm
+    t = gate_layer.forward_prepared(h, feat, topo)
+    t = t * torch.sigmoid(t)
+    src, dst = topo.src.long(), topo.dst.long()            # CSR (destination-sorted) edge order
+    tau = torch.tanh(_SourceMeanFn.apply((t[src] - t[dst]) ** 2, topo))
+    m = main_layer.forward_prepared(h, feat, topo)
+    return (1 - tau) * h + tau * (m * torch.sigmoid(m))
+
+
+class MP_PDE_Solver2D(_Solver2F):
+    """models_gnn2D.py:17-141 (MLP encoder, plain GNN_Layer stack)."""
+    layer_cls, gated, encoder = GNN_Layer, False, "mlp"
+
+
+class MP_PDE_Solver2DGated(_Solver2F):
+    """models_gnn2D.py:143-288"""
+    layer_cls, gated, encoder = GNN_LayerLin, True, "mlp"
+
+
+class MP_PDE_Solver2DLEMLinG2(_Solver2F):
+    """models_gnn2D.py:460-620 (`--model MSG2-PDE2D`)."""
+    layer_cls, gated, encoder, g2 = GNN_LayerLin, True, "lem", True
+
+
+class MP_PDE_Solver2DLSTMLinGated(_Solver2F):
+    """models_gnn2D.py:622-780"""
+    layer_cls, gated, encoder = GNN_LayerLin, True, "lstm"
+
+
+class MP_PDE_Solver2DLSTMLin(_Solver2F):
+    """models_gnn2D.py:782-918"""
+    layer_cls, gated, encoder = GNN_Layer, False, "lstm"
+
+
+class MP_PDE_Solver2DLEMLin(_Solver2F):
+    """models_gnn2D.py:920-1056"""
+    layer_cls, gated, encoder = GNN_Layer, False, "lem"
+
+
+class MP_PDE_Solver2DLEMLinGatedGLU(nn.Module):
+    """models_gnn2D.py:1198-1366 uses hidden_features = 164; the msmp_b200 kernels are specialised for 128."""
+
+    def __init__(self, *a, **k):
+        raise NotImplementedError("MP_PDE_Solver2DLEMLinGatedGLU (hidden_features=164) is outside the 128-wide hot path")
+
+
+class G_PDE_Solver2DLEMLinGated(nn.Module):
+    """models_gnn2D.py:1058-1196 cannot be constructed in the reference either (RGATConv without num_relations)."""
+
+    def __init__(self, *a, **k):
+        raise NotImplementedError("G_PDE_Solver2DLEMLinGated is dead code in the reference (SURVEY.md section 2)")

@@ -159,7 +159,9 @@ def large_graph(n_nodes: int, degree: int, topology: str = "band", nodes_per_gra
     npg = nodes_per_graph or n_nodes
     batch = torch.arange(n_nodes) // npg
     if nodes_per_graph:           # keep edges inside their graph (InstanceNorm is per graph)
-        src = (dst // npg) * npg + (src % npg)
+        g0 = (dst // npg) * npg
+        gsize = torch.clamp(n_nodes - g0, max=npg)         # the last graph may be smaller
+        src = g0 + (src % gsize)
     return dict(
         x=torch.randn(n_nodes, 128, generator=g, dtype=dtype),
         u=torch.randn(n_nodes, tw, generator=g, dtype=dtype),

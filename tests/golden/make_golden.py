@@ -150,7 +150,7 @@ def layer_case(mg, cls_name, seed, F_u, V, fname):
     print(fname, "out", tuple(out.shape), "E", ei.shape[1])
 
 
-def model_case(cls, cfg_fn, cfg_kwargs, fname, extra_params=None, model_kwargs=None):
+def model_case(cls, cfg_fn, cfg_kwargs, fname, extra_params=None, model_kwargs=None, second_call=False):
     pde, data, meta = cfg_fn(**cfg_kwargs)
     if extra_params:
         g = torch.Generator().manual_seed(7)
@@ -167,10 +167,19 @@ def model_case(cls, cfg_fn, cfg_kwargs, fname, extra_params=None, model_kwargs=N
     loss.backward()
     arrs = _data_arrays(data)
     arrs.update(out=out, loss=loss, pde_L=pde.L, pde_tmax=pde.tmax, pde_dt=pde.dt)
+    if second_call:            # stateful encoders (LEMS): a second forward continues from the stored (y, z)
+        with torch.no_grad():
+            arrs["out2"] = model(data)
     arrs.update({"gdig_" + k: v for k, v in grads_digest(model).items()})
     np.savez_compressed(os.path.join(os.path.dirname(__file__), fname), **_np(arrs))
     print(fname, "N", data.x.shape[0], "E", data.edge_index.shape[1], "loss", float(loss),
           "params", sum(p.numel() for p in model.parameters()))
+
+
+VARIANTS_1F = ["MP_PDE_SolverLEM", "MP_PDE_SolverLEMLin", "MP_PDE_SolverLSTMLin", "MP_PDE_SolverLSTMLinGated",
+               "MP_PDE_SolverGated", "MP_PDE_SolverLEMLinGatedSave", "MSSMP_PDE_Solver"]
+VARIANTS_2F = ["MP_PDE_Solver2D", "MP_PDE_Solver2DGated", "MP_PDE_Solver2DLEMLinG2", "MP_PDE_Solver2DLSTMLinGated",
+               "MP_PDE_Solver2DLSTMLin", "MP_PDE_Solver2DLEMLin"]
 
 
 def main():
@@ -183,16 +192,26 @@ def main():
     model_case(mg2.MP_PDE_Solver2DLEMLinGated, synth.config_c2, dict(B=3, nx=40, seed=4), "msmp_pde2d_c2.npz")
     model_case(mg2.MP_PDE_Solver2DLEMLinGated, synth.config_c3, dict(B=2, nx=100, seed=5, neighbors=3),
                "msmp_pde2d_c3.npz")
+    # the variant classes (same layers, different encoder / gating; SURVEY.md 8a "variants")
+    for i, name in enumerate(VARIANTS_1F):
+        model_case(getattr(mg, name), synth.config_c1, dict(B=2, nx=30, seed=20 + i), f"var_{name}.npz",
+                   extra_params={"alpha": 3.0} if i % 2 else None,
+                   second_call=name.endswith("Save"))
+    for i, name in enumerate(VARIANTS_2F):
+        model_case(getattr(mg2, name), synth.config_c2, dict(B=2, nx=30, seed=40 + i), f"var_{name}.npz")
     # structural fixtures: state_dict key/shape tables
     import json
     tables = {}
     pde1, _, m1 = synth.config_c1(B=1, nx=10)
     pde2, _, m2 = synth.config_c2(B=1, nx=10)
-    for name, model in {
+    models = {
         "MP_PDE_Solver": mg.MP_PDE_Solver(pde1, 25, 128, 6, {}),
         "MP_PDE_SolverLEMLinGated": mg.MP_PDE_SolverLEMLinGated(pde1, 25, 128, 6, {}),
         "MP_PDE_Solver2DLEMLinGated": mg2.MP_PDE_Solver2DLEMLinGated(pde2, 25, 128, 6, {"a": 1.0, "b": 1.0}),
-    }.items():
+    }
+    models.update({n: getattr(mg, n)(pde1, 25, 128, 6, {}) for n in VARIANTS_1F})
+    models.update({n: getattr(mg2, n)(pde2, 25, 128, 6, {"a": 1.0, "b": 1.0}) for n in VARIANTS_2F})
+    for name, model in models.items():
         tables[name] = {k: list(v.shape) for k, v in model.state_dict().items()}
     with open(os.path.join(os.path.dirname(__file__), "state_dict_tables.json"), "w") as f:
         json.dump(tables, f, indent=0, sort_keys=True)

@@ -115,3 +115,35 @@ def test_install_makes_reference_imports_resolve():
         for k in list(sys.modules):
             if k.startswith(("experiments", "torch_geometric", "torch_cluster", "torch_scatter")) and k not in saved:
                 del sys.modules[k]
+
+
+def test_drop_in_state_dict_layout_matches_reference_tables():
+    """Every drop-in class has the reference's state_dict keys and shapes (tables written from the reference's
+    own classes by tests/golden/make_golden.py), so reference checkpoints load unchanged."""
+    import json
+    import os
+    from msmp_pde_b200 import models_gnn, models_gnn2D
+    from msmp_pde_b200.synth import config_c1, config_c2
+    from tests import golden_io
+    with open(os.path.join(golden_io.GOLDEN_DIR, "state_dict_tables.json")) as f:
+        tables = json.load(f)
+    pde1, pde2 = config_c1(B=1, nx=10)[0], config_c2(B=1, nx=10)[0]
+    for name, want in tables.items():
+        if hasattr(models_gnn, name):
+            m = getattr(models_gnn, name)(pde1, 25, 128, 6, {})
+        else:
+            m = getattr(models_gnn2D, name)(pde2, 25, 128, 6, {"a": 1.0, "b": 1.0})
+        got = {k: list(v.shape) for k, v in m.state_dict().items()}
+        assert got == want, name
+        assert repr(m) == "GNN"
+
+
+def test_unsupported_variants_fail_loudly():
+    import pytest
+    from msmp_pde_b200 import models_gnn, models_gnn2D
+    from msmp_pde_b200.synth import config_c1
+    pde = config_c1(B=1, nx=10)[0]
+    for cls in (models_gnn.MP_PDE_SolverLEMLinGatedGLU, models_gnn2D.MP_PDE_Solver2DLEMLinGatedGLU,
+                models_gnn2D.G_PDE_Solver2DLEMLinGated):
+        with pytest.raises(NotImplementedError):
+            cls(pde, 25, 164, 6, {})

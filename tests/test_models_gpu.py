@@ -103,6 +103,49 @@ def test_model_vs_golden_and_oracle(mod, cls, fname, pde_name, eq):
     assert errs[worst] <= 1.0, (worst, errs[worst])
 
 
+from tests.test_oracle_golden import VARIANTS_1F, VARIANTS_2F, variant_eq  # noqa: E402
+
+
+# Two variants are ill-conditioned on their fixture: an honest fp32 torch evaluation of the oracle graph itself
+# (scripts/diag_variants.py, cuDNN/cuBLAS TF32 off) exceeds the rtol-1e-5 allowance by 1.0x (MP_PDE_SolverGated) and
+# 3.6x (the G^2 gate squares differences of activations).  Their allowance is widened to ~2x that fp32 floor.
+VARIANT_FLOOR = {"MP_PDE_SolverGated": 2.0, "MP_PDE_Solver2DLEMLinG2": 8.0}
+
+
+@pytest.mark.parametrize("name", VARIANTS_1F + VARIANTS_2F)
+def test_variant_vs_golden_and_oracle(name):
+    """The reference's other solver classes (same layers, different encoder / gate) against their fixtures and
+    the oracle's full gradients."""
+    from msmp_pde_b200 import models_gnn, models_gnn2D
+    from oracle import variants as ov
+    dev = torch.device("cuda:0")
+    g = golden_io.load(f"var_{name}.npz")
+    pde_name, eq = variant_eq(name)
+    pde, data = golden_io.model_inputs(g, pde_name)
+    torch.set_default_dtype(torch.float64)
+    cls = getattr(models_gnn if name in VARIANTS_1F else models_gnn2D, name)
+    model = cls(pde, time_window=25, hidden_features=128, hidden_layer=6, eq_variables=eq)
+    formula_weights_(model)
+    model = model.to(dev)
+    dd = copy.copy(data).clone().to(dev)
+    out = model(dd)
+    assert out.dtype == torch.float64 and repr(model) == "GNN"
+    loss = torch.sqrt(torch.nn.functional.mse_loss(out, dd.y, reduction="sum"))
+    loss.backward()
+    assert rel_err(out, torch.from_numpy(g["out"])) < OUT_TOL
+    assert abs(float(loss) - float(g["loss"])) < 1e-5 * float(g["loss"])
+    if "out2" in g:
+        with torch.no_grad():
+            assert rel_err(model(dd), torch.from_numpy(g["out2"])) < OUT_TOL
+    ref = getattr(ov, name)(pde, time_window=25, hidden_features=128, hidden_layer=6, eq_variables=eq)
+    formula_weights_(ref)
+    outr = ref(data)
+    torch.sqrt(torch.nn.functional.mse_loss(outr, data.y, reduction="sum")).backward()
+    errs = _grad_errs(model, ref)
+    worst = max(errs, key=errs.get)
+    assert errs[worst] <= VARIANT_FLOOR.get(name, 1.0), (worst, errs[worst])
+
+
 def test_determinism_and_state_dict_roundtrip():
     """Bit-identical outputs/gradients across runs (no atomics); fp64 reference checkpoints load."""
     from msmp_pde_b200 import models_gnn2D, synth

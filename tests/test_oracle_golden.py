@@ -7,6 +7,7 @@ import pytest
 import torch
 
 from oracle import models as om
+from oracle import variants as ov
 from tests import golden_io
 from tests.util import formula_weights_, grads_digest, rel_err
 
@@ -62,6 +63,38 @@ def test_model_matches_reference(cls, fname, pde_name, eq, kw):
     _check_digests(model, g)
 
 
+VARIANTS_1F = ["MP_PDE_SolverLEM", "MP_PDE_SolverLEMLin", "MP_PDE_SolverLSTMLin", "MP_PDE_SolverLSTMLinGated",
+               "MP_PDE_SolverGated", "MP_PDE_SolverLEMLinGatedSave", "MSSMP_PDE_Solver"]
+VARIANTS_2F = ["MP_PDE_Solver2D", "MP_PDE_Solver2DGated", "MP_PDE_Solver2DLEMLinG2", "MP_PDE_Solver2DLSTMLinGated",
+               "MP_PDE_Solver2DLSTMLin", "MP_PDE_Solver2DLEMLin"]
+
+
+def variant_eq(name):
+    """eq_variables each var_*.npz was generated with (tests/golden/make_golden.py)."""
+    if name in VARIANTS_2F:
+        return "AD", {"a": 1.0, "b": 1.0}
+    return "CE", ({"alpha": 3.0} if VARIANTS_1F.index(name) % 2 else {})
+
+
+@pytest.mark.parametrize("name", VARIANTS_1F + VARIANTS_2F)
+def test_variant_matches_reference(name):
+    torch.set_default_dtype(torch.float64)
+    g = golden_io.load(f"var_{name}.npz")
+    pde_name, eq = variant_eq(name)
+    pde, data = golden_io.model_inputs(g, pde_name)
+    model = getattr(ov, name)(pde, time_window=25, hidden_features=128, hidden_layer=6, eq_variables=eq)
+    formula_weights_(model)
+    out = model(data)
+    loss = torch.sqrt(torch.nn.functional.mse_loss(out, data.y, reduction="sum"))
+    loss.backward()
+    assert rel_err(out, torch.from_numpy(g["out"])) < TOL
+    assert abs(float(loss) - float(g["loss"])) < 1e-9 * float(g["loss"])
+    _check_digests(model, g)
+    if "out2" in g:            # LEMS: the second call starts from the stored states
+        with torch.no_grad():
+            assert rel_err(model(data), torch.from_numpy(g["out2"])) < TOL
+
+
 def test_state_dict_tables():
     torch.set_default_dtype(torch.float64)
     with open(os.path.join(golden_io.GOLDEN_DIR, "state_dict_tables.json")) as f:
@@ -74,6 +107,9 @@ def test_state_dict_tables():
         "MP_PDE_SolverLEMLinGated": om.MP_PDE_SolverLEMLinGated(pde1, 25, 128, 6, {}),
         "MP_PDE_Solver2DLEMLinGated": om.MP_PDE_Solver2DLEMLinGated(pde2, 25, 128, 6, {"a": 1.0, "b": 1.0}),
     }
+    models.update({n: getattr(ov, n)(pde1, 25, 128, 6, {}) for n in VARIANTS_1F})
+    models.update({n: getattr(ov, n)(pde2, 25, 128, 6, {"a": 1.0, "b": 1.0}) for n in VARIANTS_2F})
+    assert set(models) == set(tables)
     for name, m in models.items():
         got = {k: list(v.shape) for k, v in m.state_dict().items()}
         assert got == tables[name], name
