@@ -216,7 +216,10 @@ def run_ours(args):
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 8},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
             "ops": table, "scatter_hbm": scatter,
-            "execution": "eager launches" if args.eager else "whole step captured as one CUDA graph (GraphedTrainStep)",
+            "execution": ("eager launches" if args.eager else
+                          "whole step captured as one CUDA graph (GraphedTrainStep)" if world == 1 else
+                          "three CUDA graphs per step (forward+loss | backward | AdamW) with the NCCL all-reduces of the "
+                          "loss terms and of the flat gradient bucket launched eagerly between them"),
         }
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(sample_graphs=8, steps=2)

@@ -64,6 +64,15 @@ int msmp_linear_tc_fwd(const float* const* A, const int* lda, const int* ka, con
 int msmp_pack_job_bytes(void);
 int msmp_pack_run(const void* jobs_dev, int njobs, int max_chunks, cudaStream_t stream);
 
+/* The inverse direction, once per backward pass: the weight-gradient kernels leave k-major blocks ([K][N], side and
+ * bias rows) in a raw buffer; one launch writes the parameter-layout gradients (what autograd's AccumulateGrad of
+ * the reference's nn.Linear / lem_cuda.backward outputs would hold, experiments/models_gnn.py:300) from records
+ * {float* dst; const float* src0, *src1; int ldd, ld0, ld1, rows, cols; float sign1; int zero}
+ * (msmp_unpack_job_bytes() bytes each):  dst[n*ldd + k] = src0[k*ld0 + n] (+ sign1 * src1[k*ld1 + n]),
+ * n < rows, k < cols; zeros when `zero`.  max_tiles = max over jobs of ceil(rows/32) * ceil(cols/32). */
+int msmp_unpack_job_bytes(void);
+int msmp_unpack_run(const void* jobs_dev, int njobs, int max_tiles, cudaStream_t stream);
+
 /* dWt[K, Nout] (+)= X[M, K]^T (swish(X) if xswish) * dY[M, Nout];
  * dWside[r (+1), Nout] (+)= [side | 1]^T * dY  (bias gradient = the implicit ones column when has_bias).
  * Deterministic: per-CTA partials over row ranges + fixed-order reduction. */
@@ -174,13 +183,17 @@ int msmp_decoder_bwd(const float* dout, const float* h, const float* za, const f
  * Backward: Wzh_img / Wh_img = images of Wz[:, :128] ([128 x 128]) and W[:, :128] ([384 x 128]) read as k-major;
  * gYt / gZt lane-major external gradients ([T] slabs, or one slab for t = T-1 when g_last_only; may be NULL);
  * dyt / dzt lane-major [Npad/32][128][32], zero on entry, gradient wrt the initial state on exit; s0 / s2 scratch
- * of the same shape; dG [T][N][384], dL [T][N][128] row-major feed the weight-gradient GEMMs. */
+ * of the same shape; dG [T][N][384], dL [T][N][128] row-major feed the weight-gradient GEMMs.
+ * One backward launch walks the steps t = t_end-1 .. t_begin; a caller that wants to overlap the weight-gradient
+ * GEMMs of finished steps with the rest of the recurrence splits [0, T) into consecutive launches, last range first
+ * (dyt / dzt carry the state gradient between them). */
 int msmp_lem_tc_fwd(const float* inp, int ninp, const float* Wt_in, const float* Wzt_in, const float* Wimg,
                     const float* Wzimg, const float* bias, const float* bias_z, float* pre, float* Y, float* Z,
                     float* Yt, float* Zt, float* gates, float dt, int T, int N, int Npad, cudaStream_t stream);
 int msmp_lem_tc_bwd(const float* Wzh_img, const float* Wh_img, const float* Yt, const float* Zt, const float* gates,
                     const float* gYt, const float* gZt, int g_last_only, float* dG, float* dL, float* dyt, float* dzt,
-                    float* s0, float* s2, float dt, int T, int N, int Npad, cudaStream_t stream);
+                    float* s0, float* s2, float dt, int T, int t_begin, int t_end, int N, int Npad,
+                    cudaStream_t stream);
 
 /* out[i] = g[i] * swish'(z[i])  (n % 4 == 0) */
 int msmp_mul_dswish(const float* g, const float* z, float* out, size_t n, cudaStream_t stream);

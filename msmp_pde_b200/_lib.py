@@ -40,6 +40,8 @@ _SIGS = {
     "msmp_linear_tc_fwd": (I, [P, P, P, P, I, P, P, P, I, I, P, I, P, I, P, I, I, P, I, P, I, I, I, P]),
     "msmp_pack_job_bytes": (I, []),
     "msmp_pack_run": (I, [P, I, I, P]),
+    "msmp_unpack_job_bytes": (I, []),
+    "msmp_unpack_run": (I, [P, I, I, P]),
     "msmp_linear_wgrad_splits": (I, [I, I, I]),
     "msmp_linear_wgrad_workspace": (S, [I, I, I, I]),
     "msmp_linear_wgrad": (I, [P, I, I, I, P, I, I, P, I, I, I, P, P, I, I, P, S, P]),
@@ -63,7 +65,7 @@ _SIGS = {
     "msmp_decoder_fwd": (I, [P, P, P, P, P, P, I, P, P, P, I, I, I, I, I, I, I, P]),
     "msmp_decoder_bwd": (I, [P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, P, S, P]),
     "msmp_lem_tc_fwd": (I, [P, I, P, P, P, P, P, P, P, P, P, P, P, P, F, I, I, I, P]),
-    "msmp_lem_tc_bwd": (I, [P, P, P, P, P, P, P, I, P, P, P, P, P, P, F, I, I, I, P]),
+    "msmp_lem_tc_bwd": (I, [P, P, P, P, P, P, P, I, P, P, P, P, P, P, F, I, I, I, I, I, P]),
     "msmp_lem_gate_z": (I, [P, P, F, P, P, I, P]),
     "msmp_lem_gate_y": (I, [P, P, P, P, I, P]),
     "msmp_lem_bwd_y": (I, [P, P, P, P, F, P, P, I, P]),

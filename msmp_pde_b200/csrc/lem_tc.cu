@@ -363,6 +363,7 @@ struct LemBwdParams {
   float* s2;             // lane-major scratch                      (dG2 of the current step)
   float dt;
   int T; int N; int Npad;
+  int t_begin; int t_end;   // this launch walks t = t_end-1 .. t_begin (the carried dy/dz live in dyt/dzt between launches)
 };
 
 __global__ void __launch_bounds__(256, 1) k_lem_bwd_tc(const LemBwdParams p) {
@@ -416,7 +417,7 @@ __global__ void __launch_bounds__(256, 1) k_lem_bwd_tc(const LemBwdParams p) {
     __syncthreads();
   };
 
-  for (int t = p.T - 1; t >= 0; --t) {
+  for (int t = p.t_end - 1; t >= p.t_begin; --t) {
     const float* g_t = p.gates + ((size_t)t * ntile) * 512 * 32;
     const float* yprev = p.Yt + ((size_t)t * ntile) * 128 * 32;
     const float* zprev = p.Zt + ((size_t)t * ntile) * 128 * 32;
@@ -424,7 +425,7 @@ __global__ void __launch_bounds__(256, 1) k_lem_bwd_tc(const LemBwdParams p) {
     const float* gy = (p.gYt && ext) ? p.gYt + (p.g_last_only ? 0 : (size_t)t * ntile * 128 * 32) : nullptr;
     const float* gz = (p.gZt && ext) ? p.gZt + (p.g_last_only ? 0 : (size_t)t * ntile * 128 * 32) : nullptr;
     float* dG_t = p.dG + (size_t)t * p.N * 384;
-    if (t > 0) {      // next step's saved activations (written by the forward pass, now in HBM) -> L2
+    if (t > p.t_begin) {      // next step's saved activations (written by the forward pass, now in HBM) -> L2
       const float* g_n = p.gates + ((size_t)(t - 1) * ntile) * 512 * 32;
 #pragma unroll
       for (int q = 0; q < 4; ++q) prefetch_lm(g_n, gt, 512, 128 * q + c0, 64, lane);
@@ -556,11 +557,12 @@ extern "C" int msmp_lem_tc_fwd(const float* inp, int ninp, const float* Wt_in, c
 
 extern "C" int msmp_lem_tc_bwd(const float* Wzh_img, const float* Wh_img, const float* Yt, const float* Zt,
                                const float* gates, const float* gYt, const float* gZt, int g_last_only, float* dG,
-                               float* dL, float* dyt, float* dzt, float* s0, float* s2, float dt, int T, int N, int Npad,
-                               cudaStream_t stream) {
-  if (T < 0 || N < 0 || Npad < N || (Npad & 127)) return MSMP_ERR_ARG;
-  if (T == 0 || N == 0) return MSMP_OK;
-  LemBwdParams p{Wzh_img, Wh_img, Yt, Zt, gates, gYt, gZt, g_last_only, dG, dL, dyt, dzt, s0, s2, dt, T, N, Npad};
+                               float* dL, float* dyt, float* dzt, float* s0, float* s2, float dt, int T, int t_begin,
+                               int t_end, int N, int Npad, cudaStream_t stream) {
+  if (T < 0 || N < 0 || Npad < N || (Npad & 127) || t_begin < 0 || t_end > T || t_begin > t_end) return MSMP_ERR_ARG;
+  if (t_begin == t_end || N == 0) return MSMP_OK;
+  LemBwdParams p{Wzh_img, Wh_img, Yt, Zt, gates, gYt, gZt, g_last_only, dG, dL, dyt, dzt, s0, s2, dt, T, N, Npad,
+                 t_begin, t_end};
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(k_lem_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_SMEM) != cudaSuccess)

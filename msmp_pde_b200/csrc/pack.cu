@@ -56,7 +56,65 @@ __global__ void __launch_bounds__(256) k_pack(const PackJob* __restrict__ jobs) 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// The inverse direction, once per backward pass: the weight-gradient kernels leave their results in the kernels'
+// k-major layouts inside one raw buffer ([K][N] blocks, side / bias rows); ONE launch scatters them into the
+// parameter-layout gradients (param.grad), overwriting them:
+//     dst[n * ldd + k] = src0[k * ld0 + n] (+ sign1 * src1[k * ld1 + n])      n < rows, k < cols     (or 0 if `zero`)
+// i.e. a transposed copy with an optional second signed source (the +/- rows of the factorised first message layer).
+struct UnpackJob {
+  float* dst;
+  const float* src0;
+  const float* src1;
+  int ldd;
+  int ld0;
+  int ld1;
+  int rows;
+  int cols;
+  float sign1;
+  int zero;
+};
+
+__global__ void __launch_bounds__(256) k_unpack(const UnpackJob* __restrict__ jobs) {
+  __shared__ float tile[32][33];
+  const UnpackJob j = jobs[blockIdx.y];
+  const int tn = (j.rows + 31) >> 5, tk = (j.cols + 31) >> 5;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int ti = blockIdx.x; ti < tn * tk; ti += gridDim.x) {
+    const int n0 = (ti % tn) << 5, k0 = (ti / tn) << 5;
+#pragma unroll
+    for (int y = ty; y < 32; y += 8) {
+      const int k = k0 + y, n = n0 + tx;
+      float v = 0.f;
+      if (!j.zero && k < j.cols && n < j.rows) {
+        v = j.src0[(size_t)k * j.ld0 + n];
+        if (j.src1) v += j.sign1 * j.src1[(size_t)k * j.ld1 + n];
+      }
+      tile[y][tx] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int y = ty; y < 32; y += 8) {
+      const int n = n0 + y, k = k0 + tx;
+      if (n < j.rows && k < j.cols) j.dst[(size_t)n * j.ldd + k] = tile[tx][y];
+    }
+    __syncthreads();
+  }
+}
+
 }  // namespace msmp
+
+extern "C" int msmp_unpack_job_bytes(void) { return (int)sizeof(msmp::UnpackJob); }
+
+// jobs_dev: device array of `njobs` UnpackJob records (layout above; see msmp_pde_b200/gradsink.py)
+extern "C" int msmp_unpack_run(const void* jobs_dev, int njobs, int max_tiles, cudaStream_t stream) {
+  if (njobs < 0 || max_tiles < 1) return MSMP_ERR_ARG;
+  if (njobs == 0) return MSMP_OK;
+  dim3 grid(max_tiles < 16 ? max_tiles : 16, njobs);
+  msmp::k_unpack<<<grid, 256, 0, stream>>>(reinterpret_cast<const msmp::UnpackJob*>(jobs_dev));
+  MSMP_CHECK_LAUNCH();
+  return MSMP_OK;
+}
 
 extern "C" int msmp_pack_job_bytes(void) { return (int)sizeof(msmp::PackJob); }
 

@@ -98,10 +98,10 @@ class LayerPack:
 
 class _Aux:
     """Non-tensor arguments of the layer function."""
-    __slots__ = ("topo", "feat", "pack", "final")
+    __slots__ = ("topo", "feat", "pack", "final", "gsink")
 
-    def __init__(self, topo: Topology, feat: NodeFeatures, pack: LayerPack, final: bool):
-        self.topo, self.feat, self.pack, self.final = topo, feat, pack, final
+    def __init__(self, topo: Topology, feat: NodeFeatures, pack: LayerPack, final: bool, gsink=None):
+        self.topo, self.feat, self.pack, self.final, self.gsink = topo, feat, pack, final, gsink
 
 
 class _LayerCoreFn(torch.autograd.Function):
@@ -139,6 +139,13 @@ class _LayerCoreFn(torch.autograd.Function):
         cur = torch.cuda.current_stream()
         wst = _side_stream(cur, h.device, "wgrad")
         tc = ops.GEMM_MODE == "tc"
+        # GraphedTrainStep: raw weight gradients stay in the model-wide sink (gradsink.GradPlan), nothing is joined here
+        plan = ops.GRAD_SINK
+        if plan is not None and not (tc and topo.E > 0):
+            raise RuntimeError("GraphedTrainStep's gradient sink needs the tensor-core path and a graph with edges")
+        gs = aux.gsink if plan is not None else None
+        if gs is not None:
+            plan.streams.add(wst)
 
         def on_side(fn, *deps):
             wst.wait_stream(cur)
@@ -147,30 +154,37 @@ class _LayerCoreFn(torch.autograd.Function):
             with torch.cuda.stream(wst):
                 return fn()
 
+        def raw(name):
+            return getattr(gs, name) if gs is not None else None
+
         # update_net_2
-        dW4t, dW4s = on_side(lambda: ops.linear_wgrad(z3, dz4, xswish=True, has_bias=True), z3, dz4)
+        dW4t, dW4s = on_side(lambda: ops.linear_wgrad(z3, dz4, xswish=True, has_bias=True, dWt=raw("dW4t"),
+                                                      dWside=raw("dW4s")), z3, dz4)
         dz3 = ops.linear_fwd([dz4], pk.W4d, Zmul=z3)
         # update_net_1
-        dW3t = torch.empty(2 * H, H, dtype=torch.float32, device=dev)
-        _, dW3s = on_side(lambda: ops.linear_wgrad(h, dz3, X1=agg, side=ft.side[:, 1:], r=V, has_bias=True, dWt=dW3t),
-                          h, agg, dz3, dW3t)
+        dW3t = raw("dW3t") if gs is not None else torch.empty(2 * H, H, dtype=torch.float32, device=dev)
+        _, dW3s = on_side(lambda: ops.linear_wgrad(h, dz3, X1=agg, side=ft.side[:, 1:], r=V, has_bias=True, dWt=dW3t,
+                                                   dWside=raw("dW3s")), h, agg, dz3, dW3t)
         dcat = ops.linear_fwd([dz3], pk.W3hx)                          # [N,256] = [dh (via x) | dagg]
         # message path
         dPQ = torch.empty(N, 2 * H, dtype=torch.float32, device=dev)
         if tc and topo.E > 0:
             dz1, a1, dz2 = ops.edge_bwd(PQ[:, :H], PQ[:, H:], topo, pk.W2d, z2, dcat[:, H:], dPQ[:, :H], defer_wgrad=True)
-            dW2t_, db2s = on_side(lambda: ops.linear_wgrad(a1, dz2, has_bias=True), a1, dz2)
+            dW2t_, db2s = on_side(lambda: ops.linear_wgrad(a1, dz2, has_bias=True, dWt=raw("dW2t"), dWside=raw("db2s")),
+                                  a1, dz2)
             dW2, db2 = dW2t_.t(), db2s[0]
         else:
             dz1, dW2, db2 = ops.edge_bwd(PQ[:, :H], PQ[:, H:], topo, pk.W2d, z2, dcat[:, H:], dPQ[:, :H])
         ops.segment_reduce(dz1, topo.colptr, perm=topo.csc_perm, out=dPQ[:, H:], N=N)
         Kp = H + ft.upad.shape[1]
-        dWpq_t = torch.empty(Kp, 2 * H, dtype=torch.float32, device=dev)
-        _, dWs = on_side(lambda: ops.linear_wgrad(h, dPQ, X1=ft.upad, side=ft.side, r=1 + V, has_bias=True, dWt=dWpq_t),
-                         dPQ, dWpq_t)
+        dWpq_t = raw("dWpq_t") if gs is not None else torch.empty(Kp, 2 * H, dtype=torch.float32, device=dev)
+        _, dWs = on_side(lambda: ops.linear_wgrad(h, dPQ, X1=ft.upad, side=ft.side, r=1 + V, has_bias=True, dWt=dWpq_t,
+                                                  dWside=raw("dWs")), dPQ, dWpq_t)
         dh = ops.linear_fwd([dPQ], pk.W1hq, R=dcat[:, :H])
         if aux.final:
             dh = dh + dy
+        if gs is not None:
+            return dh, None, None, None, None, None, None, None, None, None
         cur.wait_stream(wst)
         for t in (dW4t, dW4s, dW3t, dW3s, dWpq_t, dWs, dW2, db2):
             t.record_stream(cur)
@@ -268,7 +282,7 @@ class _LayerBase(nn.Module):
         """h -> propagate(h) (before the norm)."""
         if feat.F_u != self.time_window or feat.V != self.n_variables:
             raise ValueError("node feature widths do not match the layer")
-        aux = _Aux(topo, feat, self.pack(), self.final_swish)
+        aux = _Aux(topo, feat, self.pack(), self.final_swish, self.__dict__.get("_msmp_gsink"))
         return _LayerCoreFn.apply(h, *self._params(), aux)
 
     def forward_prepared(self, h, feat, topo):

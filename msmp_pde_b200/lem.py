@@ -20,7 +20,7 @@ import torch
 from torch import nn
 
 from . import ops
-from .layers import H, pad32
+from .layers import H, _side_stream, pad32
 
 
 class _LEMFn(torch.autograd.Function):
@@ -29,7 +29,7 @@ class _LEMFn(torch.autograd.Function):
     whole history (what LEM / LEMS consume, models_gnn.py:340-342,354-357)."""
 
     @staticmethod
-    def forward(ctx, inputs, weights, weights_lin_z, bias, bias_lin_z, y0, z0, dt, packs, last_only):
+    def forward(ctx, inputs, weights, weights_lin_z, bias, bias_lin_z, y0, z0, dt, packs, last_only, gsink=None):
         T, N, ninp = inputs.shape
         dev = inputs.device
         ip = pad32(ninp)
@@ -54,6 +54,7 @@ class _LEMFn(torch.autograd.Function):
                 ops.lem_gate_y(L, Y[t], gates[t], Y[t + 1])
             ctx.save_for_backward(inp, Y, Z, gates)
         ctx.dt, ctx.ninp, ctx.packs, ctx.persistent, ctx.last_only = dt, ninp, packs, persistent, last_only
+        ctx.gsink = gsink
         if last_only:
             return Y[T], Z[T]
         return Y[1:], Z[1:]
@@ -69,12 +70,49 @@ class _LEMFn(torch.autograd.Function):
         gY, gZ = gY.contiguous(), gZ.contiguous()
         dG = torch.empty(T, N, 3 * H, dtype=torch.float32, device=dev)
         dL = torch.empty(T, N, H, dtype=torch.float32, device=dev)
+        Kp = H + ip
+        gs = ctx.gsink if (ops.GRAD_SINK is not None and ctx.persistent) else None
+        if gs is not None:       # GraphedTrainStep: raw gradients stay in the sink, the side stream is joined once per step
+            dWt, dWzt, dbias, dbz = gs.dWt, gs.dWzt, gs.dbias, gs.dbz
+        else:
+            dWt = torch.empty(Kp, 3 * H, dtype=torch.float32, device=dev)
+            dWzt = torch.empty(Kp, H, dtype=torch.float32, device=dev)
+            dbias = torch.empty(1, 3 * H, dtype=torch.float32, device=dev)
+            dbz = torch.empty(1, H, dtype=torch.float32, device=dev)
+
+        def wgrads(t0, t1, accumulate):
+            """weight gradients of steps [t0, t1) (M = (t1 - t0) * N rows per GEMM)"""
+            rows = (t1 - t0) * N
+            inpf = inp[t0:t1].view(rows, ip)
+            ops.linear_wgrad(Y[t0:t1].view(rows, H), dG[t0:t1].view(rows, 3 * H), X1=inpf, has_bias=True, dWt=dWt,
+                             dWside=dbias, accumulate=accumulate)
+            ops.linear_wgrad(Z[1 + t0:1 + t1].view(rows, H), dL[t0:t1].view(rows, H), X1=inpf, has_bias=True, dWt=dWzt,
+                             dWside=dbz, accumulate=accumulate)
+
         if ctx.persistent:
+            # The recurrence runs on Npad / 128 SMs only; it is cut into LEM_BWD_SEGMENTS launches so that the weight
+            # gradient GEMMs of the steps already walked run on a side stream next to the remaining steps.
             Yt, Zt = saved[4], saved[5]
             Npad = Yt.shape[1] * 32
-            dyt, dzt = ops.lem_tc_bwd(Wzh, Wh, Yt, Zt, gates, ops.to_lane_major(gY, Npad), ops.to_lane_major(gZ, Npad),
-                                      ctx.last_only, dG, dL, dt, N)
-            dy, dz = ops.from_lane_major(dyt, N), ops.from_lane_major(dzt, N)
+            gYt, gZt = ops.to_lane_major(gY, Npad), ops.to_lane_major(gZ, Npad)
+            state = ops.lem_tc_bwd_state(gates)
+            cur = torch.cuda.current_stream()
+            wst = _side_stream(cur, dev, "wgrad")
+            nseg = max(1, min(ops.LEM_BWD_SEGMENTS, T))
+            bounds = [T * i // nseg for i in range(nseg + 1)]
+            for i in range(nseg - 1, -1, -1):
+                t0, t1 = bounds[i], bounds[i + 1]
+                ops.lem_tc_bwd(Wzh, Wh, Yt, Zt, gates, gYt, gZt, ctx.last_only, dG, dL, dt, N, state, t0, t1)
+                wst.wait_stream(cur)
+                with torch.cuda.stream(wst):
+                    wgrads(t0, t1, accumulate=i != nseg - 1)
+            for t_ in (inp, Y, Z, dG, dL, dWt, dWzt, dbias, dbz):
+                t_.record_stream(wst)
+            dy, dz = ops.from_lane_major(state[0], N), ops.from_lane_major(state[1], N)
+            if gs is not None:
+                ops.GRAD_SINK.streams.add(wst)
+                return None, None, None, None, None, dy, dz, None, None, None, None
+            cur.wait_stream(wst)
         else:
             if ctx.last_only:
                 gy_full = torch.zeros(T, N, H, dtype=torch.float32, device=dev)
@@ -93,17 +131,10 @@ class _LEMFn(torch.autograd.Function):
                 ops.lem_bwd_z(dz_tot, gZ[t], Z[t], gates[t], dt, dG[t], dz)
                 # dy_{t-1} += dG W[:, :H]
                 ops.linear_fwd([dG[t]], Wh, R=dy, out=dy)
-        # weight gradients over all steps at once (M = T*N rows)
-        Kp = H + ip
-        dWt = torch.empty(Kp, 3 * H, dtype=torch.float32, device=dev)
-        dGf, dLf = dG.view(T * N, 3 * H), dL.view(T * N, H)
-        inpf = inp.view(T * N, ip)
-        _, dbias = ops.linear_wgrad(Y[:T].view(T * N, H), dGf, X1=inpf, has_bias=True, dWt=dWt)
-        dWzt = torch.empty(Kp, H, dtype=torch.float32, device=dev)
-        _, dbz = ops.linear_wgrad(Z[1:].reshape(T * N, H), dLf, X1=inpf, has_bias=True, dWt=dWzt)
+            wgrads(0, T, accumulate=False)
         dW = torch.cat([dWt[:H].t(), dWt[H:H + ninp].t()], 1)
         dWz = torch.cat([dWzt[:H].t(), dWzt[H:H + ninp].t()], 1)
-        return None, dW, dWz, dbias[0], dbz[0], dy, dz, None, None, None
+        return None, dW, dWz, dbias[0], dbz[0], dy, dz, None, None, None, None
 
 
 class LEMcuda(nn.Module):
@@ -157,7 +188,7 @@ class LEMcuda(nn.Module):
         else:
             y, z = states[0].float().contiguous(), states[1].float().contiguous()
         return _LEMFn.apply(x, self.weights, self.weights_lin_z, self.bias, self.bias_lin_z, y, z, self.dt,
-                            self.packs(), last_only)
+                            self.packs(), last_only, self.__dict__.get("_msmp_gsink"))
 
 
 class LEM(nn.Module):

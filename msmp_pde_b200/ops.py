@@ -82,6 +82,12 @@ def _p(t):
 GEMM_MODE = "tc"
 # Persistent (all-T-steps-in-one-launch) LEM kernels; False = one GEMM + one gate kernel per step.
 LEM_PERSISTENT = True
+# The persistent backward recurrence is cut into this many launches; the weight-gradient GEMMs of finished steps
+# overlap the remaining ones on a side stream (lem._LEMFn.backward).
+LEM_BWD_SEGMENTS = 5
+# gradsink.GradPlan of the backward pass in flight (set by GraphedTrainStep): the backward Functions then leave their
+# weight gradients in the plan's raw buffer and return None for the parameters; None = plain autograd behaviour.
+GRAD_SINK = None
 _IMG_CACHE: dict = {}
 
 
@@ -385,13 +391,14 @@ def decoder_fwd(h, w1, b1, w2, b2, u, dt, geom):
     return out, za
 
 
-def decoder_bwd(dout, h, za, w1, w2, dt, geom):
+def decoder_bwd(dout, h, za, w1, w2, dt, geom, dW=None):
     """Returns (dh [N, C*128], dW flat [w1 | b1 | w2 | b2])."""
     C, K1, S1, L1, K2, TW = geom
     N = h.shape[0]
     dev = h.device
     dh = torch.empty_like(h)
-    dW = torch.empty(lib.msmp_decoder_nweights(C, K1, K2), dtype=torch.float32, device=dev)
+    if dW is None:
+        dW = torch.empty(lib.msmp_decoder_nweights(C, K1, K2), dtype=torch.float32, device=dev)
     ws = _workspace(lib.msmp_decoder_bwd_workspace(N, C, K1, K2), dev)
     check(lib.msmp_decoder_bwd(dout.data_ptr(), h.data_ptr(), za.data_ptr(), w1.data_ptr(), w2.data_ptr(),
                                dt.data_ptr(), dh.data_ptr(), dW.data_ptr(), N, C, K1, S1, L1, K2, TW, ws.data_ptr(),
@@ -443,19 +450,28 @@ def lem_tc_fwd(inp, ninp, Wt_in, Wzt_in, Wt_h, Wzt_h, bias, bias_z, Y, Z, dt):
     return Yt, Zt, gates
 
 
-def lem_tc_bwd(Wzh, Wh, Yt, Zt, gates, gYt, gZt, last_only, dG, dL, dt, N):
-    """Returns the lane-major gradients (dyt, dzt) wrt the initial state; fills dG [T,N,384], dL [T,N,128]."""
-    T, nt = gates.shape[0], gates.shape[1]
-    Npad = nt * 32
-    dev = gates.device
+def lem_tc_bwd_state(gates):
+    """(dyt, dzt, s0, s2): zeroed carried state gradients and scratch slabs of one backward recurrence."""
+    nt, dev = gates.shape[1], gates.device
     dyt = torch.zeros(nt, H, 32, dtype=torch.float32, device=dev)
     dzt = torch.zeros(nt, H, 32, dtype=torch.float32, device=dev)
     s0 = torch.empty(nt, H, 32, dtype=torch.float32, device=dev)
     s2 = torch.empty(nt, H, 32, dtype=torch.float32, device=dev)
-    with _timed("lem_tc_bwd", 2.0 * T * N * H * 4 * H, 4.0 * T * N * (512 + 512 + 6 * H)):
+    return dyt, dzt, s0, s2
+
+
+def lem_tc_bwd(Wzh, Wh, Yt, Zt, gates, gYt, gZt, last_only, dG, dL, dt, N, state, t_begin=0, t_end=None):
+    """Steps t_end-1 .. t_begin of the backward recurrence (state = lem_tc_bwd_state(); dyt / dzt carry the gradient
+    between calls and hold d/d(y0, z0) after the call with t_begin = 0); fills dG[t], dL[t] of those steps."""
+    T, nt = gates.shape[0], gates.shape[1]
+    t_end = T if t_end is None else t_end
+    Npad = nt * 32
+    dyt, dzt, s0, s2 = state
+    nst = t_end - t_begin
+    with _timed("lem_tc_bwd", 2.0 * nst * N * H * 4 * H, 4.0 * nst * N * (512 + 512 + 6 * H)):
       check(lib.msmp_lem_tc_bwd(_img_of(Wzh).data_ptr(), _img_of(Wh).data_ptr(), Yt.data_ptr(),
                               Zt.data_ptr(), gates.data_ptr(), _p(gYt), _p(gZt), int(bool(last_only)), dG.data_ptr(),
                               dL.data_ptr(), dyt.data_ptr(), dzt.data_ptr(), s0.data_ptr(), s2.data_ptr(), float(dt),
-                              T, N, Npad, _stream()), "msmp_lem_tc_bwd")
+                              T, t_begin, t_end, N, Npad, _stream()), "msmp_lem_tc_bwd")
     _count(1)
     return dyt, dzt

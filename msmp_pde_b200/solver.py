@@ -5,7 +5,7 @@ import torch
 from torch import nn
 
 from . import ops
-from .layers import H, NodeFeatures, Swish, pad32
+from .layers import H, NodeFeatures, Swish, _side_stream, pad32
 
 _EQ_ORDER_1F = ("alpha", "beta", "gamma", "bc_left", "bc_right", "c", "D", "r")
 
@@ -27,13 +27,13 @@ class _LinearActFn(torch.autograd.Function):
     """y = act(x W^T + b) on msmp_linear_fwd / msmp_linear_wgrad.  x is [M, Kp] with Kp % 32 == 0 (zero padded)."""
 
     @staticmethod
-    def forward(ctx, x, W, b, act: bool, packs):
+    def forward(ctx, x, W, b, act: bool, packs, gsink=None):
         Nout, K = W.shape
         x = x.contiguous()
         Wt, Wd = packs
         z = torch.empty(x.shape[0], Nout, dtype=torch.float32, device=x.device) if act else None
         y = ops.linear_fwd([x], Wt, bias=b, Ypre=z, act=act)
-        ctx.act, ctx.K, ctx.Wd = act, K, Wd
+        ctx.act, ctx.K, ctx.Wd, ctx.gsink = act, K, Wd, gsink
         ctx.save_for_backward(x, z)
         return y
 
@@ -42,13 +42,26 @@ class _LinearActFn(torch.autograd.Function):
         x, z = ctx.saved_tensors
         dy = dy.contiguous()
         dz = ops.mul_dswish(dy, z) if ctx.act else dy
-        dWt, dbs = ops.linear_wgrad(x, dz, has_bias=True)
+        gs = ctx.gsink if (ops.GRAD_SINK is not None and ops.GEMM_MODE == "tc") else None
+        if gs is not None:       # GraphedTrainStep: raw gradient stays in the sink, side stream joined once per step
+            cur = torch.cuda.current_stream()
+            wst = _side_stream(cur, x.device, "wgrad")
+            ops.GRAD_SINK.streams.add(wst)
+            wst.wait_stream(cur)
+            x.record_stream(wst)
+            dz.record_stream(wst)
+            with torch.cuda.stream(wst):
+                ops.linear_wgrad(x, dz, has_bias=True, dWt=gs.dWt, dWside=gs.dbs)
+        else:
+            dWt, dbs = ops.linear_wgrad(x, dz, has_bias=True)
         dx = None
         if ctx.needs_input_grad[0]:
             if ctx.K != x.shape[1]:
                 raise RuntimeError("input gradient of a zero-padded linear layer is not needed on this path")
             dx = ops.linear_fwd([dz], ctx.Wd)       # W [Nout][K] is the reduction-major dgrad operand
-        return dx, dWt[:ctx.K].t(), dbs[0], None, None
+        if gs is not None:
+            return dx, None, None, None, None, None
+        return dx, dWt[:ctx.K].t(), dbs[0], None, None, None
 
 
 def _linear_packs(linear: nn.Linear, Kp: int):
@@ -65,7 +78,8 @@ def _linear_packs(linear: nn.Linear, Kp: int):
 
 
 def linear_act(x, linear: nn.Linear, act: bool = True):
-    return _LinearActFn.apply(x, linear.weight, linear.bias, act, _linear_packs(linear, x.shape[1]))
+    return _LinearActFn.apply(x, linear.weight, linear.bias, act, _linear_packs(linear, x.shape[1]),
+                              linear.__dict__.get("_msmp_gsink"))
 
 
 def pad_cols(x: torch.Tensor) -> torch.Tensor:
@@ -100,10 +114,10 @@ class _DecoderFn(torch.autograd.Function):
     """out = base(u) + dt * Conv1d(Swish(Conv1d(h)))  on msmp_decoder_fwd / msmp_decoder_bwd."""
 
     @staticmethod
-    def forward(ctx, h, w1, b1, w2, b2, u, dt, geom):
+    def forward(ctx, h, w1, b1, w2, b2, u, dt, geom, gsink=None):
         h = h.contiguous()
         out, za = ops.decoder_fwd(h, w1, b1, w2, b2, u, dt, geom)
-        ctx.geom = geom
+        ctx.geom, ctx.gsink = geom, gsink
         ctx.save_for_backward(h, za, w1, w2, dt)
         return out
 
@@ -111,11 +125,14 @@ class _DecoderFn(torch.autograd.Function):
     def backward(ctx, dout):
         h, za, w1, w2, dt = ctx.saved_tensors
         C, K1, S1, L1, K2, TW = ctx.geom
-        dh, dW = ops.decoder_bwd(dout.contiguous(), h, za, w1, w2, dt, ctx.geom)
+        gs = ctx.gsink if ops.GRAD_SINK is not None else None
+        dh, dW = ops.decoder_bwd(dout.contiguous(), h, za, w1, w2, dt, ctx.geom, dW=gs.dW if gs is not None else None)
+        if gs is not None:
+            return dh, None, None, None, None, None, None, None, None
         n1 = 8 * C * K1
         n2 = C * 8 * K2
         return (dh, dW[:n1].view(8, C, K1), dW[n1:n1 + 8], dW[n1 + 8:n1 + 8 + n2].view(C, 8, K2),
-                dW[n1 + 8 + n2:], None, None, None)
+                dW[n1 + 8 + n2:], None, None, None, None)
 
 
 def decode(h, output_mlp: nn.Sequential, u, dt, channels: int, time_window: int):
@@ -124,7 +141,8 @@ def decode(h, output_mlp: nn.Sequential, u, dt, channels: int, time_window: int)
     K1, S1, K2 = c1.kernel_size[0], c1.stride[0], c2.kernel_size[0]
     L1 = (H - K1) // S1 + 1
     geom = (channels, K1, S1, L1, K2, time_window)
-    return _DecoderFn.apply(h, c1.weight, c1.bias, c2.weight, c2.bias, u, dt.reshape(-1).contiguous(), geom)
+    return _DecoderFn.apply(h, c1.weight, c1.bias, c2.weight, c2.bias, u, dt.reshape(-1).contiguous(), geom,
+                            output_mlp.__dict__.get("_msmp_gsink"))
 
 
 def cumulative_dt(pde, time_window, device):

@@ -87,6 +87,7 @@ class GraphedTrainStep:
         self.fields = [k for k in self.static.keys()
                        if torch.is_tensor(getattr(self.static, k)) and getattr(self.static, k).is_floating_point()]
         self.bucket = FlatGradBucket(model.parameters())
+        self.gplan = None          # gradsink.GradPlan, built after the first eager step (the packs exist by then)
         self.use_graph = use_graph
         self.graph = None
         self.graphs = None
@@ -97,8 +98,10 @@ class GraphedTrainStep:
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
-            for _ in range(warmup):
+            for i in range(max(warmup, 1)):
                 self._eager_step()
+                if i == 0:
+                    self._make_grad_plan()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         if not use_graph:
@@ -121,21 +124,50 @@ class GraphedTrainStep:
         torch.cuda.synchronize()
 
     # ---- pieces of one step -------------------------------------------------------------------------
+    def _make_grad_plan(self):
+        """Route the weight gradients of the msmp modules through one unpack launch (gradsink.py); models without
+        tensor-core packs (or foreign modules only) keep plain autograd accumulation."""
+        from . import ops
+        if ops.GEMM_MODE != "tc" or self.model.__dict__.get("_msmp_pack_plan") is None and not any(
+                m.__dict__.get("_msmp_pack_plan") is not None for m in self.model.modules()):
+            return
+        from .gradsink import GradPlan
+        self.gplan = GradPlan(self.model)
+
     def _fwd(self):
-        self.bucket.zero_()
+        if self.gplan is None:
+            self.bucket.zero_()          # with a GradPlan the covered gradients are overwritten, the others zeroed in begin()
+        self._fwd_stream = torch.cuda.current_stream()
         pred = self.model(self.static)
         self._sse_local = ((pred - self.static.y) ** 2).sum()          # train_helper.py:126 (reduction='sum')
+        self._sse_val = self._sse_local.detach()                       # same storage, no autograd graph
 
     def _reduce_loss(self):
         """global SSE (all ranks) -> loss and the backward seed d loss / d sse_local = 1 / (2 loss)."""
-        self._sse_total.copy_(self._sse_local.detach())
+        self._sse_total.copy_(self._sse_val)
         if self.world > 1:
             dist.all_reduce(self._sse_total, group=self.group)
         self.loss = torch.sqrt(self._sse_total)
         self._seed.copy_(0.5 / self.loss)
 
     def _bwd(self):
-        self._sse_local.backward(self._seed.to(self._sse_local.dtype))
+        # The AccumulateGrad nodes of this step were created on the forward's stream and the engine syncs the
+        # caller's stream with it after the backward pass even when a node only saw an undefined gradient (the
+        # sink returns None for the parameters).  When the backward runs on another stream (separate CUDA graphs
+        # in the data-parallel step) that stream is forked here so the sync stays inside the capture.
+        cur = torch.cuda.current_stream()
+        if self._fwd_stream != cur:
+            self._fwd_stream.wait_stream(cur)
+        if self.gplan is not None:
+            self.gplan.begin()
+        try:
+            self._sse_local.backward(self._seed.to(self._sse_local.dtype))
+        finally:
+            if self.gplan is not None:
+                self.gplan.finish()
+            # drop the autograd graph now: AccumulateGrad nodes kept alive across steps stay bound to the stream of
+            # the step that created them (a warm-up stream outside any later capture)
+            self._sse_local = None
 
     def _eager_step(self):
         self._fwd()

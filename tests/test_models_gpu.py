@@ -240,3 +240,35 @@ def test_rollout_reuses_topology_and_no_grad():
     assert torch.equal(p1, ref1)
     assert len(G._CACHE) == n_topo == 1                          # edge_index identity unchanged => one topology
     assert p2.shape == p1.shape and bool(torch.isfinite(p2).all())
+
+
+@pytest.mark.parametrize("mod,name", [("models_gnn2D", "MP_PDE_Solver2DLEMLinGated"), ("models_gnn", "MP_PDE_Solver"),
+                                      ("models_gnn", "MP_PDE_SolverLSTMLin"), ("models_gnn", "MSSMP_PDE_Solver")])
+@pytest.mark.parametrize("graphed", [False, True])
+def test_train_step_gradient_sink_equals_autograd(mod, name, graphed):
+    """GraphedTrainStep leaves the raw weight gradients in one buffer and writes every param.grad with a single
+    unpack launch (gradsink.py): the result must equal plain autograd accumulation bit for bit."""
+    import importlib
+    from msmp_pde_b200 import synth
+    from msmp_pde_b200.train_step import GraphedTrainStep
+    dev = torch.device("cuda:0")
+    two = mod == "models_gnn2D"
+    pde, data, meta = (synth.config_c2 if two else synth.config_c1)(B=3, nx=50, seed=5)
+    torch.manual_seed(1)
+    cls = getattr(importlib.import_module("msmp_pde_b200." + mod), name)
+    model = cls(pde, 25, 128, 6, meta["eq_variables"]).to(dev)
+    ref = copy.deepcopy(model)
+    g = data.clone().to(dev)
+    opt = torch.optim.AdamW(model.parameters(), lr=0.0, weight_decay=0.0, fused=True, capturable=True)
+    step = GraphedTrainStep(model, opt, g, warmup=2, use_graph=graphed)
+    assert step.gplan is not None
+    for p in model.parameters():              # poison: the unpack launch must overwrite, not accumulate
+        p.grad.fill_(123.0)
+    step(g)
+    torch.cuda.synchronize()
+    out = ref(g)
+    sse = ((out - g.y) ** 2).sum()
+    sse.backward(step._seed.to(sse.dtype))
+    assert abs(float(step.loss) - float(torch.sqrt(sse))) < 1e-9 * float(step.loss)
+    for (n, p), (_, q) in zip(model.named_parameters(), ref.named_parameters()):
+        assert torch.equal(p.grad, q.grad), n
