@@ -21,11 +21,14 @@ _SIDE_STREAMS: dict = {}
 
 
 def _side_stream(cur, device, tag):
-    """A helper stream per (device, current stream, role); created once."""
+    """A helper stream per (device, current stream, role); created once.  Weight-gradient streams get the lowest
+    priority and everything else (gate layers) a high one: the dgrad chain is the critical path of the backward pass,
+    so when both have thread blocks pending the chain's are scheduled first (GraphedTrainStep also runs its main
+    stream at high priority; stream priorities are recorded in captured kernel nodes)."""
     key = (device.index, cur.cuda_stream, tag)
     st = _SIDE_STREAMS.get(key)
     if st is None:
-        st = torch.cuda.Stream(device=device)
+        st = torch.cuda.Stream(device=device, priority=0 if tag == "wgrad" else -1)
         _SIDE_STREAMS[key] = st
     return st
 

@@ -95,7 +95,7 @@ class GraphedTrainStep:
         dev = self.bucket.flat.device
         self._sse_total = torch.zeros((), dtype=torch.float64, device=dev)
         self._seed = torch.zeros((), dtype=torch.float64, device=dev)
-        side = torch.cuda.Stream()
+        side = torch.cuda.Stream(priority=-1)      # high priority: weight-gradient side streams run below it
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for i in range(max(warmup, 1)):
@@ -108,17 +108,17 @@ class GraphedTrainStep:
             return
         if self.world == 1:
             self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph):
+            with torch.cuda.graph(self.graph, stream=side):
                 self._eager_step()
         else:
             g_fwd, g_bwd, g_opt = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g_fwd):
+            with torch.cuda.graph(g_fwd, stream=side):
                 self._fwd()
             self._reduce_loss()
-            with torch.cuda.graph(g_bwd, pool=g_fwd.pool()):
+            with torch.cuda.graph(g_bwd, pool=g_fwd.pool(), stream=side):
                 self._bwd()
             self.bucket.all_reduce(self.group)
-            with torch.cuda.graph(g_opt, pool=g_fwd.pool()):
+            with torch.cuda.graph(g_opt, pool=g_fwd.pool(), stream=side):
                 self.opt.step()
             self.graphs = (g_fwd, g_bwd, g_opt)
         torch.cuda.synchronize()
