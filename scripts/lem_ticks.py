@@ -13,7 +13,11 @@ torch.cuda.synchronize()
 buf = (ctypes.c_longlong * 64)()
 _lib.lib.msmp_lem_debug_ticks.argtypes = [ctypes.c_void_p]
 _lib.lib.msmp_lem_debug_ticks(buf)
-t = list(buf)[:7]
-names = ["G gemm (12 chunks)", "gate_z epilogue", "image->Z", "L gemm (4 chunks)", "gate_y epilogue", "image->Y"]
-for i, n in enumerate(names):
-    print(f"{n:22s} {t[i+1]-t[i]:8d} cycles")
+t = list(buf)
+seq = [(0, "start"), (1, "G gemm issued+done (gemm_wait)"), (10, "gate_z: tmem ld + first batch math"), (11, "wait_peer_free"),
+       (12, "gate_z: remaining batches + stores"), (2, "publish (fence + bar + remote arrive)"),
+       (13, "L gemm issue (incl. wait xfull)"), (3, "Z copy-out"), (4, "L gemm wait"), (5, "gate_y epilogue + publish"),
+       (6, "Y copy-out")]
+for (i0, _), (i1, name) in zip(seq[:-1], seq[1:]):
+    print(f"{name:45s} {t[i1]-t[i0]:8d} cycles")
+print("step total", t[6] - t[0])
