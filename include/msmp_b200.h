@@ -172,28 +172,27 @@ int msmp_decoder_bwd(const float* dout, const float* h, const float* za, const f
                      const float* dt, float* dh, float* dW, int N, int C, int K1, int S1, int L1, int K2, int TW,
                      void* workspace, size_t ws_bytes, cudaStream_t stream);
 
-/* Persistent tensor-core LEM: ALL T steps in one launch, one CTA per 128 nodes (the recurrence is per node).
- * inp [T][N][32] zero-padded inputs (ninp <= 8 real columns).  Npad = N rounded up to 128.  Arrays private to the
- * recurrence are LANE-MAJOR: element (row n, channel c) of a C-channel array at ((n/32)*C + c)*32 + n%32.
- *   pre   lane-major [T][Npad/32][512][32] scratch: [bias | bias_z] + inp [Wt_in | Wzt_in], Wt_in / Wzt_in = rows
- *         128.. of the k-major packs W^T [160 x 384] / Wz^T [160 x 128]
+/* Persistent tensor-core LEM: ALL T steps in one launch, one CTA per 64 nodes (the recurrence is per node); the
+ * GEMMs are issued transposed (weights = A operand, state tile = B operand, N = 64 nodes), see csrc/lem_tc.cu.
+ * inp [T][N][32] zero-padded inputs (ninp <= 8 real columns).  Npad = N rounded up to 64.  Every array is row-major.
+ *   Wt_in / Wzt_in = rows 128.. of the k-major packs W^T [160 x 384] / Wz^T [160 x 128]: the input part of both
+ *         affine maps, bias + inp . w_in, is evaluated in registers inside the gate epilogues
  *   Wimg / Wzimg: tile images (msmp_linear_tc_fwd format) of the STATE rows W^T[:128] / Wz^T[:128]
- *   Y, Z  row-major [T+1][N][128] (Y[0], Z[0] = initial state);  Yt, Zt lane-major copies (slab 0 initialised)
- *   gates lane-major [T][Npad/32][512][32] = a | b | zc | tL
+ *   Y, Z  [T+1][N][128] (Y[0], Z[0] = initial state; slabs 1..T are written)
+ *   gates [T][Npad][512] = a | b | zc | tL  (kept for the backward)
  * Backward: Wzh_img / Wh_img = images of Wz[:, :128] ([128 x 128]) and W[:, :128] ([384 x 128]) read as k-major;
- * gYt / gZt lane-major external gradients ([T] slabs, or one slab for t = T-1 when g_last_only; may be NULL);
- * dyt / dzt lane-major [Npad/32][128][32], zero on entry, gradient wrt the initial state on exit; s0 / s2 scratch
- * of the same shape; dG [T][N][384], dL [T][N][128] row-major feed the weight-gradient GEMMs.
+ * gY / gZ external gradients ([T][N][128], or [N][128] for t = T-1 when g_last_only; may be NULL);
+ * dy / dz [Npad][128], zero on entry, gradient wrt the initial state on exit; dG [T][N][384], dL [T][N][128] feed
+ * the weight-gradient GEMMs.
  * One backward launch walks the steps t = t_end-1 .. t_begin; a caller that wants to overlap the weight-gradient
  * GEMMs of finished steps with the rest of the recurrence splits [0, T) into consecutive launches, last range first
- * (dyt / dzt carry the state gradient between them). */
+ * (dy / dz carry the state gradient between them). */
 int msmp_lem_tc_fwd(const float* inp, int ninp, const float* Wt_in, const float* Wzt_in, const float* Wimg,
-                    const float* Wzimg, const float* bias, const float* bias_z, float* pre, float* Y, float* Z,
-                    float* Yt, float* Zt, float* gates, float dt, int T, int N, int Npad, cudaStream_t stream);
-int msmp_lem_tc_bwd(const float* Wzh_img, const float* Wh_img, const float* Yt, const float* Zt, const float* gates,
-                    const float* gYt, const float* gZt, int g_last_only, float* dG, float* dL, float* dyt, float* dzt,
-                    float* s0, float* s2, float dt, int T, int t_begin, int t_end, int N, int Npad,
-                    cudaStream_t stream);
+                    const float* Wzimg, const float* bias, const float* bias_z, float* Y, float* Z, float* gates,
+                    float dt, int T, int N, int Npad, cudaStream_t stream);
+int msmp_lem_tc_bwd(const float* Wzh_img, const float* Wh_img, const float* Y, const float* Z, const float* gates,
+                    const float* gY, const float* gZ, int g_last_only, float* dG, float* dL, float* dy, float* dz,
+                    float dt, int T, int t_begin, int t_end, int N, int Npad, cudaStream_t stream);
 
 /* out[i] = g[i] * swish'(z[i])  (n % 4 == 0) */
 int msmp_mul_dswish(const float* g, const float* z, float* out, size_t n, cudaStream_t stream);

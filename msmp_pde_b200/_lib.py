@@ -64,8 +64,8 @@ _SIGS = {
     "msmp_decoder_bwd_workspace": (S, [I, I, I, I]),
     "msmp_decoder_fwd": (I, [P, P, P, P, P, P, I, P, P, P, I, I, I, I, I, I, I, P]),
     "msmp_decoder_bwd": (I, [P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, P, S, P]),
-    "msmp_lem_tc_fwd": (I, [P, I, P, P, P, P, P, P, P, P, P, P, P, P, F, I, I, I, P]),
-    "msmp_lem_tc_bwd": (I, [P, P, P, P, P, P, P, I, P, P, P, P, P, P, F, I, I, I, I, I, P]),
+    "msmp_lem_tc_fwd": (I, [P, I, P, P, P, P, P, P, P, P, P, F, I, I, I, P]),
+    "msmp_lem_tc_bwd": (I, [P, P, P, P, P, P, P, I, P, P, P, P, F, I, I, I, I, I, P]),
     "msmp_lem_gate_z": (I, [P, P, F, P, P, I, P]),
     "msmp_lem_gate_y": (I, [P, P, P, P, I, P]),
     "msmp_lem_bwd_y": (I, [P, P, P, P, F, P, P, I, P]),

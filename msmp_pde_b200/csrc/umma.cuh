@@ -91,6 +91,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// 32 lanes x 8 consecutive columns (issue only; pair with tmem_ld_wait before using the values)
+__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 // ---- descriptors ----------------------------------------------------------------------------------
 // Shared-memory matrix descriptor, SWIZZLE_128B, sm_100 version field.  lbo / sbo in bytes.
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint32_t layout_type = 2) {
@@ -116,6 +124,22 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// One lane of a fully converged warp (the same lane on every call).  tcgen05.mma takes its descriptors from the
+// uniform datapath: issue it from a warp that runs the whole issue loop convergently with warp-uniform operands and
+// guard only the instruction itself with elect_one().  A lone `if (threadIdx.x == 0)` thread makes the compiler
+// broadcast every operand through R2UR for every MMA (measured: ~100 cycles per tcgen05.mma instead of its 32-64).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, q;\n\t}"
+      : "=r"(ok));
+  return ok != 0;
+}
+// warp index that the compiler can prove warp-uniform
+__device__ __forceinline__ int warp_index_uniform() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+
 // All previously issued MMAs of this thread arrive on the mbarrier when they complete.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))

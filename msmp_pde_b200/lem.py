@@ -41,8 +41,8 @@ class _LEMFn(torch.autograd.Function):
         Y[0], Z[0] = y0, z0
         persistent = ops.GEMM_MODE == "tc" and ops.LEM_PERSISTENT and ip == 32 and ninp <= 8
         if persistent:
-            Yt, Zt, gates = ops.lem_tc_fwd(inp, ninp, Wt_in, Wzt_in, Wt_h, Wzt_h, bias, bias_lin_z, Y, Z, dt)
-            ctx.save_for_backward(inp, Y, Z, gates, Yt, Zt)
+            gates = ops.lem_tc_fwd(inp, ninp, Wt_in, Wzt_in, Wt_h, Wzt_h, bias, bias_lin_z, Y, Z, dt)
+            ctx.save_for_backward(inp, Y, Z, gates)
         else:
             gates = torch.empty(T, 4, N, H, dtype=torch.float32, device=dev)   # dt_bar, dt_z, tanh(G2), tanh(L)
             G = torch.empty(N, 3 * H, dtype=torch.float32, device=dev)
@@ -92,9 +92,6 @@ class _LEMFn(torch.autograd.Function):
         if ctx.persistent:
             # The recurrence runs on Npad / 128 SMs only; it is cut into LEM_BWD_SEGMENTS launches so that the weight
             # gradient GEMMs of the steps already walked run on a side stream next to the remaining steps.
-            Yt, Zt = saved[4], saved[5]
-            Npad = Yt.shape[1] * 32
-            gYt, gZt = ops.to_lane_major(gY, Npad), ops.to_lane_major(gZ, Npad)
             state = ops.lem_tc_bwd_state(gates)
             cur = torch.cuda.current_stream()
             wst = _side_stream(cur, dev, "wgrad")
@@ -102,13 +99,13 @@ class _LEMFn(torch.autograd.Function):
             bounds = [T * i // nseg for i in range(nseg + 1)]
             for i in range(nseg - 1, -1, -1):
                 t0, t1 = bounds[i], bounds[i + 1]
-                ops.lem_tc_bwd(Wzh, Wh, Yt, Zt, gates, gYt, gZt, ctx.last_only, dG, dL, dt, N, state, t0, t1)
+                ops.lem_tc_bwd(Wzh, Wh, Y, Z, gates, gY, gZ, ctx.last_only, dG, dL, dt, N, state, t0, t1)
                 wst.wait_stream(cur)
                 with torch.cuda.stream(wst):
                     wgrads(t0, t1, accumulate=i != nseg - 1)
             for t_ in (inp, Y, Z, dG, dL, dWt, dWzt, dbias, dbz):
                 t_.record_stream(wst)
-            dy, dz = ops.from_lane_major(state[0], N), ops.from_lane_major(state[1], N)
+            dy, dz = state[0][:N], state[1][:N]
             if gs is not None:
                 ops.GRAD_SINK.streams.add(wst)
                 return None, None, None, None, None, dy, dz, None, None, None, None

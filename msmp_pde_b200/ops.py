@@ -427,51 +427,44 @@ def _img_of(w):
     return w.img if isinstance(w, TcW) else _cached_images(w)
 
 
+LEM_TILE = 64         # nodes per CTA of the persistent LEM kernels (csrc/lem_tc.cu LT_NODES)
+
+
 def lem_tc_fwd(inp, ninp, Wt_in, Wzt_in, Wt_h, Wzt_h, bias, bias_z, Y, Z, dt):
-    """Persistent tensor-core LEM forward (input projection + all T steps, two launches).
+    """Persistent tensor-core LEM forward (input projection fused, all T steps, one launch).
     Wt_in [>= ninp, 384] / Wzt_in [>= ninp, 128]: input rows of the k-major W^T / Wz^T; Wt_h / Wzt_h: their state rows
-    (TcW images or k-major tensors).  Y, Z: row-major [T+1, N, 128] with slab 0 set.
-    Returns the lane-major (Yt, Zt, gates) kept for the backward."""
+    (TcW images or k-major tensors).  Y, Z: row-major [T+1, N, 128] with slab 0 set; slabs 1..T are written.
+    Returns the gate activations [T, Npad, 512] kept for the backward."""
     T, N = inp.shape[0], inp.shape[1]
-    Npad = (N + 127) // 128 * 128
+    Npad = (N + LEM_TILE - 1) // LEM_TILE * LEM_TILE
     dev = inp.device
-    pre = torch.empty(T, Npad // 32, 512, 32, dtype=torch.float32, device=dev)
-    gates = torch.empty(T, Npad // 32, 512, 32, dtype=torch.float32, device=dev)
-    Yt = torch.empty(T + 1, Npad // 32, H, 32, dtype=torch.float32, device=dev)
-    Zt = torch.empty(T + 1, Npad // 32, H, 32, dtype=torch.float32, device=dev)
-    Yt[0] = to_lane_major(Y[0], Npad)
-    Zt[0] = to_lane_major(Z[0], Npad)
-    with _timed("lem_tc_fwd", 2.0 * T * N * H * 4 * H, 4.0 * T * N * (512 * 2 + 4 * H)):
+    gates = torch.empty(T, Npad, 512, dtype=torch.float32, device=dev)
+    with _timed("lem_tc_fwd", 2.0 * T * N * H * 4 * H, 4.0 * T * N * (512 + 4 * H + 8)):
       check(lib.msmp_lem_tc_fwd(inp.data_ptr(), int(ninp), Wt_in.data_ptr(), Wzt_in.data_ptr(), _img_of(Wt_h).data_ptr(),
-                              _img_of(Wzt_h).data_ptr(), bias.data_ptr(), bias_z.data_ptr(), pre.data_ptr(),
-                              Y.data_ptr(), Z.data_ptr(), Yt.data_ptr(), Zt.data_ptr(), gates.data_ptr(), float(dt), T,
-                              N, Npad, _stream()), "msmp_lem_tc_fwd")
-    _count(2)
-    return Yt, Zt, gates
+                              _img_of(Wzt_h).data_ptr(), bias.data_ptr(), bias_z.data_ptr(),
+                              Y.data_ptr(), Z.data_ptr(), gates.data_ptr(), float(dt), T, N, Npad, _stream()),
+            "msmp_lem_tc_fwd")
+    _count(1)
+    return gates
 
 
 def lem_tc_bwd_state(gates):
-    """(dyt, dzt, s0, s2): zeroed carried state gradients and scratch slabs of one backward recurrence."""
-    nt, dev = gates.shape[1], gates.device
-    dyt = torch.zeros(nt, H, 32, dtype=torch.float32, device=dev)
-    dzt = torch.zeros(nt, H, 32, dtype=torch.float32, device=dev)
-    s0 = torch.empty(nt, H, 32, dtype=torch.float32, device=dev)
-    s2 = torch.empty(nt, H, 32, dtype=torch.float32, device=dev)
-    return dyt, dzt, s0, s2
+    """(dy, dz): zeroed carried state gradients [Npad, 128] of one backward recurrence."""
+    Npad, dev = gates.shape[1], gates.device
+    return (torch.zeros(Npad, H, dtype=torch.float32, device=dev), torch.zeros(Npad, H, dtype=torch.float32, device=dev))
 
 
-def lem_tc_bwd(Wzh, Wh, Yt, Zt, gates, gYt, gZt, last_only, dG, dL, dt, N, state, t_begin=0, t_end=None):
-    """Steps t_end-1 .. t_begin of the backward recurrence (state = lem_tc_bwd_state(); dyt / dzt carry the gradient
-    between calls and hold d/d(y0, z0) after the call with t_begin = 0); fills dG[t], dL[t] of those steps."""
-    T, nt = gates.shape[0], gates.shape[1]
+def lem_tc_bwd(Wzh, Wh, Y, Z, gates, gY, gZ, last_only, dG, dL, dt, N, state, t_begin=0, t_end=None):
+    """Steps t_end-1 .. t_begin of the backward recurrence (state = lem_tc_bwd_state(); dy / dz carry the gradient
+    between calls and hold d/d(y0, z0) in their first N rows after the call with t_begin = 0); fills dG[t], dL[t]."""
+    T, Npad = gates.shape[0], gates.shape[1]
     t_end = T if t_end is None else t_end
-    Npad = nt * 32
-    dyt, dzt, s0, s2 = state
+    dy, dz = state
     nst = t_end - t_begin
     with _timed("lem_tc_bwd", 2.0 * nst * N * H * 4 * H, 4.0 * nst * N * (512 + 512 + 6 * H)):
-      check(lib.msmp_lem_tc_bwd(_img_of(Wzh).data_ptr(), _img_of(Wh).data_ptr(), Yt.data_ptr(),
-                              Zt.data_ptr(), gates.data_ptr(), _p(gYt), _p(gZt), int(bool(last_only)), dG.data_ptr(),
-                              dL.data_ptr(), dyt.data_ptr(), dzt.data_ptr(), s0.data_ptr(), s2.data_ptr(), float(dt),
-                              T, t_begin, t_end, N, Npad, _stream()), "msmp_lem_tc_bwd")
+      check(lib.msmp_lem_tc_bwd(_img_of(Wzh).data_ptr(), _img_of(Wh).data_ptr(), Y.data_ptr(), Z.data_ptr(),
+                              gates.data_ptr(), _p(gY), _p(gZ), int(bool(last_only)), dG.data_ptr(), dL.data_ptr(),
+                              dy.data_ptr(), dz.data_ptr(), float(dt), T, t_begin, t_end, N, Npad, _stream()),
+            "msmp_lem_tc_bwd")
     _count(1)
-    return dyt, dzt
+    return dy, dz

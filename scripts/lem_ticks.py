@@ -6,7 +6,8 @@ from msmp_pde_b200.lem import LEMcuda
 dev = torch.device("cuda:0")
 ops.LEM_PERSISTENT = True
 rnn = LEMcuda(6, 128, 1.0).to(dev)
-x = torch.randn(25, 6400, 6, device=dev)
+NN = int(os.environ.get('NN', 6400))
+x = torch.randn(25, NN, 6, device=dev)
 for _ in range(3):
     ys, zs = rnn(x, last_only=True)
 torch.cuda.synchronize()
@@ -14,10 +15,12 @@ buf = (ctypes.c_longlong * 64)()
 _lib.lib.msmp_lem_debug_ticks.argtypes = [ctypes.c_void_p]
 _lib.lib.msmp_lem_debug_ticks(buf)
 t = list(buf)
-seq = [(0, "start"), (1, "G gemm issued+done (gemm_wait)"), (10, "gate_z: tmem ld + first batch math"), (11, "wait_peer_free"),
-       (12, "gate_z: remaining batches + stores"), (2, "publish (fence + bar + remote arrive)"),
-       (13, "L gemm issue (incl. wait xfull)"), (3, "Z copy-out"), (4, "L gemm wait"), (5, "gate_y epilogue + publish"),
-       (6, "Y copy-out")]
+seq = [(0, "start"), (1, "G gemm (12 chunks) issue + wait"), (2, "gate_z epilogue + publish"),
+       (3, "L gemm (4 chunks) issue + wait"), (4, "gate_y epilogue + publish")]
 for (i0, _), (i1, name) in zip(seq[:-1], seq[1:]):
     print(f"{name:45s} {t[i1]-t[i0]:8d} cycles")
-print("step total", t[6] - t[0])
+print("step total", t[4] - t[0])
+
+print("per chunk (cycles since step start): data-ready, issued")
+for j in range(16):
+    print(j, t[16 + 2 * j] - t[0], t[17 + 2 * j] - t[0])
