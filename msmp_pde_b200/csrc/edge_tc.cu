@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(256, 1) k_edge_tc(const EdgeTcParams p) {
   int* s_dst = s_src + ETC_TILE;
   int* seg_start = s_dst + ETC_TILE;                                 // [129]
   int* s_misc = seg_start + ETC_TILE + 1;                            // [5]
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = warp_index_uniform(), lane = tid & 31;
 
   if (warp == 0) tmem_alloc(tmem_slot, 128);
   if (tid == 32) {
@@ -125,23 +125,28 @@ __global__ void __launch_bounds__(256, 1) k_edge_tc(const EdgeTcParams p) {
       if (c + 1 < 4) gather(c + 1);
       fence_proxy_async();
       __syncthreads();
-      if (tid == 0) {
+      if (warp == 0) {      // the whole warp runs the issue code convergently, one elected lane issues (see elect_one())
         if (!w_ready) {
           mbar_wait(&bars[0], 0);
           w_ready = true;
         }
         tc_fence_after();
+        const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
         const uint32_t a_hi = smem_u32(st), a_lo = a_hi + IMG_BYTES;
         const uint32_t b_hi = smem_u32(smW + c * 2 * IMG_BYTES), b_lo = b_hi + IMG_BYTES;
+        const bool leader = elect_one();
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const uint64_t dah = umma_desc(a_hi + 32 * k, 16, 1024), dal = umma_desc(a_lo + 32 * k, 16, 1024);
           const uint64_t dbh = umma_desc(b_hi + 32 * k, 16, 1024), dbl = umma_desc(b_lo + 32 * k, 16, 1024);
-          umma_tf32(tmem, dah, dbh, IDESC, (c | k) ? 1u : 0u);
-          umma_tf32(tmem, dal, dbh, IDESC, 1u);
-          umma_tf32(tmem, dah, dbl, IDESC, 1u);
+          if (leader) {
+            umma_tf32(tm, dah, dbh, IDESC, (c | k) ? 1u : 0u);
+            umma_tf32(tm, dal, dbh, IDESC, 1u);
+            umma_tf32(tm, dah, dbl, IDESC, 1u);
+          }
         }
-        umma_commit(&bars[1 + s]);
+        if (leader) umma_commit(&bars[1 + s]);
+        __syncwarp();
       }
     }
     // ---- wait for the accumulator: both stages' last commits (also frees the A ring for the tile below)

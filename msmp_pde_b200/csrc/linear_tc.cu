@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(256, 1) k_linear_tc(const LinTcParams p) {
   uint8_t* smemB = smem + TC_A_STAGES * TC_A_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smemB + TC_B_STAGES * TC_B_BYTES);     // bfull[4], done[2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = warp_index_uniform(), lane = tid & 31;
   const int row0 = blockIdx.x * 128;
   const int ntile = blockIdx.y;
 
@@ -124,20 +124,25 @@ __global__ void __launch_bounds__(256, 1) k_linear_tc(const LinTcParams p) {
     if (c + 1 < nchunks) prefetch(c + 1);
     fence_proxy_async();
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0) {      // the whole warp runs the issue code convergently, one elected lane issues (see elect_one())
       mbar_wait(&bars[c & 3], (c >> 2) & 1);                         // weights of this chunk have landed
       tc_fence_after();
+      const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
       const uint32_t a_hi = smem_u32(st), a_lo = a_hi + IMG_BYTES;
       const uint32_t b_hi = smem_u32(smemB + (c & 3) * TC_B_BYTES), b_lo = b_hi + IMG_BYTES;
+      const bool leader = elect_one();
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const uint64_t dah = umma_desc(a_hi + 32 * k, 16, 1024), dal = umma_desc(a_lo + 32 * k, 16, 1024);
         const uint64_t dbh = umma_desc(b_hi + 32 * k, 16, 1024), dbl = umma_desc(b_lo + 32 * k, 16, 1024);
-        umma_tf32(tmem, dah, dbh, IDESC, (c | k) ? 1u : 0u);
-        umma_tf32(tmem, dal, dbh, IDESC, 1u);
-        umma_tf32(tmem, dah, dbl, IDESC, 1u);
+        if (leader) {
+          umma_tf32(tm, dah, dbh, IDESC, (c | k) ? 1u : 0u);
+          umma_tf32(tm, dal, dbh, IDESC, 1u);
+          umma_tf32(tm, dah, dbl, IDESC, 1u);
+        }
       }
-      umma_commit(&bars[4 + s]);
+      if (leader) umma_commit(&bars[4 + s]);
+      __syncwarp();
     }
   }
   // accumulator complete when the last commit arrives

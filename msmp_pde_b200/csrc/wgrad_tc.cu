@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(256, 1) k_wgrad_tc(const WgradTcParams p) {
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * WT_STAGE_BYTES);     // free[2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
   float* sred = reinterpret_cast<float*>(smem + 2 * WT_STAGE_BYTES + 256);     // [8 warps][8 side rows][128]
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = warp_index_uniform(), lane = tid & 31;
   const int split = blockIdx.x;
   const int k0 = blockIdx.y * 128, n0 = blockIdx.z * 128;
   // column block of X handled by this CTA: [X | X1] concatenated at K0 (K0 % 128 == 0 when X1 is given)
@@ -119,19 +119,24 @@ __global__ void __launch_bounds__(256, 1) k_wgrad_tc(const WgradTcParams p) {
     if (c + 1 < nchunks) prefetch(c + 1);
     fence_proxy_async();
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0) {      // the whole warp runs the issue code convergently, one elected lane issues (see elect_one())
       tc_fence_after();
+      const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
       const uint32_t xh = smem_u32(st), xl = xh + WT_OP_BYTES, yh = xh + 2 * WT_OP_BYTES, yl = xh + 3 * WT_OP_BYTES;
+      const bool leader = elect_one();
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const uint32_t ko = 1024 * k;      // 8 rows per k-step; LBO = 4096 (next 32 columns), SBO = 512 (next 4 rows)
         const uint64_t dxh = umma_desc(xh + ko, 4096, 512, 1), dxl = umma_desc(xl + ko, 4096, 512, 1);
         const uint64_t dyh = umma_desc(yh + ko, 4096, 512, 1), dyl = umma_desc(yl + ko, 4096, 512, 1);
-        umma_tf32(tmem, dxh, dyh, IDESC, (c | k) ? 1u : 0u);
-        umma_tf32(tmem, dxl, dyh, IDESC, 1u);
-        umma_tf32(tmem, dxh, dyl, IDESC, 1u);
+        if (leader) {
+          umma_tf32(tm, dxh, dyh, IDESC, (c | k) ? 1u : 0u);
+          umma_tf32(tm, dxl, dyh, IDESC, 1u);
+          umma_tf32(tm, dxh, dyl, IDESC, 1u);
+        }
       }
-      umma_commit(&bars[s]);
+      if (leader) umma_commit(&bars[s]);
+      __syncwarp();
     }
   }
   float* out = p.part + (size_t)split * p.K * p.Nout;
