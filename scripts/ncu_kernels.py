@@ -24,7 +24,7 @@ for rep in range(2):          # first pass warms caches / builds images; ncu ski
     dz1, dW2, db2 = ops.edge_bwd(PQ[:, :128], PQ[:, 128:], topo, W2, z2, r(N, 128), dPQ[:, :128])
     seg = ops.segment_reduce(dz1, topo.colptr, perm=topo.csc_perm)
     rnn = LEMcuda(6, 128, 1.0).to(dev)
-    ys, zs = rnn(r(4, N, 6))
+    ys, zs = rnn(r(25, N, 6))
     (ys.sum() + zs.sum()).backward()
     torch.cuda.synchronize()
 print("ok")
