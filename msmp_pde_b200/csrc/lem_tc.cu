@@ -213,16 +213,28 @@ struct LemFwdParams {
   int T; int N; int Npad; int ninp;
 };
 
-__global__ void __launch_bounds__(LT_THREADS, 1) k_lem_fwd_tc(const LemFwdParams p) {
+// Forward kernel roles: warps 0..7 gate epilogues, warp 8 weight ring producer, warp 9 MMA issue.
+constexpr int LF_THREADS = LT_EPI + 64;
+// TMEM columns (512 allocated): the G accumulator (3 gates x 64 nodes), the L accumulator, and the input projections
+// of the four gates (bias + I_t . w_in), written by the epilogue warps while the G GEMM runs and added to the
+// accumulators in the gate epilogues.  (Initialising the accumulators with them instead was measured slightly less
+// accurate: every MMA then adds onto a full-magnitude partial sum.)
+constexpr uint32_t LF_G = 0, LF_L = 192, LF_PRE = 256;
+
+// producer / consumer named barrier between the 256 epilogue threads (arrive) and the MMA warp (sync)
+__device__ __forceinline__ void state_ready_arrive() { asm volatile("bar.arrive 2, 288;" ::: "memory"); }
+__device__ __forceinline__ void state_ready_wait() { asm volatile("bar.sync 2, 288;" ::: "memory"); }
+
+__global__ void __launch_bounds__(LF_THREADS, 1) k_lem_fwd_tc(const LemFwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   const LemSmem m = lem_smem(smem_raw);
   const int tid = threadIdx.x, warp = warp_index_uniform(), lane = tid & 31;
   const int row0 = blockIdx.x * LT_NODES;
   const size_t plane = (size_t)p.N * 128;
-  lem_init(m, 256);
+  lem_init(m, 512);
 
-  if (warp >= 8) {
-    // ---- weight ring producers: 12 G chunks + 4 L chunks per step, running ahead of the MMA thread
+  if (warp == 8) {
+    // ---- weight ring producer: 12 G chunks + 4 L chunks per step, running ahead of the MMA warp
     const Ring rg{m.smB, &m.bars[0], &m.bars[LT_STAGES]};
     if (elect_one()) {
       uint32_t n = 0;
@@ -232,9 +244,19 @@ __global__ void __launch_bounds__(LT_THREADS, 1) k_lem_fwd_tc(const LemFwdParams
       }
     }
     __syncwarp();
+  } else if (warp == 9) {
+    // ---- MMA issue (whole warp convergent, elected lane issues)
+    Epi e = lem_epi(m);
+    for (int t = 0; t < p.T; ++t) {
+      state_ready_wait();                                   // y_{t-1} tile written, G accumulator of step t-1 consumed
+      gemm_issue(e, 12, LF_G, false);
+      state_ready_wait();                                   // z_t tile written, L accumulator of step t-1 consumed
+      gemm_issue(e, 4, LF_L, false);
+    }
   } else {
     Epi e = lem_epi(m);
-    // epilogue ownership: thread = hidden channel c (TMEM lane), nodes [j0, j0 + 32) of the tile
+    // epilogue ownership: thread = hidden channel c (TMEM lane), nodes [j0, j0 + 32) of the tile, for all T steps:
+    // its y / z state lives in registers.
     const int c = 32 * (warp & 3) + lane;
     const int j0 = 32 * (warp >> 2);
     const uint32_t tbase = e.tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)j0;
@@ -249,114 +271,137 @@ __global__ void __launch_bounds__(LT_THREADS, 1) k_lem_fwd_tc(const LemFwdParams
         win[g][q] = q < p.ninp ? (g < 3 ? __ldg(p.Wt_in + (size_t)q * 384 + 128 * g + c) : __ldg(p.Wzt_in + (size_t)q * 128 + c))
                                : 0.f;
     }
-    // pre-activation of gate g for input row x (8 floats; entries >= ninp multiply zero weights)
-    auto inproj = [&](int g, const float4& xa, const float4& xb) {
-      float acc = bia[g];
-      acc = fmaf(xa.x, win[g][0], acc);
-      acc = fmaf(xa.y, win[g][1], acc);
-      acc = fmaf(xa.z, win[g][2], acc);
-      acc = fmaf(xa.w, win[g][3], acc);
-      acc = fmaf(xb.x, win[g][4], acc);
-      acc = fmaf(xb.y, win[g][5], acc);
-      acc = fmaf(xb.z, win[g][6], acc);
-      acc = fmaf(xb.w, win[g][7], acc);
-      return acc;
-    };
-
-    // y_{-1} tile from the row-major Y[0]
-    for (int j = j0; j < j0 + 32; ++j) {
-      const int g = row0 + j;
-      state_store(e.smS, state_off(j, c), g < p.N ? __ldg(p.Y + (size_t)g * 128 + c) : 0.f);
-    }
-    publish();
-
-    for (int t = 0; t < p.T; ++t) {
+    // input projections of the four gates for step t: bias + I_t[node] . w_in (exact fp32) -> TMEM columns LF_PRE + 64 g;
+    // I_t[node] is a warp-uniform 32-byte load.  Runs while the G GEMM of the same step occupies the tensor pipe.
+    auto inproj = [&](int t) {
       const float* x_t = p.inp + ((size_t)t * p.N + row0) * 32;
-      float* g_t = p.gates + ((size_t)t * p.Npad + row0) * 512;
-      const float* zprev = p.Z + (size_t)t * plane + (size_t)row0 * 128;
-      float* znext = p.Z + (size_t)(t + 1) * plane + (size_t)row0 * 128;
-      const float* yprev = p.Y + (size_t)t * plane + (size_t)row0 * 128;
-      float* ynext = p.Y + (size_t)(t + 1) * plane + (size_t)row0 * 128;
-      // ---- G^T = W_h y^T : 3 m-tiles x 4 chunks -> TMEM columns 0..191
-      LEM_TICK(0);
-#ifdef MSMP_LEM_TICKS
-      if (blockIdx.x == 0 && tid == 0) g_lem_chunk_tick = (t == 2) ? 0 : -1;
-#endif
-      if (warp == 0) gemm_issue(e, 12, 0, false);
-      gemm_wait(e);
-      LEM_TICK(1);
-      // ---- gate_z, 8 nodes at a time: all loads of a batch are issued before any dependent math
 #pragma unroll 1
-      for (int jj = 0; jj < 32; jj += 8) {
-        uint32_t r0[8], r1[8], r2[8];
-        tmem_ld8_nowait(tbase + jj, r0);
-        tmem_ld8_nowait(tbase + 64 + jj, r1);
-        tmem_ld8_nowait(tbase + 128 + jj, r2);
-        float4 xa[8], xb[8];
-        float zp[8];
+      for (int jj = 0; jj < 32; jj += 4) {
+        float4 xa[4], xb[4];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
+        for (int q = 0; q < 4; ++q) {
           const int j = j0 + jj + q;
           const bool ok = row0 + j < p.N;
           xa[q] = ok ? ldg4(x_t + (size_t)j * 32) : zero4();
           xb[q] = ok ? ldg4(x_t + (size_t)j * 32 + 4) : zero4();
-          zp[q] = ok ? __ldcg(zprev + (size_t)j * 128 + c) : 0.f;
         }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float v[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float acc = bia[g];
+            acc = fmaf(xa[q].x, win[g][0], acc);
+            acc = fmaf(xa[q].y, win[g][1], acc);
+            acc = fmaf(xa[q].z, win[g][2], acc);
+            acc = fmaf(xa[q].w, win[g][3], acc);
+            acc = fmaf(xb[q].x, win[g][4], acc);
+            acc = fmaf(xb[q].y, win[g][5], acc);
+            acc = fmaf(xb[q].z, win[g][6], acc);
+            acc = fmaf(xb[q].w, win[g][7], acc);
+            v[q] = acc;
+          }
+          tmem_st4(tbase + LF_PRE + 64 * g + jj, v);
+        }
+      }
+      tmem_st_wait();
+    };
+    // make state-tile stores (generic proxy) and TMEM stores visible to the MMA warp, then signal it
+    auto publish_to_mma = [&]() {
+      fence_proxy_async();
+      tc_fence_before();
+      state_ready_arrive();
+    };
+    auto wait_acc = [&]() {
+      mbar_wait_warp(e.acc, e.nacc & 1);
+      ++e.nacc;
+      tc_fence_after();
+    };
+
+    // initial state: registers + the y_{-1} tile
+    float yreg[32], zreg[32];
+#pragma unroll
+    for (int q = 0; q < 32; ++q) {
+      const int g = row0 + j0 + q;
+      yreg[q] = g < p.N ? __ldg(p.Y + (size_t)g * 128 + c) : 0.f;
+      zreg[q] = g < p.N ? __ldg(p.Z + (size_t)g * 128 + c) : 0.f;
+      state_store(e.smS, state_off(j0 + q, c), yreg[q]);
+    }
+    publish_to_mma();
+
+    for (int t = 0; t < p.T; ++t) {
+      float* g_t = p.gates + ((size_t)t * p.Npad + row0) * 512;
+      float* znext = p.Z + (size_t)(t + 1) * plane + (size_t)row0 * 128;
+      float* ynext = p.Y + (size_t)(t + 1) * plane + (size_t)row0 * 128;
+      const uint32_t gbuf = tbase + LF_G;
+      LEM_TICK(0);
+      // ---- while G^T = W_h y^T runs: this step's input projections -> TMEM
+      inproj(t);
+      LEM_TICK(1);
+      wait_acc();
+      LEM_TICK(2);
+      // ---- gate_z (no global loads: accumulators from TMEM, z_{t-1} from registers)
+#pragma unroll
+      for (int jj = 0; jj < 32; jj += 8) {
+        uint32_t r0[8], r1[8], r2[8], q0[8], q1[8], q2[8];
+        tmem_ld8_nowait(gbuf + jj, r0);
+        tmem_ld8_nowait(gbuf + 64 + jj, r1);
+        tmem_ld8_nowait(gbuf + 128 + jj, r2);
+        tmem_ld8_nowait(tbase + LF_PRE + jj, q0);
+        tmem_ld8_nowait(tbase + LF_PRE + 64 + jj, q1);
+        tmem_ld8_nowait(tbase + LF_PRE + 128 + jj, q2);
         tmem_ld_wait();
+        float av[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           const int j = j0 + jj + q;
-          const float a = p.dt * sigmoidf_(__uint_as_float(r0[q]) + inproj(0, xa[q], xb[q]));
-          const float b = p.dt * sigmoidf_(__uint_as_float(r1[q]) + inproj(1, xa[q], xb[q]));
-          const float zc = tanh_acc(__uint_as_float(r2[q]) + inproj(2, xa[q], xb[q]));
-          const float zn = (1.f - b) * zp[q] + b * zc;
+          const float a = p.dt * sigmoidf_(__uint_as_float(r0[q]) + __uint_as_float(q0[q]));
+          const float b = p.dt * sigmoidf_(__uint_as_float(r1[q]) + __uint_as_float(q1[q]));
+          const float zc = tanh_acc(__uint_as_float(r2[q]) + __uint_as_float(q2[q]));
+          const float zn = (1.f - b) * zreg[jj + q] + b * zc;
+          zreg[jj + q] = zn;
+          av[q] = a;
           g_t[(size_t)j * 512 + c] = a;
           g_t[(size_t)j * 512 + 128 + c] = b;
           g_t[(size_t)j * 512 + 256 + c] = zc;
           if (row0 + j < p.N) znext[(size_t)j * 128 + c] = zn;
           state_store(e.smS, state_off(j, c), zn);      // z_t: B operand of the L GEMM
         }
+        tmem_st8(tbase + LF_PRE + jj, av);      // the gate-0 projection columns are consumed: stash a for gate_y there
       }
-      publish();
-      LEM_TICK(2);
-      // ---- L^T = Wz_h z^T : 4 chunks -> TMEM columns 192..255
-      if (warp == 0) gemm_issue(e, 4, 192, false);
-      gemm_wait(e);
+      tmem_st_wait();
+      publish_to_mma();
       LEM_TICK(3);
+      // ---- L^T = Wz_h z^T
+      wait_acc();
+      LEM_TICK(4);
       // ---- gate_y
-#pragma unroll 1
-      for (int jj = 0; jj < 32; jj += 8) {
-        uint32_t r3[8];
-        tmem_ld8_nowait(tbase + 192 + jj, r3);
-        float4 xa[8], xb[8];
-        float av[8], yp[8];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const int j = j0 + jj + q;
-          const bool ok = row0 + j < p.N;
-          xa[q] = ok ? ldg4(x_t + (size_t)j * 32) : zero4();
-          xb[q] = ok ? ldg4(x_t + (size_t)j * 32 + 4) : zero4();
-          av[q] = __ldcg(g_t + (size_t)j * 512 + c);
-          yp[q] = ok ? __ldcg(yprev + (size_t)j * 128 + c) : 0.f;
-        }
+      for (int jj = 0; jj < 32; jj += 8) {
+        uint32_t r3[8], q3[8], ra[8];
+        tmem_ld8_nowait(tbase + LF_L + jj, r3);
+        tmem_ld8_nowait(tbase + LF_PRE + 192 + jj, q3);
+        tmem_ld8_nowait(tbase + LF_PRE + jj, ra);
         tmem_ld_wait();
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           const int j = j0 + jj + q;
-          const float tl = tanh_acc(__uint_as_float(r3[q]) + inproj(3, xa[q], xb[q]));
-          const float yn = (1.f - av[q]) * yp[q] + av[q] * tl;
+          const float a = __uint_as_float(ra[q]);
+          const float tl = tanh_acc(__uint_as_float(r3[q]) + __uint_as_float(q3[q]));
+          const float yn = (1.f - a) * yreg[jj + q] + a * tl;
+          yreg[jj + q] = yn;
           g_t[(size_t)j * 512 + 384 + c] = tl;
           if (row0 + j < p.N) ynext[(size_t)j * 128 + c] = yn;
           state_store(e.smS, state_off(j, c), yn);      // y_t: B operand of the next G GEMM
         }
       }
-      publish();
-      LEM_TICK(4);
+      if (t + 1 < p.T) publish_to_mma();
+      LEM_TICK(5);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(*m.tmem_slot, 256);
+  if (warp == 0) tmem_dealloc(*m.tmem_slot, 512);
 }
 
 // ------------------------------------------------------------------------------------------------ backward
@@ -555,7 +600,7 @@ extern "C" int msmp_lem_tc_fwd(const float* inp, int ninp, const float* Wt_in, c
       return MSMP_ERR_CUDA;
     attr_set = true;
   }
-  k_lem_fwd_tc<<<Npad / LT_NODES, LT_THREADS, LT_SMEM, stream>>>(p);
+  k_lem_fwd_tc<<<Npad / LT_NODES, LF_THREADS, LT_SMEM, stream>>>(p);
   MSMP_CHECK_LAUNCH();
   return MSMP_OK;
 }

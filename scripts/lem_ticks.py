@@ -15,12 +15,11 @@ buf = (ctypes.c_longlong * 64)()
 _lib.lib.msmp_lem_debug_ticks.argtypes = [ctypes.c_void_p]
 _lib.lib.msmp_lem_debug_ticks(buf)
 t = list(buf)
-seq = [(0, "start"), (1, "G gemm (12 chunks) issue + wait"), (2, "gate_z epilogue + publish"),
-       (3, "L gemm (4 chunks) issue + wait"), (4, "gate_y epilogue + publish")]
+seq = [(0, "start"), (1, "accumulator pre-init (overlaps the G GEMM)"), (2, "rest of the G GEMM wait"),
+       (3, "gate_z epilogue + publish"), (4, "L GEMM wait"), (5, "gate_y epilogue + publish")]
 for (i0, _), (i1, name) in zip(seq[:-1], seq[1:]):
     print(f"{name:45s} {t[i1]-t[i0]:8d} cycles")
-print("step total", t[4] - t[0])
-
+print("step total", t[5] - t[0])
 print("per chunk (cycles since step start): data-ready, issued")
 for j in range(16):
     print(j, t[16 + 2 * j] - t[0], t[17 + 2 * j] - t[0])
