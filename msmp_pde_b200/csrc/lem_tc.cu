@@ -46,8 +46,7 @@ constexpr int LT_NODES = 64;                       // nodes per CTA = MMA N
 constexpr int LT_SCHUNK = LT_NODES * 128;          // one hi (or lo) state k-chunk image: 64 rows x 128 B = 8 KiB
 constexpr int LT_S_BYTES = 4 * 2 * LT_SCHUNK;      // state tile: 4 k-chunks x (hi | lo) = 64 KiB
 constexpr int LT_STAGE_BYTES = 2 * IMG_BYTES;      // one weight chunk: [128 x 32] hi | lo = 32 KiB
-constexpr int LT_STAGES = 5;
-constexpr int LT_SMEM = LT_S_BYTES + LT_STAGES * LT_STAGE_BYTES + 1024 + 256;
+constexpr int LT_SMEM = 7 * LT_STAGE_BYTES + 1024 + 256;      // forward: 1 state tile + 5 ring stages; backward: 2 + 3
 constexpr int LT_EPI = 256;                        // warps 0..7: gate epilogues (thread 0 also issues the MMAs)
 constexpr int LT_THREADS = LT_EPI + 32;            // warp 8: weight ring producer (one elected lane issues bulk copies)
 
@@ -59,14 +58,15 @@ __device__ int g_lem_chunk_tick = -1;      // >= 0: ring_mma stamps (data ready,
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }      // the 8 epilogue warps
 
 struct Ring {
-  uint8_t* smB;        // LT_STAGES stages
-  uint64_t* bfull;     // [LT_STAGES], one arrival (expect_tx) + 32 KiB of bulk-copy bytes
-  uint64_t* bfree;     // [LT_STAGES], one arrival (tcgen05.commit)
+  uint8_t* smB;        // nst stages
+  uint64_t* bfull;     // [nst], one arrival (expect_tx) + 32 KiB of bulk-copy bytes
+  uint64_t* bfree;     // [nst], one arrival (tcgen05.commit)
+  uint32_t nst;
 };
 
 // producer lane: one 32 KiB bulk copy of weight chunk image `src` (hi | lo, contiguous) into ring stage i
 __device__ __forceinline__ void ring_load(const Ring& rg, uint32_t i, const float* src) {
-  const uint32_t s = i % LT_STAGES, use = i / LT_STAGES;
+  const uint32_t s = i % rg.nst, use = i / rg.nst;
   if (use > 0) mbar_wait(&rg.bfree[s], (use - 1) & 1);            // MMAs that read this stage are complete
   mbar_expect_tx(&rg.bfull[s], LT_STAGE_BYTES);
   bulk_g2s(rg.smB + s * LT_STAGE_BYTES, src, LT_STAGE_BYTES, &rg.bfull[s]);
@@ -74,7 +74,7 @@ __device__ __forceinline__ void ring_load(const Ring& rg, uint32_t i, const floa
 
 // MMA-issuing warp (all lanes, convergent): weight chunk in ring slot i (A, 128 channels x 32 k) times state k-chunk at s_img (B, 64 nodes x 32 k)
 __device__ __forceinline__ void ring_mma(const Ring& rg, uint32_t i, uint32_t s_img, uint32_t tmem_d, bool accumulate) {
-  const uint32_t s = i % LT_STAGES, use = i / LT_STAGES;
+  const uint32_t s = i % rg.nst, use = i / rg.nst;
   mbar_wait(&rg.bfull[s], use & 1);                               // (bulk copies write through the async proxy)
 #ifdef MSMP_LEM_TICKS
   if (blockIdx.x == 0 && g_lem_chunk_tick >= 0 && g_lem_chunk_tick < 16) g_lem_dbg[16 + 2 * g_lem_chunk_tick] = clock64();
@@ -111,14 +111,16 @@ struct Epi {
   uint32_t tmem;
 };
 
-// Warp 0 (all lanes): issue one GEMM phase of `nchunks` ring chunks; chunk j multiplies state k-chunk (j & 3) into TMEM columns
-// dcol + 64 * (j >> 2) (the first chunk of every 64-column block overwrites unless acc_first).  Returns after the commit.
-__device__ __forceinline__ void gemm_issue(Epi& e, uint32_t nchunks, uint32_t dcol, bool acc_first) {
+// MMA warp (all lanes): issue one GEMM phase of `nchunks` ring chunks; chunk j multiplies k-chunk (j & 3) of the state
+// tile at `sbase` into TMEM columns dcol + 64 * (j >> 2) (the first chunk of every 64-column block overwrites unless
+// acc_first), then commits to `done` (if not null).
+__device__ __forceinline__ void gemm_issue(Epi& e, uint32_t sbase, uint32_t nchunks, uint32_t dcol, bool acc_first,
+                                           uint64_t* done) {
   tc_fence_after();
   for (uint32_t j = 0; j < nchunks; ++j)
-    ring_mma(e.rg, e.nchunk + j, e.smS + (j & 3) * 2 * LT_SCHUNK, e.tmem + dcol + LT_NODES * (j >> 2), acc_first || (j & 3) != 0);
+    ring_mma(e.rg, e.nchunk + j, sbase + (j & 3) * 2 * LT_SCHUNK, e.tmem + dcol + LT_NODES * (j >> 2), acc_first || (j & 3) != 0);
   e.nchunk += nchunks;
-  if (elect_one()) umma_commit(e.acc);
+  if (done != nullptr && elect_one()) umma_commit(done);
   __syncwarp();
 }
 
@@ -156,19 +158,21 @@ __device__ __forceinline__ void state_store(uint32_t smS, uint32_t off, float v)
 #endif
 
 struct LemSmem {
-  uint8_t* smS;
-  uint8_t* smB;
-  uint64_t* bars;      // bfull[5], bfree[5], acc
+  uint8_t* smS;        // nbuf state tiles of LT_S_BYTES
+  uint8_t* smB;        // nst ring stages
+  uint64_t* bars;      // bfull[8], bfree[8], acc, acc_mid
   uint32_t* tmem_slot;
+  uint32_t nst;
 };
 
-__device__ __forceinline__ LemSmem lem_smem(uint8_t* smem_raw) {
+__device__ __forceinline__ LemSmem lem_smem(uint8_t* smem_raw, int nbuf, int nst) {      // 2 * nbuf + nst * 2 == 14 half-stages
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   LemSmem m;
   m.smS = smem;
-  m.smB = smem + LT_S_BYTES;
-  m.bars = reinterpret_cast<uint64_t*>(m.smB + LT_STAGES * LT_STAGE_BYTES);
-  m.tmem_slot = reinterpret_cast<uint32_t*>(m.bars + 16);
+  m.smB = smem + nbuf * LT_S_BYTES;
+  m.bars = reinterpret_cast<uint64_t*>(m.smB + nst * LT_STAGE_BYTES);
+  m.tmem_slot = reinterpret_cast<uint32_t*>(m.bars + 24);
+  m.nst = (uint32_t)nst;
   return m;
 }
 
@@ -176,11 +180,12 @@ __device__ __forceinline__ void lem_init(const LemSmem& m, uint32_t tmem_cols) {
   const int tid = threadIdx.x, warp = tid >> 5;
   if (warp == 0) tmem_alloc(m.tmem_slot, tmem_cols);
   if (tid == 32) {
-    for (int i = 0; i < LT_STAGES; ++i) {
+    for (int i = 0; i < 8; ++i) {
       mbar_init(&m.bars[i], 1);
-      mbar_init(&m.bars[LT_STAGES + i], 1);
+      mbar_init(&m.bars[8 + i], 1);
     }
-    mbar_init(&m.bars[2 * LT_STAGES], 1);
+    mbar_init(&m.bars[16], 1);
+    mbar_init(&m.bars[17], 1);
     fence_barrier_init();
   }
   tc_fence_before();
@@ -190,8 +195,8 @@ __device__ __forceinline__ void lem_init(const LemSmem& m, uint32_t tmem_cols) {
 
 __device__ __forceinline__ Epi lem_epi(const LemSmem& m) {
   Epi e;
-  e.rg = Ring{m.smB, &m.bars[0], &m.bars[LT_STAGES]};
-  e.acc = &m.bars[2 * LT_STAGES];
+  e.rg = Ring{m.smB, &m.bars[0], &m.bars[8], m.nst};
+  e.acc = &m.bars[16];
   e.nacc = e.nchunk = 0;
   e.smS = smem_u32(m.smS);
   e.tmem = __shfl_sync(0xffffffffu, *m.tmem_slot, 0);
@@ -227,7 +232,7 @@ __device__ __forceinline__ void state_ready_wait() { asm volatile("bar.sync 2, 2
 
 __global__ void __launch_bounds__(LF_THREADS, 1) k_lem_fwd_tc(const LemFwdParams p) {
   extern __shared__ uint8_t smem_raw[];
-  const LemSmem m = lem_smem(smem_raw);
+  const LemSmem m = lem_smem(smem_raw, 1, 5);
   const int tid = threadIdx.x, warp = warp_index_uniform(), lane = tid & 31;
   const int row0 = blockIdx.x * LT_NODES;
   const size_t plane = (size_t)p.N * 128;
@@ -235,7 +240,7 @@ __global__ void __launch_bounds__(LF_THREADS, 1) k_lem_fwd_tc(const LemFwdParams
 
   if (warp == 8) {
     // ---- weight ring producer: 12 G chunks + 4 L chunks per step, running ahead of the MMA warp
-    const Ring rg{m.smB, &m.bars[0], &m.bars[LT_STAGES]};
+    const Ring rg{m.smB, &m.bars[0], &m.bars[8], m.nst};
     if (elect_one()) {
       uint32_t n = 0;
       for (int t = 0; t < p.T; ++t) {
@@ -249,9 +254,9 @@ __global__ void __launch_bounds__(LF_THREADS, 1) k_lem_fwd_tc(const LemFwdParams
     Epi e = lem_epi(m);
     for (int t = 0; t < p.T; ++t) {
       state_ready_wait();                                   // y_{t-1} tile written, G accumulator of step t-1 consumed
-      gemm_issue(e, 12, LF_G, false);
+      gemm_issue(e, e.smS, 12, LF_G, false, e.acc);
       state_ready_wait();                                   // z_t tile written, L accumulator of step t-1 consumed
-      gemm_issue(e, 4, LF_L, false);
+      gemm_issue(e, e.smS, 4, LF_L, false, e.acc);
     }
   } else {
     Epi e = lem_epi(m);
@@ -423,17 +428,22 @@ struct LemBwdParams {
   int t_begin; int t_end;   // this launch walks t = t_end-1 .. t_begin (the carried dy/dz live in dy/dz between launches)
 };
 
-__global__ void __launch_bounds__(LT_THREADS, 1) k_lem_bwd_tc(const LemBwdParams p) {
+// TMEM columns of the backward kernel (256 allocated): acc1, acc2, and the dG2 / dG0 blocks of the current step
+// (stashed by the thread that computed them until their k-block of the acc2 GEMM is staged).
+constexpr uint32_t LB_ACC1 = 0, LB_ACC2 = 64, LB_S2 = 128, LB_S0 = 192;
+
+__global__ void __launch_bounds__(LF_THREADS, 1) k_lem_bwd_tc(const LemBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
-  const LemSmem m = lem_smem(smem_raw);
+  const LemSmem m = lem_smem(smem_raw, 2, 3);      // two state tiles (X, Y) + 3 ring stages
   const int tid = threadIdx.x, warp = warp_index_uniform(), lane = tid & 31;
   const int row0 = blockIdx.x * LT_NODES;
   const size_t plane = (size_t)p.N * 128;
-  lem_init(m, 128);
+  lem_init(m, 256);
+  uint64_t* acc_mid = &m.bars[17];
 
-  if (warp >= 8) {
-    // ---- weight ring producers: per step Wz chunks 0..3, then W chunks 4..7 (dG1), 8..11 (dG2), 0..3 (dG0)
-    const Ring rg{m.smB, &m.bars[0], &m.bars[LT_STAGES]};
+  if (warp == 8) {
+    // ---- weight ring producer: per step Wz chunks 0..3, then W chunks 4..7 (dG1), 8..11 (dG2), 0..3 (dG0)
+    const Ring rg{m.smB, &m.bars[0], &m.bars[8], m.nst};
     if (elect_one()) {
       uint32_t n = 0;
       for (int t = p.t_end - 1; t >= p.t_begin; --t) {
@@ -442,32 +452,48 @@ __global__ void __launch_bounds__(LT_THREADS, 1) k_lem_bwd_tc(const LemBwdParams
       }
     }
     __syncwarp();
+  } else if (warp == 9) {
+    // ---- MMA issue (whole warp convergent, elected lane issues)
+    Epi e = lem_epi(m);
+    const uint32_t X = e.smS, Y = e.smS + LT_S_BYTES;
+    for (int t = p.t_end - 1; t >= p.t_begin; --t) {
+      state_ready_wait();                                         // dL in X
+      gemm_issue(e, X, 4, LB_ACC1, false, e.acc);                 // acc1 = Wz[:, :128]^T dL^T
+      state_ready_wait();                                         // dG1 in X, dG2 in Y
+      gemm_issue(e, X, 4, LB_ACC2, false, acc_mid);               // acc2  = W[128:256, :128]^T dG1^T   (X free afterwards)
+      gemm_issue(e, Y, 4, LB_ACC2, true, nullptr);                // acc2 += W[256:384, :128]^T dG2^T
+      state_ready_wait();                                         // dG0 in X
+      gemm_issue(e, X, 4, LB_ACC2, true, e.acc);                  // acc2 += W[0:128, :128]^T dG0^T
+    }
   } else {
     Epi e = lem_epi(m);
+    // epilogue ownership: thread = hidden channel c (TMEM lane), nodes [j0, j0 + 32): its carried dy / dz live in registers
     const int c = 32 * (warp & 3) + lane;
     const int j0 = 32 * (warp >> 2);
     const uint32_t tbase = e.tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)j0;
+    const uint32_t X = e.smS, Y = e.smS + LT_S_BYTES;
     const float inv_dt = 1.0f / p.dt;
     float* dyc = p.dy + (size_t)row0 * 128 + c;
     float* dzc = p.dz + (size_t)row0 * 128 + c;
+    uint32_t nmid = 0;
 
-    // restage one 128-channel block of this step's dG (written by this thread earlier in the step) into the state tile
-    auto stage = [&](const float* blk) {
-#pragma unroll 1
-      for (int jj = 0; jj < 32; jj += 16) {
-        float g[16];
-#pragma unroll
-        for (int q = 0; q < 16; ++q) {
-          const int j = j0 + jj + q;
-          g[q] = (row0 + j < p.N) ? __ldcg(blk + (size_t)j * 384 + c) : 0.f;
-        }
-#pragma unroll
-        for (int q = 0; q < 16; ++q) {
-          const int j = j0 + jj + q;
-          state_store(e.smS, state_off(j, c), g[q]);
-        }
-      }
+    auto publish_to_mma = [&]() {
+      fence_proxy_async();
+      tc_fence_before();
+      state_ready_arrive();
     };
+    auto wait_bar = [&](uint64_t* bar, uint32_t& n) {
+      mbar_wait_warp(bar, n & 1);
+      ++n;
+      tc_fence_after();
+    };
+
+    float dyreg[32], dzreg[32];
+#pragma unroll
+    for (int q = 0; q < 32; ++q) {
+      dyreg[q] = __ldcg(dyc + (size_t)(j0 + q) * 128);
+      dzreg[q] = __ldcg(dzc + (size_t)(j0 + q) * 128);
+    }
 
     for (int t = p.t_end - 1; t >= p.t_begin; --t) {
       const float* g_t = p.gates + ((size_t)t * p.Npad + row0) * 512;
@@ -478,21 +504,15 @@ __global__ void __launch_bounds__(LT_THREADS, 1) k_lem_bwd_tc(const LemBwdParams
       const float* gz = (p.gZ && ext) ? p.gZ + (p.g_last_only ? 0 : (size_t)t * plane) + (size_t)row0 * 128 : nullptr;
       float* dG_t = p.dG + (size_t)t * p.N * 384 + (size_t)row0 * 384;
       float* dL_t = p.dL + (size_t)t * plane + (size_t)row0 * 128;
-      if (t > p.t_begin && (warp & 3) == 0) {      // next step's saved activations (HBM) -> L2
-        const float* g_n = p.gates + ((size_t)(t - 1) * p.Npad + row0) * 512;
-        for (int q = lane; q < 32 * 16; q += 32)
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(g_n + (size_t)(j0 + (q >> 4)) * 512 + 32 * (q & 15)));
-      }
-      // ---- bwd_y : dL -> state tile + global, dG0 -> global, dy <- d (1 - a)
-#pragma unroll 1
+      // ---- bwd_y : dL -> tile X + global, dG0 -> global + TMEM stash, dy <- d (1 - a)
+#pragma unroll
       for (int jj = 0; jj < 32; jj += 8) {
-        float dv[8], av[8], tv[8], yv[8];
+        float gv[8], av[8], tv[8], yv[8], g0[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           const int j = j0 + jj + q;
           const bool ok = row0 + j < p.N;
-          dv[q] = __ldcg(dyc + (size_t)j * 128);
-          if (gy && ok) dv[q] += __ldg(gy + (size_t)j * 128 + c);
+          gv[q] = (gy && ok) ? __ldg(gy + (size_t)j * 128 + c) : 0.f;
           av[q] = __ldg(g_t + (size_t)j * 512 + c);
           tv[q] = __ldg(g_t + (size_t)j * 512 + 384 + c);
           yv[q] = ok ? __ldg(yprev + (size_t)j * 128 + c) : 0.f;
@@ -501,81 +521,87 @@ __global__ void __launch_bounds__(LT_THREADS, 1) k_lem_bwd_tc(const LemBwdParams
         for (int q = 0; q < 8; ++q) {
           const int j = j0 + jj + q;
           const bool ok = row0 + j < p.N;
-          const float d = dv[q], a = av[q], tl = tv[q];
+          const float d = dyreg[jj + q] + gv[q], a = av[q], tl = tv[q];
           const float dl = ok ? d * a * (1.f - tl * tl) : 0.f;
+          g0[q] = ok ? d * (tl - yv[q]) * a * (1.f - a * inv_dt) : 0.f;
           if (ok) {
             dL_t[(size_t)j * 128 + c] = dl;
-            dG_t[(size_t)j * 384 + c] = d * (tl - yv[q]) * a * (1.f - a * inv_dt);
+            dG_t[(size_t)j * 384 + c] = g0[q];
           }
-          dyc[(size_t)j * 128] = d * (1.f - a);
-          state_store(e.smS, state_off(j, c), dl);
+          dyreg[jj + q] = d * (1.f - a);
+          state_store(X, state_off(j, c), dl);
+        }
+        tmem_st8(tbase + LB_S0 + jj, g0);
+      }
+      tmem_st_wait();
+      publish_to_mma();
+      // ---- acc1^T = Wz[:, :128]^T dL^T
+      wait_bar(e.acc, e.nacc);
+      // ---- bwd_z : dG1 -> tile X + global, dG2 -> tile Y + global, dz <- d (1 - b)
+#pragma unroll
+      for (int jj = 0; jj < 32; jj += 8) {
+        uint32_t r1[8];
+        tmem_ld8_nowait(tbase + LB_ACC1 + jj, r1);
+        float gv[8], bv[8], zcv[8], zpv[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int j = j0 + jj + q;
+          const bool ok = row0 + j < p.N;
+          gv[q] = (gz && ok) ? __ldg(gz + (size_t)j * 128 + c) : 0.f;
+          bv[q] = __ldg(g_t + (size_t)j * 512 + 128 + c);
+          zcv[q] = __ldg(g_t + (size_t)j * 512 + 256 + c);
+          zpv[q] = ok ? __ldg(zprev + (size_t)j * 128 + c) : 0.f;
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int j = j0 + jj + q;
+          const bool ok = row0 + j < p.N;
+          const float d = dzreg[jj + q] + gv[q] + __uint_as_float(r1[q]), b = bv[q], zc = zcv[q];
+          const float g1 = ok ? d * (zc - zpv[q]) * b * (1.f - b * inv_dt) : 0.f;
+          const float g2 = ok ? d * b * (1.f - zc * zc) : 0.f;
+          if (ok) {
+            dG_t[(size_t)j * 384 + 128 + c] = g1;
+            dG_t[(size_t)j * 384 + 256 + c] = g2;
+          }
+          dzreg[jj + q] = d * (1.f - b);
+          state_store(X, state_off(j, c), g1);
+          state_store(Y, state_off(j, c), g2);
         }
       }
-      publish();
-      // ---- acc1^T = Wz[:, :128]^T dL^T -> TMEM columns 0..63
-      if (warp == 0) gemm_issue(e, 4, 0, false);
-      gemm_wait(e);
-      // ---- bwd_z : dG1 -> state tile + global, dG2 -> global, dz <- d (1 - b)
-      {
-        float v[32];
-        tmem_ld32(tbase, v);
+      publish_to_mma();
+      // ---- acc2^T = W[:, :128]^T [dG1 | dG2 | dG0]^T: the dG0 block is staged into X as soon as the dG1 GEMM has read it
+      wait_bar(acc_mid, nmid);
 #pragma unroll
-        for (int jj = 0; jj < 32; jj += 8) {
-          float dv[8], bv[8], zcv[8], zpv[8];
+      for (int jj = 0; jj < 32; jj += 8) {
+        uint32_t r0[8];
+        tmem_ld8_nowait(tbase + LB_S0 + jj, r0);
+        tmem_ld_wait();
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const int j = j0 + jj + q;
-            const bool ok = row0 + j < p.N;
-            dv[q] = __ldcg(dzc + (size_t)j * 128) + v[jj + q];
-            if (gz && ok) dv[q] += __ldg(gz + (size_t)j * 128 + c);
-            bv[q] = __ldg(g_t + (size_t)j * 512 + 128 + c);
-            zcv[q] = __ldg(g_t + (size_t)j * 512 + 256 + c);
-            zpv[q] = ok ? __ldg(zprev + (size_t)j * 128 + c) : 0.f;
-          }
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const int j = j0 + jj + q;
-            const bool ok = row0 + j < p.N;
-            const float d = dv[q], b = bv[q], zc = zcv[q];
-            const float g1 = ok ? d * (zc - zpv[q]) * b * (1.f - b * inv_dt) : 0.f;
-            if (ok) {
-              dG_t[(size_t)j * 384 + 128 + c] = g1;
-              dG_t[(size_t)j * 384 + 256 + c] = d * b * (1.f - zc * zc);
-            }
-            dzc[(size_t)j * 128] = d * (1.f - b);
-            state_store(e.smS, state_off(j, c), g1);
-          }
-        }
+        for (int q = 0; q < 8; ++q) state_store(X, state_off(j0 + jj + q, c), __uint_as_float(r0[q]));
       }
-      // ---- acc2^T = W[:, :128]^T [dG1 | dG2 | dG0]^T -> TMEM columns 64..127 (weight chunks 4..7, 8..11, 0..3)
-      publish();
-      if (warp == 0) gemm_issue(e, 4, 64, false);
-      gemm_wait(e);
-      stage(dG_t + 256);
-      publish();
-      if (warp == 0) gemm_issue(e, 4, 64, true);
-      gemm_wait(e);
-      stage(dG_t);
-      publish();
-      if (warp == 0) gemm_issue(e, 4, 64, true);
-      gemm_wait(e);
+      publish_to_mma();
+      wait_bar(e.acc, e.nacc);
       // ---- dy += acc2
-      {
-        float v[32];
-        tmem_ld32(tbase + 64, v);
-        float cur[32];
 #pragma unroll
-        for (int q = 0; q < 32; ++q) cur[q] = __ldcg(dyc + (size_t)(j0 + q) * 128);
+      for (int jj = 0; jj < 32; jj += 8) {
+        uint32_t r2[8];
+        tmem_ld8_nowait(tbase + LB_ACC2 + jj, r2);
+        tmem_ld_wait();
 #pragma unroll
-        for (int q = 0; q < 32; ++q) dyc[(size_t)(j0 + q) * 128] = cur[q] + v[q];
+        for (int q = 0; q < 8; ++q) dyreg[jj + q] += __uint_as_float(r2[q]);
       }
       tc_fence_before();
-      epi_bar();
+    }
+#pragma unroll
+    for (int q = 0; q < 32; ++q) {
+      dyc[(size_t)(j0 + q) * 128] = dyreg[q];
+      dzc[(size_t)(j0 + q) * 128] = dzreg[q];
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(*m.tmem_slot, 128);
+  if (warp == 0) tmem_dealloc(*m.tmem_slot, 256);
 }
 
 }  // namespace msmp
@@ -618,7 +644,7 @@ extern "C" int msmp_lem_tc_bwd(const float* Wzh_img, const float* Wh_img, const 
       return MSMP_ERR_CUDA;
     attr_set = true;
   }
-  k_lem_bwd_tc<<<Npad / LT_NODES, LT_THREADS, LT_SMEM, stream>>>(p);
+  k_lem_bwd_tc<<<Npad / LT_NODES, LF_THREADS, LT_SMEM, stream>>>(p);
   MSMP_CHECK_LAUNCH();
   return MSMP_OK;
 }
