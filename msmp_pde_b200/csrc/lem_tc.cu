@@ -335,9 +335,9 @@ __global__ void __launch_bounds__(LF_THREADS, 1) k_lem_fwd_tc(const LemFwdParams
     publish_to_mma();
 
     for (int t = 0; t < p.T; ++t) {
-      float* g_t = p.gates + ((size_t)t * p.Npad + row0) * 512;
-      float* znext = p.Z + (size_t)(t + 1) * plane + (size_t)row0 * 128;
-      float* ynext = p.Y + (size_t)(t + 1) * plane + (size_t)row0 * 128;
+      float* __restrict__ g_t = p.gates + ((size_t)t * p.Npad + row0) * 512;
+      float* __restrict__ znext = p.Z + (size_t)(t + 1) * plane + (size_t)row0 * 128;
+      float* __restrict__ ynext = p.Y + (size_t)(t + 1) * plane + (size_t)row0 * 128;
       const uint32_t gbuf = tbase + LF_G;
       LEM_TICK(0);
       // ---- while G^T = W_h y^T runs: this step's input projections -> TMEM
@@ -496,15 +496,33 @@ __global__ void __launch_bounds__(LF_THREADS, 1) k_lem_bwd_tc(const LemBwdParams
     }
 
     for (int t = p.t_end - 1; t >= p.t_begin; --t) {
-      const float* g_t = p.gates + ((size_t)t * p.Npad + row0) * 512;
-      const float* yprev = p.Y + (size_t)t * plane + (size_t)row0 * 128;
-      const float* zprev = p.Z + (size_t)t * plane + (size_t)row0 * 128;
+      const float* __restrict__ g_t = p.gates + ((size_t)t * p.Npad + row0) * 512;
+      const float* __restrict__ yprev = p.Y + (size_t)t * plane + (size_t)row0 * 128;
+      const float* __restrict__ zprev = p.Z + (size_t)t * plane + (size_t)row0 * 128;
       const bool ext = !p.g_last_only || t == p.T - 1;
-      const float* gy = (p.gY && ext) ? p.gY + (p.g_last_only ? 0 : (size_t)t * plane) + (size_t)row0 * 128 : nullptr;
-      const float* gz = (p.gZ && ext) ? p.gZ + (p.g_last_only ? 0 : (size_t)t * plane) + (size_t)row0 * 128 : nullptr;
-      float* dG_t = p.dG + (size_t)t * p.N * 384 + (size_t)row0 * 384;
-      float* dL_t = p.dL + (size_t)t * plane + (size_t)row0 * 128;
+      const float* __restrict__ gy = (p.gY && ext) ? p.gY + (p.g_last_only ? 0 : (size_t)t * plane) + (size_t)row0 * 128 : nullptr;
+      const float* __restrict__ gz = (p.gZ && ext) ? p.gZ + (p.g_last_only ? 0 : (size_t)t * plane) + (size_t)row0 * 128 : nullptr;
+      float* __restrict__ dG_t = p.dG + (size_t)t * p.N * 384 + (size_t)row0 * 384;
+      float* __restrict__ dL_t = p.dL + (size_t)t * plane + (size_t)row0 * 128;
+      if (t > p.t_begin) {
+        // the activations saved by the forward pass are in HBM by now: pull the next step's rows of this thread's
+        // node half into L2 (gates 2 KiB, y and z 512 B per node; one 128-byte line per prefetch)
+        const float* g_n = p.gates + ((size_t)(t - 1) * p.Npad + row0 + j0) * 512;
+        const float* y_n = p.Y + (size_t)(t - 1) * plane + (size_t)(row0 + j0) * 128;
+        const float* z_n = p.Z + (size_t)(t - 1) * plane + (size_t)(row0 + j0) * 128;
+        const int part = warp & 3;      // the four warps of a node half share the work
+        for (int q = lane + 32 * part; q < 32 * 16; q += 128)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(g_n + (size_t)(q >> 4) * 512 + 32 * (q & 15)));
+        for (int q = lane + 32 * part; q < 32 * 4; q += 128) {
+          const int j = q >> 2;
+          if (row0 + j0 + j < p.N) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(y_n + (size_t)j * 128 + 32 * (q & 3)));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(z_n + (size_t)j * 128 + 32 * (q & 3)));
+          }
+        }
+      }
       // ---- bwd_y : dL -> tile X + global, dG0 -> global + TMEM stash, dy <- d (1 - a)
+      LEM_TICK(32);
 #pragma unroll
       for (int jj = 0; jj < 32; jj += 8) {
         float gv[8], av[8], tv[8], yv[8], g0[8];
@@ -535,8 +553,10 @@ __global__ void __launch_bounds__(LF_THREADS, 1) k_lem_bwd_tc(const LemBwdParams
       }
       tmem_st_wait();
       publish_to_mma();
+      LEM_TICK(33);
       // ---- acc1^T = Wz[:, :128]^T dL^T
       wait_bar(e.acc, e.nacc);
+      LEM_TICK(34);
       // ---- bwd_z : dG1 -> tile X + global, dG2 -> tile Y + global, dz <- d (1 - b)
 #pragma unroll
       for (int jj = 0; jj < 32; jj += 8) {
@@ -570,8 +590,10 @@ __global__ void __launch_bounds__(LF_THREADS, 1) k_lem_bwd_tc(const LemBwdParams
         }
       }
       publish_to_mma();
+      LEM_TICK(35);
       // ---- acc2^T = W[:, :128]^T [dG1 | dG2 | dG0]^T: the dG0 block is staged into X as soon as the dG1 GEMM has read it
       wait_bar(acc_mid, nmid);
+      LEM_TICK(36);
 #pragma unroll
       for (int jj = 0; jj < 32; jj += 8) {
         uint32_t r0[8];
@@ -581,7 +603,9 @@ __global__ void __launch_bounds__(LF_THREADS, 1) k_lem_bwd_tc(const LemBwdParams
         for (int q = 0; q < 8; ++q) state_store(X, state_off(j0 + jj + q, c), __uint_as_float(r0[q]));
       }
       publish_to_mma();
+      LEM_TICK(37);
       wait_bar(e.acc, e.nacc);
+      LEM_TICK(38);
       // ---- dy += acc2
 #pragma unroll
       for (int jj = 0; jj < 32; jj += 8) {
@@ -592,6 +616,7 @@ __global__ void __launch_bounds__(LF_THREADS, 1) k_lem_bwd_tc(const LemBwdParams
         for (int q = 0; q < 8; ++q) dyreg[jj + q] += __uint_as_float(r2[q]);
       }
       tc_fence_before();
+      LEM_TICK(39);
     }
 #pragma unroll
     for (int q = 0; q < 32; ++q) {

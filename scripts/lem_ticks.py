@@ -20,6 +20,13 @@ seq = [(0, "start"), (1, "accumulator pre-init (overlaps the G GEMM)"), (2, "res
 for (i0, _), (i1, name) in zip(seq[:-1], seq[1:]):
     print(f"{name:45s} {t[i1]-t[i0]:8d} cycles")
 print("step total", t[5] - t[0])
-print("per chunk (cycles since step start): data-ready, issued")
-for j in range(16):
-    print(j, t[16 + 2 * j] - t[0], t[17 + 2 * j] - t[0])
+(ys.sum() + zs.sum()).backward()
+torch.cuda.synchronize()
+_lib.lib.msmp_lem_debug_ticks(buf)
+t = list(buf)
+seq = [(32, "start"), (33, "bwd_y epilogue + publish"), (34, "acc1 GEMM wait"), (35, "bwd_z epilogue + publish"),
+       (36, "dG1 GEMM wait (acc_mid)"), (37, "restage dG0 + publish"), (38, "dG2 / dG0 GEMM wait"), (39, "dy += acc2")]
+print("backward:")
+for (i0, _), (i1, name) in zip(seq[:-1], seq[1:]):
+    print(f"{name:45s} {t[i1]-t[i0]:8d} cycles")
+print("step total", t[39] - t[32])
