@@ -14,29 +14,41 @@
 //     row-major [node][channel] and every access is one full 128-byte line per warp -- no lane-major copies, no
 //     staged copy-out.
 //
-// forward, per step t.  The input part of both affine maps never touches memory: a thread's
-// channel is fixed, so it keeps its <= 8 input weights per gate and the bias in registers and adds
-// pre = b + I_t[node] . w_in (exact fp32 FMAs, I_t[node] is a warp-uniform 32-byte load) inside the gate epilogue.
+// Roles (320 threads): warps 0..7 run the gate epilogues, one lane of warp 8 streams the weights, warp 9 issues the
+// MMAs convergently (3xTF32: hi*hi + lo*hi + hi*lo; see elect_one() in umma.cuh).  The epilogue warps hand the state
+// tile to the MMA warp through a named barrier (bar.arrive / bar.sync) and wait for the accumulators on an mbarrier
+// that receives the tcgen05.commit.  The weights (pre-split, pre-swizzled [128 x 32] images, 512 KiB per step) are
+// streamed from L2 through a ring of 32 KiB bulk copies; the producer runs ahead of the MMA warp across phase
+// boundaries (the weights do not depend on the step), so the next GEMM's first chunks land while a gate epilogue runs.
+// The tensor pipe reads both operands from shared memory (6 KiB per 128x64x8 MMA, ~65 cycles measured): the GEMM phases
+// are bound by that, not by the stream.  An epilogue thread keeps its channel for all steps, so its recurrent state
+// (y, z forward; dy, dz backward: 64 registers) never leaves the register file.
+//
+// forward, per step t:
 //   G^T[3 x 128][64] = W_h y_{t-1}^T            12 weight chunks (3 m-tiles x 4 k-chunks), TMEM columns 0..191
 //   gate_z      : a = dt sig(G0 + pre), b = dt sig(G1 + pre), zc = tanh(G2 + pre), z_t = (1-b) z_{t-1} + b zc
 //   L^T[128][64]     = Wz_h z_t^T               4 weight chunks, TMEM columns 192..255
 //   gate_y      : tL = tanh(L + pre), y_t = (1-a) y_{t-1} + a tL
-// The state operand (y, then z, then y again) lives in shared memory as a tf32 hi/lo tile image [64 nodes x 128 k]
-// written by the gate epilogues.  The weights (pre-split, pre-swizzled [128 x 32] images, 512 KiB per step) are
-// streamed from L2 through a 5-stage ring (160 KiB in flight): one producer lane issues a 32 KiB bulk copy per chunk
-// and runs ahead of the MMA warp across phase boundaries (the weights do not depend on the step), so the next GEMM's
-// first chunks land while the gate epilogue runs.  Warp 0 issues the MMAs convergently (3xTF32: hi*hi + lo*hi +
-// hi*lo; see elect_one() in umma.cuh), eight warps run the gate epilogues.  The tensor pipe reads both operands from
-// shared memory (6 KiB per 128x64x8 MMA, ~65 cycles measured): the GEMM phases are bound by that, not by the stream.
+// The input part of both affine maps never touches memory: a thread's channel is fixed, so it keeps its <= 8 input
+// weights per gate and the bias in registers; while the G GEMM occupies the tensor pipe it evaluates
+// pre = b + I_t[node] . w_in (exact fp32 FMAs, I_t[node] is a warp-uniform 32-byte load) for the four gates into
+// TMEM columns 256..511, from where the gate epilogues add it to the accumulators.  The gate epilogues issue no
+// global loads at all; per node-step they write the four gate activations (for the backward) and y, z.
+// Shared memory: one state tile [64 nodes x 128 k] (tf32 hi | lo images, 64 KiB) + 5 ring stages.
 //
-// backward, per step t = t_end-1 .. t_begin (dy, dz carried in global scratch, owned by the same thread):
+// backward, per step t = t_end-1 .. t_begin (the carried dy, dz enter and leave through global memory once per launch):
 //   bwd_y : d = dy + gY[t]; dL = d a (1-tL^2); dG0 = d (tL - y_{t-1}) a (1 - a/dt); dy = d (1-a)
 //   acc1  = Wz[:, :128]^T dL^T                    4 chunks
 //   bwd_z : d = dz + gZ[t] + acc1; dG1 = d (zc - z_{t-1}) b (1 - b/dt); dG2 = d b (1-zc^2); dz = d (1-b)
-//   acc2  = W[:, :128]^T [dG1 | dG2 | dG0]^T      3 x 4 chunks (the state tile is restaged per 128-row k-block)
+//   acc2  = W[:, :128]^T [dG1 | dG2 | dG0]^T      3 x 4 chunks
 //   dy   += acc2
+// Shared memory: TWO state tiles + 3 ring stages.  bwd_y puts dL into tile X (and stashes dG0 in TMEM); bwd_z puts dG1
+// into X and dG2 into Y, so the MMA warp runs the dG1 and dG2 k-blocks back to back; as soon as the dG1 block has been
+// read (its own commit) the epilogue restages dG0 from TMEM into X for the third k-block.
 // dG [T,N,384] and dL [T,N,128] are written (coalesced, by the epilogue itself) for the four weight-gradient GEMMs
-// (msmp_linear_wgrad_tc).
+// (msmp_linear_wgrad_tc2).  Measured per step (CTA 0, clock64): forward 31.4 k cycles (input projection 5.4 k inside
+// the 13.9 k G GEMM, gate_z 8.5 k, L GEMM 4.3 k, gate_y 4.7 k); backward 49 k (bwd_y 16 k, bwd_z 16 k, GEMM waits 16 k):
+// the backward epilogues are bound by the number of 4-byte-per-lane global load/store instructions, not by HBM.
 #include "umma.cuh"
 #include "msmp_b200.h"
 
@@ -47,15 +59,12 @@ constexpr int LT_SCHUNK = LT_NODES * 128;          // one hi (or lo) state k-chu
 constexpr int LT_S_BYTES = 4 * 2 * LT_SCHUNK;      // state tile: 4 k-chunks x (hi | lo) = 64 KiB
 constexpr int LT_STAGE_BYTES = 2 * IMG_BYTES;      // one weight chunk: [128 x 32] hi | lo = 32 KiB
 constexpr int LT_SMEM = 7 * LT_STAGE_BYTES + 1024 + 256;      // forward: 1 state tile + 5 ring stages; backward: 2 + 3
-constexpr int LT_EPI = 256;                        // warps 0..7: gate epilogues (thread 0 also issues the MMAs)
-constexpr int LT_THREADS = LT_EPI + 32;            // warp 8: weight ring producer (one elected lane issues bulk copies)
+constexpr int LT_EPI = 256;                        // warps 0..7: gate epilogues; warp 8: ring producer; warp 9: MMA issue
 
 #ifdef MSMP_LEM_TICKS
 __device__ long long g_lem_dbg[64];
 __device__ int g_lem_chunk_tick = -1;      // >= 0: ring_mma stamps (data ready, issued) of the next chunks
 #endif
-
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }      // the 8 epilogue warps
 
 struct Ring {
   uint8_t* smB;        // nst stages
@@ -122,21 +131,6 @@ __device__ __forceinline__ void gemm_issue(Epi& e, uint32_t sbase, uint32_t nchu
   e.nchunk += nchunks;
   if (done != nullptr && elect_one()) umma_commit(done);
   __syncwarp();
-}
-
-// All epilogue threads: wait for the GEMM issued last (one thread polls, the others park at the named barrier).
-__device__ __forceinline__ void gemm_wait(Epi& e) {
-  if (warp_index_uniform() == 0) mbar_wait(e.acc, e.nacc & 1);
-  ++e.nacc;
-  epi_bar();
-  tc_fence_after();
-}
-
-// All epilogue threads, after the last store of a state-tile refill: make it visible to the MMA (async proxy).
-__device__ __forceinline__ void publish() {
-  fence_proxy_async();
-  tc_fence_before();
-  epi_bar();
 }
 
 // state tile element (node j, k): k-chunk k >> 5, row j, column k & 31 of a [64 x 32] 128B-swizzled image (hi, then lo)
