@@ -30,3 +30,11 @@ def install():
     sys.modules["experiments.models_gnn"] = models_gnn
     sys.modules["experiments.models_gnn2D"] = models_gnn2D
     pkg.models_gnn, pkg.models_gnn2D = models_gnn, models_gnn2D
+    # the step in front of the models: vectorised, device-capable GraphCreator with a cached topology
+    # (common/utils.py:267-471); patched in when the reference checkout is importable
+    try:
+        import common.utils as cu
+        from .graph_creator import GraphCreator
+        cu.GraphCreator = GraphCreator
+    except Exception:      # reference not on sys.path (or its own imports unavailable): nothing to patch
+        pass

@@ -85,9 +85,11 @@ __global__ void __launch_bounds__(256, 1) k_linear_tc(const LinTcParams p) {
   };
   // software pipeline: the fp32 rows of chunk c+1 are in flight (registers) while chunk c is split/stored and
   // its MMAs run; weights of chunk c arrive by bulk copy while the A operand is being staged.
-  float4 pre[4];
-  bool pre_sw;
-  auto prefetch = [&](int c) {
+  // Two register sets: chunks c+1 and c+2 are in flight while chunk c is staged (a single set issued the loads only a
+  // few hundred cycles before they were needed).
+  float4 preA[4], preB[4];
+  bool swA, swB;
+  auto prefetch = [&](int c, float4 (&pre)[4], bool& pre_sw) {
     const float* A;
     int lda, koff;
     locate(c, A, lda, koff, pre_sw);
@@ -98,7 +100,8 @@ __global__ void __launch_bounds__(256, 1) k_linear_tc(const LinTcParams p) {
       pre[i] = (grow < p.M) ? ldg4(A + (size_t)grow * lda + koff + 4 * (idx & 7)) : zero4();
     }
   };
-  prefetch(0);
+  prefetch(0, preA, swA);
+  if (nchunks > 1) prefetch(1, preB, swB);
   const float* bsrc = p.Bimg + (size_t)ntile * nchunks * (TC_B_BYTES / 4);
   auto issue_b = [&](int c) {      // thread 0: bulk copy of the (hi | lo) weight images of chunk c
     uint64_t* bar = &bars[c & 3];
@@ -107,7 +110,7 @@ __global__ void __launch_bounds__(256, 1) k_linear_tc(const LinTcParams p) {
   };
   if (tid == 0)
     for (int c = 0; c < nchunks && c < TC_B_STAGES; ++c) issue_b(c);
-  for (int c = 0; c < nchunks; ++c) {
+  auto chunk = [&](int c, float4 (&pre)[4], bool& pre_sw) {
     const int s = c & 1, use = c >> 1;
     uint8_t* st = smem + s * TC_A_BYTES;
     if (c >= 2) {
@@ -121,7 +124,7 @@ __global__ void __launch_bounds__(256, 1) k_linear_tc(const LinTcParams p) {
       if (pre_sw) v = swish4(v);
       store_split4(st, st + IMG_BYTES, img_off(idx >> 3, idx & 7), v);
     }
-    if (c + 1 < nchunks) prefetch(c + 1);
+    if (c + 2 < nchunks) prefetch(c + 2, pre, pre_sw);
     fence_proxy_async();
     __syncthreads();
     if (warp == 0) {      // the whole warp runs the issue code convergently, one elected lane issues (see elect_one())
@@ -144,6 +147,10 @@ __global__ void __launch_bounds__(256, 1) k_linear_tc(const LinTcParams p) {
       if (leader) umma_commit(&bars[4 + s]);
       __syncwarp();
     }
+  };
+  for (int c = 0; c < nchunks; c += 2) {
+    chunk(c, preA, swA);
+    if (c + 1 < nchunks) chunk(c + 1, preB, swB);
   }
   // accumulator complete when the last commit arrives
   {

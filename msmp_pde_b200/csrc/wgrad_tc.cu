@@ -71,11 +71,13 @@ __global__ void __launch_bounds__(256, 1) k_wgrad_tc(const WgradTcParams p) {
   constexpr uint32_t IDESC = umma_idesc_tf32(128, 128, 1, 1);      // both operands MN-major
 
   // each thread stages 4 float4 of X and 4 of dY per chunk: element idx -> (row mm = idx >> 5, chunk c4 = idx & 31)
-  float4 px[4], py[4];
+  // Two register sets: the rows of chunks c+1 and c+2 are in flight while chunk c is split / stored and its MMAs are
+  // issued (with a single set the loads were issued a few hundred cycles before they were needed).
+  float4 pxA[4], pyA[4], pxB[4], pyB[4];
   float sacc[8][4];
 #pragma unroll
   for (int q = 0; q < 8; ++q) sacc[q][0] = sacc[q][1] = sacc[q][2] = sacc[q][3] = 0.f;
-  auto prefetch = [&](int c) {
+  auto prefetch = [&](int c, float4 (&px)[4], float4 (&py)[4]) {
     const int mb = m_begin + c * WT_CHUNK;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -86,8 +88,9 @@ __global__ void __launch_bounds__(256, 1) k_wgrad_tc(const WgradTcParams p) {
       py[i] = (okm && n0 + 4 * c4 < p.Nout) ? ldg4(p.dY + (size_t)m * p.lddy + n0 + 4 * c4) : zero4();
     }
   };
-  if (nchunks > 0) prefetch(0);
-  for (int c = 0; c < nchunks; ++c) {
+  if (nchunks > 0) prefetch(0, pxA, pyA);
+  if (nchunks > 1) prefetch(1, pxB, pyB);
+  auto chunk = [&](int c, float4 (&px)[4], float4 (&py)[4]) {
     const int s = c & 1, use = c >> 1;
     uint8_t* st = smem + s * WT_STAGE_BYTES;
     if (c >= 2) mbar_wait_warp(&bars[s], (use - 1) & 1);
@@ -116,7 +119,7 @@ __global__ void __launch_bounds__(256, 1) k_wgrad_tc(const WgradTcParams p) {
         }
       }
     }
-    if (c + 1 < nchunks) prefetch(c + 1);
+    if (c + 2 < nchunks) prefetch(c + 2, px, py);
     fence_proxy_async();
     __syncthreads();
     if (warp == 0) {      // the whole warp runs the issue code convergently, one elected lane issues (see elect_one())
@@ -138,6 +141,10 @@ __global__ void __launch_bounds__(256, 1) k_wgrad_tc(const WgradTcParams p) {
       if (leader) umma_commit(&bars[s]);
       __syncwarp();
     }
+  };
+  for (int c = 0; c < nchunks; c += 2) {
+    chunk(c, pxA, pyA);
+    if (c + 1 < nchunks) chunk(c + 1, pxB, pyB);
   }
   float* out = p.part + (size_t)split * p.K * p.Nout;
   if (nchunks > 0) {

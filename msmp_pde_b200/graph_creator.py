@@ -1,0 +1,158 @@
+"""Drop-in for ``common.utils.GraphCreator`` (common/utils.py:267-471): the step either side of the hot path.
+
+Same constructor, same three methods, same outputs -- values, dtypes, field order and the edge list are identical
+to the reference's (checked bit for bit against fixtures written by the reference class, tests/golden/graph_*.npz).
+What changes is how they are produced:
+
+* the reference builds every field with Python loops and ``torch.cat`` (one iteration per sample, and one per NODE
+  for the equation parameters, ``:388-426``) on the CPU; here each field is one vectorised expression that runs on
+  whatever device the inputs live on;
+* the topology depends only on the grid and the batch size (``:365-380``), so the edge list is built once per
+  (grid, batch size, device) and the SAME ``edge_index`` / ``batch`` tensors are handed out afterwards -- the model's
+  CSR / CSC topology cache (``graph.get_topology``, keyed on tensor identity) then hits on every step and the
+  captured training step (``GraphedTrainStep``) can be replayed.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+from torch import nn
+
+from .compat.torch_cluster import knn_graph, radius_graph
+from .compat.torch_geometric.data import Data
+
+_RADIUS_PDES = ("CE", "KF", "KS", "AD")
+
+
+class GraphCreator(nn.Module):
+    def __init__(self, pde, neighbors: int = 2, time_window: int = 5, t_resolution: int = 250,
+                 x_resolution: int = 100) -> None:
+        super().__init__()
+        self.pde = pde
+        self.n = neighbors
+        self.tw = time_window
+        self.t_res = t_resolution
+        self.x_res = x_resolution
+        self.random_probability = 0          # common/utils.py:296 (random extra edges are disabled upstream)
+        assert isinstance(self.n, int)
+        assert isinstance(self.tw, int)
+        self._topo_cache: dict = {}
+
+    # ------------------------------------------------------------------------------------------------
+    def create_data(self, datapoints: torch.Tensor, steps: list):
+        """common/utils.py:300-318: data = dp[step-tw:step], labels = dp[step:step+tw] per sample."""
+        steps_t = torch.as_tensor(steps, device=datapoints.device).long()
+        off = torch.arange(self.tw, device=datapoints.device)
+        b = torch.arange(datapoints.shape[0], device=datapoints.device)[:, None]
+        data = datapoints[b, (steps_t[:, None] - self.tw + off)]
+        labels = datapoints[b, (steps_t[:, None] + off)]
+        dt = torch.promote_types(torch.get_default_dtype(), datapoints.dtype)      # torch.Tensor() seeds the cat upstream
+        return data.to(dt), labels.to(dt)
+
+    # ------------------------------------------------------------------------------------------------
+    def _name(self) -> str:
+        return f"{self.pde}"
+
+    def _stack(self, block: torch.Tensor) -> torch.Tensor:
+        """[B, tw, nx] -> [B*nx, tw];  AD: [B, tw, 2, nx] -> [B*nx, 2*tw] (field-major columns, :350-353)."""
+        if self._name() == "AD":
+            B, tw, F, nx = block.shape
+            return block.permute(0, 3, 2, 1).reshape(B * nx, F * tw)
+        B, tw, nx = block.shape
+        return block.permute(0, 2, 1).reshape(B * nx, tw)
+
+    def _times(self, steps, nx, device, dtype):
+        nt = self.pde.grid_size[0]
+        t = torch.linspace(self.pde.tmin, self.pde.tmax, nt)                      # default dtype, CPU: as upstream
+        steps_t = torch.as_tensor(steps).long().cpu()
+        return (torch.ones(nx, dtype=t.dtype)[None, :] * t[steps_t][:, None]).reshape(-1).to(device=device, dtype=dtype)
+
+    def _topology(self, x0: torch.Tensor, B: int):
+        """(edge_index, batch) for B copies of the grid x0 -- built once per grid / batch size / device."""
+        key = (x0.device.type, x0.device.index, B, self.n, self._name(),
+               bool(getattr(self.pde, "untructured_grid", False)), x0.dtype, x0.detach().cpu().numpy().tobytes())
+        hit = self._topo_cache.get(key)
+        if hit is not None:
+            return hit
+        nx = x0.numel()
+        dev = x0.device
+        name = self._name()
+        batch = torch.arange(B, device=dev).repeat_interleave(nx)
+        x_pos = x0.repeat(B)
+        if name in _RADIUS_PDES:
+            dx = x0[1] - x0[0]
+            radius = self.n * dx + 0.0001
+            edge_index = radius_graph(x_pos, r=radius, batch=batch, loop=False)
+            if self.random_probability > 0:
+                raise NotImplementedError("random extra edges (erdos_renyi_graph) are switched off in the reference")
+            if name == "AD" and getattr(self.pde, "untructured_grid", False):
+                edge_index = knn_graph(self._periodic(x0).repeat(B, 1), k=self.n, batch=batch, loop=False)
+        elif name == "WE":
+            edge_index = knn_graph(x_pos, k=self.n, batch=batch, loop=False)
+        else:
+            raise Exception("Wrong experiment")
+        self._topo_cache[key] = (edge_index, batch)
+        return edge_index, batch
+
+    @staticmethod
+    def _periodic(x0: torch.Tensor) -> torch.Tensor:
+        """cylindrical embedding of the periodic coordinate (common/utils.py:343-346)"""
+        X = 2 * np.pi * x0 / (torch.max(x0) - 1e-3)
+        x_per = torch.zeros(len(X), 2, device=x0.device)                           # default dtype, as upstream
+        x_per[:, 0] = torch.cos(X)
+        x_per[:, 1] = torch.sin(X)
+        return x_per
+
+    def create_graph(self, data: torch.Tensor, labels: torch.Tensor, x: torch.Tensor, variables: dict,
+                     steps: list) -> Data:
+        """common/utils.py:320-426"""
+        name = self._name()
+        nx = self.pde.grid_size[1]
+        B = data.shape[0]
+        dev = data.device
+        fdt = torch.promote_types(torch.get_default_dtype(), data.dtype)
+        u = self._stack(data).to(fdt)
+        y = self._stack(labels).to(torch.promote_types(torch.get_default_dtype(), labels.dtype))
+        x0 = x[0].to(dev)
+        xdt = torch.promote_types(torch.get_default_dtype(), x0.dtype)
+        x_pos = x0.repeat(B).to(xdt)
+        t_pos = self._times(steps, nx, dev, torch.get_default_dtype())
+        edge_index, batch = self._topology(x0, B)
+
+        graph = Data(x=u, edge_index=edge_index)
+        graph.y = y
+        graph.pos = torch.cat((t_pos[:, None].to(torch.promote_types(t_pos.dtype, x_pos.dtype)),
+                               x_pos[:, None].to(torch.promote_types(t_pos.dtype, x_pos.dtype))), 1)
+        graph.batch = batch
+
+        def per_node(key, sign=1.0):
+            v = variables[key]
+            v = torch.stack([torch.as_tensor(e) for e in v]) if isinstance(v, (list, tuple)) else torch.as_tensor(v)
+            v = v.reshape(-1)[:B].to(dev)
+            col = (v * sign)[batch][:, None]
+            return col.to(torch.promote_types(torch.get_default_dtype(), col.dtype))
+
+        if name == "CE":
+            graph.alpha = per_node("alpha")
+            graph.beta = per_node("beta", -1.0)
+            graph.gamma = per_node("gamma")
+        elif name == "KF":
+            graph.r = per_node("r")
+            graph.D = per_node("D")
+        elif name == "WE":
+            graph.bc_left = per_node("bc_left")
+            graph.bc_right = per_node("bc_right")
+            graph.c = per_node("c")
+        elif name == "AD":
+            graph.a = per_node("a")
+            graph.b = per_node("b")
+        return graph
+
+    def create_next_graph(self, graph: Data, pred: torch.Tensor, labels: torch.Tensor, steps: list) -> Data:
+        """common/utils.py:431-471: the prediction becomes the input, labels and time stamps advance."""
+        keep = 2 * self.tw if self._name() == "AD" else self.tw
+        graph.x = torch.cat((graph.x, pred), 1)[:, keep:]
+        nx = self.pde.grid_size[1]
+        graph.y = self._stack(labels).to(torch.promote_types(torch.get_default_dtype(), labels.dtype)).to(graph.x.device)
+        graph.pos[:, 0] = self._times(steps, nx, graph.pos.device, torch.get_default_dtype())
+        return graph

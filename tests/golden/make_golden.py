@@ -182,8 +182,45 @@ VARIANTS_2F = ["MP_PDE_Solver2D", "MP_PDE_Solver2DGated", "MP_PDE_Solver2DLEMLin
                "MP_PDE_Solver2DLSTMLin", "MP_PDE_Solver2DLEMLin"]
 
 
+def graph_cases():
+    """Fixtures of the reference's own GraphCreator (common/utils.py:267-471): every field of create_data,
+    create_graph and create_next_graph on seeded trajectories, for the four graph-construction branches."""
+    import common.utils as cu
+    from msmp_pde_b200.synth import SyntheticPDE, pseudo_random_grid
+    out = {}
+    for tag, name, unstructured, fields, n, dt_in in (
+            ("ce", "CE", False, 1, 2, torch.float64), ("ad", "AD", False, 2, 3, torch.float32),
+            ("adu", "AD", True, 2, 3, torch.float64), ("we", "WE", False, 1, 2, torch.float64)):
+        nt, nx, tw, B = 90, 28, 10, 3
+        pde = SyntheticPDE(name, L=16.0, tmax=4.0, grid_size=(nt, nx), untructured_grid=unstructured)
+        g = torch.Generator().manual_seed(100 + len(out))
+        shape = (B, nt, nx) if fields == 1 else (B, nt, fields, nx)
+        traj = torch.randn(*shape, generator=g, dtype=torch.float64).to(dt_in)
+        grid = pseudo_random_grid(0.0, 16.0, nx) if unstructured else np.linspace(0.0, 16.0, nx)
+        x = torch.tensor(grid, dtype=torch.float64).repeat(B, 1)
+        keys = {"CE": ("alpha", "beta", "gamma"), "AD": ("a", "b"), "WE": ("bc_left", "bc_right", "c")}[name]
+        variables = {k: torch.rand(B, generator=g, dtype=torch.float64) for k in keys}
+        steps, steps2 = [10, 37, 52], [20, 47, 62]
+        gc = cu.GraphCreator(pde=pde, neighbors=n, time_window=tw, t_resolution=nt, x_resolution=nx)
+        data, labels = gc.create_data(traj, steps)
+        graph = gc.create_graph(data, labels, x, variables, steps)
+        arrs = {"traj": traj, "x": x, "data": data, "labels": labels, "steps": np.array(steps), "steps2": np.array(steps2)}
+        arrs.update({"var_" + k: v for k, v in variables.items()})
+        arrs.update({"g_" + k: graph[k].clone() for k in graph.keys()})
+        pred = torch.randn(graph.x.shape[0], fields * tw, generator=g, dtype=torch.float64)
+        _, labels2 = gc.create_data(traj, steps2)
+        nxt = gc.create_next_graph(graph, pred, labels2, steps2)
+        arrs.update({"pred": pred, "labels2": labels2})
+        arrs.update({"n_" + k: nxt[k].clone() for k in ("x", "y", "pos")})
+        np.savez_compressed(os.path.join(os.path.dirname(__file__), f"graph_{tag}.npz"), **_np(arrs))
+        out[tag] = {k: str(v.dtype) for k, v in arrs.items() if torch.is_tensor(v)}
+        print(f"graph_{tag}.npz", "E", graph.edge_index.shape[1], out[tag]["g_x"], out[tag]["g_pos"])
+    return out
+
+
 def main():
     mg, mg2 = _load_reference()
+    graph_cases()
     layer_case(mg, "GNN_Layer", 11, 25, 1, "layer_gnn.npz")
     layer_case(mg, "GNN_LayerLin", 12, 50, 3, "layer_gnnlin.npz")
     model_case(mg.MP_PDE_Solver, synth.config_c1, dict(B=3, nx=40), "mp_pde_c1.npz")
