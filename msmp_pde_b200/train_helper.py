@@ -1,0 +1,107 @@
+"""``training_loop`` of the reference (experiments/train_helper.py:66-148) for the drop-in GNN solvers.
+
+Same signature, same order of ``random`` draws (number of unrollings, then the start indices), same pushforward trick
+(``:106-112``: the unrolled predictions are computed without gradients and fed back through
+``create_next_graph``), same loss ``sqrt(criterion(pred, graph.y))`` and the same returned ``losses / batch_size``.
+
+What differs is the execution of the gradient step: when the optimizer is capturable (``torch.optim.AdamW(...,
+capturable=True)``) and the graphs keep one topology (fixed grid and batch size, which is what ``GraphCreator``
+produces), forward + loss + backward + optimizer update run as ONE CUDA-graph replay (``GraphedTrainStep``); the
+graph fields are copied into its static buffers.  With any other optimizer the step runs eagerly -- still on the CUDA
+kernels -- exactly like the reference loop.
+"""
+from __future__ import annotations
+
+import random
+
+import torch
+
+from .models_gnn import MP_PDE_SolverLEMLinGatedSave
+from .train_step import GraphedTrainStep
+
+
+def reset_state_bool(model) -> bool:
+    """experiments/train_helper.py:10-13"""
+    inst = isinstance(model, MP_PDE_SolverLEMLinGatedSave)
+    has = hasattr(model, "save_state")
+    return inst or (has and model.save_state is not None and model.save_state)
+
+
+def _is_sum_mse(criterion) -> bool:
+    return isinstance(criterion, torch.nn.MSELoss) and criterion.reduction == "sum"
+
+
+def training_loop(model: torch.nn.Module, unrolling: list, batch_size: int, optimizer, loader, graph_creator, criterion,
+                  device="cpu") -> torch.Tensor:
+    """One training epoch with random starting points for every trajectory (experiments/train_helper.py:66-148)."""
+    if f"{model}" != "GNN":
+        raise NotImplementedError("msmp_pde_b200.train_helper.training_loop drives the GNN solvers only")
+    capturable = bool(optimizer.param_groups and all(g.get("capturable", False) for g in optimizer.param_groups))
+    fused_step = capturable and _is_sum_mse(criterion) and not reset_state_bool(model) \
+        and torch.device(device).type == "cuda"
+    cache = model.__dict__.setdefault("_msmp_graphed_steps", {})
+    losses = []
+    for (u_base, u_super, x, variables) in loader:
+        if not fused_step:
+            optimizer.zero_grad()          # (the captured step overwrites every gradient; its buffers must stay allocated)
+        # graphs are built on the target device: the creator then hands out the same device-resident edge list for
+        # every batch and the model's topology cache / the captured step are reused
+        u_super, x = u_super.to(device), x.to(device)
+        # Randomly choose number of unrollings, then the starting (time) points on the solution manifold
+        unrolled_graphs = random.choice(unrolling)
+        steps = [t for t in range(graph_creator.tw,
+                                  graph_creator.t_res - graph_creator.tw - (graph_creator.tw * unrolled_graphs) + 1)]
+        random_steps = random.choices(steps, k=batch_size)
+        data, labels = graph_creator.create_data(u_super, random_steps)
+        graph = graph_creator.create_graph(data, labels, x, variables, random_steps).to(device)
+
+        with torch.no_grad():                               # the pushforward trick
+            for _ in range(unrolled_graphs):
+                random_steps = [rs + graph_creator.tw for rs in random_steps]
+                _, labels = graph_creator.create_data(u_super, random_steps)
+                pred = model(graph)
+                graph = graph_creator.create_next_graph(graph, pred, labels, random_steps).to(device)
+
+        if fused_step:
+            key = (id(optimizer), id(graph.edge_index), tuple(graph.x.shape))
+            step = cache.get(key)
+            if step is None:
+                # the constructor runs its warm-up steps on a scratch copy of the state so that this call still
+                # performs exactly one optimizer update
+                state = ({k: v.detach().clone() for k, v in model.state_dict().items()},
+                         _clone_opt_state(optimizer))
+                step = GraphedTrainStep(model, optimizer, graph, warmup=1)
+                model.load_state_dict(state[0])
+                _restore_opt_state(optimizer, state[1])
+                cache[key] = step
+            loss = step(graph).to(graph.x.dtype)
+            losses.append(loss.detach().clone() / batch_size)
+        else:
+            pred = model(graph)
+            loss = torch.sqrt(criterion(pred, graph.y))
+            loss.backward()
+            losses.append(loss.detach() / batch_size)
+            optimizer.step()
+
+        if reset_state_bool(model):                          # reset the hidden state of LEM for new data
+            model.embedding_lem.reset_states()
+    return torch.stack(losses)
+
+
+def _clone_opt_state(optimizer):
+    return {id(p): {k: (v.detach().clone() if torch.is_tensor(v) else v) for k, v in st.items()}
+            for p, st in optimizer.state.items()}
+
+
+def _restore_opt_state(optimizer, saved):
+    for p in list(optimizer.state.keys()):
+        if id(p) in saved:
+            for k, v in saved[id(p)].items():
+                if torch.is_tensor(v):
+                    optimizer.state[p][k].copy_(v)
+                else:
+                    optimizer.state[p][k] = v
+        else:                                                # state created by the warm-up: back to "never stepped"
+            for k, v in optimizer.state[p].items():
+                if torch.is_tensor(v):
+                    v.zero_()

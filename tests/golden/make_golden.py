@@ -218,9 +218,44 @@ def graph_cases():
     return out
 
 
+def training_loop_case(mg2):
+    """Three batches of the reference's own training_loop (experiments/train_helper.py:66-148) with its own
+    GraphCreator and MP_PDE_Solver2DLEMLinGated on seeded synthetic AD trajectories (float64, CPU): the per-batch
+    losses it returns, with and without the pushforward unrolling."""
+    import random
+    import common.utils as cu
+    import experiments.train_helper as th
+    from msmp_pde_b200.synth import SyntheticPDE
+    nt, nx, tw, B, nb = 120, 40, 25, 4, 3
+    pde = SyntheticPDE("AD", L=16.0, tmax=4.0, grid_size=(nt, nx))
+    g = torch.Generator().manual_seed(77)
+    loader = []
+    for _ in range(nb):
+        traj = torch.randn(B, nt, 2, nx, generator=g, dtype=torch.float64)
+        x = torch.linspace(0.0, 16.0, nx, dtype=torch.float64).repeat(B, 1)
+        variables = {"a": 0.1 + 0.9 * torch.rand(B, generator=g, dtype=torch.float64),
+                     "b": 1.0 + 9.0 * torch.rand(B, generator=g, dtype=torch.float64)}
+        loader.append((traj, traj, x, variables))
+    arrs = {}
+    for i, (u_b, u_s, x, v) in enumerate(loader):
+        arrs[f"traj{i}"], arrs[f"x{i}"], arrs[f"a{i}"], arrs[f"b{i}"] = u_s, x, v["a"], v["b"]
+    for tag, unrolling in (("u0", [0]), ("u01", [0, 1])):
+        model = mg2.MP_PDE_Solver2DLEMLinGated(pde, time_window=tw, hidden_features=128, hidden_layer=6,
+                                                eq_variables={"a": 1.0, "b": 1.0})
+        formula_weights_(model)
+        gc = cu.GraphCreator(pde=pde, neighbors=3, time_window=tw, t_resolution=nt, x_resolution=nx)
+        opt = torch.optim.AdamW(model.parameters(), lr=1e-4)
+        random.seed(5)
+        losses = th.training_loop(model, unrolling, B, opt, loader, gc, torch.nn.MSELoss(reduction="sum"), "cpu")
+        arrs["losses_" + tag] = losses
+        print("training_loop", tag, [float(l) for l in losses])
+    np.savez_compressed(os.path.join(os.path.dirname(__file__), "training_loop_ad.npz"), **_np(arrs))
+
+
 def main():
     mg, mg2 = _load_reference()
     graph_cases()
+    training_loop_case(mg2)
     layer_case(mg, "GNN_Layer", 11, 25, 1, "layer_gnn.npz")
     layer_case(mg, "GNN_LayerLin", 12, 50, 3, "layer_gnnlin.npz")
     model_case(mg.MP_PDE_Solver, synth.config_c1, dict(B=3, nx=40), "mp_pde_c1.npz")
