@@ -105,3 +105,71 @@ def _restore_opt_state(optimizer, saved):
             for k, v in optimizer.state[p].items():
                 if torch.is_tensor(v):
                     v.zero_()
+
+
+def test_timestep_losses(model, steps: list, batch_size: int, loader, graph_creator, criterion, device="cpu") -> None:
+    """Loss of one forward pass at the time points that are multiples of the time window
+    (experiments/train_helper.py:150-203); prints like the reference, returns None."""
+    if f"{model}" != "GNN":
+        raise NotImplementedError("msmp_pde_b200.train_helper drives the GNN solvers only")
+    for step in steps:
+        if step != graph_creator.tw and step % graph_creator.tw != 0:
+            continue
+        losses = []
+        for (u_base, u_super, x, variables) in loader:
+            with torch.no_grad():
+                u_super, x = u_super.to(device), x.to(device)
+                same_steps = [step] * batch_size
+                data, labels = graph_creator.create_data(u_super, same_steps)
+                graph = graph_creator.create_graph(data, labels, x, variables, same_steps).to(device)
+                pred = model(graph)
+                losses.append(criterion(pred, graph.y) / batch_size)
+            if reset_state_bool(model):
+                model.embedding_lem.reset_states()
+        losses = torch.stack(losses)
+        print(f'Step {step}, mean loss {torch.mean(losses)}')
+
+
+def test_unrolled_losses(model, steps: list, batch_size: int, nr_gt_steps: int, nx_base_resolution: int, loader,
+                         graph_creator, criterion, device="cpu") -> torch.Tensor:
+    """Loss of the full autoregressive rollout of every trajectory (experiments/train_helper.py:205-292): the
+    prediction of one window is the input of the next through ``create_next_graph``."""
+    if f"{model}" != "GNN":
+        raise NotImplementedError("msmp_pde_b200.train_helper drives the GNN solvers only")
+    losses, losses_base = [], []
+    tw = graph_creator.tw
+    for (u_base, u_super, x, variables) in loader:
+        losses_tmp, losses_base_tmp = [], []
+        with torch.no_grad():
+            u_base, u_super, x = u_base.to(device), u_super.to(device), x.to(device)
+            same_steps = [tw * nr_gt_steps] * batch_size
+            data, labels = graph_creator.create_data(u_super, same_steps)
+            graph = graph_creator.create_graph(data, labels, x, variables, same_steps).to(device)
+            pred = model(graph)
+            losses_tmp.append(criterion(pred, graph.y) / nx_base_resolution / batch_size)
+            # unroll the trajectory; every window adds its loss
+            for step in range(tw * (nr_gt_steps + 1), graph_creator.t_res - tw + 1, tw):
+                same_steps = [step] * batch_size
+                _, labels = graph_creator.create_data(u_super, same_steps)
+                graph = graph_creator.create_next_graph(graph, pred, labels, same_steps).to(device)
+                pred = model(graph)
+                losses_tmp.append(criterion(pred, graph.y) / nx_base_resolution / batch_size)
+            if reset_state_bool(model):
+                model.embedding_lem.reset_states()
+            # losses of the numerical baseline
+            for step in range(tw * nr_gt_steps, graph_creator.t_res - tw + 1, tw):
+                same_steps = [step] * batch_size
+                _, labels_super = graph_creator.create_data(u_super, same_steps)
+                _, labels_base = graph_creator.create_data(u_base, same_steps)
+                losses_base_tmp.append(criterion(labels_super, labels_base) / nx_base_resolution / batch_size)
+        losses.append(torch.sum(torch.stack(losses_tmp)))
+        losses_base.append(torch.sum(torch.stack(losses_base_tmp)))
+    losses = torch.stack(losses)
+    losses_base = torch.stack(losses_base)
+    print(f'Unrolled forward losses {torch.mean(losses)}')
+    print(f'Unrolled forward base losses {torch.mean(losses_base)}')
+    return losses
+
+
+test_timestep_losses.__test__ = False      # (named as in the reference; not pytest tests)
+test_unrolled_losses.__test__ = False

@@ -249,6 +249,12 @@ def training_loop_case(mg2):
         losses = th.training_loop(model, unrolling, B, opt, loader, gc, torch.nn.MSELoss(reduction="sum"), "cpu")
         arrs["losses_" + tag] = losses
         print("training_loop", tag, [float(l) for l in losses])
+    # full autoregressive rollout of the same trajectories (experiments/train_helper.py:205-292), closed-form weights
+    model = mg2.MP_PDE_Solver2DLEMLinGated(pde, time_window=tw, hidden_features=128, hidden_layer=6,
+                                            eq_variables={"a": 1.0, "b": 1.0})
+    formula_weights_(model)
+    arrs["unrolled"] = th.test_unrolled_losses(model, [], B, 1, nx, loader, gc, torch.nn.MSELoss(reduction="sum"), "cpu")
+    print("test_unrolled_losses", [float(l) for l in arrs["unrolled"]])
     np.savez_compressed(os.path.join(os.path.dirname(__file__), "training_loop_ad.npz"), **_np(arrs))
 
 
