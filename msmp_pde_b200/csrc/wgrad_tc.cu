@@ -17,7 +17,10 @@ namespace msmp {
 constexpr int WT_CHUNK = 32;                               // rows (MMA-K) per stage
 constexpr int WT_OP_BYTES = WT_CHUNK * 128 * 4;            // one [32 x 128] operand image = 16 KiB
 constexpr int WT_STAGE_BYTES = 4 * WT_OP_BYTES;            // X_hi, X_lo, dY_hi, dY_lo
-constexpr int WT_SMEM = 2 * WT_STAGE_BYTES + 1024 + 256 + 8 * 8 * 128 * 4;
+constexpr int WT_TAIL_COLS = 64;                           // a narrow second column block (K1 <= 64) rides along, see below
+constexpr int WT_TAIL_OP_BYTES = WT_CHUNK * WT_TAIL_COLS * 4;     // one [32 x 64] operand image = 8 KiB
+constexpr int WT_TAIL_STAGE_BYTES = 2 * WT_TAIL_OP_BYTES;  // X1_hi, X1_lo
+constexpr int WT_SMEM = 2 * WT_STAGE_BYTES + 2 * WT_TAIL_STAGE_BYTES + 1024 + 256 + 8 * 8 * 128 * 4;
 
 struct WgradTcParams {
   const float* X; int ldx; int K; int xswish;     // K = rows of dWt in total
@@ -27,6 +30,8 @@ struct WgradTcParams {
   float* part;         // [S][K][Nout]
   float* part_side;    // [S][nside][Nout]
   int M; int rows_per_split;
+  int tail;            // > 0: X1 has `tail` (<= 64) columns and is NOT a k-block of the grid: the CTAs of k-block 0 also
+                       // compute D'[n][k1] = dY^T X1 (operands swapped: M = 128 outputs, N = 64) into TMEM columns 128..191
 };
 
 // byte offset of (row m in 0..31, 16-byte chunk c4 in 0..31) of a [32 x 128] MN-major (BASE32B) operand image:
@@ -40,9 +45,10 @@ __device__ __forceinline__ uint32_t mn_off(int m, int c4) {
 __global__ void __launch_bounds__(256, 1) k_wgrad_tc(const WgradTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * WT_STAGE_BYTES);     // free[2]
+  uint8_t* smem_tail = smem + 2 * WT_STAGE_BYTES;                              // 2 stages of (X1_hi | X1_lo)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_tail + 2 * WT_TAIL_STAGE_BYTES);     // free[2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
-  float* sred = reinterpret_cast<float*>(smem + 2 * WT_STAGE_BYTES + 256);     // [8 warps][8 side rows][128]
+  float* sred = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);        // [8 warps][8 side rows][128]
   const int tid = threadIdx.x, warp = warp_index_uniform(), lane = tid & 31;
   const int split = blockIdx.x;
   const int k0 = blockIdx.y * 128, n0 = blockIdx.z * 128;
@@ -57,8 +63,9 @@ __global__ void __launch_bounds__(256, 1) k_wgrad_tc(const WgradTcParams p) {
   const int nchunks = (m_end > m_begin) ? (m_end - m_begin + WT_CHUNK - 1) / WT_CHUNK : 0;
   const int nside = p.r + p.has_bias;
   const bool do_side = (blockIdx.y == 0) && nside > 0;
+  const bool do_tail = p.tail > 0 && blockIdx.y == 0;
 
-  if (warp == 0) tmem_alloc(tmem_slot, 128);
+  if (warp == 0) tmem_alloc(tmem_slot, 256);
   if (tid == 32) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
@@ -74,11 +81,20 @@ __global__ void __launch_bounds__(256, 1) k_wgrad_tc(const WgradTcParams p) {
   // Two register sets: the rows of chunks c+1 and c+2 are in flight while chunk c is split / stored and its MMAs are
   // issued (with a single set the loads were issued a few hundred cycles before they were needed).
   float4 pxA[4], pyA[4], pxB[4], pyB[4];
+  float4 ptA[2], ptB[2];      // the narrow tail block: 32 rows x 64 columns = 2 float4 per thread
   float sacc[8][4];
 #pragma unroll
   for (int q = 0; q < 8; ++q) sacc[q][0] = sacc[q][1] = sacc[q][2] = sacc[q][3] = 0.f;
-  auto prefetch = [&](int c, float4 (&px)[4], float4 (&py)[4]) {
+  auto prefetch = [&](int c, float4 (&px)[4], float4 (&py)[4], float4 (&pt)[2]) {
     const int mb = m_begin + c * WT_CHUNK;
+    if (do_tail) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int idx = tid + 256 * i;
+        const int m = mb + (idx >> 4), c4 = idx & 15;
+        pt[i] = (m < m_end && 4 * c4 < p.tail) ? ldg4(p.X1 + (size_t)m * p.ldx1 + 4 * c4) : zero4();
+      }
+    }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int idx = tid + 256 * i;
@@ -88,11 +104,13 @@ __global__ void __launch_bounds__(256, 1) k_wgrad_tc(const WgradTcParams p) {
       py[i] = (okm && n0 + 4 * c4 < p.Nout) ? ldg4(p.dY + (size_t)m * p.lddy + n0 + 4 * c4) : zero4();
     }
   };
-  if (nchunks > 0) prefetch(0, pxA, pyA);
-  if (nchunks > 1) prefetch(1, pxB, pyB);
-  auto chunk = [&](int c, float4 (&px)[4], float4 (&py)[4]) {
+  if (nchunks > 0) prefetch(0, pxA, pyA, ptA);
+  if (nchunks > 1) prefetch(1, pxB, pyB, ptB);
+  constexpr uint32_t IDESC_TAIL = umma_idesc_tf32(128, WT_TAIL_COLS, 1, 1);
+  auto chunk = [&](int c, float4 (&px)[4], float4 (&py)[4], float4 (&pt)[2]) {
     const int s = c & 1, use = c >> 1;
     uint8_t* st = smem + s * WT_STAGE_BYTES;
+    uint8_t* stt = smem_tail + s * WT_TAIL_STAGE_BYTES;
     if (c >= 2) mbar_wait_warp(&bars[s], (use - 1) & 1);
     const int mb = m_begin + c * WT_CHUNK;
 #pragma unroll
@@ -119,7 +137,16 @@ __global__ void __launch_bounds__(256, 1) k_wgrad_tc(const WgradTcParams p) {
         }
       }
     }
-    if (c + 2 < nchunks) prefetch(c + 2, px, py);
+    if (do_tail) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int idx = tid + 256 * i;
+        float4 x = pt[i];
+        if (p.xswish) x = swish4(x);
+        store_split4(stt, stt + WT_TAIL_OP_BYTES, mn_off(idx >> 4, idx & 15), x);
+      }
+    }
+    if (c + 2 < nchunks) prefetch(c + 2, px, py, pt);
     fence_proxy_async();
     __syncthreads();
     if (warp == 0) {      // the whole warp runs the issue code convergently, one elected lane issues (see elect_one())
@@ -137,14 +164,23 @@ __global__ void __launch_bounds__(256, 1) k_wgrad_tc(const WgradTcParams p) {
           umma_tf32(tm, dxl, dyh, IDESC, 1u);
           umma_tf32(tm, dxh, dyl, IDESC, 1u);
         }
+        if (do_tail) {      // D'[n][k1] += dY^T X1: the dY images are the A operand here, the X1 images the (64-wide) B operand
+          const uint32_t th = smem_u32(stt), tl = th + WT_TAIL_OP_BYTES;
+          const uint64_t dth = umma_desc(th + ko, 4096, 512, 1), dtl = umma_desc(tl + ko, 4096, 512, 1);
+          if (leader) {
+            umma_tf32(tm + 128, dyh, dth, IDESC_TAIL, (c | k) ? 1u : 0u);
+            umma_tf32(tm + 128, dyl, dth, IDESC_TAIL, 1u);
+            umma_tf32(tm + 128, dyh, dtl, IDESC_TAIL, 1u);
+          }
+        }
       }
       if (leader) umma_commit(&bars[s]);
       __syncwarp();
     }
   };
   for (int c = 0; c < nchunks; c += 2) {
-    chunk(c, pxA, pyA);
-    if (c + 1 < nchunks) chunk(c + 1, pxB, pyB);
+    chunk(c, pxA, pyA, ptA);
+    if (c + 1 < nchunks) chunk(c + 1, pxB, pyB, ptB);
   }
   float* out = p.part + (size_t)split * p.K * p.Nout;
   if (nchunks > 0) {
@@ -175,6 +211,24 @@ __global__ void __launch_bounds__(256, 1) k_wgrad_tc(const WgradTcParams p) {
       }
     }
   }
+  // narrow tail block: TMEM lanes = output columns n, columns = k1; rows K0 + k1 of the partial dWt
+  if (do_tail) {
+    const int n = n0 + 32 * (warp & 3) + lane;
+    const int kb = 32 * (warp >> 2);
+    float v[32];
+    if (nchunks > 0) {
+      __syncwarp();
+      tmem_ld32(tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(128 + kb), v);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = 0.f;
+    }
+    if (n < p.Nout) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (kb + j < p.tail) out[(size_t)(p.K0 + kb + j) * p.Nout + n] = v[j];
+    }
+  }
   // side / bias partials: fixed-order reduction over the 8 warps (thread lane owns columns 4*lane..4*lane+3)
   if (do_side) {
 #pragma unroll
@@ -190,7 +244,7 @@ __global__ void __launch_bounds__(256, 1) k_wgrad_tc(const WgradTcParams p) {
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, 128);
+  if (warp == 0) tmem_dealloc(tmem, 256);
 }
 
 }  // namespace msmp
@@ -221,7 +275,13 @@ extern "C" int msmp_linear_wgrad_tc2(const float* X, int ldx, int K0, const floa
   if (X1 && ((K0 & 127) || (K1 & 3) || (ldx1 & 3) || K1 <= 0)) return MSMP_ERR_ARG;
   const int nside = (side ? r : 0) + (has_bias ? 1 : 0);
   if (ws_bytes < msmp_linear_wgrad_workspace(M, K, Nout, nside)) return MSMP_ERR_WORKSPACE;
-  const int S = msmp_linear_wgrad_splits(M, K, Nout);
+  int S = msmp_linear_wgrad_splits(M, K, Nout);
+  const int tail = (X1 && K1 <= WT_TAIL_COLS) ? K1 : 0;
+  if (tail) {      // fewer CTAs per split than the workspace query assumed: stay within one wave of 148 SMs
+    const int tiles = ((K0 + 127) / 128) * ((Nout + 127) / 128);
+    const int one_wave = 148 / tiles > 0 ? 148 / tiles : 1;
+    if (S > one_wave) S = one_wave;
+  }
   WgradTcParams p{};
   p.X = X; p.ldx = ldx; p.K = K; p.xswish = xswish; p.dY = dY; p.lddy = lddy; p.Nout = Nout;
   p.X1 = X1; p.ldx1 = ldx1; p.K0 = K0;
@@ -229,6 +289,9 @@ extern "C" int msmp_linear_wgrad_tc2(const float* X, int ldx, int K0, const floa
   p.part = reinterpret_cast<float*>(workspace);
   p.part_side = p.part + (size_t)S * K * Nout;
   p.M = M;
+  // a narrow second block (the zero-padded inputs of the LEM maps, the u columns of the P|Q projection) does not get
+  // k-block CTAs of its own -- three quarters of their MMA rows and of their staging would be padding
+  p.tail = tail;
   int rps = (M + S - 1) / S;
   rps = ((rps + WT_CHUNK - 1) / WT_CHUNK) * WT_CHUNK;
   if (rps < WT_CHUNK) rps = WT_CHUNK;
@@ -239,7 +302,7 @@ extern "C" int msmp_linear_wgrad_tc2(const float* X, int ldx, int K0, const floa
       return MSMP_ERR_CUDA;
     attr_set = true;
   }
-  dim3 grid(S, (K + 127) / 128, (Nout + 127) / 128);
+  dim3 grid(S, ((p.tail ? K0 : K) + 127) / 128, (Nout + 127) / 128);
   k_wgrad_tc<<<grid, 256, WT_SMEM, stream>>>(p);
   MSMP_CHECK_LAUNCH();
   {
