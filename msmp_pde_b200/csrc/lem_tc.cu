@@ -498,23 +498,6 @@ __global__ void __launch_bounds__(LF_THREADS, 1) k_lem_bwd_tc(const LemBwdParams
       const float* __restrict__ gz = (p.gZ && ext) ? p.gZ + (p.g_last_only ? 0 : (size_t)t * plane) + (size_t)row0 * 128 : nullptr;
       float* __restrict__ dG_t = p.dG + (size_t)t * p.N * 384 + (size_t)row0 * 384;
       float* __restrict__ dL_t = p.dL + (size_t)t * plane + (size_t)row0 * 128;
-      if (t > p.t_begin) {
-        // the activations saved by the forward pass are in HBM by now: pull the next step's rows of this thread's
-        // node half into L2 (gates 2 KiB, y and z 512 B per node; one 128-byte line per prefetch)
-        const float* g_n = p.gates + ((size_t)(t - 1) * p.Npad + row0 + j0) * 512;
-        const float* y_n = p.Y + (size_t)(t - 1) * plane + (size_t)(row0 + j0) * 128;
-        const float* z_n = p.Z + (size_t)(t - 1) * plane + (size_t)(row0 + j0) * 128;
-        const int part = warp & 3;      // the four warps of a node half share the work
-        for (int q = lane + 32 * part; q < 32 * 16; q += 128)
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(g_n + (size_t)(q >> 4) * 512 + 32 * (q & 15)));
-        for (int q = lane + 32 * part; q < 32 * 4; q += 128) {
-          const int j = q >> 2;
-          if (row0 + j0 + j < p.N) {
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(y_n + (size_t)j * 128 + 32 * (q & 3)));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(z_n + (size_t)j * 128 + 32 * (q & 3)));
-          }
-        }
-      }
       // ---- bwd_y : dL -> tile X + global, dG0 -> global + TMEM stash, dy <- d (1 - a)
       LEM_TICK(32);
 #pragma unroll
@@ -544,6 +527,7 @@ __global__ void __launch_bounds__(LF_THREADS, 1) k_lem_bwd_tc(const LemBwdParams
           state_store(X, state_off(j, c), dl);
         }
         tmem_st8(tbase + LB_S0 + jj, g0);
+        LEM_TICK(40 + jj / 8);
       }
       tmem_st_wait();
       publish_to_mma();
@@ -585,6 +569,24 @@ __global__ void __launch_bounds__(LF_THREADS, 1) k_lem_bwd_tc(const LemBwdParams
       }
       publish_to_mma();
       LEM_TICK(35);
+      if (t > p.t_begin) {
+        // the activations saved by the forward pass are in HBM by now: while the acc2 GEMMs run (the memory pipe is idle)
+        // pull the next step's rows of this thread's node half into L2 (gates 2 KiB, y and z 512 B per node; one
+        // 128-byte line per prefetch).  Issued in front of bwd_y the prefetches queued ahead of its demand loads.
+        const float* g_n = p.gates + ((size_t)(t - 1) * p.Npad + row0 + j0) * 512;
+        const float* y_n = p.Y + (size_t)(t - 1) * plane + (size_t)(row0 + j0) * 128;
+        const float* z_n = p.Z + (size_t)(t - 1) * plane + (size_t)(row0 + j0) * 128;
+        const int part = warp & 3;      // the four warps of a node half share the work
+        for (int q = lane + 32 * part; q < 32 * 16; q += 128)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(g_n + (size_t)(q >> 4) * 512 + 32 * (q & 15)));
+        for (int q = lane + 32 * part; q < 32 * 4; q += 128) {
+          const int j = q >> 2;
+          if (row0 + j0 + j < p.N) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(y_n + (size_t)j * 128 + 32 * (q & 3)));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(z_n + (size_t)j * 128 + 32 * (q & 3)));
+          }
+        }
+      }
       // ---- acc2^T = W[:, :128]^T [dG1 | dG2 | dG0]^T: the dG0 block is staged into X as soon as the dG1 GEMM has read it
       wait_bar(acc_mid, nmid);
       LEM_TICK(36);

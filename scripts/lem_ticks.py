@@ -30,3 +30,5 @@ print("backward:")
 for (i0, _), (i1, name) in zip(seq[:-1], seq[1:]):
     print(f"{name:45s} {t[i1]-t[i0]:8d} cycles")
 print("step total", t[39] - t[32])
+
+print("bwd_y batches (cycles since bwd_y start):", [t[40 + i] - t[32] for i in range(4)])
