@@ -425,8 +425,16 @@ struct LemBwdParams {
 // TMEM columns of the backward kernel (256 allocated): acc1, acc2, and the dG2 / dG0 blocks of the current step
 // (stashed by the thread that computed them until their k-block of the acc2 GEMM is staged).
 constexpr uint32_t LB_ACC1 = 0, LB_ACC2 = 64, LB_S2 = 128, LB_S0 = 192;
+// The backward epilogues are bound by memory latency (saved activations in, dG / dL out), not by issue slots: sixteen
+// epilogue warps (16 nodes per thread instead of 32) keep twice as many loads in flight.
+constexpr int LB_EPI_WARPS = 16;
+constexpr int LB_NPT = LT_NODES / (LB_EPI_WARPS / 4);       // nodes per thread
+constexpr int LB_THREADS = 32 * LB_EPI_WARPS + 64;          // + ring producer warp + MMA warp
 
-__global__ void __launch_bounds__(LF_THREADS, 1) k_lem_bwd_tc(const LemBwdParams p) {
+__device__ __forceinline__ void bwd_ready_arrive() { asm volatile("bar.arrive 2, %0;" ::"n"(32 * LB_EPI_WARPS + 32) : "memory"); }
+__device__ __forceinline__ void bwd_ready_wait() { asm volatile("bar.sync 2, %0;" ::"n"(32 * LB_EPI_WARPS + 32) : "memory"); }
+
+__global__ void __launch_bounds__(LB_THREADS, 1) k_lem_bwd_tc(const LemBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   const LemSmem m = lem_smem(smem_raw, 2, 3);      // two state tiles (X, Y) + 3 ring stages
   const int tid = threadIdx.x, warp = warp_index_uniform(), lane = tid & 31;
@@ -435,7 +443,7 @@ __global__ void __launch_bounds__(LF_THREADS, 1) k_lem_bwd_tc(const LemBwdParams
   lem_init(m, 256);
   uint64_t* acc_mid = &m.bars[17];
 
-  if (warp == 8) {
+  if (warp == LB_EPI_WARPS) {
     // ---- weight ring producer: per step Wz chunks 0..3, then W chunks 4..7 (dG1), 8..11 (dG2), 0..3 (dG0)
     const Ring rg{m.smB, &m.bars[0], &m.bars[8], m.nst};
     if (elect_one()) {
@@ -446,24 +454,24 @@ __global__ void __launch_bounds__(LF_THREADS, 1) k_lem_bwd_tc(const LemBwdParams
       }
     }
     __syncwarp();
-  } else if (warp == 9) {
+  } else if (warp == LB_EPI_WARPS + 1) {
     // ---- MMA issue (whole warp convergent, elected lane issues)
     Epi e = lem_epi(m);
     const uint32_t X = e.smS, Y = e.smS + LT_S_BYTES;
     for (int t = p.t_end - 1; t >= p.t_begin; --t) {
-      state_ready_wait();                                         // dL in X
+      bwd_ready_wait();                                         // dL in X
       gemm_issue(e, X, 4, LB_ACC1, false, e.acc);                 // acc1 = Wz[:, :128]^T dL^T
-      state_ready_wait();                                         // dG1 in X, dG2 in Y
+      bwd_ready_wait();                                         // dG1 in X, dG2 in Y
       gemm_issue(e, X, 4, LB_ACC2, false, acc_mid);               // acc2  = W[128:256, :128]^T dG1^T   (X free afterwards)
       gemm_issue(e, Y, 4, LB_ACC2, true, nullptr);                // acc2 += W[256:384, :128]^T dG2^T
-      state_ready_wait();                                         // dG0 in X
+      bwd_ready_wait();                                         // dG0 in X
       gemm_issue(e, X, 4, LB_ACC2, true, e.acc);                  // acc2 += W[0:128, :128]^T dG0^T
     }
   } else {
     Epi e = lem_epi(m);
-    // epilogue ownership: thread = hidden channel c (TMEM lane), nodes [j0, j0 + 32): its carried dy / dz live in registers
+    // epilogue ownership: thread = hidden channel c (TMEM lane), nodes [j0, j0 + LB_NPT): its carried dy / dz live in registers
     const int c = 32 * (warp & 3) + lane;
-    const int j0 = 32 * (warp >> 2);
+    const int j0 = LB_NPT * (warp >> 2);
     const uint32_t tbase = e.tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)j0;
     const uint32_t X = e.smS, Y = e.smS + LT_S_BYTES;
     const float inv_dt = 1.0f / p.dt;
@@ -474,7 +482,7 @@ __global__ void __launch_bounds__(LF_THREADS, 1) k_lem_bwd_tc(const LemBwdParams
     auto publish_to_mma = [&]() {
       fence_proxy_async();
       tc_fence_before();
-      state_ready_arrive();
+      bwd_ready_arrive();
     };
     auto wait_bar = [&](uint64_t* bar, uint32_t& n) {
       mbar_wait_warp(bar, n & 1);
@@ -482,9 +490,9 @@ __global__ void __launch_bounds__(LF_THREADS, 1) k_lem_bwd_tc(const LemBwdParams
       tc_fence_after();
     };
 
-    float dyreg[32], dzreg[32];
+    float dyreg[LB_NPT], dzreg[LB_NPT];
 #pragma unroll
-    for (int q = 0; q < 32; ++q) {
+    for (int q = 0; q < LB_NPT; ++q) {
       dyreg[q] = __ldcg(dyc + (size_t)(j0 + q) * 128);
       dzreg[q] = __ldcg(dzc + (size_t)(j0 + q) * 128);
     }
@@ -501,7 +509,7 @@ __global__ void __launch_bounds__(LF_THREADS, 1) k_lem_bwd_tc(const LemBwdParams
       // ---- bwd_y : dL -> tile X + global, dG0 -> global + TMEM stash, dy <- d (1 - a)
       LEM_TICK(32);
 #pragma unroll
-      for (int jj = 0; jj < 32; jj += 8) {
+      for (int jj = 0; jj < LB_NPT; jj += 8) {
         float gv[8], av[8], tv[8], yv[8], g0[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
@@ -537,7 +545,7 @@ __global__ void __launch_bounds__(LF_THREADS, 1) k_lem_bwd_tc(const LemBwdParams
       LEM_TICK(34);
       // ---- bwd_z : dG1 -> tile X + global, dG2 -> tile Y + global, dz <- d (1 - b)
 #pragma unroll
-      for (int jj = 0; jj < 32; jj += 8) {
+      for (int jj = 0; jj < LB_NPT; jj += 8) {
         uint32_t r1[8];
         tmem_ld8_nowait(tbase + LB_ACC1 + jj, r1);
         float gv[8], bv[8], zcv[8], zpv[8];
@@ -577,9 +585,9 @@ __global__ void __launch_bounds__(LF_THREADS, 1) k_lem_bwd_tc(const LemBwdParams
         const float* y_n = p.Y + (size_t)(t - 1) * plane + (size_t)(row0 + j0) * 128;
         const float* z_n = p.Z + (size_t)(t - 1) * plane + (size_t)(row0 + j0) * 128;
         const int part = warp & 3;      // the four warps of a node half share the work
-        for (int q = lane + 32 * part; q < 32 * 16; q += 128)
+        for (int q = lane + 32 * part; q < LB_NPT * 16; q += 128)
           asm volatile("prefetch.global.L2 [%0];" ::"l"(g_n + (size_t)(q >> 4) * 512 + 32 * (q & 15)));
-        for (int q = lane + 32 * part; q < 32 * 4; q += 128) {
+        for (int q = lane + 32 * part; q < LB_NPT * 4; q += 128) {
           const int j = q >> 2;
           if (row0 + j0 + j < p.N) {
             asm volatile("prefetch.global.L2 [%0];" ::"l"(y_n + (size_t)j * 128 + 32 * (q & 3)));
@@ -591,7 +599,7 @@ __global__ void __launch_bounds__(LF_THREADS, 1) k_lem_bwd_tc(const LemBwdParams
       wait_bar(acc_mid, nmid);
       LEM_TICK(36);
 #pragma unroll
-      for (int jj = 0; jj < 32; jj += 8) {
+      for (int jj = 0; jj < LB_NPT; jj += 8) {
         uint32_t r0[8];
         tmem_ld8_nowait(tbase + LB_S0 + jj, r0);
         tmem_ld_wait();
@@ -604,7 +612,7 @@ __global__ void __launch_bounds__(LF_THREADS, 1) k_lem_bwd_tc(const LemBwdParams
       LEM_TICK(38);
       // ---- dy += acc2
 #pragma unroll
-      for (int jj = 0; jj < 32; jj += 8) {
+      for (int jj = 0; jj < LB_NPT; jj += 8) {
         uint32_t r2[8];
         tmem_ld8_nowait(tbase + LB_ACC2 + jj, r2);
         tmem_ld_wait();
@@ -615,7 +623,7 @@ __global__ void __launch_bounds__(LF_THREADS, 1) k_lem_bwd_tc(const LemBwdParams
       LEM_TICK(39);
     }
 #pragma unroll
-    for (int q = 0; q < 32; ++q) {
+    for (int q = 0; q < LB_NPT; ++q) {
       dyc[(size_t)(j0 + q) * 128] = dyreg[q];
       dzc[(size_t)(j0 + q) * 128] = dzreg[q];
     }
@@ -665,7 +673,7 @@ extern "C" int msmp_lem_tc_bwd(const float* Wzh_img, const float* Wh_img, const 
       return MSMP_ERR_CUDA;
     attr_set = true;
   }
-  k_lem_bwd_tc<<<Npad / LT_NODES, LF_THREADS, LT_SMEM, stream>>>(p);
+  k_lem_bwd_tc<<<Npad / LT_NODES, LB_THREADS, LT_SMEM, stream>>>(p);
   MSMP_CHECK_LAUNCH();
   return MSMP_OK;
 }
