@@ -122,6 +122,19 @@ int msmp_edge_tc_bwd(const float* P, const float* Q, int ldpq, const int* src, c
                      float* dz2, float* a1, float* dz1, float* dP, int lddp, int E, int N, void* workspace,
                      size_t ws_bytes, cudaStream_t stream);
 
+/* Warp-specialised tensor-core variants (edge_ws.cu): gather / MMA / epilogue roles overlap across 128-edge tiles and
+ * the weight matrix is resident in tensor memory.  W is read as fp32 with explicit strides: the A operand of
+ * D^T[m][edge] is A[m][k] = W[m * w_rs + k * w_cs]  (forward: A = W2[n][k], i.e. the message_net_2.0.weight parameter
+ * itself with w_rs = 128, w_cs = 1, models_gnn.py:52-54; backward: A = W2^T, the same parameter with w_rs = 1,
+ * w_cs = 128).  inv_deg_e[e] = inv_deg[dst[e]].  Same outputs, workspace and carry rules as the _tc_ entry points. */
+int msmp_edge_ws_fwd(const float* P, const float* Q, int ldpq, const int* src, const int* dst, const int* rowptr,
+                     const float* inv_deg, const float* W, int w_rs, int w_cs, const float* b2, float* z2, float* agg,
+                     int E, int N, void* workspace, size_t ws_bytes, cudaStream_t stream);
+int msmp_edge_ws_bwd(const float* P, const float* Q, int ldpq, const int* src, const int* dst, const int* rowptr,
+                     const float* inv_deg_e, const float* W, int w_rs, int w_cs, const float* z2, const float* dagg,
+                     int lddagg, float* dz2, float* a1, float* dz1, float* dP, int lddp, int E, int N, void* workspace,
+                     size_t ws_bytes, cudaStream_t stream);
+
 /* out[n, 0:128] = scale[n] * sum_{k in [ptr[n], ptr[n+1])} src[perm ? perm[k] : k, 0:128]
  * (scale == NULL -> sum; scale = 1/max(count,1) -> mean).  One warp per segment, fixed order, no atomics. */
 int msmp_segment_reduce(const float* src, int lds, const int* perm, const int* ptr, const float* scale,

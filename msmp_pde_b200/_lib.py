@@ -11,7 +11,8 @@ import re
 from ctypes import c_float, c_int, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libmsmp_b200.so")
+# MSMP_B200_LIB: A/B runs of another build of the same C ABI (scripts/), never a different implementation
+LIB_PATH = os.environ.get("MSMP_B200_LIB") or os.path.join(_HERE, "csrc", "libmsmp_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "msmp_b200.h")
 
 
@@ -55,6 +56,8 @@ _SIGS = {
     "msmp_edge_bwd": (I, [P, P, I, P, P, P, P, P, P, P, I, P, P, I, P, P, I, I, P, S, P]),
     "msmp_edge_tc_fwd": (I, [P, P, I, P, P, P, P, P, P, P, P, I, I, P, S, P]),
     "msmp_edge_tc_bwd": (I, [P, P, I, P, P, P, P, P, P, P, I, P, P, P, P, I, I, I, P, S, P]),
+    "msmp_edge_ws_fwd": (I, [P, P, I, P, P, P, P, P, I, I, P, P, P, I, I, P, S, P]),
+    "msmp_edge_ws_bwd": (I, [P, P, I, P, P, P, P, P, I, I, P, P, I, P, P, P, P, I, I, I, P, S, P]),
     "msmp_segment_reduce": (I, [P, I, P, P, P, P, I, I, P]),
     "msmp_instnorm_workspace": (S, [I, I]),
     "msmp_instnorm_fwd": (I, [P, P, I, P, P, P, P, P, I, I, I, I, F, P, P, P, S, P]),

@@ -28,6 +28,7 @@ class Topology:
     dst: torch.Tensor            # int32 [E]
     rowptr: torch.Tensor         # int32 [N+1] CSR offsets by destination
     inv_deg: torch.Tensor        # fp32  [N]   1 / max(in-degree, 1)
+    inv_deg_e: torch.Tensor      # fp32  [E]   inv_deg[dst[e]] (streamed by the backward edge kernel)
     colptr: torch.Tensor         # int32 [N+1] CSC offsets by source
     csc_perm: torch.Tensor       # int32 [E]   CSR edge ids sorted (stably) by source
     csr_perm: torch.Tensor | None  # int64 [E] original edge id of CSR edge e (None if already sorted)
@@ -76,6 +77,7 @@ def build_topology(edge_index: torch.Tensor, batch: torch.Tensor, num_nodes: int
     ce = torch.minimum(cb + CHUNK_ROWS, gptr[chunk_graph + 1])
     i32 = lambda t: t.to(torch.int32).contiguous()
     return Topology(N=N, E=E, B=B, src=i32(src64), dst=i32(dst64), rowptr=i32(rowptr), inv_deg=inv_deg.contiguous(),
+                    inv_deg_e=inv_deg[dst64].contiguous(),
                     colptr=i32(colptr), csc_perm=i32(csc_perm), csr_perm=csr_perm, node_graph=i32(batch),
                     chunk_begin=i32(cb), chunk_end=i32(ce), graph_chunk_ptr=i32(gcp))
 

@@ -116,7 +116,7 @@ class _LayerCoreFn(torch.autograd.Function):
         V = ft.V
         h = h.contiguous()
         PQ = ops.linear_fwd([h, ft.upad], pk.Wpq_t, bias=pk.bias_pq, side=ft.side, r=1 + V, Wside=pk.Wpq_side)
-        agg, z2 = ops.edge_fwd(PQ[:, :H], PQ[:, H:], topo, pk.W2t, b2)
+        agg, z2 = ops.edge_fwd(PQ[:, :H], PQ[:, H:], topo, pk.W2t, b2, W2raw=W2)
         z3 = ops.linear_fwd([h, agg], pk.W3t, bias=b3, side=ft.side[:, 1:], r=V, Wside=pk.W3side)
         if aux.final:       # GNN_Layer: y = h + swish(z4)
             z4 = torch.empty_like(h)
@@ -172,12 +172,13 @@ class _LayerCoreFn(torch.autograd.Function):
         # message path
         dPQ = torch.empty(N, 2 * H, dtype=torch.float32, device=dev)
         if tc and topo.E > 0:
-            dz1, a1, dz2 = ops.edge_bwd(PQ[:, :H], PQ[:, H:], topo, pk.W2d, z2, dcat[:, H:], dPQ[:, :H], defer_wgrad=True)
+            dz1, a1, dz2 = ops.edge_bwd(PQ[:, :H], PQ[:, H:], topo, pk.W2d, z2, dcat[:, H:], dPQ[:, :H], defer_wgrad=True,
+                                        W2raw=W2)
             dW2t_, db2s = on_side(lambda: ops.linear_wgrad(a1, dz2, has_bias=True, dWt=raw("dW2t"), dWside=raw("db2s")),
                                   a1, dz2)
             dW2, db2 = dW2t_.t(), db2s[0]
         else:
-            dz1, dW2, db2 = ops.edge_bwd(PQ[:, :H], PQ[:, H:], topo, pk.W2d, z2, dcat[:, H:], dPQ[:, :H])
+            dz1, dW2, db2 = ops.edge_bwd(PQ[:, :H], PQ[:, H:], topo, pk.W2d, z2, dcat[:, H:], dPQ[:, :H], W2raw=W2)
         ops.segment_reduce(dz1, topo.colptr, perm=topo.csc_perm, out=dPQ[:, H:], N=N)
         Kp = H + ft.upad.shape[1]
         dWpq_t = raw("dWpq_t") if gs is not None else torch.empty(Kp, 2 * H, dtype=torch.float32, device=dev)

@@ -6,6 +6,7 @@ device pointers to ``libmsmp_b200.so``.  CPU tensors are rejected: there is no f
 from __future__ import annotations
 
 import ctypes
+import os
 
 import torch
 
@@ -82,6 +83,8 @@ def _p(t):
 GEMM_MODE = "tc"
 # Persistent (all-T-steps-in-one-launch) LEM kernels; False = one GEMM + one gate kernel per step.
 LEM_PERSISTENT = True
+# tensor-core edge kernels: warp-specialised, weights in tensor memory (edge_ws.cu) | single-role (edge_tc.cu)
+EDGE_WS = os.environ.get("MSMP_EDGE_WS", "1") != "0"
 # The persistent backward recurrence can be cut into several launches so that the weight-gradient GEMMs of finished
 # steps overlap the remaining ones on a side stream (lem._LEMFn.backward).  Measured on the C2 workload after the
 # recurrence kernel got its own MMA warp and 16 epilogue warps: 1 launch 4.11 ms/step, 2: 4.16, 3: 4.19, 5: 4.28,
@@ -236,13 +239,40 @@ def linear_wgrad(X, dY, K=None, xswish=False, side=None, r=0, has_bias=False, dW
     return dWt, dWside
 
 
-def edge_fwd(P, Q, topo, W2t, b2, save_z2=True):
+def _ws_operand(W2raw, Wk, what):
+    """(tensor, row stride, column stride) of the warp-specialised edge kernels' A operand [m][k]."""
+    if W2raw is not None:                 # the parameter W2[n][k] itself
+        _req(W2raw, "W2")
+        if tuple(W2raw.shape) != (H, H) or W2raw.stride(0) != H:
+            raise ValueError("W2: expected a contiguous [128, 128] tensor")
+        return (W2raw, H, 1) if what == "fwd" else (W2raw, 1, H)
+    if isinstance(Wk, TcW):
+        return None
+    _req(Wk, "W2")
+    if tuple(Wk.shape) != (H, H) or Wk.stride(0) != H:
+        raise ValueError("W2: expected a contiguous [128, 128] tensor")
+    return (Wk, 1, H)                     # fwd: W2t[k][n] read as A[n][k];  bwd: W2[n][k] read as A[k][n]
+
+
+def edge_fwd(P, Q, topo, W2t, b2, save_z2=True, W2raw=None):
+    """W2t: k-major W2^T (tensor or packed images).  W2raw: the [n][k] parameter itself; with it (or a plain W2t) the
+    tensor-core mode runs the warp-specialised kernel, which keeps the weights in tensor memory."""
     _req(P, "P")
     _req(Q, "Q")
     dev = P.device
     agg = torch.empty(topo.N, H, dtype=torch.float32, device=dev)
     z2 = torch.empty(topo.E, H, dtype=torch.float32, device=dev) if save_z2 else None
     ws = _workspace(lib.msmp_edge_fwd_workspace(topo.E), dev)
+    wsop = _ws_operand(W2raw, W2t, "fwd") if (EDGE_WS and (GEMM_MODE == "tc" or isinstance(W2t, TcW))) else None
+    if wsop is not None:
+        Wa, rs, cs = wsop
+        with _timed("edge_ws_fwd", 2.0 * topo.E * H * H, 4.0 * H * (3 * topo.E + topo.N)):
+            check(lib.msmp_edge_ws_fwd(P.data_ptr(), Q.data_ptr(), _ld(P), topo.src.data_ptr(), topo.dst.data_ptr(),
+                                       topo.rowptr.data_ptr(), topo.inv_deg.data_ptr(), Wa.data_ptr(), rs, cs,
+                                       b2.data_ptr(), _p(z2), agg.data_ptr(), topo.E, topo.N, ws.data_ptr(), ws.numel(),
+                                       _stream()), "msmp_edge_ws_fwd")
+        _count(2)
+        return agg, z2
     if GEMM_MODE == "tc" or isinstance(W2t, TcW):
         img = W2t.img if isinstance(W2t, TcW) else _cached_images(W2t)
         with _timed("edge_tc_fwd", 2.0 * topo.E * H * H, 4.0 * H * (3 * topo.E + topo.N)):
@@ -261,7 +291,7 @@ def edge_fwd(P, Q, topo, W2t, b2, save_z2=True):
     return agg, z2
 
 
-def edge_bwd(P, Q, topo, W2, z2, dagg, dP, defer_wgrad=False):
+def edge_bwd(P, Q, topo, W2, z2, dagg, dP, defer_wgrad=False, W2raw=None):
     """Returns dz1 [E,128], dW2 [128,128] ([n][k] = parameter layout), db2 [128]; writes dP in place.
     defer_wgrad (tensor-core path): returns (dz1, a1, dz2) instead; the caller runs
     ``linear_wgrad(a1, dz2, has_bias=True)`` itself (e.g. on a side stream)."""
@@ -270,14 +300,24 @@ def edge_bwd(P, Q, topo, W2, z2, dagg, dP, defer_wgrad=False):
     if GEMM_MODE == "tc" or isinstance(W2, TcW):
         dz2 = torch.empty(topo.E, H, dtype=torch.float32, device=dev)
         a1 = torch.empty(topo.E, H, dtype=torch.float32, device=dev)
-        img = W2.img if isinstance(W2, TcW) else _cached_images(W2)
         ws = _workspace(lib.msmp_edge_fwd_workspace(topo.E), dev)
-        with _timed("edge_tc_bwd", 2.0 * topo.E * H * H, 4.0 * H * (6 * topo.E + topo.N)):
-            check(lib.msmp_edge_tc_bwd(P.data_ptr(), Q.data_ptr(), _ld(P), topo.src.data_ptr(), topo.dst.data_ptr(),
-                                       topo.rowptr.data_ptr(), topo.inv_deg.data_ptr(), img.data_ptr(), z2.data_ptr(),
-                                       dagg.data_ptr(), _ld(dagg), dz2.data_ptr(), a1.data_ptr(), dz1.data_ptr(),
-                                       dP.data_ptr(), _ld(dP), topo.E, topo.N, ws.data_ptr(), ws.numel(), _stream()),
-                  "msmp_edge_tc_bwd")
+        wsop = _ws_operand(W2raw, W2, "bwd") if EDGE_WS else None
+        if wsop is not None:
+            Wa, rs, cs = wsop
+            with _timed("edge_ws_bwd", 2.0 * topo.E * H * H, 4.0 * H * (7 * topo.E + topo.N)):
+                check(lib.msmp_edge_ws_bwd(P.data_ptr(), Q.data_ptr(), _ld(P), topo.src.data_ptr(), topo.dst.data_ptr(),
+                                           topo.rowptr.data_ptr(), topo.inv_deg_e.data_ptr(), Wa.data_ptr(), rs, cs,
+                                           z2.data_ptr(), dagg.data_ptr(), _ld(dagg), dz2.data_ptr(), a1.data_ptr(),
+                                           dz1.data_ptr(), dP.data_ptr(), _ld(dP), topo.E, topo.N, ws.data_ptr(),
+                                           ws.numel(), _stream()), "msmp_edge_ws_bwd")
+        else:
+            img = W2.img if isinstance(W2, TcW) else _cached_images(W2)
+            with _timed("edge_tc_bwd", 2.0 * topo.E * H * H, 4.0 * H * (6 * topo.E + topo.N)):
+                check(lib.msmp_edge_tc_bwd(P.data_ptr(), Q.data_ptr(), _ld(P), topo.src.data_ptr(), topo.dst.data_ptr(),
+                                           topo.rowptr.data_ptr(), topo.inv_deg.data_ptr(), img.data_ptr(), z2.data_ptr(),
+                                           dagg.data_ptr(), _ld(dagg), dz2.data_ptr(), a1.data_ptr(), dz1.data_ptr(),
+                                           dP.data_ptr(), _ld(dP), topo.E, topo.N, ws.data_ptr(), ws.numel(),
+                                           _stream()), "msmp_edge_tc_bwd")
         _count(2)
         if defer_wgrad:
             return dz1, a1, dz2
