@@ -126,7 +126,9 @@ int msmp_edge_tc_bwd(const float* P, const float* Q, int ldpq, const int* src, c
  * the weight matrix is resident in tensor memory.  W is read as fp32 with explicit strides: the A operand of
  * D^T[m][edge] is A[m][k] = W[m * w_rs + k * w_cs]  (forward: A = W2[n][k], i.e. the message_net_2.0.weight parameter
  * itself with w_rs = 128, w_cs = 1, models_gnn.py:52-54; backward: A = W2^T, the same parameter with w_rs = 1,
- * w_cs = 128).  inv_deg_e[e] = inv_deg[dst[e]].  Same outputs, workspace and carry rules as the _tc_ entry points. */
+ * w_cs = 128).  inv_deg_e[e] = inv_deg[dst[e]].  Same outputs and carry rules as the _tc_ entry points;
+ * workspace: msmp_edge_ws_workspace(E). */
+size_t msmp_edge_ws_workspace(int E);
 int msmp_edge_ws_fwd(const float* P, const float* Q, int ldpq, const int* src, const int* dst, const int* rowptr,
                      const float* inv_deg, const float* W, int w_rs, int w_cs, const float* b2, float* z2, float* agg,
                      int E, int N, void* workspace, size_t ws_bytes, cudaStream_t stream);

@@ -56,6 +56,7 @@ _SIGS = {
     "msmp_edge_bwd": (I, [P, P, I, P, P, P, P, P, P, P, I, P, P, I, P, P, I, I, P, S, P]),
     "msmp_edge_tc_fwd": (I, [P, P, I, P, P, P, P, P, P, P, P, I, I, P, S, P]),
     "msmp_edge_tc_bwd": (I, [P, P, I, P, P, P, P, P, P, P, I, P, P, P, P, I, I, I, P, S, P]),
+    "msmp_edge_ws_workspace": (S, [I]),
     "msmp_edge_ws_fwd": (I, [P, P, I, P, P, P, P, P, I, I, P, P, P, I, I, P, S, P]),
     "msmp_edge_ws_bwd": (I, [P, P, I, P, P, P, P, P, I, I, P, P, I, P, P, P, P, I, I, I, P, S, P]),
     "msmp_segment_reduce": (I, [P, I, P, P, P, P, I, I, P]),

@@ -27,10 +27,18 @@ namespace msmp {
 constexpr int EW_TILE = 128;
 constexpr int EW_STAGES = 3;
 constexpr int EW_STAGE_BYTES = 2 * IMG_BYTES;          // hi | lo image of one [128 edges x 32 columns] chunk
-constexpr int EW_EPI_WARPS = 4, EW_PROD_WARPS = 8;
-constexpr int EW_PROD_T0 = 32 * (EW_EPI_WARPS + 1);    // first producer thread
+constexpr int EW_EH = 2;                               // epilogue warps per TMEM lane quadrant
+constexpr int EW_UNIT = EW_TILE / EW_EH;               // edges walked by one epilogue thread = carry granularity
+constexpr int EW_EPI_WARPS = 4 * EW_EH, EW_PROD_WARPS = 8;
+constexpr int EW_PROD_T0 = 32 * EW_EPI_WARPS;          // first producer thread
 constexpr int EW_PROD_THREADS = 32 * EW_PROD_WARPS;
-constexpr int EW_THREADS = EW_PROD_T0 + EW_PROD_THREADS;
+constexpr int EW_MMA_WARP = EW_EPI_WARPS + EW_PROD_WARPS;
+// Warps 0..7 epilogue, 8..15 producers, 16 MMA issue (17..19 only fill its warpgroup).  640 threads start with 96
+// registers each; the MMA warpgroup hands registers to the producers with setmaxnreg (40 / 120), whose two float4
+// register sets would otherwise spill.
+constexpr int EW_THREADS = 32 * (EW_MMA_WARP + 4);
+template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 constexpr int EW_SLOTS = 8;                            // index ring (tiles): a slot is rewritten 7 tiles later, when the
                                                        // epilogue that read it has long finished
 constexpr int EW_DST_LD = 132;                         // dst[-1 .. 128] of a tile (+ padding)
@@ -50,7 +58,7 @@ struct EdgeWsParams {
   const float* dagg; int lddagg;    // bwd
   float* dz2; float* a1; float* dz1;      // bwd outs [E][128]
   float* out; int ldo;              // fwd: agg [N][128] (mean);  bwd: dP [N][ldo] (sum)
-  float* carry;                     // [T][2][128]
+  float* carry;                     // [T * EW_EH][2][128], per unit of EW_UNIT edges
   int E; int T;
 };
 
@@ -103,7 +111,7 @@ __global__ void __launch_bounds__(EW_THREADS, 1) k_edge_ws(const EdgeWsParams p)
   const int tb = (int)((long long)blockIdx.x * p.T / gridDim.x);
   const int ntile = (int)((long long)(blockIdx.x + 1) * p.T / gridDim.x) - tb;
 
-  if (warp == EW_EPI_WARPS) tmem_alloc(tmem_slot, 512);
+  if (warp == EW_MMA_WARP) tmem_alloc(tmem_slot, 512);
   if (tid == 0) {
     for (int i = 0; i < EW_STAGES; ++i) {
       mbar_init(&full[i], EW_PROD_WARPS);
@@ -125,11 +133,12 @@ __global__ void __launch_bounds__(EW_THREADS, 1) k_edge_ws(const EdgeWsParams p)
 
   if (warp < EW_EPI_WARPS) {
     // =========================================================================== epilogue warps
-    const int ch = 32 * warp + lane;
-    const uint32_t lane_off = (uint32_t)(32 * warp) << 16;
-    // ---- weights -> tensor memory (row ch of the A operand, tf32 hi | lo)
+    const int ch = 32 * (warp & 3) + lane;
+    const int uh = warp >> 2;                                  // which EW_UNIT-edge part of every tile
+    const uint32_t lane_off = (uint32_t)(32 * (warp & 3)) << 16;
+    // ---- weights -> tensor memory (row ch of the A operand, tf32 hi | lo); the warps of a quadrant share the columns
 #pragma unroll 1
-    for (int kb = 0; kb < 128; kb += 32) {
+    for (int kb = 32 * uh; kb < 128; kb += 32 * EW_EH) {
       float w[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) w[j] = __ldg(p.W + (size_t)ch * p.w_rs + (size_t)(kb + j) * p.w_cs);
@@ -147,8 +156,8 @@ __global__ void __launch_bounds__(EW_THREADS, 1) k_edge_ws(const EdgeWsParams p)
     __syncwarp();
     if (lane == 0) mbar_arrive(w_full);
     const float bias = BWD ? 0.f : __ldg(p.b2 + ch);
-    s_inv[ch + 1] = 1.0f / (float)(ch + 1);
-    asm volatile("bar.sync 2, 128;" ::: "memory");
+    if (uh == 0) s_inv[ch + 1] = 1.0f / (float)(ch + 1);
+    asm volatile("bar.sync 2, %0;" ::"n"(32 * EW_EPI_WARPS) : "memory");
     EW_TICK_DECL(t_acc); EW_TICK_DECL(t_s); EW_TICK_DECL(t_all);
 #ifdef MSMP_EW_TICKS
     const long long t_begin = clock64();
@@ -167,27 +176,30 @@ __global__ void __launch_bounds__(EW_THREADS, 1) k_edge_ws(const EdgeWsParams p)
       // Destination-segment sums: running sums in registers.  The segment boundaries are warp-uniform bit masks
       // (ballots over the tile's destination indices incl. the two neighbouring edges), the element-wise math of a
       // 32-edge block is branch-free (32 independent chains in flight), and only a segment's last edge branches.
+      const int u0 = EW_UNIT * uh;                     // this warp's unit = tile rows [u0, min(u0 + EW_UNIT, valid))
+      const int uvalid = min(u0 + EW_UNIT, valid);
+      const int unit = tile * EW_EH + uh;
       float sum = 0.f;
-      int seg0 = 0;
-      bool left = sd[-1] != sd[0];          // does the tile's first segment start here?
+      int seg0 = u0;
+      bool left = sd[u0 - 1] != sd[u0];          // does the unit's first segment start here?
 #pragma unroll 1
-      for (int cb = 0; cb < 4; ++cb) {
+      for (int cb = 0; cb < 4 / EW_EH; ++cb) {
         float v[32];
         __syncwarp();
-        tmem_ld32(tmem + lane_off + EW_ACC + (uint32_t)(128 * buf + 32 * cb), v);
-        if (cb == 3) {          // accumulator drained: the MMA warp may start the tile after next
+        tmem_ld32(tmem + lane_off + EW_ACC + (uint32_t)(128 * buf + u0 + 32 * cb), v);
+        if (cb == 4 / EW_EH - 1) {          // accumulator drained: the MMA warp may start the tile after next
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&acc_empty[buf]);
         }
-        const int eb = 32 * cb;
+        const int eb = u0 + 32 * cb;
         const int nb = min(32, valid - eb);          // live edges of this block
         if (nb <= 0) continue;
         const int dj = sd[eb + lane];
         const uint32_t live = nb >= 32 ? 0xffffffffu : ((1u << nb) - 1u);
         const uint32_t smask = __ballot_sync(0xffffffffu, dj != sd[eb + lane - 1]) & live;      // first edge of a segment
         const uint32_t emask = __ballot_sync(0xffffffffu, dj != sd[eb + lane + 1]) & live;      // last edge of a segment
-        const uint32_t fmask = emask | (eb + nb == valid ? (1u << (nb - 1)) : 0u);              // + the tile's last edge
+        const uint32_t fmask = emask | (eb + nb == uvalid ? (1u << (nb - 1)) : 0u);             // + the unit's last edge
         if (!BWD) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] += bias;
@@ -214,7 +226,7 @@ __global__ void __launch_bounds__(EW_THREADS, 1) k_edge_ws(const EdgeWsParams p)
           sum = st ? v[j] : sum + v[j];
           seg0 = st ? eb + j : seg0;
           if ((fmask >> j) & 1u) {
-            // Segment rows [seg0, e] of node sd[e].  It lies inside the tile iff it started here (left) and ends
+            // Segment rows [seg0, e] of node sd[e].  It lies inside the unit iff it started here (left) and ends
             // here (right); its in-degree is then e + 1 - seg0, and s_inv[] holds the same IEEE 1.0f / deg that
             // built inv_deg.  Otherwise the partial sum goes to the carry buffer (slot 1: starts here, continues).
             const int e = eb + j;
@@ -222,7 +234,7 @@ __global__ void __launch_bounds__(EW_THREADS, 1) k_edge_ws(const EdgeWsParams p)
             if (left && right) {
               p.out[(size_t)sd[e] * p.ldo + ch] = BWD ? sum : sum * s_inv[e + 1 - seg0];
             } else {
-              p.carry[((size_t)tile * 2 + (left ? 1 : 0)) * 128 + ch] = sum;
+              p.carry[((size_t)unit * 2 + (left ? 1 : 0)) * 128 + ch] = sum;
             }
             left = true;
           }
@@ -238,8 +250,10 @@ __global__ void __launch_bounds__(EW_THREADS, 1) k_edge_ws(const EdgeWsParams p)
     if (blockIdx.x == 0 && tid == 0)
       printf("edge_ws<%d> epilogue: tiles %d total %lld wait_acc %lld wait_s %lld\n", (int)BWD, ntile, t_all, t_acc, t_s);
 #endif
-  } else if (warp == EW_EPI_WARPS) {
-    // =========================================================================== MMA warp
+  } else if (warp >= EW_MMA_WARP) {
+    // =========================================================================== MMA warp (+ 3 idle warps)
+    reg_dec<40>();
+    if (warp == EW_MMA_WARP) {
     constexpr uint32_t IDESC = umma_idesc_tf32(128, 128, 0, 0);
     mbar_wait_warp(w_full, 0);
     tc_fence_after();
@@ -286,8 +300,10 @@ __global__ void __launch_bounds__(EW_THREADS, 1) k_edge_ws(const EdgeWsParams p)
     if (blockIdx.x == 0 && lane == 0)
       printf("edge_ws<%d> mma: total %lld wait_full %lld wait_acc_empty %lld\n", (int)BWD, clock64() - t_begin, t_full, t_ae);
 #endif
+    }
   } else {
     // =========================================================================== producer warps
+    reg_inc<120>();
     const int pt = tid - EW_PROD_T0;
     // ---- index ring: (src, dst, scale) of a tile's 128 rows + the two neighbouring destinations
     auto idx_issue = [&](int i, int& rs, int& rd, float& rsc) {
@@ -434,7 +450,7 @@ __global__ void __launch_bounds__(EW_THREADS, 1) k_edge_ws(const EdgeWsParams p)
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == EW_EPI_WARPS) tmem_dealloc(tmem, 512);
+  if (warp == EW_MMA_WARP) tmem_dealloc(tmem, 512);
 }
 
 // ordered fix-up of segments cut by tile boundaries: the tile where a segment starts owns it
@@ -444,13 +460,14 @@ __global__ void k_carry_fix_ws(const float* __restrict__ carry, const int* __res
   const int lane = threadIdx.x & 31;
   const int tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (tile >= T) return;
-  const int e0 = tile * EW_TILE;
-  const int e_last = min(E, e0 + EW_TILE) - 1;
+  const int e0 = tile * EW_UNIT;            // ("tile" = unit of EW_UNIT edges here, T = number of units)
+  if (e0 >= E) return;
+  const int e_last = min(E, e0 + EW_UNIT) - 1;
   const int node = dst[e_last];
   const int seg_begin = rowptr[node], seg_end = rowptr[node + 1];
   if (seg_end <= e_last + 1 || seg_begin < e0) return;
   float4 sum = ldcg4(carry + ((size_t)tile * 2 + 1) * 128 + 4 * lane);
-  for (int t = tile + 1; t < T && t * EW_TILE < seg_end; ++t)
+  for (int t = tile + 1; t < T && t * EW_UNIT < seg_end; ++t)
     sum = add4(sum, ldcg4(carry + ((size_t)t * 2 + 0) * 128 + 4 * lane));
   const float sc = scale ? scale[node] : 1.0f;
   st4(out + (size_t)node * ldo + 4 * lane, scale4(sum, sc));
@@ -481,6 +498,8 @@ static int launch_edge_ws(const EdgeWsParams& p, cudaStream_t stream) {
 
 using namespace msmp;
 
+extern "C" size_t msmp_edge_ws_workspace(int E) { return (size_t)msmp_edge_tiles(E) * EW_EH * 2 * 128 * sizeof(float); }
+
 extern "C" int msmp_edge_ws_fwd(const float* P, const float* Q, int ldpq, const int* src, const int* dst,
                                 const int* rowptr, const float* inv_deg, const float* W, int w_rs, int w_cs,
                                 const float* b2, float* z2, float* agg, int E, int N, void* workspace, size_t ws_bytes,
@@ -488,14 +507,14 @@ extern "C" int msmp_edge_ws_fwd(const float* P, const float* Q, int ldpq, const 
   if (E < 0 || N < 0 || (ldpq & 3)) return MSMP_ERR_ARG;
   if (cudaMemsetAsync(agg, 0, (size_t)N * 128 * sizeof(float), stream) != cudaSuccess) return MSMP_ERR_CUDA;
   if (E == 0) return MSMP_OK;
-  if (ws_bytes < msmp_edge_fwd_workspace(E)) return MSMP_ERR_WORKSPACE;
+  if (ws_bytes < msmp_edge_ws_workspace(E)) return MSMP_ERR_WORKSPACE;
   EdgeWsParams p{};
   p.P = P; p.Q = Q; p.ldpq = ldpq; p.src = src; p.dst = dst; p.W = W; p.w_rs = w_rs; p.w_cs = w_cs;
   p.b2 = b2; p.z2 = z2; p.out = agg; p.ldo = 128;
   p.carry = reinterpret_cast<float*>(workspace); p.E = E; p.T = msmp_edge_tiles(E);
   int rc = launch_edge_ws<false>(p, stream);
   if (rc) return rc;
-  k_carry_fix_ws<<<(p.T + 7) / 8, 256, 0, stream>>>(p.carry, dst, rowptr, inv_deg, agg, 128, E, p.T);
+  k_carry_fix_ws<<<(p.T * EW_EH + 7) / 8, 256, 0, stream>>>(p.carry, dst, rowptr, inv_deg, agg, 128, E, p.T * EW_EH);
   MSMP_CHECK_LAUNCH();
   return MSMP_OK;
 }
@@ -509,7 +528,7 @@ extern "C" int msmp_edge_ws_bwd(const float* P, const float* Q, int ldpq, const 
   if (cudaMemset2DAsync(dP, (size_t)lddp * sizeof(float), 0, 128 * sizeof(float), N, stream) != cudaSuccess)
     return MSMP_ERR_CUDA;
   if (E == 0) return MSMP_OK;
-  if (ws_bytes < msmp_edge_fwd_workspace(E)) return MSMP_ERR_WORKSPACE;
+  if (ws_bytes < msmp_edge_ws_workspace(E)) return MSMP_ERR_WORKSPACE;
   EdgeWsParams p{};
   p.P = P; p.Q = Q; p.ldpq = ldpq; p.src = src; p.dst = dst; p.inv_deg_e = inv_deg_e;
   p.W = W; p.w_rs = w_rs; p.w_cs = w_cs; p.z2 = const_cast<float*>(z2); p.dagg = dagg; p.lddagg = lddagg;
@@ -517,7 +536,7 @@ extern "C" int msmp_edge_ws_bwd(const float* P, const float* Q, int ldpq, const 
   p.carry = reinterpret_cast<float*>(workspace); p.E = E; p.T = msmp_edge_tiles(E);
   int rc = launch_edge_ws<true>(p, stream);
   if (rc) return rc;
-  k_carry_fix_ws<<<(p.T + 7) / 8, 256, 0, stream>>>(p.carry, dst, rowptr, nullptr, dP, lddp, E, p.T);
+  k_carry_fix_ws<<<(p.T * EW_EH + 7) / 8, 256, 0, stream>>>(p.carry, dst, rowptr, nullptr, dP, lddp, E, p.T * EW_EH);
   MSMP_CHECK_LAUNCH();
   return MSMP_OK;
 }

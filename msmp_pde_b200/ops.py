@@ -85,6 +85,12 @@ GEMM_MODE = "tc"
 LEM_PERSISTENT = True
 # tensor-core edge kernels: warp-specialised, weights in tensor memory (edge_ws.cu) | single-role (edge_tc.cu)
 EDGE_WS = os.environ.get("MSMP_EDGE_WS", "1") != "0"
+# ... from this many 128-edge tiles on (four per SM).  Measured on B200 (scripts/edge_sweep.py, op alone, cold L2): the
+# pipelined forward is faster at every size, the backward from about five tiles per SM; inside the captured C2 step
+# (two tiles per SM, gate || main layers on two streams) the single-role kernels are 1-3 % faster: they hold 128
+# tensor-memory columns instead of all 512, so the other stream's kernels can share the SM.
+EDGE_WS_MIN_TILES_FWD = int(os.environ.get("MSMP_EDGE_WS_MIN_TILES_FWD", "592"))
+EDGE_WS_MIN_TILES_BWD = int(os.environ.get("MSMP_EDGE_WS_MIN_TILES_BWD", "592"))
 # The persistent backward recurrence can be cut into several launches so that the weight-gradient GEMMs of finished
 # steps overlap the remaining ones on a side stream (lem._LEMFn.backward).  Measured on the C2 workload after the
 # recurrence kernel got its own MMA warp and 16 epilogue warps: 1 launch 4.11 ms/step, 2: 4.16, 3: 4.19, 5: 4.28,
@@ -263,9 +269,11 @@ def edge_fwd(P, Q, topo, W2t, b2, save_z2=True, W2raw=None):
     agg = torch.empty(topo.N, H, dtype=torch.float32, device=dev)
     z2 = torch.empty(topo.E, H, dtype=torch.float32, device=dev) if save_z2 else None
     ws = _workspace(lib.msmp_edge_fwd_workspace(topo.E), dev)
-    wsop = _ws_operand(W2raw, W2t, "fwd") if (EDGE_WS and (GEMM_MODE == "tc" or isinstance(W2t, TcW))) else None
+    use_ws = EDGE_WS and (GEMM_MODE == "tc" or isinstance(W2t, TcW)) and topo.E >= 128 * EDGE_WS_MIN_TILES_FWD
+    wsop = _ws_operand(W2raw, W2t, "fwd") if use_ws else None
     if wsop is not None:
         Wa, rs, cs = wsop
+        ws = _workspace(lib.msmp_edge_ws_workspace(topo.E), dev)
         with _timed("edge_ws_fwd", 2.0 * topo.E * H * H, 4.0 * H * (3 * topo.E + topo.N)):
             check(lib.msmp_edge_ws_fwd(P.data_ptr(), Q.data_ptr(), _ld(P), topo.src.data_ptr(), topo.dst.data_ptr(),
                                        topo.rowptr.data_ptr(), topo.inv_deg.data_ptr(), Wa.data_ptr(), rs, cs,
@@ -301,9 +309,10 @@ def edge_bwd(P, Q, topo, W2, z2, dagg, dP, defer_wgrad=False, W2raw=None):
         dz2 = torch.empty(topo.E, H, dtype=torch.float32, device=dev)
         a1 = torch.empty(topo.E, H, dtype=torch.float32, device=dev)
         ws = _workspace(lib.msmp_edge_fwd_workspace(topo.E), dev)
-        wsop = _ws_operand(W2raw, W2, "bwd") if EDGE_WS else None
+        wsop = _ws_operand(W2raw, W2, "bwd") if (EDGE_WS and topo.E >= 128 * EDGE_WS_MIN_TILES_BWD) else None
         if wsop is not None:
             Wa, rs, cs = wsop
+            ws = _workspace(lib.msmp_edge_ws_workspace(topo.E), dev)
             with _timed("edge_ws_bwd", 2.0 * topo.E * H * H, 4.0 * H * (7 * topo.E + topo.N)):
                 check(lib.msmp_edge_ws_bwd(P.data_ptr(), Q.data_ptr(), _ld(P), topo.src.data_ptr(), topo.dst.data_ptr(),
                                            topo.rowptr.data_ptr(), topo.inv_deg_e.data_ptr(), Wa.data_ptr(), rs, cs,
