@@ -175,6 +175,7 @@ def run_ours(args):
     launches = launches_per_step * args.steps
 
     scatter = scatter_bandwidth(dev) if rank == 0 else None
+    message = message_bandwidth(dev) if rank == 0 else None
     ms = sum(times) / len(times)
     ms_e2e = sum(e2e_times) / len(e2e_times)
     t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
@@ -215,7 +216,7 @@ def run_ours(args):
             "e2e": {"value": round(world * N / (ms_e2e * 1e-3), 1), "unit": UNIT, "ms_per_step": round(ms_e2e, 4),
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 8},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
-            "ops": table, "scatter_hbm": scatter,
+            "ops": table, "scatter_hbm": scatter, "message_hbm": message,
             "execution": ("eager launches" if args.eager else
                           "whole step captured as one CUDA graph (GraphedTrainStep)" if world == 1 else
                           "three CUDA graphs per step (forward+loss | backward | AdamW) with the NCCL all-reduces of the "
@@ -260,6 +261,50 @@ def scatter_bandwidth(dev, n_nodes=1 << 20, degree=6, reps=10):
             "contiguous_gbs": res["contiguous"]["gbs"], "contiguous_frac": round(res["contiguous"]["gbs"] / peak, 4),
             "permuted_gbs": res["permuted"]["gbs"], "permuted_frac": round(res["permuted"]["gbs"] / peak, 4),
             "peak_gbs": peak}
+
+
+def message_bandwidth(dev, n_nodes=1 << 20, degree=6, reps=5):
+    """The message kernels (fused gather + second message-MLP layer on the tensor pipe + mean aggregation, forward and
+    backward) on the config-5 shape, 1 Mi nodes x 6 Mi edges, as a fraction of the measured HBM copy peak.
+    Algorithmic bytes per edge (gathers counted without reuse): forward 2 x 512 gathered (P[dst],
+    Q[src]) + 512 written (z2) + 8 index = 1544; backward 4 x 512 read (dagg[dst], z2, P[dst], Q[src]) + 3 x 512 written
+    (dz2, a1, dz1) + 12 index/scale = 3596; plus 512 per node for the aggregated output.  'band' sources are neighbours
+    on a ring (gathers mostly hit L2), 'random' sources are uniform over the whole graph (every gather is an HBM row)."""
+    import torch
+    from msmp_pde_b200 import ops, synth
+    from msmp_pde_b200.graph import build_topology
+    gen = torch.Generator(device=dev).manual_seed(0)
+    PQ = torch.randn(n_nodes, 256, device=dev, generator=gen)
+    W2 = (torch.randn(128, 128, device=dev, generator=gen) / 11).contiguous()
+    b2 = torch.randn(128, device=dev, generator=gen) * 0.1
+    dagg = torch.randn(n_nodes, 128, device=dev, generator=gen)
+    dP = torch.empty(n_nodes, 128, device=dev)
+    peak = _peaks()["hbm_gbs"]
+    res = {"kernel": "k_edge_ws<fwd> / k_edge_ws<bwd>", "nodes": n_nodes, "edges": n_nodes * degree, "peak_gbs": peak}
+    for topo_name, npg in (("band", 100), ("random", 0)):
+        g = synth.large_graph(n_nodes, degree, topology=topo_name, nodes_per_graph=npg, seed=0)
+        topo = build_topology(g["edge_index"].to(dev), g["batch"].to(dev), n_nodes)
+        del g
+        E = topo.E
+        tf = tb = 0.0
+        for it in range(2 + reps):
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            ev[0].record()
+            agg, z2 = ops.edge_fwd(PQ[:, :128], PQ[:, 128:], topo, None, b2, W2raw=W2)
+            ev[1].record()
+            out = ops.edge_bwd(PQ[:, :128], PQ[:, 128:], topo, None, z2, dagg, dP, defer_wgrad=True, W2raw=W2)
+            ev[2].record()
+            torch.cuda.synchronize()
+            del out
+            if it >= 2:
+                tf += ev[0].elapsed_time(ev[1]) / reps
+                tb += ev[1].elapsed_time(ev[2]) / reps
+        bf, bb = E * 1544 + n_nodes * 512, E * 3596 + n_nodes * 512
+        res[topo_name] = {"fwd_ms": round(tf, 4), "fwd_gbs": round(bf / tf / 1e6, 1), "fwd_frac": round(bf / tf / 1e6 / peak, 4),
+                          "bwd_ms": round(tb, 4), "bwd_gbs": round(bb / tb / 1e6, 1), "bwd_frac": round(bb / tb / 1e6 / peak, 4),
+                          "fwd_executed_tf32_tflops": round(3 * 2 * E * 128 * 128 / tf / 1e9, 1)}
+        del topo, agg, z2
+    return res
 
 
 # ------------------------------------------------------------------------------------------ reference

@@ -75,6 +75,34 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
       "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Activations on the MUFU pipe: sigmoid(x) = rcp(1 + ex2(-x log2 e)), 5 instructions per swish instead of the 13 of
+// the expf-based common.cuh version (the two roles of this kernel are instruction-issue bound: ncu shows 58 % issue
+// slots busy with 31 % of the warp slots occupied).  ex2.approx / rcp.approx are 1-2 ulp; the one extra error, the
+// rounding of x log2 e (6e-8 |x| relative in e^-x), reaches the result scaled by sigmoid (1 - sigmoid) and stays below
+// 1e-7 of the activation: within the fp32 noise of the GEMM next to it (parity tests: tests/test_kernels_gpu.py).
+__device__ __forceinline__ float sigmoid_mufu(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return r;
+}
+__device__ __forceinline__ float swish_m(float x) { return x * sigmoid_mufu(x); }
+__device__ __forceinline__ float dswish_m(float x) {
+  const float sg = sigmoid_mufu(x);
+  return sg * (1.0f + x * (1.0f - sg));
+}
+// Polling with a 100 ns back-off: the waiting lanes of 17 warps share four schedulers with the working warps
+// (the 20 ns loop of mbar_wait cost 17 % of the kernel's issued instructions).  Bounded: a bug traps after ~2 s.
+__device__ __forceinline__ void ew_wait(uint64_t* bar, uint32_t parity) {
+  if ((threadIdx.x & 31) == 0 && !mbar_try_wait(bar, parity)) {
+    uint32_t n = 0;
+    while (!mbar_try_wait(bar, parity)) {
+      __nanosleep(100);
+      if (++n > 20000000u) __trap();
+    }
+  }
+  __syncwarp();
+}
 __device__ __forceinline__ void producer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(EW_PROD_THREADS) : "memory"); }
 
 // -DMSMP_EW_TICKS: CTA 0 prints the cycles each role spent waiting on its barriers (diagnostic builds only)
@@ -170,8 +198,8 @@ __global__ void __launch_bounds__(EW_THREADS, 1) k_edge_ws(const EdgeWsParams p)
       const int valid = min(EW_TILE, p.E - e0);
       const int buf = i & 1;
       const int* sd = s_dst + (i & (EW_SLOTS - 1)) * EW_DST_LD + 1;
-      EW_TIMED(t_acc, mbar_wait_warp(&acc_full[buf], (i >> 1) & 1));
-      if (BWD) EW_TIMED(t_s, mbar_wait_warp(s_full, i & 1));
+      EW_TIMED(t_acc, ew_wait(&acc_full[buf], (i >> 1) & 1));
+      if (BWD) EW_TIMED(t_s, ew_wait(s_full, i & 1));
       tc_fence_after();
       // Destination-segment sums: running sums in registers.  The segment boundaries are warp-uniform bit masks
       // (ballots over the tile's destination indices incl. the two neighbouring edges), the element-wise math of a
@@ -197,9 +225,10 @@ __global__ void __launch_bounds__(EW_THREADS, 1) k_edge_ws(const EdgeWsParams p)
         if (nb <= 0) continue;
         const int dj = sd[eb + lane];
         const uint32_t live = nb >= 32 ? 0xffffffffu : ((1u << nb) - 1u);
-        const uint32_t smask = __ballot_sync(0xffffffffu, dj != sd[eb + lane - 1]) & live;      // first edge of a segment
-        const uint32_t emask = __ballot_sync(0xffffffffu, dj != sd[eb + lane + 1]) & live;      // last edge of a segment
-        const uint32_t fmask = emask | (eb + nb == uvalid ? (1u << (nb - 1)) : 0u);             // + the unit's last edge
+        // (the shuffles from lane 0 let the compiler see the masks as warp-uniform: plain branches, no BSSY / BSYNC)
+        const uint32_t smask = __shfl_sync(0xffffffffu, __ballot_sync(0xffffffffu, dj != sd[eb + lane - 1]) & live, 0);
+        const uint32_t emask = __shfl_sync(0xffffffffu, __ballot_sync(0xffffffffu, dj != sd[eb + lane + 1]) & live, 0);
+        const uint32_t fmask = emask | (eb + nb == uvalid ? (1u << (nb - 1)) : 0u);      // last edges of segments + of the unit
         if (!BWD) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] += bias;
@@ -210,7 +239,7 @@ __global__ void __launch_bounds__(EW_THREADS, 1) k_edge_ws(const EdgeWsParams p)
               if (j < nb) zp[j * 128] = v[j];
           }
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = swish(v[j]);
+          for (int j = 0; j < 32; ++j) v[j] = swish_m(v[j]);
         } else {
           const float* sp = smS + eb * 128 + ch;
 #pragma unroll
@@ -255,7 +284,7 @@ __global__ void __launch_bounds__(EW_THREADS, 1) k_edge_ws(const EdgeWsParams p)
     reg_dec<40>();
     if (warp == EW_MMA_WARP) {
     constexpr uint32_t IDESC = umma_idesc_tf32(128, 128, 0, 0);
-    mbar_wait_warp(w_full, 0);
+    ew_wait(w_full, 0);
     tc_fence_after();
     const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
     const bool leader = elect_one();
@@ -267,12 +296,12 @@ __global__ void __launch_bounds__(EW_THREADS, 1) k_edge_ws(const EdgeWsParams p)
 #pragma unroll 1
     for (int i = 0; i < ntile; ++i) {
       const int buf = i & 1;
-      if (i >= 2) EW_TIMED(t_ae, mbar_wait_warp(&acc_empty[buf], ((i >> 1) - 1) & 1));
+      if (i >= 2) EW_TIMED(t_ae, ew_wait(&acc_empty[buf], ((i >> 1) - 1) & 1));
       tc_fence_after();
       const uint32_t acc = tm + EW_ACC + 128 * buf;
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
-        EW_TIMED(t_full, mbar_wait_warp(&full[s], ph));
+        EW_TIMED(t_full, ew_wait(&full[s], ph));
         tc_fence_after();
         const uint32_t b_hi = smem_u32(smB + s * EW_STAGE_BYTES), b_lo = b_hi + IMG_BYTES;
 #pragma unroll
@@ -347,21 +376,18 @@ __global__ void __launch_bounds__(EW_THREADS, 1) k_edge_ws(const EdgeWsParams p)
       const int valid = min(EW_TILE, p.E - e0);
       const int slot = i & (EW_SLOTS - 1);
       const int col = 32 * c + 4 * c16;
+      // Rows past the end of the edge list (last tile only) re-read the last live row: they become extra COLUMNS of
+      // D^T that nobody reads, so they need no zero fill, only in-bounds addresses.
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const int r = (pt >> 3) + 32 * q;
-        if (r < valid) {
-          const int d = s_dst[slot * EW_DST_LD + 1 + r];
-          if (!BWD || j >= 4) {
-            ga[q] = ldg4(p.P + (size_t)d * p.ldpq + col);
-            gb[q] = ldg4(p.Q + (size_t)s_src[slot * EW_TILE + r] * p.ldpq + col);
-          } else {
-            ga[q] = ldg4(p.dagg + (size_t)d * p.lddagg + col);
-            gb[q] = ldg4(p.z2 + (size_t)(e0 + r) * 128 + col);
-          }
+        const int r = min((pt >> 3) + 32 * q, valid - 1);
+        const int d = s_dst[slot * EW_DST_LD + 1 + r];
+        if (!BWD || j >= 4) {
+          ga[q] = ldg4(p.P + (size_t)d * p.ldpq + col);
+          gb[q] = ldg4(p.Q + (size_t)s_src[slot * EW_TILE + r] * p.ldpq + col);
         } else {
-          ga[q] = zero4();
-          gb[q] = zero4();
+          ga[q] = ldg4(p.dagg + (size_t)d * p.lddagg + col);
+          gb[q] = ldg4(p.z2 + (size_t)(e0 + r) * 128 + col);
         }
       }
     };
@@ -377,19 +403,19 @@ __global__ void __launch_bounds__(EW_THREADS, 1) k_edge_ws(const EdgeWsParams p)
       const int slot = i & (EW_SLOTS - 1);
       if (!BWD || j < 4) {
         // ---- operand chunk -> ring stage
-        if (nfill >= EW_STAGES) EW_TIMED(t_empty, mbar_wait_warp(&empty[s], ph ^ 1));
+        if (nfill >= EW_STAGES) EW_TIMED(t_empty, ew_wait(&empty[s], ph ^ 1));
         uint8_t* st = smB + s * EW_STAGE_BYTES;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int r = (pt >> 3) + 32 * q;
           float4 v;
           if (!BWD) {
-            v = swish4(add4(ga[q], gb[q]));
-            if (r >= valid) v = zero4();
+            const float4 z1 = add4(ga[q], gb[q]);
+            v = make_float4(swish_m(z1.x), swish_m(z1.y), swish_m(z1.z), swish_m(z1.w));
           } else {
-            const float sc = (r < valid) ? s_sc[slot * EW_TILE + r] : 0.f;
-            v = make_float4(ga[q].x * sc * dswish(gb[q].x), ga[q].y * sc * dswish(gb[q].y),
-                            ga[q].z * sc * dswish(gb[q].z), ga[q].w * sc * dswish(gb[q].w));
+            const float sc = s_sc[slot * EW_TILE + min(r, valid - 1)];
+            v = make_float4(ga[q].x * sc * dswish_m(gb[q].x), ga[q].y * sc * dswish_m(gb[q].y),
+                            ga[q].z * sc * dswish_m(gb[q].z), ga[q].w * sc * dswish_m(gb[q].w));
             if (r < valid) st4(p.dz2 + (size_t)(e0 + r) * 128 + 32 * c + 4 * c16, v);
           }
           store_split4(st, st + IMG_BYTES, img_off(r, c16), v);
@@ -404,13 +430,16 @@ __global__ void __launch_bounds__(EW_THREADS, 1) k_edge_ws(const EdgeWsParams p)
         }
       } else {
         // ---- backward: z1 chunk -> a1 (global), sw'(z1) (shared tile for the epilogue)
-        if (j == 4 && i >= 1) EW_TIMED(t_se, mbar_wait_warp(s_empty, (i - 1) & 1));
+        if (j == 4 && i >= 1) EW_TIMED(t_se, ew_wait(s_empty, (i - 1) & 1));
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int r = (pt >> 3) + 32 * q;
           const float4 z1 = add4(ga[q], gb[q]);
-          if (r < valid) st4(p.a1 + (size_t)(e0 + r) * 128 + 32 * c + 4 * c16, swish4(z1));
-          st4(smS + r * 128 + 32 * c + 4 * c16, make_float4(dswish(z1.x), dswish(z1.y), dswish(z1.z), dswish(z1.w)));
+          if (r < valid)
+            st4(p.a1 + (size_t)(e0 + r) * 128 + 32 * c + 4 * c16,
+                make_float4(swish_m(z1.x), swish_m(z1.y), swish_m(z1.z), swish_m(z1.w)));
+          st4(smS + r * 128 + 32 * c + 4 * c16,
+              make_float4(dswish_m(z1.x), dswish_m(z1.y), dswish_m(z1.z), dswish_m(z1.w)));
         }
         if (j == 7) {
           __syncwarp();

@@ -321,7 +321,7 @@ def edge_bwd(P, Q, topo, W2, z2, dagg, dP, defer_wgrad=False, W2raw=None):
                                            ws.numel(), _stream()), "msmp_edge_ws_bwd")
         else:
             img = W2.img if isinstance(W2, TcW) else _cached_images(W2)
-            with _timed("edge_tc_bwd", 2.0 * topo.E * H * H, 4.0 * H * (6 * topo.E + topo.N)):
+            with _timed("edge_tc_bwd", 2.0 * topo.E * H * H, 4.0 * H * (7 * topo.E + topo.N)):
                 check(lib.msmp_edge_tc_bwd(P.data_ptr(), Q.data_ptr(), _ld(P), topo.src.data_ptr(), topo.dst.data_ptr(),
                                            topo.rowptr.data_ptr(), topo.inv_deg.data_ptr(), img.data_ptr(), z2.data_ptr(),
                                            dagg.data_ptr(), _ld(dagg), dz2.data_ptr(), a1.data_ptr(), dz1.data_ptr(),

@@ -45,6 +45,19 @@ def gemm_mode(request):
     ops.GEMM_MODE = prev
 
 
+@pytest.fixture(params=["tc", "ws", "ffma"])
+def edge_mode(request):
+    """tc: single-role tensor-core edge kernels (edge_tc.cu); ws: warp-specialised ones (edge_ws.cu) forced for every
+    size (the default dispatch only uses them from four tiles per SM on); ffma: exact-fp32 CUDA-core kernels."""
+    from msmp_pde_b200 import ops
+    prev = ops.GEMM_MODE, ops.EDGE_WS, ops.EDGE_WS_MIN_TILES_FWD, ops.EDGE_WS_MIN_TILES_BWD
+    ops.GEMM_MODE = "ffma" if request.param == "ffma" else "tc"
+    ops.EDGE_WS = request.param == "ws"
+    ops.EDGE_WS_MIN_TILES_FWD = ops.EDGE_WS_MIN_TILES_BWD = 0
+    yield request.param
+    ops.GEMM_MODE, ops.EDGE_WS, ops.EDGE_WS_MIN_TILES_FWD, ops.EDGE_WS_MIN_TILES_BWD = prev
+
+
 def test_abi_loaded():
     from msmp_pde_b200 import _lib
     assert _lib.lib.msmp_abi_version() == 1
@@ -174,7 +187,7 @@ def _edge_ref(ei, N, PQ, W2, b2):
 
 @pytest.mark.parametrize("sizes,deg,hub", [([50, 37, 64], 5.0, None), ([300, 500], 7.0, 450), ([20], 1.5, None),
                                            ([2000, 1000], 16.0, None)])
-def test_edge_fwd(dev, gemm_mode, sizes, deg, hub):
+def test_edge_fwd(dev, edge_mode, sizes, deg, hub):
     from msmp_pde_b200 import ops
     ei, batch, N, PQ, W2, b2, topo = _edge_inputs(sizes, deg, 1, hub, dev)
     PQd = PQ.to(dev)
@@ -187,7 +200,7 @@ def test_edge_fwd(dev, gemm_mode, sizes, deg, hub):
 
 
 @pytest.mark.parametrize("sizes,deg,hub", [([50, 37, 64], 5.0, None), ([300, 500], 7.0, 450), ([2000, 1000], 16.0, None)])
-def test_edge_bwd(dev, gemm_mode, sizes, deg, hub):
+def test_edge_bwd(dev, edge_mode, sizes, deg, hub):
     from msmp_pde_b200 import ops
     ei, batch, N, PQ, W2, b2, topo = _edge_inputs(sizes, deg, 2, hub, dev)
     g = torch.Generator().manual_seed(9)
@@ -210,6 +223,37 @@ def test_edge_bwd(dev, gemm_mode, sizes, deg, hub):
     assert rel_err(dPQ[:, 128:], dQ_ref) < TOL
     assert rel_err(dW2, dW2_ref) < TOL
     assert rel_err(db2, db2_ref) < TOL
+
+
+@pytest.mark.parametrize("sizes,deg,hub", [([300, 500], 7.0, 450), ([3000, 2500, 4000], 9.0, None)])
+def test_edge_ws_matches_edge_tc(dev, sizes, deg, hub):
+    """The warp-specialised kernels read the [n][k] parameter itself (weights resident in tensor memory) and must give
+    the single-role kernels' results: z2 / dz2 / a1 / dz1 identical up to the MMA's accumulation order, the
+    destination-segment sums in the same fixed order."""
+    from msmp_pde_b200 import ops
+    ei, batch, N, PQ, W2, b2, topo = _edge_inputs(sizes, deg, 3, hub, dev)
+    g = torch.Generator().manual_seed(11)
+    dagg = torch.randn(N, 128, generator=g).to(dev)
+    PQd, W2d, b2d = PQ.to(dev), W2.to(dev).contiguous(), b2.to(dev)
+    prev = ops.EDGE_WS, ops.EDGE_WS_MIN_TILES_FWD, ops.EDGE_WS_MIN_TILES_BWD
+    res = {}
+    try:
+        ops.EDGE_WS_MIN_TILES_FWD = ops.EDGE_WS_MIN_TILES_BWD = 0
+        for mode in ("tc", "ws"):
+            ops.EDGE_WS = mode == "ws"
+            agg, z2 = ops.edge_fwd(PQd[:, :128], PQd[:, 128:], topo, W2d.t().contiguous(), b2d, W2raw=W2d)
+            dP = torch.full((N, 128), float("nan"), device=dev)
+            dz1, a1, dz2 = ops.edge_bwd(PQd[:, :128], PQd[:, 128:], topo, W2d, z2, dagg, dP, defer_wgrad=True, W2raw=W2d)
+            res[mode] = (agg, z2, dP, dz1, a1, dz2)
+    finally:
+        ops.EDGE_WS, ops.EDGE_WS_MIN_TILES_FWD, ops.EDGE_WS_MIN_TILES_BWD = prev
+    _, _, z2_ref, agg_ref, _ = _edge_ref(ei, N, PQ, W2, b2)
+    assert rel_err(res["ws"][0], agg_ref) < TOL and rel_err(res["ws"][1], z2_ref) < TOL
+    for a, b in zip(res["tc"], res["ws"]):
+        assert not torch.isnan(b).any()
+        assert rel_err(b, a.double().cpu()) < 2e-6
+    # a1 = sw(P[dst] + Q[src]) involves no GEMM: only the activation differs (MUFU ex2 / rcp against expf)
+    assert rel_err(res["ws"][4], res["tc"][4]) < 5e-7
 
 
 def test_segment_mean_standalone(dev):
