@@ -85,12 +85,11 @@ GEMM_MODE = "tc"
 LEM_PERSISTENT = True
 # tensor-core edge kernels: warp-specialised, weights in tensor memory (edge_ws.cu) | single-role (edge_tc.cu)
 EDGE_WS = os.environ.get("MSMP_EDGE_WS", "1") != "0"
-# ... from this many 128-edge tiles on (four per SM).  Measured on B200 (scripts/edge_sweep.py, op alone, cold L2): the
-# pipelined forward is faster at every size, the backward from about five tiles per SM; inside the captured C2 step
-# (two tiles per SM, gate || main layers on two streams) the single-role kernels are 1-3 % faster: they hold 128
-# tensor-memory columns instead of all 512, so the other stream's kernels can share the SM.
-EDGE_WS_MIN_TILES_FWD = int(os.environ.get("MSMP_EDGE_WS_MIN_TILES_FWD", "592"))
-EDGE_WS_MIN_TILES_BWD = int(os.environ.get("MSMP_EDGE_WS_MIN_TILES_BWD", "592"))
+# ... from this many 128-edge tiles on.  Measured on B200 (scripts/edge_sweep.py and bench.py): the pipelined kernels
+# are faster from about three tiles per SM on (2.4x at 1 Mi x 6 Mi) and equal below; inside the captured C2 step
+# (two tiles per SM) they are 3 % faster than the single-role kernels, so the default is "always".
+EDGE_WS_MIN_TILES_FWD = int(os.environ.get("MSMP_EDGE_WS_MIN_TILES_FWD", "0"))
+EDGE_WS_MIN_TILES_BWD = int(os.environ.get("MSMP_EDGE_WS_MIN_TILES_BWD", "0"))
 # The persistent backward recurrence can be cut into several launches so that the weight-gradient GEMMs of finished
 # steps overlap the remaining ones on a side stream (lem._LEMFn.backward).  Measured on the C2 workload after the
 # recurrence kernel got its own MMA warp and 16 epilogue warps: 1 launch 4.11 ms/step, 2: 4.16, 3: 4.19, 5: 4.28,
