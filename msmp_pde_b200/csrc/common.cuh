@@ -131,6 +131,38 @@ static __global__ void k_reduce_partials(const float* __restrict__ part, float* 
   out[i] = accumulate ? out[i] + s : s;
 }
 
+// The same for few outputs and MANY partials (decoder weight gradients: 490 outputs, one partial per 8 nodes): a CTA
+// of 8 warps owns 32 consecutive outputs; warp w adds the partials w, w + 8, ... in order (coalesced 128-byte rows, four
+// loads in flight), the eight warp sums are then added in warp order.  Fixed order => deterministic.
+static __global__ void __launch_bounds__(256) k_reduce_partials_tall(const float* __restrict__ part,
+                                                                     float* __restrict__ out, int count, int S,
+                                                                     size_t stride) {
+  __shared__ float sh[8][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + lane;
+  float s = 0.f;
+  if (i < count) {
+    int q = w;
+    for (; q + 24 < S; q += 32) {
+      const float a = part[(size_t)q * stride + i], b = part[(size_t)(q + 8) * stride + i];
+      const float c = part[(size_t)(q + 16) * stride + i], d = part[(size_t)(q + 24) * stride + i];
+      s += a;
+      s += b;
+      s += c;
+      s += d;
+    }
+    for (; q < S; q += 8) s += part[(size_t)q * stride + i];
+  }
+  sh[w][lane] = s;
+  __syncthreads();
+  if (w == 0 && i < count) {
+    float t = sh[0][lane];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) t += sh[k][lane];
+    out[i] = t;
+  }
+}
+
 // Two partial sets in one launch (main weight tile + side/bias rows of a weight-gradient call).
 static __global__ void k_reduce_partials2(const float* __restrict__ part0, float* __restrict__ out0, int count0,
                                           size_t stride0, const float* __restrict__ part1, float* __restrict__ out1,

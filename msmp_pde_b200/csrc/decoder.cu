@@ -21,6 +21,17 @@ struct DecGeom {
   int C, K1, S1, L1, K2, TW;
 };
 
+// Geometry either from the launch parameters (FC = 0) or fixed at compile time: with the tw = 25 geometry of the
+// reference's default runs (K1 = 16, S1 = 3, L1 = 38, K2 = 14) as constants, the inner loops unroll and the index
+// divisions fold; the kernels are instruction bound (two shared-memory loads per FMA), not bandwidth bound.
+template <int FC, int FK1, int FS1, int FL1, int FK2, int FTW>
+struct GeomT {
+  int C, K1, S1, L1, K2, TW;
+  __device__ __forceinline__ explicit GeomT(const DecGeom& r)
+      : C(FC ? FC : r.C), K1(FC ? FK1 : r.K1), S1(FC ? FS1 : r.S1), L1(FC ? FL1 : r.L1), K2(FC ? FK2 : r.K2),
+        TW(FC ? FTW : r.TW) {}
+};
+
 struct DecFwdParams {
   const float* h;       // [N][C*128]
   const float* w1; const float* b1; const float* w2; const float* b2;
@@ -32,11 +43,12 @@ struct DecFwdParams {
   DecGeom g;
 };
 
+template <int FC, int FK1, int FS1, int FL1, int FK2, int FTW>
 __global__ void __launch_bounds__(256) k_decoder_fwd(const DecFwdParams p) {
   __shared__ __align__(16) float sh[DEC_NB_F * 2 * DEC_LIN];
   __shared__ float sa[DEC_NB_F * DEC_OC * DEC_MAXL1];
   __shared__ float sw1[8 * 2 * 16], sw2[2 * 8 * 16], sb1[8], sb2[2], sdt[64];
-  const DecGeom g = p.g;
+  const GeomT<FC, FK1, FS1, FL1, FK2, FTW> g(p.g);
   const int tid = threadIdx.x;
   const int n0 = blockIdx.x * DEC_NB_F;
   const int nb = min(DEC_NB_F, p.N - n0);
@@ -91,13 +103,14 @@ struct DecBwdParams {
   DecGeom g;
 };
 
+template <int FC, int FK1, int FS1, int FL1, int FK2, int FTW>
 __global__ void __launch_bounds__(256) k_decoder_bwd(const DecBwdParams p) {
   __shared__ __align__(16) float sh[DEC_NB_B * 2 * DEC_LIN];
   __shared__ float sa[DEC_NB_B * DEC_OC * DEC_MAXL1];     // a = swish(za)
   __shared__ float sz[DEC_NB_B * DEC_OC * DEC_MAXL1];     // za, then dza
   __shared__ float sdd[DEC_NB_B * 2 * 64];                // dout * dt
   __shared__ float sw1[8 * 2 * 16], sw2[2 * 8 * 16];
-  const DecGeom g = p.g;
+  const GeomT<FC, FK1, FS1, FL1, FK2, FTW> g(p.g);
   const int tid = threadIdx.x;
   const int n0 = blockIdx.x * DEC_NB_B;
   const int nb = min(DEC_NB_B, p.N - n0);
@@ -214,7 +227,13 @@ extern "C" int msmp_decoder_fwd(const float* h, const float* w1, const float* b1
   if (!geom_ok(g) || N < 0) return MSMP_ERR_ARG;
   if (N == 0) return MSMP_OK;
   DecFwdParams p{h, w1, b1, w2, b2, u, ldu, dt, za, out, N, g};
-  k_decoder_fwd<<<(N + DEC_NB_F - 1) / DEC_NB_F, 256, 0, stream>>>(p);
+  const int grid = (N + DEC_NB_F - 1) / DEC_NB_F;
+  if (K1 == 16 && S1 == 3 && L1 == 38 && K2 == 14 && TW == 25 && C == 1)
+    k_decoder_fwd<1, 16, 3, 38, 14, 25><<<grid, 256, 0, stream>>>(p);
+  else if (K1 == 16 && S1 == 3 && L1 == 38 && K2 == 14 && TW == 25 && C == 2)
+    k_decoder_fwd<2, 16, 3, 38, 14, 25><<<grid, 256, 0, stream>>>(p);
+  else
+    k_decoder_fwd<0, 0, 0, 0, 0, 0><<<grid, 256, 0, stream>>>(p);
   MSMP_CHECK_LAUNCH();
   return MSMP_OK;
 }
@@ -233,9 +252,14 @@ extern "C" int msmp_decoder_bwd(const float* dout, const float* h, const float* 
   if (ws_bytes < msmp_decoder_bwd_workspace(N, C, K1, K2)) return MSMP_ERR_WORKSPACE;
   const int ctas = (N + DEC_NB_B - 1) / DEC_NB_B;
   DecBwdParams p{dout, h, za, w1, w2, dt, dh, reinterpret_cast<float*>(workspace), N, g};
-  k_decoder_bwd<<<ctas, 256, 0, stream>>>(p);
+  if (K1 == 16 && S1 == 3 && L1 == 38 && K2 == 14 && TW == 25 && C == 1)
+    k_decoder_bwd<1, 16, 3, 38, 14, 25><<<ctas, 256, 0, stream>>>(p);
+  else if (K1 == 16 && S1 == 3 && L1 == 38 && K2 == 14 && TW == 25 && C == 2)
+    k_decoder_bwd<2, 16, 3, 38, 14, 25><<<ctas, 256, 0, stream>>>(p);
+  else
+    k_decoder_bwd<0, 0, 0, 0, 0, 0><<<ctas, 256, 0, stream>>>(p);
   MSMP_CHECK_LAUNCH();
-  k_reduce_partials<<<(nW + 255) / 256, 256, 0, stream>>>(p.part, dW, nW, ctas, (size_t)nW, 0);
+  k_reduce_partials_tall<<<(nW + 31) / 32, 256, 0, stream>>>(p.part, dW, nW, ctas, (size_t)nW);
   MSMP_CHECK_LAUNCH();
   return MSMP_OK;
 }

@@ -59,7 +59,7 @@ struct EdgeWsParams {
   float* dz2; float* a1; float* dz1;      // bwd outs [E][128]
   float* out; int ldo;              // fwd: agg [N][128] (mean);  bwd: dP [N][ldo] (sum)
   float* carry;                     // [T * EW_EH][2][128], per unit of EW_UNIT edges
-  int E; int T;
+  int E; int T; int N;
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -229,6 +229,18 @@ __global__ void __launch_bounds__(EW_THREADS, 1) k_edge_ws(const EdgeWsParams p)
         const uint32_t smask = __shfl_sync(0xffffffffu, __ballot_sync(0xffffffffu, dj != sd[eb + lane - 1]) & live, 0);
         const uint32_t emask = __shfl_sync(0xffffffffu, __ballot_sync(0xffffffffu, dj != sd[eb + lane + 1]) & live, 0);
         const uint32_t fmask = emask | (eb + nb == uvalid ? (1u << (nb - 1)) : 0u);      // last edges of segments + of the unit
+        // Nodes without in-edges never get a segment: their output rows are the gaps between consecutive destinations
+        // (plus the rows before the first and after the last edge's destination).  Zeroed here: no memset launch.
+        {
+          const int prev = (e0 + eb + lane == 0) ? -1 : sd[eb + lane - 1];
+          uint32_t gm = __shfl_sync(0xffffffffu, __ballot_sync(0xffffffffu, dj - prev > 1) & live, 0);
+          for (; gm; gm &= gm - 1) {
+            const int e = eb + __ffs(gm) - 1;
+            for (int n = (e0 + e == 0) ? 0 : sd[e - 1] + 1; n < sd[e]; ++n) p.out[(size_t)n * p.ldo + ch] = 0.f;
+          }
+          if (e0 + eb + nb == p.E)
+            for (int n = sd[eb + nb - 1] + 1; n < p.N; ++n) p.out[(size_t)n * p.ldo + ch] = 0.f;
+        }
         if (!BWD) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] += bias;
@@ -534,13 +546,15 @@ extern "C" int msmp_edge_ws_fwd(const float* P, const float* Q, int ldpq, const 
                                 const float* b2, float* z2, float* agg, int E, int N, void* workspace, size_t ws_bytes,
                                 cudaStream_t stream) {
   if (E < 0 || N < 0 || (ldpq & 3)) return MSMP_ERR_ARG;
-  if (cudaMemsetAsync(agg, 0, (size_t)N * 128 * sizeof(float), stream) != cudaSuccess) return MSMP_ERR_CUDA;
-  if (E == 0) return MSMP_OK;
+  if (E == 0) {      // (with edges, the kernel itself zeroes the rows of nodes without in-edges)
+    if (cudaMemsetAsync(agg, 0, (size_t)N * 128 * sizeof(float), stream) != cudaSuccess) return MSMP_ERR_CUDA;
+    return MSMP_OK;
+  }
   if (ws_bytes < msmp_edge_ws_workspace(E)) return MSMP_ERR_WORKSPACE;
   EdgeWsParams p{};
   p.P = P; p.Q = Q; p.ldpq = ldpq; p.src = src; p.dst = dst; p.W = W; p.w_rs = w_rs; p.w_cs = w_cs;
   p.b2 = b2; p.z2 = z2; p.out = agg; p.ldo = 128;
-  p.carry = reinterpret_cast<float*>(workspace); p.E = E; p.T = msmp_edge_tiles(E);
+  p.carry = reinterpret_cast<float*>(workspace); p.E = E; p.T = msmp_edge_tiles(E); p.N = N;
   int rc = launch_edge_ws<false>(p, stream);
   if (rc) return rc;
   k_carry_fix_ws<<<(p.T * EW_EH + 7) / 8, 256, 0, stream>>>(p.carry, dst, rowptr, inv_deg, agg, 128, E, p.T * EW_EH);
@@ -554,15 +568,17 @@ extern "C" int msmp_edge_ws_bwd(const float* P, const float* Q, int ldpq, const 
                                 float* dP, int lddp, int E, int N, void* workspace, size_t ws_bytes,
                                 cudaStream_t stream) {
   if (E < 0 || N < 0 || (ldpq & 3) || (lddagg & 3) || (lddp & 3)) return MSMP_ERR_ARG;
-  if (cudaMemset2DAsync(dP, (size_t)lddp * sizeof(float), 0, 128 * sizeof(float), N, stream) != cudaSuccess)
-    return MSMP_ERR_CUDA;
-  if (E == 0) return MSMP_OK;
+  if (E == 0) {
+    if (cudaMemset2DAsync(dP, (size_t)lddp * sizeof(float), 0, 128 * sizeof(float), N, stream) != cudaSuccess)
+      return MSMP_ERR_CUDA;
+    return MSMP_OK;
+  }
   if (ws_bytes < msmp_edge_ws_workspace(E)) return MSMP_ERR_WORKSPACE;
   EdgeWsParams p{};
   p.P = P; p.Q = Q; p.ldpq = ldpq; p.src = src; p.dst = dst; p.inv_deg_e = inv_deg_e;
   p.W = W; p.w_rs = w_rs; p.w_cs = w_cs; p.z2 = const_cast<float*>(z2); p.dagg = dagg; p.lddagg = lddagg;
   p.dz2 = dz2; p.a1 = a1; p.dz1 = dz1; p.out = dP; p.ldo = lddp;
-  p.carry = reinterpret_cast<float*>(workspace); p.E = E; p.T = msmp_edge_tiles(E);
+  p.carry = reinterpret_cast<float*>(workspace); p.E = E; p.T = msmp_edge_tiles(E); p.N = N;
   int rc = launch_edge_ws<true>(p, stream);
   if (rc) return rc;
   k_carry_fix_ws<<<(p.T * EW_EH + 7) / 8, 256, 0, stream>>>(p.carry, dst, rowptr, nullptr, dP, lddp, E, p.T * EW_EH);

@@ -44,7 +44,7 @@ for i, e in enumerate(grp):
 pts.sort()
 active = set(); last = t0; idle = 0.0
 alone = collections.Counter(); shared = collections.Counter(); cnt = collections.Counter(); tot = collections.Counter()
-short = lambda n: n.split("(")[0].split("<")[0][-60:]
+short = lambda n: (n[:118] if "at::native" in n else n.split("(")[0].split("<")[0][-60:])
 for e in grp:
     cnt[short(e["name"])] += 1; tot[short(e["name"])] += e["dur"]
 for t, d, i in pts:
@@ -67,7 +67,7 @@ for n, _ in sorted(tot.items(), key=lambda kv: -(alone[kv[0]] + shared[kv[0]])):
 # coarse phases: first/last occurrence of marker kernels
 def first(name): return next((e["ts"] - t0 for e in grp if name in e["name"]), None)
 def lastt(name): return next((e["ts"] + e["dur"] - t0 for e in reversed(grp) if name in e["name"]), None)
-for nm in ("k_pack", "k_lem_fwd_tc", "k_edge_tc", "k_decoder_fwd", "k_decoder_bwd", "k_lem_bwd_tc", "multi_tensor", "adam"):
+for nm in ("k_pack", "k_lem_fwd_tc", "k_edge_", "k_decoder_fwd", "k_decoder_bwd", "k_lem_bwd_tc", "multi_tensor", "adam"):
     print(f"  {nm:16s} first start {first(nm)} us, last end {lastt(nm)} us")
 
 if os.environ.get("TAIL_US"):
