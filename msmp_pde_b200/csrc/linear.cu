@@ -8,6 +8,7 @@
 //                       row ranges into per-CTA partials, then msmp_reduce_partials sums the
 //                       partials in a fixed order => run-to-run bit-identical weight gradients
 //                       (no float atomics anywhere).
+#include <cstdlib>
 #include "common.cuh"
 #include "msmp_b200.h"
 
@@ -341,11 +342,20 @@ extern "C" int msmp_linear_fwd(const float* const* A, const int* lda, const int*
   return MSMP_OK;
 }
 
+// Split-M factor of the weight-gradient kernels.  MSMP_WGRAD_CTAS (CTAs aimed at per call) and MSMP_WGRAD_MIN_ROWS
+// (rows per split at least) override the defaults for tuning runs.
+static int wgrad_env(const char* name, int dflt) {
+  const char* v = getenv(name);
+  const int x = v ? atoi(v) : 0;
+  return x > 0 ? x : dflt;
+}
 extern "C" int msmp_linear_wgrad_splits(int M, int K, int Nout) {
+  static const int want_ctas = wgrad_env("MSMP_WGRAD_CTAS", 2 * 148);
+  static const int min_rows = wgrad_env("MSMP_WGRAD_MIN_ROWS", 8 * WG_MC);      // 256: C2 step 3.94 -> 3.84 ms vs 128
   if (M <= 0) return 1;
   int tiles = ((K + 127) / 128) * ((Nout + 127) / 128);
-  int want = (2 * 148 + tiles - 1) / tiles;
-  int max_splits = (M + 4 * WG_MC - 1) / (4 * WG_MC);      // at least 128 rows per split
+  int want = (want_ctas + tiles - 1) / tiles;
+  int max_splits = (M + min_rows - 1) / min_rows;
   int s = want < max_splits ? want : max_splits;
   return s < 1 ? 1 : s;
 }
