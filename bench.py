@@ -263,7 +263,7 @@ def scatter_bandwidth(dev, n_nodes=1 << 20, degree=6, reps=10):
             "peak_gbs": peak}
 
 
-def message_bandwidth(dev, n_nodes=1 << 20, degree=6, reps=5):
+def message_bandwidth(dev, n_nodes=1 << 20, degree=6, reps=7):
     """The message kernels (fused gather + second message-MLP layer on the tensor pipe + mean aggregation, forward and
     backward) on the config-5 shape, 1 Mi nodes x 6 Mi edges, as a fraction of the measured HBM copy peak.
     Algorithmic bytes per edge (gathers counted without reuse): forward 2 x 512 gathered (P[dst],
@@ -280,14 +280,15 @@ def message_bandwidth(dev, n_nodes=1 << 20, degree=6, reps=5):
     dagg = torch.randn(n_nodes, 128, device=dev, generator=gen)
     dP = torch.empty(n_nodes, 128, device=dev)
     peak = _peaks()["hbm_gbs"]
-    res = {"kernel": "k_edge_ws<fwd> / k_edge_ws<bwd>", "nodes": n_nodes, "edges": n_nodes * degree, "peak_gbs": peak}
+    res = {"kernel": "k_edge_ws<fwd> / k_edge_ws<bwd>", "nodes": n_nodes, "edges": n_nodes * degree, "peak_gbs": peak,
+           "timing": f"CUDA events around the op (kernel + memset + carry fix-up), median of {reps} after 3 warm-ups"}
     for topo_name, npg in (("band", 100), ("random", 0)):
         g = synth.large_graph(n_nodes, degree, topology=topo_name, nodes_per_graph=npg, seed=0)
         topo = build_topology(g["edge_index"].to(dev), g["batch"].to(dev), n_nodes)
         del g
         E = topo.E
-        tf = tb = 0.0
-        for it in range(2 + reps):
+        tfs, tbs = [], []
+        for it in range(3 + reps):
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
             ev[0].record()
             agg, z2 = ops.edge_fwd(PQ[:, :128], PQ[:, 128:], topo, None, b2, W2raw=W2)
@@ -296,9 +297,10 @@ def message_bandwidth(dev, n_nodes=1 << 20, degree=6, reps=5):
             ev[2].record()
             torch.cuda.synchronize()
             del out
-            if it >= 2:
-                tf += ev[0].elapsed_time(ev[1]) / reps
-                tb += ev[1].elapsed_time(ev[2]) / reps
+            if it >= 3:       # the first passes pay for the allocator's cudaMallocs of the 3.2 GB edge tensors
+                tfs.append(ev[0].elapsed_time(ev[1]))
+                tbs.append(ev[1].elapsed_time(ev[2]))
+        tf, tb = sorted(tfs)[len(tfs) // 2], sorted(tbs)[len(tbs) // 2]       # median of `reps`
         bf, bb = E * 1544 + n_nodes * 512, E * 3596 + n_nodes * 512
         res[topo_name] = {"fwd_ms": round(tf, 4), "fwd_gbs": round(bf / tf / 1e6, 1), "fwd_frac": round(bf / tf / 1e6 / peak, 4),
                           "bwd_ms": round(tb, 4), "bwd_gbs": round(bb / tb / 1e6, 1), "bwd_frac": round(bb / tb / 1e6 / peak, 4),

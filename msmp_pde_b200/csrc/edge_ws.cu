@@ -19,6 +19,7 @@
 //                         destination-segment sums as running sums in registers (segment boundaries are warp-uniform;
 //                         fixed order, no atomics).  Segments cut by a tile boundary use the carry buffer + ordered
 //                         fix-up exactly like edge_tc.cu.
+#include <cstdlib>
 #include "umma.cuh"
 #include "msmp_b200.h"
 
@@ -114,7 +115,7 @@ __device__ __forceinline__ void producer_sync() { asm volatile("bar.sync 1, %0;"
 #define EW_TIMED(acc, stmt) do { stmt; } while (0)
 #endif
 
-template <bool BWD>
+template <bool BWD, bool ZFILL>
 __global__ void __launch_bounds__(EW_THREADS, 1) k_edge_ws(const EdgeWsParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -230,8 +231,10 @@ __global__ void __launch_bounds__(EW_THREADS, 1) k_edge_ws(const EdgeWsParams p)
         const uint32_t emask = __shfl_sync(0xffffffffu, __ballot_sync(0xffffffffu, dj != sd[eb + lane + 1]) & live, 0);
         const uint32_t fmask = emask | (eb + nb == uvalid ? (1u << (nb - 1)) : 0u);      // last edges of segments + of the unit
         // Nodes without in-edges never get a segment: their output rows are the gaps between consecutive destinations
-        // (plus the rows before the first and after the last edge's destination).  Zeroed here: no memset launch.
-        {
+        // (plus the rows before the first and after the last edge's destination).  ZFILL: zeroed here, no memset launch
+        // (small graphs, where a launch costs as much as the kernel; on large ones the memset is cheaper than these
+        // extra instructions in the epilogue, the busiest role: 1 Mi x 6 Mi forward 1.97 ms against 2.26 ms).
+        if (ZFILL) {
           const int prev = (e0 + eb + lane == 0) ? -1 : sd[eb + lane - 1];
           uint32_t gm = __shfl_sync(0xffffffffu, __ballot_sync(0xffffffffu, dj - prev > 1) & live, 0);
           for (; gm; gm &= gm - 1) {
@@ -521,16 +524,28 @@ static int ws_sm_count() {
   return sms;
 }
 
-template <bool BWD>
+// in-kernel zero fill of the rows of in-degree-0 nodes (instead of a memset in front of the kernel) up to this many tiles
+static int ws_zfill_tiles() {
+  static const int v = [] { const char* e = getenv("MSMP_EDGE_WS_ZFILL_TILES"); return e ? atoi(e) : 16 * 148; }();
+  return v;
+}
+
+template <bool BWD, bool ZFILL>
 static int launch_edge_ws(const EdgeWsParams& p, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(k_edge_ws<BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, ew_smem<BWD>()) != cudaSuccess)
+    if (cudaFuncSetAttribute(k_edge_ws<BWD, ZFILL>, cudaFuncAttributeMaxDynamicSharedMemorySize, ew_smem<BWD>()) !=
+        cudaSuccess)
       return MSMP_ERR_CUDA;
     attr_set = true;
   }
+  // One persistent CTA per SM, but at least `tpc` tiles per CTA: a CTA that walks several tiles overlaps its roles, and
+  // on small graphs the SMs left free run the other stream's kernels (MSMP_EDGE_WS_TPC overrides for tuning runs).
+  static const int tpc = [] { const char* v = getenv("MSMP_EDGE_WS_TPC"); const int x = v ? atoi(v) : 0; return x > 0 ? x : 1; }();
   const int sms = ws_sm_count();
-  k_edge_ws<BWD><<<p.T < sms ? p.T : sms, EW_THREADS, ew_smem<BWD>(), stream>>>(p);
+  int grid = (p.T + tpc - 1) / tpc;
+  if (grid > sms) grid = sms;
+  k_edge_ws<BWD, ZFILL><<<grid, EW_THREADS, ew_smem<BWD>(), stream>>>(p);
   MSMP_CHECK_LAUNCH();
   return MSMP_OK;
 }
@@ -546,16 +561,15 @@ extern "C" int msmp_edge_ws_fwd(const float* P, const float* Q, int ldpq, const 
                                 const float* b2, float* z2, float* agg, int E, int N, void* workspace, size_t ws_bytes,
                                 cudaStream_t stream) {
   if (E < 0 || N < 0 || (ldpq & 3)) return MSMP_ERR_ARG;
-  if (E == 0) {      // (with edges, the kernel itself zeroes the rows of nodes without in-edges)
-    if (cudaMemsetAsync(agg, 0, (size_t)N * 128 * sizeof(float), stream) != cudaSuccess) return MSMP_ERR_CUDA;
-    return MSMP_OK;
-  }
+  const bool zfill = E > 0 && msmp_edge_tiles(E) <= ws_zfill_tiles();
+  if (!zfill && cudaMemsetAsync(agg, 0, (size_t)N * 128 * sizeof(float), stream) != cudaSuccess) return MSMP_ERR_CUDA;
+  if (E == 0) return MSMP_OK;
   if (ws_bytes < msmp_edge_ws_workspace(E)) return MSMP_ERR_WORKSPACE;
   EdgeWsParams p{};
   p.P = P; p.Q = Q; p.ldpq = ldpq; p.src = src; p.dst = dst; p.W = W; p.w_rs = w_rs; p.w_cs = w_cs;
   p.b2 = b2; p.z2 = z2; p.out = agg; p.ldo = 128;
   p.carry = reinterpret_cast<float*>(workspace); p.E = E; p.T = msmp_edge_tiles(E); p.N = N;
-  int rc = launch_edge_ws<false>(p, stream);
+  int rc = zfill ? launch_edge_ws<false, true>(p, stream) : launch_edge_ws<false, false>(p, stream);
   if (rc) return rc;
   k_carry_fix_ws<<<(p.T * EW_EH + 7) / 8, 256, 0, stream>>>(p.carry, dst, rowptr, inv_deg, agg, 128, E, p.T * EW_EH);
   MSMP_CHECK_LAUNCH();
@@ -568,18 +582,18 @@ extern "C" int msmp_edge_ws_bwd(const float* P, const float* Q, int ldpq, const 
                                 float* dP, int lddp, int E, int N, void* workspace, size_t ws_bytes,
                                 cudaStream_t stream) {
   if (E < 0 || N < 0 || (ldpq & 3) || (lddagg & 3) || (lddp & 3)) return MSMP_ERR_ARG;
-  if (E == 0) {
-    if (cudaMemset2DAsync(dP, (size_t)lddp * sizeof(float), 0, 128 * sizeof(float), N, stream) != cudaSuccess)
-      return MSMP_ERR_CUDA;
-    return MSMP_OK;
-  }
+  const bool zfill = E > 0 && msmp_edge_tiles(E) <= ws_zfill_tiles();
+  if (!zfill &&
+      cudaMemset2DAsync(dP, (size_t)lddp * sizeof(float), 0, 128 * sizeof(float), N, stream) != cudaSuccess)
+    return MSMP_ERR_CUDA;
+  if (E == 0) return MSMP_OK;
   if (ws_bytes < msmp_edge_ws_workspace(E)) return MSMP_ERR_WORKSPACE;
   EdgeWsParams p{};
   p.P = P; p.Q = Q; p.ldpq = ldpq; p.src = src; p.dst = dst; p.inv_deg_e = inv_deg_e;
   p.W = W; p.w_rs = w_rs; p.w_cs = w_cs; p.z2 = const_cast<float*>(z2); p.dagg = dagg; p.lddagg = lddagg;
   p.dz2 = dz2; p.a1 = a1; p.dz1 = dz1; p.out = dP; p.ldo = lddp;
   p.carry = reinterpret_cast<float*>(workspace); p.E = E; p.T = msmp_edge_tiles(E); p.N = N;
-  int rc = launch_edge_ws<true>(p, stream);
+  int rc = zfill ? launch_edge_ws<true, true>(p, stream) : launch_edge_ws<true, false>(p, stream);
   if (rc) return rc;
   k_carry_fix_ws<<<(p.T * EW_EH + 7) / 8, 256, 0, stream>>>(p.carry, dst, rowptr, nullptr, dP, lddp, E, p.T * EW_EH);
   MSMP_CHECK_LAUNCH();
