@@ -63,6 +63,8 @@ _SIGS = {
     "msmp_instnorm_workspace": (S, [I, I]),
     "msmp_instnorm_fwd": (I, [P, P, I, P, P, P, P, P, I, I, I, I, F, P, P, P, S, P]),
     "msmp_instnorm_bwd": (I, [P, P, P, I, P, P, P, P, P, P, I, I, I, I, P, P, I, P, P, S, P]),
+    "msmp_instnorm1_fwd": (I, [P, P, I, P, P, P, I, I, I, F, P, P, P]),
+    "msmp_instnorm1_bwd": (I, [P, P, P, I, P, P, P, P, I, I, I, P, P, I, P, P]),
     "msmp_mul_dswish": (I, [P, P, P, S, P]),
     "msmp_decoder_nweights": (I, [I, I, I]),
     "msmp_decoder_bwd_workspace": (S, [I, I, I, I]),

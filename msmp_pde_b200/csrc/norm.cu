@@ -201,6 +201,133 @@ __global__ void __launch_bounds__(256) k_in_bwd_apply(const float* __restrict__ 
   dh[idx] = dhv;
 }
 
+// ---- one launch per direction when every graph is exactly one chunk (graphs of <= 128 nodes: the reference's 100-node
+// grids).  Chunk g is graph g; the arithmetic and its order are those of the three-kernel path above (two strided row
+// groups for the statistics, eight for the backward sums, Chan merge of a single chunk = identity), so both paths give
+// the same bits; what goes away is two launches and two trips through global memory per call.
+__global__ void __launch_bounds__(256) k_in_fused_fwd(const float* __restrict__ y0, const float* __restrict__ y1, int ld,
+                                                      const int* __restrict__ chunk_begin,
+                                                      const int* __restrict__ chunk_end, const float* __restrict__ h,
+                                                      float* __restrict__ stat, float* __restrict__ out, int B, int mode,
+                                                      float eps) {
+  __shared__ float red[2][128];
+  __shared__ __align__(16) float st[2][2][128];      // [tensor][mu | rstd][c]
+  const int gI = blockIdx.x;
+  const int c = threadIdx.x & 127, g = threadIdx.x >> 7;
+  const int b = chunk_begin[gI], e = chunk_end[gI];
+  const float n = (float)(e - b);
+  for (int t = 0; t <= mode; ++t) {
+    const float* y = t == 0 ? y0 : y1;
+    float s = 0.f;
+    for (int r = b + g; r < e; r += 2) s += __ldg(y + (size_t)r * ld + c);
+    red[g][c] = s;
+    __syncthreads();
+    const float mean = (red[0][c] + red[1][c]) / fmaxf(n, 1.f);
+    __syncthreads();
+    float q = 0.f;
+    for (int r = b + g; r < e; r += 2) {
+      float d = __ldg(y + (size_t)r * ld + c) - mean;
+      q = fmaf(d, d, q);
+    }
+    red[g][c] = q;
+    __syncthreads();
+    if (g == 0) {
+      // k_in_finalize with one chunk: mean = 0 + (mb - 0) * (nb / nb) = mb;  m2 = 0 + qb + d * d * 0 = qb
+      const float rs = rsqrtf((red[0][c] + red[1][c]) / fmaxf(n, 1.f) + eps);
+      st[t][0][c] = mean;
+      st[t][1][c] = rs;
+      float* o = stat + ((size_t)t * B + gI) * 256;
+      o[c] = mean;
+      o[128 + c] = rs;
+    }
+    __syncthreads();
+  }
+  for (int idx = threadIdx.x; idx < (e - b) * 32; idx += 256) {
+    const int row = b + (idx >> 5), c4 = (idx & 31) * 4;
+    const float4 mu = *reinterpret_cast<const float4*>(&st[0][0][c4]), rs = *reinterpret_cast<const float4*>(&st[0][1][c4]);
+    const float4 y = ldg4(y0 + (size_t)row * ld + c4);
+    const float4 o = make_float4((y.x - mu.x) * rs.x, (y.y - mu.y) * rs.y, (y.z - mu.z) * rs.z, (y.w - mu.w) * rs.w);
+    if (mode == 0) {
+      st4(out + (size_t)row * 128 + c4, o);
+      continue;
+    }
+    const float4 mu1 = *reinterpret_cast<const float4*>(&st[1][0][c4]), rs1 = *reinterpret_cast<const float4*>(&st[1][1][c4]);
+    const float4 ym = ldg4(y1 + (size_t)row * ld + c4);
+    const float4 om = make_float4((ym.x - mu1.x) * rs1.x, (ym.y - mu1.y) * rs1.y, (ym.z - mu1.z) * rs1.z, (ym.w - mu1.w) * rs1.w);
+    const float4 hh = ldg4(h + (size_t)row * 128 + c4);
+    float4 r;
+    float t;
+    t = sigmoidf_(o.x); r.x = (1.f - t) * hh.x + t * swish(om.x);
+    t = sigmoidf_(o.y); r.y = (1.f - t) * hh.y + t * swish(om.y);
+    t = sigmoidf_(o.z); r.z = (1.f - t) * hh.z + t * swish(om.z);
+    t = sigmoidf_(o.w); r.w = (1.f - t) * hh.w + t * swish(om.w);
+    st4(out + (size_t)row * 128 + c4, r);
+  }
+}
+
+__global__ void __launch_bounds__(1024) k_in_fused_bwd(const float* __restrict__ dout, const float* __restrict__ y0,
+                                                       const float* __restrict__ y1, int ld,
+                                                       const float* __restrict__ stat, const float* __restrict__ h,
+                                                       const int* __restrict__ chunk_begin,
+                                                       const int* __restrict__ chunk_end, float* __restrict__ dy0,
+                                                       float* __restrict__ dy1, int lddy, float* __restrict__ dh, int B,
+                                                       int mode) {
+  __shared__ float red[8][4][128];
+  __shared__ float gm[4][128];
+  const int gI = blockIdx.x;
+  const int c = threadIdx.x & 127, grp = threadIdx.x >> 7;
+  const int b = chunk_begin[gI], e = chunk_end[gI];
+  const float mu0 = stat[(size_t)gI * 256 + c], rs0 = stat[(size_t)gI * 256 + 128 + c];
+  float mu1 = 0.f, rs1 = 0.f;
+  if (mode == 1) {
+    mu1 = stat[((size_t)B + gI) * 256 + c];
+    rs1 = stat[((size_t)B + gI) * 256 + 128 + c];
+  }
+  float s[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int r = b + grp; r < e; r += 8) {
+    const float d = __ldg(dout + (size_t)r * 128 + c);
+    const float o0 = (__ldg(y0 + (size_t)r * ld + c) - mu0) * rs0;
+    if (mode == 0) {
+      s[0] += d;
+      s[1] = fmaf(d, o0, s[1]);
+    } else {
+      const float o1 = (__ldg(y1 + (size_t)r * ld + c) - mu1) * rs1;
+      float dog, dom, dhv;
+      blend_grads(d, o0, o1, __ldg(h + (size_t)r * 128 + c), dog, dom, dhv);
+      s[0] += dog;
+      s[1] = fmaf(dog, o0, s[1]);
+      s[2] += dom;
+      s[3] = fmaf(dom, o1, s[3]);
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) red[grp][q][c] = s[q];
+  __syncthreads();
+  if (threadIdx.x < 512) {
+    const int q = threadIdx.x >> 7;
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][q][c];
+    gm[q][c] = t / fmaxf((float)(e - b), 1.f);          // k_in_bwd_finalize with one chunk
+  }
+  __syncthreads();
+  for (int r = b + grp; r < e; r += 8) {
+    const size_t idx = (size_t)r * 128 + c;
+    const float d = dout[idx];
+    const float o0 = (y0[(size_t)r * ld + c] - mu0) * rs0;
+    if (mode == 0) {
+      dy0[(size_t)r * lddy + c] = rs0 * (d - gm[0][c] - o0 * gm[1][c]);
+      continue;
+    }
+    const float o1 = (y1[(size_t)r * ld + c] - mu1) * rs1;
+    float dog, dom, dhv;
+    blend_grads(d, o0, o1, h[idx], dog, dom, dhv);
+    dy0[(size_t)r * lddy + c] = rs0 * (dog - gm[0][c] - o0 * gm[1][c]);
+    dy1[(size_t)r * lddy + c] = rs1 * (dom - gm[2][c] - o1 * gm[3][c]);
+    dh[idx] = dhv;
+  }
+}
+
 }  // namespace msmp
 
 using namespace msmp;
@@ -244,6 +371,27 @@ extern "C" int msmp_instnorm_bwd(const float* dout, const float* y0, const float
   MSMP_CHECK_LAUNCH();
   k_in_bwd_apply<<<(N * 128 + 255) / 256, 256, 0, stream>>>(dout, y0, y1, ld, stat, h, gm, node_graph, dy0, dy1, lddy, dh,
                                                             N, B, mode);
+  MSMP_CHECK_LAUNCH();
+  return MSMP_OK;
+}
+
+/* One chunk per graph (chunk g = graph g; the caller guarantees it: every graph has 1..128 nodes): one launch each. */
+extern "C" int msmp_instnorm1_fwd(const float* y0, const float* y1, int ld, const float* h, const int* chunk_begin,
+                                  const int* chunk_end, int B, int N, int mode, float eps, float* stat, float* out,
+                                  cudaStream_t stream) {
+  if (N < 0 || B < 0 || (mode != 0 && mode != 1) || (ld & 3)) return MSMP_ERR_ARG;
+  if (N == 0 || B == 0) return MSMP_OK;
+  k_in_fused_fwd<<<B, 256, 0, stream>>>(y0, y1, ld, chunk_begin, chunk_end, h, stat, out, B, mode, eps);
+  MSMP_CHECK_LAUNCH();
+  return MSMP_OK;
+}
+
+extern "C" int msmp_instnorm1_bwd(const float* dout, const float* y0, const float* y1, int ld, const float* h,
+                                  const float* stat, const int* chunk_begin, const int* chunk_end, int B, int N,
+                                  int mode, float* dy0, float* dy1, int lddy, float* dh, cudaStream_t stream) {
+  if (N < 0 || B < 0 || (mode != 0 && mode != 1)) return MSMP_ERR_ARG;
+  if (N == 0 || B == 0) return MSMP_OK;
+  k_in_fused_bwd<<<B, 1024, 0, stream>>>(dout, y0, y1, ld, stat, h, chunk_begin, chunk_end, dy0, dy1, lddy, dh, B, mode);
   MSMP_CHECK_LAUNCH();
   return MSMP_OK;
 }

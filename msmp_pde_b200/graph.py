@@ -29,6 +29,7 @@ class Topology:
     rowptr: torch.Tensor         # int32 [N+1] CSR offsets by destination
     inv_deg: torch.Tensor        # fp32  [N]   1 / max(in-degree, 1)
     inv_deg_e: torch.Tensor      # fp32  [E]   inv_deg[dst[e]] (streamed by the backward edge kernel)
+    one_chunk_per_graph: bool    # every graph has 1..CHUNK_ROWS nodes: statistics chunk g is graph g
     colptr: torch.Tensor         # int32 [N+1] CSC offsets by source
     csc_perm: torch.Tensor       # int32 [E]   CSR edge ids sorted (stably) by source
     csr_perm: torch.Tensor | None  # int64 [E] original edge id of CSR edge e (None if already sorted)
@@ -78,6 +79,7 @@ def build_topology(edge_index: torch.Tensor, batch: torch.Tensor, num_nodes: int
     i32 = lambda t: t.to(torch.int32).contiguous()
     return Topology(N=N, E=E, B=B, src=i32(src64), dst=i32(dst64), rowptr=i32(rowptr), inv_deg=inv_deg.contiguous(),
                     inv_deg_e=inv_deg[dst64].contiguous(),
+                    one_chunk_per_graph=bool(B > 0 and int(counts.min()) >= 1 and int(counts.max()) <= CHUNK_ROWS),
                     colptr=i32(colptr), csc_perm=i32(csc_perm), csr_perm=csr_perm, node_graph=i32(batch),
                     chunk_begin=i32(cb), chunk_end=i32(ce), graph_chunk_ptr=i32(gcp))
 

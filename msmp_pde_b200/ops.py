@@ -90,6 +90,8 @@ EDGE_WS = os.environ.get("MSMP_EDGE_WS", "1") != "0"
 # (two tiles per SM) they are 3 % faster than the single-role kernels, so the default is "always".
 EDGE_WS_MIN_TILES_FWD = int(os.environ.get("MSMP_EDGE_WS_MIN_TILES_FWD", "0"))
 EDGE_WS_MIN_TILES_BWD = int(os.environ.get("MSMP_EDGE_WS_MIN_TILES_BWD", "0"))
+# InstanceNorm (+ gate blend) as one launch per direction when every graph of the batch fits one statistics chunk
+INSTNORM_FUSED = os.environ.get("MSMP_INSTNORM_FUSED", "1") != "0"
 # The persistent backward recurrence can be cut into several launches so that the weight-gradient GEMMs of finished
 # steps overlap the remaining ones on a side stream (lem._LEMFn.backward).  Measured on the C2 workload after the
 # recurrence kernel got its own MMA warp and 16 epilogue warps: 1 launch 4.11 ms/step, 2: 4.16, 3: 4.19, 5: 4.28,
@@ -367,6 +369,12 @@ def instnorm_fwd(y0, topo, y1=None, h=None, eps=1e-5):
     dev = y0.device
     out = torch.empty(topo.N, H, dtype=torch.float32, device=dev)
     stat = torch.empty(mode + 1, topo.B, 2, H, dtype=torch.float32, device=dev)
+    if INSTNORM_FUSED and topo.one_chunk_per_graph:
+        check(lib.msmp_instnorm1_fwd(y0.data_ptr(), _p(y1), _ld(y0), _p(h), topo.chunk_begin.data_ptr(),
+                                     topo.chunk_end.data_ptr(), topo.B, topo.N, mode, eps, stat.data_ptr(),
+                                     out.data_ptr(), _stream()), "msmp_instnorm1_fwd")
+        _count(1)
+        return out, stat
     ws = _workspace(lib.msmp_instnorm_workspace(topo.nchunks, topo.B), dev)
     check(lib.msmp_instnorm_fwd(y0.data_ptr(), _p(y1), _ld(y0), _p(h), topo.chunk_begin.data_ptr(),
                                 topo.chunk_end.data_ptr(), topo.graph_chunk_ptr.data_ptr(), topo.node_graph.data_ptr(),
@@ -384,6 +392,12 @@ def instnorm_bwd(dout, y0, topo, stat, y1=None, h=None):
     dy0 = torch.empty(topo.N, H, dtype=torch.float32, device=dev)
     dy1 = torch.empty(topo.N, H, dtype=torch.float32, device=dev) if mode else None
     dh = torch.empty(topo.N, H, dtype=torch.float32, device=dev) if mode else None
+    if INSTNORM_FUSED and topo.one_chunk_per_graph:
+        check(lib.msmp_instnorm1_bwd(dout.data_ptr(), y0.data_ptr(), _p(y1), _ld(y0), _p(h), stat.data_ptr(),
+                                     topo.chunk_begin.data_ptr(), topo.chunk_end.data_ptr(), topo.B, topo.N, mode,
+                                     dy0.data_ptr(), _p(dy1), H, _p(dh), _stream()), "msmp_instnorm1_bwd")
+        _count(1)
+        return dy0 if mode == 0 else (dy0, dy1, dh)
     ws = _workspace(lib.msmp_instnorm_workspace(topo.nchunks, topo.B), dev)
     check(lib.msmp_instnorm_bwd(dout.data_ptr(), y0.data_ptr(), _p(y1), _ld(y0), _p(h), stat.data_ptr(),
                                 topo.chunk_begin.data_ptr(), topo.chunk_end.data_ptr(),

@@ -305,6 +305,37 @@ def test_instnorm(dev, sizes, mode):
     assert rel_err(dy0, y0.grad) < 2e-4
 
 
+@pytest.mark.parametrize("mode", [0, 1])
+def test_instnorm_single_launch_equals_three_kernel_path(dev, mode):
+    """Batches of <= 128-node graphs take one launch per direction (msmp_instnorm1_*): same arithmetic in the same
+    order as the chunked three-kernel path, so the results must be bit-identical."""
+    from msmp_pde_b200 import ops
+    from msmp_pde_b200.graph import build_topology
+    sizes = [100, 128, 1, 37, 100]
+    batch = torch.cat([torch.full((n,), b) for b, n in enumerate(sizes)])
+    N = batch.numel()
+    topo = build_topology(torch.stack([torch.arange(N), torch.arange(N)]).to(dev), batch.to(dev), N)
+    assert topo.one_chunk_per_graph
+    g = torch.Generator().manual_seed(8)
+    y0, y1, h, w = [torch.randn(N, 128, generator=g).to(dev) for _ in range(4)]
+    kw = dict(y1=y1, h=h) if mode else {}
+    res = []
+    prev = ops.INSTNORM_FUSED
+    try:
+        for fused in (False, True):
+            ops.INSTNORM_FUSED = fused
+            out, stat = ops.instnorm_fwd(y0, topo, **kw)
+            grads = ops.instnorm_bwd(w, y0, topo, stat, **kw)
+            res.append([out, stat] + (list(grads) if mode else [grads]))
+    finally:
+        ops.INSTNORM_FUSED = prev
+    for a, b in zip(*res):
+        assert torch.equal(a, b)
+    big = build_topology(torch.stack([torch.arange(300), torch.arange(300)]).to(dev),
+                         torch.cat([torch.zeros(200), torch.ones(100)]).long().to(dev), 300)
+    assert not big.one_chunk_per_graph
+
+
 @pytest.mark.parametrize("persistent", [False, True])
 def test_lem_matches_oracle(dev, gemm_mode, persistent):
     from oracle.models import lem_forward
