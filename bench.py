@@ -99,9 +99,15 @@ def run_ours(args):
     def say(msg):
         if args.verbose:
             print(f"[bench rank {rank}] {msg}", file=sys.stderr, flush=True)
+    saved_stdout = None
     if world > 1:
         # CUDA-graph capture of NCCL collectives: the watchdog thread must not touch the capturing context
         os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")
+        # NCCL writes its version banner to the C-level stdout; the contract is ONE JSON line there, so fd 1 points at
+        # stderr until that line is printed
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -235,6 +241,9 @@ def run_ours(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(sample_graphs=8, steps=2)
+        if saved_stdout is not None:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()
