@@ -205,62 +205,77 @@ __global__ void __launch_bounds__(256) k_in_bwd_apply(const float* __restrict__ 
 // grids).  Chunk g is graph g; the arithmetic and its order are those of the three-kernel path above (two strided row
 // groups for the statistics, eight for the backward sums, Chan merge of a single chunk = identity), so both paths give
 // the same bits; what goes away is two launches and two trips through global memory per call.
-__global__ void __launch_bounds__(256) k_in_fused_fwd(const float* __restrict__ y0, const float* __restrict__ y1, int ld,
-                                                      const int* __restrict__ chunk_begin,
-                                                      const int* __restrict__ chunk_end, const float* __restrict__ h,
-                                                      float* __restrict__ stat, float* __restrict__ out, int B, int mode,
-                                                      float eps) {
-  __shared__ float red[2][128];
+__global__ void __launch_bounds__(1024) k_in_fused_fwd(const float* __restrict__ y0, const float* __restrict__ y1, int ld,
+                                                       const int* __restrict__ chunk_begin,
+                                                       const int* __restrict__ chunk_end, const float* __restrict__ h,
+                                                       float* __restrict__ stat, float* __restrict__ out, int B, int mode,
+                                                       float eps) {
+  // The graph's rows of both tensors are staged in shared memory once (all 1024 threads, float4), the statistics
+  // (512 threads: tensor x row group x channel, the chunked path's two row groups and order) and the apply pass read
+  // them from there.
+  extern __shared__ __align__(16) float tile[];      // [mode + 1][128 rows][128]
+  __shared__ float red[2][2][128];
   __shared__ __align__(16) float st[2][2][128];      // [tensor][mu | rstd][c]
-  const int gI = blockIdx.x;
-  const int c = threadIdx.x & 127, g = threadIdx.x >> 7;
+  const int gI = blockIdx.x, tid = threadIdx.x;
   const int b = chunk_begin[gI], e = chunk_end[gI];
-  const float n = (float)(e - b);
+  const int nrows = e - b;
+  const float n = (float)nrows;
   for (int t = 0; t <= mode; ++t) {
     const float* y = t == 0 ? y0 : y1;
+    for (int i = tid; i < nrows * 32; i += 1024)
+      st4(tile + (t * 128 + (i >> 5)) * 128 + 4 * (i & 31), ldg4(y + (size_t)(b + (i >> 5)) * ld + 4 * (i & 31)));
+  }
+  __syncthreads();
+  const int t = tid >> 8, g = (tid >> 7) & 1, c = tid & 127;
+  const bool worker = tid < 512 && t <= mode;
+  const float* col = tile + t * 128 * 128 + c;
+  float mean = 0.f;
+  if (worker) {
     float s = 0.f;
-    for (int r = b + g; r < e; r += 2) s += __ldg(y + (size_t)r * ld + c);
-    red[g][c] = s;
-    __syncthreads();
-    const float mean = (red[0][c] + red[1][c]) / fmaxf(n, 1.f);
-    __syncthreads();
+    for (int r = g; r < nrows; r += 2) s += col[r * 128];
+    red[t][g][c] = s;
+  }
+  __syncthreads();
+  if (worker) mean = (red[t][0][c] + red[t][1][c]) / fmaxf(n, 1.f);
+  __syncthreads();
+  if (worker) {
     float q = 0.f;
-    for (int r = b + g; r < e; r += 2) {
-      float d = __ldg(y + (size_t)r * ld + c) - mean;
+    for (int r = g; r < nrows; r += 2) {
+      const float d = col[r * 128] - mean;
       q = fmaf(d, d, q);
     }
-    red[g][c] = q;
-    __syncthreads();
-    if (g == 0) {
-      // k_in_finalize with one chunk: mean = 0 + (mb - 0) * (nb / nb) = mb;  m2 = 0 + qb + d * d * 0 = qb
-      const float rs = rsqrtf((red[0][c] + red[1][c]) / fmaxf(n, 1.f) + eps);
-      st[t][0][c] = mean;
-      st[t][1][c] = rs;
-      float* o = stat + ((size_t)t * B + gI) * 256;
-      o[c] = mean;
-      o[128 + c] = rs;
-    }
-    __syncthreads();
+    red[t][g][c] = q;
   }
-  for (int idx = threadIdx.x; idx < (e - b) * 32; idx += 256) {
-    const int row = b + (idx >> 5), c4 = (idx & 31) * 4;
+  __syncthreads();
+  if (worker && g == 0) {
+    // k_in_finalize with one chunk: mean = 0 + (mb - 0) * (nb / nb) = mb;  m2 = 0 + qb + d * d * 0 = qb
+    const float rs = rsqrtf((red[t][0][c] + red[t][1][c]) / fmaxf(n, 1.f) + eps);
+    st[t][0][c] = mean;
+    st[t][1][c] = rs;
+    float* o = stat + ((size_t)t * B + gI) * 256;
+    o[c] = mean;
+    o[128 + c] = rs;
+  }
+  __syncthreads();
+  for (int idx = tid; idx < nrows * 32; idx += 1024) {
+    const int rl = idx >> 5, row = b + rl, c4 = (idx & 31) * 4;
     const float4 mu = *reinterpret_cast<const float4*>(&st[0][0][c4]), rs = *reinterpret_cast<const float4*>(&st[0][1][c4]);
-    const float4 y = ldg4(y0 + (size_t)row * ld + c4);
+    const float4 y = *reinterpret_cast<const float4*>(tile + rl * 128 + c4);
     const float4 o = make_float4((y.x - mu.x) * rs.x, (y.y - mu.y) * rs.y, (y.z - mu.z) * rs.z, (y.w - mu.w) * rs.w);
     if (mode == 0) {
       st4(out + (size_t)row * 128 + c4, o);
       continue;
     }
     const float4 mu1 = *reinterpret_cast<const float4*>(&st[1][0][c4]), rs1 = *reinterpret_cast<const float4*>(&st[1][1][c4]);
-    const float4 ym = ldg4(y1 + (size_t)row * ld + c4);
+    const float4 ym = *reinterpret_cast<const float4*>(tile + (128 + rl) * 128 + c4);
     const float4 om = make_float4((ym.x - mu1.x) * rs1.x, (ym.y - mu1.y) * rs1.y, (ym.z - mu1.z) * rs1.z, (ym.w - mu1.w) * rs1.w);
     const float4 hh = ldg4(h + (size_t)row * 128 + c4);
     float4 r;
-    float t;
-    t = sigmoidf_(o.x); r.x = (1.f - t) * hh.x + t * swish(om.x);
-    t = sigmoidf_(o.y); r.y = (1.f - t) * hh.y + t * swish(om.y);
-    t = sigmoidf_(o.z); r.z = (1.f - t) * hh.z + t * swish(om.z);
-    t = sigmoidf_(o.w); r.w = (1.f - t) * hh.w + t * swish(om.w);
+    float tt;
+    tt = sigmoidf_(o.x); r.x = (1.f - tt) * hh.x + tt * swish(om.x);
+    tt = sigmoidf_(o.y); r.y = (1.f - tt) * hh.y + tt * swish(om.y);
+    tt = sigmoidf_(o.z); r.z = (1.f - tt) * hh.z + tt * swish(om.z);
+    tt = sigmoidf_(o.w); r.w = (1.f - tt) * hh.w + tt * swish(om.w);
     st4(out + (size_t)row * 128 + c4, r);
   }
 }
@@ -381,7 +396,14 @@ extern "C" int msmp_instnorm1_fwd(const float* y0, const float* y1, int ld, cons
                                   cudaStream_t stream) {
   if (N < 0 || B < 0 || (mode != 0 && mode != 1) || (ld & 3)) return MSMP_ERR_ARG;
   if (N == 0 || B == 0) return MSMP_OK;
-  k_in_fused_fwd<<<B, 256, 0, stream>>>(y0, y1, ld, chunk_begin, chunk_end, h, stat, out, B, mode, eps);
+  const int smem = (mode + 1) * 128 * 128 * (int)sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(k_in_fused_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 128 * 128 * 4) != cudaSuccess)
+      return MSMP_ERR_CUDA;
+    attr_set = true;
+  }
+  k_in_fused_fwd<<<B, 1024, smem, stream>>>(y0, y1, ld, chunk_begin, chunk_end, h, stat, out, B, mode, eps);
   MSMP_CHECK_LAUNCH();
   return MSMP_OK;
 }

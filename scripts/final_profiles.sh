@@ -8,4 +8,9 @@ python scripts/ncu_kernels.py > gpurun_out/r1f_plain_k.log 2>&1 && \
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_lem|k_wgrad_tc|k_linear_tc|k_edge_ws|k_segment_reduce" -c 24 -o gpurun_out/r1f_c2_kernels -f python scripts/ncu_kernels.py > gpurun_out/r1f_ncu_k.log 2>&1; echo "ncu c2 rc=$?"
 REPS=2 python scripts/edge_ticks.py > gpurun_out/r1f_plain_edge.log 2>&1 && \
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:k_edge_ws -s 2 -c 2 -o gpurun_out/r1f_edge_ws_large -f env REPS=2 python scripts/edge_ticks.py > gpurun_out/r1f_ncu_edge.log 2>&1; echo "ncu edge rc=$?"
-ls -la gpurun_out/
+
+python scripts/timeline.py > gpurun_out/r1f_timeline.txt 2>&1; rm -f gpurun_out/trace.json
+python scripts/bench_configs.py > gpurun_out/r1f_bench_configs.jsonl 2>&1
+python scripts/bench_large.py > gpurun_out/r1f_bench_large.jsonl 2>&1
+python scripts/edge_sweep.py > gpurun_out/r1f_edge_sweep.txt 2>&1
+ls -la gpurun_out/ | tail -25
