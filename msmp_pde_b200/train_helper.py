@@ -171,5 +171,72 @@ def test_unrolled_losses(model, steps: list, batch_size: int, nr_gt_steps: int, 
     return losses
 
 
+def _sq_norm_over_fields(t: torch.Tensor) -> torch.Tensor:
+    if t.dim() != 4:
+        raise ValueError("expected [B, n_t, d, n_x]")
+    return t.sum(dim=2)          # |.|^2 on R^d  ->  [B, n_t, n_x]
+
+
+def compute_spacetime_L2_norms(losses: torch.Tensor, norms: torch.Tensor):
+    """Absolute and relative error in L2(Omega x [0, T]) (experiments/train_helper.py:299-329).
+    ``losses = (pred - true)^2`` and ``norms = true^2``, both [B, n_t, d, n_x]; returns two scalars: the sample mean of
+    sqrt(mean over space and time of the squared R^d norm), and its ratio to the same functional of ``norms``."""
+    assert losses.shape == norms.shape, "loss and norms do not have the same shape"
+    err = _sq_norm_over_fields(losses).mean(dim=(1, 2)).sqrt().mean()
+    ref = _sq_norm_over_fields(norms).mean(dim=(1, 2)).sqrt().mean()
+    return err, err / ref
+
+
+def compute_space_L2_norms(losses: torch.Tensor, norms: torch.Tensor):
+    """Per time point: absolute and relative error in L2(Omega) (experiments/train_helper.py:331-360); returns two
+    [n_t] vectors (sample means)."""
+    assert losses.shape == norms.shape, "loss and norms do not have the same shape"
+    err = _sq_norm_over_fields(losses).mean(dim=2).sqrt().mean(dim=0)
+    ref = _sq_norm_over_fields(norms).mean(dim=2).sqrt().mean(dim=0)
+    return err, err / ref
+
+
+def compute_L2_norms(model, batch_size: int, nr_gt_steps: int, loader, graph_creator, device="cpu"):
+    """The metric the reference reports (experiments/train_helper.py:362-471): every trajectory is rolled out
+    autoregressively over its whole length (the prediction of one window is the next window's input), the squared
+    errors and squared targets of all windows are laid out as [B, n_t, d, n_x] and reduced with
+    ``compute_spacetime_L2_norms``.  Prints like the reference and returns ``(L2 error, relative L2 error)`` as floats."""
+    if f"{model}" != "GNN":
+        raise NotImplementedError("msmp_pde_b200.train_helper drives the GNN solvers only")
+    tw = graph_creator.tw
+    err_all, ref_all = [], []
+    for (u_base, u_super, x, variables) in loader:
+        bs = u_super.size(0)
+        d = u_super.size(2) if u_super.dim() == 4 else 1
+
+        def fields(t):          # [B * n_x, d * tw] -> [B, tw, d, n_x]
+            return t.reshape(bs, -1, d, tw).permute(0, 3, 2, 1)
+
+        err_w, ref_w = [], []
+        with torch.no_grad():
+            u_super, x = u_super.to(device), x.to(device)
+            steps = [tw * nr_gt_steps] * bs
+            data, labels = graph_creator.create_data(u_super, steps)
+            graph = graph_creator.create_graph(data, labels, x, variables, steps).to(device)
+            pred = model(graph)
+            err_w.append(fields(torch.square(pred - graph.y)))
+            ref_w.append(fields(torch.square(graph.y)))
+            for step in range(tw * (nr_gt_steps + 1), graph_creator.t_res - tw + 1, tw):
+                steps = [step] * bs
+                _, labels = graph_creator.create_data(u_super, steps)
+                graph = graph_creator.create_next_graph(graph, pred, labels, steps).to(device)
+                pred = model(graph)
+                err_w.append(fields(torch.square(pred - graph.y)))
+                ref_w.append(fields(torch.square(graph.y)))
+            if reset_state_bool(model):
+                model.embedding_lem.reset_states()
+        err_all.append(torch.cat(err_w, 1))
+        ref_all.append(torch.cat(ref_w, 1))
+    l2, l2_rel = compute_spacetime_L2_norms(torch.cat(err_all, 0), torch.cat(ref_all, 0))
+    print(f'L2 error {l2.item()}')
+    print(f'L2 relative error {100 * l2_rel.item()} %')
+    return l2.item(), l2_rel.item()
+
+
 test_timestep_losses.__test__ = False      # (named as in the reference; not pytest tests)
 test_unrolled_losses.__test__ = False

@@ -258,10 +258,47 @@ def training_loop_case(mg2):
     np.savez_compressed(os.path.join(os.path.dirname(__file__), "training_loop_ad.npz"), **_np(arrs))
 
 
+def l2_norms_case(mg2):
+    """The reference's evaluation metric (experiments/train_helper.py:299-471): compute_L2_norms of the full rollout of
+    the seeded AD trajectories of training_loop_case (same model, closed-form weights), and the two tensor helpers
+    compute_spacetime_L2_norms / compute_space_L2_norms on seeded [B, n_t, d, n_x] inputs."""
+    import common.utils as cu
+    import experiments.train_helper as th
+    from msmp_pde_b200.synth import SyntheticPDE
+    nt, nx, tw, B, nb = 120, 40, 25, 4, 3
+    pde = SyntheticPDE("AD", L=16.0, tmax=4.0, grid_size=(nt, nx))
+    g = torch.Generator().manual_seed(77)
+    loader = []
+    for _ in range(nb):          # the same draws as training_loop_case
+        traj = torch.randn(B, nt, 2, nx, generator=g, dtype=torch.float64)
+        x = torch.linspace(0.0, 16.0, nx, dtype=torch.float64).repeat(B, 1)
+        variables = {"a": 0.1 + 0.9 * torch.rand(B, generator=g, dtype=torch.float64),
+                     "b": 1.0 + 9.0 * torch.rand(B, generator=g, dtype=torch.float64)}
+        loader.append((traj, traj, x, variables))
+    model = mg2.MP_PDE_Solver2DLEMLinGated(pde, time_window=tw, hidden_features=128, hidden_layer=6,
+                                            eq_variables={"a": 1.0, "b": 1.0})
+    formula_weights_(model)
+    gc = cu.GraphCreator(pde=pde, neighbors=3, time_window=tw, t_resolution=nt, x_resolution=nx)
+    l2, l2_rel = th.compute_L2_norms(model, B, 1, loader, gc, "cpu")
+    print("compute_L2_norms", l2, l2_rel)
+    g2 = torch.Generator().manual_seed(78)
+    losses = torch.rand(5, 7, 2, 11, generator=g2, dtype=torch.float64)
+    norms = 0.5 + torch.rand(5, 7, 2, 11, generator=g2, dtype=torch.float64)
+    st, st_rel = th.compute_spacetime_L2_norms(losses, norms)
+    sp, sp_rel = th.compute_space_L2_norms(losses, norms)
+    np.savez_compressed(os.path.join(os.path.dirname(__file__), "l2_norms_ad.npz"),
+                        l2=np.array([l2, l2_rel]), losses=losses.numpy(), norms=norms.numpy(),
+                        spacetime=np.array([float(st), float(st_rel)]), space=sp.numpy(), space_rel=sp_rel.numpy())
+
+
 def main():
     mg, mg2 = _load_reference()
+    if "--l2-only" in sys.argv:
+        l2_norms_case(mg2)
+        return
     graph_cases()
     training_loop_case(mg2)
+    l2_norms_case(mg2)
     layer_case(mg, "GNN_Layer", 11, 25, 1, "layer_gnn.npz")
     layer_case(mg, "GNN_LayerLin", 12, 50, 3, "layer_gnnlin.npz")
     model_case(mg.MP_PDE_Solver, synth.config_c1, dict(B=3, nx=40), "mp_pde_c1.npz")

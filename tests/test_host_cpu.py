@@ -147,3 +147,19 @@ def test_unsupported_variants_fail_loudly():
                 models_gnn2D.G_PDE_Solver2DLEMLinGated):
         with pytest.raises(NotImplementedError):
             cls(pde, 25, 164, 6, {})
+
+
+def test_l2_norm_helpers_match_reference_functions():
+    """compute_spacetime_L2_norms / compute_space_L2_norms (experiments/train_helper.py:299-360) against the outputs
+    of the reference's own functions on seeded [B, n_t, d, n_x] inputs (tests/golden/l2_norms_ad.npz)."""
+    import numpy as np
+    import torch
+    from tests import golden_io
+    from msmp_pde_b200.train_helper import compute_space_L2_norms, compute_spacetime_L2_norms
+    g = golden_io.load("l2_norms_ad.npz")
+    losses, norms = torch.from_numpy(g["losses"]), torch.from_numpy(g["norms"])
+    a, r = compute_spacetime_L2_norms(losses, norms)
+    np.testing.assert_allclose([float(a), float(r)], g["spacetime"], rtol=1e-13)
+    a, r = compute_space_L2_norms(losses, norms)
+    np.testing.assert_allclose(a.numpy(), g["space"], rtol=1e-13)
+    np.testing.assert_allclose(r.numpy(), g["space_rel"], rtol=1e-13)

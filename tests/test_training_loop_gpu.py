@@ -74,3 +74,31 @@ def test_unrolled_losses_match_reference():
     got = losses.detach().double().cpu()
     assert got.shape == want.shape
     assert float((got - want).abs().max()) < 2e-5 * float(want.abs().max()), (got, want)      # three chained windows
+
+
+def test_compute_L2_norms_match_reference():
+    """The reference's reported metric (experiments/train_helper.py:362-471): full rollout + space-time L2 norms, against
+    the values its own compute_L2_norms returns on the same trajectories (float64 CPU fixture)."""
+    from msmp_pde_b200 import models_gnn2D
+    from msmp_pde_b200.graph_creator import GraphCreator
+    from msmp_pde_b200.synth import SyntheticPDE
+    from msmp_pde_b200.train_helper import compute_L2_norms
+    torch.set_default_dtype(torch.float64)
+    dev = torch.device("cuda:0")
+    g = golden_io.load("training_loop_ad.npz")
+    want = golden_io.load("l2_norms_ad.npz")["l2"]
+    nt, nx, tw, B = 120, 40, 25, 4
+    pde = SyntheticPDE("AD", L=16.0, tmax=4.0, grid_size=(nt, nx))
+    loader = []
+    for i in range(3):
+        traj = torch.from_numpy(g[f"traj{i}"])
+        loader.append((traj, traj, torch.from_numpy(g[f"x{i}"]),
+                       {"a": torch.from_numpy(g[f"a{i}"]), "b": torch.from_numpy(g[f"b{i}"])}))
+    model = models_gnn2D.MP_PDE_Solver2DLEMLinGated(pde, time_window=tw, hidden_features=128, hidden_layer=6,
+                                                    eq_variables={"a": 1.0, "b": 1.0})
+    formula_weights_(model)
+    model = model.to(dev)
+    gc = GraphCreator(pde=pde, neighbors=3, time_window=tw, t_resolution=nt, x_resolution=nx)
+    l2, l2_rel = compute_L2_norms(model, B, 1, loader, gc, dev)
+    assert abs(l2 - want[0]) < 2e-5 * want[0], (l2, want)
+    assert abs(l2_rel - want[1]) < 2e-5 * want[1], (l2_rel, want)
