@@ -1,7 +1,7 @@
 """Diagnostic: per-parameter gradient error of the CUDA model vs the fp64 oracle, next to the error of an
 honest fp32 torch run of the oracle itself (the fp32 floor).  Not part of the product."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 torch.backends.cudnn.allow_tf32 = False
 torch.backends.cuda.matmul.allow_tf32 = False

@@ -1,7 +1,7 @@
 """Diagnostic: worst gradient-allowance excess of the CUDA variant models next to an honest fp32 torch run of the
 oracle variant (the fp32 floor) on the golden inputs.  Not part of the product."""
 import sys, os, copy
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 torch.backends.cudnn.allow_tf32 = False
 torch.backends.cuda.matmul.allow_tf32 = False

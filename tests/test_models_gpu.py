@@ -107,7 +107,7 @@ from tests.test_oracle_golden import VARIANTS_1F, VARIANTS_2F, variant_eq  # noq
 
 
 # Two variants are ill-conditioned on their fixture: an honest fp32 torch evaluation of the oracle graph itself
-# (scripts/diag_variants.py, cuDNN/cuBLAS TF32 off) exceeds the rtol-1e-5 allowance by 1.0x (MP_PDE_SolverGated) and
+# (tests/diag/diag_variants.py, cuDNN/cuBLAS TF32 off) exceeds the rtol-1e-5 allowance by 1.0x (MP_PDE_SolverGated) and
 # 3.6x (the G^2 gate squares differences of activations).  Their allowance is widened to ~2x that fp32 floor.
 VARIANT_FLOOR = {"MP_PDE_SolverGated": 2.0, "MP_PDE_Solver2DLEMLinG2": 8.0}
 
