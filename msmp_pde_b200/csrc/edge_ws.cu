@@ -38,8 +38,6 @@ constexpr int EW_MMA_WARP = EW_EPI_WARPS + EW_PROD_WARPS;
 // registers each; the MMA warpgroup hands registers to the producers with setmaxnreg (40 / 120), whose two float4
 // register sets would otherwise spill.
 constexpr int EW_THREADS = 32 * (EW_MMA_WARP + 4);
-template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
-template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 constexpr int EW_SLOTS = 8;                            // index ring (tiles): a slot is rewritten 7 tiles later, when the
                                                        // epilogue that read it has long finished
 constexpr int EW_DST_LD = 132;                         // dst[-1 .. 128] of a tile (+ padding)
@@ -63,19 +61,6 @@ struct EdgeWsParams {
   int E; int T; int N;
 };
 
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// A operand from tensor memory (lane = row m, one 32-bit column per k), B from a shared-memory descriptor
-__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
-                                             uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
 // Activations on the MUFU pipe: sigmoid(x) = rcp(1 + ex2(-x log2 e)), 5 instructions per swish instead of the 13 of
 // the expf-based common.cuh version (the two roles of this kernel are instruction-issue bound: ncu shows 58 % issue
 // slots busy with 31 % of the warp slots occupied).  ex2.approx / rcp.approx are 1-2 ulp; the one extra error, the
@@ -91,18 +76,6 @@ __device__ __forceinline__ float swish_m(float x) { return x * sigmoid_mufu(x); 
 __device__ __forceinline__ float dswish_m(float x) {
   const float sg = sigmoid_mufu(x);
   return sg * (1.0f + x * (1.0f - sg));
-}
-// Polling with a 100 ns back-off: the waiting lanes of 17 warps share four schedulers with the working warps
-// (the 20 ns loop of mbar_wait cost 17 % of the kernel's issued instructions).  Bounded: a bug traps after ~2 s.
-__device__ __forceinline__ void ew_wait(uint64_t* bar, uint32_t parity) {
-  if ((threadIdx.x & 31) == 0 && !mbar_try_wait(bar, parity)) {
-    uint32_t n = 0;
-    while (!mbar_try_wait(bar, parity)) {
-      __nanosleep(100);
-      if (++n > 20000000u) __trap();
-    }
-  }
-  __syncwarp();
 }
 __device__ __forceinline__ void producer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(EW_PROD_THREADS) : "memory"); }
 
@@ -199,8 +172,8 @@ __global__ void __launch_bounds__(EW_THREADS, 1) k_edge_ws(const EdgeWsParams p)
       const int valid = min(EW_TILE, p.E - e0);
       const int buf = i & 1;
       const int* sd = s_dst + (i & (EW_SLOTS - 1)) * EW_DST_LD + 1;
-      EW_TIMED(t_acc, ew_wait(&acc_full[buf], (i >> 1) & 1));
-      if (BWD) EW_TIMED(t_s, ew_wait(s_full, i & 1));
+      EW_TIMED(t_acc, mbar_wait_backoff(&acc_full[buf], (i >> 1) & 1));
+      if (BWD) EW_TIMED(t_s, mbar_wait_backoff(s_full, i & 1));
       tc_fence_after();
       // Destination-segment sums: running sums in registers.  The segment boundaries are warp-uniform bit masks
       // (ballots over the tile's destination indices incl. the two neighbouring edges), the element-wise math of a
@@ -299,7 +272,7 @@ __global__ void __launch_bounds__(EW_THREADS, 1) k_edge_ws(const EdgeWsParams p)
     reg_dec<40>();
     if (warp == EW_MMA_WARP) {
     constexpr uint32_t IDESC = umma_idesc_tf32(128, 128, 0, 0);
-    ew_wait(w_full, 0);
+    mbar_wait_backoff(w_full, 0);
     tc_fence_after();
     const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
     const bool leader = elect_one();
@@ -311,12 +284,12 @@ __global__ void __launch_bounds__(EW_THREADS, 1) k_edge_ws(const EdgeWsParams p)
 #pragma unroll 1
     for (int i = 0; i < ntile; ++i) {
       const int buf = i & 1;
-      if (i >= 2) EW_TIMED(t_ae, ew_wait(&acc_empty[buf], ((i >> 1) - 1) & 1));
+      if (i >= 2) EW_TIMED(t_ae, mbar_wait_backoff(&acc_empty[buf], ((i >> 1) - 1) & 1));
       tc_fence_after();
       const uint32_t acc = tm + EW_ACC + 128 * buf;
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
-        EW_TIMED(t_full, ew_wait(&full[s], ph));
+        EW_TIMED(t_full, mbar_wait_backoff(&full[s], ph));
         tc_fence_after();
         const uint32_t b_hi = smem_u32(smB + s * EW_STAGE_BYTES), b_lo = b_hi + IMG_BYTES;
 #pragma unroll
@@ -418,7 +391,7 @@ __global__ void __launch_bounds__(EW_THREADS, 1) k_edge_ws(const EdgeWsParams p)
       const int slot = i & (EW_SLOTS - 1);
       if (!BWD || j < 4) {
         // ---- operand chunk -> ring stage
-        if (nfill >= EW_STAGES) EW_TIMED(t_empty, ew_wait(&empty[s], ph ^ 1));
+        if (nfill >= EW_STAGES) EW_TIMED(t_empty, mbar_wait_backoff(&empty[s], ph ^ 1));
         uint8_t* st = smB + s * EW_STAGE_BYTES;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -445,7 +418,7 @@ __global__ void __launch_bounds__(EW_THREADS, 1) k_edge_ws(const EdgeWsParams p)
         }
       } else {
         // ---- backward: z1 chunk -> a1 (global), sw'(z1) (shared tile for the epilogue)
-        if (j == 4 && i >= 1) EW_TIMED(t_se, ew_wait(s_empty, (i - 1) & 1));
+        if (j == 4 && i >= 1) EW_TIMED(t_se, mbar_wait_backoff(s_empty, (i - 1) & 1));
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int r = (pt >> 3) + 32 * q;

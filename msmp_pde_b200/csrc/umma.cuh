@@ -181,4 +181,34 @@ __device__ __forceinline__ void store_split4(uint8_t* hi_img, uint8_t* lo_img, u
 
 constexpr int IMG_BYTES = 128 * 32 * 4;      // one [128 x 32 fp32] tile image = 16 KiB
 
+// ---- helpers of the warp-specialised kernels (edge_ws.cu, linear_tc.cu: k_linear_ws) ---------------------------------
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// A operand from tensor memory (lane = row m, one 32-bit column per k), B from a shared-memory descriptor
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Polling with a 100 ns back-off: the waiting lanes of 17 warps share four schedulers with the working warps
+// (the 20 ns loop of mbar_wait cost 17 % of the kernel's issued instructions).  Bounded: a bug traps after ~2 s.
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+  if ((threadIdx.x & 31) == 0 && !mbar_try_wait(bar, parity)) {
+    uint32_t n = 0;
+    while (!mbar_try_wait(bar, parity)) {
+      __nanosleep(100);
+      if (++n > 20000000u) __trap();
+    }
+  }
+  __syncwarp();
+}
+// setmaxnreg: a warpgroup (4 warps, all of them) hands registers back to / takes registers from the CTA's pool
+template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+
 }  // namespace msmp

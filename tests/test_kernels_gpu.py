@@ -130,6 +130,32 @@ def test_linear_fwd_plain_and_strided(dev):
     assert rel_err(y, ref) < TOL
 
 
+def test_linear_ws_equals_linear_tc(dev):
+    """The persistent warp-specialised linear kernel (used from two tiles per SM on) runs the same MMAs and the same
+    epilogue as k_linear_tc: bit-identical outputs.  M is chosen so that the default dispatch picks it (320 row tiles
+    x 2 column tiles, ragged last tile)."""
+    from msmp_pde_b200 import ops
+    g = torch.Generator().manual_seed(21)
+    M = 128 * 320 - 37
+    A0, A1 = torch.randn(M, 128, generator=g).to(dev), torch.randn(M, 64, generator=g).to(dev)
+    Wt = (torch.randn(192, 256, generator=g) / 14).to(dev)
+    bias, side, Ws = torch.randn(256, generator=g).to(dev), torch.randn(M, 8, generator=g).to(dev), torch.randn(8, 256, generator=g).to(dev)
+    R, Z = torch.randn(M, 256, generator=g).to(dev), torch.randn(M, 256, generator=g).to(dev)
+    ypre = torch.empty(M, 256, device=dev)
+    y_ws = ops.linear_fwd([A0, A1], Wt, bias=bias, side=side, r=3, Wside=Ws, Zmul=Z, Ypre=ypre, act=True, R=R, aswish=[1, 0])
+    ref = (torch.cat([_sw(A0.double()), A1.double()], 1) @ Wt.double() + bias.double() + side.double()[:, :3] @ Ws.double()[:3]) \
+        * _dsw(Z.double())
+    assert rel_err(ypre, ref) < TOL
+    assert rel_err(y_ws, _sw(ref) + R.double()) < TOL
+    # the single-tile kernel on the same rows, 100 tiles at a time (below the dispatch threshold)
+    for lo in range(0, M, 128 * 50):
+        hi = min(M, lo + 128 * 50)
+        yp = torch.empty(hi - lo, 256, device=dev)
+        y_tc = ops.linear_fwd([A0[lo:hi], A1[lo:hi]], Wt, bias=bias, side=side[lo:hi], r=3, Wside=Ws, Zmul=Z[lo:hi], Ypre=yp,
+                              act=True, R=R[lo:hi], aswish=[1, 0])
+        assert torch.equal(y_tc, y_ws[lo:hi]) and torch.equal(yp, ypre[lo:hi])
+
+
 @pytest.mark.parametrize("M,K,Nout", [(1000, 192, 256), (130, 128, 128), (5000, 160, 384), (40, 64, 128)])
 def test_linear_wgrad(dev, gemm_mode, M, K, Nout):
     from msmp_pde_b200 import ops
