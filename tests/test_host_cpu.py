@@ -22,6 +22,8 @@ def test_workspace_queries_are_host_only():
     assert _lib.lib.msmp_edge_tiles(9408) == 74
     assert _lib.lib.msmp_edge_fwd_workspace(9408) == 74 * 2 * 128 * 4
     assert _lib.lib.msmp_linear_wgrad_splits(100000, 128, 128) >= 148
+    assert _lib.lib.msmp_linear_wgrad_splits(6400, 128, 256) == 25          # at least 256 rows per split
+    assert _lib.lib.msmp_edge_ws_workspace(9408) == 74 * 2 * 2 * 128 * 4      # two 64-edge units per tile
 
 
 def test_radius_graph_matches_bruteforce_and_closed_form():
@@ -85,6 +87,11 @@ def test_topology_bit_exact_vs_numpy():
         for c0, c1 in zip(cb, ce):
             assert len(set(batch[c0:c1].tolist())) == 1
         assert t.graph_chunk_ptr.tolist() == [0, 1, 4, 5, 7]
+        # per-edge scale streamed by the backward edge kernel; the one-launch InstanceNorm needs <= 128-node graphs
+        assert np.array_equal(t.inv_deg_e.numpy(), (1.0 / deg).astype(np.float32)[d_sorted])
+        assert not t.one_chunk_per_graph
+    small = build_topology(ei[:, ei[1] < 23], batch[:23], 23)
+    assert small.one_chunk_per_graph and small.nchunks == small.B == 1
 
 
 def test_no_cpu_fallback():
