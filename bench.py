@@ -211,7 +211,7 @@ def run_ours(args):
             ach = d["flops"] / (d["ms"] * 1e-3) / 1e12
             roof = {"kernel": "k_" + dom, "bound": "tensor", "achieved": round(ach, 3),
                     "peak": peaks["tensor_tflops"], "unit": "TFLOP/s", "frac": round(ach / peaks["tensor_tflops"], 5),
-                    "traffic": None, "avg_launch_ms": round(d["ms"] / max(d["n"], 1), 5),
+                    "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH.get(dom), "avg_launch_ms": round(d["ms"] / max(d["n"], 1), 5),
                     "share_of_step": round(d["ms"] / sum(v["ms"] for v in kern.values()), 4),
                     "eager_step_ms": round(eager_ms, 4),
                     "peak_source": peaks["source"],
@@ -281,6 +281,13 @@ def scatter_bandwidth(dev, n_nodes=1 << 20, degree=6, reps=10):
             "contiguous_gbs": res["contiguous"]["gbs"], "contiguous_frac": round(res["contiguous"]["gbs"] / peak, 4),
             "permuted_gbs": res["permuted"]["gbs"], "permuted_frac": round(res["permuted"]["gbs"] / peak, 4),
             "peak_gbs": peak}
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of the C2 shapes
+# (profiles/r1_final_kernels_ncu_raw.csv): the step's 53 weight-gradient launches are 36 node-level (9.9 MB), 12 edge-level
+# (38.6 MB), the two LEM ones (355 MB, 190 MB) and 3 small ones -> 25.7 MB on average, against 4 * M * (K + N) bytes
+# of operands (the algorithmic traffic: every operand element is read once).
+NCU_TRAFFIC_BYTES_PER_LAUNCH = {"wgrad_tc": 25.7e6}
 
 
 def message_bandwidth(dev, n_nodes=1 << 20, degree=6, reps=7):
