@@ -220,6 +220,24 @@ int msmp_lem_tc_bwd(const float* Wzh_img, const float* Wh_img, const float* Y, c
 /* out[i] = g[i] * swish'(z[i])  (n % 4 == 0) */
 int msmp_mul_dswish(const float* g, const float* z, float* out, size_t n, cudaStream_t stream);
 
+/* ---- optimizer step of the captured training step ---------------------------------------------------------------
+ * torch.optim.AdamW semantics (experiments/train.py:410; decoupled weight decay, no amsgrad / maximize) over any number
+ * of tensors in ONE launch, every hyper-parameter read from DEVICE memory so that a CUDA-graph replay follows the
+ * scheduler (train.py:411,437 rewrites param_group['lr'] only).  jobs_dev: records {float* p, *g, *m, *v; int n, group}
+ * (msmp_adamw_job_bytes() each; m / v are the optimizer's own exp_avg / exp_avg_sq).  chunks_dev: int2 {job, first
+ * element}, one per CTA, msmp_adamw_chunk() elements each.  hyper_dev: msmp_adamw_hyper_floats() floats per param group
+ * = {lr, beta1, beta2, eps, weight_decay, 1 - beta1^t, sqrt(1 - beta2^t), 0}.  gscale_dev (may be NULL): device scalar
+ * every gradient is multiplied by first (and written back), e.g. 1 / (2 sqrt(SSE)) of loss = sqrt(SSE),
+ * experiments/train_helper.py:126,138. */
+int msmp_adamw_job_bytes(void);
+int msmp_adamw_chunk(void);
+int msmp_adamw_hyper_floats(void);
+int msmp_adamw_run(const void* jobs_dev, const void* chunks_dev, int nchunks, const float* hyper_dev,
+                   const float* gscale_dev, cudaStream_t stream);
+/* loss = sqrt(sse_hi_lo[0] + sse_hi_lo[1]) (double), gscale = 0.5 / loss: the two scalars of a step whose summed squared
+ * error arrives as a float pair (hi + lo) -- the last two elements of the all-reduced gradient bucket. */
+int msmp_loss_scalars(const float* sse_hi_lo, double* loss, float* gscale, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

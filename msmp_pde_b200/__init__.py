@@ -30,6 +30,10 @@ def install():
     sys.modules["experiments.models_gnn"] = models_gnn
     sys.modules["experiments.models_gnn2D"] = models_gnn2D
     pkg.models_gnn, pkg.models_gnn2D = models_gnn, models_gnn2D
+    # the native extension of the reference's own LEM classes (models_gnn.py:287-302) -- only if it is missing
+    if "lem_cuda" not in sys.modules:
+        from .compat import lem_cuda
+        sys.modules["lem_cuda"] = lem_cuda
     # the step in front of the models: vectorised, device-capable GraphCreator with a cached topology
     # (common/utils.py:267-471); patched in when the reference checkout is importable
     try:
@@ -38,3 +42,46 @@ def install():
         cu.GraphCreator = GraphCreator
     except Exception:      # reference not on sys.path (or its own imports unavailable): nothing to patch
         pass
+    _install_train_helper(pkg)
+
+
+def _install_train_helper(pkg) -> None:
+    """``from experiments.train_helper import *`` (train.py:21, cv.py:17, eval.py:15) must hand the scripts this package's
+    loops for the GNN solvers -- the captured training step and the device-side rollouts -- and the reference's own
+    functions for everything else (FNO / CNN baselines, deprecated helpers)."""
+    import sys
+    import types
+
+    from . import train_helper as ours
+
+    ref = None
+    try:
+        import importlib
+        sys.modules.pop("experiments.train_helper", None)
+        ref = importlib.import_module("experiments.train_helper")          # needs the reference checkout on sys.path
+    except Exception:
+        ref = None
+    mod = types.ModuleType("experiments.train_helper")
+    if ref is not None:
+        mod.__dict__.update({k: v for k, v in ref.__dict__.items() if not k.startswith("__")})
+
+    def dispatch(name):
+        mine = getattr(ours, name)
+        theirs = getattr(ref, name, None) if ref is not None else None
+
+        def fn(model, *a, **k):
+            if theirs is None or f"{model}" == "GNN":
+                return mine(model, *a, **k)
+            return theirs(model, *a, **k)
+        fn.__name__ = name
+        fn.__doc__ = mine.__doc__
+        fn.__test__ = False
+        return fn
+
+    for name in ("training_loop", "test_timestep_losses", "test_unrolled_losses", "compute_L2_norms"):
+        setattr(mod, name, dispatch(name))
+    for name in ("reset_state_bool", "compute_spacetime_L2_norms", "compute_space_L2_norms"):
+        setattr(mod, name, getattr(ours, name))
+    mod.unflatten_u = sys.modules["experiments.models_gnn2D"].unflatten_u
+    sys.modules["experiments.train_helper"] = mod
+    pkg.train_helper = mod

@@ -72,6 +72,11 @@ _SIGS = {
     "msmp_decoder_bwd": (I, [P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, P, S, P]),
     "msmp_lem_tc_fwd": (I, [P, I, P, P, P, P, P, P, P, P, P, F, I, I, I, P]),
     "msmp_lem_tc_bwd": (I, [P, P, P, P, P, P, P, I, P, P, P, P, F, I, I, I, I, I, P]),
+    "msmp_adamw_job_bytes": (I, []),
+    "msmp_adamw_chunk": (I, []),
+    "msmp_adamw_hyper_floats": (I, []),
+    "msmp_adamw_run": (I, [P, P, I, P, P, P]),
+    "msmp_loss_scalars": (I, [P, P, P, P]),
     "msmp_lem_gate_z": (I, [P, P, F, P, P, I, P]),
     "msmp_lem_gate_y": (I, [P, P, P, P, I, P]),
     "msmp_lem_bwd_y": (I, [P, P, P, P, F, P, P, I, P]),

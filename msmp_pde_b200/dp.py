@@ -39,3 +39,42 @@ def shard_graph(data, rank: int, world: int):
         else:
             setattr(out, k, v)
     return out
+
+
+def dp_selfcheck(make_model, make_optimizer, data_global, device, group=None, use_graph: bool = True) -> dict:
+    """One training step of the SAME global batch two ways on every rank -- data parallel over the ranks' graph shards
+    (one NCCL all-reduce of the gradient bucket) and as a single-process full-batch step -- and how far they differ:
+    the loss, the gradient of the loss (``param.grad`` after the step) and the updated weights.  The two differ only by
+    the order of the floating-point sums (per-rank partial sums, then the all-reduce).  ``make_model()`` must build
+    identically initialised models (seed inside).  Returns maxima over all ranks.
+
+    AdamW's first update is ``lr * g / (|g| + eps)``: an entry whose gradient is numerically zero may flip its sign
+    between the two evaluations, so the weights are reported as the largest difference in units of ``lr`` (<= 2 by
+    construction) and as the fraction of entries that moved differently by more than ``1e-3 lr``."""
+    import torch.distributed as dist
+
+    from .train_step import GraphedTrainStep
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    shard = shard_graph(data_global, rank, world).to(device)
+    full = data_global.clone().to(device)
+    out = {}
+    res = []
+    for graph, grp in ((shard, group), (full, False)):
+        model = make_model().to(device)
+        opt = make_optimizer(model)
+        step = GraphedTrainStep(model, opt, graph, group=grp, warmup=1, use_graph=use_graph, preserve_state=True)
+        loss = step(graph)
+        torch.cuda.synchronize()
+        res.append((float(loss), step.bucket.flat[:step.bucket.n].detach().double().clone(),
+                    torch.cat([p.detach().reshape(-1) for p in model.parameters()]).double(),
+                    float(opt.param_groups[0]["lr"])))
+        del step, model, opt
+    (l_dp, g_dp, w_dp, lr), (l_1, g_1, w_1, _) = res
+    dw = (w_dp - w_1).abs()
+    vals = torch.tensor([abs(l_dp - l_1) / abs(l_1), float((g_dp - g_1).abs().max() / g_1.abs().max()),
+                         float(dw.max()) / lr, float((dw > 1e-3 * lr).double().mean())], dtype=torch.float64,
+                        device=device)
+    dist.all_reduce(vals, op=dist.ReduceOp.MAX, group=group)
+    out = {"loss_rel_err": float(vals[0]), "grad_max_rel_err": float(vals[1]), "weight_max_abs_err_over_lr": float(vals[2]),
+           "weight_mismatch_frac": float(vals[3]), "world": world, "graphs_global": int(data_global.batch.max()) + 1}
+    return out

@@ -7,7 +7,7 @@ The topology is constant across the 6-12 layer calls of a forward pass and acros
 computed once per ``edge_index`` tensor and cached on its identity.
 
 All index work is integer and exact; it is cross-checked bit-for-bit against a numpy restatement in
-tests/test_graph_construction.py.
+tests/test_host_cpu.py (CSR / CSC arrays) and tests/test_graph_creator.py (edge lists).
 """
 from __future__ import annotations
 

@@ -37,6 +37,7 @@ class GraphCreator(nn.Module):
         assert isinstance(self.n, int)
         assert isinstance(self.tw, int)
         self._topo_cache: dict = {}
+        self._topo_ident: dict = {}
 
     # ------------------------------------------------------------------------------------------------
     def create_data(self, datapoints: torch.Tensor, steps: list):
@@ -67,12 +68,25 @@ class GraphCreator(nn.Module):
         steps_t = torch.as_tensor(steps).long().cpu()
         return (torch.ones(nx, dtype=t.dtype)[None, :] * t[steps_t][:, None]).reshape(-1).to(device=device, dtype=dtype)
 
-    def _topology(self, x0: torch.Tensor, B: int):
-        """(edge_index, batch) for B copies of the grid x0 -- built once per grid / batch size / device."""
-        key = (x0.device.type, x0.device.index, B, self.n, self._name(),
-               bool(getattr(self.pde, "untructured_grid", False)), x0.dtype, x0.detach().cpu().numpy().tobytes())
+    def _topology(self, x0: torch.Tensor, B: int, x_src: torch.Tensor = None):
+        """(edge_index, batch) for B copies of the grid x0 -- built once per grid / batch size / device.
+        The cache key holds the grid's bytes.  They are taken from ``x_src`` (the caller's coordinate tensor) when that
+        still lives on the host -- no device round trip; a device-resident ``x_src`` is recognised by object identity
+        (a strong reference is kept, so its address cannot be recycled) and hashed with one blocking copy otherwise."""
+        head = (x0.device.type, x0.device.index, B, self.n, self._name(),
+                bool(getattr(self.pde, "untructured_grid", False)), x0.dtype)
+        if x_src is not None and x_src.is_cuda:
+            ent = self._topo_ident.get(id(x_src))
+            if ent is not None and ent[0] is x_src and ent[1] == x_src._version and ent[2] == head:
+                return ent[3]
+        grid = x_src[0] if (x_src is not None and not x_src.is_cuda) else x0
+        key = head + (grid.detach().to(x0.dtype).cpu().numpy().tobytes(),)
         hit = self._topo_cache.get(key)
         if hit is not None:
+            if x_src is not None and x_src.is_cuda:
+                if len(self._topo_ident) > 16:
+                    self._topo_ident.clear()
+                self._topo_ident[id(x_src)] = (x_src, x_src._version, head, hit)
             return hit
         nx = x0.numel()
         dev = x0.device
@@ -92,6 +106,8 @@ class GraphCreator(nn.Module):
         else:
             raise Exception("Wrong experiment")
         self._topo_cache[key] = (edge_index, batch)
+        if x_src is not None and x_src.is_cuda:
+            self._topo_ident[id(x_src)] = (x_src, x_src._version, head, (edge_index, batch))
         return edge_index, batch
 
     @staticmethod
@@ -117,7 +133,7 @@ class GraphCreator(nn.Module):
         xdt = torch.promote_types(torch.get_default_dtype(), x0.dtype)
         x_pos = x0.repeat(B).to(xdt)
         t_pos = self._times(steps, nx, dev, torch.get_default_dtype())
-        edge_index, batch = self._topology(x0, B)
+        edge_index, batch = self._topology(x0, B, x)
 
         graph = Data(x=u, edge_index=edge_index)
         graph.y = y

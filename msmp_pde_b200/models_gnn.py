@@ -17,8 +17,30 @@ from .lem import LEM, LEMS, LEMcuda  # noqa: F401 (re-exported)
 from .solver import (cumulative_dt, decode, linear_act, make_decoder, mlp2, pad_cols, require_cuda, variables_1field)
 
 
+class _LSTMNoTF32Fn(torch.autograd.Function):
+    """cuDNN LSTM with TF32 off in BOTH directions and the process-wide flag left as the caller set it: the forward and
+    the backward each run inside ``torch.backends.cudnn.flags(allow_tf32=False)`` (a plain context manager around the
+    module call would have closed before autograd runs the backward kernels)."""
+
+    @staticmethod
+    def forward(ctx, x, rnn, *params):
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False), torch.enable_grad():
+            out, _ = rnn(x.detach())
+        ctx.out, ctx.params = out, params
+        return out.detach()
+
+    @staticmethod
+    def backward(ctx, gout):
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+            grads = torch.autograd.grad(ctx.out, ctx.params, gout.contiguous(), allow_unused=True)
+        ctx.out = None
+        return (None, None) + tuple(grads)
+
+
 class LSTM(nn.Module):
-    """models_gnn.py:758-767 (cuDNN LSTM encoder of the LSTM variants; not on the BASELINE path)."""
+    """models_gnn.py:758-767 (cuDNN LSTM encoder of the LSTM variants; not on the BASELINE path).  fp32 parity needs
+    cuDNN's TF32 RNN kernels off; that is scoped to this module's own forward / backward (_LSTMNoTF32Fn).  The inputs
+    carry no gradient in the reference either (they are built from data)."""
 
     def __init__(self, ninp, nhid):
         super().__init__()
@@ -26,10 +48,7 @@ class LSTM(nn.Module):
         self.rnn = nn.LSTM(ninp, nhid, dtype=torch.float32)
 
     def forward(self, input):
-        # fp32 parity: cuDNN's RNN kernels default to TF32 (forward here, backward later from autograd), so the flag
-        # is cleared process-wide rather than in a context manager that would have closed before backward runs.
-        torch.backends.cudnn.allow_tf32 = False
-        output, _ = self.rnn(input.float())
+        output = _LSTMNoTF32Fn.apply(input.float(), self.rnn, *self.rnn.parameters())
         return output[-1]
 
 

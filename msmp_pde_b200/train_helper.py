@@ -4,11 +4,12 @@ Same signature, same order of ``random`` draws (number of unrollings, then the s
 (``:106-112``: the unrolled predictions are computed without gradients and fed back through
 ``create_next_graph``), same loss ``sqrt(criterion(pred, graph.y))`` and the same returned ``losses / batch_size``.
 
-What differs is the execution of the gradient step: when the optimizer is capturable (``torch.optim.AdamW(...,
-capturable=True)``) and the graphs keep one topology (fixed grid and batch size, which is what ``GraphCreator``
-produces), forward + loss + backward + optimizer update run as ONE CUDA-graph replay (``GraphedTrainStep``); the
-graph fields are copied into its static buffers.  With any other optimizer the step runs eagerly -- still on the CUDA
-kernels -- exactly like the reference loop.
+What differs is the execution of the gradient step: with the optimizer the reference's scripts build
+(``optim.AdamW(model.parameters(), lr=args.lr)``, experiments/train.py:410 -- or any capturable optimizer) and graphs
+that keep one topology (fixed grid and batch size, which is what ``GraphCreator`` produces), forward + loss + backward
++ optimizer update run as ONE CUDA-graph replay (``GraphedTrainStep``); the graph fields are copied into its static
+buffers and the optimizer's hyper-parameters are re-read every step, so ``MultiStepLR`` (train.py:411,437) acts as in the
+reference.  Otherwise the step runs eagerly -- still on the CUDA kernels -- exactly like the reference loop.
 """
 from __future__ import annotations
 
@@ -16,6 +17,7 @@ import random
 
 import torch
 
+from . import optim as moptim
 from .models_gnn import MP_PDE_SolverLEMLinGatedSave
 from .train_step import GraphedTrainStep
 
@@ -37,16 +39,17 @@ def training_loop(model: torch.nn.Module, unrolling: list, batch_size: int, opti
     if f"{model}" != "GNN":
         raise NotImplementedError("msmp_pde_b200.train_helper.training_loop drives the GNN solvers only")
     capturable = bool(optimizer.param_groups and all(g.get("capturable", False) for g in optimizer.param_groups))
-    fused_step = capturable and _is_sum_mse(criterion) and not reset_state_bool(model) \
-        and torch.device(device).type == "cuda"
+    fused_step = torch.device(device).type == "cuda" and _is_sum_mse(criterion) and not reset_state_bool(model) \
+        and (capturable or moptim.supported(optimizer))
     cache = model.__dict__.setdefault("_msmp_graphed_steps", {})
     losses = []
     for (u_base, u_super, x, variables) in loader:
         if not fused_step:
             optimizer.zero_grad()          # (the captured step overwrites every gradient; its buffers must stay allocated)
         # graphs are built on the target device: the creator then hands out the same device-resident edge list for
-        # every batch and the model's topology cache / the captured step are reused
-        u_super, x = u_super.to(device), x.to(device)
+        # every batch and the model's topology cache / the captured step are reused.  The grid coordinates x stay on
+        # the host: the creator keys its topology cache on their bytes (no device round trip) and moves one row itself.
+        u_super = u_super.to(device)
         # Randomly choose number of unrollings, then the starting (time) points on the solution manifold
         unrolled_graphs = random.choice(unrolling)
         steps = [t for t in range(graph_creator.tw,
@@ -63,16 +66,17 @@ def training_loop(model: torch.nn.Module, unrolling: list, batch_size: int, opti
                 graph = graph_creator.create_next_graph(graph, pred, labels, random_steps).to(device)
 
         if fused_step:
-            key = (id(optimizer), id(graph.edge_index), tuple(graph.x.shape))
+            # keyed on the storage and size of the topology (Python ids are recycled); the step itself verifies that
+            # a graph arriving under the same key really has the captured edge list (GraphedTrainStep._check_topology)
+            ei = graph.edge_index
+            key = (id(optimizer), ei.data_ptr(), int(ei.shape[1]), tuple(graph.x.shape), str(ei.device))
             step = cache.get(key)
+            if step is not None and step.opt is not optimizer:
+                step = None
             if step is None:
-                # the constructor runs its warm-up steps on a scratch copy of the state so that this call still
-                # performs exactly one optimizer update
-                state = ({k: v.detach().clone() for k, v in model.state_dict().items()},
-                         _clone_opt_state(optimizer))
-                step = GraphedTrainStep(model, optimizer, graph, warmup=1)
-                model.load_state_dict(state[0])
-                _restore_opt_state(optimizer, state[1])
+                # the constructor's warm-up steps run on a snapshot of parameters and optimizer state, so that this
+                # call still performs exactly one optimizer update
+                step = GraphedTrainStep(model, optimizer, graph, warmup=1, preserve_state=True)
                 cache[key] = step
             loss = step(graph).to(graph.x.dtype)
             losses.append(loss.detach().clone() / batch_size)
@@ -88,25 +92,6 @@ def training_loop(model: torch.nn.Module, unrolling: list, batch_size: int, opti
     return torch.stack(losses)
 
 
-def _clone_opt_state(optimizer):
-    return {id(p): {k: (v.detach().clone() if torch.is_tensor(v) else v) for k, v in st.items()}
-            for p, st in optimizer.state.items()}
-
-
-def _restore_opt_state(optimizer, saved):
-    for p in list(optimizer.state.keys()):
-        if id(p) in saved:
-            for k, v in saved[id(p)].items():
-                if torch.is_tensor(v):
-                    optimizer.state[p][k].copy_(v)
-                else:
-                    optimizer.state[p][k] = v
-        else:                                                # state created by the warm-up: back to "never stepped"
-            for k, v in optimizer.state[p].items():
-                if torch.is_tensor(v):
-                    v.zero_()
-
-
 def test_timestep_losses(model, steps: list, batch_size: int, loader, graph_creator, criterion, device="cpu") -> None:
     """Loss of one forward pass at the time points that are multiples of the time window
     (experiments/train_helper.py:150-203); prints like the reference, returns None."""
@@ -118,7 +103,7 @@ def test_timestep_losses(model, steps: list, batch_size: int, loader, graph_crea
         losses = []
         for (u_base, u_super, x, variables) in loader:
             with torch.no_grad():
-                u_super, x = u_super.to(device), x.to(device)
+                u_super = u_super.to(device)
                 same_steps = [step] * batch_size
                 data, labels = graph_creator.create_data(u_super, same_steps)
                 graph = graph_creator.create_graph(data, labels, x, variables, same_steps).to(device)
@@ -141,7 +126,7 @@ def test_unrolled_losses(model, steps: list, batch_size: int, nr_gt_steps: int, 
     for (u_base, u_super, x, variables) in loader:
         losses_tmp, losses_base_tmp = [], []
         with torch.no_grad():
-            u_base, u_super, x = u_base.to(device), u_super.to(device), x.to(device)
+            u_base, u_super = u_base.to(device), u_super.to(device)
             same_steps = [tw * nr_gt_steps] * batch_size
             data, labels = graph_creator.create_data(u_super, same_steps)
             graph = graph_creator.create_graph(data, labels, x, variables, same_steps).to(device)
@@ -214,7 +199,7 @@ def compute_L2_norms(model, batch_size: int, nr_gt_steps: int, loader, graph_cre
 
         err_w, ref_w = [], []
         with torch.no_grad():
-            u_super, x = u_super.to(device), x.to(device)
+            u_super = u_super.to(device)
             steps = [tw * nr_gt_steps] * bs
             data, labels = graph_creator.create_data(u_super, steps)
             graph = graph_creator.create_graph(data, labels, x, variables, steps).to(device)

@@ -1,4 +1,4 @@
-"""Whole-step execution: forward + loss + backward (+ gradient all-reduce) + optimizer update as ONE CUDA graph.
+"""Whole-step execution: forward + loss + backward (+ gradient all-reduce) + optimizer update as CUDA graph replays.
 
 The reference trains with a Python loop (experiments/train_helper.py:90-145): per step it builds a graph, moves
 it to the device, runs ``model(graph)``, ``loss = sqrt(MSE_sum(pred, graph.y))``, ``loss.backward()``,
@@ -6,17 +6,25 @@ it to the device, runs ``model(graph)``, ``loss = sqrt(MSE_sum(pred, graph.y))``
 step.  On the reference's fixed grids the topology (``edge_index``, ``batch``) is identical for every step
 (common/utils.py:365-377 depends only on the grid and the batch size), so the whole step is captured once
 and replayed: per step the host only copies the new ``x, y, pos`` (+ PDE parameters) into static device
-buffers and launches one graph -- no per-kernel launch or Python overhead on the critical path.
+buffers, refreshes eight floats of optimizer hyper-parameters and launches one graph.
 
-Data parallelism: whole graphs are sharded across ranks; because the loss is the
-square root of the *batch-global* summed squared error (train_helper.py:126,138) the local sum is all-reduced
-before the backward seed is formed, and the flat gradient bucket is SUM-all-reduced (NCCL) inside the same
-captured graph, followed by the identical AdamW update on every rank.
+How the loss enters (train_helper.py:126,138): ``loss = sqrt(SSE)`` with ``SSE`` the squared error summed over the
+whole (all-rank) batch, so ``d loss / d theta = (1 / (2 sqrt(SSE))) * d SSE / d theta``.  The backward pass is seeded with
+1 (it produces ``d SSE_local / d theta``), the local ``SSE`` rides along as the last two elements (an exact float pair) of
+the flat gradient bucket, and the factor ``1 / (2 sqrt(SSE))`` is applied by the optimizer kernel, which also writes the
+scaled gradient back -- after the step ``param.grad`` is the gradient of the loss, as in the reference.
+
+Data parallelism: whole graphs are sharded across ranks.  Because the squared error travels
+inside the bucket, a step needs exactly ONE collective: a SUM all-reduce (NCCL) of the bucket, launched between the two
+captured graphs (forward + backward | optimizer); every rank then applies the identical update.
 """
 from __future__ import annotations
 
 import torch
 import torch.distributed as dist
+
+from . import optim as moptim
+from ._lib import check, lib
 
 
 class _GlobalSqrtSSE(torch.autograd.Function):
@@ -46,14 +54,17 @@ def global_rmse_loss(pred, y, group=None):
 
 
 class FlatGradBucket:
-    """One contiguous buffer (the parameters' dtype; fp32 for the msmp modules) holding every parameter gradient (``p.grad`` are views into it), so the
-    data-parallel reduction is a single NCCL all-reduce on a fixed address."""
+    """One contiguous buffer (the parameters' dtype; fp32 for the msmp modules) holding every parameter gradient
+    (``p.grad`` are views into it) plus ``extra`` trailing scalars, so the data-parallel reduction is a single NCCL
+    all-reduce on a fixed address."""
 
-    def __init__(self, params):
+    def __init__(self, params, extra: int = 0):
         self.params = [p for p in params if p.requires_grad]
         n = sum(p.numel() for p in self.params)
         dev = self.params[0].device
-        self.flat = torch.zeros(n, dtype=self.params[0].dtype, device=dev)
+        self.n = n
+        self.flat = torch.zeros(n + extra, dtype=self.params[0].dtype, device=dev)
+        self.tail = self.flat[n:]
         off = 0
         for p in self.params:
             p.grad = self.flat[off:off + p.numel()].view_as(p)
@@ -63,65 +74,113 @@ class FlatGradBucket:
         self.flat.zero_()
 
     def all_reduce(self, group=None):
-        dist.all_reduce(self.flat, group=group)          # SUM: the loss already is the global one
+        dist.all_reduce(self.flat, group=group)          # SUM: gradients of the summed squared error + the error itself
 
 
 class GraphedTrainStep:
-    """Captures ``model(graph) -> loss -> backward -> (all-reduce) -> optimizer.step()`` into CUDA graphs.
+    """Captures ``model(graph) -> loss -> backward -> (all-reduce) -> optimizer update`` into CUDA graphs.
 
     >>> step = GraphedTrainStep(model, optimizer, example_graph_on_device)
     >>> loss = step(host_or_device_graph)        # copies the float fields into the static graph and replays
 
-    Single GPU: ONE graph for the whole step.  Data parallel (world > 1): three graphs -- forward (+ local
-    squared error), backward (seeded with 1 / (2 sqrt(global SSE))), optimizer -- with the two NCCL all-reduces
-    (one scalar, one flat gradient bucket) launched eagerly between them on the same stream.
+    Single GPU: ONE graph for the whole step.  Data parallel (world > 1): two graphs -- forward + backward | optimizer --
+    with the one NCCL all-reduce of the gradient bucket (which carries the local squared error) launched between them.
 
-    ``optimizer`` must be capturable (``torch.optim.AdamW(..., capturable=True)``).  The topology of later
-    graphs must equal the example's (only floating-point fields are refreshed)."""
+    ``optimizer``: any ``torch.optim.AdamW`` without amsgrad / maximize, e.g. exactly the one experiments/train.py:410
+    builds, is driven by the package's own update kernel (optim.FusedAdamW: learning-rate schedulers keep working);
+    other optimizers must be ``capturable`` and are captured as they are.  ``group=False`` forces the single-process
+    step inside an initialised process group.  The topology of later graphs must equal the example's (only floating-point
+    fields are refreshed; a different ``edge_index`` / ``batch`` raises)."""
 
-    def __init__(self, model, optimizer, example, group=None, warmup: int = 3, use_graph: bool = True):
-        self.model, self.opt, self.group = model, optimizer, group
-        self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+    def __init__(self, model, optimizer, example, group=None, warmup: int = 3, use_graph: bool = True,
+                 preserve_state: bool = False):
+        self.model, self.opt = model, optimizer
+        if group is False:
+            self.group, self.world = None, 1
+        else:
+            self.group = group
+            self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
         self.static = example.clone()
+        self._topo_src = (example.edge_index, example.batch)          # strong references: identity = same topology
+        self._topo_ok = {(example.edge_index.data_ptr(), example.edge_index._version)}
         # floating-point fields are refreshed every step; integer fields (edge_index, batch) are the static topology
         self.fields = [k for k in self.static.keys()
                        if torch.is_tensor(getattr(self.static, k)) and getattr(self.static, k).is_floating_point()]
-        self.bucket = FlatGradBucket(model.parameters())
+        self.bucket = FlatGradBucket(model.parameters(), extra=2)
         self.gplan = None          # gradsink.GradPlan, built after the first eager step (the packs exist by then)
         self.use_graph = use_graph
         self.graph = None
         self.graphs = None
-        self.loss = None
         dev = self.bucket.flat.device
-        self._sse_total = torch.zeros((), dtype=torch.float64, device=dev)
-        self._seed = torch.zeros((), dtype=torch.float64, device=dev)
+        self.loss = torch.zeros((), dtype=torch.float64, device=dev)
+        self.gscale = torch.zeros((), dtype=torch.float32, device=dev)
+        self.fused = moptim.FusedAdamW(optimizer) if moptim.supported(optimizer) else None
+        if self.fused is None and use_graph and not all(g.get("capturable", False) for g in optimizer.param_groups):
+            raise ValueError("GraphedTrainStep captures torch.optim.AdamW (any flavour) with its own update kernel; "
+                             "other optimizers must be built with capturable=True")
+        if self.fused is None and use_graph:
+            # a Python-float lr would be baked into the captured kernels: schedulers fill_ a tensor lr in place instead
+            for g in optimizer.param_groups:
+                if not torch.is_tensor(g["lr"]):
+                    g["lr"] = torch.tensor(float(g["lr"]), dtype=torch.float32, device=dev)
+        # preserve_state: the warm-up steps below really train; a caller that wants its first call to be the first
+        # update (train_helper.training_loop) gets parameters and optimizer state put back afterwards
+        snap = self._snapshot() if preserve_state else None
         side = torch.cuda.Stream(priority=-1)      # high priority: weight-gradient side streams run below it
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for i in range(max(warmup, 1)):
+                self._host_prologue()
                 self._eager_step()
                 if i == 0:
                     self._make_grad_plan()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        if snap is not None:
+            self._restore(snap)
         if not use_graph:
             return
         if self.world == 1:
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph, stream=side):
-                self._eager_step()
+                self._fwd_bwd()
+                self._update()
         else:
-            g_fwd, g_bwd, g_opt = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g_fwd, stream=side):
-                self._fwd()
-            self._reduce_loss()
-            with torch.cuda.graph(g_bwd, pool=g_fwd.pool(), stream=side):
-                self._bwd()
+            g_a, g_b = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_a, stream=side):
+                self._fwd_bwd()
             self.bucket.all_reduce(self.group)
-            with torch.cuda.graph(g_opt, pool=g_fwd.pool(), stream=side):
-                self.opt.step()
-            self.graphs = (g_fwd, g_bwd, g_opt)
+            with torch.cuda.graph(g_b, pool=g_a.pool(), stream=side):
+                self._update()
+            self.graphs = (g_a, g_b)
         torch.cuda.synchronize()
+
+    def _snapshot(self):
+        params = [p.detach().clone() for p in self.model.parameters()]
+        bufs = [b.detach().clone() for b in self.model.buffers()]
+        state = {id(p): {k: (v.detach().clone() if torch.is_tensor(v) else v) for k, v in st.items()}
+                 for p, st in self.opt.state.items()}
+        return params, bufs, state
+
+    def _restore(self, snap):
+        params, bufs, state = snap
+        with torch.no_grad():
+            for p, q in zip(self.model.parameters(), params):
+                p.copy_(q)
+            for b, q in zip(self.model.buffers(), bufs):
+                b.copy_(q)
+            for p, st in self.opt.state.items():
+                old = state.get(id(p))
+                for k, v in st.items():
+                    if torch.is_tensor(v):
+                        if old is not None and k in old:
+                            v.copy_(old[k])
+                        else:
+                            v.zero_()          # state created by the warm-up: back to "never stepped"
+                    elif old is not None and k in old:
+                        st[k] = old[k]
+        if self.fused is not None:
+            self.fused.resync()
 
     # ---- pieces of one step -------------------------------------------------------------------------
     def _make_grad_plan(self):
@@ -134,51 +193,73 @@ class GraphedTrainStep:
         from .gradsink import GradPlan
         self.gplan = GradPlan(self.model)
 
-    def _fwd(self):
+    def _host_prologue(self):
+        if self.fused is not None:
+            self.fused.host_update()
+
+    def _fwd_bwd(self):
+        """forward, local squared error, backward with unit seed; leaves d SSE_local / d theta in the bucket and the
+        squared error (fp64 split exactly into two floats) in its two trailing elements."""
         if self.gplan is None:
             self.bucket.zero_()          # with a GradPlan the covered gradients are overwritten, the others zeroed in begin()
-        self._fwd_stream = torch.cuda.current_stream()
         pred = self.model(self.static)
-        self._sse_local = ((pred - self.static.y) ** 2).sum()          # train_helper.py:126 (reduction='sum')
-        self._sse_val = self._sse_local.detach()                       # same storage, no autograd graph
-
-    def _reduce_loss(self):
-        """global SSE (all ranks) -> loss and the backward seed d loss / d sse_local = 1 / (2 loss)."""
-        self._sse_total.copy_(self._sse_val)
-        if self.world > 1:
-            dist.all_reduce(self._sse_total, group=self.group)
-        self.loss = torch.sqrt(self._sse_total)
-        self._seed.copy_(0.5 / self.loss)
-
-    def _bwd(self):
-        # The AccumulateGrad nodes of this step were created on the forward's stream and the engine syncs the
-        # caller's stream with it after the backward pass even when a node only saw an undefined gradient (the
-        # sink returns None for the parameters).  When the backward runs on another stream (separate CUDA graphs
-        # in the data-parallel step) that stream is forked here so the sync stays inside the capture.
-        cur = torch.cuda.current_stream()
-        if self._fwd_stream != cur:
-            self._fwd_stream.wait_stream(cur)
+        sse = ((pred - self.static.y) ** 2).sum()          # train_helper.py:126 (reduction='sum')
         if self.gplan is not None:
             self.gplan.begin()
         try:
-            self._sse_local.backward(self._seed.to(self._sse_local.dtype))
+            sse.backward()
         finally:
             if self.gplan is not None:
                 self.gplan.finish()
-            # drop the autograd graph now: AccumulateGrad nodes kept alive across steps stay bound to the stream of
-            # the step that created them (a warm-up stream outside any later capture)
-            self._sse_local = None
+        s64 = sse.detach().double()
+        hi = s64.float()
+        self.bucket.tail[0] = hi
+        self.bucket.tail[1] = (s64 - hi.double()).float()
+
+    def _update(self):
+        """loss = sqrt(SSE), gradient scale 1 / (2 loss), optimizer update (and p.grad <- gradient of the loss)."""
+        check(lib.msmp_loss_scalars(self.bucket.tail.data_ptr(), self.loss.data_ptr(), self.gscale.data_ptr(),
+                                    torch.cuda.current_stream().cuda_stream), "msmp_loss_scalars")
+        if self.fused is not None:
+            self.fused.launch(self.gscale)
+        else:
+            self.bucket.flat[:self.bucket.n].mul_(self.gscale)
+            self.opt.step()
+
+    def eager(self, graph=None):
+        """The same step launched kernel by kernel (no graph replay); used for per-kernel timing."""
+        if graph is not None and graph is not self.static:
+            self.load(graph)
+        self._host_prologue()
+        self._eager_step()
+        return self.loss
 
     def _eager_step(self):
-        self._fwd()
-        self._reduce_loss()
-        self._bwd()
+        self._fwd_bwd()
         if self.world > 1:
             self.bucket.all_reduce(self.group)
-        self.opt.step()
+        self._update()
+
+    def _check_topology(self, graph):
+        ei = graph.edge_index
+        if ei is self._topo_src[0] and graph.batch is self._topo_src[1]:
+            return
+        key = (ei.data_ptr(), ei._version)
+        if key in self._topo_ok and ei.shape == self.static.edge_index.shape:
+            return
+        same = (ei.shape == self.static.edge_index.shape and graph.batch.shape == self.static.batch.shape
+                and bool(torch.equal(ei.to(self.static.edge_index.device), self.static.edge_index))
+                and bool(torch.equal(graph.batch.to(self.static.batch.device), self.static.batch)))
+        if not same:
+            raise ValueError("GraphedTrainStep: this graph's edge_index / batch differ from the captured topology; build "
+                             "a new GraphedTrainStep for it")
+        if len(self._topo_ok) > 256:
+            self._topo_ok.clear()
+        self._topo_ok.add(key)
 
     def load(self, graph):
         """Copy the floating-point fields of ``graph`` (host or device) into the static device buffers."""
+        self._check_topology(graph)
         for k in self.fields:
             src = getattr(graph, k)
             dst = getattr(self.static, k)
@@ -191,14 +272,16 @@ class GraphedTrainStep:
     def __call__(self, graph=None):
         if graph is not None and graph is not self.static:
             self.load(graph)
+        if self.fused is not None and not self.fused.valid():
+            raise RuntimeError("GraphedTrainStep: parameter / gradient / optimizer-state storage was replaced after the "
+                               "capture (e.g. optimizer.load_state_dict or zero_grad(set_to_none=True)); build a new step")
+        self._host_prologue()
         if self.graph is not None:
             self.graph.replay()
         elif self.graphs is not None:
             self.graphs[0].replay()
-            self._reduce_loss()
-            self.graphs[1].replay()
             self.bucket.all_reduce(self.group)
-            self.graphs[2].replay()
+            self.graphs[1].replay()
         else:
             self._eager_step()
         return self.loss

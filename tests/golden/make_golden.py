@@ -291,10 +291,22 @@ def l2_norms_case(mg2):
                         spacetime=np.array([float(st), float(st_rel)]), space=sp.numpy(), space_rel=sp_rel.numpy())
 
 
+def time_window_cases(mg, mg2):
+    """The other constructible time windows (models_gnn.py:176,208-224: 20 / 25 / 50; models_gnn2D.py:322,382-391:
+    25 / 50): decoder geometries 128 -> 29 -> 20 and 128 -> 59 -> 50, F_u = 20 / 50 / 100 input columns, LEM T = 50."""
+    model_case(mg.MP_PDE_Solver, synth.config_c1, dict(B=2, nx=30, tw=20, seed=60), "tw20_MP_PDE_Solver.npz")
+    model_case(mg.MP_PDE_Solver, synth.config_c1, dict(B=2, nx=30, tw=50, seed=61), "tw50_MP_PDE_Solver.npz")
+    model_case(mg2.MP_PDE_Solver2DLEMLinGated, synth.config_c2, dict(B=2, nx=30, tw=50, seed=62),
+               "tw50_MP_PDE_Solver2DLEMLinGated.npz")
+
+
 def main():
     mg, mg2 = _load_reference()
     if "--l2-only" in sys.argv:
         l2_norms_case(mg2)
+        return
+    if "--tw-only" in sys.argv:
+        time_window_cases(mg, mg2)
         return
     graph_cases()
     training_loop_case(mg2)
@@ -314,6 +326,7 @@ def main():
                    second_call=name.endswith("Save"))
     for i, name in enumerate(VARIANTS_2F):
         model_case(getattr(mg2, name), synth.config_c2, dict(B=2, nx=30, seed=40 + i), f"var_{name}.npz")
+    time_window_cases(mg, mg2)
     # structural fixtures: state_dict key/shape tables
     import json
     tables = {}

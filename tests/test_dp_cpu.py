@@ -59,3 +59,41 @@ def test_global_loss_and_flat_bucket_gloo_world2():
     port = 29500 + (os.getpid() % 400)
     mp.spawn(_worker, args=(2, port, ret), nprocs=2, join=True)
     assert ret[0] and ret[1]
+
+
+def _worker_single_collective(rank, world, port, ret):
+    """The scheme of GraphedTrainStep (train_step.py): unit-seeded backward of the LOCAL squared error, the squared error
+    itself as an exact float pair in the two trailing bucket elements, ONE all-reduce, then the factor 1 / (2 sqrt(SSE))."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from msmp_pde_b200.train_step import FlatGradBucket
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(6, 8), torch.nn.Tanh(), torch.nn.Linear(8, 3)).float()
+    g = torch.Generator().manual_seed(1)
+    X = torch.randn(10, 6, generator=g)
+    Y = torch.randn(10, 3, generator=g).double()
+    ref = torch.sqrt(((net(X).double() - Y) ** 2).sum())
+    ref_grads = torch.autograd.grad(ref, list(net.parameters()))
+    sl = slice(0, 6) if rank == 0 else slice(6, 10)
+    bucket = FlatGradBucket(net.parameters(), extra=2)
+    sse = ((net(X[sl]).double() - Y[sl]) ** 2).sum()
+    sse.backward()
+    hi = sse.detach().float()
+    bucket.tail[0] = hi
+    bucket.tail[1] = (sse.detach() - hi.double()).float()
+    bucket.all_reduce()
+    total = bucket.tail[0].double() + bucket.tail[1].double()
+    loss = torch.sqrt(total)
+    scale = (0.5 / loss).float()
+    ok_loss = abs(float(loss) - float(ref)) < 1e-6 * float(ref)
+    ok_grad = all(torch.allclose(p.grad * scale, g_, rtol=1e-5, atol=1e-7) for p, g_ in zip(net.parameters(), ref_grads))
+    ret[rank] = bool(ok_loss and ok_grad)
+    dist.destroy_process_group()
+
+
+def test_single_collective_step_gloo_world2():
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 29900 + (os.getpid() % 90)
+    mp.spawn(_worker_single_collective, args=(2, port, ret), nprocs=2, join=True)
+    assert ret[0] and ret[1]

@@ -266,9 +266,13 @@ def test_train_step_gradient_sink_equals_autograd(mod, name, graphed):
         p.grad.fill_(123.0)
     step(g)
     torch.cuda.synchronize()
+    # the captured step differentiates the summed squared error with a unit seed and applies 1 / (2 sqrt(SSE)) in the
+    # optimizer kernel (lr = 0 here, so only the scaled gradient is written back): the same two operations with autograd
     out = ref(g)
     sse = ((out - g.y) ** 2).sum()
-    sse.backward(step._seed.to(sse.dtype))
+    sse.backward()
     assert abs(float(step.loss) - float(torch.sqrt(sse))) < 1e-9 * float(step.loss)
+    scale = torch.tensor(0.5 / float(torch.sqrt(sse.detach().double())), dtype=torch.float32, device=dev)
+    assert float(step.gscale) == float(scale)
     for (n, p), (_, q) in zip(model.named_parameters(), ref.named_parameters()):
-        assert torch.equal(p.grad, q.grad), n
+        assert torch.equal(p.grad, q.grad * scale), n

@@ -40,6 +40,12 @@ def test_layer_matches_reference(cls, fname, F_u, V):
     _check_digests(layer, g)
 
 
+TW_CASES = [          # (class, fixture, pde name, eq_variables, time_window) -- the other constructible time windows
+    ("MP_PDE_Solver", "tw20_MP_PDE_Solver.npz", "CE", {}, 20),
+    ("MP_PDE_Solver", "tw50_MP_PDE_Solver.npz", "CE", {}, 50),
+    ("MP_PDE_Solver2DLEMLinGated", "tw50_MP_PDE_Solver2DLEMLinGated.npz", "AD", {"a": 1.0, "b": 1.0}, 50),
+]
+
 CASES = [
     ("MP_PDE_Solver", "mp_pde_c1.npz", "CE", {}, {}),
     ("MP_PDE_SolverLEMLinGated", "msmp_pde_1f.npz", "CE", {"alpha": 3.0, "beta": 0.4, "gamma": 1.0}, {}),
@@ -54,6 +60,23 @@ def test_model_matches_reference(cls, fname, pde_name, eq, kw):
     g = golden_io.load(fname)
     pde, data = golden_io.model_inputs(g, pde_name)
     model = getattr(om, cls)(pde, time_window=25, hidden_features=128, hidden_layer=6, eq_variables=eq, **kw)
+    formula_weights_(model)
+    out = model(data)
+    loss = torch.sqrt(torch.nn.functional.mse_loss(out, data.y, reduction="sum"))
+    loss.backward()
+    assert rel_err(out, torch.from_numpy(g["out"])) < TOL
+    assert abs(float(loss) - float(g["loss"])) < 1e-9 * float(g["loss"])
+    _check_digests(model, g)
+
+
+@pytest.mark.parametrize("cls,fname,pde_name,eq,tw", TW_CASES)
+def test_time_windows_match_reference(cls, fname, pde_name, eq, tw):
+    """time_window 20 / 50 (models_gnn.py:176,208-224; models_gnn2D.py:322,382-391): other decoder geometries,
+    F_u = 20 / 50 / 100, LEM over 50 steps."""
+    torch.set_default_dtype(torch.float64)
+    g = golden_io.load(fname)
+    pde, data = golden_io.model_inputs(g, pde_name)
+    model = getattr(om, cls)(pde, time_window=tw, hidden_features=128, hidden_layer=6, eq_variables=eq)
     formula_weights_(model)
     out = model(data)
     loss = torch.sqrt(torch.nn.functional.mse_loss(out, data.y, reduction="sum"))

@@ -1,0 +1,225 @@
+"""Round-2 parity tests (B200): the benchmarked shapes at full size, the other time windows, the lem_cuda boundary, the
+captured step with the optimizer the reference's train.py builds, and the NCCL data-parallel step."""
+import copy
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from tests import golden_io  # noqa: E402
+from tests.test_models_gpu import GRAD_TOL, OUT_TOL, _grad_errs  # noqa: E402
+from tests.test_oracle_golden import TW_CASES  # noqa: E402
+from tests.util import formula_weights_, rel_err  # noqa: E402
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _model_vs_oracle(pde, data, meta, tw=25):
+    from msmp_pde_b200 import models_gnn2D
+    from oracle import models as om
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    model = models_gnn2D.MP_PDE_Solver2DLEMLinGated(pde, tw, 128, 6, meta["eq_variables"]).to(dev)
+    torch.set_default_dtype(torch.float64)
+    torch.set_num_threads(os.cpu_count())
+    ref = om.MP_PDE_Solver2DLEMLinGated(pde, tw, 128, 6, meta["eq_variables"])
+    ref.load_state_dict({k: v.double().cpu() for k, v in model.state_dict().items()})
+    dd = data.clone().to(dev)
+    out = model(dd)
+    torch.sqrt(((out - dd.y) ** 2).sum()).backward()
+    outr = ref(data)
+    torch.sqrt(((outr - data.y) ** 2).sum()).backward()
+    assert rel_err(out, outr) < OUT_TOL
+    errs = _grad_errs(model, ref)
+    worst = max(errs, key=errs.get)
+    assert errs[worst] <= 1.0, (worst, errs[worst])
+
+
+def test_c2_full_bench_shape():
+    """BASELINE config 2 at the size bench.py runs as a sub-record: 64 graphs x 100 nodes (N = 6400, E = 37632), outputs and
+    every parameter gradient against the float64 oracle."""
+    from msmp_pde_b200 import synth
+    _model_vs_oracle(*synth.config_c2(B=64, nx=100, seed=0))
+
+
+def test_c4_full_lattice_graph():
+    """One full 128 x 128 lattice graph of BASELINE config 4 (16384 nodes, 65024 edges, 128 InstanceNorm chunks per graph,
+    256 LEM node tiles): outputs and gradients against the float64 oracle."""
+    from msmp_pde_b200 import synth
+    _model_vs_oracle(*synth.config_c4(B=1, side=128, seed=3))
+
+
+@pytest.mark.parametrize("cls,fname,pde_name,eq,tw", TW_CASES)
+def test_time_windows_vs_golden_and_oracle(cls, fname, pde_name, eq, tw):
+    """time_window 20 / 50: generic decoder geometry (128 -> 29 -> 20, 128 -> 59 -> 50), F_u = 20 / 50 / 100 (zero padded to
+    32 / 64 / 128 columns), LEM over 50 steps -- against fixtures written by the reference classes and the oracle's
+    gradients."""
+    import importlib
+    from oracle import models as om
+    dev = torch.device("cuda:0")
+    g = golden_io.load(fname)
+    pde, data = golden_io.model_inputs(g, pde_name)
+    mod = importlib.import_module("msmp_pde_b200." + ("models_gnn2D" if "2D" in cls else "models_gnn"))
+    torch.set_default_dtype(torch.float64)
+    model = getattr(mod, cls)(pde, time_window=tw, hidden_features=128, hidden_layer=6, eq_variables=eq)
+    formula_weights_(model)
+    model = model.to(dev)
+    dd = copy.copy(data).clone().to(dev)
+    out = model(dd)
+    loss = torch.sqrt(torch.nn.functional.mse_loss(out, dd.y, reduction="sum"))
+    loss.backward()
+    assert out.shape == dd.y.shape
+    assert rel_err(out, torch.from_numpy(g["out"])) < OUT_TOL
+    assert abs(float(loss) - float(g["loss"])) < 1e-5 * float(g["loss"])
+    ref = getattr(om, cls)(pde, time_window=tw, hidden_features=128, hidden_layer=6, eq_variables=eq)
+    formula_weights_(ref)
+    outr = ref(data)
+    torch.sqrt(torch.nn.functional.mse_loss(outr, data.y, reduction="sum")).backward()
+    errs = _grad_errs(model, ref)
+    worst = max(errs, key=errs.get)
+    assert errs[worst] <= 1.0, (worst, errs[worst])
+
+
+# ---------------------------------------------------------------------------------------------- lem_cuda boundary
+class _RefLEMFunction(torch.autograd.Function):
+    """The reference's LEMFunction (experiments/models_gnn.py:285-302), restated verbatim in behaviour: forwards 8
+    arguments to ``lem_cuda.forward``, saves 11 tensors, hands 13 to ``lem_cuda.backward`` and returns 7 of its outputs."""
+    lem_cuda = None
+
+    @staticmethod
+    def forward(ctx, inputs, weights, weights_lin_z, bias, bias_lin_z, initial_y_state, initial_z_state, dt):
+        all_y, all_z, all_X, all_X2, all_ms, all_lin = _RefLEMFunction.lem_cuda.forward(
+            inputs, weights, weights_lin_z, bias, bias_lin_z, initial_y_state, initial_z_state, dt)
+        ctx.save_for_backward(all_X, all_X2, all_ms, all_lin, weights, weights_lin_z, bias, bias_lin_z,
+                              initial_y_state, initial_z_state, dt)
+        return all_y, all_z
+
+    @staticmethod
+    def backward(ctx, grad_y_states, grad_z_states):
+        outputs = _RefLEMFunction.lem_cuda.backward(grad_y_states.contiguous(), grad_z_states.contiguous(),
+                                                    *ctx.saved_tensors)
+        d_inputs, d_w, d_wz, d_b, d_bz, d_y0, d_z0 = outputs
+        return None, d_w, d_wz, d_b, d_bz, d_y0, d_z0, None
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_lem_cuda_module_contract(dtype):
+    """``msmp_pde_b200.compat.lem_cuda`` behind the reference's own call pattern: 8 in / 6 out, 13 in / 7 out, all T
+    states returned, gradients wrt weights, biases and the initial state against the float64 oracle recurrence; float64
+    tensors (the reference's default dtype) are accepted and returned."""
+    import msmp_pde_b200
+    from msmp_pde_b200.compat import lem_cuda
+    from oracle.models import lem_forward
+    sys.modules.pop("lem_cuda", None)
+    msmp_pde_b200.install()
+    assert sys.modules["lem_cuda"] is lem_cuda
+    _RefLEMFunction.lem_cuda = lem_cuda
+    dev = torch.device("cuda:0")
+    T, N, ninp, Hh = 25, 300, 6, 128
+    g = torch.Generator().manual_seed(3)
+    mk = lambda *s: ((torch.rand(*s, generator=g, dtype=torch.float64) * 2 - 1) / Hh ** 0.5)
+    cpu = dict(inputs=torch.randn(T, N, ninp, generator=g, dtype=torch.float64), W=mk(3 * Hh, ninp + Hh),
+               Wz=mk(Hh, ninp + Hh), b=mk(3 * Hh), bz=mk(Hh), y0=0.3 * torch.randn(N, Hh, generator=g, dtype=torch.float64),
+               z0=0.3 * torch.randn(N, Hh, generator=g, dtype=torch.float64))
+    wy, wz = torch.randn(T, N, Hh, generator=g, dtype=torch.float64), torch.randn(T, N, Hh, generator=g, dtype=torch.float64)
+    # oracle
+    leaves = {k: v.clone().requires_grad_(k != "inputs") for k, v in cpu.items()}
+    ys, zs = lem_forward(leaves["inputs"], leaves["W"], leaves["Wz"], leaves["b"], leaves["bz"], leaves["y0"], leaves["z0"], 1.0)
+    ((ys * wy).sum() + (zs * wz).sum()).backward()
+    # the shim through the reference's Function
+    d = {k: v.to(dev, dtype).requires_grad_(k != "inputs") for k, v in cpu.items()}
+    dt = torch.tensor(1.0, dtype=dtype).reshape(1, 1).to(dev)
+    all_y, all_z = _RefLEMFunction.apply(d["inputs"], d["W"], d["Wz"], d["b"], d["bz"], d["y0"], d["z0"], dt)
+    assert all_y.shape == (T, N, Hh) and all_y.dtype == dtype
+    ((all_y * wy.to(dev, dtype)).sum() + (all_z * wz.to(dev, dtype)).sum()).backward()
+    assert rel_err(all_y, ys) < OUT_TOL and rel_err(all_z, zs) < OUT_TOL
+    gscale = max(float(leaves[k].grad.abs().max()) for k in ("W", "Wz", "b", "bz", "y0", "z0"))
+    for k in ("W", "Wz", "b", "bz", "y0", "z0"):
+        ref = leaves[k].grad
+        allow = GRAD_TOL * float(ref.abs().max()) + 1e-6 * gscale
+        assert d[k].grad.dtype == dtype
+        assert float((d[k].grad.double().cpu() - ref).abs().max()) <= allow, k
+
+
+# ------------------------------------------------------------------------- captured step with train.py's optimizer
+def test_captured_step_with_plain_adamw_and_scheduler():
+    """experiments/train.py:410-411 builds ``optim.AdamW(model.parameters(), lr)`` (not capturable) and a MultiStepLR
+    that rewrites param_group['lr'].  The captured step must (a) accept that optimizer, (b) follow the scheduler, and
+    (c) leave the optimizer's own state where torch's eager step would have: three epochs of two steps each against the
+    eager reference loop on a copy of the model, then one more eager ``optimizer.step()`` on both."""
+    from msmp_pde_b200 import models_gnn2D, synth
+    from msmp_pde_b200.train_step import GraphedTrainStep
+    dev = torch.device("cuda:0")
+    pde, data, meta = synth.config_c2(B=3, nx=50, seed=9)
+    torch.manual_seed(2)
+    model = models_gnn2D.MP_PDE_Solver2DLEMLinGated(pde, 25, 128, 6, meta["eq_variables"]).to(dev)
+    ref = copy.deepcopy(model)
+    g = data.clone().to(dev)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-3)
+    sched = torch.optim.lr_scheduler.MultiStepLR(opt, milestones=[1, 2], gamma=0.4)
+    opt_r = torch.optim.AdamW(ref.parameters(), lr=1e-3)
+    sched_r = torch.optim.lr_scheduler.MultiStepLR(opt_r, milestones=[1, 2], gamma=0.4)
+    step = GraphedTrainStep(model, opt, g, warmup=1, preserve_state=True)
+    assert step.fused is not None and step.graph is not None
+    crit = torch.nn.MSELoss(reduction="sum")
+    for epoch in range(3):
+        for _ in range(2):
+            loss = step(g)
+            opt_r.zero_grad()
+            loss_r = torch.sqrt(crit(ref(g), g.y))
+            loss_r.backward()
+            opt_r.step()
+            assert abs(float(loss) - float(loss_r)) < 2e-5 * float(loss_r)
+        sched.step()
+        sched_r.step()
+    assert opt.param_groups[0]["lr"] == pytest.approx(1e-3 * 0.16)
+    sd = opt.state_dict()                                             # flushes the step counters
+    assert all(float(s["step"]) == 6.0 for s in sd["state"].values())
+    for (n, p), (_, q) in zip(model.named_parameters(), ref.named_parameters()):
+        assert rel_err(p, q) < 2e-5, n
+    # hand over to torch's own eager step: same state => same next update
+    for m, o in ((model, opt), (ref, opt_r)):
+        o.zero_grad(set_to_none=False)
+        torch.sqrt(crit(m(g), g.y)).backward()
+        o.step()
+    for (n, p), (_, q) in zip(model.named_parameters(), ref.named_parameters()):
+        assert rel_err(p, q) < 2e-5, n
+
+
+def test_captured_step_rejects_other_topology():
+    from msmp_pde_b200 import models_gnn, synth
+    from msmp_pde_b200.train_step import GraphedTrainStep
+    dev = torch.device("cuda:0")
+    pde, data, meta = synth.config_c1(B=2, nx=40, seed=1)
+    torch.manual_seed(0)
+    model = models_gnn.MP_PDE_Solver(pde, 25, 128, 6, {}).to(dev)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4)
+    g = data.clone().to(dev)
+    step = GraphedTrainStep(model, opt, g, warmup=1)
+    same = g.clone()                                  # equal edge list in another tensor: accepted (checked once)
+    step(same)
+    _, other, _ = synth.config_c1(B=2, nx=40, seed=1, neighbors=2)      # same node count, different edge list
+    with pytest.raises(ValueError):
+        step(other.clone().to(dev))
+
+
+# ------------------------------------------------------------------------------------------------- NCCL data parallel
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (run with gpurun --gpus 2)")
+def test_dp_nccl_step_equals_single_gpu():
+    """SURVEY section 4 'Multi-GPU': the 3-graphs-per-rank NCCL step (sharded graphs, one all-reduce of the gradient bucket
+    that also carries the squared error) against the single-GPU full-batch step: loss, gradient and updated weights."""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29541", os.path.join(ROOT, "tests", "dp_nccl_worker.py")]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-4000:]
+    line = [l for l in p.stdout.splitlines() if l.startswith("DPCHECK ")][-1]
+    res = json.loads(line[len("DPCHECK "):])
+    for mode, r in res.items():
+        assert r["loss_rel_err"] < 1e-6, (mode, r)
+        assert r["grad_max_rel_err"] < 1e-5, (mode, r)
+        assert r["weight_max_abs_err_over_lr"] <= 2.0 + 1e-6 and r["weight_mismatch_frac"] < 1e-3, (mode, r)
