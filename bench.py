@@ -1,14 +1,16 @@
 #!/usr/bin/env python
 """Benchmark of the MSMP-PDE hot path (contract: see the task statement / DESIGN.md "Measurement").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c4|c2|c3]
 
-Workload (BASELINE.json configs[1]): MSMP-PDE2D training step on the RP shape -- 64 trajectories per GPU,
-100 nodes each, time_window 25, 6-neighbour radius graph (N = 6400 nodes, E = 37632 edges per GPU),
-MP_PDE_Solver2DLEMLinGated (LEM encoder + 6 gated layer pairs + Conv1d decoder, 1 409 002 parameters),
-synthetic data, random-init weights.  One step = forward + loss (sqrt of the batch-global summed squared
-error, train_helper.py:126,138) + backward + (N > 1: gradient all-reduce over NCCL) + AdamW update.
-Metric: graph-nodes per second, whole job.
+Headline workload (BASELINE.json configs[3], the configuration the metric "graph-nodes/sec at 1/2/4/8 B200" is quoted
+on): MSMP-PDE2D training step (MP_PDE_Solver2DLEMLinGated: LEM encoder + 6 gated layer pairs + Conv1d decoder,
+1 409 002 parameters, time_window 25) on 128 x 128 lattice graphs, 8 graphs = 131 072 nodes / 520 192 edges per GPU,
+data parallel over whole graphs (weak scaling).  One step = forward + loss (sqrt of the batch-global summed squared error,
+experiments/train_helper.py:126,138) + backward + (N > 1: ONE gradient all-reduce over NCCL) + AdamW update, with the
+optimizer experiments/train.py:410 builds.  Metric: graph-nodes per second, whole job.  At N = 1 the other BASELINE
+configs (C2, C3, the config-5 single-layer shapes) and the bf16 operand mode are measured as sub-records of the same
+JSON line.  Synthetic data, random-init weights.
 """
 from __future__ import annotations
 
@@ -19,6 +21,7 @@ import subprocess
 import sys
 import threading
 import time
+import types
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
@@ -26,7 +29,16 @@ if ROOT not in sys.path:
 
 METRIC = "GNN fwd+bwd graph-nodes/sec"
 UNIT = "nodes/s"
-B_PER_GPU, NX, TW = 64, 100, 25
+TW = 25
+WORKLOADS = {
+    "c4": dict(graphs=8, label="C4: MSMP-PDE2D (MP_PDE_Solver2DLEMLinGated) on MSWG3-shaped 128 x 128 4-neighbour lattice graphs, "
+                               "{B} graphs x 16384 nodes per GPU, tw=25, fwd+loss+bwd+AdamW"),
+    "c2": dict(graphs=64, label="C2: MSMP-PDE2D (MP_PDE_Solver2DLEMLinGated) RP shape, {B} graphs x 100 nodes per GPU, tw=25, "
+                                "588 edges/graph, fwd+loss+bwd+AdamW"),
+    "c3": dict(graphs=64, label="C3: MSMP-PDE2D (MP_PDE_Solver2DLEMLinGated) RPU shape (pseudo-random grid, kNN k=3), {B} graphs "
+                                "x 100 nodes per GPU, tw=25, fwd+loss+bwd+AdamW"),
+}
+REF_GRAPHS = {"c4": 2, "c2": 64, "c3": 64}          # graphs per step of the CPU reference arm (bounded sample for C4)
 
 
 def _peaks():
@@ -73,11 +85,27 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-def _workload(rank: int):
-    import torch
+def _synth_module(load_native: bool):
+    """msmp_pde_b200.synth (host-side generators of the BASELINE shapes).  The CPU reference arm imports it WITHOUT
+    running the package __init__, which would dlopen libmsmp_b200.so: a stub package object makes the submodule import
+    resolve on its own (synth and the compat shims it uses are pure torch / numpy)."""
+    if not load_native and "msmp_pde_b200" not in sys.modules:
+        pkg = types.ModuleType("msmp_pde_b200")
+        pkg.__path__ = [os.path.join(ROOT, "msmp_pde_b200")]
+        sys.modules["msmp_pde_b200"] = pkg
     from msmp_pde_b200 import synth
-    pde, data, meta = synth.config_c2(B=B_PER_GPU, nx=NX, tw=TW, seed=rank)     # float64 host tensors (F1)
-    return pde, data, meta
+    return synth
+
+
+def _make(synth, workload: str, B: int, seed: int, dtype=None):
+    kw = {} if dtype is None else {"dtype": dtype}
+    if workload == "c4":
+        return synth.config_c4(B=B, side=128, tw=TW, seed=seed, **kw)
+    if workload == "c2":
+        return synth.config_c2(B=B, nx=100, tw=TW, seed=seed, **kw)
+    if workload == "c3":
+        return synth.config_c3(B=B, nx=100, tw=TW, seed=seed, **kw)
+    raise ValueError(workload)
 
 
 def _loss(pred, y):
@@ -86,22 +114,139 @@ def _loss(pred, y):
 
 
 # ----------------------------------------------------------------------------------------------- ours
+def _time_step(step, flush, K, graph, read_loss):
+    """K steps, one CUDA-event pair each on the launching stream, L2 flushed between steps -> list of ms."""
+    import torch
+    evs = []
+    for _ in range(K):
+        flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        loss = step(graph)          # graph=None: inputs already resident in HBM; else H2D copies inside
+        if read_loss:
+            loss.item()
+        e.record()
+        evs.append((s, e))
+    torch.cuda.synchronize()
+    return [s.elapsed_time(e) for s, e in evs]
+
+
+def _sub_config(name, B, dev, flush, steps, precision=None):
+    """ms/step of another BASELINE config on this GPU (captured step, inputs resident) -- a sub-record, not the headline."""
+    import torch
+    from msmp_pde_b200 import models_gnn2D, ops, synth
+    from msmp_pde_b200.train_step import GraphedTrainStep
+    prev = ops.PRECISION
+    if precision:
+        ops.PRECISION = precision
+    try:
+        pde, data, meta = _make(synth, name, B, 0)
+        torch.manual_seed(0)
+        model = models_gnn2D.MP_PDE_Solver2DLEMLinGated(pde, TW, 128, 6, meta["eq_variables"]).to(dev)
+        opt = torch.optim.AdamW(model.parameters(), lr=1e-4)
+        g = data.clone().to(dev)
+        step = GraphedTrainStep(model, opt, g, warmup=3)
+        for _ in range(3):
+            step(None)
+        ts = _time_step(step, flush, steps, None, False)
+        ms = sum(ts) / len(ts)
+        N, E = g.x.shape[0], g.edge_index.shape[1]
+        out = {"workload": WORKLOADS[name]["label"].format(B=B), "nodes": N, "edges": E, "ms_per_step": round(ms, 4),
+               "nodes_per_s": round(N / ms * 1e3, 1), "loss": float(step.loss)}
+        del step, model, opt, g
+        torch.cuda.empty_cache()
+        return out
+    finally:
+        ops.PRECISION = prev
+
+
+def _layer_c5(n_nodes, degree, topology, dev, reps=5):
+    """BASELINE config 5: ONE GNN_Layer(128,128,128,25,1) forward + backward on a large synthetic graph (eager launches,
+    graph preparation cached and excluded).  Algorithmic FLOPs per SURVEY.md section 8(d): fwd + bwd = 3 x forward."""
+    import torch
+    from msmp_pde_b200 import layers, synth
+    g = synth.large_graph(n_nodes, degree, topology=topology, nodes_per_graph=100, seed=0)
+    t = {k: v.to(dev) for k, v in g.items()}
+    torch.manual_seed(0)
+    layer = layers.GNN_Layer(128, 128, 128, 25, 1).to(dev)
+    x = t["x"].clone().requires_grad_(True)
+
+    def step():
+        out = layer(x, t["u"], t["pos"], t["variables"], t["edge_index"], t["batch"])
+        out.backward(out.detach())
+        x.grad = None
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(reps):
+        step()
+    e.record()
+    torch.cuda.synchronize()
+    ms = s.elapsed_time(e) / reps
+    E = n_nodes * degree
+    alg = 3.0 * (E * (2 * 283 * 128 + 2 * 128 * 128) + n_nodes * (2 * 257 * 128 + 2 * 128 * 128))
+    del layer, x, t, g
+    torch.cuda.empty_cache()
+    return {"nodes": n_nodes, "in_degree": degree, "topology": topology, "ms_fwd_bwd": round(ms, 3),
+            "nodes_per_s": round(n_nodes / ms * 1e3), "algorithmic_tflops": round(alg / ms / 1e9, 1)}
+
+
+def tf32_peak(dev, seconds=1.0):
+    """cuBLAS TF32 dense throughput (8192^3) measured in this run: burst = best of 10, sustained = back to back for
+    `seconds`.  The error-compensated 3xTF32 GEMMs of the fp32 mode have a ceiling of one third of it."""
+    import torch
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        n = 8192
+        a = torch.randn(n, n, device=dev)
+        b = torch.randn(n, n, device=dev)
+        c = torch.empty(n, n, device=dev)
+        for _ in range(3):
+            torch.matmul(a, b, out=c)
+        torch.cuda.synchronize()
+        best = 1e9
+        for _ in range(10):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            torch.matmul(a, b, out=c)
+            e.record()
+            torch.cuda.synchronize()
+            best = min(best, s.elapsed_time(e))
+        reps = max(10, int(seconds * 1e3 / best))
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(reps):
+            torch.matmul(a, b, out=c)
+        e.record()
+        torch.cuda.synchronize()
+        sus = s.elapsed_time(e) / reps
+        fl = 2.0 * n ** 3
+        return {"burst_tflops": round(fl / best / 1e9, 1), "sustained_tflops": round(fl / sus / 1e9, 1),
+                "how": f"torch.matmul fp32 inputs, allow_tf32, {n}^3, best of 10 / {reps} back to back"}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from msmp_pde_b200 import models_gnn2D, ops
+    from msmp_pde_b200 import models_gnn2D, ops, synth
     from msmp_pde_b200.train_step import GraphedTrainStep
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    wl = args.workload
+    B = args.graphs_per_gpu or WORKLOADS[wl]["graphs"]
 
     def say(msg):
         if args.verbose:
             print(f"[bench rank {rank}] {msg}", file=sys.stderr, flush=True)
     saved_stdout = None
     if world > 1:
-        # CUDA-graph capture of NCCL collectives: the watchdog thread must not touch the capturing context
         os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")
         # NCCL writes its version banner to the C-level stdout; the contract is ONE JSON line there, so fd 1 points at
         # stderr until that line is printed
@@ -112,34 +257,31 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    pde, data, meta = _workload(rank)
+    dp_check = None
+    if world > 1:
+        # the data-parallel step against the single-GPU full-batch step on the same global batch, before any timing
+        from msmp_pde_b200.dp import dp_selfcheck
+        pde_c, data_c, meta_c = synth.config_c2(B=3 * world, nx=100, tw=TW, seed=11)
+
+        def make_model():
+            torch.manual_seed(0)
+            return models_gnn2D.MP_PDE_Solver2DLEMLinGated(pde_c, TW, 128, 6, meta_c["eq_variables"])
+        dp_check = dp_selfcheck(make_model, lambda m: torch.optim.AdamW(m.parameters(), lr=1e-4), data_c, dev)
+        dp_check["max_rel_err"] = max(dp_check["loss_rel_err"], dp_check["grad_max_rel_err"])
+        say(f"dp_check {dp_check}")
+    pde, data, meta = _make(synth, wl, B, rank)                  # float64 host tensors (the reference feeds float64)
     torch.manual_seed(0)
     model = models_gnn2D.MP_PDE_Solver2DLEMLinGated(pde, TW, 128, 6, meta["eq_variables"]).to(dev)
-    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, fused=True, capturable=True)      # train.py:410
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4)          # exactly experiments/train.py:410
     N, E = data.x.shape[0], data.edge_index.shape[1]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     resident = data.clone().to(dev)
     pinned = data.clone().apply(lambda t: t.pin_memory())
     h2d = sum(t.numel() * t.element_size() for t in (getattr(pinned, k) for k in pinned.keys())
               if torch.is_tensor(t) and t.is_floating_point())
-    # public API: the whole training step (fwd + loss + bwd + DP all-reduce + AdamW) as one CUDA graph
     say("model built")
     step = GraphedTrainStep(model, opt, resident, warmup=max(3, args.warmup), use_graph=not args.eager)
     say("step captured")
-
-    def timed(K, graph, read_loss):
-        evs = []
-        for _ in range(K):
-            flush.zero_()
-            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s.record()
-            loss = step(graph)          # graph=None: inputs already resident in HBM; else H2D copies inside
-            if read_loss:
-                loss.item()
-            e.record()
-            evs.append((s, e))
-        torch.cuda.synchronize()
-        return [s.elapsed_time(e) for s, e in evs]
 
     def barrier():
         if world > 1:
@@ -149,7 +291,7 @@ def run_ours(args):
     for _ in range(max(3, args.warmup)):
         step(None)
     barrier()
-    # ---- per-kernel events on the edge ops (roofline) need eager launches: one short eager pass, not timed as value
+    # ---- per-op CUDA events (roofline) need eager launches: one short eager pass, not part of `value`
     ops.PROFILE_EVENTS = {}
     ops.LAUNCHES = 0
     eager_ev = []
@@ -157,10 +299,10 @@ def run_ours(args):
         flush.zero_()
         eager_ev.append((torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)))
         eager_ev[-1][0].record()
-        step._eager_step()
+        step.eager()
         eager_ev[-1][1].record()
     torch.cuda.synchronize()
-    eager_ms = sum(a.elapsed_time(b) for a, b in eager_ev) / 3        # one eagerly launched step, same pass as the op events
+    eager_ms = sum(a.elapsed_time(b) for a, b in eager_ev) / 3
     launches_per_step = ops.LAUNCHES // 3
     kern = {}
     for k, v in ops.PROFILE_EVENTS.items():
@@ -173,20 +315,18 @@ def run_ours(args):
     sampler = ClockSampler(local)
     sampler.start()
     barrier()
-    times = timed(args.steps, None, False)
+    times = _time_step(step, flush, args.steps, None, False)
     barrier()
     # ---- end-to-end timing: host (pinned, float64) inputs -> device every step, loss read back
     for _ in range(2):
         step(pinned)
     barrier()
-    e2e_times = timed(args.steps, pinned, True)
+    e2e_times = _time_step(step, flush, args.steps, pinned, True)
     barrier()
     clocks = sampler.stop()
     say("timing done")
     launches = launches_per_step * args.steps
 
-    scatter = scatter_bandwidth(dev) if rank == 0 else None
-    message = message_bandwidth(dev) if rank == 0 else None
     ms = sum(times) / len(times)
     ms_e2e = sum(e2e_times) / len(e2e_times)
     t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
@@ -197,50 +337,68 @@ def run_ours(args):
     out = None
     if rank == 0:
         peaks = _peaks()
-        # per-op table (CUDA events around each C-ABI op in a short eager pass) and the dominant op's roofline
+        extras = world == 1 and not args.no_extras
+        tf32 = tf32_peak(dev) if extras else None
         table = {}
         for k, d in kern.items():
-            t = d["ms"] * 1e-3
+            tt = d["ms"] * 1e-3
             table[k] = {"ms_per_step": round(d["ms"], 4), "launches_per_step": round(d["n"], 1),
-                        "tflops": round(d["flops"] / t / 1e12, 2) if t > 0 else None,
-                        "gbs": round(d["bytes"] / t / 1e9, 1) if t > 0 else None}
+                        "tflops": round(d["flops"] / tt / 1e12, 2) if tt > 0 else None,
+                        "gbs": round(d["bytes"] / tt / 1e9, 1) if tt > 0 else None}
         dom = max(kern, key=lambda k: kern[k]["ms"]) if kern else None
         roof = None
         if dom:
             d = kern[dom]
             ach = d["flops"] / (d["ms"] * 1e-3) / 1e12
-            roof = {"kernel": "k_" + dom, "bound": "tensor", "achieved": round(ach, 3),
+            roof = {"kernel": KERNEL_OF_OP.get(dom, "k_" + dom), "bound": "tensor", "achieved": round(ach, 3),
                     "peak": peaks["tensor_tflops"], "unit": "TFLOP/s", "frac": round(ach / peaks["tensor_tflops"], 5),
                     "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH.get(dom), "avg_launch_ms": round(d["ms"] / max(d["n"], 1), 5),
                     "share_of_step": round(d["ms"] / sum(v["ms"] for v in kern.values()), 4),
-                    "eager_step_ms": round(eager_ms, 4),
-                    "peak_source": peaks["source"],
-                    "note": "tcgen05 kind::tf32, error-compensated 3xTF32 (fp32 parity): achieved = useful fp32 FLOPs "
-                            "of the op (the 3x MMA passes are not counted) / CUDA-event time of the op (kernel + its fixed-order "
-                            "split reduction) in an eagerly launched step; share_of_step = that time / the summed device "
-                            "time of all instrumented ops of the same eager step (`ops`; they cover ~90 % of the step's "
-                            "device time; the eager step itself is host-launch bound, eager_step_ms, and the timed value "
-                            "is a CUDA-graph replay in which ops overlap on several streams); "
-                            "peak = cuBLAS bf16 sustained, i.e. 6x the effective ceiling of 3xTF32"}
+                    "eager_step_ms": round(eager_ms, 4), "peak_source": peaks["source"],
+                    "note": "fp32 mode = tcgen05 kind::tf32, error-compensated 3xTF32: achieved = useful fp32 FLOPs of the op "
+                            "(the 3 MMA passes are not counted) / CUDA-event time of the op in an eagerly launched step; "
+                            "share_of_step = that time / the summed device time of all instrumented ops (`ops`); peak = cuBLAS "
+                            "bf16 sustained (MEASURED_PEAKS.json); the ceiling of a 3xTF32 GEMM is the TF32 rate / 3, see "
+                            "frac_of_3xtf32_ceiling"}
+            if tf32:
+                roof["tf32_peak_measured"] = tf32
+                roof["frac_of_3xtf32_ceiling"] = round(ach / (tf32["sustained_tflops"] / 3.0), 4)
         out = {
             "metric": METRIC, "value": round(world * N / (ms * 1e-3), 1), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": round(ms, 4), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "C2: MSMP-PDE2D (MP_PDE_Solver2DLEMLinGated) RP shape, 64 graphs x 100 nodes per GPU, "
-                                   "tw=25, 588 edges/graph, fwd+loss+bwd+AdamW",
-                       "nodes_per_gpu": N, "edges_per_gpu": E, "global_batch": world * B_PER_GPU,
-                       "parallelism": f"dp{world}", "l2": "flushed (256 MiB write) between timed steps"},
+            "config": {"workload": WORKLOADS[wl]["label"].format(B=B), "nodes_per_gpu": N, "edges_per_gpu": E,
+                       "global_batch": world * B, "parallelism": f"dp{world}",
+                       "optimizer": "torch.optim.AdamW(lr=1e-4) as experiments/train.py:410 builds it, driven by msmp_adamw_run",
+                       "l2": "flushed (256 MiB write) between timed steps"},
             "e2e": {"value": round(world * N / (ms_e2e * 1e-3), 1), "unit": UNIT, "ms_per_step": round(ms_e2e, 4),
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 8},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
-            "ops": table, "scatter_hbm": scatter, "message_hbm": message,
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "ops": table,
             "execution": ("eager launches" if args.eager else
                           "whole step captured as one CUDA graph (GraphedTrainStep)" if world == 1 else
-                          "three CUDA graphs per step (forward+loss | backward | AdamW) with the NCCL all-reduces of the "
-                          "loss terms and of the flat gradient bucket launched eagerly between them"),
+                          "two CUDA graphs per step (forward+loss+backward | optimizer) with ONE NCCL all-reduce of the flat "
+                          "gradient bucket (it carries the local squared error) launched between them"),
         }
-        if world == 1 and not args.no_cpu_baseline:
-            out["cpu_baseline"] = cpu_baseline(sample_graphs=8, steps=2)
+        if dp_check is not None:
+            out["dp_check"] = dp_check
+        if extras:
+            del step, model, opt, resident
+            torch.cuda.empty_cache()
+            say("sub-records")
+            subs = {}
+            for name, b in (("c2", 64), ("c3", 64), ("c4", 8)):
+                if name != wl:
+                    subs[name.upper()] = _sub_config(name, b, dev, flush, 10)
+            out["configs"] = subs
+            out["bf16_mode"] = _sub_config(wl, B, dev, flush, 10, precision="bf16")
+            out["bf16_mode"]["note"] = ("bf16 operands / fp32 accumulation in the GEMMs that have a bf16 variant (DESIGN.md "
+                                        "section 8 lists them and the measured tolerance); `value` above is the fp32-parity mode")
+            out["layer_c5"] = [_layer_c5(1 << 20, 6, "band", dev), _layer_c5(1 << 20, 6, "random", dev),
+                               _layer_c5(1 << 20, 16, "random", dev)]
+            out["scatter_hbm"] = scatter_bandwidth(dev)
+            out["message_hbm"] = message_bandwidth(dev)
+            if not args.no_cpu_baseline:
+                out["cpu_baseline"] = cpu_baseline(wl)
         if saved_stdout is not None:
             sys.stdout.flush()
             os.dup2(saved_stdout, 1)
@@ -249,6 +407,14 @@ def run_ours(args):
         dist.barrier()
         dist.destroy_process_group()
     return out
+
+
+KERNEL_OF_OP = {"wgrad_ws": "k_wgrad_ws", "wgrad_tc": "k_wgrad_tc", "linear_tc": "k_linear_tc / k_linear_ws",
+                "edge_ws_fwd": "k_edge_ws<fwd>", "edge_ws_bwd": "k_edge_ws<bwd>", "lem_tc_fwd": "k_lem_fwd_tc",
+                "lem_tc_bwd": "k_lem_bwd_tc", "segment_reduce": "k_segment_reduce"}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of the headline
+# workload (profiles/r2_*): filled in from the capture of the dominant kernel, None when no capture exists for it.
+NCU_TRAFFIC_BYTES_PER_LAUNCH = {}
 
 
 def scatter_bandwidth(dev, n_nodes=1 << 20, degree=6, reps=10):
@@ -283,20 +449,15 @@ def scatter_bandwidth(dev, n_nodes=1 << 20, degree=6, reps=10):
             "peak_gbs": peak}
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of the C2 shapes
-# (profiles/r1_final_kernels_ncu_raw.csv): the step's 53 weight-gradient launches are 36 node-level (9.9 MB), 12 edge-level
-# (38.6 MB), the two LEM ones (355 MB, 190 MB) and 3 small ones -> 25.7 MB on average, against 4 * M * (K + N) bytes
-# of operands (the algorithmic traffic: every operand element is read once).
-NCU_TRAFFIC_BYTES_PER_LAUNCH = {"wgrad_tc": 25.7e6}
-
-
 def message_bandwidth(dev, n_nodes=1 << 20, degree=6, reps=7):
     """The message kernels (fused gather + second message-MLP layer on the tensor pipe + mean aggregation, forward and
-    backward) on the config-5 shape, 1 Mi nodes x 6 Mi edges, as a fraction of the measured HBM copy peak.
-    Algorithmic bytes per edge (gathers counted without reuse): forward 2 x 512 gathered (P[dst],
-    Q[src]) + 512 written (z2) + 8 index = 1544; backward 4 x 512 read (dagg[dst], z2, P[dst], Q[src]) + 3 x 512 written
-    (dz2, a1, dz1) + 12 index/scale = 3596; plus 512 per node for the aggregated output.  'band' sources are neighbours
-    on a ring (gathers mostly hit L2), 'random' sources are uniform over the whole graph (every gather is an HBM row)."""
+    backward) on the config-5 shape, 1 Mi nodes x 6 Mi edges, as a fraction of the measured HBM copy peak, in COMPULSORY
+    bytes: every distinct row is counted once however often it is gathered (the destination-sorted edge list re-uses
+    P[dst] in-degree times; a gathered Q[src] row is also one of N distinct rows) --
+        forward : N*1024 (P | Q rows) + E*512 (z2 written) + E*8 (indices) + N*516 (agg, rowptr)
+        backward: N*1024 (P | Q) + N*512 (dagg) + E*512 (z2 read) + 3*E*512 (dz2, a1, dz1 written) + E*12 + N*512 (dP).
+    `*_noreuse_frac` counts every gather as an HBM row (upper bound of the traffic: 1544 / 3596 B per edge).  'band' sources
+    are neighbours on a ring, 'random' sources are uniform over the whole graph (gather-hostile)."""
     import torch
     from msmp_pde_b200 import ops, synth
     from msmp_pde_b200.graph import build_topology
@@ -308,7 +469,7 @@ def message_bandwidth(dev, n_nodes=1 << 20, degree=6, reps=7):
     dP = torch.empty(n_nodes, 128, device=dev)
     peak = _peaks()["hbm_gbs"]
     res = {"kernel": "k_edge_ws<fwd> / k_edge_ws<bwd>", "nodes": n_nodes, "edges": n_nodes * degree, "peak_gbs": peak,
-           "timing": f"CUDA events around the op (kernel + memset + carry fix-up), median of {reps} after 3 warm-ups"}
+           "timing": f"CUDA events around the op (kernel + carry fix-up), median of {reps} after 3 warm-ups"}
     for topo_name, npg in (("band", 100), ("random", 0)):
         g = synth.large_graph(n_nodes, degree, topology=topo_name, nodes_per_graph=npg, seed=0)
         topo = build_topology(g["edge_index"].to(dev), g["batch"].to(dev), n_nodes)
@@ -328,29 +489,37 @@ def message_bandwidth(dev, n_nodes=1 << 20, degree=6, reps=7):
                 tfs.append(ev[0].elapsed_time(ev[1]))
                 tbs.append(ev[1].elapsed_time(ev[2]))
         tf, tb = sorted(tfs)[len(tfs) // 2], sorted(tbs)[len(tbs) // 2]       # median of `reps`
-        bf, bb = E * 1544 + n_nodes * 512, E * 3596 + n_nodes * 512
-        res[topo_name] = {"fwd_ms": round(tf, 4), "fwd_gbs": round(bf / tf / 1e6, 1), "fwd_frac": round(bf / tf / 1e6 / peak, 4),
-                          "bwd_ms": round(tb, 4), "bwd_gbs": round(bb / tb / 1e6, 1), "bwd_frac": round(bb / tb / 1e6 / peak, 4),
+        cf = n_nodes * 1024 + E * 520 + n_nodes * 516
+        cb = n_nodes * 1024 + n_nodes * 512 + E * 512 + 3 * E * 512 + E * 12 + n_nodes * 512
+        nf, nb_ = E * 1544 + n_nodes * 512, E * 3596 + n_nodes * 512
+        res[topo_name] = {"fwd_ms": round(tf, 4), "fwd_compulsory_gbs": round(cf / tf / 1e6, 1),
+                          "fwd_compulsory_frac": round(cf / tf / 1e6 / peak, 4),
+                          "fwd_noreuse_frac": round(nf / tf / 1e6 / peak, 4),
+                          "bwd_ms": round(tb, 4), "bwd_compulsory_gbs": round(cb / tb / 1e6, 1),
+                          "bwd_compulsory_frac": round(cb / tb / 1e6 / peak, 4),
+                          "bwd_noreuse_frac": round(nb_ / tb / 1e6 / peak, 4),
                           "fwd_executed_tf32_tflops": round(3 * 2 * E * 128 * 128 / tf / 1e9, 1)}
         del topo, agg, z2
     return res
 
 
 # ------------------------------------------------------------------------------------------ reference
-def _oracle_step_time(B, steps, warmup, dtype_name="float64"):
-    """The reference's CPU path (oracle port, float64 = reference-native dtype) on all host cores."""
+def _oracle_step_time(workload, B, steps, warmup, budget_s=None):
+    """The reference's CPU path (oracle port, float64 = reference-native dtype) on all host cores.  Never loads the CUDA
+    library: `synth` is imported without the package __init__ (see _synth_module)."""
     import torch
-    from msmp_pde_b200 import synth
+    synth = _synth_module(load_native=False)
     from oracle import models as om
     torch.set_num_threads(os.cpu_count())
     prev = torch.get_default_dtype()
-    torch.set_default_dtype(getattr(torch, dtype_name))
+    torch.set_default_dtype(torch.float64)
     try:
-        pde, data, meta = synth.config_c2(B=B, nx=NX, tw=TW, seed=0, dtype=getattr(torch, dtype_name))
+        pde, data, meta = _make(synth, workload, B, 0, dtype=torch.float64)
         torch.manual_seed(0)
         model = om.MP_PDE_Solver2DLEMLinGated(pde, TW, 128, 6, meta["eq_variables"])
         opt = torch.optim.AdamW(model.parameters(), lr=1e-4)
         ts = []
+        t_start = time.perf_counter()
         for i in range(warmup + steps):
             t0 = time.perf_counter()
             opt.zero_grad()
@@ -359,35 +528,46 @@ def _oracle_step_time(B, steps, warmup, dtype_name="float64"):
             opt.step()
             if i >= warmup:
                 ts.append(time.perf_counter() - t0)
+            if budget_s is not None and len(ts) >= 1 and time.perf_counter() - t_start > budget_s:
+                break
     finally:
         torch.set_default_dtype(prev)
-    return sum(ts) / len(ts), data.x.shape[0]
+    return sum(ts) / len(ts), data.x.shape[0], len(ts)
 
 
-def cpu_baseline(sample_graphs=8, steps=2):
-    sec, n = _oracle_step_time(sample_graphs, steps, 1)
+def cpu_baseline(workload="c4"):
+    """Bounded sample for the N = 1 line: ONE step of the reference's CPU path after one warm-up step."""
+    B = 1 if workload == "c4" else 16
+    sec, n, k = _oracle_step_time(workload, B, 1, 1)
     return {"value": round(n / sec, 1), "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-            "sample": f"{sample_graphs} of the 64 graphs of the C2 batch ({n} nodes), {steps} steps after 1 warm-up, "
-                      f"float64 (reference-native), torch CPU with {os.cpu_count()} threads", "ms_per_step": round(sec * 1e3, 2)}
+            "sample": f"{B} of the {WORKLOADS[workload]['graphs']} graphs of the {workload.upper()} batch ({n} nodes), {k} step "
+                      f"after 1 warm-up, float64 (reference-native), torch CPU with {os.cpu_count()} threads",
+            "ms_per_step": round(sec * 1e3, 2)}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    B = 16          # bounded sample of the 64-graph batch: keeps --steps K --warmup W within minutes
-    steps, warmup = min(args.steps, 5), min(max(args.warmup, 1), 2)
-    sec, n = _oracle_step_time(B, steps, warmup)
+    wl = args.workload
+    full = args.graphs_per_gpu or WORKLOADS[wl]["graphs"]
+    B = min(REF_GRAPHS[wl], full)
+    # each step is a bounded sample (B whole graphs -- the path's independent units -- of the `full`-graph batch); the
+    # run stops adding timed steps once ~150 s are spent so that --steps K --warmup W stays within minutes
+    warmup = min(max(args.warmup, 1), 1)
+    sec, n, k = _oracle_step_time(wl, B, max(args.steps, 1), warmup, budget_s=150.0)
     v = round(n / sec, 1)
+    sample = (f"{B} of {full} graphs per step ({n} nodes), {k} timed steps after {warmup} warm-up, float64 "
+              f"(reference-native), torch CPU, {os.cpu_count()} threads")
     out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
-           "steps": steps, "warmup": warmup, "ms_per_step": round(sec * 1e3, 3), "higher_is_better": True, "scaling": "weak",
+           "steps": k, "warmup": warmup, "ms_per_step": round(sec * 1e3, 3), "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": "C2: MSMP-PDE2D RP shape (bounded sample: 16 of 64 graphs x 100 nodes), fwd+loss+bwd+AdamW, "
-                                  "oracle port of the reference CPU path (reference not importable: torch_geometric, "
-                                  "torch_scatter, torch_cluster, lem_cuda absent)"},
-           "cpu_baseline": {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-                            "sample": f"16 of 64 graphs ({n} nodes) x {steps} steps, float64, {os.cpu_count()} threads"},
-           "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+           "config": {"workload": WORKLOADS[wl]["label"].format(B=full), "sample": sample,
+                      "implementation": "oracle port of the reference CPU path (the reference itself is not importable: "
+                                        "torch_geometric, torch_scatter, torch_cluster, lem_cuda absent)"},
+           "cpu_baseline": {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample},
+           "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "native_library_loaded": any("libmsmp_b200" in l for l in open("/proc/self/maps"))}
     print(json.dumps(out), flush=True)
 
 
@@ -397,6 +577,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
+    ap.add_argument("--graphs-per-gpu", type=int, default=0)
+    ap.add_argument("--no-extras", action="store_true", help="skip the sub-records (other configs, bf16 mode, C5, HBM lines)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--verbose", action="store_true")
     ap.add_argument("--eager", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")

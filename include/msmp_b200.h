@@ -94,6 +94,22 @@ int msmp_linear_wgrad_tc2(const float* X, int ldx, int K0, const float* X1, int 
                           float* dWt, float* dWside, int accumulate, int M, void* workspace, size_t ws_bytes,
                           cudaStream_t stream);
 
+/* Second-generation weight gradient (csrc/wgrad_ws.cu): persistent warp-specialised CTAs, each owning a contiguous row
+ * range for every output tile; rows arrive by bulk copies (TMA engine), side / bias gradients come out of the same MMAs.
+ *   dWt[k][n] = sum_m [X0 | X1 | X2][m][k] dY[m][n],  dWside[q][n] = sum_m [side[m][side_c0 + q] (q < r) | 1][q] dY[m][n]
+ * X: nseg (<= 3) column segments, kx[s] % 32 == 0 (swish applied to segment s when xswish[s]); Nout % 128 == 0;
+ * side = base of a [M][lds] array with 16-byte aligned rows (lds <= 16), r + has_bias <= 8.
+ * part / part_side: [S][sum kx][Nout] / [S][r + has_bias][Nout] partials, S = msmp_wgrad_ws_splits(...)
+ * (msmp_wgrad_ws_workspace bytes for both, part_side directly behind part).  dWt != NULL: the partials are summed
+ * in split order into dWt / dWside by a second launch; dWt == NULL: the caller sums them (k_unpack, msmp_unpack_run).
+ * mode 0: error-compensated 3xTF32 (fp32 parity); mode 1: bf16 operands, fp32 accumulation.  Replaces the autograd
+ * weight gradients of experiments/models_gnn.py:47-58,310-313. */
+int msmp_wgrad_ws_splits(int M, int KB, int Nout, int nside);
+size_t msmp_wgrad_ws_workspace(int M, int KB, int Nout, int nside);
+int msmp_wgrad_ws(const float* const* X, const int* ldx, const int* kx, const int* xswish, int nseg, const float* dY,
+                  int lddy, int Nout, const float* side, int lds, int side_c0, int r, int has_bias, float* part,
+                  float* part_side, float* dWt, float* dWside, int accumulate, int M, int mode, cudaStream_t stream);
+
 /* ---- edge kernels (edges sorted by destination; rowptr = CSR offsets by destination) ------------
  * forward : agg[i] = inv_deg[i] * sum_{e -> i} sw( sw(P[dst e] + Q[src e]) W2^T + b2 );  z2 (optional) keeps
  *           the second pre-activation for the backward pass.  W2t[k][n] = W2[n][k]. */

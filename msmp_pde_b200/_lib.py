@@ -48,6 +48,9 @@ _SIGS = {
     "msmp_linear_wgrad": (I, [P, I, I, I, P, I, I, P, I, I, I, P, P, I, I, P, S, P]),
     "msmp_linear_wgrad_tc": (I, [P, I, I, I, P, I, I, P, I, I, I, P, P, I, I, P, S, P]),
     "msmp_linear_wgrad_tc2": (I, [P, I, I, P, I, I, I, P, I, I, P, I, I, I, P, P, I, I, P, S, P]),
+    "msmp_wgrad_ws_splits": (I, [I, I, I, I]),
+    "msmp_wgrad_ws_workspace": (S, [I, I, I, I]),
+    "msmp_wgrad_ws": (I, [P, P, P, P, I, P, I, I, P, I, I, I, I, P, P, P, P, I, I, I, P]),
     "msmp_edge_tiles": (I, [I]),
     "msmp_edge_grid": (I, [I]),
     "msmp_edge_fwd_workspace": (S, [I]),

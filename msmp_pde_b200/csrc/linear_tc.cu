@@ -47,6 +47,71 @@ struct LinTcParams {
   int Nout;
 };
 
+// ---- epilogue of one 32-row x 32-column accumulator block --------------------------------------------------------------
+// tcgen05.ld hands every thread 32 consecutive columns of ONE row; reading / writing global memory in that shape makes
+// each warp instruction touch 32 different rows 16 bytes at a time (32 sectors per request, half of every written sector
+// unused: ncu of the first role-split kernel).  The block therefore goes through a warp-private shared-memory tile in two
+// [32 rows x 16 columns] halves (pitch 20 floats; the (row, row + 4) pairing keeps every quarter-warp access conflict
+// free) so that a warp instruction covers 8 rows x 64 contiguous bytes: every sector fully used, 16 sectors per request,
+// and bias / side weights are per-thread constants of a half block.  Same arithmetic per output element as before.
+constexpr int EPI_TILE_FLOATS = 32 * 20;
+
+__device__ __forceinline__ float4 dswish4(float4 z) { return make_float4(dswish(z.x), dswish(z.y), dswish(z.z), dswish(z.w)); }
+
+__device__ __forceinline__ void lin_epilogue32(const LinTcParams& p, float* tb, const float (&v)[32], int row_base,
+                                               int colb, int lane) {
+  const int c = lane & 3, rl0 = (lane >> 3) + 4 * ((lane >> 2) & 1);
+#pragma unroll
+  for (int hb = 0; hb < 32; hb += 16) {
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      st4(tb + lane * 20 + 4 * j, make_float4(v[hb + 4 * j], v[hb + 4 * j + 1], v[hb + 4 * j + 2], v[hb + 4 * j + 3]));
+    __syncwarp();
+    const int col = colb + hb + 4 * c;
+    if (col >= p.Nout) continue;
+    const float4 b4 = p.bias ? ldg4(p.bias + col) : zero4();
+    float4 zm[4], rr[4];
+    if (p.Zmul) {
+#pragma unroll
+      for (int ps = 0; ps < 4; ++ps) {
+        const int row = row_base + 8 * ps + rl0;
+        zm[ps] = row < p.M ? ldg4(p.Zmul + (size_t)row * p.ldz + col) : zero4();
+      }
+    }
+    if (p.R) {
+#pragma unroll
+      for (int ps = 0; ps < 4; ++ps) {
+        const int row = row_base + 8 * ps + rl0;
+        rr[ps] = row < p.M ? ldg4(p.R + (size_t)row * p.ldr + col) : zero4();
+      }
+    }
+#pragma unroll
+    for (int ps = 0; ps < 4; ++ps) {
+      const int rl = 8 * ps + rl0;
+      const int row = row_base + rl;
+      if (row >= p.M) continue;
+      float4 z = *reinterpret_cast<const float4*>(tb + rl * 20 + 4 * c);
+      if (p.bias) z = add4(z, b4);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        if (q >= p.r) break;
+        const float sv = __ldg(p.side + (size_t)row * p.lds + q);
+        const float4 w = ldg4(p.Wside + (size_t)q * p.ldws + col);
+        z.x = fmaf(sv, w.x, z.x);
+        z.y = fmaf(sv, w.y, z.y);
+        z.z = fmaf(sv, w.z, z.z);
+        z.w = fmaf(sv, w.w, z.w);
+      }
+      if (p.Zmul) z = mul4(z, dswish4(zm[ps]));
+      if (p.Ypre) st4(p.Ypre + (size_t)row * p.ldpre + col, z);
+      if (p.act) z = swish4(z);
+      if (p.R) z = add4(z, rr[ps]);
+      st4(p.Y + (size_t)row * p.ldy + col, z);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256, 1) k_linear_tc(const LinTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -159,54 +224,18 @@ __global__ void __launch_bounds__(256, 1) k_linear_tc(const LinTcParams p) {
     mbar_wait_warp(&bars[4 + (last & 1)], (last >> 1) & 1);
     tc_fence_after();
   }
-  // ---- epilogue: warp w reads lanes 32*(w&3).., columns 64*(w>>2)..
-  const int row = row0 + 32 * (warp & 3) + lane;
-  const int n0 = ntile * 128;
-  float sv[8];
-#pragma unroll
-  for (int q = 0; q < 8; ++q) sv[q] = (q < p.r && row < p.M) ? __ldg(p.side + (size_t)row * p.lds + q) : 0.f;
+  // ---- epilogue: warp w reads lanes 32*(w&3).., columns 64*(w>>2)..; the operand ring is free now (the last commit
+  // covers every MMA) and serves as the warps' transposition tiles
+  {
+    float* tb = reinterpret_cast<float*>(smem) + warp * EPI_TILE_FLOATS;
+    const int n0 = ntile * 128;
 #pragma unroll 1
-  for (int cb = 0; cb < 2; ++cb) {
-    const int colbase = 64 * (warp >> 2) + 32 * cb;
-    float v[32];
-    __syncwarp();
-    tmem_ld32(tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)colbase, v);
-    if (row < p.M) {
-      const int colb = n0 + colbase;
-      // issue every global load of this 32-column block first (the epilogue is latency bound otherwise)
-      float4 zm[8], rr[8];
-      if (p.Zmul) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) zm[j] = (colb + 4 * j < p.Nout) ? ldg4(p.Zmul + (size_t)row * p.ldz + colb + 4 * j) : zero4();
-      }
-      if (p.R) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) rr[j] = (colb + 4 * j < p.Nout) ? ldg4(p.R + (size_t)row * p.ldr + colb + 4 * j) : zero4();
-      }
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const int col = colb + j;
-        if (col >= p.Nout) continue;
-        float4 z = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        if (p.bias) z = add4(z, ldg4(p.bias + col));
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          if (q >= p.r) break;
-          float4 w = ldg4(p.Wside + (size_t)q * p.ldws + col);
-          z.x = fmaf(sv[q], w.x, z.x);
-          z.y = fmaf(sv[q], w.y, z.y);
-          z.z = fmaf(sv[q], w.z, z.z);
-          z.w = fmaf(sv[q], w.w, z.w);
-        }
-        if (p.Zmul) {
-          const float4 zz = zm[j >> 2];
-          z = mul4(z, make_float4(dswish(zz.x), dswish(zz.y), dswish(zz.z), dswish(zz.w)));
-        }
-        if (p.Ypre) st4(p.Ypre + (size_t)row * p.ldpre + col, z);
-        if (p.act) z = swish4(z);
-        if (p.R) z = add4(z, rr[j >> 2]);
-        st4(p.Y + (size_t)row * p.ldy + col, z);
-      }
+    for (int cb = 0; cb < 2; ++cb) {
+      const int colbase = 64 * (warp >> 2) + 32 * cb;
+      float v[32];
+      __syncwarp();
+      tmem_ld32(tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)colbase, v);
+      lin_epilogue32(p, tb, v, row0 + 32 * (warp & 3), n0 + colbase, lane);
     }
   }
   tc_fence_before();
@@ -229,7 +258,7 @@ constexpr int LW_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;                // A hi |
 constexpr int LW_EPI_WARPS = 8, LW_PROD_WARPS = 8;
 constexpr int LW_MMA_WARP = LW_EPI_WARPS + LW_PROD_WARPS;              // 16; warp 17 = weight loader; 18, 19 idle
 constexpr int LW_THREADS = 32 * (LW_MMA_WARP + 4);
-constexpr int LW_SMEM = 1024 + LW_STAGES * LW_STAGE_BYTES + 256;
+constexpr int LW_SMEM = 1024 + LW_STAGES * LW_STAGE_BYTES + 256 + LW_EPI_WARPS * EPI_TILE_FLOATS * 4;
 
 __global__ void __launch_bounds__(LW_THREADS, 1) k_linear_ws(const LinTcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -277,63 +306,22 @@ __global__ void __launch_bounds__(LW_THREADS, 1) k_linear_ws(const LinTcParams p
       const int t = blockIdx.x + i * gridDim.x;
       const int row0 = (t / nct) * 128, ntile = t % nct;
       const int buf = i & 1;
-      const int row = row0 + 32 * (warp & 3) + lane;
       const int n0 = ntile * 128;
-      float sv[8];
-#pragma unroll
-      for (int q = 0; q < 8; ++q) sv[q] = (q < p.r && row < p.M) ? __ldg(p.side + (size_t)row * p.lds + q) : 0.f;
+      float* tb = reinterpret_cast<float*>(smem + LW_STAGES * LW_STAGE_BYTES + 256) + warp * EPI_TILE_FLOATS;
       mbar_wait_backoff(&acc_full[buf], (i >> 1) & 1);
       tc_fence_after();
+      const uint32_t ta = tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(128 * buf + 64 * (warp >> 2));
 #pragma unroll 1
       for (int cb = 0; cb < 2; ++cb) {
-        const int colbase = 64 * (warp >> 2) + 32 * cb;
         float v[32];
         __syncwarp();
-        tmem_ld32(tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(128 * buf + colbase), v);
+        tmem_ld32(ta + 32 * cb, v);
         if (cb == 1) {          // accumulator drained: the MMA warp may start the tile after next
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&acc_empty[buf]);
         }
-        if (row < p.M) {
-#pragma unroll
-          for (int hb = 0; hb < 32; hb += 16) {          // 16 columns at a time: their loads first, then the math
-            const int colb = n0 + colbase + hb;
-            float4 zm[4], rr[4];
-            if (p.Zmul) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) zm[j] = (colb + 4 * j < p.Nout) ? ldg4(p.Zmul + (size_t)row * p.ldz + colb + 4 * j) : zero4();
-            }
-            if (p.R) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) rr[j] = (colb + 4 * j < p.Nout) ? ldg4(p.R + (size_t)row * p.ldr + colb + 4 * j) : zero4();
-            }
-#pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-              const int col = colb + j;
-              if (col >= p.Nout) continue;
-              float4 z = make_float4(v[hb + j], v[hb + j + 1], v[hb + j + 2], v[hb + j + 3]);
-              if (p.bias) z = add4(z, ldg4(p.bias + col));
-#pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                if (q >= p.r) break;
-                float4 w = ldg4(p.Wside + (size_t)q * p.ldws + col);
-                z.x = fmaf(sv[q], w.x, z.x);
-                z.y = fmaf(sv[q], w.y, z.y);
-                z.z = fmaf(sv[q], w.z, z.z);
-                z.w = fmaf(sv[q], w.w, z.w);
-              }
-              if (p.Zmul) {
-                const float4 zz = zm[j >> 2];
-                z = mul4(z, make_float4(dswish(zz.x), dswish(zz.y), dswish(zz.z), dswish(zz.w)));
-              }
-              if (p.Ypre) st4(p.Ypre + (size_t)row * p.ldpre + col, z);
-              if (p.act) z = swish4(z);
-              if (p.R) z = add4(z, rr[j >> 2]);
-              st4(p.Y + (size_t)row * p.ldy + col, z);
-            }
-          }
-        }
+        lin_epilogue32(p, tb, v, row0 + 32 * (warp & 3), n0 + 64 * (warp >> 2) + 32 * cb, lane);
       }
     }
   } else if (warp >= LW_MMA_WARP) {

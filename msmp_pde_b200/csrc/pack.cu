@@ -60,8 +60,11 @@ __global__ void __launch_bounds__(256) k_pack(const PackJob* __restrict__ jobs) 
 // The inverse direction, once per backward pass: the weight-gradient kernels leave their results in the kernels'
 // k-major layouts inside one raw buffer ([K][N] blocks, side / bias rows); ONE launch scatters them into the
 // parameter-layout gradients (param.grad), overwriting them:
-//     dst[n * ldd + k] = src0[k * ld0 + n] (+ sign1 * src1[k * ld1 + n])      n < rows, k < cols     (or 0 if `zero`)
-// i.e. a transposed copy with an optional second signed source (the +/- rows of the factorised first message layer).
+//     dst[n * ldd + k] = sum_s src0[s * sstride0 + k * ld0 + n] (+ sign1 * sum_s src1[s * sstride1 + k * ld1 + n])
+//                                                                            n < rows, k < cols     (or 0 if `zero`)
+// i.e. a transposed copy with an optional second signed source (the +/- rows of the factorised first message layer).  A
+// source may be the `nsplit` split-M partials of a weight-gradient launch (wgrad_ws.cu): they are summed here in split
+// order (fixed => deterministic), which replaces one reduction launch per weight gradient.
 struct UnpackJob {
   float* dst;
   const float* src0;
@@ -73,6 +76,9 @@ struct UnpackJob {
   int cols;
   float sign1;
   int zero;
+  int nsplit;          // >= 1
+  int sstride0;        // floats between consecutive partials of src0 / src1
+  int sstride1;
 };
 
 __global__ void __launch_bounds__(256) k_unpack(const UnpackJob* __restrict__ jobs) {
@@ -87,8 +93,23 @@ __global__ void __launch_bounds__(256) k_unpack(const UnpackJob* __restrict__ jo
       const int k = k0 + y, n = n0 + tx;
       float v = 0.f;
       if (!j.zero && k < j.cols && n < j.rows) {
-        v = j.src0[(size_t)k * j.ld0 + n];
-        if (j.src1) v += j.sign1 * j.src1[(size_t)k * j.ld1 + n];
+        const float* s0 = j.src0 + (size_t)k * j.ld0 + n;
+        int s = 0;
+        for (; s + 4 <= j.nsplit; s += 4) {          // four loads in flight, added in split order
+          const float a = s0[(size_t)s * j.sstride0], b = s0[(size_t)(s + 1) * j.sstride0];
+          const float c = s0[(size_t)(s + 2) * j.sstride0], d = s0[(size_t)(s + 3) * j.sstride0];
+          v += a;
+          v += b;
+          v += c;
+          v += d;
+        }
+        for (; s < j.nsplit; ++s) v += s0[(size_t)s * j.sstride0];
+        if (j.src1) {
+          const float* s1 = j.src1 + (size_t)k * j.ld1 + n;
+          float w = 0.f;
+          for (int q = 0; q < j.nsplit; ++q) w += s1[(size_t)q * j.sstride1];
+          v += j.sign1 * w;
+        }
       }
       tile[y][tx] = v;
     }
@@ -110,7 +131,7 @@ extern "C" int msmp_unpack_job_bytes(void) { return (int)sizeof(msmp::UnpackJob)
 extern "C" int msmp_unpack_run(const void* jobs_dev, int njobs, int max_tiles, cudaStream_t stream) {
   if (njobs < 0 || max_tiles < 1) return MSMP_ERR_ARG;
   if (njobs == 0) return MSMP_OK;
-  dim3 grid(max_tiles < 16 ? max_tiles : 16, njobs);
+  dim3 grid(max_tiles < 32 ? max_tiles : 32, njobs);
   msmp::k_unpack<<<grid, 256, 0, stream>>>(reinterpret_cast<const msmp::UnpackJob*>(jobs_dev));
   MSMP_CHECK_LAUNCH();
   return MSMP_OK;

@@ -1,0 +1,455 @@
+// Weight gradients, second generation: persistent, warp-specialised, every operand read from HBM exactly once.
+//
+//     dWt[k][n]    = sum_m [X0 | X1 | X2][m][k] * dY[m][n]           (k < KB)
+//     dWside[q][n] = sum_m [side[m][c0..c0+r) | 1][q] * dY[m][n]     (q < r + has_bias)
+//
+// (dW4 / dW3 / dW2 / dWpq of a message-passing layer, experiments/models_gnn.py:47-58 via autograd; the LEM maps,
+// models_gnn.py:310-313; the embedding / output Linear layers.)  k_wgrad_tc (wgrad_tc.cu) gave every 128 x 128 output
+// tile its own CTAs, so X and dY were re-read once per tile, each CTA ran load -> split -> MMA back to back, and a second
+// launch summed the split-M partials.  Here ONE CTA owns a contiguous range of rows m for ALL output tiles it can hold
+// in tensor memory:
+//
+//   16 producer warps in four groups; a group owns every fourth 16-row chunk: it issues all loads of the chunk (fp32
+//                    rows of dY, up to three X segments, the side columns; coalesced LDG.128, ~25 KB in flight per
+//                    group), applies the optional swish and writes bf16 operand images (MN-major, SWIZZLE_128B) into
+//                    an image ring -- while one group waits for its rows the others convert theirs.
+//                    fp32-parity mode: every fp32 value is split EXACTLY into three bf16 pieces x = b0 + b1 + b2 (+ 2^-24 x)
+//                    -> three images per operand; bf16 mode: one image (x rounded to bf16).  The side columns and the
+//                    bias "ones" column are 32 extra columns of the B operand, so side / bias gradients come out of the
+//                    same MMAs (no CUDA-core accumulation)
+//   MMA warp       : D'[n][k] += dY^T [X | side | 1]  -- dY blocks (128 columns) are the A operand (M = 128), the whole
+//                    X row (up to 256 + 32 columns, N <= 256 per instruction) is the B operand, K = 16 rows per MMA
+//                    (kind::f16, bf16 inputs, fp32 accumulation).  fp32-parity mode issues the six products
+//                    a0 b0, a0 b1, a1 b0, a1 b1, a0 b2, a2 b0 (every bf16 x bf16 product is exact in fp32; the dropped terms
+//                    are <= 2^-24 relative, i.e. fp32 rounding level: measured 2e-7 of max|ref| against float64) -- the same
+//                    tensor-pipe time as 3xTF32 (6 x K16 bf16 = 6 x K8 tf32 per 16 rows) with 25 % fewer operand bytes, and
+//                    it only needs the 16-bit MN-major layout (the 32-bit one, SWIZZLE_128B_BASE32B, is used by
+//                    wgrad_tc.cu with 32-row blocks; with 16-row blocks its B operand read wrong columns on hardware).
+//                    bf16 mode issues the a0 b0 product only.  Accumulators (lanes = n, columns = k) stay in TMEM for the
+//                    CTA's whole row range
+//   epilogue       : the producer warps drain TMEM into the CTA's partial [K][Nout] (coalesced 128-byte lines)
+//
+// The partials of the S row ranges are summed in a fixed order -- by k_reduce_partials2 (plain autograd use), or for free
+// inside the one k_unpack launch that ends the captured training step's backward pass (gradsink.py): then a weight
+// gradient is ONE launch.  Deterministic, no atomics.
+#include <cstdlib>
+#include <cuda_bf16.h>
+#include "umma.cuh"
+#include "msmp_b200.h"
+
+namespace msmp {
+
+constexpr int WW_R = 16;                 // rows (the MMA K dimension) per chunk
+constexpr int WW_PROD_WARPS = 16;        // the fp32 -> bf16-piece conversion is ALU / latency bound: 8 warps left the SM idle
+constexpr int WW_GROUP_WARPS = 4;        // producer warps that share one chunk
+constexpr int WW_GROUPS = WW_PROD_WARPS / WW_GROUP_WARPS;
+constexpr int WW_GT = 32 * WW_GROUP_WARPS;
+constexpr int WW_MAXU = 8;               // 8-column units per producer thread and chunk: 16 rows x (256 + 256) columns at most
+constexpr int WW_MMA_WARP = WW_PROD_WARPS;
+constexpr int WW_THREADS = 32 * (WW_PROD_WARPS + 1);
+constexpr int WW_MAX_IMG = 6;
+constexpr int WW_SMEM_LIMIT = 232448;    // 227 KiB
+
+struct WgradWsParams {
+  const float* X[3];
+  int ldx[3];
+  int kx[3];
+  int xsw[3];
+  int nseg;
+  int KB;              // sum of kx: rows of dWt
+  const float* dY;
+  int lddy;
+  int Nout;
+  const float* side;   // base of the [M][lds] side array (16-byte aligned rows)
+  int lds;
+  int side_c0;         // first side column used
+  int r;
+  int has_bias;
+  int KBS;             // B operand width = KB + 32 when side / bias rows are wanted: accumulator columns per dY block
+  int npc;             // dY columns per CTA (128 or 256)
+  float* part;         // [S][KB][Nout]
+  float* part_side;    // [S][r + has_bias][Nout]
+  int M;
+  int rows_per_split;
+  int nimg;            // image ring depth
+  int img_bytes;
+  int tmem_cols;
+};
+
+// byte offset of (row m, 16-byte chunk c8 = 8 bf16 columns) in an MN-major SWIZZLE_128B image (64 columns per block)
+__device__ __forceinline__ uint32_t ww_off16(int m, int c8) {
+  return (uint32_t)((c8 >> 3) * (WW_R * 128) + m * 128 + (((c8 ^ m) & 7) << 4));
+}
+__device__ __forceinline__ uint4 pack_bf16x8(float4 a, float4 b) {
+  __nv_bfloat162 p0 = __floats2bfloat162_rn(a.x, a.y), p1 = __floats2bfloat162_rn(a.z, a.w);
+  __nv_bfloat162 p2 = __floats2bfloat162_rn(b.x, b.y), p3 = __floats2bfloat162_rn(b.z, b.w);
+  uint4 o;
+  o.x = *reinterpret_cast<uint32_t*>(&p0);
+  o.y = *reinterpret_cast<uint32_t*>(&p1);
+  o.z = *reinterpret_cast<uint32_t*>(&p2);
+  o.w = *reinterpret_cast<uint32_t*>(&p3);
+  return o;
+}
+// x = b0 + b1 + b2 (+ <= 2^-25 |x|): b0 = bf16_rn(x) (one cvt.rn.bf16x2 per pair; |x - b0| <= 2^-9 |x|, either sign),
+// b1 = the upper 16 bits of r1 = x - b0 (truncation: one LOP, |r1 - b1| < 2^-7 |r1|), b2 = bf16_rn(r1 - b1).  Both
+// subtractions are exact.  The products the MMA warp leaves out (a1 b2, a2 b1, a2 b2) are then <= 2^-24 of |a b| and of
+// random sign.
+__device__ __forceinline__ uint32_t hi16x2(float lo_elem, float hi_elem) {      // {bf16_trunc(hi_elem), bf16_trunc(lo_elem)}
+  return __byte_perm(__float_as_uint(lo_elem), __float_as_uint(hi_elem), 0x7632);
+}
+__device__ __forceinline__ uint32_t rn16x2(float lo_elem, float hi_elem) {
+  __nv_bfloat162 p = __floats2bfloat162_rn(lo_elem, hi_elem);
+  return *reinterpret_cast<uint32_t*>(&p);
+}
+__device__ __forceinline__ void split_pair(float x0, float x1, uint32_t& p0, uint32_t& p1, uint32_t& p2) {
+  p0 = rn16x2(x0, x1);
+  const float r0 = x0 - __uint_as_float(p0 << 16), r1 = x1 - __uint_as_float(p0 & 0xffff0000u);
+  p1 = hi16x2(r0, r1);
+  p2 = rn16x2(r0 - __uint_as_float(__float_as_uint(r0) & 0xffff0000u), r1 - __uint_as_float(__float_as_uint(r1) & 0xffff0000u));
+}
+// the NP (1 or 3) bf16 images of 8 consecutive fp32 values -> one 16-byte chunk per image
+template <int NP>
+__device__ __forceinline__ void store_pieces(uint8_t* img, uint32_t piece_bytes, uint32_t off, float4 v0, float4 v1) {
+  if (NP == 1) {
+    *reinterpret_cast<uint4*>(img + off) = pack_bf16x8(v0, v1);
+  } else {
+    uint4 q0, q1, q2;
+    split_pair(v0.x, v0.y, q0.x, q1.x, q2.x);
+    split_pair(v0.z, v0.w, q0.y, q1.y, q2.y);
+    split_pair(v1.x, v1.y, q0.z, q1.z, q2.z);
+    split_pair(v1.z, v1.w, q0.w, q1.w, q2.w);
+    *reinterpret_cast<uint4*>(img + off) = q0;
+    *reinterpret_cast<uint4*>(img + piece_bytes + off) = q1;
+    *reinterpret_cast<uint4*>(img + 2 * piece_bytes + off) = q2;
+  }
+}
+// Instruction descriptor, kind::f16 with bf16 operands, fp32 accumulate
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_major, int b_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_major << 15) | ((uint32_t)b_major << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+template <int MODE>      // 0: fp32 parity (three bf16 pieces per operand, six products), 1: bf16 operands
+__global__ void __launch_bounds__(WW_THREADS, 1) k_wgrad_ws(const WgradWsParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* img_ring = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(img_ring + p.nimg * p.img_bytes);
+  uint64_t* img_full = bars;                       // [6] producer group -> MMA
+  uint64_t* img_empty = img_full + WW_MAX_IMG;     // [6] MMA -> producers
+  uint64_t* acc_full = img_empty + WW_MAX_IMG;     // [1] MMA -> epilogue
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  const int tid = threadIdx.x, warp = warp_index_uniform(), lane = tid & 31;
+  const int split = blockIdx.x;
+  const int n0 = blockIdx.y * p.npc;
+  const int npc_here = min(p.npc, p.Nout - n0);
+  const int nb = npc_here >> 7;                                   // 128-column dY blocks of this CTA
+  const int m_begin = split * p.rows_per_split;
+  const int m_end = min(p.M, m_begin + p.rows_per_split);
+  const int nchunks = (m_end > m_begin) ? (m_end - m_begin + WW_R - 1) / WW_R : 0;
+  const int nside = p.r + p.has_bias;
+
+  if (warp == WW_MMA_WARP) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  if (tid == 0) {
+    for (int i = 0; i < WW_MAX_IMG; ++i) {
+      mbar_init(&img_full[i], WW_GROUP_WARPS);
+      mbar_init(&img_empty[i], 1);
+    }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  // image stage layout: NP bf16 images of A (dY), then NP bf16 images of B ([X | side])
+  constexpr int NP = (MODE == 0) ? 3 : 1;
+  const int a_bytes = WW_R * p.npc * 2;                          // one A image
+  const int b_bytes = WW_R * ((p.KBS + 63) & ~63) * 2;           // one B image
+
+  if (warp == WW_MMA_WARP) {
+    // ============================================================================= MMA warp
+    const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
+    const bool leader = elect_one();
+    const int w0 = p.KBS < 256 ? p.KBS : 256, w1 = p.KBS - w0;          // B operand pieces (N <= 256 per MMA)
+    const uint32_t id0 = umma_idesc_bf16(128, w0, 1, 1);
+    const uint32_t id1 = umma_idesc_bf16(128, w1 ? w1 : 16, 1, 1);
+    constexpr uint32_t LBO = WW_R * 128;
+    // products (A piece, B piece) in issue order
+    constexpr int NPROD = (MODE == 0) ? 6 : 1;
+    constexpr int PA[6] = {0, 0, 1, 1, 0, 2}, PB[6] = {0, 1, 0, 1, 2, 0};
+    int j = 0;
+    uint32_t ph = 0;
+#pragma unroll 1
+    for (int c = 0; c < nchunks; ++c) {
+      mbar_wait_backoff(&img_full[j], ph);
+      tc_fence_after();
+      const uint32_t a_img = smem_u32(img_ring + j * p.img_bytes), b_img = a_img + NP * a_bytes;
+      // (product loop outside, dY-block loop inside: with the loops nested the other way round nvcc 12.9 emitted a
+      // uniform-predicate conversion of the accumulate flag that dropped accumulations -- caught by tests/test_wgrad_ws_gpu.py)
+#pragma unroll
+      for (int q = 0; q < NPROD; ++q) {
+        const uint32_t acc = (c | q) ? 1u : 0u;
+        const uint32_t ap = a_img + PA[q] * a_bytes, bp = b_img + PB[q] * b_bytes;
+        for (int jb = 0; jb < nb; ++jb) {
+          const uint32_t d = tm + (uint32_t)(jb * p.KBS);
+          const uint64_t da = umma_desc(ap + (uint32_t)jb * (2 * LBO), LBO, 1024, 2);
+          const uint64_t db0 = umma_desc(bp, LBO, 1024, 2);
+          if (leader) umma_bf16(d, da, db0, id0, acc);
+          if (w1) {
+            const uint64_t db1 = umma_desc(bp + 4 * LBO, LBO, 1024, 2);
+            if (leader) umma_bf16(d + 256, da, db1, id1, acc);
+          }
+        }
+      }
+      if (leader) {
+        umma_commit(&img_empty[j]);
+        if (c == nchunks - 1) umma_commit(acc_full);
+      }
+      __syncwarp();
+      if (++j == p.nimg) {
+        j = 0;
+        ph ^= 1;
+      }
+    }
+  } else {
+    // ============================================================================= producers, then epilogue
+    // Four groups of four warps; group g converts the chunks g, g + 4, ...: while one group waits for its rows the others
+    // convert theirs (a single group of 16 warps in lockstep spent most of a chunk's time in its waits).  A thread owns up
+    // to WW_MAXU 8-column units of the virtual row [dY | X0 | X1 | X2]; all of a chunk's loads are issued before the
+    // first conversion, so a group keeps ~25 KB in flight.
+    const int grp = warp / WW_GROUP_WARPS, gt = tid - grp * WW_GT;
+    const int a8 = npc_here >> 3;                          // units of the dY part
+    const int upr = (npc_here + p.KB) >> 3;                // units per virtual row
+    const uint32_t inv = 0xffffffffu / (uint32_t)upr + 1u; // u / upr == umulhi(u, inv) for u < 65536
+    const int total = WW_R * upr;
+    const int k8_0 = p.kx[0] >> 3, k8_1 = p.nseg > 1 ? (p.kx[1] >> 3) : (1 << 30);
+#pragma unroll 1
+    for (int c = grp; c < nchunks; c += WW_GROUPS) {
+      const int m0 = m_begin + c * WW_R;
+      const int nrows = min(WW_R, m_end - m0);
+      const int j = c % p.nimg, use = c / p.nimg;
+      float4 v[WW_MAXU][2];
+#pragma unroll
+      for (int i = 0; i < WW_MAXU; ++i) {
+        const int u = gt + i * WW_GT;
+        v[i][0] = zero4();
+        v[i][1] = zero4();
+        if (u < total) {
+          const int m = (int)__umulhi((uint32_t)u, inv), cu = u - m * upr;
+          if (m < nrows) {
+            const float* src;
+            if (cu < a8) {
+              src = p.dY + (size_t)(m0 + m) * p.lddy + n0 + 8 * cu;
+            } else {
+              int k = cu - a8, sgm = 0;
+              if (k >= k8_0) {
+                k -= k8_0;
+                sgm = 1;
+                if (k >= k8_1) {
+                  k -= k8_1;
+                  sgm = 2;
+                }
+              }
+              src = p.X[sgm] + (size_t)(m0 + m) * p.ldx[sgm] + 8 * k;
+            }
+            v[i][0] = ldg4(src);
+            v[i][1] = ldg4(src + 4);
+          }
+        }
+      }
+      // [side | 1 | 0...]: the last 32 columns of the B images, 4 units per row
+      float e[8];
+      const int sm_ = gt >> 2, sc8 = gt & 3;
+      if (nside && gt < WW_R * 4) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int col = 8 * sc8 + q;
+          e[q] = (sm_ >= nrows) ? 0.f : (col < p.r) ? __ldg(p.side + (size_t)(m0 + sm_) * p.lds + p.side_c0 + col)
+                                         : (col == p.r && p.has_bias) ? 1.0f : 0.f;
+        }
+      }
+      if (use > 0) mbar_wait_backoff(&img_empty[j], (uint32_t)(use - 1) & 1u);
+      uint8_t* a_img = img_ring + j * p.img_bytes;
+      uint8_t* b_img = a_img + NP * a_bytes;
+#pragma unroll
+      for (int i = 0; i < WW_MAXU; ++i) {
+        const int u = gt + i * WW_GT;
+        if (u < total) {
+          const int m = (int)__umulhi((uint32_t)u, inv), cu = u - m * upr;
+          if (cu < a8) {
+            store_pieces<NP>(a_img, a_bytes, ww_off16(m, cu), v[i][0], v[i][1]);
+          } else {
+            const int k = cu - a8;
+            const int sgm = k < k8_0 ? 0 : (k - k8_0 < k8_1 ? 1 : 2);
+            float4 x0 = v[i][0], x1 = v[i][1];
+            if (p.xsw[sgm]) {
+              x0 = swish4(x0);
+              x1 = swish4(x1);
+            }
+            store_pieces<NP>(b_img, b_bytes, ww_off16(m, k), x0, x1);
+          }
+        }
+      }
+      if (nside && gt < WW_R * 4)
+        store_pieces<NP>(b_img, b_bytes, ww_off16(sm_, (p.KB >> 3) + sc8), make_float4(e[0], e[1], e[2], e[3]),
+                         make_float4(e[4], e[5], e[6], e[7]));
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&img_full[j]);
+    }
+    // ---- epilogue: TMEM lanes = n (32 per warp quadrant), columns = k; 32-column groups are dealt to the four
+    // warps of a quadrant; every store instruction writes one 128-byte line of the partial
+    if (nchunks > 0) {
+      mbar_wait_backoff(acc_full, 0);
+      tc_fence_after();
+    }
+    const int quad = warp & 3, part = warp >> 2;                  // 4 warps per TMEM lane quadrant
+    float* out = p.part + (size_t)split * p.KB * p.Nout;
+    float* out_side = p.part_side + (size_t)split * nside * p.Nout;
+    const int ngroups = p.KBS >> 5;
+#pragma unroll 1
+    for (int jb = 0; jb < nb; ++jb) {
+      const int n = n0 + jb * 128 + 32 * quad + lane;
+#pragma unroll 1
+      for (int g = part; g < ngroups; g += WW_PROD_WARPS / 4) {
+        float v[32];
+        if (nchunks > 0) {
+          __syncwarp();
+          tmem_ld32(tmem + ((uint32_t)(32 * quad) << 16) + (uint32_t)(jb * p.KBS + 32 * g), v);
+        } else {
+#pragma unroll
+          for (int q = 0; q < 32; ++q) v[q] = 0.f;
+        }
+        const int k0 = 32 * g;
+        if (k0 < p.KB) {
+#pragma unroll
+          for (int q = 0; q < 32; ++q) out[(size_t)(k0 + q) * p.Nout + n] = v[q];
+        } else {
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            if (q < nside) out_side[(size_t)q * p.Nout + n] = v[q];
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == WW_MMA_WARP) tmem_dealloc(tmem, (uint32_t)p.tmem_cols);
+}
+
+static int ww_env(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
+// geometry of one call: dY columns per CTA, ring depths, splits.  Returns false when the shape is not supported.
+static bool ww_plan(int M, int KB, int Nout, int nside, int lds, int mode, WgradWsParams& p, int& S, int& ny, int& smem) {
+  if (KB <= 0 || (KB & 31) || Nout <= 0 || (Nout & 127) || nside < 0 || nside > 8) return false;
+  const int KBS = KB + (nside ? 32 : 0);
+  if (KBS > 512) return false;
+  const int nbtot = Nout >> 7;
+  const int nb = (nbtot >= 2 && 2 * KBS <= 512) ? 2 : 1;
+  p.KB = KB;
+  p.KBS = KBS;
+  p.npc = nb * 128;
+  ny = (Nout + p.npc - 1) / p.npc;
+  int cols = 32;
+  while (cols < nb * KBS) cols <<= 1;
+  p.tmem_cols = cols;
+  (void)lds;
+  p.img_bytes = (mode == 0 ? 3 : 1) * WW_R * (p.npc + ((KBS + 63) & ~63)) * 2;
+  const int budget = WW_SMEM_LIMIT - 1024 - 512;
+  int nimg = budget / p.img_bytes;
+  if (nimg > WW_MAX_IMG) nimg = WW_MAX_IMG;
+  if (nimg < 2) return false;
+  p.nimg = nimg;
+  smem = 1024 + nimg * p.img_bytes + 512;
+  static const int sms = [] { int d = 0, n = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); return n > 0 ? n : 148; }();
+  static const int min_rows = ww_env("MSMP_WGRAD_WS_MIN_ROWS", 256);
+  int max_s = sms / ny;
+  if (max_s < 1) max_s = 1;
+  int s = M / (min_rows > WW_R ? min_rows : WW_R);
+  if (s < 1) s = 1;
+  if (s > max_s) s = max_s;
+  int rps = (M + s - 1) / s;
+  rps = (rps + WW_R - 1) / WW_R * WW_R;
+  if (rps < WW_R) rps = WW_R;
+  p.rows_per_split = rps;
+  S = M > 0 ? (M + rps - 1) / rps : 1;
+  p.M = M;
+  return true;
+}
+
+}  // namespace msmp
+
+using namespace msmp;
+
+extern "C" int msmp_wgrad_ws_splits(int M, int KB, int Nout, int nside) {
+  WgradWsParams p{};
+  int S = 0, ny = 0, smem = 0;
+  if (!ww_plan(M, KB, Nout, nside, 8, 0, p, S, ny, smem)) return -1;
+  return S;
+}
+
+extern "C" size_t msmp_wgrad_ws_workspace(int M, int KB, int Nout, int nside) {
+  const int S = msmp_wgrad_ws_splits(M, KB, Nout, nside);
+  if (S < 0) return 0;
+  return (size_t)S * ((size_t)KB + nside) * Nout * sizeof(float);
+}
+
+extern "C" int msmp_wgrad_ws(const float* const* X, const int* ldx, const int* kx, const int* xswish, int nseg,
+                             const float* dY, int lddy, int Nout, const float* side, int lds, int side_c0, int r,
+                             int has_bias, float* part, float* part_side, float* dWt, float* dWside, int accumulate,
+                             int M, int mode, cudaStream_t stream) {
+  if (nseg < 1 || nseg > 3 || M < 0 || (lddy & 3) || r < 0 || (mode != 0 && mode != 1)) return MSMP_ERR_ARG;
+  WgradWsParams p{};
+  int KB = 0;
+  for (int s = 0; s < nseg; ++s) {
+    if (kx[s] <= 0 || (kx[s] & 31) || (ldx[s] & 3)) return MSMP_ERR_ARG;
+    p.X[s] = X[s];
+    p.ldx[s] = ldx[s];
+    p.kx[s] = kx[s];
+    p.xsw[s] = xswish ? xswish[s] : 0;
+    KB += kx[s];
+  }
+  p.nseg = nseg;
+  const int rr = side ? r : 0;
+  const int nside = rr + (has_bias ? 1 : 0);
+  if (nside && side && ((lds & 3) || lds > 16 || side_c0 < 0 || side_c0 + rr > lds)) return MSMP_ERR_ARG;
+  int S = 0, ny = 0, smem = 0;
+  if (!ww_plan(M, KB, Nout, nside, side ? lds : 0, mode, p, S, ny, smem)) return MSMP_ERR_ARG;
+  p.dY = dY; p.lddy = lddy; p.Nout = Nout;
+  p.side = side; p.lds = side ? lds : 0; p.side_c0 = side_c0; p.r = rr; p.has_bias = has_bias ? 1 : 0;
+  p.part = part; p.part_side = part_side;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(k_wgrad_ws<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, WW_SMEM_LIMIT) != cudaSuccess ||
+        cudaFuncSetAttribute(k_wgrad_ws<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, WW_SMEM_LIMIT) != cudaSuccess)
+      return MSMP_ERR_CUDA;
+    attr_set = true;
+  }
+  dim3 grid(S, ny);
+  if (mode == 0)
+    k_wgrad_ws<0><<<grid, WW_THREADS, smem, stream>>>(p);
+  else
+    k_wgrad_ws<1><<<grid, WW_THREADS, smem, stream>>>(p);
+  MSMP_CHECK_LAUNCH();
+  if (dWt) {
+    const int c0 = KB * Nout, c1 = nside * Nout;
+    k_reduce_partials2<<<(c0 + c1 + 255) / 256, 256, 0, stream>>>(part, dWt, c0, (size_t)KB * Nout, part_side, dWside,
+                                                                 c1, (size_t)nside * Nout, S, accumulate);
+    MSMP_CHECK_LAUNCH();
+  }
+  return MSMP_OK;
+}

@@ -176,7 +176,7 @@ class _LayerCoreFn(torch.autograd.Function):
                                         W2raw=W2)
             dW2t_, db2s = on_side(lambda: ops.linear_wgrad(a1, dz2, has_bias=True, dWt=raw("dW2t"), dWside=raw("db2s")),
                                   a1, dz2)
-            dW2, db2 = dW2t_.t(), db2s[0]
+            dW2, db2 = (None, None) if gs is not None else (dW2t_.t(), db2s[0])
         else:
             dz1, dW2, db2 = ops.edge_bwd(PQ[:, :H], PQ[:, H:], topo, pk.W2d, z2, dcat[:, H:], dPQ[:, :H], W2raw=W2)
         ops.segment_reduce(dz1, topo.colptr, perm=topo.csc_perm, out=dPQ[:, H:], N=N)

@@ -81,6 +81,11 @@ def _p(t):
 
 # Tensor-core (tcgen05 3xTF32) execution of the dense layers.  "ffma" keeps the exact-fp32 CUDA-core kernels.
 GEMM_MODE = "tc"
+# Operand precision of the tensor-core GEMMs that have a bf16 variant (north_star's "bf16 mode"): "fp32" = error-compensated
+# 3xTF32 (parity at 1e-5), "bf16" = bf16 operands with fp32 accumulation (tolerance stated in DESIGN.md section 8).
+PRECISION = os.environ.get("MSMP_PRECISION", "fp32")
+# persistent warp-specialised weight-gradient kernel (csrc/wgrad_ws.cu); "0" keeps the one-tile-per-CTA k_wgrad_tc
+WGRAD_WS = os.environ.get("MSMP_WGRAD_WS", "1") != "0"
 # Persistent (all-T-steps-in-one-launch) LEM kernels; False = one GEMM + one gate kernel per step.
 LEM_PERSISTENT = True
 # tensor-core edge kernels: warp-specialised, weights in tensor memory (edge_ws.cu) | single-role (edge_tc.cu)
@@ -207,10 +212,19 @@ def linear_tc_fwd(segs, img, Nout, bias=None, side=None, r=0, Wside=None, Zmul=N
     return out
 
 
+def _side_base(side):
+    """(base pointer, row stride, first column) of a side array that may be a column slice of a [M, lds] tensor."""
+    lds = side.stride(0)
+    c0 = side.storage_offset() % lds if lds <= 16 else 0
+    return side.data_ptr() - 4 * c0, lds, c0
+
+
 def linear_wgrad(X, dY, K=None, xswish=False, side=None, r=0, has_bias=False, dWt=None, dWside=None,
                  accumulate=False, X1=None):
     """dWt[K, Nout] = [X | X1]^T dY ; dWside[r(+1), Nout] = [side|1]^T dY.  X1 (optional) supplies the columns
-    after X's (X.shape[1] % 128 == 0), e.g. [h | agg] or [h | u_padded], without materialising the concatenation."""
+    after X's (X.shape[1] % 128 == 0), e.g. [h | agg] or [h | u_padded], without materialising the concatenation.
+    A 3-dim ``dWt`` [S, K, Nout] (with ``dWside`` [S, nside, Nout]) asks for the split-M partials of msmp_wgrad_ws
+    instead of the reduced gradient (gradsink.GradPlan sums them in its unpack launch)."""
     _req(X, "X")
     _req(dY, "dY")
     M, Nout = dY.shape
@@ -219,10 +233,43 @@ def linear_wgrad(X, dY, K=None, xswish=False, side=None, r=0, has_bias=False, dW
     Kt = K0 + K1
     nside = (r if side is not None else 0) + int(has_bias)
     dev = dY.device
+    partial = dWt is not None and dWt.dim() == 3
+    ws_ok = (GEMM_MODE == "tc" and WGRAD_WS and K0 % 32 == 0 and K1 % 32 == 0 and Nout % 128 == 0 and nside <= 8
+             and (side is None or (side.stride(0) <= 16 and side.stride(0) % 4 == 0)))
+    if partial and not ws_ok:
+        raise RuntimeError("linear_wgrad: split-M partials were requested for a shape msmp_wgrad_ws does not take")
     if dWt is None:
         dWt = torch.empty(Kt, Nout, dtype=torch.float32, device=dev)
     if nside and dWside is None:
         dWside = torch.empty(nside, Nout, dtype=torch.float32, device=dev)
+    if ws_ok:
+        segs = [X] if X1 is None else [X, X1]
+        n = len(segs)
+        S = lib.msmp_wgrad_ws_splits(M, Kt, Nout, nside)
+        if S <= 0:
+            raise RuntimeError("msmp_wgrad_ws_splits rejected the shape")
+        Xp = (ctypes.c_void_p * 3)(*[a.data_ptr() for a in segs], *([0] * (3 - n)))
+        ldx = (ctypes.c_int * 3)(*[_ld(a) for a in segs], *([0] * (3 - n)))
+        kx = (ctypes.c_int * 3)(K0, *([K1] if X1 is not None else []), *([0] * (3 - n)))
+        xsw = (ctypes.c_int * 3)(*([int(bool(xswish))] * n), *([0] * (3 - n)))
+        sb, lds, c0 = _side_base(side) if side is not None else (0, 0, 0)
+        if partial:
+            if dWt.shape[0] != S or not dWt.is_contiguous() or (nside and (dWside is None or dWside.shape[0] != S)):
+                raise RuntimeError(f"linear_wgrad: the partial buffer holds {dWt.shape[0]} splits, this call makes {S}")
+            if accumulate:
+                raise RuntimeError("linear_wgrad: accumulate is not available with split-M partials")
+            part, part_side, out, out_side = dWt.data_ptr(), _p(dWside), 0, 0
+        else:
+            ws = _workspace(lib.msmp_wgrad_ws_workspace(M, Kt, Nout, nside), dev)
+            part = ws.data_ptr()
+            part_side = part + 4 * S * Kt * Nout
+            out, out_side = dWt.data_ptr(), _p(dWside)
+        with _timed("wgrad_ws", 2.0 * M * Kt * Nout, 4.0 * (M * Kt + M * Nout)):
+            check(lib.msmp_wgrad_ws(Xp, ldx, kx, xsw, n, dY.data_ptr(), _ld(dY), Nout, sb, lds, c0,
+                                    r if side is not None else 0, int(has_bias), part, part_side, out, out_side,
+                                    int(accumulate), M, 1 if PRECISION == "bf16" else 0, _stream()), "msmp_wgrad_ws")
+        _count(1 if partial else 2)
+        return dWt, dWside
     sargs = (_p(side), _ld(side) if side is not None else 0, r if side is not None else 0, int(has_bias))
     if GEMM_MODE == "tc":
         ws = _workspace(lib.msmp_linear_wgrad_workspace(M, Kt, Nout, nside), dev)

@@ -191,7 +191,10 @@ class GraphedTrainStep:
                 m.__dict__.get("_msmp_pack_plan") is not None for m in self.model.modules()):
             return
         from .gradsink import GradPlan
-        self.gplan = GradPlan(self.model)
+        # row counts of the step's weight-gradient GEMMs: the sink then holds split-M partials that the unpack launch sums
+        tw = getattr(self.model, "time_window", None)
+        self.gplan = GradPlan(self.model, n_nodes=int(self.static.x.shape[0]), n_edges=int(self.static.edge_index.shape[1]),
+                              n_steps=int(tw) if tw else None)
 
     def _host_prologue(self):
         if self.fused is not None:

@@ -180,15 +180,63 @@ def test_captured_step_with_plain_adamw_and_scheduler():
     assert opt.param_groups[0]["lr"] == pytest.approx(1e-3 * 0.16)
     sd = opt.state_dict()                                             # flushes the step counters
     assert all(float(s["step"]) == 6.0 for s in sd["state"].values())
+    # Adam's update lr * m / (sqrt(v) + eps) amplifies the fp32 noise of entries whose gradient is numerically zero (up
+    # to 2 lr per step if the sign flips), so the trajectories are compared in units of the summed learning rate; the
+    # update kernel itself is held to torch's on identical gradients in test_fused_adamw_equals_torch_adamw.
+    lr_sum = 2 * 1e-3 * (1 + 0.4 + 0.16)
     for (n, p), (_, q) in zip(model.named_parameters(), ref.named_parameters()):
-        assert rel_err(p, q) < 2e-5, n
+        assert float((p - q).abs().max()) < 0.02 * lr_sum, n
     # hand over to torch's own eager step: same state => same next update
     for m, o in ((model, opt), (ref, opt_r)):
         o.zero_grad(set_to_none=False)
         torch.sqrt(crit(m(g), g.y)).backward()
         o.step()
     for (n, p), (_, q) in zip(model.named_parameters(), ref.named_parameters()):
-        assert rel_err(p, q) < 2e-5, n
+        assert float((p - q).abs().max()) < 0.02 * (lr_sum + 1e-3 * 0.16), n
+
+
+def test_fused_adamw_equals_torch_adamw():
+    """msmp_adamw_run against torch.optim.AdamW on IDENTICAL gradients: two param groups with different lr / weight decay /
+    betas, a scheduler step in between, a gradient scale; parameters and both moments after 5 steps, then a hand-over
+    to torch's own step()."""
+    from msmp_pde_b200.optim import FusedAdamW
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(5)
+    shapes = [(128, 310), (128,), (7, 3, 5), (1,), (1025,)]
+    mk = lambda: [torch.nn.Parameter(torch.randn(*s, device=dev, generator=g)) for s in shapes]
+    pa = mk()
+    pb = [torch.nn.Parameter(p.detach().clone()) for p in pa]
+    groups = lambda ps: [dict(params=ps[:3], lr=1e-2, weight_decay=0.1, betas=(0.8, 0.95)), dict(params=ps[3:], lr=3e-3)]
+    oa, ob = torch.optim.AdamW(groups(pa)), torch.optim.AdamW(groups(pb))
+    for p in pa:
+        p.grad = torch.zeros_like(p)
+    fused = FusedAdamW(oa)
+    scale = torch.tensor(0.37, device=dev)
+    for it in range(5):
+        for p, q in zip(pa, pb):
+            gr = torch.randn(p.shape, device=dev, generator=g) * (10.0 ** (it - 2))
+            p.grad.copy_(gr)
+            q.grad = gr * 0.37
+        fused.host_update()
+        fused.launch(scale)
+        ob.step()
+        if it == 2:
+            for o in (oa, ob):
+                for grp in o.param_groups:
+                    grp["lr"] *= 0.5
+    for p, q in zip(pa, pb):
+        assert rel_err(p, q) < 2e-6
+        assert rel_err(p.grad, q.grad) < 1e-6                     # the scaled gradient is written back
+        assert rel_err(oa.state[p]["exp_avg"], ob.state[q]["exp_avg"]) < 2e-6
+        assert rel_err(oa.state[p]["exp_avg_sq"], ob.state[q]["exp_avg_sq"]) < 2e-6
+    for p, q in zip(pa, pb):
+        p.grad.fill_(0.01)
+        q.grad.fill_(0.01)
+    oa.step()                                                        # pre-hook flushes the step counters
+    ob.step()
+    assert all(float(oa.state[p]["step"]) == 6.0 for p in pa)
+    for p, q in zip(pa, pb):
+        assert rel_err(p, q) < 2e-6
 
 
 def test_captured_step_rejects_other_topology():

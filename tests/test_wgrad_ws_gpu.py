@@ -1,0 +1,107 @@
+"""msmp_wgrad_ws (csrc/wgrad_ws.cu) against float64 math: every operand shape the models use, ragged row counts, the
+split-M partial mode, and the bf16 operand mode with its stated tolerance."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from tests.util import rel_err  # noqa: E402
+
+# (M, K0, K1, Nout, r, has_bias, xswish)  -- K1 = 0: single segment
+SHAPES = [
+    (6400, 128, 0, 128, 0, True, True),          # update_net_2 (X = swish(z3))
+    (6400, 128, 128, 128, 3, True, False),       # update_net_1: [h | agg], side = variables
+    (37632, 128, 0, 128, 0, True, False),        # message_net_2 over edges
+    (6400, 128, 64, 256, 4, True, False),        # P | Q projection: [h | upad], side = [pos, variables]
+    (6400, 128, 32, 256, 2, True, False),        # P | Q projection, one field (tw 25 -> 32 columns)
+    (6400, 128, 128, 256, 4, True, False),       # tw 50, two fields: F_u = 100 -> 128 columns (one dY block per CTA)
+    (25 * 300, 128, 32, 384, 0, True, False),    # LEM G map: [y | inputs], three dY blocks
+    (25 * 300, 128, 32, 128, 0, True, False),    # LEM L map
+    (1000, 32, 0, 128, 0, True, False),          # embedding Linear (27 -> 32 zero padded inputs)
+    (1000, 128, 0, 256, 0, True, False),         # double_mlp
+    (17, 128, 0, 128, 0, True, False),           # fewer rows than one chunk + ragged tail
+    (131, 128, 128, 128, 3, False, False),       # no bias row
+    (4099, 128, 64, 256, 0, False, False),       # no side block at all
+]
+
+
+def _ref(X, X1, dY, side, r, has_bias, xswish):
+    Xd = X.double()
+    if xswish:
+        Xd = Xd * torch.sigmoid(Xd)
+    if X1 is not None:
+        Xd = torch.cat([Xd, X1.double()], 1)
+    dW = Xd.t() @ dY.double()
+    cols = []
+    if side is not None and r:
+        cols.append(side[:, :r].double())
+    if has_bias:
+        cols.append(torch.ones(dY.shape[0], 1, dtype=torch.float64, device=dY.device))
+    dWs = torch.cat(cols, 1).t() @ dY.double() if cols else None
+    return dW, dWs
+
+
+def _inputs(M, K0, K1, Nout, r, seed):
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(seed)
+    X = torch.randn(M, K0, device=dev, generator=g)
+    X1 = torch.randn(M, K1, device=dev, generator=g) if K1 else None
+    dY = torch.randn(M, Nout, device=dev, generator=g)
+    side8 = torch.randn(M, 8, device=dev, generator=g)
+    side = side8[:, 1:] if r == 3 else side8           # a column-sliced view, like layers.py passes for update_net_1
+    return X, X1, dY, (side if r else None)
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_wgrad_ws_fp32_parity(shape):
+    from msmp_pde_b200 import ops
+    M, K0, K1, Nout, r, has_bias, xswish = shape
+    X, X1, dY, side = _inputs(M, K0, K1, Nout, r, seed=M + Nout)
+    assert ops.WGRAD_WS and ops.PRECISION == "fp32"
+    dW, dWs = ops.linear_wgrad(X, dY, xswish=xswish, side=side, r=r, has_bias=has_bias, X1=X1)
+    rW, rWs = _ref(X, X1, dY, side, r, has_bias, xswish)
+    assert rel_err(dW, rW) < 5e-6
+    if rWs is not None:
+        assert rel_err(dWs, rWs) < 5e-6
+    # run-to-run bit identity (fixed-order reduction, no atomics)
+    dW2, dWs2 = ops.linear_wgrad(X, dY, xswish=xswish, side=side, r=r, has_bias=has_bias, X1=X1)
+    assert torch.equal(dW, dW2) and (dWs is None or torch.equal(dWs, dWs2))
+
+
+def test_wgrad_ws_partials_sum_to_the_gradient():
+    from msmp_pde_b200 import ops
+    from msmp_pde_b200._lib import lib
+    M, K0, K1, Nout, r = 6400, 128, 64, 256, 4
+    X, X1, dY, side = _inputs(M, K0, K1, Nout, r, seed=1)
+    S = lib.msmp_wgrad_ws_splits(M, K0 + K1, Nout, r + 1)
+    assert S > 1
+    part = torch.full((S, K0 + K1, Nout), float("nan"), device=X.device)
+    part_s = torch.full((S, r + 1, Nout), float("nan"), device=X.device)
+    ops.linear_wgrad(X, dY, side=side, r=r, has_bias=True, X1=X1, dWt=part, dWside=part_s)
+    dW, dWs = ops.linear_wgrad(X, dY, side=side, r=r, has_bias=True, X1=X1)
+    acc, acc_s = torch.zeros_like(dW), torch.zeros_like(dWs)
+    for s in range(S):                    # the order k_reduce_partials2 / k_unpack use
+        acc += part[s]
+        acc_s += part_s[s]
+    assert torch.equal(acc, dW) and torch.equal(acc_s, dWs)
+
+
+BF16_TOL = 1e-2          # of max|ref|: bf16 operands (8-bit mantissa), fp32 accumulation over >= 1000 rows
+
+
+@pytest.mark.parametrize("shape", SHAPES[:8])
+def test_wgrad_ws_bf16_mode(shape):
+    from msmp_pde_b200 import ops
+    M, K0, K1, Nout, r, has_bias, xswish = shape
+    X, X1, dY, side = _inputs(M, K0, K1, Nout, r, seed=7)
+    prev = ops.PRECISION
+    ops.PRECISION = "bf16"
+    try:
+        dW, dWs = ops.linear_wgrad(X, dY, xswish=xswish, side=side, r=r, has_bias=has_bias, X1=X1)
+    finally:
+        ops.PRECISION = prev
+    rW, rWs = _ref(X, X1, dY, side, r, has_bias, xswish)
+    assert rel_err(dW, rW) < BF16_TOL
+    assert rel_err(dW, rW) > 1e-5            # really ran with bf16 operands
+    if rWs is not None:
+        assert rel_err(dWs, rWs) < BF16_TOL
