@@ -38,7 +38,7 @@ WORKLOADS = {
     "c3": dict(graphs=64, label="C3: MSMP-PDE2D (MP_PDE_Solver2DLEMLinGated) RPU shape (pseudo-random grid, kNN k=3), {B} graphs "
                                 "x 100 nodes per GPU, tw=25, fwd+loss+bwd+AdamW"),
 }
-REF_GRAPHS = {"c4": 2, "c2": 64, "c3": 64}          # graphs per step of the CPU reference arm (bounded sample for C4)
+REF_GRAPHS = {"c4": 8, "c2": 64, "c3": 64}          # graphs per step of the CPU reference arm: the full per-GPU batch
 
 
 def _peaks():

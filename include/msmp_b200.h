@@ -242,7 +242,7 @@ int msmp_mul_dswish(const float* g, const float* z, float* out, size_t n, cudaSt
  * scheduler (train.py:411,437 rewrites param_group['lr'] only).  jobs_dev: records {float* p, *g, *m, *v; int n, group}
  * (msmp_adamw_job_bytes() each; m / v are the optimizer's own exp_avg / exp_avg_sq).  chunks_dev: int2 {job, first
  * element}, one per CTA, msmp_adamw_chunk() elements each.  hyper_dev: msmp_adamw_hyper_floats() floats per param group
- * = {lr, beta1, beta2, eps, weight_decay, 1 - beta1^t, sqrt(1 - beta2^t), 0}.  gscale_dev (may be NULL): device scalar
+ * = {lr, 1 - beta1, beta2, eps, weight_decay, 1 - beta1^t, sqrt(1 - beta2^t), 1 - beta2}.  gscale_dev (may be NULL): device scalar
  * every gradient is multiplied by first (and written back), e.g. 1 / (2 sqrt(SSE)) of loss = sqrt(SSE),
  * experiments/train_helper.py:126,138. */
 int msmp_adamw_job_bytes(void);

@@ -29,14 +29,15 @@ struct AdamJob {
 };
 
 constexpr int ADAM_CHUNK = 1024;       // elements per CTA: 256 threads x 4 (strided, coalesced)
-constexpr int ADAM_HYPER = 8;          // floats per param group: lr, beta1, beta2, eps, wd, bc1, sqrt(bc2), unused
+constexpr int ADAM_HYPER = 8;          // floats per param group: lr, 1 - beta1, beta2, eps, wd, bc1, sqrt(bc2), 1 - beta2
+                                       // (the complements are formed in double on the host, as torch does: 1 - 0.999f != 0.001f)
 
 __global__ void __launch_bounds__(256) k_adamw(const AdamJob* __restrict__ jobs, const int2* __restrict__ chunks,
                                               const float* __restrict__ hyper, const float* __restrict__ gscale) {
   const int2 c = chunks[blockIdx.x];
   const AdamJob j = jobs[c.x];
   const float* h = hyper + j.group * ADAM_HYPER;
-  const float lr = h[0], b1 = h[1], b2 = h[2], eps = h[3], wd = h[4], bc1 = h[5], sbc2 = h[6];
+  const float lr = h[0], omb1 = h[1], b2 = h[2], eps = h[3], wd = h[4], bc1 = h[5], sbc2 = h[6], omb2 = h[7];
   const float gs = gscale ? *gscale : 1.0f;
   const float decay = 1.0f - lr * wd, step = lr / bc1;
 #pragma unroll
@@ -46,8 +47,8 @@ __global__ void __launch_bounds__(256) k_adamw(const AdamJob* __restrict__ jobs,
     const float g = j.g[i] * gs;
     float m = j.m[i], v = j.v[i], p = j.p[i];
     p *= decay;
-    m = m + (1.0f - b1) * (g - m);
-    v = b2 * v + (1.0f - b2) * g * g;
+    m = m + omb1 * (g - m);
+    v = b2 * v + omb2 * g * g;
     p -= step * m / (sqrtf(v) / sbc2 + eps);
     j.p[i] = p;
     j.m[i] = m;

@@ -9,10 +9,10 @@
 // launch summed the split-M partials.  Here ONE CTA owns a contiguous range of rows m for ALL output tiles it can hold
 // in tensor memory:
 //
-//   16 producer warps in four groups; a group owns every fourth 16-row chunk: it issues all loads of the chunk (fp32
-//                    rows of dY, up to three X segments, the side columns; coalesced LDG.128, ~25 KB in flight per
-//                    group), applies the optional swish and writes bf16 operand images (MN-major, SWIZZLE_128B) into
-//                    an image ring -- while one group waits for its rows the others convert theirs.
+//   loader warp    : the fp32 rows of a 16-row chunk (dY, up to three X segments, the side columns) arrive in a raw
+//                    ring by 1-D bulk copies (TMA engine; one copy per operand when its rows are contiguous) -- loads
+//                    never wait on registers, up to six chunks are in flight per SM
+//   16 producer warps: raw rows -> optional swish -> bf16 operand images (MN-major, SWIZZLE_128B) in an image ring.
 //                    fp32-parity mode: every fp32 value is split EXACTLY into three bf16 pieces x = b0 + b1 + b2 (+ 2^-24 x)
 //                    -> three images per operand; bf16 mode: one image (x rounded to bf16).  The side columns and the
 //                    bias "ones" column are 32 extra columns of the B operand, so side / bias gradients come out of the
@@ -41,13 +41,10 @@ namespace msmp {
 
 constexpr int WW_R = 16;                 // rows (the MMA K dimension) per chunk
 constexpr int WW_PROD_WARPS = 16;        // the fp32 -> bf16-piece conversion is ALU / latency bound: 8 warps left the SM idle
-constexpr int WW_GROUP_WARPS = 4;        // producer warps that share one chunk
-constexpr int WW_GROUPS = WW_PROD_WARPS / WW_GROUP_WARPS;
-constexpr int WW_GT = 32 * WW_GROUP_WARPS;
-constexpr int WW_MAXU = 8;               // 8-column units per producer thread and chunk: 16 rows x (256 + 256) columns at most
-constexpr int WW_MMA_WARP = WW_PROD_WARPS;
-constexpr int WW_THREADS = 32 * (WW_PROD_WARPS + 1);
-constexpr int WW_MAX_IMG = 6;
+constexpr int WW_PROD_THREADS = 32 * WW_PROD_WARPS;
+constexpr int WW_MMA_WARP = WW_PROD_WARPS, WW_LOAD_WARP = WW_PROD_WARPS + 1;
+constexpr int WW_THREADS = 32 * (WW_PROD_WARPS + 2);
+constexpr int WW_MAX_RAW = 6, WW_MAX_IMG = 4;
 constexpr int WW_SMEM_LIMIT = 232448;    // 227 KiB
 
 struct WgradWsParams {
@@ -71,11 +68,17 @@ struct WgradWsParams {
   float* part_side;    // [S][r + has_bias][Nout]
   int M;
   int rows_per_split;
-  int nimg;            // image ring depth
-  int img_bytes;
+  int nraw, nimg;      // ring depths
+  int raw_bytes, img_bytes;
   int tmem_cols;
 };
 
+__device__ __forceinline__ void mbar_wait_all(uint64_t* bar, uint32_t parity) {
+  // lane 0 polls with back-off, then every lane observes the completed phase itself (acquire for TMA-written data)
+  mbar_wait_backoff(bar, parity);
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
 // byte offset of (row m, 16-byte chunk c8 = 8 bf16 columns) in an MN-major SWIZZLE_128B image (64 columns per block)
 __device__ __forceinline__ uint32_t ww_off16(int m, int c8) {
   return (uint32_t)((c8 >> 3) * (WW_R * 128) + m * 128 + (((c8 ^ m) & 7) << 4));
@@ -143,9 +146,12 @@ __global__ void __launch_bounds__(WW_THREADS, 1) k_wgrad_ws(const WgradWsParams 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* img_ring = smem;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(img_ring + p.nimg * p.img_bytes);
-  uint64_t* img_full = bars;                       // [6] producer group -> MMA
-  uint64_t* img_empty = img_full + WW_MAX_IMG;     // [6] MMA -> producers
+  uint8_t* raw_ring = img_ring + p.nimg * p.img_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(raw_ring + p.nraw * p.raw_bytes);
+  uint64_t* raw_full = bars;                       // [6] TMA -> producers
+  uint64_t* raw_empty = bars + WW_MAX_RAW;         // [6] producers -> loader
+  uint64_t* img_full = bars + 2 * WW_MAX_RAW;      // [4] producers -> MMA
+  uint64_t* img_empty = img_full + WW_MAX_IMG;     // [4] MMA -> producers
   uint64_t* acc_full = img_empty + WW_MAX_IMG;     // [1] MMA -> epilogue
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
   const int tid = threadIdx.x, warp = warp_index_uniform(), lane = tid & 31;
@@ -160,8 +166,12 @@ __global__ void __launch_bounds__(WW_THREADS, 1) k_wgrad_ws(const WgradWsParams 
 
   if (warp == WW_MMA_WARP) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
   if (tid == 0) {
+    for (int i = 0; i < WW_MAX_RAW; ++i) {
+      mbar_init(&raw_full[i], 1);
+      mbar_init(&raw_empty[i], WW_PROD_WARPS);
+    }
     for (int i = 0; i < WW_MAX_IMG; ++i) {
-      mbar_init(&img_full[i], WW_GROUP_WARPS);
+      mbar_init(&img_full[i], WW_PROD_WARPS);
       mbar_init(&img_empty[i], 1);
     }
     mbar_init(acc_full, 1);
@@ -172,12 +182,47 @@ __global__ void __launch_bounds__(WW_THREADS, 1) k_wgrad_ws(const WgradWsParams 
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
+  // raw stage layout (floats): [dY: R x npc][X0: R x kx0][X1][X2][side: R x lds]
+  const int raw_x0 = WW_R * p.npc;
+  const int raw_side = raw_x0 + WW_R * p.KB;
   // image stage layout: NP bf16 images of A (dY), then NP bf16 images of B ([X | side])
   constexpr int NP = (MODE == 0) ? 3 : 1;
   const int a_bytes = WW_R * p.npc * 2;                          // one A image
   const int b_bytes = WW_R * ((p.KBS + 63) & ~63) * 2;           // one B image
 
-  if (warp == WW_MMA_WARP) {
+  if (warp == WW_LOAD_WARP) {
+    // ============================================================================= loader: bulk copies of raw fp32 rows
+    int i = 0;
+    uint32_t ph = 0;
+    const uint32_t row_bytes = (uint32_t)(npc_here + p.KB + (p.r > 0 ? p.lds : 0)) * 4u;
+#pragma unroll 1
+    for (int c = 0; c < nchunks; ++c) {
+      if (c >= p.nraw) mbar_wait_backoff(&raw_empty[i], ph ^ 1);
+      const int m0 = m_begin + c * WW_R;
+      const int nrows = min(WW_R, m_end - m0);
+      float* rs = reinterpret_cast<float*>(raw_ring + i * p.raw_bytes);
+      if (lane == 0) mbar_expect_tx(&raw_full[i], (uint32_t)nrows * row_bytes);
+      __syncwarp();
+      auto copy_rows = [&](float* dst, const float* src, int ld, int width, int pitch) {
+        if (ld == width && pitch == width) {
+          if (lane == 0) bulk_g2s(dst, src, (uint32_t)(nrows * width) * 4u, &raw_full[i]);
+        } else if (lane < nrows) {
+          bulk_g2s(dst + lane * pitch, src + (size_t)lane * ld, (uint32_t)width * 4u, &raw_full[i]);
+        }
+      };
+      copy_rows(rs, p.dY + (size_t)m0 * p.lddy + n0, p.lddy, npc_here, p.npc);
+      int off = raw_x0;
+      for (int s = 0; s < p.nseg; ++s) {
+        copy_rows(rs + off, p.X[s] + (size_t)m0 * p.ldx[s], p.ldx[s], p.kx[s], p.kx[s]);
+        off += WW_R * p.kx[s];
+      }
+      if (p.r > 0) copy_rows(rs + raw_side, p.side + (size_t)m0 * p.lds, p.lds, p.lds, p.lds);
+      if (++i == p.nraw) {
+        i = 0;
+        ph ^= 1;
+      }
+    }
+  } else if (warp == WW_MMA_WARP) {
     // ============================================================================= MMA warp
     const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
     const bool leader = elect_one();
@@ -224,89 +269,77 @@ __global__ void __launch_bounds__(WW_THREADS, 1) k_wgrad_ws(const WgradWsParams 
     }
   } else {
     // ============================================================================= producers, then epilogue
-    // Four groups of four warps; group g converts the chunks g, g + 4, ...: while one group waits for its rows the others
-    // convert theirs (a single group of 16 warps in lockstep spent most of a chunk's time in its waits).  A thread owns up
-    // to WW_MAXU 8-column units of the virtual row [dY | X0 | X1 | X2]; all of a chunk's loads are issued before the
-    // first conversion, so a group keeps ~25 KB in flight.
-    const int grp = warp / WW_GROUP_WARPS, gt = tid - grp * WW_GT;
-    const int a8 = npc_here >> 3;                          // units of the dY part
-    const int upr = (npc_here + p.KB) >> 3;                // units per virtual row
-    const uint32_t inv = 0xffffffffu / (uint32_t)upr + 1u; // u / upr == umulhi(u, inv) for u < 65536
-    const int total = WW_R * upr;
-    const int k8_0 = p.kx[0] >> 3, k8_1 = p.nseg > 1 ? (p.kx[1] >> 3) : (1 << 30);
+    const int pt = tid;                                  // 0 .. WW_PROD_THREADS - 1
+    int i = 0, j = 0;
+    uint32_t phr = 0, phi = 0;
+    const int ash8 = (npc_here == 256) ? 5 : 4;          // 16-byte bf16 chunks (8 columns) per dY row: 32 or 16
 #pragma unroll 1
-    for (int c = grp; c < nchunks; c += WW_GROUPS) {
+    for (int c = 0; c < nchunks; ++c) {
       const int m0 = m_begin + c * WW_R;
       const int nrows = min(WW_R, m_end - m0);
-      const int j = c % p.nimg, use = c / p.nimg;
-      float4 v[WW_MAXU][2];
-#pragma unroll
-      for (int i = 0; i < WW_MAXU; ++i) {
-        const int u = gt + i * WW_GT;
-        v[i][0] = zero4();
-        v[i][1] = zero4();
-        if (u < total) {
-          const int m = (int)__umulhi((uint32_t)u, inv), cu = u - m * upr;
-          if (m < nrows) {
-            const float* src;
-            if (cu < a8) {
-              src = p.dY + (size_t)(m0 + m) * p.lddy + n0 + 8 * cu;
-            } else {
-              int k = cu - a8, sgm = 0;
-              if (k >= k8_0) {
-                k -= k8_0;
-                sgm = 1;
-                if (k >= k8_1) {
-                  k -= k8_1;
-                  sgm = 2;
-                }
-              }
-              src = p.X[sgm] + (size_t)(m0 + m) * p.ldx[sgm] + 8 * k;
-            }
-            v[i][0] = ldg4(src);
-            v[i][1] = ldg4(src + 4);
-          }
-        }
-      }
-      // [side | 1 | 0...]: the last 32 columns of the B images, 4 units per row
-      float e[8];
-      const int sm_ = gt >> 2, sc8 = gt & 3;
-      if (nside && gt < WW_R * 4) {
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const int col = 8 * sc8 + q;
-          e[q] = (sm_ >= nrows) ? 0.f : (col < p.r) ? __ldg(p.side + (size_t)(m0 + sm_) * p.lds + p.side_c0 + col)
-                                         : (col == p.r && p.has_bias) ? 1.0f : 0.f;
-        }
-      }
-      if (use > 0) mbar_wait_backoff(&img_empty[j], (uint32_t)(use - 1) & 1u);
+      mbar_wait_all(&raw_full[i], phr);
+      if (c >= p.nimg) mbar_wait_backoff(&img_empty[j], phi ^ 1);
+      const float* rs = reinterpret_cast<const float*>(raw_ring + i * p.raw_bytes);
       uint8_t* a_img = img_ring + j * p.img_bytes;
       uint8_t* b_img = a_img + NP * a_bytes;
-#pragma unroll
-      for (int i = 0; i < WW_MAXU; ++i) {
-        const int u = gt + i * WW_GT;
-        if (u < total) {
-          const int m = (int)__umulhi((uint32_t)u, inv), cu = u - m * upr;
-          if (cu < a8) {
-            store_pieces<NP>(a_img, a_bytes, ww_off16(m, cu), v[i][0], v[i][1]);
-          } else {
-            const int k = cu - a8;
-            const int sgm = k < k8_0 ? 0 : (k - k8_0 < k8_1 ? 1 : 2);
-            float4 x0 = v[i][0], x1 = v[i][1];
-            if (p.xsw[sgm]) {
-              x0 = swish4(x0);
-              x1 = swish4(x1);
-            }
-            store_pieces<NP>(b_img, b_bytes, ww_off16(m, k), x0, x1);
-          }
+      for (int idx = pt; idx < (WW_R << ash8); idx += WW_PROD_THREADS) {
+        const int m = idx >> ash8, c8 = idx & ((1 << ash8) - 1);
+        float4 v0 = zero4(), v1 = zero4();
+        if (m < nrows) {
+          v0 = *reinterpret_cast<const float4*>(rs + m * p.npc + 8 * c8);
+          v1 = *reinterpret_cast<const float4*>(rs + m * p.npc + 8 * c8 + 4);
         }
+        store_pieces<NP>(a_img, a_bytes, ww_off16(m, c8), v0, v1);
       }
-      if (nside && gt < WW_R * 4)
-        store_pieces<NP>(b_img, b_bytes, ww_off16(sm_, (p.KB >> 3) + sc8), make_float4(e[0], e[1], e[2], e[3]),
+      int off = raw_x0, cb8 = 0;
+      for (int s = 0; s < p.nseg; ++s) {
+        const int k8 = p.kx[s] >> 3;
+        const bool sw = p.xsw[s] != 0;
+        const int sh = (k8 & (k8 - 1)) ? -1 : 31 - __clz(k8);          // power-of-two widths (all of the models'): shifts
+        for (int idx = pt; idx < WW_R * k8; idx += WW_PROD_THREADS) {
+          const int m = sh >= 0 ? (idx >> sh) : idx / k8, c8 = idx - m * k8;
+          float4 v0 = zero4(), v1 = zero4();
+          if (m < nrows) {
+            v0 = *reinterpret_cast<const float4*>(rs + off + m * p.kx[s] + 8 * c8);
+            v1 = *reinterpret_cast<const float4*>(rs + off + m * p.kx[s] + 8 * c8 + 4);
+          }
+          if (sw) {
+            v0 = swish4(v0);
+            v1 = swish4(v1);
+          }
+          store_pieces<NP>(b_img, b_bytes, ww_off16(m, cb8 + c8), v0, v1);
+        }
+        off += WW_R * p.kx[s];
+        cb8 += k8;
+      }
+      // [side | 1 | 0...] -> the last 32 columns of the B images (the last two warps: they have the fewest units above)
+      if (nside && pt >= WW_PROD_THREADS - WW_R * 4) {
+        const int q4 = pt - (WW_PROD_THREADS - WW_R * 4);
+        const int m = q4 >> 2, c8 = q4 & 3;
+        float e[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int col = 8 * c8 + q;
+          e[q] = (m >= nrows) ? 0.f : (col < p.r) ? rs[raw_side + m * p.lds + p.side_c0 + col]
+                                     : (col == p.r && p.has_bias) ? 1.0f : 0.f;
+        }
+        store_pieces<NP>(b_img, b_bytes, ww_off16(m, cb8 + c8), make_float4(e[0], e[1], e[2], e[3]),
                          make_float4(e[4], e[5], e[6], e[7]));
+      }
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&img_full[j]);
+      if (lane == 0) {
+        mbar_arrive(&img_full[j]);
+        mbar_arrive(&raw_empty[i]);
+      }
+      if (++i == p.nraw) {
+        i = 0;
+        phr ^= 1;
+      }
+      if (++j == p.nimg) {
+        j = 0;
+        phi ^= 1;
+      }
     }
     // ---- epilogue: TMEM lanes = n (32 per warp quadrant), columns = k; 32-column groups are dealt to the four
     // warps of a quadrant; every store instruction writes one 128-byte line of the partial
@@ -367,14 +400,19 @@ static bool ww_plan(int M, int KB, int Nout, int nside, int lds, int mode, Wgrad
   int cols = 32;
   while (cols < nb * KBS) cols <<= 1;
   p.tmem_cols = cols;
-  (void)lds;
+  const int raw = WW_R * (p.npc + KB + lds) * 4;      // lds = 0 when no side columns are read
+  p.raw_bytes = (raw + 127) & ~127;
   p.img_bytes = (mode == 0 ? 3 : 1) * WW_R * (p.npc + ((KBS + 63) & ~63)) * 2;
   const int budget = WW_SMEM_LIMIT - 1024 - 512;
-  int nimg = budget / p.img_bytes;
-  if (nimg > WW_MAX_IMG) nimg = WW_MAX_IMG;
-  if (nimg < 2) return false;
+  int nraw = 2, nimg = 2;
+  if (nraw * p.raw_bytes + nimg * p.img_bytes > budget) return false;
+  // deeper rings while they fit: first a third image stage, then raw stages (loads in flight)
+  if (nraw * p.raw_bytes + (nimg + 1) * p.img_bytes <= budget) ++nimg;
+  while (nraw < WW_MAX_RAW && (nraw + 1) * p.raw_bytes + nimg * p.img_bytes <= budget) ++nraw;
+  if (nimg < WW_MAX_IMG && nraw == WW_MAX_RAW && nraw * p.raw_bytes + (nimg + 1) * p.img_bytes <= budget) ++nimg;
+  p.nraw = nraw;
   p.nimg = nimg;
-  smem = 1024 + nimg * p.img_bytes + 512;
+  smem = 1024 + nraw * p.raw_bytes + nimg * p.img_bytes + 512;
   static const int sms = [] { int d = 0, n = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); return n > 0 ? n : 148; }();
   static const int min_rows = ww_env("MSMP_WGRAD_WS_MIN_ROWS", 256);
   int max_s = sms / ny;

@@ -81,7 +81,7 @@ class GradPlan:
         side split): [S, K, N] / [S, nside, N] partials when the row count is known and msmp_wgrad_ws takes the shape."""
         M = self.rows[kind]
         S = 0
-        if M is not None and ops.WGRAD_WS and K % 32 == 0 and N % 128 == 0:
+        if M is not None and ops.wgrad_use_ws(int(M), K, N, nside):
             S = lib.msmp_wgrad_ws_splits(int(M), K, N, nside)
         if S > 0:
             return (self._alloc(S, K, N), self._alloc(S, nside, N), (S, K, N), (S, nside, N), (S, K * N), (S, nside * N))

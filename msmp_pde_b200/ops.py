@@ -86,6 +86,24 @@ GEMM_MODE = "tc"
 PRECISION = os.environ.get("MSMP_PRECISION", "fp32")
 # persistent warp-specialised weight-gradient kernel (csrc/wgrad_ws.cu); "0" keeps the one-tile-per-CTA k_wgrad_tc
 WGRAD_WS = os.environ.get("MSMP_WGRAD_WS", "1") != "0"
+# ... except for the very tall, narrow products (the LEM weight gradients of the large-graph configs: T x N >= 1 Mi rows,
+# K = 160): there the MMAs of both kernels are bound by the MN-major operand fetch, k_wgrad_ws has no re-read to save and
+# k_wgrad_tc measured faster (3.3 Mi rows x 384: 3.5 against 4.4 ms, profiles/r2_bench_wgrad.jsonl).  fp32 mode only.
+WGRAD_WS_MAX_TALL_ROWS = int(os.environ.get("MSMP_WGRAD_WS_MAX_TALL_ROWS", str(1 << 20)))
+# ... and for small row counts (the reference's 100-node graphs: 6 400 nodes / 37 632 edges per step), where a launch is
+# latency bound either way and the persistent kernel's longer prologue costs more than its single read of the operands
+# saves: C2 step 3.74 ms with k_wgrad_tc against 3.87 ms (C4, 131 072 nodes: 46.9 against 46.0 ms).
+WGRAD_WS_MIN_ROWS = int(os.environ.get("MSMP_WGRAD_WS_MIN_ROWS_USE", str(1 << 16)))
+
+
+def wgrad_use_ws(M: int, Kt: int, Nout: int, nside: int = 1) -> bool:
+    """Which weight-gradient kernel a [M, Kt]^T [M, Nout] product takes in tensor-core mode (gradsink.GradPlan lays its
+    sink regions out accordingly)."""
+    if not (GEMM_MODE == "tc" and WGRAD_WS and Kt % 32 == 0 and Nout % 128 == 0 and nside <= 8):
+        return False
+    if PRECISION == "bf16":
+        return True
+    return M >= WGRAD_WS_MIN_ROWS and not (M >= WGRAD_WS_MAX_TALL_ROWS and Kt <= 192)
 # Persistent (all-T-steps-in-one-launch) LEM kernels; False = one GEMM + one gate kernel per step.
 LEM_PERSISTENT = True
 # tensor-core edge kernels: warp-specialised, weights in tensor memory (edge_ws.cu) | single-role (edge_tc.cu)
@@ -234,8 +252,8 @@ def linear_wgrad(X, dY, K=None, xswish=False, side=None, r=0, has_bias=False, dW
     nside = (r if side is not None else 0) + int(has_bias)
     dev = dY.device
     partial = dWt is not None and dWt.dim() == 3
-    ws_ok = (GEMM_MODE == "tc" and WGRAD_WS and K0 % 32 == 0 and K1 % 32 == 0 and Nout % 128 == 0 and nside <= 8
-             and (side is None or (side.stride(0) <= 16 and side.stride(0) % 4 == 0)))
+    ws_ok = (K0 % 32 == 0 and K1 % 32 == 0 and (side is None or (side.stride(0) <= 16 and side.stride(0) % 4 == 0))
+             and (partial or wgrad_use_ws(M, Kt, Nout, nside)))
     if partial and not ws_ok:
         raise RuntimeError("linear_wgrad: split-M partials were requested for a shape msmp_wgrad_ws does not take")
     if dWt is None:

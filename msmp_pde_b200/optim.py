@@ -105,8 +105,8 @@ class FusedAdamW:
             b1, b2 = g["betas"]
             lr = g["lr"]
             lr = float(lr) if not torch.is_tensor(lr) else float(lr.item())
-            h[gi * self.nh:gi * self.nh + 7] = (lr, b1, b2, g["eps"], g["weight_decay"], 1.0 - b1 ** t,
-                                                (1.0 - b2 ** t) ** 0.5)
+            h[gi * self.nh:gi * self.nh + 8] = (lr, 1.0 - b1, b2, g["eps"], g["weight_decay"], 1.0 - b1 ** t,
+                                                (1.0 - b2 ** t) ** 0.5, 1.0 - b2)
         self.hyper.copy_(torch.from_numpy(h), non_blocking=True)       # pageable source: staged before the call returns
         self._dirty = True
 

