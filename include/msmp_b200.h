@@ -55,7 +55,8 @@ size_t msmp_linear_tc_image_floats(int K, int Nout);
 int msmp_linear_tc_fwd(const float* const* A, const int* lda, const int* ka, const int* aswish, int nseg,
                        const float* Bimg, const float* bias, const float* side, int lds, int r, const float* Wside,
                        int ldws, const float* Zmul, int ldz, float* Ypre, int ldpre, int act, const float* R,
-                       int ldr, float* Y, int ldy, int M, int Nout, cudaStream_t stream);
+                       int ldr, float* Y, int ldy, int M, int Nout, int mode, cudaStream_t stream);
+/* mode 0: error-compensated 3xTF32 (fp32 parity); mode 1: reduced precision -- operands rounded to tf32, one MMA pass. */
 
 /* One launch packs any number of weight blocks into tile images / plain side arrays.  jobs_dev: device array of
  * records {const float* src; float* dst; int ld, transpose; float sign; int kvalid, nvalid, nchunks, kind, ldd}
@@ -147,11 +148,11 @@ int msmp_edge_tc_bwd(const float* P, const float* Q, int ldpq, const int* src, c
 size_t msmp_edge_ws_workspace(int E);
 int msmp_edge_ws_fwd(const float* P, const float* Q, int ldpq, const int* src, const int* dst, const int* rowptr,
                      const float* inv_deg, const float* W, int w_rs, int w_cs, const float* b2, float* z2, float* agg,
-                     int E, int N, void* workspace, size_t ws_bytes, cudaStream_t stream);
+                     int E, int N, int no_isolated, void* workspace, size_t ws_bytes, cudaStream_t stream);
 int msmp_edge_ws_bwd(const float* P, const float* Q, int ldpq, const int* src, const int* dst, const int* rowptr,
                      const float* inv_deg_e, const float* W, int w_rs, int w_cs, const float* z2, const float* dagg,
-                     int lddagg, float* dz2, float* a1, float* dz1, float* dP, int lddp, int E, int N, void* workspace,
-                     size_t ws_bytes, cudaStream_t stream);
+                     int lddagg, float* dz2, float* a1, float* dz1, float* dP, int lddp, int E, int N, int no_isolated,
+                     void* workspace, size_t ws_bytes, cudaStream_t stream);
 
 /* out[n, 0:128] = scale[n] * sum_{k in [ptr[n], ptr[n+1])} src[perm ? perm[k] : k, 0:128]
  * (scale == NULL -> sum; scale = 1/max(count,1) -> mean).  One warp per segment, fixed order, no atomics. */
@@ -228,10 +229,10 @@ int msmp_decoder_bwd(const float* dout, const float* h, const float* za, const f
  * (dy / dz carry the state gradient between them). */
 int msmp_lem_tc_fwd(const float* inp, int ninp, const float* Wt_in, const float* Wzt_in, const float* Wimg,
                     const float* Wzimg, const float* bias, const float* bias_z, float* Y, float* Z, float* gates,
-                    float dt, int T, int N, int Npad, cudaStream_t stream);
+                    float dt, int T, int N, int Npad, int mode, cudaStream_t stream);
 int msmp_lem_tc_bwd(const float* Wzh_img, const float* Wh_img, const float* Y, const float* Z, const float* gates,
                     const float* gY, const float* gZ, int g_last_only, float* dG, float* dL, float* dy, float* dz,
-                    float dt, int T, int t_begin, int t_end, int N, int Npad, cudaStream_t stream);
+                    float dt, int T, int t_begin, int t_end, int N, int Npad, int mode, cudaStream_t stream);
 
 /* out[i] = g[i] * swish'(z[i])  (n % 4 == 0) */
 int msmp_mul_dswish(const float* g, const float* z, float* out, size_t n, cudaStream_t stream);

@@ -38,7 +38,7 @@ _SIGS = {
     "msmp_abi_version": (I, []),
     "msmp_linear_fwd": (I, [P, P, P, P, I, P, I, P, P, I, I, P, P, I, P, I, I, P, I, P, I, I, I, P]),
     "msmp_linear_tc_image_floats": (S, [I, I]),
-    "msmp_linear_tc_fwd": (I, [P, P, P, P, I, P, P, P, I, I, P, I, P, I, P, I, I, P, I, P, I, I, I, P]),
+    "msmp_linear_tc_fwd": (I, [P, P, P, P, I, P, P, P, I, I, P, I, P, I, P, I, I, P, I, P, I, I, I, I, P]),
     "msmp_pack_job_bytes": (I, []),
     "msmp_pack_run": (I, [P, I, I, P]),
     "msmp_unpack_job_bytes": (I, []),
@@ -60,8 +60,8 @@ _SIGS = {
     "msmp_edge_tc_fwd": (I, [P, P, I, P, P, P, P, P, P, P, P, I, I, P, S, P]),
     "msmp_edge_tc_bwd": (I, [P, P, I, P, P, P, P, P, P, P, I, P, P, P, P, I, I, I, P, S, P]),
     "msmp_edge_ws_workspace": (S, [I]),
-    "msmp_edge_ws_fwd": (I, [P, P, I, P, P, P, P, P, I, I, P, P, P, I, I, P, S, P]),
-    "msmp_edge_ws_bwd": (I, [P, P, I, P, P, P, P, P, I, I, P, P, I, P, P, P, P, I, I, I, P, S, P]),
+    "msmp_edge_ws_fwd": (I, [P, P, I, P, P, P, P, P, I, I, P, P, P, I, I, I, P, S, P]),
+    "msmp_edge_ws_bwd": (I, [P, P, I, P, P, P, P, P, I, I, P, P, I, P, P, P, P, I, I, I, I, P, S, P]),
     "msmp_segment_reduce": (I, [P, I, P, P, P, P, I, I, P]),
     "msmp_instnorm_workspace": (S, [I, I]),
     "msmp_instnorm_fwd": (I, [P, P, I, P, P, P, P, P, I, I, I, I, F, P, P, P, S, P]),
@@ -73,8 +73,8 @@ _SIGS = {
     "msmp_decoder_bwd_workspace": (S, [I, I, I, I]),
     "msmp_decoder_fwd": (I, [P, P, P, P, P, P, I, P, P, P, I, I, I, I, I, I, I, P]),
     "msmp_decoder_bwd": (I, [P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, P, S, P]),
-    "msmp_lem_tc_fwd": (I, [P, I, P, P, P, P, P, P, P, P, P, F, I, I, I, P]),
-    "msmp_lem_tc_bwd": (I, [P, P, P, P, P, P, P, I, P, P, P, P, F, I, I, I, I, I, P]),
+    "msmp_lem_tc_fwd": (I, [P, I, P, P, P, P, P, P, P, P, P, F, I, I, I, I, P]),
+    "msmp_lem_tc_bwd": (I, [P, P, P, P, P, P, P, I, P, P, P, P, F, I, I, I, I, I, I, P]),
     "msmp_adamw_job_bytes": (I, []),
     "msmp_adamw_chunk": (I, []),
     "msmp_adamw_hyper_floats": (I, []),

@@ -74,14 +74,19 @@ struct Ring {
 };
 
 // producer lane: one 32 KiB bulk copy of weight chunk image `src` (hi | lo, contiguous) into ring stage i
+// FAST (reduced-precision mode, see linear_tc.cu): only the hi image is copied, only the hi x hi product is issued and the
+// epilogues store only the tf32-rounded state -- half the weight stream from L2 and a third of the MMAs.
+template <bool FAST>
 __device__ __forceinline__ void ring_load(const Ring& rg, uint32_t i, const float* src) {
   const uint32_t s = i % rg.nst, use = i / rg.nst;
   if (use > 0) mbar_wait(&rg.bfree[s], (use - 1) & 1);            // MMAs that read this stage are complete
-  mbar_expect_tx(&rg.bfull[s], LT_STAGE_BYTES);
-  bulk_g2s(rg.smB + s * LT_STAGE_BYTES, src, LT_STAGE_BYTES, &rg.bfull[s]);
+  constexpr uint32_t NB = FAST ? IMG_BYTES : LT_STAGE_BYTES;
+  mbar_expect_tx(&rg.bfull[s], NB);
+  bulk_g2s(rg.smB + s * LT_STAGE_BYTES, src, NB, &rg.bfull[s]);
 }
 
 // MMA-issuing warp (all lanes, convergent): weight chunk in ring slot i (A, 128 channels x 32 k) times state k-chunk at s_img (B, 64 nodes x 32 k)
+template <bool FAST>
 __device__ __forceinline__ void ring_mma(const Ring& rg, uint32_t i, uint32_t s_img, uint32_t tmem_d, bool accumulate) {
   const uint32_t s = i % rg.nst, use = i / rg.nst;
   mbar_wait(&rg.bfull[s], use & 1);                               // (bulk copies write through the async proxy)
@@ -99,8 +104,10 @@ __device__ __forceinline__ void ring_mma(const Ring& rg, uint32_t i, uint32_t s_
     const uint64_t dsh = umma_desc(s_hi + 32 * k, 16, 1024), dsl = umma_desc(s_lo + 32 * k, 16, 1024);
     if (leader) {
       umma_tf32(tmem_d, dwh, dsh, IDESC, (accumulate || k) ? 1u : 0u);
-      umma_tf32(tmem_d, dwl, dsh, IDESC, 1u);
-      umma_tf32(tmem_d, dwh, dsl, IDESC, 1u);
+      if (!FAST) {
+        umma_tf32(tmem_d, dwl, dsh, IDESC, 1u);
+        umma_tf32(tmem_d, dwh, dsl, IDESC, 1u);
+      }
     }
   }
   if (leader) umma_commit(&rg.bfree[s]);
@@ -123,11 +130,12 @@ struct Epi {
 // MMA warp (all lanes): issue one GEMM phase of `nchunks` ring chunks; chunk j multiplies k-chunk (j & 3) of the state
 // tile at `sbase` into TMEM columns dcol + 64 * (j >> 2) (the first chunk of every 64-column block overwrites unless
 // acc_first), then commits to `done` (if not null).
+template <bool FAST>
 __device__ __forceinline__ void gemm_issue(Epi& e, uint32_t sbase, uint32_t nchunks, uint32_t dcol, bool acc_first,
                                            uint64_t* done) {
   tc_fence_after();
   for (uint32_t j = 0; j < nchunks; ++j)
-    ring_mma(e.rg, e.nchunk + j, sbase + (j & 3) * 2 * LT_SCHUNK, e.tmem + dcol + LT_NODES * (j >> 2), acc_first || (j & 3) != 0);
+    ring_mma<FAST>(e.rg, e.nchunk + j, sbase + (j & 3) * 2 * LT_SCHUNK, e.tmem + dcol + LT_NODES * (j >> 2), acc_first || (j & 3) != 0);
   e.nchunk += nchunks;
   if (done != nullptr && elect_one()) umma_commit(done);
   __syncwarp();
@@ -137,11 +145,12 @@ __device__ __forceinline__ void gemm_issue(Epi& e, uint32_t sbase, uint32_t nchu
 __device__ __forceinline__ uint32_t state_off(int j, int k) {
   return (uint32_t)(k >> 5) * (2 * LT_SCHUNK) + img_off(j, (k & 31) >> 2) + 4u * (uint32_t)(k & 3);
 }
+template <bool FAST>
 __device__ __forceinline__ void state_store(uint32_t smS, uint32_t off, float v) {
   float h, l;
   split_tf32(v, h, l);
   asm volatile("st.shared.f32 [%0], %1;" ::"r"(smS + off), "f"(h) : "memory");
-  asm volatile("st.shared.f32 [%0], %1;" ::"r"(smS + off + LT_SCHUNK), "f"(l) : "memory");
+  if (!FAST) asm volatile("st.shared.f32 [%0], %1;" ::"r"(smS + off + LT_SCHUNK), "f"(l) : "memory");
 }
 
 // clock64() phase stamps of CTA 0 at step 2 (scripts/lem_ticks.py); compiled in only with -DMSMP_LEM_TICKS.
@@ -224,6 +233,7 @@ constexpr uint32_t LF_G = 0, LF_L = 192, LF_PRE = 256;
 __device__ __forceinline__ void state_ready_arrive() { asm volatile("bar.arrive 2, 288;" ::: "memory"); }
 __device__ __forceinline__ void state_ready_wait() { asm volatile("bar.sync 2, 288;" ::: "memory"); }
 
+template <bool FAST>
 __global__ void __launch_bounds__(LF_THREADS, 1) k_lem_fwd_tc(const LemFwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   const LemSmem m = lem_smem(smem_raw, 1, 5);
@@ -238,8 +248,8 @@ __global__ void __launch_bounds__(LF_THREADS, 1) k_lem_fwd_tc(const LemFwdParams
     if (elect_one()) {
       uint32_t n = 0;
       for (int t = 0; t < p.T; ++t) {
-        for (int j = 0; j < 12; ++j) ring_load(rg, n++, p.Wimg + (size_t)j * 2 * (IMG_BYTES / 4));
-        for (int j = 0; j < 4; ++j) ring_load(rg, n++, p.Wzimg + (size_t)j * 2 * (IMG_BYTES / 4));
+        for (int j = 0; j < 12; ++j) ring_load<FAST>(rg, n++, p.Wimg + (size_t)j * 2 * (IMG_BYTES / 4));
+        for (int j = 0; j < 4; ++j) ring_load<FAST>(rg, n++, p.Wzimg + (size_t)j * 2 * (IMG_BYTES / 4));
       }
     }
     __syncwarp();
@@ -248,9 +258,9 @@ __global__ void __launch_bounds__(LF_THREADS, 1) k_lem_fwd_tc(const LemFwdParams
     Epi e = lem_epi(m);
     for (int t = 0; t < p.T; ++t) {
       state_ready_wait();                                   // y_{t-1} tile written, G accumulator of step t-1 consumed
-      gemm_issue(e, e.smS, 12, LF_G, false, e.acc);
+      gemm_issue<FAST>(e, e.smS, 12, LF_G, false, e.acc);
       state_ready_wait();                                   // z_t tile written, L accumulator of step t-1 consumed
-      gemm_issue(e, e.smS, 4, LF_L, false, e.acc);
+      gemm_issue<FAST>(e, e.smS, 4, LF_L, false, e.acc);
     }
   } else {
     Epi e = lem_epi(m);
@@ -324,7 +334,7 @@ __global__ void __launch_bounds__(LF_THREADS, 1) k_lem_fwd_tc(const LemFwdParams
       const int g = row0 + j0 + q;
       yreg[q] = g < p.N ? __ldg(p.Y + (size_t)g * 128 + c) : 0.f;
       zreg[q] = g < p.N ? __ldg(p.Z + (size_t)g * 128 + c) : 0.f;
-      state_store(e.smS, state_off(j0 + q, c), yreg[q]);
+      state_store<FAST>(e.smS, state_off(j0 + q, c), yreg[q]);
     }
     publish_to_mma();
 
@@ -364,7 +374,7 @@ __global__ void __launch_bounds__(LF_THREADS, 1) k_lem_fwd_tc(const LemFwdParams
           g_t[(size_t)j * 512 + 128 + c] = b;
           g_t[(size_t)j * 512 + 256 + c] = zc;
           if (row0 + j < p.N) znext[(size_t)j * 128 + c] = zn;
-          state_store(e.smS, state_off(j, c), zn);      // z_t: B operand of the L GEMM
+          state_store<FAST>(e.smS, state_off(j, c), zn);      // z_t: B operand of the L GEMM
         }
         tmem_st8(tbase + LF_PRE + jj, av);      // the gate-0 projection columns are consumed: stash a for gate_y there
       }
@@ -391,7 +401,7 @@ __global__ void __launch_bounds__(LF_THREADS, 1) k_lem_fwd_tc(const LemFwdParams
           yreg[jj + q] = yn;
           g_t[(size_t)j * 512 + 384 + c] = tl;
           if (row0 + j < p.N) ynext[(size_t)j * 128 + c] = yn;
-          state_store(e.smS, state_off(j, c), yn);      // y_t: B operand of the next G GEMM
+          state_store<FAST>(e.smS, state_off(j, c), yn);      // y_t: B operand of the next G GEMM
         }
       }
       if (t + 1 < p.T) publish_to_mma();
@@ -434,6 +444,7 @@ constexpr int LB_THREADS = 32 * LB_EPI_WARPS + 64;          // + ring producer w
 __device__ __forceinline__ void bwd_ready_arrive() { asm volatile("bar.arrive 2, %0;" ::"n"(32 * LB_EPI_WARPS + 32) : "memory"); }
 __device__ __forceinline__ void bwd_ready_wait() { asm volatile("bar.sync 2, %0;" ::"n"(32 * LB_EPI_WARPS + 32) : "memory"); }
 
+template <bool FAST>
 __global__ void __launch_bounds__(LB_THREADS, 1) k_lem_bwd_tc(const LemBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   const LemSmem m = lem_smem(smem_raw, 2, 3);      // two state tiles (X, Y) + 3 ring stages
@@ -449,8 +460,8 @@ __global__ void __launch_bounds__(LB_THREADS, 1) k_lem_bwd_tc(const LemBwdParams
     if (elect_one()) {
       uint32_t n = 0;
       for (int t = p.t_end - 1; t >= p.t_begin; --t) {
-        for (int j = 0; j < 4; ++j) ring_load(rg, n++, p.Wzh_img + (size_t)j * 2 * (IMG_BYTES / 4));
-        for (int j = 0; j < 12; ++j) ring_load(rg, n++, p.Wh_img + (size_t)((j + 4) % 12) * 2 * (IMG_BYTES / 4));
+        for (int j = 0; j < 4; ++j) ring_load<FAST>(rg, n++, p.Wzh_img + (size_t)j * 2 * (IMG_BYTES / 4));
+        for (int j = 0; j < 12; ++j) ring_load<FAST>(rg, n++, p.Wh_img + (size_t)((j + 4) % 12) * 2 * (IMG_BYTES / 4));
       }
     }
     __syncwarp();
@@ -460,12 +471,12 @@ __global__ void __launch_bounds__(LB_THREADS, 1) k_lem_bwd_tc(const LemBwdParams
     const uint32_t X = e.smS, Y = e.smS + LT_S_BYTES;
     for (int t = p.t_end - 1; t >= p.t_begin; --t) {
       bwd_ready_wait();                                         // dL in X
-      gemm_issue(e, X, 4, LB_ACC1, false, e.acc);                 // acc1 = Wz[:, :128]^T dL^T
+      gemm_issue<FAST>(e, X, 4, LB_ACC1, false, e.acc);                 // acc1 = Wz[:, :128]^T dL^T
       bwd_ready_wait();                                         // dG1 in X, dG2 in Y
-      gemm_issue(e, X, 4, LB_ACC2, false, acc_mid);               // acc2  = W[128:256, :128]^T dG1^T   (X free afterwards)
-      gemm_issue(e, Y, 4, LB_ACC2, true, nullptr);                // acc2 += W[256:384, :128]^T dG2^T
+      gemm_issue<FAST>(e, X, 4, LB_ACC2, false, acc_mid);               // acc2  = W[128:256, :128]^T dG1^T   (X free afterwards)
+      gemm_issue<FAST>(e, Y, 4, LB_ACC2, true, nullptr);                // acc2 += W[256:384, :128]^T dG2^T
       bwd_ready_wait();                                         // dG0 in X
-      gemm_issue(e, X, 4, LB_ACC2, true, e.acc);                  // acc2 += W[0:128, :128]^T dG0^T
+      gemm_issue<FAST>(e, X, 4, LB_ACC2, true, e.acc);                  // acc2 += W[0:128, :128]^T dG0^T
     }
   } else {
     Epi e = lem_epi(m);
@@ -532,7 +543,7 @@ __global__ void __launch_bounds__(LB_THREADS, 1) k_lem_bwd_tc(const LemBwdParams
             dG_t[(size_t)j * 384 + c] = g0[q];
           }
           dyreg[jj + q] = d * (1.f - a);
-          state_store(X, state_off(j, c), dl);
+          state_store<FAST>(X, state_off(j, c), dl);
         }
         tmem_st8(tbase + LB_S0 + jj, g0);
         LEM_TICK(40 + jj / 8);
@@ -571,8 +582,8 @@ __global__ void __launch_bounds__(LB_THREADS, 1) k_lem_bwd_tc(const LemBwdParams
             dG_t[(size_t)j * 384 + 256 + c] = g2;
           }
           dzreg[jj + q] = d * (1.f - b);
-          state_store(X, state_off(j, c), g1);
-          state_store(Y, state_off(j, c), g2);
+          state_store<FAST>(X, state_off(j, c), g1);
+          state_store<FAST>(Y, state_off(j, c), g2);
         }
       }
       publish_to_mma();
@@ -604,7 +615,7 @@ __global__ void __launch_bounds__(LB_THREADS, 1) k_lem_bwd_tc(const LemBwdParams
         tmem_ld8_nowait(tbase + LB_S0 + jj, r0);
         tmem_ld_wait();
 #pragma unroll
-        for (int q = 0; q < 8; ++q) state_store(X, state_off(j0 + jj + q, c), __uint_as_float(r0[q]));
+        for (int q = 0; q < 8; ++q) state_store<FAST>(X, state_off(j0 + jj + q, c), __uint_as_float(r0[q]));
       }
       publish_to_mma();
       LEM_TICK(37);
@@ -645,17 +656,21 @@ extern "C" int msmp_lem_debug_ticks(long long* host_out) {
 
 extern "C" int msmp_lem_tc_fwd(const float* inp, int ninp, const float* Wt_in, const float* Wzt_in, const float* Wimg,
                                const float* Wzimg, const float* bias, const float* bias_z, float* Y, float* Z,
-                               float* gates, float dt, int T, int N, int Npad, cudaStream_t stream) {
+                               float* gates, float dt, int T, int N, int Npad, int mode, cudaStream_t stream) {
   if (T < 0 || N < 0 || ninp < 0 || ninp > 8 || Npad < N || (Npad % LT_NODES)) return MSMP_ERR_ARG;
   if (T == 0 || N == 0) return MSMP_OK;
   LemFwdParams p{inp, Wt_in, Wzt_in, bias, bias_z, Wimg, Wzimg, Y, Z, gates, dt, T, N, Npad, ninp};
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(k_lem_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_SMEM) != cudaSuccess)
+    if (cudaFuncSetAttribute(k_lem_fwd_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(k_lem_fwd_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_SMEM) != cudaSuccess)
       return MSMP_ERR_CUDA;
     attr_set = true;
   }
-  k_lem_fwd_tc<<<Npad / LT_NODES, LF_THREADS, LT_SMEM, stream>>>(p);
+  if (mode)
+    k_lem_fwd_tc<true><<<Npad / LT_NODES, LF_THREADS, LT_SMEM, stream>>>(p);
+  else
+    k_lem_fwd_tc<false><<<Npad / LT_NODES, LF_THREADS, LT_SMEM, stream>>>(p);
   MSMP_CHECK_LAUNCH();
   return MSMP_OK;
 }
@@ -663,17 +678,21 @@ extern "C" int msmp_lem_tc_fwd(const float* inp, int ninp, const float* Wt_in, c
 extern "C" int msmp_lem_tc_bwd(const float* Wzh_img, const float* Wh_img, const float* Y, const float* Z,
                                const float* gates, const float* gY, const float* gZ, int g_last_only, float* dG,
                                float* dL, float* dy, float* dz, float dt, int T, int t_begin, int t_end, int N,
-                               int Npad, cudaStream_t stream) {
+                               int Npad, int mode, cudaStream_t stream) {
   if (T < 0 || N < 0 || Npad < N || (Npad % LT_NODES) || t_begin < 0 || t_end > T || t_begin > t_end) return MSMP_ERR_ARG;
   if (t_begin == t_end || N == 0) return MSMP_OK;
   LemBwdParams p{Wzh_img, Wh_img, Y, Z, gates, gY, gZ, g_last_only, dG, dL, dy, dz, dt, T, N, Npad, t_begin, t_end};
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(k_lem_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_SMEM) != cudaSuccess)
+    if (cudaFuncSetAttribute(k_lem_bwd_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(k_lem_bwd_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_SMEM) != cudaSuccess)
       return MSMP_ERR_CUDA;
     attr_set = true;
   }
-  k_lem_bwd_tc<<<Npad / LT_NODES, LB_THREADS, LT_SMEM, stream>>>(p);
+  if (mode)
+    k_lem_bwd_tc<true><<<Npad / LT_NODES, LB_THREADS, LT_SMEM, stream>>>(p);
+  else
+    k_lem_bwd_tc<false><<<Npad / LT_NODES, LB_THREADS, LT_SMEM, stream>>>(p);
   MSMP_CHECK_LAUNCH();
   return MSMP_OK;
 }

@@ -56,6 +56,19 @@ struct LinTcParams {
 // and bias / side weights are per-thread constants of a half block.  Same arithmetic per output element as before.
 constexpr int EPI_TILE_FLOATS = 32 * 20;
 
+// FAST (reduced-precision mode): operands rounded to tf32 once, ONE MMA pass (hi x hi): no lo images are written, only
+// the hi half of every weight chunk is copied (16 instead of 32 KiB from L2) and 4 instead of 12 MMAs run per chunk.
+// Error of a K = 256 product: ~3e-4 of max|ref| (tf32 keeps 10 mantissa bits, three more than bf16).
+__device__ __forceinline__ void store_hi4(uint8_t* hi_img, uint32_t off, float4 v) {
+  float4 h;
+  float l;
+  split_tf32(v.x, h.x, l);
+  split_tf32(v.y, h.y, l);
+  split_tf32(v.z, h.z, l);
+  split_tf32(v.w, h.w, l);
+  *reinterpret_cast<float4*>(hi_img + off) = h;
+}
+
 __device__ __forceinline__ float4 dswish4(float4 z) { return make_float4(dswish(z.x), dswish(z.y), dswish(z.z), dswish(z.w)); }
 
 __device__ __forceinline__ void lin_epilogue32(const LinTcParams& p, float* tb, const float (&v)[32], int row_base,
@@ -112,6 +125,7 @@ __device__ __forceinline__ void lin_epilogue32(const LinTcParams& p, float* tb, 
   }
 }
 
+template <bool FAST>
 __global__ void __launch_bounds__(256, 1) k_linear_tc(const LinTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -171,8 +185,9 @@ __global__ void __launch_bounds__(256, 1) k_linear_tc(const LinTcParams p) {
   const float* bsrc = p.Bimg + (size_t)ntile * nchunks * (TC_B_BYTES / 4);
   auto issue_b = [&](int c) {      // thread 0: bulk copy of the (hi | lo) weight images of chunk c
     uint64_t* bar = &bars[c & 3];
-    mbar_expect_tx(bar, TC_B_BYTES);
-    bulk_g2s(smemB + (c & 3) * TC_B_BYTES, bsrc + (size_t)c * (TC_B_BYTES / 4), TC_B_BYTES, bar);
+    constexpr uint32_t NB = FAST ? IMG_BYTES : TC_B_BYTES;
+    mbar_expect_tx(bar, NB);
+    bulk_g2s(smemB + (c & 3) * TC_B_BYTES, bsrc + (size_t)c * (TC_B_BYTES / 4), NB, bar);
   };
   if (tid == 0)
     for (int c = 0; c < nchunks && c < TC_B_STAGES; ++c) issue_b(c);
@@ -188,7 +203,10 @@ __global__ void __launch_bounds__(256, 1) k_linear_tc(const LinTcParams p) {
       const int idx = tid + 256 * i;
       float4 v = pre[i];
       if (pre_sw) v = swish4(v);
-      store_split4(st, st + IMG_BYTES, img_off(idx >> 3, idx & 7), v);
+      if (FAST)
+        store_hi4(st, img_off(idx >> 3, idx & 7), v);
+      else
+        store_split4(st, st + IMG_BYTES, img_off(idx >> 3, idx & 7), v);
     }
     if (c + 2 < nchunks) prefetch(c + 2, pre, pre_sw);
     fence_proxy_async();
@@ -206,8 +224,10 @@ __global__ void __launch_bounds__(256, 1) k_linear_tc(const LinTcParams p) {
         const uint64_t dbh = umma_desc(b_hi + 32 * k, 16, 1024), dbl = umma_desc(b_lo + 32 * k, 16, 1024);
         if (leader) {
           umma_tf32(tm, dah, dbh, IDESC, (c | k) ? 1u : 0u);
-          umma_tf32(tm, dal, dbh, IDESC, 1u);
-          umma_tf32(tm, dah, dbl, IDESC, 1u);
+          if (!FAST) {
+            umma_tf32(tm, dal, dbh, IDESC, 1u);
+            umma_tf32(tm, dah, dbl, IDESC, 1u);
+          }
         }
       }
       if (leader) umma_commit(&bars[4 + s]);
@@ -260,6 +280,7 @@ constexpr int LW_MMA_WARP = LW_EPI_WARPS + LW_PROD_WARPS;              // 16; wa
 constexpr int LW_THREADS = 32 * (LW_MMA_WARP + 4);
 constexpr int LW_SMEM = 1024 + LW_STAGES * LW_STAGE_BYTES + 256 + LW_EPI_WARPS * EPI_TILE_FLOATS * 4;
 
+template <bool FAST>
 __global__ void __launch_bounds__(LW_THREADS, 1) k_linear_ws(const LinTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -351,8 +372,10 @@ __global__ void __launch_bounds__(LW_THREADS, 1) k_linear_ws(const LinTcParams p
             const uint64_t dbh = umma_desc(b_hi + 32 * k, 16, 1024), dbl = umma_desc(b_lo + 32 * k, 16, 1024);
             if (leader) {
               umma_tf32(acc, dah, dbh, IDESC, (c | k) ? 1u : 0u);
-              umma_tf32(acc, dal, dbh, IDESC, 1u);
-              umma_tf32(acc, dah, dbl, IDESC, 1u);
+              if (!FAST) {
+                umma_tf32(acc, dal, dbh, IDESC, 1u);
+                umma_tf32(acc, dah, dbl, IDESC, 1u);
+              }
             }
           }
           if (leader) {
@@ -375,8 +398,9 @@ __global__ void __launch_bounds__(LW_THREADS, 1) k_linear_ws(const LinTcParams p
           const float* bsrc = p.Bimg + (size_t)(t % nct) * nchunks * (TC_B_BYTES / 4);
           for (int c = 0; c < nchunks; ++c, ++n) {
             if (n >= LW_STAGES) mbar_wait(&empty[s], ph ^ 1);
-            mbar_expect_tx(&w_full[s], TC_B_BYTES);
-            bulk_g2s(smem + s * LW_STAGE_BYTES + TC_A_BYTES, bsrc + (size_t)c * (TC_B_BYTES / 4), TC_B_BYTES, &w_full[s]);
+            constexpr uint32_t NB = FAST ? IMG_BYTES : TC_B_BYTES;
+            mbar_expect_tx(&w_full[s], NB);
+            bulk_g2s(smem + s * LW_STAGE_BYTES + TC_A_BYTES, bsrc + (size_t)c * (TC_B_BYTES / 4), NB, &w_full[s]);
             if (++s == LW_STAGES) {
               s = 0;
               ph ^= 1;
@@ -416,7 +440,10 @@ __global__ void __launch_bounds__(LW_THREADS, 1) k_linear_ws(const LinTcParams p
       for (int q = 0; q < 4; ++q) {
         float4 v = pre[q];
         if (sw) v = swish4(v);
-        store_split4(st, st + IMG_BYTES, img_off((pt >> 3) + 32 * q, c16), v);
+        if (FAST)
+          store_hi4(st, img_off((pt >> 3) + 32 * q, c16), v);
+        else
+          store_split4(st, st + IMG_BYTES, img_off((pt >> 3) + 32 * q, c16), v);
       }
       fence_proxy_async();
       __syncwarp();
@@ -472,7 +499,7 @@ extern "C" size_t msmp_linear_tc_image_floats(int K, int Nout) {
 extern "C" int msmp_linear_tc_fwd(const float* const* A, const int* lda, const int* ka, const int* aswish, int nseg,
                                   const float* Bimg, const float* bias, const float* side, int lds, int r,
                                   const float* Wside, int ldws, const float* Zmul, int ldz, float* Ypre, int ldpre,
-                                  int act, const float* R, int ldr, float* Y, int ldy, int M, int Nout,
+                                  int act, const float* R, int ldr, float* Y, int ldy, int M, int Nout, int mode,
                                   cudaStream_t stream) {
   if (nseg < 1 || nseg > 3 || M < 0 || Nout <= 0 || (Nout & 3) || r < 0 || r > 8) return MSMP_ERR_ARG;
   if (M == 0) return MSMP_OK;
@@ -489,8 +516,10 @@ extern "C" int msmp_linear_tc_fwd(const float* const* A, const int* lda, const i
   p.Y = Y; p.ldy = ldy; p.M = M; p.Nout = Nout;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(k_linear_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM) != cudaSuccess ||
-        cudaFuncSetAttribute(k_linear_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, LW_SMEM) != cudaSuccess)
+    if (cudaFuncSetAttribute(k_linear_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(k_linear_ws<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LW_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(k_linear_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(k_linear_ws<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LW_SMEM) != cudaSuccess)
       return MSMP_ERR_CUDA;
     attr_set = true;
   }
@@ -502,11 +531,17 @@ extern "C" int msmp_linear_tc_fwd(const float* const* A, const int* lda, const i
   static const int sms = [] { int d = 0, n = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); return n; }();
   const int ntiles = (int)(grid.x * grid.y);
   if (ws_min_tiles > 0 && ntiles >= ws_min_tiles) {
-    k_linear_ws<<<ntiles < sms ? ntiles : sms, LW_THREADS, LW_SMEM, stream>>>(p);
+    if (mode)
+      k_linear_ws<true><<<ntiles < sms ? ntiles : sms, LW_THREADS, LW_SMEM, stream>>>(p);
+    else
+      k_linear_ws<false><<<ntiles < sms ? ntiles : sms, LW_THREADS, LW_SMEM, stream>>>(p);
     MSMP_CHECK_LAUNCH();
     return MSMP_OK;
   }
-  k_linear_tc<<<grid, 256, TC_SMEM, stream>>>(p);
+  if (mode)
+    k_linear_tc<true><<<grid, 256, TC_SMEM, stream>>>(p);
+  else
+    k_linear_tc<false><<<grid, 256, TC_SMEM, stream>>>(p);
   MSMP_CHECK_LAUNCH();
   return MSMP_OK;
 }

@@ -37,6 +37,7 @@ class Topology:
     chunk_begin: torch.Tensor    # int32 [C]
     chunk_end: torch.Tensor      # int32 [C]
     graph_chunk_ptr: torch.Tensor  # int32 [B+1]
+    no_isolated: bool = False    # every node has at least one in-edge: the edge kernels' outputs need no zero fill
 
     @property
     def nchunks(self) -> int:
@@ -81,7 +82,8 @@ def build_topology(edge_index: torch.Tensor, batch: torch.Tensor, num_nodes: int
                     inv_deg_e=inv_deg[dst64].contiguous(),
                     one_chunk_per_graph=bool(B > 0 and int(counts.min()) >= 1 and int(counts.max()) <= CHUNK_ROWS),
                     colptr=i32(colptr), csc_perm=i32(csc_perm), csr_perm=csr_perm, node_graph=i32(batch),
-                    chunk_begin=i32(cb), chunk_end=i32(ce), graph_chunk_ptr=i32(gcp))
+                    chunk_begin=i32(cb), chunk_end=i32(ce), graph_chunk_ptr=i32(gcp),
+                    no_isolated=bool(N > 0 and E > 0 and int(deg.min()) > 0))
 
 
 _CACHE: dict = {}

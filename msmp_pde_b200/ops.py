@@ -225,7 +225,7 @@ def linear_tc_fwd(segs, img, Nout, bias=None, side=None, r=0, Wside=None, Zmul=N
                                  _ld(Wside) if Wside is not None else 0, _p(Zmul),
                                  _ld(Zmul) if Zmul is not None else 0, _p(Ypre), _ld(Ypre) if Ypre is not None else 0,
                                  int(act), _p(R), _ld(R) if R is not None else 0, out.data_ptr(), _ld(out), M, Nout,
-                                 _stream()), "msmp_linear_tc_fwd")
+                                 1 if PRECISION == "bf16" else 0, _stream()), "msmp_linear_tc_fwd")
     _count(1)
     return out
 
@@ -343,8 +343,8 @@ def edge_fwd(P, Q, topo, W2t, b2, save_z2=True, W2raw=None):
         with _timed("edge_ws_fwd", 2.0 * topo.E * H * H, 4.0 * H * (3 * topo.E + topo.N)):
             check(lib.msmp_edge_ws_fwd(P.data_ptr(), Q.data_ptr(), _ld(P), topo.src.data_ptr(), topo.dst.data_ptr(),
                                        topo.rowptr.data_ptr(), topo.inv_deg.data_ptr(), Wa.data_ptr(), rs, cs,
-                                       b2.data_ptr(), _p(z2), agg.data_ptr(), topo.E, topo.N, ws.data_ptr(), ws.numel(),
-                                       _stream()), "msmp_edge_ws_fwd")
+                                       b2.data_ptr(), _p(z2), agg.data_ptr(), topo.E, topo.N, int(topo.no_isolated),
+                                       ws.data_ptr(), ws.numel(), _stream()), "msmp_edge_ws_fwd")
         _count(2)
         return agg, z2
     if GEMM_MODE == "tc" or isinstance(W2t, TcW):
@@ -383,8 +383,8 @@ def edge_bwd(P, Q, topo, W2, z2, dagg, dP, defer_wgrad=False, W2raw=None):
                 check(lib.msmp_edge_ws_bwd(P.data_ptr(), Q.data_ptr(), _ld(P), topo.src.data_ptr(), topo.dst.data_ptr(),
                                            topo.rowptr.data_ptr(), topo.inv_deg_e.data_ptr(), Wa.data_ptr(), rs, cs,
                                            z2.data_ptr(), dagg.data_ptr(), _ld(dagg), dz2.data_ptr(), a1.data_ptr(),
-                                           dz1.data_ptr(), dP.data_ptr(), _ld(dP), topo.E, topo.N, ws.data_ptr(),
-                                           ws.numel(), _stream()), "msmp_edge_ws_bwd")
+                                           dz1.data_ptr(), dP.data_ptr(), _ld(dP), topo.E, topo.N, int(topo.no_isolated),
+                                           ws.data_ptr(), ws.numel(), _stream()), "msmp_edge_ws_bwd")
         else:
             img = W2.img if isinstance(W2, TcW) else _cached_images(W2)
             with _timed("edge_tc_bwd", 2.0 * topo.E * H * H, 4.0 * H * (7 * topo.E + topo.N)):
@@ -571,7 +571,8 @@ def lem_tc_fwd(inp, ninp, Wt_in, Wzt_in, Wt_h, Wzt_h, bias, bias_z, Y, Z, dt):
     with _timed("lem_tc_fwd", 2.0 * T * N * H * 4 * H, 4.0 * T * N * (512 + 4 * H + 8)):
       check(lib.msmp_lem_tc_fwd(inp.data_ptr(), int(ninp), Wt_in.data_ptr(), Wzt_in.data_ptr(), _img_of(Wt_h).data_ptr(),
                               _img_of(Wzt_h).data_ptr(), bias.data_ptr(), bias_z.data_ptr(),
-                              Y.data_ptr(), Z.data_ptr(), gates.data_ptr(), float(dt), T, N, Npad, _stream()),
+                              Y.data_ptr(), Z.data_ptr(), gates.data_ptr(), float(dt), T, N, Npad,
+                              1 if PRECISION == "bf16" else 0, _stream()),
             "msmp_lem_tc_fwd")
     _count(1)
     return gates
@@ -593,7 +594,8 @@ def lem_tc_bwd(Wzh, Wh, Y, Z, gates, gY, gZ, last_only, dG, dL, dt, N, state, t_
     with _timed("lem_tc_bwd", 2.0 * nst * N * H * 4 * H, 4.0 * nst * N * (512 + 512 + 6 * H)):
       check(lib.msmp_lem_tc_bwd(_img_of(Wzh).data_ptr(), _img_of(Wh).data_ptr(), Y.data_ptr(), Z.data_ptr(),
                               gates.data_ptr(), _p(gY), _p(gZ), int(bool(last_only)), dG.data_ptr(), dL.data_ptr(),
-                              dy.data_ptr(), dz.data_ptr(), float(dt), T, t_begin, t_end, N, Npad, _stream()),
+                              dy.data_ptr(), dz.data_ptr(), float(dt), T, t_begin, t_end, N, Npad,
+                              1 if PRECISION == "bf16" else 0, _stream()),
             "msmp_lem_tc_bwd")
     _count(1)
     return dy, dz

@@ -271,3 +271,46 @@ def test_dp_nccl_step_equals_single_gpu():
         assert r["loss_rel_err"] < 1e-6, (mode, r)
         assert r["grad_max_rel_err"] < 1e-5, (mode, r)
         assert r["weight_max_abs_err_over_lr"] <= 2.0 + 1e-6 and r["weight_mismatch_frac"] < 1e-3, (mode, r)
+
+
+# ------------------------------------------------------------------------------------------- reduced-precision mode
+BF16_OUT_TOL = 2e-3          # of max|ref|  (measured 3e-4 .. 6e-4 on these fixtures)
+BF16_GRAD_TOL = 3e-2         # per tensor, of max|ref_t| + 5e-3 of the largest gradient
+
+
+@pytest.mark.parametrize("cfg", ["c2", "c3"])
+def test_reduced_precision_mode_tolerance(cfg):
+    """north_star's 'bf16 mode': ops.PRECISION = 'bf16' runs the weight gradients with bf16 operands (fp32 accumulation)
+    and the node-level / LEM GEMMs with operands rounded once to tf32 (one MMA pass); the message kernel stays
+    error-compensated.  Outputs and gradients against the float64 oracle at the stated looser tolerance, and the mode must
+    really be active (error above the fp32-parity bar)."""
+    from msmp_pde_b200 import models_gnn2D, ops, synth
+    from oracle import models as om
+    dev = torch.device("cuda:0")
+    pde, data, meta = (synth.config_c2 if cfg == "c2" else synth.config_c3)(B=6, nx=100, seed=5)
+    torch.manual_seed(1)
+    model = models_gnn2D.MP_PDE_Solver2DLEMLinGated(pde, 25, 128, 6, meta["eq_variables"]).to(dev)
+    torch.set_default_dtype(torch.float64)
+    ref = om.MP_PDE_Solver2DLEMLinGated(pde, 25, 128, 6, meta["eq_variables"])
+    ref.load_state_dict({k: v.double().cpu() for k, v in model.state_dict().items()})
+    outr = ref(data)
+    torch.sqrt(((outr - data.y) ** 2).sum()).backward()
+    dd = data.clone().to(dev)
+    prev = ops.PRECISION
+    ops.PRECISION = "bf16"
+    try:
+        out = model(dd)
+        torch.sqrt(((out - dd.y) ** 2).sum()).backward()
+    finally:
+        ops.PRECISION = prev
+    e_out = rel_err(out, outr)
+    refs = dict(ref.named_parameters())
+    gscale = max(float(p.grad.abs().max()) for p in refs.values())
+    worst = 0.0
+    for name, p in model.named_parameters():
+        r = refs[name].grad
+        allow = BF16_GRAD_TOL * float(r.abs().max()) + 5e-3 * gscale
+        worst = max(worst, float((p.grad.double().cpu() - r).abs().max()) / allow)
+    print(f"reduced precision {cfg}: out rel err {e_out:.2e}, worst gradient error / allowance {worst:.3f}")
+    assert 1e-5 < e_out < BF16_OUT_TOL
+    assert worst <= 1.0

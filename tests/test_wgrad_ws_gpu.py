@@ -5,6 +5,16 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
+
+@pytest.fixture(autouse=True)
+def _always_the_persistent_kernel():
+    """ops.wgrad_use_ws() hands small / very tall products to k_wgrad_tc; these tests are about k_wgrad_ws itself."""
+    from msmp_pde_b200 import ops
+    prev = (ops.WGRAD_WS_MIN_ROWS, ops.WGRAD_WS_MAX_TALL_ROWS)
+    ops.WGRAD_WS_MIN_ROWS, ops.WGRAD_WS_MAX_TALL_ROWS = 0, 1 << 62
+    yield
+    ops.WGRAD_WS_MIN_ROWS, ops.WGRAD_WS_MAX_TALL_ROWS = prev
+
 from tests.util import rel_err  # noqa: E402
 
 # (M, K0, K1, Nout, r, has_bias, xswish)  -- K1 = 0: single segment
@@ -105,3 +115,18 @@ def test_wgrad_ws_bf16_mode(shape):
     assert rel_err(dW, rW) > 1e-5            # really ran with bf16 operands
     if rWs is not None:
         assert rel_err(dWs, rWs) < BF16_TOL
+
+
+def test_kernel_selection_policy():
+    """Small and very tall products go to k_wgrad_tc, the rest to k_wgrad_ws; both give the same gradient to fp32 accuracy."""
+    from msmp_pde_b200 import ops
+    ops.WGRAD_WS_MIN_ROWS, ops.WGRAD_WS_MAX_TALL_ROWS = 1 << 16, 1 << 20
+    assert not ops.wgrad_use_ws(6400, 256, 128, 4)
+    assert ops.wgrad_use_ws(131072, 256, 128, 4)
+    assert not ops.wgrad_use_ws(25 * 131072, 160, 384, 1)
+    assert ops.wgrad_use_ws(25 * 131072, 256, 128, 1)
+    X, X1, dY, side = _inputs(70000, 128, 64, 256, 4, seed=3)
+    a, a_s = ops.linear_wgrad(X, dY, side=side, r=4, has_bias=True, X1=X1)              # k_wgrad_ws
+    ops.WGRAD_WS_MIN_ROWS = 1 << 30
+    b, b_s = ops.linear_wgrad(X, dY, side=side, r=4, has_bias=True, X1=X1)              # k_wgrad_tc
+    assert rel_err(a, b) < 5e-6 and rel_err(a_s, b_s) < 5e-6
