@@ -11,119 +11,14 @@
 //              releases the stage; production of chunk c+1 overlaps the MMAs of chunk c
 //   epilogue : tcgen05.ld (32 lanes x 32 columns per warp) -> bias / side / swish / residual -> global
 #include <cstdlib>
-#include "umma.cuh"
+#include "linear_common.cuh"
 #include "msmp_b200.h"
 
 namespace msmp {
 
 constexpr int TC_A_STAGES = 2;                                // A_hi, A_lo per stage (32 KiB)
 constexpr int TC_B_STAGES = 4;                                // B_hi, B_lo per stage (32 KiB), prefetched ahead
-constexpr int TC_A_BYTES = 2 * IMG_BYTES, TC_B_BYTES = 2 * IMG_BYTES;
 constexpr int TC_SMEM = TC_A_STAGES * TC_A_BYTES + TC_B_STAGES * TC_B_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-
-struct LinTcParams {
-  const float* A[3];
-  int lda[3];
-  int ka[3];
-  int aswish[3];
-  int nseg;
-  const float* Bimg;
-  const float* bias;
-  const float* side;
-  int lds;
-  int r;
-  const float* Wside;
-  int ldws;
-  const float* Zmul;
-  int ldz;
-  float* Ypre;
-  int ldpre;
-  int act;
-  const float* R;
-  int ldr;
-  float* Y;
-  int ldy;
-  int M;
-  int Nout;
-};
-
-// ---- epilogue of one 32-row x 32-column accumulator block --------------------------------------------------------------
-// tcgen05.ld hands every thread 32 consecutive columns of ONE row; reading / writing global memory in that shape makes
-// each warp instruction touch 32 different rows 16 bytes at a time (32 sectors per request, half of every written sector
-// unused: ncu of the first role-split kernel).  The block therefore goes through a warp-private shared-memory tile in two
-// [32 rows x 16 columns] halves (pitch 20 floats; the (row, row + 4) pairing keeps every quarter-warp access conflict
-// free) so that a warp instruction covers 8 rows x 64 contiguous bytes: every sector fully used, 16 sectors per request,
-// and bias / side weights are per-thread constants of a half block.  Same arithmetic per output element as before.
-constexpr int EPI_TILE_FLOATS = 32 * 20;
-
-// FAST (reduced-precision mode): operands rounded to tf32 once, ONE MMA pass (hi x hi): no lo images are written, only
-// the hi half of every weight chunk is copied (16 instead of 32 KiB from L2) and 4 instead of 12 MMAs run per chunk.
-// Error of a K = 256 product: ~3e-4 of max|ref| (tf32 keeps 10 mantissa bits, three more than bf16).
-__device__ __forceinline__ void store_hi4(uint8_t* hi_img, uint32_t off, float4 v) {
-  float4 h;
-  float l;
-  split_tf32(v.x, h.x, l);
-  split_tf32(v.y, h.y, l);
-  split_tf32(v.z, h.z, l);
-  split_tf32(v.w, h.w, l);
-  *reinterpret_cast<float4*>(hi_img + off) = h;
-}
-
-__device__ __forceinline__ float4 dswish4(float4 z) { return make_float4(dswish(z.x), dswish(z.y), dswish(z.z), dswish(z.w)); }
-
-__device__ __forceinline__ void lin_epilogue32(const LinTcParams& p, float* tb, const float (&v)[32], int row_base,
-                                               int colb, int lane) {
-  const int c = lane & 3, rl0 = (lane >> 3) + 4 * ((lane >> 2) & 1);
-#pragma unroll
-  for (int hb = 0; hb < 32; hb += 16) {
-    __syncwarp();
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-      st4(tb + lane * 20 + 4 * j, make_float4(v[hb + 4 * j], v[hb + 4 * j + 1], v[hb + 4 * j + 2], v[hb + 4 * j + 3]));
-    __syncwarp();
-    const int col = colb + hb + 4 * c;
-    if (col >= p.Nout) continue;
-    const float4 b4 = p.bias ? ldg4(p.bias + col) : zero4();
-    float4 zm[4], rr[4];
-    if (p.Zmul) {
-#pragma unroll
-      for (int ps = 0; ps < 4; ++ps) {
-        const int row = row_base + 8 * ps + rl0;
-        zm[ps] = row < p.M ? ldg4(p.Zmul + (size_t)row * p.ldz + col) : zero4();
-      }
-    }
-    if (p.R) {
-#pragma unroll
-      for (int ps = 0; ps < 4; ++ps) {
-        const int row = row_base + 8 * ps + rl0;
-        rr[ps] = row < p.M ? ldg4(p.R + (size_t)row * p.ldr + col) : zero4();
-      }
-    }
-#pragma unroll
-    for (int ps = 0; ps < 4; ++ps) {
-      const int rl = 8 * ps + rl0;
-      const int row = row_base + rl;
-      if (row >= p.M) continue;
-      float4 z = *reinterpret_cast<const float4*>(tb + rl * 20 + 4 * c);
-      if (p.bias) z = add4(z, b4);
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        if (q >= p.r) break;
-        const float sv = __ldg(p.side + (size_t)row * p.lds + q);
-        const float4 w = ldg4(p.Wside + (size_t)q * p.ldws + col);
-        z.x = fmaf(sv, w.x, z.x);
-        z.y = fmaf(sv, w.y, z.y);
-        z.z = fmaf(sv, w.z, z.z);
-        z.w = fmaf(sv, w.w, z.w);
-      }
-      if (p.Zmul) z = mul4(z, dswish4(zm[ps]));
-      if (p.Ypre) st4(p.Ypre + (size_t)row * p.ldpre + col, z);
-      if (p.act) z = swish4(z);
-      if (p.R) z = add4(z, rr[ps]);
-      st4(p.Y + (size_t)row * p.ldy + col, z);
-    }
-  }
-}
 
 template <bool FAST>
 __global__ void __launch_bounds__(256, 1) k_linear_tc(const LinTcParams p) {
@@ -488,6 +383,8 @@ __global__ void __launch_bounds__(LW_THREADS, 1) k_linear_ws(const LinTcParams p
   if (warp == LW_MMA_WARP) tmem_dealloc(tmem, 256);
 }
 
+int launch_linear_tma(const LinTcParams& p, int mode, int grid, cudaStream_t stream);      // linear_tma.cu
+
 }  // namespace msmp
 
 using namespace msmp;
@@ -531,6 +428,9 @@ extern "C" int msmp_linear_tc_fwd(const float* const* A, const int* lda, const i
   static const int sms = [] { int d = 0, n = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); return n; }();
   const int ntiles = (int)(grid.x * grid.y);
   if (ws_min_tiles > 0 && ntiles >= ws_min_tiles) {
+    // A operand by tensor-map TMA (linear_tma.cu); falls back to the register-staged kernel when a map cannot be made
+    const int rc = launch_linear_tma(p, mode, ntiles < sms ? ntiles : sms, stream);
+    if (rc <= 0) return rc;
     if (mode)
       k_linear_ws<true><<<ntiles < sms ? ntiles : sms, LW_THREADS, LW_SMEM, stream>>>(p);
     else
