@@ -19,7 +19,7 @@ import torch
 
 from . import optim as moptim
 from .models_gnn import MP_PDE_SolverLEMLinGatedSave
-from .train_step import GraphedTrainStep
+from .train_step import GraphedForward, GraphedTrainStep
 
 
 def reset_state_bool(model) -> bool:
@@ -92,6 +92,27 @@ def training_loop(model: torch.nn.Module, unrolling: list, batch_size: int, opti
     return torch.stack(losses)
 
 
+# Evaluation rollouts replay the forward pass as a CUDA graph (one replay per window); "0" keeps eager launches.
+EVAL_GRAPH = True
+
+
+def _forward(model, graph):
+    """``model(graph)`` under no_grad -- as a CUDA-graph replay when the graph lives on a CUDA device and the model keeps no
+    state between calls (the stateful LEMS variants run eagerly).  One captured forward per topology is cached on the
+    model; a graph with another topology or other field shapes gets its own."""
+    if not (EVAL_GRAPH and graph.x.is_cuda and not reset_state_bool(model) and not torch.is_grad_enabled()):
+        return model(graph)
+    cache = model.__dict__.setdefault("_msmp_graphed_forwards", [])
+    for gf in cache:
+        if gf.matches(graph):
+            return gf(graph)
+    if len(cache) >= 4:
+        cache.pop(0)
+    gf = GraphedForward(model, graph)
+    cache.append(gf)
+    return gf(graph)
+
+
 def test_timestep_losses(model, steps: list, batch_size: int, loader, graph_creator, criterion, device="cpu") -> None:
     """Loss of one forward pass at the time points that are multiples of the time window
     (experiments/train_helper.py:150-203); prints like the reference, returns None."""
@@ -107,7 +128,7 @@ def test_timestep_losses(model, steps: list, batch_size: int, loader, graph_crea
                 same_steps = [step] * batch_size
                 data, labels = graph_creator.create_data(u_super, same_steps)
                 graph = graph_creator.create_graph(data, labels, x, variables, same_steps).to(device)
-                pred = model(graph)
+                pred = _forward(model, graph)
                 losses.append(criterion(pred, graph.y) / batch_size)
             if reset_state_bool(model):
                 model.embedding_lem.reset_states()
@@ -130,14 +151,14 @@ def test_unrolled_losses(model, steps: list, batch_size: int, nr_gt_steps: int, 
             same_steps = [tw * nr_gt_steps] * batch_size
             data, labels = graph_creator.create_data(u_super, same_steps)
             graph = graph_creator.create_graph(data, labels, x, variables, same_steps).to(device)
-            pred = model(graph)
+            pred = _forward(model, graph)
             losses_tmp.append(criterion(pred, graph.y) / nx_base_resolution / batch_size)
             # unroll the trajectory; every window adds its loss
             for step in range(tw * (nr_gt_steps + 1), graph_creator.t_res - tw + 1, tw):
                 same_steps = [step] * batch_size
                 _, labels = graph_creator.create_data(u_super, same_steps)
                 graph = graph_creator.create_next_graph(graph, pred, labels, same_steps).to(device)
-                pred = model(graph)
+                pred = _forward(model, graph)
                 losses_tmp.append(criterion(pred, graph.y) / nx_base_resolution / batch_size)
             if reset_state_bool(model):
                 model.embedding_lem.reset_states()
@@ -203,14 +224,14 @@ def compute_L2_norms(model, batch_size: int, nr_gt_steps: int, loader, graph_cre
             steps = [tw * nr_gt_steps] * bs
             data, labels = graph_creator.create_data(u_super, steps)
             graph = graph_creator.create_graph(data, labels, x, variables, steps).to(device)
-            pred = model(graph)
+            pred = _forward(model, graph)
             err_w.append(fields(torch.square(pred - graph.y)))
             ref_w.append(fields(torch.square(graph.y)))
             for step in range(tw * (nr_gt_steps + 1), graph_creator.t_res - tw + 1, tw):
                 steps = [step] * bs
                 _, labels = graph_creator.create_data(u_super, steps)
                 graph = graph_creator.create_next_graph(graph, pred, labels, steps).to(device)
-                pred = model(graph)
+                pred = _forward(model, graph)
                 err_w.append(fields(torch.square(pred - graph.y)))
                 ref_w.append(fields(torch.square(graph.y)))
             if reset_state_bool(model):

@@ -170,3 +170,51 @@ def test_l2_norm_helpers_match_reference_functions():
     a, r = compute_space_L2_norms(losses, norms)
     np.testing.assert_allclose(a.numpy(), g["space"], rtol=1e-13)
     np.testing.assert_allclose(r.numpy(), g["space_rel"], rtol=1e-13)
+
+
+def test_custom_ops_are_registered_with_fake_implementations():
+    """torch.ops.msmp.* exist after importing torch_ops, trace with fake tensors (shape inference without a GPU) and have
+    no CPU kernels (a CPU tensor fails in the dispatcher: no fallback)."""
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    from msmp_pde_b200 import torch_ops
+    for name in torch_ops.names():
+        assert hasattr(torch.ops.msmp, name), name
+    with FakeTensorMode():
+        src = torch.empty(10, 128, device="cuda")
+        ptr = torch.empty(5, dtype=torch.int32, device="cuda")
+        assert tuple(torch.ops.msmp.scatter_mean(src, ptr, None, True).shape) == (4, 128)
+        x, w = torch.empty(7, 64, device="cuda"), torch.empty(128, 64, device="cuda")
+        assert tuple(torch.ops.msmp.linear(x, w, None, True).shape) == (7, 128)
+        dW, db = torch.ops.msmp.linear_wgrad(x, torch.empty(7, 128, device="cuda"))
+        assert tuple(dW.shape) == (128, 64) and tuple(db.shape) == (128,)
+    with pytest.raises(NotImplementedError):
+        torch.ops.msmp.linear(torch.zeros(4, 32), torch.zeros(128, 32), None, False)
+
+
+def test_install_routes_train_helper_and_lem_cuda():
+    """install() puts this package's loops at experiments.train_helper (train.py:21 star-imports it) and the lem_cuda shim
+    at the name the reference's LEMFunction imports (models_gnn.py:287-302)."""
+    import sys
+    import msmp_pde_b200
+    keep = ("experiments", "torch_geometric", "torch_cluster", "torch_scatter", "lem_cuda")
+    saved = {k: v for k, v in sys.modules.items() if k.startswith(keep)}
+    try:
+        sys.modules.pop("lem_cuda", None)
+        msmp_pde_b200.install()
+        import lem_cuda
+        from msmp_pde_b200.compat import lem_cuda as shim
+        assert lem_cuda is shim and callable(lem_cuda.forward) and callable(lem_cuda.backward)
+        from experiments.train_helper import training_loop, test_unrolled_losses, compute_L2_norms, unflatten_u  # noqa: F401
+        from msmp_pde_b200 import train_helper as ours
+        assert training_loop.__doc__ == ours.training_loop.__doc__
+
+        class NotAGnn:
+            def __repr__(self):
+                return "CNN"
+        with pytest.raises((NotImplementedError, TypeError, AttributeError)):
+            training_loop(NotAGnn(), [0], 1, None, [], None, None)       # not routed to the GNN loop
+    finally:
+        for k in [k for k in sys.modules if k.startswith(keep)]:
+            if k not in saved:
+                del sys.modules[k]
+        sys.modules.update(saved)
