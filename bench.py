@@ -131,6 +131,26 @@ def _time_step(step, flush, K, graph, read_loss):
     return [s.elapsed_time(e) for s, e in evs]
 
 
+def _time_e2e(step, flush, K, host_graph):
+    """End to end through the public API with a prefetching loader: every step's inputs are copied from pinned host memory
+    (step.prefetch, on a copy stream: the copy of step k+1 overlaps the compute of step k) and every step's loss is read
+    back.  K steps are timed as ONE region (first copy issued inside it, last loss read inside it): ms per step."""
+    import torch
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    step.prefetch(host_graph)
+    for k in range(K):
+        flush.zero_()
+        loss = step(None)               # waits for the staged inputs, D2D into the static buffers, replays
+        if k + 1 < K:
+            step.prefetch(host_graph)   # next step's H2D copies, behind this step's kernels on the copy stream
+        loss.item()
+    e.record()
+    torch.cuda.synchronize()
+    return [s.elapsed_time(e) / K]
+
+
 def _sub_config(name, B, dev, flush, steps, precision=None):
     """ms/step of another BASELINE config on this GPU (captured step, inputs resident) -- a sub-record, not the headline."""
     import torch
@@ -178,13 +198,15 @@ def _layer_c5(n_nodes, degree, topology, dev, reps=5):
     for _ in range(3):
         step()
     torch.cuda.synchronize()
-    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s.record()
+    ts = []
     for _ in range(reps):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
         step()
-    e.record()
-    torch.cuda.synchronize()
-    ms = s.elapsed_time(e) / reps
+        e.record()
+        torch.cuda.synchronize()
+        ts.append(s.elapsed_time(e))
+    ms = sorted(ts)[len(ts) // 2]
     E = n_nodes * degree
     alg = 3.0 * (E * (2 * 283 * 128 + 2 * 128 * 128) + n_nodes * (2 * 257 * 128 + 2 * 128 * 128))
     del layer, x, t, g
@@ -291,7 +313,12 @@ def run_ours(args):
     for _ in range(max(3, args.warmup)):
         step(None)
     barrier()
-    # ---- per-op CUDA events (roofline) need eager launches: one short eager pass, not part of `value`
+    # ---- per-op CUDA events (roofline) need eager launches: one short eager pass, not part of `value`.  The pass runs
+    # with the side streams switched off (ops.SERIALIZE): every kernel has the GPU to itself, so the event pair around an
+    # op is that kernel's own duration (in the replayed step kernels of different streams share the SMs).
+    ops.SERIALIZE = True
+    for _ in range(2):
+        step.eager()
     ops.PROFILE_EVENTS = {}
     ops.LAUNCHES = 0
     eager_ev = []
@@ -310,6 +337,7 @@ def run_ours(args):
         kern[k] = dict(ms=sum(ms_) / 3, n=len(v) / 3, flops=sum(f for _, _, f, _ in v) / 3,
                        bytes=sum(b for _, _, _, b in v) / 3)
     ops.PROFILE_EVENTS = None
+    ops.SERIALIZE = False
     say("eager profiling pass done")
     # ---- device-resident timing (value)
     sampler = ClockSampler(local)
@@ -320,8 +348,9 @@ def run_ours(args):
     # ---- end-to-end timing: host (pinned, float64) inputs -> device every step, loss read back
     for _ in range(2):
         step(pinned)
+    _time_e2e(step, flush, 2, pinned)
     barrier()
-    e2e_times = _time_step(step, flush, args.steps, pinned, True)
+    e2e_times = _time_e2e(step, flush, args.steps, pinned)
     barrier()
     clocks = sampler.stop()
     say("timing done")
@@ -355,11 +384,12 @@ def run_ours(args):
                     "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH.get(dom), "avg_launch_ms": round(d["ms"] / max(d["n"], 1), 5),
                     "share_of_step": round(d["ms"] / sum(v["ms"] for v in kern.values()), 4),
                     "eager_step_ms": round(eager_ms, 4), "peak_source": peaks["source"],
-                    "note": "fp32 mode = tcgen05 kind::tf32, error-compensated 3xTF32: achieved = useful fp32 FLOPs of the op "
-                            "(the 3 MMA passes are not counted) / CUDA-event time of the op in an eagerly launched step; "
-                            "share_of_step = that time / the summed device time of all instrumented ops (`ops`); peak = cuBLAS "
-                            "bf16 sustained (MEASURED_PEAKS.json); the ceiling of a 3xTF32 GEMM is the TF32 rate / 3, see "
-                            "frac_of_3xtf32_ceiling"}
+                    "note": "fp32-parity mode = error-compensated tensor-core products (3 x kind::tf32, or 6 x kind::f16 on bf16 "
+                            "pieces in k_wgrad_ws): achieved = useful fp32 FLOPs of the op (the extra passes are not counted) / "
+                            "CUDA-event time of the op in an eagerly launched, single-stream pass of the same step (every "
+                            "kernel alone on the GPU); share_of_step = that time / the summed time of all instrumented ops "
+                            "(`ops`); peak = cuBLAS bf16 sustained (MEASURED_PEAKS.json); the ceiling of an fp32-parity GEMM "
+                            "is the measured TF32 rate / 3, see frac_of_3xtf32_ceiling"}
             if tf32:
                 roof["tf32_peak_measured"] = tf32
                 roof["frac_of_3xtf32_ceiling"] = round(ach / (tf32["sustained_tflops"] / 3.0), 4)
@@ -409,12 +439,15 @@ def run_ours(args):
     return out
 
 
-KERNEL_OF_OP = {"wgrad_ws": "k_wgrad_ws", "wgrad_tc": "k_wgrad_tc", "linear_tc": "k_linear_tc / k_linear_ws",
+KERNEL_OF_OP = {"wgrad_ws": "k_wgrad_ws", "wgrad_tc": "k_wgrad_tc", "linear_tc": "k_linear_tma (k_linear_tc below 296 tiles)",
                 "edge_ws_fwd": "k_edge_ws<fwd>", "edge_ws_bwd": "k_edge_ws<bwd>", "lem_tc_fwd": "k_lem_fwd_tc",
                 "lem_tc_bwd": "k_lem_bwd_tc", "segment_reduce": "k_segment_reduce"}
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of the headline
-# workload (profiles/r2_*): filled in from the capture of the dominant kernel, None when no capture exists for it.
-NCU_TRAFFIC_BYTES_PER_LAUNCH = {}
+# workload (profiles/r2_full_c4_ncu_raw.csv, `scripts/ncu_step.py c4 8`): k_linear_tma, mean of the ten captured launches
+# (the forward GEMMs of the first layer pairs: 67-139 MB read, 21-86 MB written back before the kernel ends; the
+# algorithmic bytes of the same launches average 4 * M * (K + N) = 184 MB -- outputs still in L2 are not counted by DRAM
+# counters); k_lem_fwd_tc: 0.56 GB read + 10.07 GB written.  None for kernels without a capture.
+NCU_TRAFFIC_BYTES_PER_LAUNCH = {"linear_tc": 145.8e6, "lem_tc_fwd": 10.62e9}
 
 
 def scatter_bandwidth(dev, n_nodes=1 << 20, degree=6, reps=10):

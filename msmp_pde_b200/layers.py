@@ -25,6 +25,8 @@ def _side_stream(cur, device, tag):
     priority and everything else (gate layers) a high one: the dgrad chain is the critical path of the backward pass,
     so when both have thread blocks pending the chain's are scheduled first (GraphedTrainStep also runs its main
     stream at high priority; stream priorities are recorded in captured kernel nodes)."""
+    if ops.SERIALIZE:          # per-kernel timing passes: everything on the caller's stream, one kernel at a time
+        return cur
     key = (device.index, cur.cuda_stream, tag)
     st = _SIDE_STREAMS.get(key)
     if st is None:

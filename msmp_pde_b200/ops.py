@@ -123,6 +123,9 @@ LEM_BWD_SEGMENTS = int(__import__('os').environ.get('MSMP_LEM_BWD_SEGMENTS', 1))
 # gradsink.GradPlan of the backward pass in flight (set by GraphedTrainStep): the backward Functions then leave their
 # weight gradients in the plan's raw buffer and return None for the parameters; None = plain autograd behaviour.
 GRAD_SINK = None
+# bench.py's per-kernel pass: no side streams (layers._side_stream returns the current stream), so that the CUDA events
+# around an op time the kernel alone and not its wait for SMs that another stream's kernels hold
+SERIALIZE = False
 _IMG_CACHE: dict = {}
 
 

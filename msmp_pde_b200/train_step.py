@@ -107,6 +107,7 @@ class GraphedTrainStep:
         self.fields = [k for k in self.static.keys()
                        if torch.is_tensor(getattr(self.static, k)) and getattr(self.static, k).is_floating_point()]
         self.bucket = FlatGradBucket(model.parameters(), extra=2)
+        self._staging, self._have_staged = None, False          # prefetch()
         self.gplan = None          # gradsink.GradPlan, built after the first eager step (the packs exist by then)
         self.use_graph = use_graph
         self.graph = None
@@ -272,9 +273,39 @@ class GraphedTrainStep:
                 raise ValueError(f"graph.{k} has shape {tuple(src.shape)}, the captured step expects {tuple(dst.shape)}")
             dst.copy_(src, non_blocking=True)
 
+    def prefetch(self, graph):
+        """Start copying the NEXT step's inputs (e.g. pinned host tensors) into device-side staging buffers on a copy
+        stream while the current step still runs; the next ``step()`` (called without a graph) moves them into the static
+        buffers with device-to-device copies before it replays.  What a prefetching data loader does for the reference's
+        loop (``graph.to(device)``, experiments/train_helper.py:99)."""
+        self._check_topology(graph)
+        if self._staging is None:
+            self._staging = {k: torch.empty_like(getattr(self.static, k)) for k in self.fields}
+            self._copy_stream = torch.cuda.Stream()
+            self._staged, self._consumed = torch.cuda.Event(), None
+        cs = self._copy_stream
+        if self._consumed is not None:
+            cs.wait_event(self._consumed)          # the previous contents have been moved into the static buffers
+        with torch.cuda.stream(cs):
+            for k in self.fields:
+                src = getattr(graph, k)
+                if src.shape != self._staging[k].shape:
+                    raise ValueError(f"graph.{k} has shape {tuple(src.shape)}, the captured step expects "
+                                     f"{tuple(self._staging[k].shape)}")
+                self._staging[k].copy_(src, non_blocking=True)
+            self._staged.record(cs)
+        self._have_staged = True
+
     def __call__(self, graph=None):
         if graph is not None and graph is not self.static:
             self.load(graph)
+        elif graph is None and self._have_staged:
+            torch.cuda.current_stream().wait_event(self._staged)
+            for k in self.fields:
+                getattr(self.static, k).copy_(self._staging[k], non_blocking=True)
+            self._consumed = torch.cuda.Event()
+            self._consumed.record(torch.cuda.current_stream())
+            self._have_staged = False
         if self.fused is not None and not self.fused.valid():
             raise RuntimeError("GraphedTrainStep: parameter / gradient / optimizer-state storage was replaced after the "
                                "capture (e.g. optimizer.load_state_dict or zero_grad(set_to_none=True)); build a new step")

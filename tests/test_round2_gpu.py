@@ -274,7 +274,7 @@ def test_dp_nccl_step_equals_single_gpu():
 
 
 # ------------------------------------------------------------------------------------------- reduced-precision mode
-BF16_OUT_TOL = 2e-3          # of max|ref|  (measured 3e-4 .. 6e-4 on these fixtures)
+BF16_OUT_TOL = 5e-4          # of max|ref|  (measured 6e-5 .. 7e-5 on these fixtures)
 BF16_GRAD_TOL = 3e-2         # per tensor, of max|ref_t| + 5e-3 of the largest gradient
 
 
@@ -314,3 +314,33 @@ def test_reduced_precision_mode_tolerance(cfg):
     print(f"reduced precision {cfg}: out rel err {e_out:.2e}, worst gradient error / allowance {worst:.3f}")
     assert 1e-5 < e_out < BF16_OUT_TOL
     assert worst <= 1.0
+
+
+def test_prefetched_inputs_equal_direct_load():
+    """GraphedTrainStep.prefetch (copy stream + staging buffers) feeds the same step as passing the graph directly."""
+    from msmp_pde_b200 import models_gnn, synth
+    from msmp_pde_b200.train_step import GraphedTrainStep
+    dev = torch.device("cuda:0")
+    pde, data, meta = synth.config_c1(B=2, nx=40, seed=1)
+    _, data2, _ = synth.config_c1(B=2, nx=40, seed=2)
+    losses = []
+    for mode in ("direct", "prefetch"):
+        torch.manual_seed(0)
+        model = models_gnn.MP_PDE_Solver(pde, 25, 128, 6, {}).to(dev)
+        opt = torch.optim.AdamW(model.parameters(), lr=1e-4)
+        step = GraphedTrainStep(model, opt, data.clone().to(dev), warmup=1, preserve_state=True)
+        pinned = [d.clone().apply(lambda t: t.pin_memory()) for d in (data, data2, data)]
+        out = []
+        if mode == "direct":
+            for g in pinned:
+                out.append(float(step(g)))
+        else:
+            step.prefetch(pinned[0])
+            for i in range(3):
+                loss = step(None)
+                if i + 1 < 3:
+                    step.prefetch(pinned[i + 1])
+                out.append(float(loss))
+        losses.append(out)
+    assert losses[0] == losses[1]
+    assert losses[0][0] != losses[0][1]
