@@ -56,8 +56,39 @@ __device__ __forceinline__ void store_hi4(uint8_t* hi_img, uint32_t off, float4 
 
 __device__ __forceinline__ float4 dswish4(float4 z) { return make_float4(dswish(z.x), dswish(z.y), dswish(z.z), dswish(z.w)); }
 
+// Tile-constant epilogue operands staged in shared memory: the 128 rows' side values [128][8], the side weights of the
+// tile's 128 columns [8][128] and its bias [128].  Read from global memory inside the per-row loop they were 44 % of the
+// kernel's stall samples (ncu source page, round 2: every FMA of the side term waited on an L2 round trip); staged once per
+// tile -- before the wait for the accumulator, so the latency hides behind the main loop -- they are short shared-memory
+// reads.  All pointers null: read global memory (k_linear_ws).
+struct EpiStage {
+  const float* side;
+  const float* ws;
+  const float* bias;
+};
+constexpr int EPI_STAGE_FLOATS = 128 * 8 + 8 * 128 + 128;
+
+// nthreads cooperating threads (index et) fill the stage for the tile at (row0, n0); the caller synchronises them before use
+__device__ __forceinline__ void epi_stage_fill(const LinTcParams& p, float* st, int row0, int n0, int et, int nthreads) {
+  float* s_side = st;
+  float* s_ws = st + 1024;
+  float* s_bias = st + 2048;
+  if (p.r > 0) {                                                  // no side term: the epilogue never reads these two
+    for (int idx = et; idx < 1024; idx += nthreads) {
+      const int row = row0 + (idx >> 3), q = idx & 7;
+      s_side[idx] = (q < p.r && row < p.M) ? __ldg(p.side + (size_t)row * p.lds + q) : 0.f;
+    }
+    for (int idx = et; idx < 128 * p.r; idx += nthreads) {
+      const int q = idx >> 7, col = n0 + (idx & 127);
+      s_ws[idx] = (col < p.Nout) ? __ldg(p.Wside + (size_t)q * p.ldws + col) : 0.f;
+    }
+  }
+  for (int idx = et; idx < 128; idx += nthreads) s_bias[idx] = (p.bias && n0 + idx < p.Nout) ? __ldg(p.bias + n0 + idx) : 0.f;
+}
+
 __device__ __forceinline__ void lin_epilogue32(const LinTcParams& p, float* tb, const float (&v)[32], int row_base,
-                                               int colb, int lane) {
+                                               int colb, int lane, const EpiStage es = EpiStage{nullptr, nullptr, nullptr},
+                                               int row0 = 0, int n0 = 0) {
   const int c = lane & 3, rl0 = (lane >> 3) + 4 * ((lane >> 2) & 1);
 #pragma unroll
   for (int hb = 0; hb < 32; hb += 16) {
@@ -68,7 +99,7 @@ __device__ __forceinline__ void lin_epilogue32(const LinTcParams& p, float* tb, 
     __syncwarp();
     const int col = colb + hb + 4 * c;
     if (col >= p.Nout) continue;
-    const float4 b4 = p.bias ? ldg4(p.bias + col) : zero4();
+    const float4 b4 = es.bias ? *reinterpret_cast<const float4*>(es.bias + (col - n0)) : (p.bias ? ldg4(p.bias + col) : zero4());
     float4 zm[4], rr[4];
     if (p.Zmul) {
 #pragma unroll
@@ -94,8 +125,15 @@ __device__ __forceinline__ void lin_epilogue32(const LinTcParams& p, float* tb, 
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         if (q >= p.r) break;
-        const float sv = __ldg(p.side + (size_t)row * p.lds + q);
-        const float4 w = ldg4(p.Wside + (size_t)q * p.ldws + col);
+        float sv;
+        float4 w;
+        if (es.side) {
+          sv = es.side[(row - row0) * 8 + q];
+          w = *reinterpret_cast<const float4*>(es.ws + q * 128 + (col - n0));
+        } else {
+          sv = __ldg(p.side + (size_t)row * p.lds + q);
+          w = ldg4(p.Wside + (size_t)q * p.ldws + col);
+        }
         z.x = fmaf(sv, w.x, z.x);
         z.y = fmaf(sv, w.y, z.y);
         z.z = fmaf(sv, w.z, z.z);

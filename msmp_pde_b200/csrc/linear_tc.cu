@@ -18,7 +18,8 @@ namespace msmp {
 
 constexpr int TC_A_STAGES = 2;                                // A_hi, A_lo per stage (32 KiB)
 constexpr int TC_B_STAGES = 4;                                // B_hi, B_lo per stage (32 KiB), prefetched ahead
-constexpr int TC_SMEM = TC_A_STAGES * TC_A_BYTES + TC_B_STAGES * TC_B_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int TC_SMEM = TC_A_STAGES * TC_A_BYTES + TC_B_STAGES * TC_B_BYTES + 1024 /*align*/ + 256 /*barriers*/ +
+                        EPI_STAGE_FLOATS * 4 /*side values, side weights, bias of the tile*/;
 
 template <bool FAST>
 __global__ void __launch_bounds__(256, 1) k_linear_tc(const LinTcParams p) {
@@ -40,6 +41,10 @@ __global__ void __launch_bounds__(256, 1) k_linear_tc(const LinTcParams p) {
     for (int s = 0; s < 6; ++s) mbar_init(&bars[s], 1);
     fence_barrier_init();
   }
+  // the epilogue's tile constants (side values, side weights, bias) -> shared memory now: their latency hides behind the
+  // main loop instead of stalling every row of the epilogue
+  float* epi_stage = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
+  epi_stage_fill(p, epi_stage, row0, ntile * 128, tid, 256);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -150,7 +155,8 @@ __global__ void __launch_bounds__(256, 1) k_linear_tc(const LinTcParams p) {
       float v[32];
       __syncwarp();
       tmem_ld32(tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)colbase, v);
-      lin_epilogue32(p, tb, v, row0 + 32 * (warp & 3), n0 + colbase, lane);
+      lin_epilogue32(p, tb, v, row0 + 32 * (warp & 3), n0 + colbase, lane, EpiStage{epi_stage, epi_stage + 1024, epi_stage + 2048},
+                     row0, n0);
     }
   }
   tc_fence_before();

@@ -25,7 +25,7 @@ constexpr int LM_EPI_WARPS = 8, LM_CV_WARPS = 4;
 constexpr int LM_MMA_WARP = LM_EPI_WARPS + LM_CV_WARPS;       // 12; warp 13 = loader
 constexpr int LM_THREADS = 32 * (LM_MMA_WARP + 2);
 constexpr int LM_RING_BYTES = 3 * (TC_A_BYTES + TC_B_BYTES);  // fp32 mode: 3 stages of 64 KiB; reduced precision: 6 of 32 KiB
-constexpr int LM_SMEM = 1024 + LM_RING_BYTES + 512 + LM_EPI_WARPS * EPI_TILE_FLOATS * 4;
+constexpr int LM_SMEM = 1024 + LM_RING_BYTES + 512 + LM_EPI_WARPS * EPI_TILE_FLOATS * 4 + EPI_STAGE_FLOATS * 4;
 constexpr int LM_MAX_STAGES = 6;
 
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
@@ -54,6 +54,7 @@ __global__ void __launch_bounds__(LM_THREADS, 1) k_linear_tma(const LinTcParams 
   uint64_t* acc_empty = acc_full + 2;                // [2] epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
   float* epi_tiles = reinterpret_cast<float*>(smem + LM_RING_BYTES + 512);
+  float* epi_stage = epi_tiles + LM_EPI_WARPS * EPI_TILE_FLOATS;
   const int tid = threadIdx.x, warp = warp_index_uniform(), lane = tid & 31;
 
   int ktot = 0;
@@ -90,6 +91,15 @@ __global__ void __launch_bounds__(LM_THREADS, 1) k_linear_tma(const LinTcParams 
       const int t = blockIdx.x + i * gridDim.x;
       const int row0 = (t / nct) * 128, n0 = (t % nct) * 128;
       const int buf = i & 1;
+      // this tile's side values / side weights / bias -> shared memory, while its MMAs are still running
+      // (launches without a side term keep their epilogue warps independent: the bias alone is a per-thread constant)
+      EpiStage es{nullptr, nullptr, nullptr};
+      if (p.r > 0) {
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * LM_EPI_WARPS) : "memory");        // the previous tile's readers are done
+        epi_stage_fill(p, epi_stage, row0, n0, tid, 32 * LM_EPI_WARPS);
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * LM_EPI_WARPS) : "memory");
+        es = EpiStage{epi_stage, epi_stage + 1024, epi_stage + 2048};
+      }
       mbar_wait_backoff(&acc_full[buf], (i >> 1) & 1);
       tc_fence_after();
       const uint32_t ta = tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(128 * buf + 64 * (warp >> 2));
@@ -103,7 +113,7 @@ __global__ void __launch_bounds__(LM_THREADS, 1) k_linear_tma(const LinTcParams 
           __syncwarp();
           if (lane == 0) mbar_arrive(&acc_empty[buf]);
         }
-        lin_epilogue32(p, tb, v, row0 + 32 * (warp & 3), n0 + 64 * (warp >> 2) + 32 * cb, lane);
+        lin_epilogue32(p, tb, v, row0 + 32 * (warp & 3), n0 + 64 * (warp >> 2) + 32 * cb, lane, es, row0, n0);
       }
     }
   } else if (warp < LM_MMA_WARP) {

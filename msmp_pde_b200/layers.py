@@ -101,6 +101,12 @@ class LayerPack:
         self.W2d = W2.clone()                                          # [n][k]: edge-backward operand
 
 
+def _pack_generation(pk):
+    """Refresh count of the PackPlan a layer pack is a view into (None for packs built per call)."""
+    plan = getattr(pk, "plan", None)
+    return None if plan is None else plan.generation
+
+
 class _Aux:
     """Non-tensor arguments of the layer function."""
     __slots__ = ("topo", "feat", "pack", "final", "gsink")
@@ -127,6 +133,7 @@ class _LayerCoreFn(torch.autograd.Function):
             z4 = None
             y = ops.linear_fwd([z3], pk.W4t, bias=b4, aswish=[1])
         ctx.aux = aux
+        ctx.pack_gen = _pack_generation(pk)
         ctx.save_for_backward(h, PQ, z2, agg, z3, z4, W2, W4)
         return y
 
@@ -135,6 +142,9 @@ class _LayerCoreFn(torch.autograd.Function):
         h, PQ, z2, agg, z3, z4, W2, W4 = ctx.saved_tensors
         aux = ctx.aux
         pk, topo, ft = aux.pack, aux.topo, aux.feat
+        if ctx.pack_gen != _pack_generation(pk):
+            raise RuntimeError("the model's packed weights were refreshed by a later forward pass before this backward pass ran: "
+                               "run forward and backward of a step back to back (or keep one model per concurrent graph)")
         V, F_u, N = ft.V, ft.F_u, ft.N
         dev = h.device
         dy = dy.contiguous()

@@ -36,7 +36,7 @@ _JOB_DTYPE = np.dtype([("src", "<u8"), ("dst", "<u8"), ("ld", "<i4"), ("transpos
 
 class LayerPackTC:
     """Packed weights of one message-passing layer (same attribute names as layers.LayerPack)."""
-    __slots__ = ("Wpq_t", "Wpq_side", "bias_pq", "W2t", "W2d", "W3t", "W3side", "W3hx", "W4t", "W4d", "W1hq")
+    __slots__ = ("Wpq_t", "Wpq_side", "bias_pq", "W2t", "W2d", "W3t", "W3side", "W3hx", "W4t", "W4d", "W1hq", "plan")
 
 
 class LemPackTC:
@@ -48,6 +48,8 @@ class LinearPackTC:
 
 
 class PackPlan:
+    generation = 0
+
     def __init__(self, device):
         assert _JOB_DTYPE.itemsize == lib.msmp_pack_job_bytes(), "PackJob layout mismatch"
         self.device = device
@@ -109,6 +111,7 @@ class PackPlan:
         self._plain(o_bias, S(b1), 1, 1.0, 1, H, 2 * H)
         self._plain(o_w3s, S(W3, 2 * H), K3, 1.0, V, H, H)
         pk = LayerPackTC()
+        pk.plan = self
 
         def late():
             pk.Wpq_t = TcW(self._view(o_pq, 2, nc_pq, 2, IMG), Kp, 2 * H)
@@ -201,7 +204,10 @@ class PackPlan:
         return tuple(p.data_ptr() for p in self.params) == self.ptr_key
 
     def refresh(self) -> None:
-        """Re-pack every weight from the current parameter values (one launch)."""
+        """Re-pack every weight from the current parameter values (one launch).  ``generation`` counts the refreshes: the
+        backward Functions compare it with the value their forward saw (the dgrad operands are views into this one
+        buffer, so a backward that runs after a LATER forward's refresh would mix old activations with new weights)."""
+        self.generation = getattr(self, "generation", 0) + 1
         check(lib.msmp_pack_run(self.jobs_dev.data_ptr(), self.njobs, self.max_chunks,
                                 torch.cuda.current_stream().cuda_stream), "msmp_pack_run")
         from . import ops
