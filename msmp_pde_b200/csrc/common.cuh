@@ -43,6 +43,24 @@ __device__ __forceinline__ float dswish(float x) {
 __device__ __forceinline__ float4 swish4(float4 v) {
   return make_float4(swish(v.x), swish(v.y), swish(v.z), swish(v.w));
 }
+// Activations on the MUFU pipe: sigmoid(x) = rcp(1 + ex2(-x log2 e)), 5 instructions per swish instead of the 13 of
+// the expf-based common.cuh version (the roles of the edge kernel and the converters / epilogues of the node GEMMs are
+// instruction-issue bound).  ex2.approx / rcp.approx are 1-2 ulp; the one extra error, the
+// rounding of x log2 e (6e-8 |x| relative in e^-x), reaches the result scaled by sigmoid (1 - sigmoid) and stays below
+// 1e-7 of the activation: within the fp32 noise of the GEMM next to it (parity tests: tests/test_kernels_gpu.py).
+__device__ __forceinline__ float sigmoid_mufu(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return r;
+}
+__device__ __forceinline__ float swish_m(float x) { return x * sigmoid_mufu(x); }
+__device__ __forceinline__ float dswish_m(float x) {
+  const float sg = sigmoid_mufu(x);
+  return sg * (1.0f + x * (1.0f - sg));
+}
+__device__ __forceinline__ float4 swish4_m(float4 v) { return make_float4(swish_m(v.x), swish_m(v.y), swish_m(v.z), swish_m(v.w)); }
+__device__ __forceinline__ float4 dswish4_m(float4 v) { return make_float4(dswish_m(v.x), dswish_m(v.y), dswish_m(v.z), dswish_m(v.w)); }
 __device__ __forceinline__ float4 add4(float4 a, float4 b) {
   return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
 }

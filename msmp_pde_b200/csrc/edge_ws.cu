@@ -61,22 +61,7 @@ struct EdgeWsParams {
   int E; int T; int N;
 };
 
-// Activations on the MUFU pipe: sigmoid(x) = rcp(1 + ex2(-x log2 e)), 5 instructions per swish instead of the 13 of
-// the expf-based common.cuh version (the two roles of this kernel are instruction-issue bound: ncu shows 58 % issue
-// slots busy with 31 % of the warp slots occupied).  ex2.approx / rcp.approx are 1-2 ulp; the one extra error, the
-// rounding of x log2 e (6e-8 |x| relative in e^-x), reaches the result scaled by sigmoid (1 - sigmoid) and stays below
-// 1e-7 of the activation: within the fp32 noise of the GEMM next to it (parity tests: tests/test_kernels_gpu.py).
-__device__ __forceinline__ float sigmoid_mufu(float x) {
-  float e, r;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
-  return r;
-}
-__device__ __forceinline__ float swish_m(float x) { return x * sigmoid_mufu(x); }
-__device__ __forceinline__ float dswish_m(float x) {
-  const float sg = sigmoid_mufu(x);
-  return sg * (1.0f + x * (1.0f - sg));
-}
+// sigmoid_mufu / swish_m / dswish_m (activations on the MUFU pipe) live in common.cuh
 __device__ __forceinline__ void producer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(EW_PROD_THREADS) : "memory"); }
 
 // -DMSMP_EW_TICKS: CTA 0 prints the cycles each role spent waiting on its barriers (diagnostic builds only)

@@ -30,6 +30,7 @@ struct LinTcParams {
   int ldy;
   int M;
   int Nout;
+  int dbg;              // experiment switches of k_linear_tma (MSMP_LIN_DBG; 0 in production): 1 no epilogue memory traffic, 2 no conversion, 4 no MMAs, 8 no weight copies, 16 no A copies
 };
 
 // ---- epilogue of one 32-row x 32-column accumulator block --------------------------------------------------------------
@@ -86,65 +87,104 @@ __device__ __forceinline__ void epi_stage_fill(const LinTcParams& p, float* st, 
   for (int idx = et; idx < 128; idx += nthreads) s_bias[idx] = (p.bias && n0 + idx < p.Nout) ? __ldg(p.bias + n0 + idx) : 0.f;
 }
 
+// explicit shared-space accesses: through the generic pointers of EpiStage / the tile the compiler emitted generic LD / ST
+// (ncu source page, round 2), and the per-row `continue`s cut the block into 8 reconvergence regions of dependent code:
+// 684 instructions per 32 x 32 block at ~10 cycles each made the EPILOGUE the bound of every large node GEMM
+// (MSMP_LIN_DBG ablation: 0.63 ms per layer with it, 0.29 ms without).  Now: LDS / STS, four independent row streams
+// (predicated accesses instead of branches), addresses formed once per block.
+__device__ __forceinline__ float4 lds4(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ float lds1(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts4(uint32_t a, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// STAGED: side values / side weights / bias come from the EpiStage in shared memory (every kernel but k_linear_ws)
+template <bool STAGED>
 __device__ __forceinline__ void lin_epilogue32(const LinTcParams& p, float* tb, const float (&v)[32], int row_base,
                                                int colb, int lane, const EpiStage es = EpiStage{nullptr, nullptr, nullptr},
                                                int row0 = 0, int n0 = 0) {
   const int c = lane & 3, rl0 = (lane >> 3) + 4 * ((lane >> 2) & 1);
+  const uint32_t tbs = smem_u32(tb);
+  const uint32_t wr = tbs + (uint32_t)lane * 80u;                        // this lane's row of the transposition tile
+  const uint32_t rd = tbs + (uint32_t)rl0 * 80u + (uint32_t)c * 16u;     // (row rl0 + 8 ps, columns 4c..4c+3): + 640 ps
+  const int r0 = row_base + rl0;
+  bool ok[4];
+#pragma unroll
+  for (int ps = 0; ps < 4; ++ps) ok[ps] = r0 + 8 * ps < p.M;
+  constexpr bool staged = STAGED;
+  const bool bias_staged = staged && es.bias != nullptr;      // (launches without a side term do not fill the stage)
+  const uint32_t s_side = bias_staged ? smem_u32(es.side) + (uint32_t)(r0 - row0) * 32u : 0u;
+  const uint32_t s_ws = bias_staged ? smem_u32(es.ws) : 0u, s_bias = bias_staged ? smem_u32(es.bias) : 0u;
+  const bool has_bias = p.bias != nullptr, has_z = p.Zmul != nullptr, has_r = p.R != nullptr, has_pre = p.Ypre != nullptr;
 #pragma unroll
   for (int hb = 0; hb < 32; hb += 16) {
+    if (p.dbg & 128) continue;
     __syncwarp();
 #pragma unroll
     for (int j = 0; j < 4; ++j)
-      st4(tb + lane * 20 + 4 * j, make_float4(v[hb + 4 * j], v[hb + 4 * j + 1], v[hb + 4 * j + 2], v[hb + 4 * j + 3]));
+      sts4(wr + 16 * j, make_float4(v[hb + 4 * j], v[hb + 4 * j + 1], v[hb + 4 * j + 2], v[hb + 4 * j + 3]));
     __syncwarp();
     const int col = colb + hb + 4 * c;
-    if (col >= p.Nout) continue;
-    const float4 b4 = es.bias ? *reinterpret_cast<const float4*>(es.bias + (col - n0)) : (p.bias ? ldg4(p.bias + col) : zero4());
-    float4 zm[4], rr[4];
-    if (p.Zmul) {
+    if (col >= p.Nout || (p.dbg & 1)) continue;
+    float4 zm[4], rr[4], z[4];
+    if (has_z) {
 #pragma unroll
-      for (int ps = 0; ps < 4; ++ps) {
-        const int row = row_base + 8 * ps + rl0;
-        zm[ps] = row < p.M ? ldg4(p.Zmul + (size_t)row * p.ldz + col) : zero4();
-      }
+      for (int ps = 0; ps < 4; ++ps)
+        zm[ps] = (ok[ps] && !(p.dbg & 64)) ? ldg4(p.Zmul + (size_t)(r0 + 8 * ps) * p.ldz + col) : zero4();
     }
-    if (p.R) {
+    if (has_r) {
 #pragma unroll
-      for (int ps = 0; ps < 4; ++ps) {
-        const int row = row_base + 8 * ps + rl0;
-        rr[ps] = row < p.M ? ldg4(p.R + (size_t)row * p.ldr + col) : zero4();
-      }
+      for (int ps = 0; ps < 4; ++ps)
+        rr[ps] = (ok[ps] && !(p.dbg & 64)) ? ldg4(p.R + (size_t)(r0 + 8 * ps) * p.ldr + col) : zero4();
     }
+    const float4 b4 = bias_staged ? lds4(s_bias + (uint32_t)(col - n0) * 4u) : (has_bias ? ldg4(p.bias + col) : zero4());
 #pragma unroll
     for (int ps = 0; ps < 4; ++ps) {
-      const int rl = 8 * ps + rl0;
-      const int row = row_base + rl;
-      if (row >= p.M) continue;
-      float4 z = *reinterpret_cast<const float4*>(tb + rl * 20 + 4 * c);
-      if (p.bias) z = add4(z, b4);
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        if (q >= p.r) break;
-        float sv;
-        float4 w;
-        if (es.side) {
-          sv = es.side[(row - row0) * 8 + q];
-          w = *reinterpret_cast<const float4*>(es.ws + q * 128 + (col - n0));
-        } else {
-          sv = __ldg(p.side + (size_t)row * p.lds + q);
-          w = ldg4(p.Wside + (size_t)q * p.ldws + col);
-        }
-        z.x = fmaf(sv, w.x, z.x);
-        z.y = fmaf(sv, w.y, z.y);
-        z.z = fmaf(sv, w.z, z.z);
-        z.w = fmaf(sv, w.w, z.w);
-      }
-      if (p.Zmul) z = mul4(z, dswish4(zm[ps]));
-      if (p.Ypre) st4(p.Ypre + (size_t)row * p.ldpre + col, z);
-      if (p.act) z = swish4(z);
-      if (p.R) z = add4(z, rr[ps]);
-      st4(p.Y + (size_t)row * p.ldy + col, z);
+      z[ps] = lds4(rd + 640u * ps);
+      if (has_bias) z[ps] = add4(z[ps], b4);
     }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      if (q >= p.r) break;
+      const float4 w = staged ? lds4(s_ws + (uint32_t)(q * 128 + (col - n0)) * 4u) : ldg4(p.Wside + (size_t)q * p.ldws + col);
+#pragma unroll
+      for (int ps = 0; ps < 4; ++ps) {
+        const float sv = staged ? lds1(s_side + (uint32_t)(64 * ps + q) * 4u)
+                                : (ok[ps] ? __ldg(p.side + (size_t)(r0 + 8 * ps) * p.lds + q) : 0.f);
+        z[ps].x = fmaf(sv, w.x, z[ps].x);
+        z[ps].y = fmaf(sv, w.y, z[ps].y);
+        z[ps].z = fmaf(sv, w.z, z[ps].z);
+        z[ps].w = fmaf(sv, w.w, z[ps].w);
+      }
+    }
+    if (has_z) {
+#pragma unroll
+      for (int ps = 0; ps < 4; ++ps) z[ps] = mul4(z[ps], dswish4_m(zm[ps]));
+    }
+    if (has_pre && !(p.dbg & 32)) {
+#pragma unroll
+      for (int ps = 0; ps < 4; ++ps)
+        if (ok[ps]) st4(p.Ypre + (size_t)(r0 + 8 * ps) * p.ldpre + col, z[ps]);
+    }
+    if (p.act) {
+#pragma unroll
+      for (int ps = 0; ps < 4; ++ps) z[ps] = swish4_m(z[ps]);
+    }
+    if (has_r) {
+#pragma unroll
+      for (int ps = 0; ps < 4; ++ps) z[ps] = add4(z[ps], rr[ps]);
+    }
+#pragma unroll
+    for (int ps = 0; ps < 4; ++ps)
+      if (ok[ps] && (!(p.dbg & 32) || z[ps].x == 123.456f)) st4(p.Y + (size_t)(r0 + 8 * ps) * p.ldy + col, z[ps]);
   }
 }
 

@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(256, 1) k_linear_tc(const LinTcParams p) {
     for (int i = 0; i < 4; ++i) {
       const int idx = tid + 256 * i;
       float4 v = pre[i];
-      if (pre_sw) v = swish4(v);
+      if (pre_sw) v = swish4_m(v);
       if (FAST)
         store_hi4(st, img_off(idx >> 3, idx & 7), v);
       else
@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(256, 1) k_linear_tc(const LinTcParams p) {
       float v[32];
       __syncwarp();
       tmem_ld32(tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)colbase, v);
-      lin_epilogue32(p, tb, v, row0 + 32 * (warp & 3), n0 + colbase, lane, EpiStage{epi_stage, epi_stage + 1024, epi_stage + 2048},
+      lin_epilogue32<true>(p, tb, v, row0 + 32 * (warp & 3), n0 + colbase, lane, EpiStage{epi_stage, epi_stage + 1024, epi_stage + 2048},
                      row0, n0);
     }
   }
@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(LW_THREADS, 1) k_linear_ws(const LinTcParams p
           __syncwarp();
           if (lane == 0) mbar_arrive(&acc_empty[buf]);
         }
-        lin_epilogue32(p, tb, v, row0 + 32 * (warp & 3), n0 + 64 * (warp >> 2) + 32 * cb, lane);
+        lin_epilogue32<false>(p, tb, v, row0 + 32 * (warp & 3), n0 + 64 * (warp >> 2) + 32 * cb, lane);
       }
     }
   } else if (warp >= LW_MMA_WARP) {
@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(LW_THREADS, 1) k_linear_ws(const LinTcParams p
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         float4 v = pre[q];
-        if (sw) v = swish4(v);
+        if (sw) v = swish4_m(v);
         if (FAST)
           store_hi4(st, img_off((pt >> 3) + 32 * q, c16), v);
         else
@@ -390,6 +390,7 @@ __global__ void __launch_bounds__(LW_THREADS, 1) k_linear_ws(const LinTcParams p
 }
 
 int launch_linear_tma(const LinTcParams& p, int mode, int grid, cudaStream_t stream);      // linear_tma.cu
+int launch_linear_ts(const LinTcParams& p, int mode, int grid, cudaStream_t stream);       // linear_ts.cu
 
 }  // namespace msmp
 
@@ -435,7 +436,10 @@ extern "C" int msmp_linear_tc_fwd(const float* const* A, const int* lda, const i
   const int ntiles = (int)(grid.x * grid.y);
   if (ws_min_tiles > 0 && ntiles >= ws_min_tiles) {
     // A operand by tensor-map TMA (linear_tma.cu); falls back to the register-staged kernel when a map cannot be made
-    const int rc = launch_linear_tma(p, mode, ntiles < sms ? ntiles : sms, stream);
+    // activation operand in tensor memory (linear_ts.cu), then the shared-memory operand variant (linear_tma.cu)
+    int rc = launch_linear_ts(p, mode, ntiles < sms ? ntiles : sms, stream);
+    if (rc <= 0) return rc;
+    rc = launch_linear_tma(p, mode, ntiles < sms ? ntiles : sms, stream);
     if (rc <= 0) return rc;
     if (mode)
       k_linear_ws<true><<<ntiles < sms ? ntiles : sms, LW_THREADS, LW_SMEM, stream>>>(p);

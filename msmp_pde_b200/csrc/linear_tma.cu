@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(LM_THREADS, 1) k_linear_tma(const LinTcParams 
           __syncwarp();
           if (lane == 0) mbar_arrive(&acc_empty[buf]);
         }
-        lin_epilogue32(p, tb, v, row0 + 32 * (warp & 3), n0 + 64 * (warp >> 2) + 32 * cb, lane, es, row0, n0);
+        lin_epilogue32<true>(p, tb, v, row0 + 32 * (warp & 3), n0 + 64 * (warp >> 2) + 32 * cb, lane, es, row0, n0);
       }
     }
   } else if (warp < LM_MMA_WARP) {
@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(LM_THREADS, 1) k_linear_tma(const LinTcParams 
     for (int w = 0; w < total; ++w) {
       const bool sw = c < k0 ? sw0 : (c - k0 < k1 ? sw1 : sw2);
       mbar_wait_backoff(&ld_full[s], ph);
-      if (!FAST || sw) {
+      if ((!FAST || sw) && !(p.dbg & 2)) {
         while (!mbar_try_wait(&ld_full[s], ph)) {          // every lane observes the TMA completion itself
         }
         uint8_t* a_hi = smem + s * STAGE_BYTES;
@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(LM_THREADS, 1) k_linear_tma(const LinTcParams 
           const int idx = ct + 128 * q;
           const uint32_t off = img_off(idx >> 3, idx & 7);
           float4 v = *reinterpret_cast<const float4*>(a_hi + off);
-          if (sw) v = swish4(v);
+          if (sw) v = swish4_m(v);
           if (FAST) {
             *reinterpret_cast<float4*>(a_hi + off) = v;
           } else {
@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(LM_THREADS, 1) k_linear_tma(const LinTcParams 
         for (int k = 0; k < 4; ++k) {
           const uint64_t dah = umma_desc(a_hi + 32 * k, 16, 1024), dal = umma_desc(a_lo + 32 * k, 16, 1024);
           const uint64_t dbh = umma_desc(b_hi + 32 * k, 16, 1024), dbl = umma_desc(b_lo + 32 * k, 16, 1024);
-          if (leader) {
+          if (leader && !(p.dbg & 4)) {
             umma_tf32(acc, dah, dbh, IDESC, (c | k) ? 1u : 0u);
             if (!FAST) {
               umma_tf32(acc, dal, dbh, IDESC, 1u);
@@ -206,11 +206,11 @@ __global__ void __launch_bounds__(LM_THREADS, 1) k_linear_tma(const LinTcParams 
         for (int c = 0; c < nchunks; ++c, ++n) {
           if (n >= (uint32_t)STAGES) mbar_wait(&empty[s], ph ^ 1);
           uint8_t* st = smem + s * STAGE_BYTES;
-          mbar_expect_tx(&ld_full[s], IMG_BYTES + B_BYTES);
+          mbar_expect_tx(&ld_full[s], ((p.dbg & 16) ? 0 : IMG_BYTES) + ((p.dbg & 8) ? 0 : B_BYTES));
           const CUtensorMap* tmap = c < k0 ? &tm0 : (c - k0 < k1 ? &tm1 : &tm2);
           const int kc = c < k0 ? c : (c - k0 < k1 ? c - k0 : c - k0 - k1);
-          tma_load_2d(st, tmap, 32 * kc, row0, &ld_full[s]);
-          bulk_g2s(st + A_BYTES, bsrc + (size_t)c * (TC_B_BYTES / 4), B_BYTES, &ld_full[s]);
+          if (!(p.dbg & 16)) tma_load_2d(st, tmap, 32 * kc, row0, &ld_full[s]);
+          if (!(p.dbg & 8)) bulk_g2s(st + A_BYTES, bsrc + (size_t)c * (TC_B_BYTES / 4), B_BYTES, &ld_full[s]);
           if (++s == STAGES) {
             s = 0;
             ph ^= 1;
@@ -242,7 +242,7 @@ static EncodeTiledFn encode_tiled() {
 }
 
 // [M x K] fp32 row-major (row stride lda floats) as a 2-D tensor map with a 32-column x 128-row box, 128-byte swizzle
-static bool make_map(CUtensorMap* tm, const float* A, int lda, int K, int M) {
+bool linear_make_map(CUtensorMap* tm, const float* A, int lda, int K, int M) {
   EncodeTiledFn enc = encode_tiled();
   if (!enc) return false;
   if ((reinterpret_cast<uintptr_t>(A) & 15) || (lda & 3)) return false;
@@ -250,19 +250,24 @@ static bool make_map(CUtensorMap* tm, const float* A, int lda, int K, int M) {
   const cuuint64_t gstride[1] = {(cuuint64_t)lda * 4};
   const cuuint32_t box[2] = {32, 128};
   const cuuint32_t estr[2] = {1, 1};
+  static const int promo = [] { const char* e = getenv("MSMP_TMA_PROMO"); return e ? atoi(e) : 128; }();
   return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(A), gdim, gstride, box, estr,
-             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+             promo == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : (promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : (promo == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B)),
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 // Returns MSMP_OK when the launch was made, 1 when this path cannot take the call (the caller falls back to k_linear_ws).
-int launch_linear_tma(const LinTcParams& p, int mode, int grid, cudaStream_t stream) {
+int launch_linear_tma(const LinTcParams& p_in, int mode, int grid, cudaStream_t stream) {
   static const bool enabled = [] { const char* e = getenv("MSMP_LINEAR_TMA"); return !(e && atoi(e) == 0); }();
   if (!enabled) return 1;
+  static const int dbg = [] { const char* e = getenv("MSMP_LIN_DBG"); return e ? atoi(e) : 0; }();
+  LinTcParams p = p_in;
+  p.dbg = dbg;
   alignas(64) CUtensorMap tm[3];
   for (int s = 0; s < 3; ++s) {
     const int q = s < p.nseg ? s : 0;
-    if (!make_map(&tm[s], p.A[q], p.lda[q], p.ka[q], p.M)) return 1;
+    if (!linear_make_map(&tm[s], p.A[q], p.lda[q], p.ka[q], p.M)) return 1;
   }
   static bool attr_set = false;
   if (!attr_set) {

@@ -24,12 +24,13 @@ CALLS = {
 tot = 0.0
 for name, (fn, fl, by) in CALLS.items():
     ts = []
-    for i in range(7):
+    for i in range(int(os.environ.get('BENCH_REPS', 7))):
         flush.zero_()
+        if os.environ.get('BENCH_FLUSH') == 'read': flush.sum()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(); fn(); b.record(); torch.cuda.synchronize()
-        if i >= 2: ts.append(a.elapsed_time(b))
+        if i >= 2 or int(os.environ.get('BENCH_REPS', 7)) < 3: ts.append(a.elapsed_time(b))
     ms = sorted(ts)[len(ts) // 2]
     tot += ms
-    print(json.dumps(dict(op=name, M=M, precision=ops.PRECISION, ms=round(ms, 4), tflops=round(fl / ms / 1e9, 1), gbs=round(by / ms / 1e6, 1))), flush=True)
+    print(f"{name:28s} {ops.PRECISION} M={M} ms={ms:.4f} tflops={fl / ms / 1e9:.1f} gbs={by / ms / 1e6:.1f}", flush=True)
 print("total ms", round(tot, 4))
