@@ -202,6 +202,12 @@ __global__ void __launch_bounds__(256) k_decoder_bwd(const DecBwdParams p) {
   }
 }
 
+// register-tiled kernels of the tw = 25 geometry (decoder_rt.cu)
+int launch_decoder_fwd_rt(const float* h, const float* w1, const float* b1, const float* w2, const float* b2, const float* u,
+                          int ldu, const float* dt, float* za, float* out, int N, int C, cudaStream_t stream);
+int launch_decoder_bwd_rt(const float* dout, const float* h, const float* za, const float* w1, const float* w2,
+                          const float* dt, float* dh, float* part, int N, int C, int* nparts, cudaStream_t stream);
+
 static bool geom_ok(const DecGeom& g) {
   if (g.C < 1 || g.C > 2 || g.K1 < 1 || g.K1 > 16 || g.K2 < 1 || g.K2 > 16 || g.S1 < 1) return false;
   if (g.L1 != (DEC_LIN - g.K1) / g.S1 + 1 || g.L1 > DEC_MAXL1) return false;
@@ -226,6 +232,10 @@ extern "C" int msmp_decoder_fwd(const float* h, const float* w1, const float* b1
   DecGeom g{C, K1, S1, L1, K2, TW};
   if (!geom_ok(g) || N < 0) return MSMP_ERR_ARG;
   if (N == 0) return MSMP_OK;
+  if (K1 == 16 && S1 == 3 && L1 == 38 && K2 == 14 && TW == 25) {
+    const int rc = launch_decoder_fwd_rt(h, w1, b1, w2, b2, u, ldu, dt, za, out, N, C, stream);
+    if (rc <= 0) return rc;
+  }
   DecFwdParams p{h, w1, b1, w2, b2, u, ldu, dt, za, out, N, g};
   const int grid = (N + DEC_NB_F - 1) / DEC_NB_F;
   if (K1 == 16 && S1 == 3 && L1 == 38 && K2 == 14 && TW == 25 && C == 1)
@@ -250,6 +260,16 @@ extern "C" int msmp_decoder_bwd(const float* dout, const float* h, const float* 
     return MSMP_OK;
   }
   if (ws_bytes < msmp_decoder_bwd_workspace(N, C, K1, K2)) return MSMP_ERR_WORKSPACE;
+  if (K1 == 16 && S1 == 3 && L1 == 38 && K2 == 14 && TW == 25) {
+    int nparts = 0;
+    const int rc = launch_decoder_bwd_rt(dout, h, za, w1, w2, dt, dh, reinterpret_cast<float*>(workspace), N, C, &nparts, stream);
+    if (rc < 0) return rc;
+    if (rc == 0) {
+      k_reduce_partials_tall<<<(nW + 31) / 32, 256, 0, stream>>>(reinterpret_cast<float*>(workspace), dW, nW, nparts, (size_t)nW);
+      MSMP_CHECK_LAUNCH();
+      return MSMP_OK;
+    }
+  }
   const int ctas = (N + DEC_NB_B - 1) / DEC_NB_B;
   DecBwdParams p{dout, h, za, w1, w2, dt, dh, reinterpret_cast<float*>(workspace), N, g};
   if (K1 == 16 && S1 == 3 && L1 == 38 && K2 == 14 && TW == 25 && C == 1)

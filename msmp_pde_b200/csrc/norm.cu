@@ -42,14 +42,20 @@ __global__ void __launch_bounds__(256) k_in_chunk_stats(const float* __restrict_
   }
 }
 
-__global__ void __launch_bounds__(128) k_in_finalize(const float* __restrict__ cstat, const int* __restrict__ chunk_begin,
-                                                     const int* __restrict__ chunk_end,
-                                                     const int* __restrict__ graph_chunk_ptr, float* __restrict__ stat,
-                                                     int nchunks, int B, float eps) {
-  const int g = blockIdx.x, c = threadIdx.x;
+// Chan merge of a graph's chunk statistics in a fixed order: 8 slices of 128 threads merge every 8th chunk each (a lattice
+// graph of the C4 batch has 128 chunks: one serial chain of dependent L2 loads took 71 us per launch), then slice 0 merges
+// the 8 partial results in slice order.  With one chunk per graph the result is that chunk's statistics, bit for bit.
+constexpr int IN_FIN_SLICES = 8;
+__global__ void __launch_bounds__(128 * IN_FIN_SLICES) k_in_finalize(const float* __restrict__ cstat,
+                                                                     const int* __restrict__ chunk_begin,
+                                                                     const int* __restrict__ chunk_end,
+                                                                     const int* __restrict__ graph_chunk_ptr,
+                                                                     float* __restrict__ stat, int nchunks, int B, float eps) {
+  __shared__ float sh[IN_FIN_SLICES][3][128];
+  const int g = blockIdx.x, c = threadIdx.x & 127, sl = threadIdx.x >> 7;
   const float* cs = cstat + (size_t)blockIdx.y * nchunks * 256;
   float n = 0.f, mean = 0.f, m2 = 0.f;
-  for (int k = graph_chunk_ptr[g]; k < graph_chunk_ptr[g + 1]; ++k) {
+  for (int k = graph_chunk_ptr[g] + sl; k < graph_chunk_ptr[g + 1]; k += IN_FIN_SLICES) {
     const float nb = (float)(chunk_end[k] - chunk_begin[k]);
     if (nb <= 0.f) continue;
     const float mb = cs[(size_t)k * 256 + c], qb = cs[(size_t)k * 256 + 128 + c];
@@ -59,9 +65,39 @@ __global__ void __launch_bounds__(128) k_in_finalize(const float* __restrict__ c
     m2 += qb + d * d * (n * nb / nt);
     n = nt;
   }
+  sh[sl][0][c] = n;
+  sh[sl][1][c] = mean;
+  sh[sl][2][c] = m2;
+  __syncthreads();
+  if (sl != 0) return;
+  for (int s2 = 1; s2 < IN_FIN_SLICES; ++s2) {
+    const float nb = sh[s2][0][c];
+    if (nb <= 0.f) continue;
+    const float mb = sh[s2][1][c], qb = sh[s2][2][c];
+    const float nt = n + nb;
+    const float d = mb - mean;
+    mean += d * (nb / nt);
+    m2 += qb + d * d * (n * nb / nt);
+    n = nt;
+  }
   float* o = stat + ((size_t)blockIdx.y * B + g) * 256;
   o[c] = mean;
   o[128 + c] = rsqrtf(m2 / fmaxf(n, 1.f) + eps);
+}
+
+// d(out)/d(o_gate), d(out)/d(o_main) for one element of the gated blend
+// (activations on the MUFU pipe, common.cuh: these element-wise kernels were bound by the three expf / divisions per element)
+__device__ __forceinline__ void blend_grads(float dout, float og, float om, float h, float& dog, float& dom, float& dh) {
+  const float t = sigmoid_mufu(og);
+  const float sm = sigmoid_mufu(om);
+  dog = dout * (om * sm - h) * t * (1.f - t);
+  dom = dout * t * (sm * (1.0f + om * (1.0f - sm)));
+  dh = dout * (1.f - t);
+}
+// out = (1 - sigmoid(o_gate)) h + sigmoid(o_gate) swish(o_main)      (models_gnn.py:1365-1368)
+__device__ __forceinline__ float blend_fwd(float og, float om, float h) {
+  const float t = sigmoid_mufu(og);
+  return (1.f - t) * h + t * swish_m(om);
 }
 
 // forward apply. y1/stat1/h only used in gated mode.
@@ -89,23 +125,15 @@ __global__ void __launch_bounds__(256) k_in_apply(const float* __restrict__ y0, 
   float4 r;
   {
     float t;
-    t = sigmoidf_(o.x); r.x = (1.f - t) * hh.x + t * swish(om.x);
-    t = sigmoidf_(o.y); r.y = (1.f - t) * hh.y + t * swish(om.y);
-    t = sigmoidf_(o.z); r.z = (1.f - t) * hh.z + t * swish(om.z);
-    t = sigmoidf_(o.w); r.w = (1.f - t) * hh.w + t * swish(om.w);
+    r.x = blend_fwd(o.x, om.x, hh.x);
+    r.y = blend_fwd(o.y, om.y, hh.y);
+    r.z = blend_fwd(o.z, om.z, hh.z);
+    r.w = blend_fwd(o.w, om.w, hh.w);
   }
   st4(out + (size_t)row * 128 + c4, r);
 }
 
 // ---- backward -------------------------------------------------------------------------------------
-// d(out)/d(o_gate), d(out)/d(o_main) for one element of the gated blend
-__device__ __forceinline__ void blend_grads(float dout, float og, float om, float h, float& dog, float& dom, float& dh) {
-  const float t = sigmoidf_(og);
-  dog = dout * (swish(om) - h) * t * (1.f - t);
-  dom = dout * t * dswish(om);
-  dh = dout * (1.f - t);
-}
-
 // per chunk: part[chunk][q][c], q = 0: sum do0, 1: sum do0*o0, 2: sum do1, 3: sum do1*o1
 __global__ void __launch_bounds__(1024) k_in_bwd_chunk(const float* __restrict__ dout, const float* __restrict__ y0,
                                                        const float* __restrict__ y1, int ld,
@@ -272,10 +300,10 @@ __global__ void __launch_bounds__(1024) k_in_fused_fwd(const float* __restrict__
     const float4 hh = ldg4(h + (size_t)row * 128 + c4);
     float4 r;
     float tt;
-    tt = sigmoidf_(o.x); r.x = (1.f - tt) * hh.x + tt * swish(om.x);
-    tt = sigmoidf_(o.y); r.y = (1.f - tt) * hh.y + tt * swish(om.y);
-    tt = sigmoidf_(o.z); r.z = (1.f - tt) * hh.z + tt * swish(om.z);
-    tt = sigmoidf_(o.w); r.w = (1.f - tt) * hh.w + tt * swish(om.w);
+    r.x = blend_fwd(o.x, om.x, hh.x);
+    r.y = blend_fwd(o.y, om.y, hh.y);
+    r.z = blend_fwd(o.z, om.z, hh.z);
+    r.w = blend_fwd(o.w, om.w, hh.w);
     st4(out + (size_t)row * 128 + c4, r);
   }
 }
@@ -363,7 +391,7 @@ extern "C" int msmp_instnorm_fwd(const float* y0, const float* y1, int ld, const
   const int nt = mode + 1;
   k_in_chunk_stats<<<dim3(nchunks, nt), 256, 0, stream>>>(y0, y1, ld, chunk_begin, chunk_end, cstat, nchunks);
   MSMP_CHECK_LAUNCH();
-  k_in_finalize<<<dim3(B, nt), 128, 0, stream>>>(cstat, chunk_begin, chunk_end, graph_chunk_ptr, stat, nchunks, B, eps);
+  k_in_finalize<<<dim3(B, nt), 128 * IN_FIN_SLICES, 0, stream>>>(cstat, chunk_begin, chunk_end, graph_chunk_ptr, stat, nchunks, B, eps);
   MSMP_CHECK_LAUNCH();
   k_in_apply<<<(N * 32 + 255) / 256, 256, 0, stream>>>(y0, y1, ld, stat, node_graph, h, out, N, B, mode);
   MSMP_CHECK_LAUNCH();

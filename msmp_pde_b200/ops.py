@@ -89,7 +89,7 @@ WGRAD_WS = os.environ.get("MSMP_WGRAD_WS", "1") != "0"
 # ... except for the very tall, narrow products (the LEM weight gradients of the large-graph configs: T x N >= 1 Mi rows,
 # K = 160): there the MMAs of both kernels are bound by the MN-major operand fetch, k_wgrad_ws has no re-read to save and
 # k_wgrad_tc measured faster (3.3 Mi rows x 384: 3.5 against 4.4 ms, profiles/r2_bench_wgrad.jsonl).  fp32 mode only.
-WGRAD_WS_MAX_TALL_ROWS = int(os.environ.get("MSMP_WGRAD_WS_MAX_TALL_ROWS", str(1 << 20)))
+WGRAD_WS_MAX_TALL_ROWS = int(os.environ.get("MSMP_WGRAD_WS_MAX_TALL_ROWS", str(1 << 18)))
 # ... and for small row counts (the reference's 100-node graphs: 6 400 nodes / 37 632 edges per step), where a launch is
 # latency bound either way and the persistent kernel's longer prologue costs more than its single read of the operands
 # saves: C2 step 3.74 ms with k_wgrad_tc against 3.87 ms (C4, 131 072 nodes: 46.9 against 46.0 ms).

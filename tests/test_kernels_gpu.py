@@ -483,3 +483,38 @@ def test_large_graph_layer_forward_backward_properties(dev):
     out3 = layer(x, t["u"], t["pos"], t["variables"], t["edge_index"], t["batch"])
     assert torch.equal(out3, out)
     assert bool(torch.isfinite(g1).all())
+
+
+@pytest.mark.parametrize("C", [1, 2])
+@pytest.mark.parametrize("N", [1, 37, 4100])
+def test_decoder_fwd_bwd_vs_conv1d(dev, C, N):
+    """msmp_decoder_fwd / _bwd on the tw = 25 geometry (register-tiled kernels of decoder_rt.cu: persistent 32-node tiles,
+    ragged last tile) against float64 torch Conv1d -> Swish -> Conv1d (models_gnn.py:208-224,275-279; models_gnn2D.py:382-391,
+    448-458): outputs, dh and all four weight gradients."""
+    from msmp_pde_b200 import ops
+    g = torch.Generator().manual_seed(100 + 7 * C + N)
+    tw = 25
+    h = torch.randn(N, C * 128, generator=g)
+    w1, b1 = torch.randn(8, C, 16, generator=g) / 4, torch.randn(8, generator=g) / 4
+    w2, b2 = torch.randn(C, 8, 14, generator=g) / 6, torch.randn(C, generator=g) / 4
+    u = torch.randn(N, C * tw + 3, generator=g)
+    dt = torch.cumsum(torch.full((tw,), 0.04), 0)
+    dout = torch.randn(N, C * tw, generator=g)
+    geom = (C, 16, 3, 38, 14, tw)
+    # float64 reference
+    hd = h.double().view(N, C, 128).requires_grad_(True)
+    p64 = [t.double().requires_grad_(True) for t in (w1, b1, w2, b2)]
+    za_ref = torch.nn.functional.conv1d(hd, p64[0], p64[1], stride=3)
+    diff = torch.nn.functional.conv1d(za_ref * torch.sigmoid(za_ref), p64[2], p64[3])
+    base = u.double()[:, tw - 1:tw, None].expand(N, 1, tw) if C == 1 else u.double()[:, :C * tw].view(N, C, tw)
+    out_ref = (base + dt.double() * diff).reshape(N, C * tw)
+    out_ref.backward(dout.double())
+    # kernels
+    d = lambda t: t.to(dev).contiguous()
+    out, za = ops.decoder_fwd(d(h), d(w1), d(b1), d(w2), d(b2), d(u), d(dt), geom)
+    dh, dW = ops.decoder_bwd(d(dout), d(h), za, d(w1), d(w2), d(dt), geom)
+    assert rel_err(out, out_ref) < TOL
+    assert rel_err(za, za_ref.reshape(N, 8 * 38)) < TOL
+    assert rel_err(dh, hd.grad.reshape(N, C * 128)) < TOL
+    dW_ref = torch.cat([p.grad.reshape(-1) for p in p64])
+    assert rel_err(dW, dW_ref) < 2 * TOL
