@@ -439,15 +439,17 @@ def run_ours(args):
     return out
 
 
-KERNEL_OF_OP = {"wgrad_ws": "k_wgrad_ws", "wgrad_tc": "k_wgrad_tc", "linear_tc": "k_linear_tma (k_linear_tc below 296 tiles)",
+KERNEL_OF_OP = {"wgrad_ws": "k_wgrad_ws", "wgrad_tc": "k_wgrad_tc (LEM weight gradients, 3.3 Mi rows; edge dW2, 520 Ki rows)",
+                "linear_tc": "k_linear_ts (k_linear_tc below 296 tiles)",
                 "edge_ws_fwd": "k_edge_ws<fwd>", "edge_ws_bwd": "k_edge_ws<bwd>", "lem_tc_fwd": "k_lem_fwd_tc",
                 "lem_tc_bwd": "k_lem_bwd_tc", "segment_reduce": "k_segment_reduce"}
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of the headline
-# workload (profiles/r2_full_c4_ncu_raw.csv, `scripts/ncu_step.py c4 8`): k_linear_tma, mean of the ten captured launches
-# (the forward GEMMs of the first layer pairs: 67-139 MB read, 21-86 MB written back before the kernel ends; the
-# algorithmic bytes of the same launches average 4 * M * (K + N) = 184 MB -- outputs still in L2 are not counted by DRAM
-# counters); k_lem_fwd_tc: 0.56 GB read + 10.07 GB written.  None for kernels without a capture.
-NCU_TRAFFIC_BYTES_PER_LAUNCH = {"linear_tc": 145.8e6, "lem_tc_fwd": 10.62e9}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch (mean over the launches of the op in one step) from the committed
+# ncu pass over the serialised headline step: `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum
+# --clock-control none --profile-from-start off python scripts/ncu_step.py c4 8` -> profiles/r2_launches_c4_step.csv
+# (311 launches).  DRAM counters do not see operands that are still in the 126 MB L2 (the node GEMMs read what the previous
+# launch wrote: 164 MB per launch against 4 M (K + N) = 184 MB of algorithmic bytes).
+NCU_TRAFFIC_BYTES_PER_LAUNCH = {"linear_tc": 163.6e6, "lem_tc_fwd": 10.617e9, "lem_tc_bwd": 18.909e9, "wgrad_tc": 1281.6e6,
+                                "wgrad_ws": 190.6e6, "edge_ws_fwd": 490.5e6, "edge_ws_bwd": 1422.5e6, "segment_reduce": 316.8e6}
 
 
 def scatter_bandwidth(dev, n_nodes=1 << 20, degree=6, reps=10):
