@@ -226,8 +226,5 @@ class MSSMP_PDE_Solver(nn.Module):
         return (1 - scale) * u[:, -1:].expand(-1, self.time_window) + dt * (scale * diff)
 
 
-class MP_PDE_SolverLEMLinGatedGLU(nn.Module):
-    """models_gnn.py:1379-1523 uses hidden_features = 164; the msmp_b200 kernels are specialised for 128."""
-
-    def __init__(self, *a, **k):
-        raise NotImplementedError("MP_PDE_SolverLEMLinGatedGLU (hidden_features=164) is outside the 128-wide hot path")
+# hidden_features = 164: not a multiple of the kernels' 128-channel block -> torch-operator implementation (glu.py)
+from .glu import MP_PDE_SolverLEMLinGatedGLU  # noqa: E402,F401

@@ -188,11 +188,8 @@ class MP_PDE_Solver2DLEMLin(_Solver2F):
     layer_cls, gated, encoder = GNN_Layer, False, "lem"
 
 
-class MP_PDE_Solver2DLEMLinGatedGLU(nn.Module):
-    """models_gnn2D.py:1198-1366 uses hidden_features = 164; the msmp_b200 kernels are specialised for 128."""
-
-    def __init__(self, *a, **k):
-        raise NotImplementedError("MP_PDE_Solver2DLEMLinGatedGLU (hidden_features=164) is outside the 128-wide hot path")
+# hidden_features = 164: not a multiple of the kernels' 128-channel block -> torch-operator implementation (glu.py)
+from .glu import MP_PDE_Solver2DLEMLinGatedGLU  # noqa: E402,F401
 
 
 class G_PDE_Solver2DLEMLinGated(nn.Module):

@@ -248,3 +248,69 @@ class MP_PDE_Solver2DLSTMLin(_Solver2F):
 class MP_PDE_Solver2DLEMLin(_Solver2F):
     """models_gnn2D.py:920-1056"""
     layer_cls, gate, encoder = GNN_Layer, None, "lem"
+
+
+def _glu_decoder(c):
+    """models_gnn.py:1455-1456, models_gnn2D.py:1284-1291: Conv1d(c, 8, 6, stride 2) -> Swish -> Conv1d(8, c, 15) on half a row
+    (82 -> 39 -> 25 for hidden_features = 164)."""
+    return nn.Sequential(nn.Conv1d(c, 8, 6, stride=2), Swish(), nn.Conv1d(8, c, 15, stride=1))
+
+
+class MP_PDE_SolverLEMLinGatedGLU(_Solver1F):
+    """models_gnn.py:1379-1523: hidden_features = 164; two decoders on the two halves of h (gate / diff),
+    out = (1 - scale) u[:, -1] + dt (scale * diff)."""
+
+    def __init__(self, pde, time_window=25, hidden_features=164, hidden_layer=6, eq_variables={}):
+        super().__init__(pde, time_window, hidden_features, hidden_layer, eq_variables)
+        del self.output_mlp
+        self.output_mlp_gate = _glu_decoder(1)
+        self.output_mlp_diff = _glu_decoder(1)
+
+    def forward(self, data):
+        u = data.x
+        pos_x = data.pos[:, 1][:, None] / self.pde.L
+        pos_t = data.pos[:, 0][:, None] / self.pde.tmax
+        variables = variables_1field(data, pos_t, self.eq_variables)
+        seq = torch.stack([torch.cat((pos_x, u[:, t:t + 1], variables), -1) for t in range(u.shape[1])])
+        h = self.lemoutput_mlp(self.embedding_lem(seq))
+        h = self._process(h, u, pos_x, variables, data.edge_index, data.batch)
+        half = h.size(1) // 2
+        scale = self.output_mlp_gate(h[:, :half][:, None]).squeeze(1)
+        diff = self.output_mlp_diff(h[:, half:][:, None]).squeeze(1)
+        dt = torch.cumsum(torch.ones(1, self.time_window, dtype=h.dtype, device=h.device) * self.pde.dt, dim=1)
+        return (1 - scale) * u[:, -1].repeat(self.time_window, 1).transpose(0, 1) + dt * (scale * diff)
+
+
+class MP_PDE_Solver2DLEMLinGatedGLU(_Solver2F):
+    """models_gnn2D.py:1198-1366: hidden_features = 164; double_mlp -> [N, 2, 164]; the gate decoder reads the first half of
+    every field's row, the diff decoder the second half; out = (1 - scale) u + dt scale diff."""
+
+    def __init__(self, pde, time_window=25, hidden_features=164, hidden_layer=6, eq_variables={}, save_state=None):
+        super().__init__(pde, time_window, hidden_features, hidden_layer, eq_variables, save_state)
+        del self.output_mlp
+        if time_window == 25:          # (the reference defines no decoder for 50: models_gnn2D.py:1283-1292)
+            self.output_mlp_diff = _glu_decoder(2)
+            self.output_mlp_gate = _glu_decoder(2)
+
+    def forward(self, data):
+        tw = self.time_window
+        u = data.x
+        pos_x = data.pos[:, 1][:, None] / self.pde.L
+        pos_t = data.pos[:, 0][:, None] / self.pde.tmax
+        variables = pos_t
+        if "a" in self.eq_variables:
+            variables = torch.cat((variables, data.a / self.eq_variables["a"]), -1)
+        if "b" in self.eq_variables:      # sic: data.a (models_gnn2D.py:1326)
+            variables = torch.cat((variables, data.a / self.eq_variables["b"]), -1)
+        dt = torch.cumsum(torch.ones(1, 1, tw, dtype=u.dtype, device=u.device) * self.pde.dt, dim=2)
+        ts = (dt + pos_t).squeeze(0)
+        seq = torch.stack([
+            torch.cat((pos_x, u[:, t:t + 1], u[:, t + tw:t + tw + 1], ts[:, t:t + 1], variables[:, 1:]), -1)
+            for t in range(tw)])
+        h = self.lemoutput_mlp(self.embedding_lem(seq))
+        h = self._process(h, u, pos_x, variables, data.edge_index, data.batch)
+        h = self.double_mlp(h)
+        half = h.size(2) // 2
+        diff = self.output_mlp_diff(h[:, :, half:])
+        scale = self.output_mlp_gate(h[:, :, :half])
+        return torch.flatten((1 - scale) * unflatten_u(u, tw) + dt * scale * diff, 1, 2)

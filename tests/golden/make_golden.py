@@ -159,8 +159,9 @@ def model_case(cls, cfg_fn, cfg_kwargs, fname, extra_params=None, model_kwargs=N
             vals = 0.2 + torch.rand(B, generator=g, dtype=torch.float64)
             setattr(data, k, vals.repeat_interleave(meta["nx"])[:, None])
     eq = meta["eq_variables"] if extra_params is None else extra_params
-    model = cls(pde, time_window=meta["tw"], hidden_features=128, hidden_layer=6, eq_variables=eq,
-                **(model_kwargs or {}))
+    mk = dict(hidden_features=128)
+    mk.update(model_kwargs or {})
+    model = cls(pde, time_window=meta["tw"], hidden_layer=6, eq_variables=eq, **mk)
     formula_weights_(model)
     out = model(data)
     loss = torch.sqrt(torch.nn.functional.mse_loss(out, data.y, reduction="sum"))   # train_helper.py:126,138
@@ -300,8 +301,29 @@ def time_window_cases(mg, mg2):
                "tw50_MP_PDE_Solver2DLEMLinGated.npz")
 
 
+def glu_cases(mg, mg2):
+    """The two GLU variants at their own width (hidden_features = 164: models_gnn.py:1379-1523, models_gnn2D.py:1198-1366)."""
+    model_case(mg.MP_PDE_SolverLEMLinGatedGLU, synth.config_c1, dict(B=2, nx=30, seed=60), "var_MP_PDE_SolverLEMLinGatedGLU.npz",
+               extra_params={"alpha": 3.0}, model_kwargs=dict(hidden_features=164))
+    model_case(mg2.MP_PDE_Solver2DLEMLinGatedGLU, synth.config_c2, dict(B=2, nx=30, seed=61),
+               "var_MP_PDE_Solver2DLEMLinGatedGLU.npz", model_kwargs=dict(hidden_features=164))
+    import json
+    pde1, _, m1 = synth.config_c1(B=1, nx=10)
+    pde2, _, m2 = synth.config_c2(B=1, nx=10)
+    path = os.path.join(os.path.dirname(__file__), "state_dict_tables.json")
+    tables = json.load(open(path))
+    for name, model in {"MP_PDE_SolverLEMLinGatedGLU": mg.MP_PDE_SolverLEMLinGatedGLU(pde1, 25, 164, 6, {}),
+                        "MP_PDE_Solver2DLEMLinGatedGLU": mg2.MP_PDE_Solver2DLEMLinGatedGLU(pde2, 25, 164, 6, {"a": 1.0, "b": 1.0})}.items():
+        tables[name] = {k: list(v.shape) for k, v in model.state_dict().items()}
+    with open(path, "w") as f:
+        json.dump(tables, f, indent=0, sort_keys=True)
+
+
 def main():
     mg, mg2 = _load_reference()
+    if "--glu-only" in sys.argv:
+        glu_cases(mg, mg2)
+        return
     if "--l2-only" in sys.argv:
         l2_norms_case(mg2)
         return
@@ -344,6 +366,7 @@ def main():
     with open(os.path.join(os.path.dirname(__file__), "state_dict_tables.json"), "w") as f:
         json.dump(tables, f, indent=0, sort_keys=True)
     print({k: len(v) for k, v in tables.items()})
+    glu_cases(mg, mg2)
 
 
 if __name__ == "__main__":

@@ -136,10 +136,11 @@ def test_drop_in_state_dict_layout_matches_reference_tables():
         tables = json.load(f)
     pde1, pde2 = config_c1(B=1, nx=10)[0], config_c2(B=1, nx=10)[0]
     for name, want in tables.items():
+        H = 164 if name.endswith("GLU") else 128          # the GLU variants' own width (torch-operator classes, glu.py)
         if hasattr(models_gnn, name):
-            m = getattr(models_gnn, name)(pde1, 25, 128, 6, {})
+            m = getattr(models_gnn, name)(pde1, 25, H, 6, {})
         else:
-            m = getattr(models_gnn2D, name)(pde2, 25, 128, 6, {"a": 1.0, "b": 1.0})
+            m = getattr(models_gnn2D, name)(pde2, 25, H, 6, {"a": 1.0, "b": 1.0})
         got = {k: list(v.shape) for k, v in m.state_dict().items()}
         assert got == want, name
         assert repr(m) == "GNN"
@@ -147,13 +148,11 @@ def test_drop_in_state_dict_layout_matches_reference_tables():
 
 def test_unsupported_variants_fail_loudly():
     import pytest
-    from msmp_pde_b200 import models_gnn, models_gnn2D
+    from msmp_pde_b200 import models_gnn2D
     from msmp_pde_b200.synth import config_c1
     pde = config_c1(B=1, nx=10)[0]
-    for cls in (models_gnn.MP_PDE_SolverLEMLinGatedGLU, models_gnn2D.MP_PDE_Solver2DLEMLinGatedGLU,
-                models_gnn2D.G_PDE_Solver2DLEMLinGated):
-        with pytest.raises(NotImplementedError):
-            cls(pde, 25, 164, 6, {})
+    with pytest.raises(NotImplementedError):
+        models_gnn2D.G_PDE_Solver2DLEMLinGated(pde, 25, 164, 6, {})
 
 
 def test_l2_norm_helpers_match_reference_functions():
@@ -218,3 +217,31 @@ def test_install_routes_train_helper_and_lem_cuda():
             if k not in saved:
                 del sys.modules[k]
         sys.modules.update(saved)
+
+
+@pytest.mark.parametrize("name", ["MP_PDE_SolverLEMLinGatedGLU", "MP_PDE_Solver2DLEMLinGatedGLU"])
+def test_glu_variants_match_reference_fixtures(name):
+    """The GLU variants (hidden_features = 164; torch-operator classes of msmp_pde_b200/glu.py, no CUDA kernels) in float64
+    against the outputs, loss and gradient digests written from the reference's own classes (make_golden.py --glu-only)."""
+    import torch
+    from msmp_pde_b200 import models_gnn, models_gnn2D
+    from tests import golden_io
+    from tests.test_oracle_golden import _check_digests, variant_eq
+    from tests.util import formula_weights_, rel_err
+    prev = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)
+    try:
+        g = golden_io.load(f"var_{name}.npz")
+        pde_name, eq = variant_eq(name)
+        pde, data = golden_io.model_inputs(g, pde_name)
+        cls = getattr(models_gnn, name, None) or getattr(models_gnn2D, name)
+        model = cls(pde, time_window=25, hidden_features=164, hidden_layer=6, eq_variables=eq)
+        formula_weights_(model)
+        out = model(data)
+        loss = torch.sqrt(torch.nn.functional.mse_loss(out, data.y, reduction="sum"))
+        loss.backward()
+        assert rel_err(out, torch.from_numpy(g["out"])) < 1e-10
+        assert abs(float(loss) - float(g["loss"])) < 1e-9 * float(g["loss"])
+        _check_digests(model, g)
+    finally:
+        torch.set_default_dtype(prev)

@@ -103,7 +103,7 @@ def test_model_vs_golden_and_oracle(mod, cls, fname, pde_name, eq):
     assert errs[worst] <= 1.0, (worst, errs[worst])
 
 
-from tests.test_oracle_golden import VARIANTS_1F, VARIANTS_2F, variant_eq  # noqa: E402
+from tests.test_oracle_golden import GLU_1F, GLU_2F, VARIANTS_1F, VARIANTS_2F, variant_eq, variant_hidden  # noqa: E402
 
 
 # Two variants are ill-conditioned on their fixture: an honest fp32 torch evaluation of the oracle graph itself
@@ -112,10 +112,11 @@ from tests.test_oracle_golden import VARIANTS_1F, VARIANTS_2F, variant_eq  # noq
 VARIANT_FLOOR = {"MP_PDE_SolverGated": 2.0, "MP_PDE_Solver2DLEMLinG2": 8.0}
 
 
-@pytest.mark.parametrize("name", VARIANTS_1F + VARIANTS_2F)
+@pytest.mark.parametrize("name", VARIANTS_1F + VARIANTS_2F + [GLU_1F, GLU_2F])
 def test_variant_vs_golden_and_oracle(name):
     """The reference's other solver classes (same layers, different encoder / gate) against their fixtures and
-    the oracle's full gradients."""
+    the oracle's full gradients.  (The two GLU classes, hidden_features = 164, are torch-operator classes -- glu.py --
+    and run in the parameters' own dtype.)"""
     from msmp_pde_b200 import models_gnn, models_gnn2D
     from oracle import variants as ov
     dev = torch.device("cuda:0")
@@ -123,8 +124,8 @@ def test_variant_vs_golden_and_oracle(name):
     pde_name, eq = variant_eq(name)
     pde, data = golden_io.model_inputs(g, pde_name)
     torch.set_default_dtype(torch.float64)
-    cls = getattr(models_gnn if name in VARIANTS_1F else models_gnn2D, name)
-    model = cls(pde, time_window=25, hidden_features=128, hidden_layer=6, eq_variables=eq)
+    cls = getattr(models_gnn if (name in VARIANTS_1F or name == GLU_1F) else models_gnn2D, name)
+    model = cls(pde, time_window=25, hidden_features=variant_hidden(name), hidden_layer=6, eq_variables=eq)
     formula_weights_(model)
     model = model.to(dev)
     dd = copy.copy(data).clone().to(dev)
@@ -137,7 +138,7 @@ def test_variant_vs_golden_and_oracle(name):
     if "out2" in g:
         with torch.no_grad():
             assert rel_err(model(dd), torch.from_numpy(g["out2"])) < OUT_TOL
-    ref = getattr(ov, name)(pde, time_window=25, hidden_features=128, hidden_layer=6, eq_variables=eq)
+    ref = getattr(ov, name)(pde, time_window=25, hidden_features=variant_hidden(name), hidden_layer=6, eq_variables=eq)
     formula_weights_(ref)
     outr = ref(data)
     torch.sqrt(torch.nn.functional.mse_loss(outr, data.y, reduction="sum")).backward()

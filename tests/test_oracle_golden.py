@@ -92,20 +92,29 @@ VARIANTS_2F = ["MP_PDE_Solver2D", "MP_PDE_Solver2DGated", "MP_PDE_Solver2DLEMLin
                "MP_PDE_Solver2DLSTMLin", "MP_PDE_Solver2DLEMLin"]
 
 
+GLU_1F, GLU_2F = "MP_PDE_SolverLEMLinGatedGLU", "MP_PDE_Solver2DLEMLinGatedGLU"      # hidden_features = 164
+
+
+def variant_hidden(name):
+    return 164 if name.endswith("GLU") else 128
+
+
 def variant_eq(name):
     """eq_variables each var_*.npz was generated with (tests/golden/make_golden.py)."""
-    if name in VARIANTS_2F:
+    if name == GLU_1F:
+        return "CE", {"alpha": 3.0}
+    if name in VARIANTS_2F or name == GLU_2F:
         return "AD", {"a": 1.0, "b": 1.0}
     return "CE", ({"alpha": 3.0} if VARIANTS_1F.index(name) % 2 else {})
 
 
-@pytest.mark.parametrize("name", VARIANTS_1F + VARIANTS_2F)
+@pytest.mark.parametrize("name", VARIANTS_1F + VARIANTS_2F + [GLU_1F, GLU_2F])
 def test_variant_matches_reference(name):
     torch.set_default_dtype(torch.float64)
     g = golden_io.load(f"var_{name}.npz")
     pde_name, eq = variant_eq(name)
     pde, data = golden_io.model_inputs(g, pde_name)
-    model = getattr(ov, name)(pde, time_window=25, hidden_features=128, hidden_layer=6, eq_variables=eq)
+    model = getattr(ov, name)(pde, time_window=25, hidden_features=variant_hidden(name), hidden_layer=6, eq_variables=eq)
     formula_weights_(model)
     out = model(data)
     loss = torch.sqrt(torch.nn.functional.mse_loss(out, data.y, reduction="sum"))
@@ -132,6 +141,8 @@ def test_state_dict_tables():
     }
     models.update({n: getattr(ov, n)(pde1, 25, 128, 6, {}) for n in VARIANTS_1F})
     models.update({n: getattr(ov, n)(pde2, 25, 128, 6, {"a": 1.0, "b": 1.0}) for n in VARIANTS_2F})
+    models[GLU_1F] = ov.MP_PDE_SolverLEMLinGatedGLU(pde1, 25, 164, 6, {})
+    models[GLU_2F] = ov.MP_PDE_Solver2DLEMLinGatedGLU(pde2, 25, 164, 6, {"a": 1.0, "b": 1.0})
     assert set(models) == set(tables)
     for name, m in models.items():
         got = {k: list(v.shape) for k, v in m.state_dict().items()}
