@@ -364,9 +364,9 @@ __global__ void __launch_bounds__(LF_THREADS, 1) k_lem_fwd_tc(const LemFwdParams
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           const int j = j0 + jj + q;
-          const float a = p.dt * sigmoidf_(__uint_as_float(r0[q]) + __uint_as_float(q0[q]));
-          const float b = p.dt * sigmoidf_(__uint_as_float(r1[q]) + __uint_as_float(q1[q]));
-          const float zc = tanh_acc(__uint_as_float(r2[q]) + __uint_as_float(q2[q]));
+          const float a = p.dt * sigmoid_r(__uint_as_float(r0[q]) + __uint_as_float(q0[q]));
+          const float b = p.dt * sigmoid_r(__uint_as_float(r1[q]) + __uint_as_float(q1[q]));
+          const float zc = tanh_r(__uint_as_float(r2[q]) + __uint_as_float(q2[q]));
           const float zn = (1.f - b) * zreg[jj + q] + b * zc;
           zreg[jj + q] = zn;
           av[q] = a;
@@ -396,7 +396,7 @@ __global__ void __launch_bounds__(LF_THREADS, 1) k_lem_fwd_tc(const LemFwdParams
         for (int q = 0; q < 8; ++q) {
           const int j = j0 + jj + q;
           const float a = __uint_as_float(ra[q]);
-          const float tl = tanh_acc(__uint_as_float(r3[q]) + __uint_as_float(q3[q]));
+          const float tl = tanh_r(__uint_as_float(r3[q]) + __uint_as_float(q3[q]));
           const float yn = (1.f - a) * yreg[jj + q] + a * tl;
           yreg[jj + q] = yn;
           g_t[(size_t)j * 512 + 384 + c] = tl;
