@@ -446,10 +446,10 @@ KERNEL_OF_OP = {"wgrad_ws": "k_wgrad_ws", "wgrad_tc": "k_wgrad_tc (LEM weight gr
 # dram__bytes_read.sum + dram__bytes_write.sum per launch (mean over the launches of the op in one step) from the committed
 # ncu pass over the serialised headline step: `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum
 # --clock-control none --profile-from-start off python scripts/ncu_step.py c4 8` -> profiles/r2_launches_c4_step.csv
-# (311 launches).  DRAM counters do not see operands that are still in the 126 MB L2 (the node GEMMs read what the previous
+# (312 launches).  DRAM counters do not see operands that are still in the 126 MB L2 (the node GEMMs read what the previous
 # launch wrote: 164 MB per launch against 4 M (K + N) = 184 MB of algorithmic bytes).
-NCU_TRAFFIC_BYTES_PER_LAUNCH = {"linear_tc": 163.6e6, "lem_tc_fwd": 10.617e9, "lem_tc_bwd": 18.909e9, "wgrad_tc": 1281.6e6,
-                                "wgrad_ws": 190.6e6, "edge_ws_fwd": 490.5e6, "edge_ws_bwd": 1422.5e6, "segment_reduce": 316.8e6}
+NCU_TRAFFIC_BYTES_PER_LAUNCH = {"linear_tc": 163.5e6, "lem_tc_fwd": 10.597e9, "lem_tc_bwd": 18.903e9, "wgrad_tc": 1260.3e6,
+                                "wgrad_ws": 190.6e6, "edge_ws_fwd": 490.9e6, "edge_ws_bwd": 1422.4e6, "segment_reduce": 316.9e6}
 
 
 def scatter_bandwidth(dev, n_nodes=1 << 20, degree=6, reps=10):
