@@ -11,7 +11,7 @@ Vectorised, deterministic, device-agnostic restatement of the upstream semantics
   distance, same orientation.
 
 The edge *set* is the bit-exactness contract; it is cross-checked against the independent
-brute-force oracle in tests/test_graph_construction.py.
+brute-force oracle in tests/test_graph_creator.py.
 """
 from __future__ import annotations
 
