@@ -32,8 +32,14 @@ namespace msmp {
 constexpr int LS_EPI_WARPS = 16, LS_CV_WARPS = 4;
 constexpr int LS_MMA_WARP = LS_EPI_WARPS + LS_CV_WARPS;       // 20; 21 = A loader, 22 = B loader, 23 idle (warpgroup padding)
 constexpr int LS_THREADS = 32 * (LS_MMA_WARP + 4);
-constexpr int LS_RA = 5;                                      // raw activation ring: 5 x 16 KiB
-constexpr int LS_RB = 3;                                      // weight ring: 3 x 32 KiB (FAST: 6 x 16 KiB)
+// Ring depths (-DLS_RA_N / -DLS_RB_N for experiments).  Measured at 131 072 rows, one layer's six launches: (5, 3) 0.428 ms,
+// (7, 2) 0.433, (3, 4) 0.426 -- with the operand in tensor memory the kernel is not sensitive to the ring depths any more.
+#ifndef LS_RA_N
+#define LS_RA_N 5
+#define LS_RB_N 3
+#endif
+constexpr int LS_RA = LS_RA_N;                                // raw activation ring: 5 x 16 KiB
+constexpr int LS_RB = LS_RB_N;                                // weight ring: 3 x 32 KiB (FAST: 6 x 16 KiB)
 constexpr int LS_TA = 4;                                      // operand stages in tensor memory
 constexpr int LS_RING_BYTES = LS_RA * IMG_BYTES + LS_RB * TC_B_BYTES;
 constexpr int LS_SMEM = 1024 + LS_RING_BYTES + 512 + LS_EPI_WARPS * EPI_TILE_FLOATS * 4 + EPI_STAGE_FLOATS * 4;
