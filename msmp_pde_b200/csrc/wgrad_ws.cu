@@ -381,18 +381,320 @@ __global__ void __launch_bounds__(WW_THREADS, 1) k_wgrad_ws(const WgradWsParams 
   if (warp == WW_MMA_WARP) tmem_dealloc(tmem, (uint32_t)p.tmem_cols);
 }
 
+// =====================================================================================================================
+// k_wgrad_ts: fp32-parity weight gradients for products with at most 160 operand columns (the LEM maps on T x N rows, the
+// edge dW2 / node dW4 products), dY^T in TENSOR MEMORY.
+//
+// Both k_wgrad_tc and k_wgrad_ws read two MN-major operands from shared memory and are bound by that fetch (~45 B/clk; see
+// above).  Here the dY block is the A operand and lives in tensor memory: a converter thread owns an output column n (its
+// TMEM lane), reads dY[m][n] of the chunk's 32 rows from the raw stage (stride-one across the warp), splits it into tf32
+// hi + exact lo and writes both with tcgen05.st -- the transposition costs nothing and the tensor pipe fetches only the X
+// operand (MN-major SWIZZLE_128B_BASE32B hi | lo images, written by eight more converter warps) from shared memory.
+// 3xTF32: (hi, hi), (lo, hi), (hi, lo), four K = 8 steps per 32-row chunk, accumulators D'[n][k] in TMEM for the CTA's whole
+// row range; the partials of the S row ranges are summed in split order exactly as for k_wgrad_ws (same layout, same
+// callers).  Side / bias gradients: 32 extra columns [side | 1 | 0...] of the X operand.
+constexpr int WT_R = 32;                                   // rows per chunk
+constexpr int WT_DY_WARPS = 4, WT_X_WARPS = 8;
+constexpr int WT_CV_WARPS = WT_DY_WARPS + WT_X_WARPS;      // 12; warp 12 = MMA, warp 13 = loader
+constexpr int WT_THREADS2 = 32 * (WT_CV_WARPS + 2);
+constexpr int WT_TA = 4;                                   // dY operand stages in tensor memory (64 columns each)
+constexpr uint32_t WT_ACOL = 256;                          // first operand-stage column; accumulator columns 0 .. KBS - 1
+constexpr int WT_MAX_KBS = 192;
+
+// byte offset of (row m in 0..31, 16-byte chunk c4) of a [32 x 32 nblk] MN-major (BASE32B) image: column block c4 >> 3,
+// row m, and inside the 128-byte row the 32-byte unit index is XORed with (m & 3)   (same layout as wgrad_tc.cu)
+__device__ __forceinline__ uint32_t wt_mn_off(int m, int c4) {
+  const int c = c4 & 7;
+  const int cs = ((((c >> 1) ^ m) & 3) << 1) | (c & 1);
+  return (uint32_t)((c4 >> 3) * 4096 + m * 128 + cs * 16);
+}
+
+__global__ void __launch_bounds__(WT_THREADS2, 1) k_wgrad_ts(const WgradWsParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* img_ring = smem;                                        // nimg stages of [X hi | X lo]
+  uint8_t* raw_ring = img_ring + p.nimg * p.img_bytes;             // nraw stages of raw fp32 rows
+  uint64_t* bars = reinterpret_cast<uint64_t*>(raw_ring + p.nraw * p.raw_bytes);
+  uint64_t* raw_full = bars;                       // [6] TMA -> converters
+  uint64_t* raw_empty = bars + WW_MAX_RAW;         // [6] converters -> loader
+  uint64_t* img_full = bars + 2 * WW_MAX_RAW;      // [4] X converters -> MMA
+  uint64_t* img_empty = img_full + WW_MAX_IMG;     // [4] MMA -> X converters
+  uint64_t* a_full = img_empty + WW_MAX_IMG;       // [4] dY converters -> MMA
+  uint64_t* a_empty = a_full + WT_TA;              // [4] MMA -> dY converters
+  uint64_t* acc_full = a_empty + WT_TA;            // [1] MMA -> epilogue
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  const int tid = threadIdx.x, warp = warp_index_uniform(), lane = tid & 31;
+  const int split = blockIdx.x;
+  const int n0 = blockIdx.y * 128;
+  const int m_begin = split * p.rows_per_split;
+  const int m_end = min(p.M, m_begin + p.rows_per_split);
+  const int nchunks = (m_end > m_begin) ? (m_end - m_begin + WT_R - 1) / WT_R : 0;
+  const int nside = p.r + p.has_bias;
+  const int half_bytes = p.img_bytes >> 1;                         // one X image (hi or lo): KBS / 32 column blocks of 4 KiB
+
+  if (warp == WT_CV_WARPS) tmem_alloc(tmem_slot, 512);
+  if (tid == 0) {
+    for (int i = 0; i < WW_MAX_RAW; ++i) {
+      mbar_init(&raw_full[i], 1);
+      mbar_init(&raw_empty[i], WT_CV_WARPS);
+    }
+    for (int i = 0; i < WW_MAX_IMG; ++i) {
+      mbar_init(&img_full[i], WT_X_WARPS);
+      mbar_init(&img_empty[i], 1);
+    }
+    for (int i = 0; i < WT_TA; ++i) {
+      mbar_init(&a_full[i], WT_DY_WARPS);
+      mbar_init(&a_empty[i], 1);
+    }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  // raw stage layout (floats): [dY: R x 128][X0: R x kx0][X1][X2][side: R x lds]
+  const int raw_x0 = WT_R * 128;
+  const int raw_side = raw_x0 + WT_R * p.KB;
+
+  if (warp == WT_CV_WARPS + 1) {
+    // ============================================================================= loader: bulk copies of raw fp32 rows
+    int i = 0;
+    uint32_t ph = 0;
+    const uint32_t row_bytes = (uint32_t)(128 + p.KB + (p.r > 0 ? p.lds : 0)) * 4u;
+#pragma unroll 1
+    for (int c = 0; c < nchunks; ++c) {
+      if (c >= p.nraw) mbar_wait_backoff(&raw_empty[i], ph ^ 1);
+      const int m0 = m_begin + c * WT_R;
+      const int nrows = min(WT_R, m_end - m0);
+      float* rs = reinterpret_cast<float*>(raw_ring + i * p.raw_bytes);
+      if (lane == 0) mbar_expect_tx(&raw_full[i], (uint32_t)nrows * row_bytes);
+      __syncwarp();
+      auto copy_rows = [&](float* dst, const float* src, int ld, int width) {
+        if (ld == width) {
+          if (lane == 0) bulk_g2s(dst, src, (uint32_t)(nrows * width) * 4u, &raw_full[i]);
+        } else if (lane < nrows) {
+          bulk_g2s(dst + lane * width, src + (size_t)lane * ld, (uint32_t)width * 4u, &raw_full[i]);
+        }
+      };
+      copy_rows(rs, p.dY + (size_t)m0 * p.lddy + n0, p.lddy, 128);
+      int off = raw_x0;
+      for (int s = 0; s < p.nseg; ++s) {
+        copy_rows(rs + off, p.X[s] + (size_t)m0 * p.ldx[s], p.ldx[s], p.kx[s]);
+        off += WT_R * p.kx[s];
+      }
+      if (p.r > 0) copy_rows(rs + raw_side, p.side + (size_t)m0 * p.lds, p.lds, p.lds);
+      if (++i == p.nraw) {
+        i = 0;
+        ph ^= 1;
+      }
+    }
+  } else if (warp == WT_CV_WARPS) {
+    // ============================================================================= MMA warp
+    const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
+    const bool leader = elect_one();
+    const uint32_t idesc = umma_idesc_tf32(128, p.KBS, 0, 1);          // A from tensor memory, B MN-major
+    int j = 0;
+    uint32_t phj = 0;
+#pragma unroll 1
+    for (int c = 0; c < nchunks; ++c) {
+      const uint32_t ts = (uint32_t)c % WT_TA, tph = ((uint32_t)c / WT_TA) & 1;
+      mbar_wait_backoff(&img_full[j], phj);
+      mbar_wait_backoff(&a_full[ts], tph);
+      tc_fence_after();
+      const uint32_t xh = smem_u32(img_ring + j * p.img_bytes), xl = xh + (uint32_t)half_bytes;
+      const uint32_t a_hi = tm + WT_ACOL + 64 * ts, a_lo = a_hi + 32;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t ko = 1024 * k;        // 8 rows per k-step; LBO = 4096 (next 32 columns), SBO = 512 (next 4 rows)
+        const uint64_t dxh = umma_desc(xh + ko, 4096, 512, 1), dxl = umma_desc(xl + ko, 4096, 512, 1);
+        if (leader) {
+          umma_tf32_ts(tm, a_hi + 8 * k, dxh, idesc, (c | k) ? 1u : 0u);
+          umma_tf32_ts(tm, a_lo + 8 * k, dxh, idesc, 1u);
+          umma_tf32_ts(tm, a_hi + 8 * k, dxl, idesc, 1u);
+        }
+      }
+      if (leader) {
+        umma_commit(&img_empty[j]);
+        umma_commit(&a_empty[ts]);
+        if (c == nchunks - 1) umma_commit(acc_full);
+      }
+      __syncwarp();
+      if (++j == p.nimg) {
+        j = 0;
+        phj ^= 1;
+      }
+    }
+  } else {
+    // ============================================================================= converters, then epilogue
+    int i = 0;
+    uint32_t phr = 0;
+    if (warp < WT_DY_WARPS) {
+      // ---- dY^T -> tensor memory: thread = output column n (TMEM lane), 32 rows of the chunk = 32 k-columns (hi | lo)
+      const int nl = 32 * warp + lane;
+      const uint32_t lane_off = (uint32_t)(32 * warp) << 16;
+      const bool ncol_ok = n0 + nl < p.Nout;
+#pragma unroll 1
+      for (int c = 0; c < nchunks; ++c) {
+        const int nrows = min(WT_R, m_end - (m_begin + c * WT_R));
+        const uint32_t ts = (uint32_t)c % WT_TA, tu = (uint32_t)c / WT_TA;
+        mbar_wait_all(&raw_full[i], phr);
+        const float* rs = reinterpret_cast<const float*>(raw_ring + i * p.raw_bytes);
+        if (tu > 0) mbar_wait_backoff(&a_empty[ts], (tu - 1) & 1);
+        tc_fence_after();
+        const uint32_t col = tmem + lane_off + WT_ACOL + 64 * ts;
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          float hi[8], lo[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const int m = 8 * h + q;
+            const float x = (m < nrows && ncol_ok) ? rs[m * 128 + nl] : 0.f;
+            split_tf32(x, hi[q], lo[q]);
+          }
+          tmem_st8(col + 8 * h, hi);
+          tmem_st8(col + 32 + 8 * h, lo);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&a_full[ts]);
+          mbar_arrive(&raw_empty[i]);
+        }
+        if (++i == p.nraw) {
+          i = 0;
+          phr ^= 1;
+        }
+      }
+    } else {
+      // ---- X (+ side | 1) -> MN-major hi | lo images
+      const int xt = tid - 32 * WT_DY_WARPS;               // 0 .. 255
+      const int kb4 = p.KB >> 2, kbs4 = p.KBS >> 2;        // float4 units per row
+      const int kx0 = p.kx[0], kx01 = kx0 + (p.nseg > 1 ? p.kx[1] : 0);
+      int j = 0;
+      uint32_t phj = 0;
+#pragma unroll 1
+      for (int c = 0; c < nchunks; ++c) {
+        const int nrows = min(WT_R, m_end - (m_begin + c * WT_R));
+        mbar_wait_all(&raw_full[i], phr);
+        if (c >= p.nimg) mbar_wait_backoff(&img_empty[j], phj ^ 1);
+        const float* rs = reinterpret_cast<const float*>(raw_ring + i * p.raw_bytes);
+        uint8_t* hi_img = img_ring + j * p.img_bytes;
+        uint8_t* lo_img = hi_img + half_bytes;
+        // thread -> row m = xt / 8 of the chunk and the 16-byte units c4 = xt % 8 + 8 i (one column block per i): all loads
+        // of a chunk are issued before the first split / store (the unit loop used to be a chain of dependent
+        // load -> split -> store steps, and the conversion latency, not the MMAs, set the pace)
+        {
+          const int m = xt >> 3, cl = xt & 7;
+          const int nit = kbs4 >> 3;                         // column blocks: KBS / 32 <= 6
+          float4 v[6];
+#pragma unroll
+          for (int it = 0; it < 6; ++it) {
+            v[it] = zero4();
+            const int c4 = cl + 8 * it;
+            if (it < nit && m < nrows) {
+              if (c4 < kb4) {
+                const int col = 4 * c4;
+                if (col < kx0) {
+                  v[it] = *reinterpret_cast<const float4*>(rs + raw_x0 + m * kx0 + col);
+                  if (p.xsw[0]) v[it] = swish4(v[it]);
+                } else if (col < kx01) {
+                  v[it] = *reinterpret_cast<const float4*>(rs + raw_x0 + WT_R * kx0 + m * p.kx[1] + (col - kx0));
+                  if (p.xsw[1]) v[it] = swish4(v[it]);
+                } else {
+                  v[it] = *reinterpret_cast<const float4*>(rs + raw_x0 + WT_R * kx01 + m * p.kx[2] + (col - kx01));
+                  if (p.xsw[2]) v[it] = swish4(v[it]);
+                }
+              } else {                                         // [side | 1 | 0 ...]
+                float e[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const int sc = 4 * (c4 - kb4) + q;
+                  e[q] = (sc < p.r) ? rs[raw_side + m * p.lds + p.side_c0 + sc] : (sc == p.r && p.has_bias) ? 1.0f : 0.f;
+                }
+                v[it] = make_float4(e[0], e[1], e[2], e[3]);
+              }
+            }
+          }
+#pragma unroll
+          for (int it = 0; it < 6; ++it)
+            if (it < nit) store_split4(hi_img, lo_img, wt_mn_off(m, cl + 8 * it), v[it]);
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&img_full[j]);
+          mbar_arrive(&raw_empty[i]);
+        }
+        if (++i == p.nraw) {
+          i = 0;
+          phr ^= 1;
+        }
+        if (++j == p.nimg) {
+          j = 0;
+          phj ^= 1;
+        }
+      }
+    }
+    // ---- epilogue: TMEM lanes = n, columns = k; the three warps of a quadrant share the 32-column groups; every store
+    // instruction writes one 128-byte line of the partial
+    if (nchunks > 0) {
+      mbar_wait_backoff(acc_full, 0);
+      tc_fence_after();
+    }
+    const int quad = warp & 3, part = warp >> 2;
+    float* out = p.part + (size_t)split * p.KB * p.Nout;
+    float* out_side = p.part_side + (size_t)split * nside * p.Nout;
+    const int n = n0 + 32 * quad + lane;
+#pragma unroll 1
+    for (int g = part; g < (p.KBS >> 5); g += WT_CV_WARPS / 4) {
+      float v[32];
+      if (nchunks > 0) {
+        __syncwarp();
+        tmem_ld32(tmem + ((uint32_t)(32 * quad) << 16) + (uint32_t)(32 * g), v);
+      } else {
+#pragma unroll
+        for (int q = 0; q < 32; ++q) v[q] = 0.f;
+      }
+      const int k0 = 32 * g;
+      if (n < p.Nout) {
+        if (k0 < p.KB) {
+#pragma unroll
+          for (int q = 0; q < 32; ++q) out[(size_t)(k0 + q) * p.Nout + n] = v[q];
+        } else {
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            if (q < nside) out_side[(size_t)q * p.Nout + n] = v[q];
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == WT_CV_WARPS) tmem_dealloc(tmem, 512);
+}
+
 static int ww_env(const char* name, int dflt) {
   const char* e = getenv(name);
   return e ? atoi(e) : dflt;
 }
 
 // geometry of one call: dY columns per CTA, ring depths, splits.  Returns false when the shape is not supported.
-static bool ww_plan(int M, int KB, int Nout, int nside, int lds, int mode, WgradWsParams& p, int& S, int& ny, int& smem) {
+static bool ww_plan(int M, int KB, int Nout, int nside, int lds, int mode, WgradWsParams& p, int& S, int& ny, int& smem,
+                    bool* use_ts = nullptr) {
   if (KB <= 0 || (KB & 31) || Nout <= 0 || (Nout & 127) || nside < 0 || nside > 8) return false;
   const int KBS = KB + (nside ? 32 : 0);
   if (KBS > 512) return false;
   const int nbtot = Nout >> 7;
-  const int nb = (nbtot >= 2 && 2 * KBS <= 512) ? 2 : 1;
+  // products with at most 192 operand columns (the LEM maps, dW2 / dW4): k_wgrad_ts in fp32-parity mode.  The row split is
+  // computed for its grid (one 128-column dY block per CTA) in BOTH modes, so that msmp_wgrad_ws_splits -- which sizes the
+  // callers' partial buffers -- does not depend on the mode.
+  static const bool ts_on = ww_env("MSMP_WGRAD_TS", 1) != 0;
+  const bool ts_shape = ts_on && KBS <= WT_MAX_KBS;
+  const bool ts = ts_shape && mode == 0;
+  if (use_ts) *use_ts = ts;
+  const int nb = ts ? 1 : ((nbtot >= 2 && 2 * KBS <= 512) ? 2 : 1);
   p.KB = KB;
   p.KBS = KBS;
   p.npc = nb * 128;
@@ -400,29 +702,38 @@ static bool ww_plan(int M, int KB, int Nout, int nside, int lds, int mode, Wgrad
   int cols = 32;
   while (cols < nb * KBS) cols <<= 1;
   p.tmem_cols = cols;
-  const int raw = WW_R * (p.npc + KB + lds) * 4;      // lds = 0 when no side columns are read
+  const int R = ts ? WT_R : WW_R;
+  const int raw = R * (p.npc + KB + lds) * 4;      // lds = 0 when no side columns are read
   p.raw_bytes = (raw + 127) & ~127;
-  p.img_bytes = (mode == 0 ? 3 : 1) * WW_R * (p.npc + ((KBS + 63) & ~63)) * 2;
+  p.img_bytes = ts ? KBS * 256 : (mode == 0 ? 3 : 1) * WW_R * (p.npc + ((KBS + 63) & ~63)) * 2;
   const int budget = WW_SMEM_LIMIT - 1024 - 512;
   int nraw = 2, nimg = 2;
   if (nraw * p.raw_bytes + nimg * p.img_bytes > budget) return false;
-  // deeper rings while they fit: first a third image stage, then raw stages (loads in flight)
-  if (nraw * p.raw_bytes + (nimg + 1) * p.img_bytes <= budget) ++nimg;
-  while (nraw < WW_MAX_RAW && (nraw + 1) * p.raw_bytes + nimg * p.img_bytes <= budget) ++nraw;
-  if (nimg < WW_MAX_IMG && nraw == WW_MAX_RAW && nraw * p.raw_bytes + (nimg + 1) * p.img_bytes <= budget) ++nimg;
+  if (ts) {
+    // raw stages (bytes in flight) first, then image stages
+    while (nraw < WW_MAX_RAW && (nraw + 1) * p.raw_bytes + nimg * p.img_bytes <= budget) ++nraw;
+    while (nimg < WW_MAX_IMG && nraw * p.raw_bytes + (nimg + 1) * p.img_bytes <= budget) ++nimg;
+  } else {
+    // deeper rings while they fit: first a third image stage, then raw stages (loads in flight)
+    if (nraw * p.raw_bytes + (nimg + 1) * p.img_bytes <= budget) ++nimg;
+    while (nraw < WW_MAX_RAW && (nraw + 1) * p.raw_bytes + nimg * p.img_bytes <= budget) ++nraw;
+    if (nimg < WW_MAX_IMG && nraw == WW_MAX_RAW && nraw * p.raw_bytes + (nimg + 1) * p.img_bytes <= budget) ++nimg;
+  }
   p.nraw = nraw;
   p.nimg = nimg;
   smem = 1024 + nraw * p.raw_bytes + nimg * p.img_bytes + 512;
   static const int sms = [] { int d = 0, n = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); return n > 0 ? n : 148; }();
   static const int min_rows = ww_env("MSMP_WGRAD_WS_MIN_ROWS", 256);
-  int max_s = sms / ny;
+  const int ny_split = ts_shape ? nbtot : ny;
+  const int rq = ts_shape ? WT_R : WW_R;              // row quantum of a split
+  int max_s = sms / ny_split;
   if (max_s < 1) max_s = 1;
-  int s = M / (min_rows > WW_R ? min_rows : WW_R);
+  int s = M / (min_rows > rq ? min_rows : rq);
   if (s < 1) s = 1;
   if (s > max_s) s = max_s;
   int rps = (M + s - 1) / s;
-  rps = (rps + WW_R - 1) / WW_R * WW_R;
-  if (rps < WW_R) rps = WW_R;
+  rps = (rps + rq - 1) / rq * rq;
+  if (rps < rq) rps = rq;
   p.rows_per_split = rps;
   S = M > 0 ? (M + rps - 1) / rps : 1;
   p.M = M;
@@ -466,19 +777,23 @@ extern "C" int msmp_wgrad_ws(const float* const* X, const int* ldx, const int* k
   const int nside = rr + (has_bias ? 1 : 0);
   if (nside && side && ((lds & 3) || lds > 16 || side_c0 < 0 || side_c0 + rr > lds)) return MSMP_ERR_ARG;
   int S = 0, ny = 0, smem = 0;
-  if (!ww_plan(M, KB, Nout, nside, side ? lds : 0, mode, p, S, ny, smem)) return MSMP_ERR_ARG;
+  bool use_ts = false;
+  if (!ww_plan(M, KB, Nout, nside, side ? lds : 0, mode, p, S, ny, smem, &use_ts)) return MSMP_ERR_ARG;
   p.dY = dY; p.lddy = lddy; p.Nout = Nout;
   p.side = side; p.lds = side ? lds : 0; p.side_c0 = side_c0; p.r = rr; p.has_bias = has_bias ? 1 : 0;
   p.part = part; p.part_side = part_side;
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(k_wgrad_ws<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, WW_SMEM_LIMIT) != cudaSuccess ||
-        cudaFuncSetAttribute(k_wgrad_ws<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, WW_SMEM_LIMIT) != cudaSuccess)
+        cudaFuncSetAttribute(k_wgrad_ws<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, WW_SMEM_LIMIT) != cudaSuccess ||
+        cudaFuncSetAttribute(k_wgrad_ts, cudaFuncAttributeMaxDynamicSharedMemorySize, WW_SMEM_LIMIT) != cudaSuccess)
       return MSMP_ERR_CUDA;
     attr_set = true;
   }
   dim3 grid(S, ny);
-  if (mode == 0)
+  if (use_ts)
+    k_wgrad_ts<<<grid, WT_THREADS2, smem, stream>>>(p);
+  else if (mode == 0)
     k_wgrad_ws<0><<<grid, WW_THREADS, smem, stream>>>(p);
   else
     k_wgrad_ws<1><<<grid, WW_THREADS, smem, stream>>>(p);

@@ -94,6 +94,8 @@ WGRAD_WS_MAX_TALL_ROWS = int(os.environ.get("MSMP_WGRAD_WS_MAX_TALL_ROWS", str(1
 # latency bound either way and the persistent kernel's longer prologue costs more than its single read of the operands
 # saves: C2 step 3.74 ms with k_wgrad_tc against 3.87 ms (C4, 131 072 nodes: 46.9 against 46.0 ms).
 WGRAD_WS_MIN_ROWS = int(os.environ.get("MSMP_WGRAD_WS_MIN_ROWS_USE", str(1 << 16)))
+# k_wgrad_ts inside msmp_wgrad_ws (fp32-parity mode, at most 192 operand columns); "0" restores the bf16-piece kernel there
+WGRAD_TS = os.environ.get("MSMP_WGRAD_TS", "1") != "0"
 
 
 def wgrad_use_ws(M: int, Kt: int, Nout: int, nside: int = 1) -> bool:
@@ -103,7 +105,14 @@ def wgrad_use_ws(M: int, Kt: int, Nout: int, nside: int = 1) -> bool:
         return False
     if PRECISION == "bf16":
         return True
-    return M >= WGRAD_WS_MIN_ROWS and not (M >= WGRAD_WS_MAX_TALL_ROWS and Kt <= 192)
+    if M < WGRAD_WS_MIN_ROWS:
+        return False
+    if M >= WGRAD_WS_MAX_TALL_ROWS and Kt <= 192:
+        # tall and narrow: msmp_wgrad_ws runs k_wgrad_ts (dY^T in tensor memory) for Kt + side block <= 192 columns; it beats
+        # k_wgrad_tc when the dY block is contiguous (Nout = 128: LEM dL product 1.00 against 1.19 ms, edge dW2 0.165
+        # against 0.210 ms) and loses with three strided blocks (LEM dG product, Nout = 384: 4.1 against 3.5 ms)
+        return WGRAD_TS and Nout == 128 and Kt + (32 if nside else 0) <= 192
+    return True
 # Persistent (all-T-steps-in-one-launch) LEM kernels; False = one GEMM + one gate kernel per step.
 LEM_PERSISTENT = True
 # tensor-core edge kernels: warp-specialised, weights in tensor memory (edge_ws.cu) | single-role (edge_tc.cu)
