@@ -439,7 +439,8 @@ def run_ours(args):
     return out
 
 
-KERNEL_OF_OP = {"wgrad_ws": "k_wgrad_ws", "wgrad_tc": "k_wgrad_tc (LEM weight gradients, 3.3 Mi rows; edge dW2, 520 Ki rows)",
+KERNEL_OF_OP = {"wgrad_ws": "k_wgrad_ws", "wgrad_tc": "k_wgrad_tc",
+                "wgrad_ts": "k_wgrad_ts (LEM weight gradients, 3.3 Mi rows; edge dW2, 520 Ki rows; dW4)",
                 "linear_tc": "k_linear_ts (k_linear_tc below 296 tiles)",
                 "edge_ws_fwd": "k_edge_ws<fwd>", "edge_ws_bwd": "k_edge_ws<bwd>", "lem_tc_fwd": "k_lem_fwd_tc",
                 "lem_tc_bwd": "k_lem_bwd_tc", "segment_reduce": "k_segment_reduce"}

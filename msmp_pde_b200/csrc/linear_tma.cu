@@ -241,20 +241,26 @@ static EncodeTiledFn encode_tiled() {
   return fn;
 }
 
-// [M x K] fp32 row-major (row stride lda floats) as a 2-D tensor map with a 32-column x 128-row box, 128-byte swizzle
-bool linear_make_map(CUtensorMap* tm, const float* A, int lda, int K, int M) {
+// [rows x cols] fp32 row-major (row stride ld floats) as a 2-D tensor map with a box_cols x box_rows box; swizzle128: the
+// 128-byte swizzle of the UMMA K-major tile image (box_cols = 32), else plain row-major boxes
+bool tensor_map_2d(CUtensorMap* tm, const float* A, int ld, int cols, int rows, int box_cols, int box_rows, bool swizzle128) {
   EncodeTiledFn enc = encode_tiled();
   if (!enc) return false;
-  if ((reinterpret_cast<uintptr_t>(A) & 15) || (lda & 3)) return false;
-  const cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)M};
-  const cuuint64_t gstride[1] = {(cuuint64_t)lda * 4};
-  const cuuint32_t box[2] = {32, 128};
+  if ((reinterpret_cast<uintptr_t>(A) & 15) || (ld & 3)) return false;
+  const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)ld * 4};
+  const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
   static const int promo = [] { const char* e = getenv("MSMP_TMA_PROMO"); return e ? atoi(e) : 128; }();
   return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(A), gdim, gstride, box, estr,
-             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
              promo == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : (promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : (promo == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B)),
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// [M x K] fp32 row-major (row stride lda floats): 32-column x 128-row boxes, 128-byte swizzle (the node GEMMs' A operand)
+bool linear_make_map(CUtensorMap* tm, const float* A, int lda, int K, int M) {
+  return tensor_map_2d(tm, A, lda, K, M, 32, 128, true);
 }
 
 // Returns MSMP_OK when the launch was made, 1 when this path cannot take the call (the caller falls back to k_linear_ws).

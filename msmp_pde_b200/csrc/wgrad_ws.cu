@@ -33,6 +33,8 @@
 // inside the one k_unpack launch that ends the captured training step's backward pass (gradsink.py): then a weight
 // gradient is ONE launch.  Deterministic, no atomics.
 #include <cstdlib>
+#include <cstring>
+#include <cuda.h>
 #include <cuda_bf16.h>
 #include "umma.cuh"
 #include "msmp_b200.h"
@@ -390,16 +392,24 @@ __global__ void __launch_bounds__(WW_THREADS, 1) k_wgrad_ws(const WgradWsParams 
 // TMEM lane), reads dY[m][n] of the chunk's 32 rows from the raw stage (stride-one across the warp), splits it into tf32
 // hi + exact lo and writes both with tcgen05.st -- the transposition costs nothing and the tensor pipe fetches only the X
 // operand (MN-major SWIZZLE_128B_BASE32B hi | lo images, written by eight more converter warps) from shared memory.
-// 3xTF32: (hi, hi), (lo, hi), (hi, lo), four K = 8 steps per 32-row chunk, accumulators D'[n][k] in TMEM for the CTA's whole
-// row range; the partials of the S row ranges are summed in split order exactly as for k_wgrad_ws (same layout, same
-// callers).  Side / bias gradients: 32 extra columns [side | 1 | 0...] of the X operand.
+// 3xTF32: (hi, hi), (lo, hi), (hi, lo), four K = 8 steps per 32-row chunk.
+//
+// ACCUMULATION.  The tensor core's fp32 accumulation truncates: over a long chain the error of D'[n][k] grows like
+// rows^1.5 (measured 3.2e-8 rows^1.5 per CTA on unit-variance data, scripts/wgrad_error_growth.py: 4.6e-4 of max|ref| for a
+// 3.3 Mi-row LEM product on 49 CTAs with k_wgrad_tc and with the first version of this kernel, where an FFMA GEMM has 5e-6).
+// So the MMA accumulator only ever holds one PERIOD of `flush` chunks (8 x 32 rows): four drain warps then add it with
+// round-to-nearest fp32 adds into a second, outer accumulator (also in tensor memory: tcgen05.ld both, add, tcgen05.st) and
+// the MMA warp starts the next period from zero.  The converters never wait for this; the MMA warp waits for the read-out.
+// Error with 8 chunks per period: 2e-6 of max|ref| at every row count.
+// Side / bias gradients ([side | 1]^T dY) do not go through the tensor pipe at all: the dY converter thread of column n has
+// every dY[m][n] in a register and accumulates them itself.
+// The partials of the S row ranges are summed in split order exactly as for k_wgrad_ws (same layout, same callers).
 constexpr int WT_R = 32;                                   // rows per chunk
 constexpr int WT_DY_WARPS = 4, WT_X_WARPS = 8;
-constexpr int WT_CV_WARPS = WT_DY_WARPS + WT_X_WARPS;      // 12; warp 12 = MMA, warp 13 = loader
-constexpr int WT_THREADS2 = 32 * (WT_CV_WARPS + 2);
-constexpr int WT_TA = 4;                                   // dY operand stages in tensor memory (64 columns each)
-constexpr uint32_t WT_ACOL = 256;                          // first operand-stage column; accumulator columns 0 .. KBS - 1
-constexpr int WT_MAX_KBS = 192;
+constexpr int WT_CV_WARPS = WT_DY_WARPS + WT_X_WARPS;      // 12; warp 12 = MMA, warp 13 = loader, warps 14..17 = drain
+constexpr int WT_THREADS2 = 32 * (WT_CV_WARPS + 2 + 4);
+constexpr int WT_MAX_TA = 4;                               // dY operand stages in tensor memory (64 columns each)
+constexpr int WT_MAX_KBS = 160;                            // operand columns (no side block: see above)
 
 // byte offset of (row m in 0..31, 16-byte chunk c4) of a [32 x 32 nblk] MN-major (BASE32B) image: column block c4 >> 3,
 // row m, and inside the 128-byte row the 32-byte unit index is XORed with (m & 3)   (same layout as wgrad_tc.cu)
@@ -409,7 +419,8 @@ __device__ __forceinline__ uint32_t wt_mn_off(int m, int c4) {
   return (uint32_t)((c4 >> 3) * 4096 + m * 128 + cs * 16);
 }
 
-__global__ void __launch_bounds__(WT_THREADS2, 1) k_wgrad_ts(const WgradWsParams p) {
+__global__ void __launch_bounds__(WT_THREADS2, 1) k_wgrad_ts(const WgradWsParams p, const __grid_constant__ CUtensorMap tm_dy,
+                                                           const int dy_tma, const int flush) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* img_ring = smem;                                        // nimg stages of [X hi | X lo]
@@ -420,17 +431,23 @@ __global__ void __launch_bounds__(WT_THREADS2, 1) k_wgrad_ts(const WgradWsParams
   uint64_t* img_full = bars + 2 * WW_MAX_RAW;      // [4] X converters -> MMA
   uint64_t* img_empty = img_full + WW_MAX_IMG;     // [4] MMA -> X converters
   uint64_t* a_full = img_empty + WW_MAX_IMG;       // [4] dY converters -> MMA
-  uint64_t* a_empty = a_full + WT_TA;              // [4] MMA -> dY converters
-  uint64_t* acc_full = a_empty + WT_TA;            // [1] MMA -> epilogue
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  uint64_t* a_empty = a_full + WT_MAX_TA;          // [4] MMA -> dY converters
+  uint64_t* acc_full = a_empty + WT_MAX_TA;        // [1] MMA -> drain warps (the accumulator of a period is complete)
+  uint64_t* acc_drained = acc_full + 1;            // [1] drain warps -> MMA (added to the outer accumulator)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_drained + 1);
   const int tid = threadIdx.x, warp = warp_index_uniform(), lane = tid & 31;
   const int split = blockIdx.x;
   const int n0 = blockIdx.y * 128;
   const int m_begin = split * p.rows_per_split;
   const int m_end = min(p.M, m_begin + p.rows_per_split);
   const int nchunks = (m_end > m_begin) ? (m_end - m_begin + WT_R - 1) / WT_R : 0;
+  const int nper = (nchunks + flush - 1) / flush;                 // accumulator periods
   const int nside = p.r + p.has_bias;
-  const int half_bytes = p.img_bytes >> 1;                         // one X image (hi or lo): KBS / 32 column blocks of 4 KiB
+  const int half_bytes = p.img_bytes >> 1;                         // one X image (hi or lo): KB / 32 column blocks of 4 KiB
+  // tensor memory: MMA accumulator at column 0, outer accumulator at KP, dY operand stages from 2 KP on
+  const uint32_t KP = p.KB <= 128 ? 128u : 160u;
+  const uint32_t acol = 2u * KP;
+  const int nta = (512 - (int)acol) / 64 < WT_MAX_TA ? (512 - (int)acol) / 64 : WT_MAX_TA;
 
   if (warp == WT_CV_WARPS) tmem_alloc(tmem_slot, 512);
   if (tid == 0) {
@@ -442,11 +459,12 @@ __global__ void __launch_bounds__(WT_THREADS2, 1) k_wgrad_ts(const WgradWsParams
       mbar_init(&img_full[i], WT_X_WARPS);
       mbar_init(&img_empty[i], 1);
     }
-    for (int i = 0; i < WT_TA; ++i) {
+    for (int i = 0; i < WT_MAX_TA; ++i) {
       mbar_init(&a_full[i], WT_DY_WARPS);
       mbar_init(&a_empty[i], 1);
     }
     mbar_init(acc_full, 1);
+    mbar_init(acc_drained, 4);
     fence_barrier_init();
   }
   tc_fence_before();
@@ -468,7 +486,10 @@ __global__ void __launch_bounds__(WT_THREADS2, 1) k_wgrad_ts(const WgradWsParams
       const int m0 = m_begin + c * WT_R;
       const int nrows = min(WT_R, m_end - m0);
       float* rs = reinterpret_cast<float*>(raw_ring + i * p.raw_bytes);
-      if (lane == 0) mbar_expect_tx(&raw_full[i], (uint32_t)nrows * row_bytes);
+      // a strided dY block (Nout > 128) arrives by ONE tensor-map copy of the [32 x 128] box (rows past M are zero filled, the
+      // box always counts 16 KiB) instead of 32 row copies of 512 bytes
+      if (lane == 0)
+        mbar_expect_tx(&raw_full[i], dy_tma ? (uint32_t)(WT_R * 128 * 4) + (uint32_t)nrows * (row_bytes - 512u) : (uint32_t)nrows * row_bytes);
       __syncwarp();
       auto copy_rows = [&](float* dst, const float* src, int ld, int width) {
         if (ld == width) {
@@ -477,7 +498,16 @@ __global__ void __launch_bounds__(WT_THREADS2, 1) k_wgrad_ts(const WgradWsParams
           bulk_g2s(dst + lane * width, src + (size_t)lane * ld, (uint32_t)width * 4u, &raw_full[i]);
         }
       };
-      copy_rows(rs, p.dY + (size_t)m0 * p.lddy + n0, p.lddy, 128);
+      if (dy_tma) {
+        if (lane == 0)
+          asm volatile(
+              "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                  smem_u32(rs)),
+              "l"(reinterpret_cast<uint64_t>(&tm_dy)), "r"(n0), "r"(m0), "r"(smem_u32(&raw_full[i]))
+              : "memory");
+      } else {
+        copy_rows(rs, p.dY + (size_t)m0 * p.lddy + n0, p.lddy, 128);
+      }
       int off = raw_x0;
       for (int s = 0; s < p.nseg; ++s) {
         copy_rows(rs + off, p.X[s] + (size_t)m0 * p.ldx[s], p.ldx[s], p.kx[s]);
@@ -493,56 +523,123 @@ __global__ void __launch_bounds__(WT_THREADS2, 1) k_wgrad_ts(const WgradWsParams
     // ============================================================================= MMA warp
     const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
     const bool leader = elect_one();
-    const uint32_t idesc = umma_idesc_tf32(128, p.KBS, 0, 1);          // A from tensor memory, B MN-major
-    int j = 0;
-    uint32_t phj = 0;
+    const uint32_t idesc = umma_idesc_tf32(128, p.KB, 0, 1);           // A from tensor memory, B MN-major
+    int j = 0, ts = 0, cf = 0, per = 0;
+    uint32_t phj = 0, tph = 0;
 #pragma unroll 1
     for (int c = 0; c < nchunks; ++c) {
-      const uint32_t ts = (uint32_t)c % WT_TA, tph = ((uint32_t)c / WT_TA) & 1;
+      if (cf == 0 && per > 0) mbar_wait_backoff(acc_drained, (uint32_t)(per - 1) & 1);      // previous period read out
       mbar_wait_backoff(&img_full[j], phj);
       mbar_wait_backoff(&a_full[ts], tph);
       tc_fence_after();
       const uint32_t xh = smem_u32(img_ring + j * p.img_bytes), xl = xh + (uint32_t)half_bytes;
-      const uint32_t a_hi = tm + WT_ACOL + 64 * ts, a_lo = a_hi + 32;
+      const uint32_t a_hi = tm + acol + 64u * (uint32_t)ts, a_lo = a_hi + 32;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const uint32_t ko = 1024 * k;        // 8 rows per k-step; LBO = 4096 (next 32 columns), SBO = 512 (next 4 rows)
         const uint64_t dxh = umma_desc(xh + ko, 4096, 512, 1), dxl = umma_desc(xl + ko, 4096, 512, 1);
         if (leader) {
-          umma_tf32_ts(tm, a_hi + 8 * k, dxh, idesc, (c | k) ? 1u : 0u);
+          umma_tf32_ts(tm, a_hi + 8 * k, dxh, idesc, (cf | k) ? 1u : 0u);
           umma_tf32_ts(tm, a_lo + 8 * k, dxh, idesc, 1u);
           umma_tf32_ts(tm, a_hi + 8 * k, dxl, idesc, 1u);
         }
       }
+      const bool period_end = cf == flush - 1 || c == nchunks - 1;
       if (leader) {
         umma_commit(&img_empty[j]);
         umma_commit(&a_empty[ts]);
-        if (c == nchunks - 1) umma_commit(acc_full);
+        if (period_end) umma_commit(acc_full);
       }
       __syncwarp();
+      if (period_end) {
+        cf = 0;
+        ++per;
+      } else {
+        ++cf;
+      }
       if (++j == p.nimg) {
         j = 0;
         phj ^= 1;
       }
+      if (++ts == nta) {
+        ts = 0;
+        tph ^= 1;
+      }
+    }
+  } else if (warp > WT_CV_WARPS + 1) {
+    // ============================================================================= drain warps (one per TMEM lane quadrant)
+    const int quad = warp & 3;
+    const uint32_t tq = tmem + ((uint32_t)(32 * quad) << 16);
+    const int ng = p.KB >> 5;
+#pragma unroll 1
+    for (int per = 0; per < nper; ++per) {
+      mbar_wait_backoff(acc_full, (uint32_t)per & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int g = 0; g < ng; ++g) {
+        float v[32], o[32];
+        __syncwarp();
+        tmem_ld32(tq + (uint32_t)(32 * g), v);
+        if (per > 0) {
+          tmem_ld32(tq + KP + (uint32_t)(32 * g), o);
+#pragma unroll
+          for (int q = 0; q < 32; ++q) v[q] += o[q];
+        }
+#pragma unroll
+        for (int q = 0; q < 32; q += 8) {
+          float w8[8];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) w8[t] = v[q + t];
+          tmem_st8(tq + KP + (uint32_t)(32 * g + q), w8);
+        }
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_drained);
+    }
+    // the CTA's partial: every store instruction writes one 128-byte line (lanes = consecutive n)
+    float* out = p.part + (size_t)split * p.KB * p.Nout;
+    const int n = n0 + 32 * quad + lane;
+#pragma unroll 1
+    for (int g = 0; g < ng; ++g) {
+      float v[32];
+      if (nper > 0) {
+        __syncwarp();
+        tmem_ld32(tq + KP + (uint32_t)(32 * g), v);
+      } else {
+#pragma unroll
+        for (int q = 0; q < 32; ++q) v[q] = 0.f;
+      }
+      if (n < p.Nout) {
+#pragma unroll
+        for (int q = 0; q < 32; ++q) out[(size_t)(32 * g + q) * p.Nout + n] = v[q];
+      }
     }
   } else {
-    // ============================================================================= converters, then epilogue
+    // ============================================================================= converters
     int i = 0;
     uint32_t phr = 0;
     if (warp < WT_DY_WARPS) {
-      // ---- dY^T -> tensor memory: thread = output column n (TMEM lane), 32 rows of the chunk = 32 k-columns (hi | lo)
+      // ---- dY^T -> tensor memory: thread = output column n (TMEM lane), 32 rows of the chunk = 32 k-columns (hi | lo);
+      // the same thread accumulates the side / bias gradients of its column
       const int nl = 32 * warp + lane;
       const uint32_t lane_off = (uint32_t)(32 * warp) << 16;
       const bool ncol_ok = n0 + nl < p.Nout;
+      float sacc[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) sacc[q] = 0.f;
+      const bool bias_only = p.r == 0 && p.has_bias != 0;
+      int ts = 0;
+      uint32_t tph = 0;
 #pragma unroll 1
       for (int c = 0; c < nchunks; ++c) {
         const int nrows = min(WT_R, m_end - (m_begin + c * WT_R));
-        const uint32_t ts = (uint32_t)c % WT_TA, tu = (uint32_t)c / WT_TA;
         mbar_wait_all(&raw_full[i], phr);
         const float* rs = reinterpret_cast<const float*>(raw_ring + i * p.raw_bytes);
-        if (tu > 0) mbar_wait_backoff(&a_empty[ts], (tu - 1) & 1);
+        if (c >= nta) mbar_wait_backoff(&a_empty[ts], tph ^ 1);
         tc_fence_after();
-        const uint32_t col = tmem + lane_off + WT_ACOL + 64 * ts;
+        const uint32_t col = tmem + lane_off + acol + 64u * (uint32_t)ts;
 #pragma unroll
         for (int h = 0; h < 4; ++h) {
           float hi[8], lo[8];
@@ -551,6 +648,15 @@ __global__ void __launch_bounds__(WT_THREADS2, 1) k_wgrad_ts(const WgradWsParams
             const int m = 8 * h + q;
             const float x = (m < nrows && ncol_ok) ? rs[m * 128 + nl] : 0.f;
             split_tf32(x, hi[q], lo[q]);
+            if (bias_only) {                                 // (every product this kernel takes in the models: one add)
+              sacc[0] += x;
+            } else if (nside) {
+#pragma unroll 1
+              for (int sq = 0; sq < nside; ++sq) {
+                const float sv = (sq < p.r) ? rs[raw_side + m * p.lds + p.side_c0 + sq] : 1.0f;      // warp-uniform address
+                sacc[sq] = fmaf(sv, x, sacc[sq]);
+              }
+            }
           }
           tmem_st8(col + 8 * h, hi);
           tmem_st8(col + 32 + 8 * h, lo);
@@ -566,11 +672,21 @@ __global__ void __launch_bounds__(WT_THREADS2, 1) k_wgrad_ts(const WgradWsParams
           i = 0;
           phr ^= 1;
         }
+        if (++ts == nta) {
+          ts = 0;
+          tph ^= 1;
+        }
+      }
+      if (nside && ncol_ok) {
+        float* out_side = p.part_side + (size_t)split * nside * p.Nout;
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          if (q < nside) out_side[(size_t)q * p.Nout + n0 + nl] = sacc[q];
       }
     } else {
-      // ---- X (+ side | 1) -> MN-major hi | lo images
+      // ---- X -> MN-major hi | lo images
       const int xt = tid - 32 * WT_DY_WARPS;               // 0 .. 255
-      const int kb4 = p.KB >> 2, kbs4 = p.KBS >> 2;        // float4 units per row
+      const int kb4 = p.KB >> 2;                           // float4 units per row
       const int kx0 = p.kx[0], kx01 = kx0 + (p.nseg > 1 ? p.kx[1] : 0);
       int j = 0;
       uint32_t phj = 0;
@@ -583,42 +699,31 @@ __global__ void __launch_bounds__(WT_THREADS2, 1) k_wgrad_ts(const WgradWsParams
         uint8_t* hi_img = img_ring + j * p.img_bytes;
         uint8_t* lo_img = hi_img + half_bytes;
         // thread -> row m = xt / 8 of the chunk and the 16-byte units c4 = xt % 8 + 8 i (one column block per i): all loads
-        // of a chunk are issued before the first split / store (the unit loop used to be a chain of dependent
-        // load -> split -> store steps, and the conversion latency, not the MMAs, set the pace)
+        // of a chunk are issued before the first split / store (a chain of dependent load -> split -> store steps made the
+        // conversion latency, not the MMAs, set the pace)
         {
           const int m = xt >> 3, cl = xt & 7;
-          const int nit = kbs4 >> 3;                         // column blocks: KBS / 32 <= 6
-          float4 v[6];
+          const int nit = kb4 >> 3;                          // column blocks: KB / 32 <= 5
+          float4 v[5];
 #pragma unroll
-          for (int it = 0; it < 6; ++it) {
+          for (int it = 0; it < 5; ++it) {
             v[it] = zero4();
-            const int c4 = cl + 8 * it;
+            const int col = 4 * (cl + 8 * it);
             if (it < nit && m < nrows) {
-              if (c4 < kb4) {
-                const int col = 4 * c4;
-                if (col < kx0) {
-                  v[it] = *reinterpret_cast<const float4*>(rs + raw_x0 + m * kx0 + col);
-                  if (p.xsw[0]) v[it] = swish4(v[it]);
-                } else if (col < kx01) {
-                  v[it] = *reinterpret_cast<const float4*>(rs + raw_x0 + WT_R * kx0 + m * p.kx[1] + (col - kx0));
-                  if (p.xsw[1]) v[it] = swish4(v[it]);
-                } else {
-                  v[it] = *reinterpret_cast<const float4*>(rs + raw_x0 + WT_R * kx01 + m * p.kx[2] + (col - kx01));
-                  if (p.xsw[2]) v[it] = swish4(v[it]);
-                }
-              } else {                                         // [side | 1 | 0 ...]
-                float e[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  const int sc = 4 * (c4 - kb4) + q;
-                  e[q] = (sc < p.r) ? rs[raw_side + m * p.lds + p.side_c0 + sc] : (sc == p.r && p.has_bias) ? 1.0f : 0.f;
-                }
-                v[it] = make_float4(e[0], e[1], e[2], e[3]);
+              if (col < kx0) {
+                v[it] = *reinterpret_cast<const float4*>(rs + raw_x0 + m * kx0 + col);
+                if (p.xsw[0]) v[it] = swish4(v[it]);
+              } else if (col < kx01) {
+                v[it] = *reinterpret_cast<const float4*>(rs + raw_x0 + WT_R * kx0 + m * p.kx[1] + (col - kx0));
+                if (p.xsw[1]) v[it] = swish4(v[it]);
+              } else {
+                v[it] = *reinterpret_cast<const float4*>(rs + raw_x0 + WT_R * kx01 + m * p.kx[2] + (col - kx01));
+                if (p.xsw[2]) v[it] = swish4(v[it]);
               }
             }
           }
 #pragma unroll
-          for (int it = 0; it < 6; ++it)
+          for (int it = 0; it < 5; ++it)
             if (it < nit) store_split4(hi_img, lo_img, wt_mn_off(m, cl + 8 * it), v[it]);
         }
         fence_proxy_async();
@@ -637,43 +742,13 @@ __global__ void __launch_bounds__(WT_THREADS2, 1) k_wgrad_ts(const WgradWsParams
         }
       }
     }
-    // ---- epilogue: TMEM lanes = n, columns = k; the three warps of a quadrant share the 32-column groups; every store
-    // instruction writes one 128-byte line of the partial
-    if (nchunks > 0) {
-      mbar_wait_backoff(acc_full, 0);
-      tc_fence_after();
-    }
-    const int quad = warp & 3, part = warp >> 2;
-    float* out = p.part + (size_t)split * p.KB * p.Nout;
-    float* out_side = p.part_side + (size_t)split * nside * p.Nout;
-    const int n = n0 + 32 * quad + lane;
-#pragma unroll 1
-    for (int g = part; g < (p.KBS >> 5); g += WT_CV_WARPS / 4) {
-      float v[32];
-      if (nchunks > 0) {
-        __syncwarp();
-        tmem_ld32(tmem + ((uint32_t)(32 * quad) << 16) + (uint32_t)(32 * g), v);
-      } else {
-#pragma unroll
-        for (int q = 0; q < 32; ++q) v[q] = 0.f;
-      }
-      const int k0 = 32 * g;
-      if (n < p.Nout) {
-        if (k0 < p.KB) {
-#pragma unroll
-          for (int q = 0; q < 32; ++q) out[(size_t)(k0 + q) * p.Nout + n] = v[q];
-        } else {
-#pragma unroll
-          for (int q = 0; q < 8; ++q)
-            if (q < nside) out_side[(size_t)q * p.Nout + n] = v[q];
-        }
-      }
-    }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == WT_CV_WARPS) tmem_dealloc(tmem, 512);
 }
+
+bool tensor_map_2d(CUtensorMap* tm, const float* A, int ld, int cols, int rows, int box_cols, int box_rows, bool swizzle128);      // linear_tma.cu
 
 static int ww_env(const char* name, int dflt) {
   const char* e = getenv(name);
@@ -687,11 +762,11 @@ static bool ww_plan(int M, int KB, int Nout, int nside, int lds, int mode, Wgrad
   const int KBS = KB + (nside ? 32 : 0);
   if (KBS > 512) return false;
   const int nbtot = Nout >> 7;
-  // products with at most 192 operand columns (the LEM maps, dW2 / dW4): k_wgrad_ts in fp32-parity mode.  The row split is
+  // products with at most 160 operand columns (the LEM maps, dW2 / dW4): k_wgrad_ts in fp32-parity mode.  The row split is
   // computed for its grid (one 128-column dY block per CTA) in BOTH modes, so that msmp_wgrad_ws_splits -- which sizes the
   // callers' partial buffers -- does not depend on the mode.
   static const bool ts_on = ww_env("MSMP_WGRAD_TS", 1) != 0;
-  const bool ts_shape = ts_on && KBS <= WT_MAX_KBS;
+  const bool ts_shape = ts_on && KB <= WT_MAX_KBS;          // (k_wgrad_ts keeps the side / bias sums out of the MMAs)
   const bool ts = ts_shape && mode == 0;
   if (use_ts) *use_ts = ts;
   const int nb = ts ? 1 : ((nbtot >= 2 && 2 * KBS <= 512) ? 2 : 1);
@@ -705,7 +780,7 @@ static bool ww_plan(int M, int KB, int Nout, int nside, int lds, int mode, Wgrad
   const int R = ts ? WT_R : WW_R;
   const int raw = R * (p.npc + KB + lds) * 4;      // lds = 0 when no side columns are read
   p.raw_bytes = (raw + 127) & ~127;
-  p.img_bytes = ts ? KBS * 256 : (mode == 0 ? 3 : 1) * WW_R * (p.npc + ((KBS + 63) & ~63)) * 2;
+  p.img_bytes = ts ? KB * 256 : (mode == 0 ? 3 : 1) * WW_R * (p.npc + ((KBS + 63) & ~63)) * 2;
   const int budget = WW_SMEM_LIMIT - 1024 - 512;
   int nraw = 2, nimg = 2;
   if (nraw * p.raw_bytes + nimg * p.img_bytes > budget) return false;
@@ -791,8 +866,13 @@ extern "C" int msmp_wgrad_ws(const float* const* X, const int* ldx, const int* k
     attr_set = true;
   }
   dim3 grid(S, ny);
-  if (use_ts)
-    k_wgrad_ts<<<grid, WT_THREADS2, smem, stream>>>(p);
+  if (use_ts) {
+    alignas(64) CUtensorMap tm;
+    const int dy_tma = (lddy != 128 && tensor_map_2d(&tm, dY, lddy, Nout, M, 128, WT_R, false)) ? 1 : 0;
+    if (!dy_tma) memset(&tm, 0, sizeof(tm));
+    static const int flush = [] { const int f = ww_env("MSMP_WGRAD_TS_FLUSH", 8); return f < 1 ? 1 : f; }();      // chunks per accumulator period
+    k_wgrad_ts<<<grid, WT_THREADS2, smem, stream>>>(p, tm, dy_tma, flush);
+  }
   else if (mode == 0)
     k_wgrad_ws<0><<<grid, WW_THREADS, smem, stream>>>(p);
   else

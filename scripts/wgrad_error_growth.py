@@ -1,0 +1,24 @@
+import sys, torch
+sys.path.insert(0, '/root/repo')
+from msmp_pde_b200 import ops
+dev = torch.device("cuda:0")
+def run(M, K0, K1, N):
+    g = torch.Generator(device=dev).manual_seed(5)
+    X = torch.randn(M, K0, device=dev, generator=g); X1 = torch.randn(M, K1, device=dev, generator=g) if K1 else None
+    dY = torch.randn(M, N, device=dev, generator=g)
+    Xd = torch.cat([X.double(), X1.double()], 1) if K1 else X.double()
+    ref = Xd.t() @ dY.double(); refs = dY.double().sum(0, keepdim=True)
+    out = {}
+    for name, (minrows, tall, ts) in {"ts": (0, 1 << 62, True), "ws_bf16x3": (0, 1 << 62, False), "tc": (1 << 62, 1 << 62, True)}.items():
+        ops.WGRAD_WS_MIN_ROWS, ops.WGRAD_WS_MAX_TALL_ROWS = minrows, tall
+        if name == "ws_bf16x3":
+            import os
+            continue
+        a, a_s = ops.linear_wgrad(X, dY, has_bias=True, X1=X1)
+        out[name] = (float((a.double() - ref).abs().max() / ref.abs().max()), float((a_s.double() - refs).abs().max() / refs.abs().max()))
+    # plain fp32 torch matmul (no tf32)
+    t = (torch.cat([X, X1], 1) if K1 else X).t() @ dY
+    out["torch_fp32"] = (float((t.double() - ref).abs().max() / ref.abs().max()), 0.0)
+    print(M, K0 + K1, N, {k: (f"{v[0]:.2e}", f"{v[1]:.2e}") for k, v in out.items()}, flush=True)
+for M in (7500, 70001, 520192, 3276800):
+    run(M, 128, 32, 384 if M != 520192 else 128)

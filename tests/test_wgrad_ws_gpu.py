@@ -118,15 +118,48 @@ def test_wgrad_ws_bf16_mode(shape):
 
 
 def test_kernel_selection_policy():
-    """Small and very tall products go to k_wgrad_tc, the rest to k_wgrad_ws; both give the same gradient to fp32 accuracy."""
+    """Small products go to k_wgrad_tc, the rest to msmp_wgrad_ws (k_wgrad_ws; k_wgrad_ts for at most 192 operand columns,
+    which also takes the very tall LEM products; a tall product that k_wgrad_ts cannot take stays on k_wgrad_tc); the kernels
+    give the same gradient to fp32 accuracy."""
     from msmp_pde_b200 import ops
-    ops.WGRAD_WS_MIN_ROWS, ops.WGRAD_WS_MAX_TALL_ROWS = 1 << 16, 1 << 20
+    ops.WGRAD_WS_MIN_ROWS, ops.WGRAD_WS_MAX_TALL_ROWS = 1 << 16, 1 << 18
     assert not ops.wgrad_use_ws(6400, 256, 128, 4)
     assert ops.wgrad_use_ws(131072, 256, 128, 4)
-    assert not ops.wgrad_use_ws(25 * 131072, 160, 384, 1)
+    assert ops.wgrad_use_ws(25 * 131072, 160, 384, 1) == ops.WGRAD_TS          # LEM dG: k_wgrad_ts
+    assert ops.wgrad_use_ws(520192, 128, 128, 1) == ops.WGRAD_TS               # edge dW2: k_wgrad_ts
+    assert not ops.wgrad_use_ws(25 * 131072, 192, 128, 1)                      # 192 + side block > 192 columns: k_wgrad_tc
     assert ops.wgrad_use_ws(25 * 131072, 256, 128, 1)
+    # k_wgrad_ts (tall rule) against k_wgrad_tc and float64 on a strided three-block dY (tensor-map copies), ragged row count
+    ops.WGRAD_WS_MAX_TALL_ROWS = 1 << 16
+    X, X1, dY, side = _inputs(70001, 128, 32, 384, 0, seed=5)
+    assert ops.wgrad_use_ws(70001, 160, 384, 1) == ops.WGRAD_TS
+    a, a_s = ops.linear_wgrad(X, dY, has_bias=True, X1=X1)
+    ops.WGRAD_WS_MIN_ROWS = 1 << 30
+    b, b_s = ops.linear_wgrad(X, dY, has_bias=True, X1=X1)
+    ops.WGRAD_WS_MIN_ROWS, ops.WGRAD_WS_MAX_TALL_ROWS = 1 << 16, 1 << 18
+    rW, rWs = _ref(X, X1, dY, None, 0, True, False)
+    assert rel_err(a, rW) < 5e-6 and rel_err(a_s, rWs) < 5e-6
+    # k_wgrad_tc keeps a row range's whole sum in the tensor-core accumulator, whose truncating adds make the error grow like
+    # rows^1.5 per CTA (1e-5 of max|ref| here; scripts/wgrad_error_growth.py) -- the reason the tall products are not its
+    assert rel_err(b, rW) < 3e-5 and rel_err(b_s, rWs) < 5e-6
     X, X1, dY, side = _inputs(70000, 128, 64, 256, 4, seed=3)
     a, a_s = ops.linear_wgrad(X, dY, side=side, r=4, has_bias=True, X1=X1)              # k_wgrad_ws
     ops.WGRAD_WS_MIN_ROWS = 1 << 30
     b, b_s = ops.linear_wgrad(X, dY, side=side, r=4, has_bias=True, X1=X1)              # k_wgrad_tc
     assert rel_err(a, b) < 5e-6 and rel_err(a_s, b_s) < 5e-6
+
+
+@pytest.mark.parametrize("M", [70001, 520192, 25 * 131072])
+def test_wgrad_ts_error_does_not_grow_with_rows(M):
+    """k_wgrad_ts reads the tensor-core accumulator out every 8 chunks of 32 rows into a round-to-nearest fp32 sum, so its error
+    stays at the 2e-6 level of a short product however tall the operand is (LEM weight gradients of the C4 batch: 3.3 Mi rows,
+    where a single tensor-core accumulation chain per CTA is off by 4.6e-4 of max|ref| and an FFMA GEMM by 5e-6)."""
+    from msmp_pde_b200 import ops
+    if not ops.WGRAD_TS:
+        pytest.skip("MSMP_WGRAD_TS=0")
+    Nout = 128 if M == 520192 else 384
+    X, X1, dY, side = _inputs(M, 128, 32, Nout, 0, seed=5)
+    a, a_s = ops.linear_wgrad(X, dY, has_bias=True, X1=X1)
+    rW, rWs = _ref(X, X1, dY, None, 0, True, False)
+    assert rel_err(a, rW) < 5e-6
+    assert rel_err(a_s, rWs) < 1e-5          # plain fp32 column sums of up to 67 Ki rows per CTA
