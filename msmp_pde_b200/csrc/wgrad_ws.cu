@@ -766,7 +766,9 @@ static bool ww_plan(int M, int KB, int Nout, int nside, int lds, int mode, Wgrad
   // computed for its grid (one 128-column dY block per CTA) in BOTH modes, so that msmp_wgrad_ws_splits -- which sizes the
   // callers' partial buffers -- does not depend on the mode.
   static const bool ts_on = ww_env("MSMP_WGRAD_TS", 1) != 0;
-  const bool ts_shape = ts_on && KB <= WT_MAX_KBS;          // (k_wgrad_ts keeps the side / bias sums out of the MMAs)
+  // (k_wgrad_ts keeps the side / bias sums out of the MMAs: one add per element for a bias, a slow loop for side columns, so
+  // products with side columns -- the P | Q projection of the one-field models, 3.6 against 1.3 ms at 1 Mi rows -- stay on k_wgrad_ws)
+  const bool ts_shape = ts_on && KB <= WT_MAX_KBS && nside <= 1;
   const bool ts = ts_shape && mode == 0;
   if (use_ts) *use_ts = ts;
   const int nb = ts ? 1 : ((nbtot >= 2 && 2 * KBS <= 512) ? 2 : 1);
@@ -806,6 +808,10 @@ static bool ww_plan(int M, int KB, int Nout, int nside, int lds, int mode, Wgrad
   int s = M / (min_rows > rq ? min_rows : rq);
   if (s < 1) s = 1;
   if (s > max_s) s = max_s;
+  // k_wgrad_ws keeps a CTA's whole row range in the tensor-core accumulator, whose truncating adds make the error grow like
+  // rows^1.5 (see k_wgrad_ts): more, shorter row ranges than SMs from 1 Ki rows per CTA on (1 Mi-row products: 1024 CTAs)
+  static const int max_rows = ww_env("MSMP_WGRAD_WS_MAX_ROWS", 1024);
+  if (!ts_shape && max_rows > 0 && (M + s - 1) / s > max_rows) s = (M + max_rows - 1) / max_rows;
   int rps = (M + s - 1) / s;
   rps = (rps + rq - 1) / rq * rq;
   if (rps < rq) rps = rq;

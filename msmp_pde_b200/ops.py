@@ -111,7 +111,7 @@ def wgrad_use_ws(M: int, Kt: int, Nout: int, nside: int = 1) -> bool:
         # tall and narrow: msmp_wgrad_ws runs k_wgrad_ts (dY^T in tensor memory) for Kt <= 160 columns: LEM dL
         # product (3.3 Mi rows) 1.00 against 1.19 ms with k_wgrad_tc, LEM dG product (three dY blocks, fetched by tensor-map
         # copies) 2.94 against 3.53 ms, edge dW2 (520 Ki rows) 0.165 against 0.210 ms
-        return WGRAD_TS and Kt <= 160
+        return WGRAD_TS and Kt <= 160 and nside <= 1
     return True
 # Persistent (all-T-steps-in-one-launch) LEM kernels; False = one GEMM + one gate kernel per step.
 LEM_PERSISTENT = True
@@ -294,7 +294,7 @@ def linear_wgrad(X, dY, K=None, xswish=False, side=None, r=0, has_bias=False, dW
             part = ws.data_ptr()
             part_side = part + 4 * S * Kt * Nout
             out, out_side = dWt.data_ptr(), _p(dWside)
-        is_ts = WGRAD_TS and PRECISION != "bf16" and Kt <= 160      # the kernel msmp_wgrad_ws will pick
+        is_ts = WGRAD_TS and PRECISION != "bf16" and Kt <= 160 and nside <= 1      # the kernel msmp_wgrad_ws will pick
         with _timed("wgrad_ts" if is_ts else "wgrad_ws", 2.0 * M * Kt * Nout, 4.0 * (M * Kt + M * Nout)):
             check(lib.msmp_wgrad_ws(Xp, ldx, kx, xsw, n, dY.data_ptr(), _ld(dY), Nout, sb, lds, c0,
                                     r if side is not None else 0, int(has_bias), part, part_side, out, out_side,

@@ -22,3 +22,14 @@ def run(M, K0, K1, N):
     print(M, K0 + K1, N, {k: (f"{v[0]:.2e}", f"{v[1]:.2e}") for k, v in out.items()}, flush=True)
 for M in (7500, 70001, 520192, 3276800):
     run(M, 128, 32, 384 if M != 520192 else 128)
+# k_wgrad_ws (bf16-piece products, wide operands): rows per CTA capped at 1024 (MSMP_WGRAD_WS_MAX_ROWS)
+def run_ws(M):
+    g = torch.Generator(device=dev).manual_seed(6)
+    X = torch.randn(M, 128, device=dev, generator=g); X1 = torch.randn(M, 128, device=dev, generator=g)
+    dY = torch.randn(M, 128, device=dev, generator=g); side = torch.randn(M, 8, device=dev, generator=g)
+    ref = torch.cat([X.double(), X1.double()], 1).t() @ dY.double()
+    ops.WGRAD_WS_MIN_ROWS, ops.WGRAD_WS_MAX_TALL_ROWS = 0, 1 << 62
+    a, a_s = ops.linear_wgrad(X, dY, side=side, r=3, has_bias=True, X1=X1)
+    print("ws", M, 256, 128, f"{float((a.double() - ref).abs().max() / ref.abs().max()):.2e}", flush=True)
+for M in (131072, 1 << 20):
+    run_ws(M)
