@@ -16,4 +16,6 @@ run(131072, 128, 128, 128, 3, True)      # dW3, k_wgrad_ws
 run(131072, 128, 128, 128, 3, False)     # dW3, k_wgrad_tc
 run(520192, 128, 0, 128, 0, True)        # dW2
 run(520192, 128, 0, 128, 0, False)
-run(25 * 131072, 128, 32, 384, 0, False)  # LEM dG
+run(25 * 131072, 128, 32, 384, 0, False)  # LEM dG, k_wgrad_tc
+run(25 * 131072, 128, 32, 384, 0, True)   # LEM dG, k_wgrad_ts (dY^T in tensor memory)
+run(25 * 131072, 128, 32, 128, 0, True)   # LEM dL, k_wgrad_ts
