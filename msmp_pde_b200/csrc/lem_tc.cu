@@ -435,6 +435,10 @@ struct LemBwdParams {
 // TMEM columns of the backward kernel (256 allocated): acc1, acc2, and the dG2 / dG0 blocks of the current step
 // (stashed by the thread that computed them until their k-block of the acc2 GEMM is staged).
 constexpr uint32_t LB_ACC1 = 0, LB_ACC2 = 64, LB_S2 = 128, LB_S0 = 192;
+// Round 2: the other half of tensor memory holds Wz[:, :128]^T (tf32 hi at columns 256.., lo at 384..; lane = hidden channel,
+// column = gate channel k), copied once per launch from the packed images: the acc1 GEMM takes its A operand from tensor
+// memory and its 4 weight chunks per step (128 KiB of the 512 KiB streamed from L2, through a ring of only 3 stages) are gone.
+constexpr uint32_t LB_WZ_HI = 256, LB_WZ_LO = 384;
 // The backward epilogues are bound by memory latency (saved activations in, dG / dL out), not by issue slots: sixteen
 // epilogue warps (16 nodes per thread instead of 32) keep twice as many loads in flight.
 constexpr int LB_EPI_WARPS = 16;
@@ -451,16 +455,15 @@ __global__ void __launch_bounds__(LB_THREADS, 1) k_lem_bwd_tc(const LemBwdParams
   const int tid = threadIdx.x, warp = warp_index_uniform(), lane = tid & 31;
   const int row0 = blockIdx.x * LT_NODES;
   const size_t plane = (size_t)p.N * 128;
-  lem_init(m, 256);
+  lem_init(m, 512);
   uint64_t* acc_mid = &m.bars[17];
 
   if (warp == LB_EPI_WARPS) {
-    // ---- weight ring producer: per step Wz chunks 0..3, then W chunks 4..7 (dG1), 8..11 (dG2), 0..3 (dG0)
+    // ---- weight ring producer: per step W chunks 4..7 (dG1), 8..11 (dG2), 0..3 (dG0)   (Wz lives in tensor memory)
     const Ring rg{m.smB, &m.bars[0], &m.bars[8], m.nst};
     if (elect_one()) {
       uint32_t n = 0;
       for (int t = p.t_end - 1; t >= p.t_begin; --t) {
-        for (int j = 0; j < 4; ++j) ring_load<FAST>(rg, n++, p.Wzh_img + (size_t)j * 2 * (IMG_BYTES / 4));
         for (int j = 0; j < 12; ++j) ring_load<FAST>(rg, n++, p.Wh_img + (size_t)((j + 4) % 12) * 2 * (IMG_BYTES / 4));
       }
     }
@@ -471,7 +474,29 @@ __global__ void __launch_bounds__(LB_THREADS, 1) k_lem_bwd_tc(const LemBwdParams
     const uint32_t X = e.smS, Y = e.smS + LT_S_BYTES;
     for (int t = p.t_end - 1; t >= p.t_begin; --t) {
       bwd_ready_wait();                                         // dL in X
-      gemm_issue<FAST>(e, X, 4, LB_ACC1, false, e.acc);                 // acc1 = Wz[:, :128]^T dL^T
+      {                                                         // acc1 = Wz[:, :128]^T dL^T, A operand from tensor memory
+        tc_fence_after();
+        constexpr uint32_t IDESC = umma_idesc_tf32(128, LT_NODES, 0, 0);
+        const bool leader = elect_one();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t s_hi = X + j * 2 * LT_SCHUNK, s_lo = s_hi + LT_SCHUNK;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t dsh = umma_desc(s_hi + 32 * k, 16, 1024), dsl = umma_desc(s_lo + 32 * k, 16, 1024);
+            const uint32_t a_hi = e.tmem + LB_WZ_HI + 32 * j + 8 * k, a_lo = e.tmem + LB_WZ_LO + 32 * j + 8 * k;
+            if (leader) {
+              umma_tf32_ts(e.tmem + LB_ACC1, a_hi, dsh, IDESC, (j | k) ? 1u : 0u);
+              if (!FAST) {
+                umma_tf32_ts(e.tmem + LB_ACC1, a_lo, dsh, IDESC, 1u);
+                umma_tf32_ts(e.tmem + LB_ACC1, a_hi, dsl, IDESC, 1u);
+              }
+            }
+          }
+        }
+        if (leader) umma_commit(e.acc);
+        __syncwarp();
+      }
       bwd_ready_wait();                                         // dG1 in X, dG2 in Y
       gemm_issue<FAST>(e, X, 4, LB_ACC2, false, acc_mid);               // acc2  = W[128:256, :128]^T dG1^T   (X free afterwards)
       gemm_issue<FAST>(e, Y, 4, LB_ACC2, true, nullptr);                // acc2 += W[256:384, :128]^T dG2^T
@@ -501,6 +526,22 @@ __global__ void __launch_bounds__(LB_THREADS, 1) k_lem_bwd_tc(const LemBwdParams
       tc_fence_after();
     };
 
+    {  // Wz[:, :128]^T -> tensor memory: row c of k-chunk (warp >> 2) of the packed hi | lo images (already split)
+      const int jk = warp >> 2;
+      const float* img = p.Wzh_img + (size_t)jk * 2 * (IMG_BYTES / 4);
+      const uint32_t lane_base = e.tmem + ((uint32_t)(32 * (warp & 3)) << 16);
+#pragma unroll
+      for (int half = 0; half < (FAST ? 1 : 2); ++half) {
+#pragma unroll
+        for (int q = 0; q < 8; q += 2) {
+          const float4 w0 = ldg4(img + half * (IMG_BYTES / 4) + img_off(c, q) / 4);
+          const float4 w1 = ldg4(img + half * (IMG_BYTES / 4) + img_off(c, q + 1) / 4);
+          const float w8[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+          tmem_st8(lane_base + (half ? LB_WZ_LO : LB_WZ_HI) + 32 * jk + 4 * q, w8);
+        }
+      }
+      tmem_st_wait();
+    }
     float dyreg[LB_NPT], dzreg[LB_NPT];
 #pragma unroll
     for (int q = 0; q < LB_NPT; ++q) {
@@ -641,7 +682,7 @@ __global__ void __launch_bounds__(LB_THREADS, 1) k_lem_bwd_tc(const LemBwdParams
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(*m.tmem_slot, 256);
+  if (warp == 0) tmem_dealloc(*m.tmem_slot, 512);
 }
 
 }  // namespace msmp
