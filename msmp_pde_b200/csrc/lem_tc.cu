@@ -443,7 +443,8 @@ constexpr uint32_t LB_WZ_HI = 256, LB_WZ_LO = 384;
 // epilogue warps (16 nodes per thread instead of 32) keep twice as many loads in flight.
 constexpr int LB_EPI_WARPS = 16;
 constexpr int LB_NPT = LT_NODES / (LB_EPI_WARPS / 4);       // nodes per thread
-constexpr int LB_THREADS = 32 * LB_EPI_WARPS + 64;          // + ring producer warp + MMA warp
+constexpr int LB_THREADS = 32 * LB_EPI_WARPS + 128;         // + ring producer warp + MMA warp + two idle warps: a full warpgroup,
+                                                            // which hands its registers to the epilogue warps (setmaxnreg 40 / 104)
 
 __device__ __forceinline__ void bwd_ready_arrive() { asm volatile("bar.arrive 2, %0;" ::"n"(32 * LB_EPI_WARPS + 32) : "memory"); }
 __device__ __forceinline__ void bwd_ready_wait() { asm volatile("bar.sync 2, %0;" ::"n"(32 * LB_EPI_WARPS + 32) : "memory"); }
@@ -458,7 +459,10 @@ __global__ void __launch_bounds__(LB_THREADS, 1) k_lem_bwd_tc(const LemBwdParams
   lem_init(m, 512);
   uint64_t* acc_mid = &m.bars[17];
 
-  if (warp == LB_EPI_WARPS) {
+  if (warp >= LB_EPI_WARPS + 2) {
+    reg_dec<40>();
+  } else if (warp == LB_EPI_WARPS) {
+    reg_dec<40>();
     // ---- weight ring producer: per step W chunks 4..7 (dG1), 8..11 (dG2), 0..3 (dG0)   (Wz lives in tensor memory)
     const Ring rg{m.smB, &m.bars[0], &m.bars[8], m.nst};
     if (elect_one()) {
@@ -469,6 +473,7 @@ __global__ void __launch_bounds__(LB_THREADS, 1) k_lem_bwd_tc(const LemBwdParams
     }
     __syncwarp();
   } else if (warp == LB_EPI_WARPS + 1) {
+    reg_dec<40>();
     // ---- MMA issue (whole warp convergent, elected lane issues)
     Epi e = lem_epi(m);
     const uint32_t X = e.smS, Y = e.smS + LT_S_BYTES;
@@ -504,6 +509,7 @@ __global__ void __launch_bounds__(LB_THREADS, 1) k_lem_bwd_tc(const LemBwdParams
       gemm_issue<FAST>(e, X, 4, LB_ACC2, true, e.acc);                  // acc2 += W[0:128, :128]^T dG0^T
     }
   } else {
+    reg_inc<104>();
     Epi e = lem_epi(m);
     // epilogue ownership: thread = hidden channel c (TMEM lane), nodes [j0, j0 + LB_NPT): its carried dy / dz live in registers
     const int c = 32 * (warp & 3) + lane;
