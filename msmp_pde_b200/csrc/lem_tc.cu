@@ -80,9 +80,9 @@ template <bool FAST>
 __device__ __forceinline__ void ring_load(const Ring& rg, uint32_t i, const float* src) {
   const uint32_t s = i % rg.nst, use = i / rg.nst;
   if (use > 0) mbar_wait(&rg.bfree[s], (use - 1) & 1);            // MMAs that read this stage are complete
-  constexpr uint32_t NB = FAST ? IMG_BYTES : LT_STAGE_BYTES;
+  constexpr uint32_t NB = FAST ? IMG_BYTES : LT_STAGE_BYTES;      // = the stage size (reduced precision: hi image only)
   mbar_expect_tx(&rg.bfull[s], NB);
-  bulk_g2s(rg.smB + s * LT_STAGE_BYTES, src, NB, &rg.bfull[s]);
+  bulk_g2s(rg.smB + s * NB, src, NB, &rg.bfull[s]);
 }
 
 // MMA-issuing warp (all lanes, convergent): weight chunk in ring slot i (A, 128 channels x 32 k) times state k-chunk at s_img (B, 64 nodes x 32 k)
@@ -95,7 +95,7 @@ __device__ __forceinline__ void ring_mma(const Ring& rg, uint32_t i, uint32_t s_
 #endif
   tc_fence_after();
   constexpr uint32_t IDESC = umma_idesc_tf32(128, LT_NODES, 0, 0);
-  const uint32_t w_hi = smem_u32(rg.smB + s * LT_STAGE_BYTES), w_lo = w_hi + IMG_BYTES;
+  const uint32_t w_hi = smem_u32(rg.smB + s * (FAST ? IMG_BYTES : LT_STAGE_BYTES)), w_lo = w_hi + IMG_BYTES;
   const uint32_t s_hi = s_img, s_lo = s_img + LT_SCHUNK;
   const bool leader = elect_one();
 #pragma unroll
@@ -236,7 +236,10 @@ __device__ __forceinline__ void state_ready_wait() { asm volatile("bar.sync 2, 2
 template <bool FAST>
 __global__ void __launch_bounds__(LF_THREADS, 1) k_lem_fwd_tc(const LemFwdParams p) {
   extern __shared__ uint8_t smem_raw[];
-  const LemSmem m = lem_smem(smem_raw, 1, 5);
+  // (reduced precision: 16 KiB stages, so the same ring memory holds 8 of them -- the GEMM phases are bound by the refill
+  // round trip of the ring, not by the MMAs; the barrier arrays hold 8 stages)
+  LemSmem m = lem_smem(smem_raw, 1, 5);
+  if (FAST) m.nst = 8;
   const int tid = threadIdx.x, warp = warp_index_uniform(), lane = tid & 31;
   const int row0 = blockIdx.x * LT_NODES;
   const size_t plane = (size_t)p.N * 128;
@@ -452,7 +455,8 @@ __device__ __forceinline__ void bwd_ready_wait() { asm volatile("bar.sync 2, %0;
 template <bool FAST>
 __global__ void __launch_bounds__(LB_THREADS, 1) k_lem_bwd_tc(const LemBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
-  const LemSmem m = lem_smem(smem_raw, 2, 3);      // two state tiles (X, Y) + 3 ring stages
+  LemSmem m = lem_smem(smem_raw, 2, 3);      // two state tiles (X, Y) + 3 ring stages (reduced precision: 6 of 16 KiB)
+  if (FAST) m.nst = 6;
   const int tid = threadIdx.x, warp = warp_index_uniform(), lane = tid & 31;
   const int row0 = blockIdx.x * LT_NODES;
   const size_t plane = (size_t)p.N * 128;
