@@ -85,23 +85,29 @@ __device__ __forceinline__ void ring_load(const Ring& rg, uint32_t i, const floa
   bulk_g2s(rg.smB + s * NB, src, NB, &rg.bfull[s]);
 }
 
-// MMA-issuing warp (all lanes, convergent): weight chunk in ring slot i (A, 128 channels x 32 k) times state k-chunk at s_img (B, 64 nodes x 32 k)
+// MMA-issuing warp (all lanes, convergent): weight chunk in ring slot `slot` (A, 128 channels x 32 k) times state k-chunk at
+// s_img (B, 64 nodes x 32 k).  The warp's own instruction stream used to set the pace of every GEMM phase (~1.1 k cycles per
+// chunk whether it issued 12 MMAs or 4, scripts/lem_ticks.py): sixteen descriptors were assembled from scratch per chunk and
+// the slot came from a modulo by a run-time ring depth.  Now: one base descriptor per operand image and chunk, the k-steps and
+// the lo images are 32-bit adds on its address field (+2 units of 16 bytes per k-step; smem addresses stay below 2^18), and
+// the caller carries slot / phase counters.
 template <bool FAST>
-__device__ __forceinline__ void ring_mma(const Ring& rg, uint32_t i, uint32_t s_img, uint32_t tmem_d, bool accumulate) {
-  const uint32_t s = i % rg.nst, use = i / rg.nst;
-  mbar_wait(&rg.bfull[s], use & 1);                               // (bulk copies write through the async proxy)
+__device__ __forceinline__ void ring_mma(const Ring& rg, uint32_t slot, uint32_t phase, uint32_t s_img, uint32_t tmem_d,
+                                         bool accumulate) {
+  mbar_wait(&rg.bfull[slot], phase);                              // (bulk copies write through the async proxy)
 #ifdef MSMP_LEM_TICKS
   if (blockIdx.x == 0 && g_lem_chunk_tick >= 0 && g_lem_chunk_tick < 16) g_lem_dbg[16 + 2 * g_lem_chunk_tick] = clock64();
 #endif
   tc_fence_after();
   constexpr uint32_t IDESC = umma_idesc_tf32(128, LT_NODES, 0, 0);
-  const uint32_t w_hi = smem_u32(rg.smB + s * (FAST ? IMG_BYTES : LT_STAGE_BYTES)), w_lo = w_hi + IMG_BYTES;
-  const uint32_t s_hi = s_img, s_lo = s_img + LT_SCHUNK;
+  const uint64_t dw = umma_desc(smem_u32(rg.smB + slot * (FAST ? IMG_BYTES : LT_STAGE_BYTES)), 16, 1024);
+  const uint64_t ds = umma_desc(s_img, 16, 1024);
+  const uint32_t dw_lo = (uint32_t)dw, dw_hi = (uint32_t)(dw >> 32), ds_lo = (uint32_t)ds, ds_hi = (uint32_t)(ds >> 32);
   const bool leader = elect_one();
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    const uint64_t dwh = umma_desc(w_hi + 32 * k, 16, 1024), dwl = umma_desc(w_lo + 32 * k, 16, 1024);
-    const uint64_t dsh = umma_desc(s_hi + 32 * k, 16, 1024), dsl = umma_desc(s_lo + 32 * k, 16, 1024);
+    const uint64_t dwh = ((uint64_t)dw_hi << 32) | (dw_lo + 2 * k), dwl = ((uint64_t)dw_hi << 32) | (dw_lo + 2 * k + (IMG_BYTES >> 4));
+    const uint64_t dsh = ((uint64_t)ds_hi << 32) | (ds_lo + 2 * k), dsl = ((uint64_t)ds_hi << 32) | (ds_lo + 2 * k + (LT_SCHUNK >> 4));
     if (leader) {
       umma_tf32(tmem_d, dwh, dsh, IDESC, (accumulate || k) ? 1u : 0u);
       if (!FAST) {
@@ -110,7 +116,7 @@ __device__ __forceinline__ void ring_mma(const Ring& rg, uint32_t i, uint32_t s_
       }
     }
   }
-  if (leader) umma_commit(&rg.bfree[s]);
+  if (leader) umma_commit(&rg.bfree[slot]);
   __syncwarp();
 #ifdef MSMP_LEM_TICKS
   if (blockIdx.x == 0 && g_lem_chunk_tick >= 0 && g_lem_chunk_tick < 16) g_lem_dbg[17 + 2 * g_lem_chunk_tick++] = clock64();
@@ -122,7 +128,8 @@ struct Epi {
   Ring rg;
   uint64_t* acc;
   uint32_t nacc;       // accumulator barrier phases consumed
-  uint32_t nchunk;     // ring chunks consumed (MMA thread)
+  uint32_t slot;       // ring slot of the next chunk (MMA warp)
+  uint32_t sphase;     // ... and its barrier phase
   uint32_t smS;        // shared::cta address of the state tile
   uint32_t tmem;
 };
@@ -134,9 +141,13 @@ template <bool FAST>
 __device__ __forceinline__ void gemm_issue(Epi& e, uint32_t sbase, uint32_t nchunks, uint32_t dcol, bool acc_first,
                                            uint64_t* done) {
   tc_fence_after();
-  for (uint32_t j = 0; j < nchunks; ++j)
-    ring_mma<FAST>(e.rg, e.nchunk + j, sbase + (j & 3) * 2 * LT_SCHUNK, e.tmem + dcol + LT_NODES * (j >> 2), acc_first || (j & 3) != 0);
-  e.nchunk += nchunks;
+  for (uint32_t j = 0; j < nchunks; ++j) {
+    ring_mma<FAST>(e.rg, e.slot, e.sphase, sbase + (j & 3) * 2 * LT_SCHUNK, e.tmem + dcol + LT_NODES * (j >> 2), acc_first || (j & 3) != 0);
+    if (++e.slot == e.rg.nst) {
+      e.slot = 0;
+      e.sphase ^= 1;
+    }
+  }
   if (done != nullptr && elect_one()) umma_commit(done);
   __syncwarp();
 }
@@ -200,7 +211,7 @@ __device__ __forceinline__ Epi lem_epi(const LemSmem& m) {
   Epi e;
   e.rg = Ring{m.smB, &m.bars[0], &m.bars[8], m.nst};
   e.acc = &m.bars[16];
-  e.nacc = e.nchunk = 0;
+  e.nacc = e.slot = e.sphase = 0;
   e.smS = smem_u32(m.smS);
   e.tmem = __shfl_sync(0xffffffffu, *m.tmem_slot, 0);
   return e;
