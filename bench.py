@@ -449,7 +449,7 @@ KERNEL_OF_OP = {"wgrad_ws": "k_wgrad_ws", "wgrad_tc": "k_wgrad_tc",
 # --clock-control none --profile-from-start off python scripts/ncu_step.py c4 8` -> profiles/r2_launches_c4_step.csv
 # (298 launches).  DRAM counters do not see operands that are still in the 126 MB L2 (the node GEMMs read what the previous
 # launch wrote: 164 MB per launch against 4 M (K + N) = 184 MB of algorithmic bytes).
-NCU_TRAFFIC_BYTES_PER_LAUNCH = {"linear_tc": 163.4e6, "lem_tc_fwd": 10.595e9, "lem_tc_bwd": 18.267e9, "wgrad_ts": 697.4e6,
+NCU_TRAFFIC_BYTES_PER_LAUNCH = {"linear_tc": 163.4e6, "lem_tc_fwd": 10.595e9, "lem_tc_bwd": 18.318e9, "wgrad_ts": 703.0e6,
                                 "wgrad_ws": 222.8e6, "edge_ws_fwd": 490.6e6, "edge_ws_bwd": 1422.3e6, "segment_reduce": 316.8e6}
 
 
