@@ -1,3 +1,5 @@
+"""Error of the weight-gradient kernels against float64 as the row count grows (unit-variance data): the tensor core's truncating
+fp32 accumulation makes a single accumulation chain per CTA drift like rows^1.5 (k_wgrad_tc), k_wgrad_ts / k_wgrad_ws bound the chain."""
 import sys, torch
 sys.path.insert(0, '/root/repo')
 from msmp_pde_b200 import ops
