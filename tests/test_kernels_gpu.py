@@ -518,3 +518,40 @@ def test_decoder_fwd_bwd_vs_conv1d(dev, C, N):
     assert rel_err(dh, hd.grad.reshape(N, C * 128)) < TOL
     dW_ref = torch.cat([p.grad.reshape(-1) for p in p64])
     assert rel_err(dW, dW_ref) < 2 * TOL
+
+
+@pytest.mark.parametrize("M,segs,Nout,opts", [
+    (38000, [128], 128, dict(act=True, res=True, aswish=[1])),
+    (38001, [128, 128], 128, dict(bias=True, side=3)),
+    (37999, [64, 32, 32], 256, dict(zmul=True, bias=True)),
+    (128 * 296, [32], 128, dict()),
+])
+def test_linear_large_m_paths_vs_float64(dev, M, segs, Nout, opts):
+    """The persistent large-M node GEMM (k_linear_ts: >= 296 tiles; activation operand in tensor memory, ragged last row
+    tile, one to three A segments, every epilogue option) against float64 math."""
+    from msmp_pde_b200 import ops
+    g = torch.Generator().manual_seed(M + Nout)
+    A = [torch.randn(M, k, generator=g).to(dev) for k in segs]
+    K = sum(segs)
+    Wt = (torch.randn(K, Nout, generator=g) / K ** 0.5).to(dev)
+    bias = torch.randn(Nout, generator=g).to(dev) if opts.get("bias") else None
+    r = opts.get("side", 0)
+    side = torch.randn(M, 8, generator=g).to(dev) if r else None
+    Ws = torch.randn(8, Nout, generator=g).to(dev) if r else None
+    Z = torch.randn(M, Nout, generator=g).to(dev) if opts.get("zmul") else None
+    R = torch.randn(M, Nout, generator=g).to(dev) if opts.get("res") else None
+    asw = opts.get("aswish", [0] * len(segs))
+    y = ops.linear_fwd(A, Wt, bias=bias, side=side, r=r, Wside=Ws, Zmul=Z, act=bool(opts.get("act")), R=R, aswish=asw)
+    Ad = torch.cat([_sw(a.double()) if s else a.double() for a, s in zip(A, asw)], 1)
+    ref = Ad @ Wt.double()
+    if bias is not None:
+        ref = ref + bias.double()
+    if r:
+        ref = ref + side.double()[:, :r] @ Ws.double()[:r]
+    if Z is not None:
+        ref = ref * _dsw(Z.double())
+    if opts.get("act"):
+        ref = _sw(ref)
+    if R is not None:
+        ref = ref + R.double()
+    assert rel_err(y, ref) < TOL
