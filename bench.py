@@ -425,6 +425,11 @@ def run_ours(args):
                                         "section 8 lists them and the measured tolerance); `value` above is the fp32-parity mode")
             out["layer_c5"] = [_layer_c5(1 << 20, 6, "band", dev), _layer_c5(1 << 20, 6, "random", dev),
                                _layer_c5(1 << 20, 16, "random", dev)]
+            try:        # the largest size of the sweep that leaves head room in 180 GB (per-edge tensors: 4 x 12.9 GB)
+                out["layer_c5"].append(_layer_c5(1 << 22, 6, "random", dev, reps=3))
+            except torch.OutOfMemoryError as exc:
+                out["layer_c5"].append({"nodes": 1 << 22, "in_degree": 6, "error": str(exc)[:120]})
+                torch.cuda.empty_cache()
             out["scatter_hbm"] = scatter_bandwidth(dev)
             out["message_hbm"] = message_bandwidth(dev)
             if not args.no_cpu_baseline:

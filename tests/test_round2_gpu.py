@@ -344,3 +344,41 @@ def test_prefetched_inputs_equal_direct_load():
         losses.append(out)
     assert losses[0] == losses[1]
     assert losses[0][0] != losses[0][1]
+
+
+@pytest.mark.parametrize("n_nodes,degree", [(1 << 22, 6), (1 << 21, 16)])
+def test_c5_multi_million_node_layer_slices_vs_oracle(n_nodes, degree):
+    """BASELINE config 5 beyond 1 Mi nodes: one GNN_Layer(128,128,128,25,1) forward + backward on 4 Mi nodes x 6 and 2 Mi nodes
+    x 16 in-neighbours (25 / 33 Mi edges: the per-edge tensors hold 3.2 / 4.3 G floats, past 32-bit element offsets).  The
+    float64 oracle cannot run the whole graph in seconds, but the layer is local to a graph (messages stay inside a graph,
+    InstanceNorm is per graph), so the graphs at the start, in the middle and at the END of the node / edge range are run
+    through the oracle on their own and must equal the corresponding rows of the full run: outputs and input gradients."""
+    from msmp_pde_b200 import layers, synth
+    from oracle import models as om
+    dev = torch.device("cuda:0")
+    npg = 2048
+    g = synth.large_graph(n_nodes, degree, topology="random", nodes_per_graph=npg, seed=5)
+    torch.manual_seed(0)
+    layer = layers.GNN_Layer(128, 128, 128, 25, 1).to(dev)
+    ref = om.GNN_Layer(128, 128, 128, 25, 1).double()
+    ref.load_state_dict({k: v.double().cpu() for k, v in layer.state_dict().items()})
+    wsum = torch.randn(n_nodes, 128, generator=torch.Generator().manual_seed(1))       # d loss / d out
+    t = {k: v.to(dev) for k, v in g.items()}
+    x = t["x"].clone().requires_grad_(True)
+    out = layer(x, t["u"], t["pos"], t["variables"], t["edge_index"], t["batch"])
+    (out * wsum.to(dev)).sum().backward()
+    torch.cuda.synchronize()
+    n_graphs = n_nodes // npg
+    src, dst = g["edge_index"]
+    for gi in (0, n_graphs // 2 - 1, n_graphs - 2):
+        lo, hi = gi * npg, (gi + 2) * npg                      # two neighbouring graphs
+        e0, e1 = lo * degree, hi * degree                      # edges are sorted by destination, `degree` per node
+        assert int(dst[e0]) == lo and int(dst[e1 - 1]) == hi - 1
+        assert int(src[e0:e1].min()) >= lo and int(src[e0:e1].max()) < hi
+        xs = g["x"][lo:hi].double().requires_grad_(True)
+        outr = ref(xs, g["u"][lo:hi].double(), g["pos"][lo:hi].double(), g["variables"][lo:hi].double(),
+                   g["edge_index"][:, e0:e1] - lo, g["batch"][lo:hi] - gi)
+        (outr * wsum[lo:hi].double()).sum().backward()
+        assert rel_err(out[lo:hi], outr) < OUT_TOL, gi
+        assert rel_err(x.grad[lo:hi], xs.grad) < GRAD_TOL, gi
+    assert bool(torch.isfinite(out).all()) and bool(torch.isfinite(x.grad).all())
