@@ -255,6 +255,39 @@ int msmp_adamw_run(const void* jobs_dev, const void* chunks_dev, int nchunks, co
  * error arrives as a float pair (hi + lo) -- the last two elements of the all-reduced gradient bucket. */
 int msmp_loss_scalars(const float* sse_hi_lo, double* loss, float* gscale, cudaStream_t stream);
 
+/* Summed squared error of the training criterion and its gradient (experiments/train_helper.py:126,138:
+ * MSELoss(reduction='sum') on float64 labels, loss = sqrt of it): sse = sum_i (double(pred[i]) - y[i])^2 over n elements,
+ * deterministic (fixed blocks, fixed summation trees); sse_hi_lo (may be NULL) receives the same value split exactly into a
+ * float pair (the two trailing elements of the gradient bucket).  workspace: msmp_sse_workspace(n) bytes.
+ * msmp_sse_bwd: dpred[i] = float(2 * g * (double(pred[i]) - y[i])), g a device scalar (NULL = 1). */
+size_t msmp_sse_workspace(size_t n);
+int msmp_sse_fwd(const float* pred, const double* y, size_t n, void* workspace, size_t ws_bytes, double* sse,
+                 float* sse_hi_lo, cudaStream_t stream);
+int msmp_sse_bwd(const float* pred, const double* y, const double* g, size_t n, float* dpred, cudaStream_t stream);
+
+/* ---- input assembly of a forward pass ------------------------------------------------------------------------------
+ * msmp_node_features: the per-forward constant node inputs every layer of the stack shares (the u_i - u_j, pos_i - pos_j
+ * and variables operands of message(), experiments/models_gnn.py:70-75): upad[n][0..ldu) = [u[n][0..F_u) | 0] and
+ * side[n][0..8) = [pos_x[n], variables[n][0..V), 0...]; all fp32, u / variables contiguous [N,F_u] / [N,V], ldu % 4 == 0.
+ * msmp_lem_inputs: the zero-padded input slab inp[t][n][0..32) of the LEM recurrence (I_t of models_gnn2D.py:421-433,
+ * models_gnn.py:1357-1360); column c < ncols is described by cols[c] (HOST array): STATIC = src[n*ld + off], TIME =
+ * src[n*ld + off + t] (src fp32), CLOCK = (float)(clock[t] + node_t[n]) evaluated in double (cumsum(dt)_t + pos_t). */
+#define MSMP_LEM_MAX_COLS 8
+#define MSMP_LEM_COL_STATIC 0
+#define MSMP_LEM_COL_TIME 1
+#define MSMP_LEM_COL_CLOCK 2
+typedef struct msmp_lem_col {
+  const void* src;
+  int ld;
+  int off;
+  int kind;
+  int reserved;
+} msmp_lem_col;
+int msmp_lem_inputs(const msmp_lem_col* cols, int ncols, const double* clock, const double* node_t, int T, int N,
+                    float* inp, cudaStream_t stream);
+int msmp_node_features(const float* u, int F_u, const float* pos_x, const float* variables, int V, int N, float* upad,
+                       int ldu, float* side, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

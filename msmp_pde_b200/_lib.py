@@ -80,6 +80,11 @@ _SIGS = {
     "msmp_adamw_hyper_floats": (I, []),
     "msmp_adamw_run": (I, [P, P, I, P, P, P]),
     "msmp_loss_scalars": (I, [P, P, P, P]),
+    "msmp_lem_inputs": (I, [P, I, P, P, I, I, P, P]),
+    "msmp_node_features": (I, [P, I, P, P, I, I, P, I, P, P]),
+    "msmp_sse_workspace": (S, [S]),
+    "msmp_sse_fwd": (I, [P, P, S, P, S, P, P, P]),
+    "msmp_sse_bwd": (I, [P, P, P, S, P, P]),
     "msmp_lem_gate_z": (I, [P, P, F, P, P, I, P]),
     "msmp_lem_gate_y": (I, [P, P, P, P, I, P]),
     "msmp_lem_bwd_y": (I, [P, P, P, P, F, P, P, I, P]),

@@ -88,31 +88,53 @@ __global__ void __launch_bounds__(256) k_unpack(const UnpackJob* __restrict__ jo
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   for (int ti = blockIdx.x; ti < tn * tk; ti += gridDim.x) {
     const int n0 = (ti % tn) << 5, k0 = (ti / tn) << 5;
+    // the four rows (k0 + ty + 8 q) of this thread are walked together: four independent chains of loads per split step
+    // (a row at a time left a thread with one chain of nsplit dependent rounds: 67 us alone at the end of the C2 step);
+    // every element is still summed in split order, so the result does not depend on the grouping
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    const int n = n0 + tx;
+    if (!j.zero && n < j.rows) {
+      const float* s0[4];
+      bool ok[4];
 #pragma unroll
-    for (int y = ty; y < 32; y += 8) {
-      const int k = k0 + y, n = n0 + tx;
-      float v = 0.f;
-      if (!j.zero && k < j.cols && n < j.rows) {
-        const float* s0 = j.src0 + (size_t)k * j.ld0 + n;
-        int s = 0;
-        for (; s + 4 <= j.nsplit; s += 4) {          // four loads in flight, added in split order
-          const float a = s0[(size_t)s * j.sstride0], b = s0[(size_t)(s + 1) * j.sstride0];
-          const float c = s0[(size_t)(s + 2) * j.sstride0], d = s0[(size_t)(s + 3) * j.sstride0];
-          v += a;
-          v += b;
-          v += c;
-          v += d;
+      for (int q = 0; q < 4; ++q) {
+        const int k = k0 + ty + 8 * q;
+        ok[q] = k < j.cols;
+        s0[q] = j.src0 + (size_t)(ok[q] ? k : k0) * j.ld0 + n;
+      }
+      int s = 0;
+      for (; s + 2 <= j.nsplit; s += 2) {
+        float a[4], b[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          a[q] = ok[q] ? s0[q][(size_t)s * j.sstride0] : 0.f;
+          b[q] = ok[q] ? s0[q][(size_t)(s + 1) * j.sstride0] : 0.f;
         }
-        for (; s < j.nsplit; ++s) v += s0[(size_t)s * j.sstride0];
-        if (j.src1) {
-          const float* s1 = j.src1 + (size_t)k * j.ld1 + n;
-          float w = 0.f;
-          for (int q = 0; q < j.nsplit; ++q) w += s1[(size_t)q * j.sstride1];
-          v += j.sign1 * w;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          v[q] += a[q];
+          v[q] += b[q];
         }
       }
-      tile[y][tx] = v;
+      if (s < j.nsplit) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[q] += ok[q] ? s0[q][(size_t)s * j.sstride0] : 0.f;
+      }
+      if (j.src1) {
+        float w[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int t = 0; t < j.nsplit; ++t) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int k = k0 + ty + 8 * q;
+            w[q] += ok[q] ? j.src1[(size_t)k * j.ld1 + n + (size_t)t * j.sstride1] : 0.f;
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[q] += j.sign1 * w[q];
+      }
     }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) tile[ty + 8 * q][tx] = v[q];
     __syncthreads();
 #pragma unroll
     for (int y = ty; y < 32; y += 8) {

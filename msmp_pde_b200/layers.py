@@ -61,6 +61,11 @@ class NodeFeatures:
             raise ValueError("at most 7 equation variables supported")
         dev = u.device
         self.F_u, self.V, self.N = F_u, V, N
+        if u.is_cuda and V >= 1 and all(t.dtype == torch.float32 for t in (u, pos_x, variables)):
+            # one launch (msmp_node_features) instead of two fills and three slice copies
+            self.upad, self.side = ops.node_features(u.contiguous(), pos_x.reshape(N, 1).contiguous(), variables.contiguous(),
+                                                     pad32(F_u))
+            return
         self.upad = torch.zeros(N, pad32(F_u), dtype=torch.float32, device=dev)
         self.upad[:, :F_u] = u
         self.side = torch.zeros(N, SIDE_LD, dtype=torch.float32, device=dev)

@@ -44,15 +44,20 @@ def use_persistent(ninp: int) -> bool:
     return ops.GEMM_MODE == "tc" and ops.LEM_PERSISTENT and pad32(ninp) == 32 and ninp <= 8
 
 
-def lem_forward(inputs, bias, bias_lin_z, y0, z0, dt, packs):
+def lem_forward(inputs, bias, bias_lin_z, y0, z0, dt, packs, ninp=None):
     """All T steps.  Returns (inp [T,N,32k] zero-padded inputs, Y, Z [T+1,N,128] with slab 0 = initial state, gates,
     persistent).  tensor-core mode: one persistent kernel (msmp_lem_tc_fwd); otherwise one msmp_linear_fwd + one fused
-    gate kernel per GEMM and step."""
-    T, N, ninp = inputs.shape
+    gate kernel per GEMM and step.  ``ninp`` < inputs.shape[2] = pad32(ninp): the slab arrives zero padded already
+    (ops.lem_inputs) and is used as it is."""
+    T, N, width = inputs.shape
+    ninp = width if ninp is None else ninp
     dev = inputs.device
     ip = pad32(ninp)
-    inp = torch.zeros(T, N, ip, dtype=torch.float32, device=dev)
-    inp[:, :, :ninp] = inputs
+    if width == ip and inputs.dtype == torch.float32 and inputs.is_contiguous():
+        inp = inputs
+    else:
+        inp = torch.zeros(T, N, ip, dtype=torch.float32, device=dev)
+        inp[:, :, :ninp] = inputs
     Wt, Wzt, Wh, Wzh, Wt_h, Wzt_h, Wt_in, Wzt_in = packs
     Y = torch.empty(T + 1, N, H, dtype=torch.float32, device=dev)
     Z = torch.empty(T + 1, N, H, dtype=torch.float32, device=dev)
@@ -148,9 +153,10 @@ class _LEMFn(torch.autograd.Function):
     LEM / LEMS consume, models_gnn.py:340-342,354-357)."""
 
     @staticmethod
-    def forward(ctx, inputs, weights, weights_lin_z, bias, bias_lin_z, y0, z0, dt, packs, last_only, gsink=None):
-        T, N, ninp = inputs.shape
-        inp, Y, Z, gates, persistent = lem_forward(inputs, bias, bias_lin_z, y0, z0, dt, packs)
+    def forward(ctx, inputs, weights, weights_lin_z, bias, bias_lin_z, y0, z0, dt, packs, last_only, gsink=None, ninp=None):
+        T, N, width = inputs.shape
+        ninp = width if ninp is None else ninp
+        inp, Y, Z, gates, persistent = lem_forward(inputs, bias, bias_lin_z, y0, z0, dt, packs, ninp)
         ctx.save_for_backward(inp, Y, Z, gates)
         ctx.dt, ctx.ninp, ctx.packs, ctx.persistent, ctx.last_only = dt, ninp, packs, persistent, last_only
         ctx.gsink = gsink
@@ -166,10 +172,10 @@ class _LEMFn(torch.autograd.Function):
         dWt, dWzt, dbias, dbz, dy, dz, joined = lem_backward(inp, Y, Z, gates, gY, gZ, ctx.dt, ctx.packs, ctx.persistent,
                                                              ctx.last_only, gs)
         if not joined:
-            return None, None, None, None, None, dy, dz, None, None, None, None
+            return None, None, None, None, None, dy, dz, None, None, None, None, None
         dW = torch.cat([dWt[:H].t(), dWt[H:H + ninp].t()], 1)
         dWz = torch.cat([dWzt[:H].t(), dWzt[H:H + ninp].t()], 1)
-        return None, dW, dWz, dbias[0], dbz[0], dy, dz, None, None, None, None
+        return None, dW, dWz, dbias[0], dbz[0], dy, dz, None, None, None, None, None
 
 
 class LEMcuda(nn.Module):
@@ -206,13 +212,19 @@ class LEMcuda(nn.Module):
         if not input.is_cuda:
             raise RuntimeError("msmp_pde_b200 LEM runs on CUDA only (no CPU fallback)")
         x = input.detach().float().contiguous()
+        # a slab assembled by ops.lem_inputs arrives zero padded to 32 columns and says how many of them are inputs
+        padded = getattr(input, "_msmp_lem_ninp", None)
+        if padded is not None and (padded != self.ninp or x.shape[2] != pad32(self.ninp)):
+            raise ValueError("padded LEM input slab does not match this module's ninp")
+        if padded is None and x.shape[2] != self.ninp:
+            raise ValueError(f"LEM input has {x.shape[2]} features, the module expects {self.ninp}")
         if states is None:
             y = x.new_zeros(x.size(1), self.nhid)
             z = x.new_zeros(x.size(1), self.nhid)
         else:
             y, z = states[0].float().contiguous(), states[1].float().contiguous()
         return _LEMFn.apply(x, self.weights, self.weights_lin_z, self.bias, self.bias_lin_z, y, z, self.dt,
-                            self.packs(), last_only, self.__dict__.get("_msmp_gsink"))
+                            self.packs(), last_only, self.__dict__.get("_msmp_gsink"), self.ninp)
 
 
 class LEM(nn.Module):

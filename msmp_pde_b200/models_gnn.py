@@ -13,8 +13,9 @@ from torch import nn
 
 from .graph import get_topology
 from .layers import GNN_Layer, GNN_LayerLin, H, NodeFeatures, Swish, gate_blend, gated_pair, prepare_packs  # noqa: F401 (re-exported)
-from .lem import LEM, LEMS, LEMcuda  # noqa: F401 (re-exported)
-from .solver import (cumulative_dt, decode, linear_act, make_decoder, mlp2, pad_cols, require_cuda, variables_1field)
+from . import ops
+from .lem import LEM, LEMS, LEMcuda, use_persistent  # noqa: F401 (re-exported)
+from .solver import (cumulative_dt, decode, linear_act, make_decoder, ops_raw_output, mlp2, pad_cols, require_cuda, variables_1field)
 
 
 class _LSTMNoTF32Fn(torch.autograd.Function):
@@ -118,15 +119,25 @@ class _Solver1F(nn.Module):
         pos_x = pos[:, 1][:, None] / self.pde.L
         pos_t = pos[:, 0][:, None] / self.pde.tmax
         variables = variables_1field(data, pos_t, self.eq_variables)
-        u = u_in.float()
-        feat = NodeFeatures(u, pos_x.float(), variables.float())
+        u = u_in.float().contiguous()
+        pos_xf, variables_f = pos_x.float(), variables.float()
+        feat = NodeFeatures(u, pos_xf, variables_f)
         topo = get_topology(data.edge_index, data.batch, u.shape[0])
 
         if self.encoder == "mlp":
             node_input = pad_cols(torch.cat((u_in, pos_x, variables), -1))
             h = mlp2(node_input, self.embedding_mlp)
+        elif self.encoder != "lstm" and use_persistent(2 + variables.shape[1]):
+            # I_t = [pos_x, u[:, t], variables]  (models_gnn.py:1357-1360), written as the recurrence's zero-padded
+            # [T, N, 32] slab by one launch
+            T, V = u.shape[1], variables.shape[1]
+            cols = [("static", pos_xf, 0), ("time", u, 0)] + [("static", variables_f, k) for k in range(V)]
+            lem_in = ops.lem_inputs(T, u.shape[0], cols)
+            lem_in._msmp_lem_ninp = 2 + V
+            h = self.embedding_lem(lem_in)
+            if self.lem_mlp:
+                h = mlp2(h, self.lemoutput_mlp)
         else:
-            # I_t = [pos_x, u[:, t], variables]  (models_gnn.py:1357-1360)
             T = u.shape[1]
             static = torch.cat((pos_x, variables), -1).float()
             lem_in = torch.empty(T, u.shape[0], 2 + variables.shape[1], dtype=torch.float32, device=u.device)
@@ -151,10 +162,10 @@ class _Solver1F(nn.Module):
         if self.diff_only:             # MSSMP_PDE_Solver_sub returns diff (models_gnn.py:1676-1680)
             out = decode(h, self.output_mlp, torch.zeros_like(u), torch.ones(self.time_window, dtype=torch.float32, device=h.device), 1,
                          self.time_window)
-            return out.to(u_in.dtype)
+            return out if ops_raw_output() else out.to(u_in.dtype)
         dt = cumulative_dt(self.pde, self.time_window, h.device)
         out = decode(h, self.output_mlp, u, dt, 1, self.time_window)     # models_gnn.py:278-279
-        return out.to(u_in.dtype)
+        return out if ops_raw_output() else out.to(u_in.dtype)
 
 
 class MP_PDE_Solver(_Solver1F):
@@ -219,8 +230,13 @@ class MSSMP_PDE_Solver(nn.Module):
         return 'GNN'
 
     def forward(self, data) -> torch.Tensor:
-        scale = self.scale(data)
-        diff = self.diff(data)
+        from . import ops
+        raw, ops.RAW_OUTPUT = ops.RAW_OUTPUT, False          # the blend below is the reference's arithmetic in the input dtype
+        try:
+            scale = self.scale(data)
+            diff = self.diff(data)
+        finally:
+            ops.RAW_OUTPUT = raw
         u = data.x
         dt = torch.cumsum(torch.ones(1, self.time_window, dtype=u.dtype, device=u.device) * self.pde.dt, dim=1)
         return (1 - scale) * u[:, -1:].expand(-1, self.time_window) + dt * (scale * diff)

@@ -10,9 +10,10 @@ from torch import nn
 
 from .graph import get_topology
 from .layers import GNN_Layer, GNN_LayerLin, H, NodeFeatures, Swish, gate_blend, gated_pair, prepare_packs  # noqa: F401
-from .lem import LEM, LEMS  # noqa: F401
+from . import ops
+from .lem import LEM, LEMS, use_persistent  # noqa: F401
 from .models_gnn import LSTM  # noqa: F401
-from .solver import decode, linear_act, make_decoder, mlp2, pad_cols, require_cuda
+from .solver import decode, linear_act, make_decoder, ops_raw_output, mlp2, pad_cols, require_cuda
 
 
 def unflatten_u(u: torch.Tensor, time_window: int):
@@ -74,6 +75,15 @@ class _Solver2F(nn.Module):
             lem, linears = None, [self.embedding_mlp[0], self.embedding_mlp[2]]
         prepare_packs(self, layers, lem, linears + [self.double_mlp[0]])
 
+    def _clock(self, device):
+        """(cumsum(dt) in float64 [1, tw], the same rounded to float32): constants of the model, built once per device."""
+        c = self.__dict__.get("_msmp_clock")
+        if c is None or c[0].device != device:
+            dt64 = torch.cumsum(torch.ones(1, self.time_window, dtype=torch.float64, device=device) * float(self.pde.dt), dim=1)
+            c = (dt64, dt64.float())
+            self.__dict__["_msmp_clock"] = c
+        return c
+
     def forward(self, data) -> torch.Tensor:
         tw = self.time_window
         u_in = data.x
@@ -87,16 +97,23 @@ class _Solver2F(nn.Module):
             variables = torch.cat((variables, data.a / self.eq_variables["a"]), -1)
         if "b" in self.eq_variables:          # sic: data.a also feeds the 'b' column (models_gnn2D.py:419)
             variables = torch.cat((variables, data.a / self.eq_variables["b"]), -1)
-        u = u_in.float()
+        u = u_in.float().contiguous()
         N = u.shape[0]
-        feat = NodeFeatures(u, pos_x.float(), variables.float())
+        pos_xf, variables_f = pos_x.float(), variables.float()
+        feat = NodeFeatures(u, pos_xf, variables_f)
         topo = get_topology(data.edge_index, data.batch, N)
-        dt64 = torch.cumsum(torch.ones(1, tw, dtype=torch.float64, device=u.device) * float(self.pde.dt), dim=1)
-        dt = dt64.float()
+        dt64, dt = self._clock(u.device)
 
-        if self.encoder in ("lem", "lstm"):
-            # I_t = [pos_x, u1[:, t], u2[:, t], cumsum(dt)_t + pos_t, variables[:, 1:]]  (models_gnn2D.py:421-433)
-            nvar = variables.shape[1] - 1
+        nvar = variables.shape[1] - 1
+        if self.encoder == "lem" and use_persistent(4 + nvar):
+            # I_t = [pos_x, u1[:, t], u2[:, t], cumsum(dt)_t + pos_t, variables[:, 1:]]  (models_gnn2D.py:421-433), written
+            # as the recurrence's zero-padded [T, N, 32] slab by one launch
+            cols = [("static", pos_xf, 0), ("time", u, 0), ("time", u, tw), ("clock",)]
+            cols += [("static", variables_f, 1 + k) for k in range(nvar)]
+            lem_in = ops.lem_inputs(tw, N, cols, clock=dt64.view(-1), node_t=pos_t.double().reshape(-1).contiguous())
+            lem_in._msmp_lem_ninp = 4 + nvar
+            h = mlp2(self.embedding_lem(lem_in), self.lemoutput_mlp)
+        elif self.encoder in ("lem", "lstm"):
             lem_in = torch.empty(tw, N, 4 + nvar, dtype=torch.float32, device=u.device)
             lem_in[:, :, 0] = pos_x.float()[:, 0]
             lem_in[:, :, 1] = u[:, :tw].t()
@@ -121,7 +138,7 @@ class _Solver2F(nn.Module):
 
         h2 = linear_act(h, self.double_mlp[0])                            # [N, 2*128] (models_gnn2D.py:444)
         out = decode(h2, self.output_mlp, u, dt, 2, tw)                   # models_gnn2D.py:448-458
-        return out.to(u_in.dtype)
+        return out if ops_raw_output() else out.to(u_in.dtype)
 
 
 class MP_PDE_Solver2DLEMLinGated(_Solver2F):

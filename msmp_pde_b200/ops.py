@@ -135,6 +135,9 @@ GRAD_SINK = None
 # bench.py's per-kernel pass: no side streams (layers._side_stream returns the current stream), so that the CUDA events
 # around an op time the kernel alone and not its wait for SMs that another stream's kernels hold
 SERIALIZE = False
+# GraphedTrainStep sets this around the model call: the solvers then return their float32 output as it leaves the decoder
+# instead of casting it to the input dtype (the fused criterion below converts on the fly)
+RAW_OUTPUT = False
 _IMG_CACHE: dict = {}
 
 
@@ -492,6 +495,106 @@ def mul_dswish(g, z):
     check(lib.msmp_mul_dswish(g.data_ptr(), z.data_ptr(), out.data_ptr(), z.numel(), _stream()), "msmp_mul_dswish")
     _count(1)
     return out
+
+
+# ---- input assembly (prep.cu) -------------------------------------------------------------------------
+class _LemCol(ctypes.Structure):
+    _fields_ = [("src", ctypes.c_void_p), ("ld", ctypes.c_int), ("off", ctypes.c_int), ("kind", ctypes.c_int),
+                ("reserved", ctypes.c_int)]
+
+
+LEM_COL_STATIC, LEM_COL_TIME, LEM_COL_CLOCK = 0, 1, 2
+
+
+def node_features(u, pos_x, variables, ldu):
+    """(upad [N, ldu] = [u | 0], side [N, 8] = [pos_x, variables..., 0]) from contiguous fp32 u [N,F_u], pos_x [N,1],
+    variables [N,V] in one launch."""
+    N, F_u = u.shape
+    V = variables.shape[1]
+    for t in (u, pos_x, variables):
+        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+            raise ValueError("node_features: contiguous float32 CUDA tensors")
+    upad = torch.empty(N, ldu, dtype=torch.float32, device=u.device)
+    side = torch.empty(N, 8, dtype=torch.float32, device=u.device)
+    check(lib.msmp_node_features(u.data_ptr(), F_u, pos_x.data_ptr(), variables.data_ptr() if V else 0, V, N, upad.data_ptr(),
+                                 ldu, side.data_ptr(), _stream()), "msmp_node_features")
+    _count(1 if N else 0)
+    return upad, side
+
+
+def lem_inputs(T, N, cols, clock=None, node_t=None):
+    """inp [T, N, 32] (zero padded) of the LEM recurrence in one launch.  ``cols``: one entry per input column,
+    ("static", x [N,k] fp32, j) -> x[n, j];  ("time", x [N,k] fp32, j) -> x[n, j + t];  ("clock",) -> float(clock[t] +
+    node_t[n]) with float64 ``clock`` [T] and ``node_t`` [N]."""
+    if not 1 <= len(cols) <= 8:
+        raise ValueError("lem_inputs: 1..8 columns")
+    arr = (_LemCol * len(cols))()
+    keep = []
+    dev = None
+    for i, c in enumerate(cols):
+        if c[0] == "clock":
+            if clock is None or node_t is None or clock.dtype != torch.float64 or node_t.dtype != torch.float64 \
+                    or clock.numel() != T or node_t.numel() != N or not (clock.is_contiguous() and node_t.is_contiguous()):
+                raise ValueError("lem_inputs: the clock column needs contiguous float64 clock [T] and node_t [N]")
+            arr[i] = _LemCol(None, 0, 0, LEM_COL_CLOCK, 0)
+            dev = clock.device
+            continue
+        kind, x, j = c
+        if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.is_contiguous() and x.shape[0] == N):
+            raise ValueError("lem_inputs: column sources are contiguous float32 [N, k] CUDA tensors")
+        span = T if kind == "time" else 1
+        if not 0 <= j <= x.shape[1] - span:
+            raise ValueError("lem_inputs: column offset out of range")
+        arr[i] = _LemCol(x.data_ptr(), x.shape[1], j, LEM_COL_TIME if kind == "time" else LEM_COL_STATIC, 0)
+        keep.append(x)
+        dev = x.device
+    inp = torch.empty(T, N, 32, dtype=torch.float32, device=dev)
+    check(lib.msmp_lem_inputs(ctypes.cast(arr, ctypes.c_void_p), len(cols), _p(clock), _p(node_t), T, N, inp.data_ptr(),
+                              _stream()), "msmp_lem_inputs")
+    _count(1 if T * N else 0)
+    return inp
+
+
+# ---- training criterion: summed squared error on float64 labels (train_helper.py:126) ----------------
+def sse_fwd(pred, y, sse_hi_lo=None):
+    """sum((pred.double() - y) ** 2) as a float64 0-dim tensor; ``sse_hi_lo`` (2 floats) also receives it as a float pair."""
+    if not (pred.is_cuda and pred.dtype == torch.float32 and y.dtype == torch.float64 and pred.shape == y.shape
+            and pred.is_contiguous() and y.is_contiguous() and y.device == pred.device):
+        raise ValueError("sse_fwd: contiguous float32 predictions and float64 labels of the same shape on one CUDA device")
+    n = pred.numel()
+    nbytes = int(lib.msmp_sse_workspace(n))
+    ws = torch.empty(nbytes // 8, dtype=torch.float64, device=pred.device)
+    sse = torch.empty((), dtype=torch.float64, device=pred.device)
+    check(lib.msmp_sse_fwd(pred.data_ptr(), y.data_ptr(), n, ws.data_ptr(), nbytes, sse.data_ptr(), _p(sse_hi_lo), _stream()),
+          "msmp_sse_fwd")
+    _count(2 if n else 1)
+    return sse
+
+
+def sse_bwd(pred, y, g):
+    """d sse / d pred = 2 g (pred - y), evaluated in float64 and rounded once to float32; ``g``: float64 device scalar."""
+    g = g.to(dtype=torch.float64, device=pred.device).contiguous()
+    out = torch.empty_like(pred)
+    check(lib.msmp_sse_bwd(pred.data_ptr(), y.data_ptr(), g.data_ptr(), pred.numel(), out.data_ptr(), _stream()), "msmp_sse_bwd")
+    _count(1)
+    return out
+
+
+class _SSEFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, y, sse_hi_lo):
+        ctx.save_for_backward(pred, y)
+        return sse_fwd(pred, y, sse_hi_lo)
+
+    @staticmethod
+    def backward(ctx, g):
+        pred, y = ctx.saved_tensors
+        return sse_bwd(pred, y, g), None, None
+
+
+def sse_loss(pred, y, sse_hi_lo=None):
+    """Differentiable summed squared error (float64 scalar) of float32 predictions against float64 labels."""
+    return _SSEFn.apply(pred, y, sse_hi_lo)
 
 
 # ---- LEM gate kernels (tensors are contiguous [N,128] slices of the step buffers) -----------------

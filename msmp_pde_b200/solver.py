@@ -7,6 +7,11 @@ from torch import nn
 from . import ops
 from .layers import H, NodeFeatures, Swish, _side_stream, pad32
 
+
+def ops_raw_output() -> bool:
+    """True while GraphedTrainStep wants the solver's float32 output uncast (ops.RAW_OUTPUT)."""
+    return ops.RAW_OUTPUT
+
 _EQ_ORDER_1F = ("alpha", "beta", "gamma", "bc_left", "bc_right", "c", "D", "r")
 
 

@@ -206,8 +206,19 @@ class GraphedTrainStep:
         squared error (fp64 split exactly into two floats) in its two trailing elements."""
         if self.gplan is None:
             self.bucket.zero_()          # with a GradPlan the covered gradients are overwritten, the others zeroed in begin()
-        pred = self.model(self.static)
-        sse = ((pred - self.static.y) ** 2).sum()          # train_helper.py:126 (reduction='sum')
+        from . import ops
+        y = self.static.y
+        ops.RAW_OUTPUT = True          # the solvers hand over their float32 output; foreign modules ignore the switch
+        try:
+            pred = self.model(self.static)
+        finally:
+            ops.RAW_OUTPUT = False
+        fused = (pred.dtype == torch.float32 and y.dtype == torch.float64 and pred.shape == y.shape and pred.is_contiguous()
+                 and y.is_contiguous())
+        if fused:          # train_helper.py:126 (reduction='sum') on float64 labels: msmp_sse_fwd / msmp_sse_bwd
+            sse = ops.sse_loss(pred, y, self.bucket.tail)
+        else:
+            sse = ((pred.to(self.static.x.dtype) - y) ** 2).sum()
         if self.gplan is not None:
             self.gplan.begin()
         try:
@@ -215,10 +226,11 @@ class GraphedTrainStep:
         finally:
             if self.gplan is not None:
                 self.gplan.finish()
-        s64 = sse.detach().double()
-        hi = s64.float()
-        self.bucket.tail[0] = hi
-        self.bucket.tail[1] = (s64 - hi.double()).float()
+        if not fused:
+            s64 = sse.detach().double()
+            hi = s64.float()
+            self.bucket.tail[0] = hi
+            self.bucket.tail[1] = (s64 - hi.double()).float()
 
     def _update(self):
         """loss = sqrt(SSE), gradient scale 1 / (2 loss), optimizer update (and p.grad <- gradient of the loss)."""

@@ -382,3 +382,71 @@ def test_c5_multi_million_node_layer_slices_vs_oracle(n_nodes, degree):
         assert rel_err(out[lo:hi], outr) < OUT_TOL, gi
         assert rel_err(x.grad[lo:hi], xs.grad) < GRAD_TOL, gi
     assert bool(torch.isfinite(out).all()) and bool(torch.isfinite(x.grad).all())
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (37, 50), (6400, 50), (131072, 50)])
+def test_sse_criterion_matches_torch_float64(shape):
+    """msmp_sse_fwd / msmp_sse_bwd (the criterion of the captured step, train_helper.py:126 with float64 labels) against
+    torch's float64 arithmetic: the sum to 1e-13, the float pair that rides in the gradient bucket to 2^-44, the gradient
+    bit-exact for a unit seed (one rounding float64 -> float32 on both sides) and to 1e-7 for a scaled seed; bit-stable."""
+    from msmp_pde_b200 import ops
+    dev = torch.device("cuda:0")
+    gen = torch.Generator(device=dev).manual_seed(shape[0])
+    pred = torch.randn(shape, device=dev, generator=gen).requires_grad_(True)
+    y = torch.randn(shape, device=dev, generator=gen, dtype=torch.float64)
+    tail = torch.zeros(2, device=dev)
+    sse = ops.sse_loss(pred, y, tail)
+    sse.backward()
+    d = pred.detach().double() - y
+    ref = float((d ** 2).sum())
+    assert sse.dtype == torch.float64 and abs(float(sse) - ref) <= 1e-13 * ref
+    assert abs(float(tail[0].double() + tail[1].double()) - float(sse)) <= 2.0 ** -44 * ref
+    assert torch.equal(pred.grad, (2.0 * d).float())
+    pred.grad = None
+    sse2 = ops.sse_loss(pred, y, None)
+    (1.7 * sse2).backward()
+    assert torch.equal(sse2, sse)
+    assert rel_err(pred.grad, 3.4 * d) < 1e-7
+
+
+@pytest.mark.parametrize("N,tw,nvar", [(1, 25, 0), (37, 25, 1), (6400, 25, 2), (4099, 50, 0), (131072, 25, 1)])
+def test_input_assembly_kernels_equal_framework_expressions(N, tw, nvar):
+    """msmp_node_features / msmp_lem_inputs (one launch each) against the slice-copy expressions they replace
+    (layers.NodeFeatures; I_t of models_gnn2D.py:421-433 and models_gnn.py:1357-1360): bit-identical."""
+    from msmp_pde_b200 import ops
+    from msmp_pde_b200.layers import pad32
+    dev = torch.device("cuda:0")
+    gen = torch.Generator(device=dev).manual_seed(N + tw)
+    u = torch.randn(N, 2 * tw, device=dev, generator=gen)
+    pos_x = torch.rand(N, 1, device=dev, generator=gen)
+    pos_t = torch.rand(N, 1, device=dev, generator=gen, dtype=torch.float64)
+    variables = torch.rand(N, 1 + nvar, device=dev, generator=gen)
+    dt64 = torch.cumsum(torch.ones(1, tw, dtype=torch.float64, device=dev) * 0.0371, dim=1)
+    # node features
+    ldu = pad32(2 * tw)
+    upad, side = ops.node_features(u, pos_x, variables, ldu)
+    upad_ref = torch.zeros(N, ldu, device=dev)
+    upad_ref[:, :2 * tw] = u
+    side_ref = torch.zeros(N, 8, device=dev)
+    side_ref[:, 0:1] = pos_x
+    side_ref[:, 1:2 + nvar] = variables
+    assert torch.equal(upad, upad_ref) and torch.equal(side, side_ref)
+    # two-field LEM input slab
+    cols = [("static", pos_x, 0), ("time", u, 0), ("time", u, tw), ("clock",)] + [("static", variables, 1 + k) for k in range(nvar)]
+    inp = ops.lem_inputs(tw, N, cols, clock=dt64.view(-1), node_t=pos_t.reshape(-1).contiguous())
+    ref = torch.zeros(tw, N, 32, device=dev)
+    ref[:, :, 0] = pos_x[:, 0]
+    ref[:, :, 1] = u[:, :tw].t()
+    ref[:, :, 2] = u[:, tw:].t()
+    ref[:, :, 3] = (dt64 + pos_t).float().t()
+    if nvar:
+        ref[:, :, 4:4 + nvar] = variables[:, 1:]
+    assert torch.equal(inp, ref)
+    # one-field slab: [pos_x, u[:, t], variables]
+    u1 = u[:, :tw].contiguous()
+    inp1 = ops.lem_inputs(tw, N, [("static", pos_x, 0), ("time", u1, 0)] + [("static", variables, k) for k in range(1 + nvar)])
+    ref1 = torch.zeros(tw, N, 32, device=dev)
+    ref1[:, :, 0] = pos_x[:, 0]
+    ref1[:, :, 1] = u1.t()
+    ref1[:, :, 2:3 + nvar] = variables
+    assert torch.equal(inp1, ref1)
