@@ -111,7 +111,8 @@ def lem_backward(inp, Y, Z, gates, gY, gZ, dt, packs, persistent, last_only, gs=
         state = ops.lem_tc_bwd_state(gates)
         cur = torch.cuda.current_stream()
         wst = _side_stream(cur, dev, "wgrad")
-        nseg = max(1, min(ops.LEM_BWD_SEGMENTS, T))
+        # GraphedTrainStep's gradient sink holds split-M partials sized for the whole recurrence: one segment there
+        nseg = 1 if gs is not None else max(1, min(ops.LEM_BWD_SEGMENTS, T))
         bounds = [T * i // nseg for i in range(nseg + 1)]
         for i in range(nseg - 1, -1, -1):
             t0, t1 = bounds[i], bounds[i + 1]

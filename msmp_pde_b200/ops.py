@@ -128,6 +128,7 @@ INSTNORM_FUSED = os.environ.get("MSMP_INSTNORM_FUSED", "1") != "0"
 # steps overlap the remaining ones on a side stream (lem._LEMFn.backward).  Measured on the C2 workload after the
 # recurrence kernel got its own MMA warp and 16 epilogue warps: 1 launch 4.11 ms/step, 2: 4.16, 3: 4.19, 5: 4.28,
 # 8: 4.40 -- the co-running GEMMs slow the latency-bound recurrence more than the overlap gains, so the default is 1.
+# Plain autograd path only: under GraphedTrainStep (gradient sink) the recurrence always runs as one launch.
 LEM_BWD_SEGMENTS = int(__import__('os').environ.get('MSMP_LEM_BWD_SEGMENTS', 1))
 # gradsink.GradPlan of the backward pass in flight (set by GraphedTrainStep): the backward Functions then leave their
 # weight gradients in the plan's raw buffer and return None for the parameters; None = plain autograd behaviour.
