@@ -174,7 +174,7 @@ __device__ __forceinline__ void state_store(uint32_t smS, uint32_t off, float v)
 struct LemSmem {
   uint8_t* smS;        // nbuf state tiles of LT_S_BYTES
   uint8_t* smB;        // nst ring stages
-  uint64_t* bars;      // bfull[8], bfree[8], acc, acc_mid
+  uint64_t* bars;      // bfull[8], bfree[8], acc, acc_mid, forward: accG[3], accL
   uint32_t* tmem_slot;
   uint32_t nst;
 };
@@ -200,6 +200,7 @@ __device__ __forceinline__ void lem_init(const LemSmem& m, uint32_t tmem_cols) {
     }
     mbar_init(&m.bars[16], 1);
     mbar_init(&m.bars[17], 1);
+    for (int i = 18; i < 22; ++i) mbar_init(&m.bars[i], 1);      // forward: one barrier per gate block of G and one for L
     fence_barrier_init();
   }
   tc_fence_before();
@@ -272,9 +273,13 @@ __global__ void __launch_bounds__(LF_THREADS, 1) k_lem_fwd_tc(const LemFwdParams
     Epi e = lem_epi(m);
     for (int t = 0; t < p.T; ++t) {
       state_ready_wait();                                   // y_{t-1} tile written, G accumulator of step t-1 consumed
-      gemm_issue<FAST>(e, e.smS, 12, LF_G, false, e.acc);
+      // one commit per gate block (4 chunks = 64 accumulator columns): the epilogue warps turn block g into its gate
+      // while blocks g + 1.. are still on the tensor pipe.  Every barrier completes exactly once per step.
+      gemm_issue<FAST>(e, e.smS, 4, LF_G, false, &m.bars[18]);
+      gemm_issue<FAST>(e, e.smS, 4, LF_G + 64, false, &m.bars[19]);
+      gemm_issue<FAST>(e, e.smS, 4, LF_G + 128, false, &m.bars[20]);
       state_ready_wait();                                   // z_t tile written, L accumulator of step t-1 consumed
-      gemm_issue<FAST>(e, e.smS, 4, LF_L, false, e.acc);
+      gemm_issue<FAST>(e, e.smS, 4, LF_L, false, &m.bars[21]);
     }
   } else {
     Epi e = lem_epi(m);
@@ -335,9 +340,8 @@ __global__ void __launch_bounds__(LF_THREADS, 1) k_lem_fwd_tc(const LemFwdParams
       tc_fence_before();
       state_ready_arrive();
     };
-    auto wait_acc = [&]() {
-      mbar_wait_warp(e.acc, e.nacc & 1);
-      ++e.nacc;
+    auto wait_acc = [&](int b, int t) {          // b: 0..2 = gate block of G, 3 = L; each completes once per step
+      mbar_wait_warp(&m.bars[18 + b], (uint32_t)t & 1u);
       tc_fence_after();
     };
 
@@ -361,42 +365,66 @@ __global__ void __launch_bounds__(LF_THREADS, 1) k_lem_fwd_tc(const LemFwdParams
       // ---- while G^T = W_h y^T runs: this step's input projections -> TMEM
       inproj(t);
       LEM_TICK(1);
-      wait_acc();
+      // ---- gate_z, block by block behind the G GEMM (no global loads: accumulators from TMEM, z_{t-1} from registers).
+      // a and b are parked in the projection columns they consume (gate 0 / gate 1) until gate_y / the z update needs them.
+      wait_acc(0, t);
       LEM_TICK(2);
-      // ---- gate_z (no global loads: accumulators from TMEM, z_{t-1} from registers)
 #pragma unroll
       for (int jj = 0; jj < 32; jj += 8) {
-        uint32_t r0[8], r1[8], r2[8], q0[8], q1[8], q2[8];
+        uint32_t r0[8], q0[8];
         tmem_ld8_nowait(gbuf + jj, r0);
-        tmem_ld8_nowait(gbuf + 64 + jj, r1);
-        tmem_ld8_nowait(gbuf + 128 + jj, r2);
         tmem_ld8_nowait(tbase + LF_PRE + jj, q0);
-        tmem_ld8_nowait(tbase + LF_PRE + 64 + jj, q1);
-        tmem_ld8_nowait(tbase + LF_PRE + 128 + jj, q2);
         tmem_ld_wait();
         float av[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          const int j = j0 + jj + q;
           const float a = p.dt * sigmoid_r(__uint_as_float(r0[q]) + __uint_as_float(q0[q]));
+          av[q] = a;
+          g_t[(size_t)(j0 + jj + q) * 512 + c] = a;
+        }
+        tmem_st8(tbase + LF_PRE + jj, av);
+      }
+      wait_acc(1, t);
+#pragma unroll
+      for (int jj = 0; jj < 32; jj += 8) {
+        uint32_t r1[8], q1[8];
+        tmem_ld8_nowait(gbuf + 64 + jj, r1);
+        tmem_ld8_nowait(tbase + LF_PRE + 64 + jj, q1);
+        tmem_ld_wait();
+        float bv[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
           const float b = p.dt * sigmoid_r(__uint_as_float(r1[q]) + __uint_as_float(q1[q]));
+          bv[q] = b;
+          g_t[(size_t)(j0 + jj + q) * 512 + 128 + c] = b;
+        }
+        tmem_st8(tbase + LF_PRE + 64 + jj, bv);
+      }
+      tmem_st_wait();
+      wait_acc(2, t);
+#pragma unroll
+      for (int jj = 0; jj < 32; jj += 8) {
+        uint32_t r2[8], q2[8], rb[8];
+        tmem_ld8_nowait(gbuf + 128 + jj, r2);
+        tmem_ld8_nowait(tbase + LF_PRE + 128 + jj, q2);
+        tmem_ld8_nowait(tbase + LF_PRE + 64 + jj, rb);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int j = j0 + jj + q;
+          const float b = __uint_as_float(rb[q]);
           const float zc = tanh_r(__uint_as_float(r2[q]) + __uint_as_float(q2[q]));
           const float zn = (1.f - b) * zreg[jj + q] + b * zc;
           zreg[jj + q] = zn;
-          av[q] = a;
-          g_t[(size_t)j * 512 + c] = a;
-          g_t[(size_t)j * 512 + 128 + c] = b;
           g_t[(size_t)j * 512 + 256 + c] = zc;
           if (row0 + j < p.N) znext[(size_t)j * 128 + c] = zn;
           state_store<FAST>(e.smS, state_off(j, c), zn);      // z_t: B operand of the L GEMM
         }
-        tmem_st8(tbase + LF_PRE + jj, av);      // the gate-0 projection columns are consumed: stash a for gate_y there
       }
-      tmem_st_wait();
       publish_to_mma();
       LEM_TICK(3);
       // ---- L^T = Wz_h z^T
-      wait_acc();
+      wait_acc(3, t);
       LEM_TICK(4);
       // ---- gate_y
 #pragma unroll
