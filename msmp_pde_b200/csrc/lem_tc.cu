@@ -346,7 +346,7 @@ __global__ void __launch_bounds__(LF_THREADS, 1) k_lem_fwd_tc(const LemFwdParams
     };
 
     // initial state: registers + the y_{-1} tile
-    float yreg[32], zreg[32];
+    float yreg[32], zreg[32], hold[32];          // hold: zc / tanh(L) of the step between their use and their global store
 #pragma unroll
     for (int q = 0; q < 32; ++q) {
       const int g = row0 + j0 + q;
@@ -416,13 +416,19 @@ __global__ void __launch_bounds__(LF_THREADS, 1) k_lem_fwd_tc(const LemFwdParams
           const float zc = tanh_r(__uint_as_float(r2[q]) + __uint_as_float(q2[q]));
           const float zn = (1.f - b) * zreg[jj + q] + b * zc;
           zreg[jj + q] = zn;
-          g_t[(size_t)j * 512 + 256 + c] = zc;
-          if (row0 + j < p.N) znext[(size_t)j * 128 + c] = zn;
+          hold[jj + q] = zc;
           state_store<FAST>(e.smS, state_off(j, c), zn);      // z_t: B operand of the L GEMM
         }
       }
       publish_to_mma();
       LEM_TICK(3);
+      // the global stores of zc and z_t are off the recurrence's critical path: they go out while the L GEMM runs
+#pragma unroll
+      for (int q = 0; q < 32; ++q) {
+        const int j = j0 + q;
+        g_t[(size_t)j * 512 + 256 + c] = hold[q];
+        if (row0 + j < p.N) znext[(size_t)j * 128 + c] = zreg[q];
+      }
       // ---- L^T = Wz_h z^T
       wait_acc(3, t);
       LEM_TICK(4);
@@ -441,13 +447,19 @@ __global__ void __launch_bounds__(LF_THREADS, 1) k_lem_fwd_tc(const LemFwdParams
           const float tl = tanh_r(__uint_as_float(r3[q]) + __uint_as_float(q3[q]));
           const float yn = (1.f - a) * yreg[jj + q] + a * tl;
           yreg[jj + q] = yn;
-          g_t[(size_t)j * 512 + 384 + c] = tl;
-          if (row0 + j < p.N) ynext[(size_t)j * 128 + c] = yn;
+          hold[jj + q] = tl;
           state_store<FAST>(e.smS, state_off(j, c), yn);      // y_t: B operand of the next G GEMM
         }
       }
       if (t + 1 < p.T) publish_to_mma();
       LEM_TICK(5);
+      // ... and those of tanh(L) and y_t while the next step's G GEMM runs
+#pragma unroll
+      for (int q = 0; q < 32; ++q) {
+        const int j = j0 + q;
+        g_t[(size_t)j * 512 + 384 + c] = hold[q];
+        if (row0 + j < p.N) ynext[(size_t)j * 128 + c] = yreg[q];
+      }
     }
   }
   tc_fence_before();
