@@ -185,19 +185,35 @@ __global__ void __launch_bounds__(1024) k_in_bwd_chunk(const float* __restrict__
   }
 }
 
-// gm[g][q][c] = (sum over the graph's chunks, fixed order) / n_g
-__global__ void __launch_bounds__(512) k_in_bwd_finalize(const float* __restrict__ part,
-                                                         const int* __restrict__ chunk_begin,
-                                                         const int* __restrict__ chunk_end,
-                                                         const int* __restrict__ graph_chunk_ptr,
-                                                         float* __restrict__ gm) {
-  const int g = blockIdx.x, q = threadIdx.x >> 7, c = threadIdx.x & 127;
-  float s = 0.f, n = 0.f;
-  for (int k = graph_chunk_ptr[g]; k < graph_chunk_ptr[g + 1]; ++k) {
-    s += part[((size_t)k * 4 + q) * 128 + c];
+// gm[g][q][c] = (sum over the graph's chunks, fixed order) / n_g.  Eight slices of 128 threads sum every 8th chunk each (all
+// four sums of a channel in one thread: four independent chains of L2 loads), then the eight partial results are added in slice
+// order -- one serial chain over the 128 chunks of a C4 lattice graph took 24 us per launch.  With one chunk per graph the result
+// is that chunk's sum, bit for bit (the fused single-chunk path below relies on it).
+__global__ void __launch_bounds__(128 * IN_FIN_SLICES) k_in_bwd_finalize(const float* __restrict__ part,
+                                                                         const int* __restrict__ chunk_begin,
+                                                                         const int* __restrict__ chunk_end,
+                                                                         const int* __restrict__ graph_chunk_ptr,
+                                                                         float* __restrict__ gm) {
+  __shared__ float sh[IN_FIN_SLICES][5][128];
+  const int g = blockIdx.x, sl = threadIdx.x >> 7, c = threadIdx.x & 127;
+  float s[4] = {0.f, 0.f, 0.f, 0.f}, n = 0.f;
+  for (int k = graph_chunk_ptr[g] + sl; k < graph_chunk_ptr[g + 1]; k += IN_FIN_SLICES) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) s[q] += part[((size_t)k * 4 + q) * 128 + c];
     n += (float)(chunk_end[k] - chunk_begin[k]);
   }
-  gm[((size_t)g * 4 + q) * 128 + c] = s / fmaxf(n, 1.f);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) sh[sl][q][c] = s[q];
+  sh[sl][4][c] = n;
+  __syncthreads();
+  if (sl >= 4) return;
+  const int q = sl;
+  float t = sh[0][q][c], nt = sh[0][4][c];
+  for (int s2 = 1; s2 < IN_FIN_SLICES; ++s2) {
+    t += sh[s2][q][c];
+    nt += sh[s2][4][c];
+  }
+  gm[((size_t)g * 4 + q) * 128 + c] = t / fmaxf(nt, 1.f);
 }
 
 // dy = rstd * (do - mean(do) - o * mean(do * o)); four channels per thread (16-byte accesses; same arithmetic per element)
@@ -421,7 +437,7 @@ extern "C" int msmp_instnorm_bwd(const float* dout, const float* y0, const float
   float* gm = part + (size_t)nchunks * 512;
   k_in_bwd_chunk<<<nchunks, 1024, 0, stream>>>(dout, y0, y1, ld, stat, h, chunk_begin, chunk_end, node_graph, part, B, mode);
   MSMP_CHECK_LAUNCH();
-  k_in_bwd_finalize<<<B, 512, 0, stream>>>(part, chunk_begin, chunk_end, graph_chunk_ptr, gm);
+  k_in_bwd_finalize<<<B, 128 * IN_FIN_SLICES, 0, stream>>>(part, chunk_begin, chunk_end, graph_chunk_ptr, gm);
   MSMP_CHECK_LAUNCH();
   k_in_bwd_apply<<<(N * 32 + 255) / 256, 256, 0, stream>>>(dout, y0, y1, ld, stat, h, gm, node_graph, dy0, dy1, lddy, dh,
                                                             N, B, mode);
