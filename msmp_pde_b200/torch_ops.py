@@ -104,5 +104,41 @@ def _(inputs, weights, weights_lin_z, bias, bias_lin_z, y0, z0, dt):
             f(T, N, (ninp + 31) // 32 * 32)]
 
 
+@custom_op("msmp::sse", mutates_args=(), device_types="cuda")
+def sse(pred: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+    """sum((pred.double() - labels) ** 2) as a float64 scalar: MSELoss(reduction='sum') of the training loop
+    (experiments/train_helper.py:126, train.py:413) on float32 predictions and float64 labels -- msmp_sse_fwd
+    (deterministic block sums)."""
+    return ops.sse_fwd(pred.contiguous(), labels.contiguous())
+
+
+@sse.register_fake
+def _(pred, labels):
+    return pred.new_empty((), dtype=torch.float64)
+
+
+@custom_op("msmp::sse_grad", mutates_args=(), device_types="cuda")
+def sse_grad(pred: torch.Tensor, labels: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
+    """d sse / d pred = 2 g (pred - labels), evaluated in float64 and rounded once to float32 -- msmp_sse_bwd."""
+    return ops.sse_bwd(pred.contiguous(), labels.contiguous(), g)
+
+
+@sse_grad.register_fake
+def _(pred, labels, g):
+    return torch.empty_like(pred)
+
+
+def _sse_setup(ctx, inputs, output):
+    ctx.save_for_backward(*inputs)
+
+
+def _sse_backward(ctx, g):
+    pred, labels = ctx.saved_tensors
+    return torch.ops.msmp.sse_grad(pred, labels, g), None
+
+
+sse.register_autograd(_sse_backward, setup_context=_sse_setup)
+
+
 def names():
-    return ["scatter_mean", "edge_mlp_scatter", "linear", "linear_wgrad", "instance_norm", "lem_forward"]
+    return ["scatter_mean", "edge_mlp_scatter", "linear", "linear_wgrad", "instance_norm", "lem_forward", "sse", "sse_grad"]

@@ -46,3 +46,13 @@ def test_custom_ops_match_reference_math():
     xr = xin.double().view(3, 50, 128)
     refn = (xr - xr.mean(1, keepdim=True)) / torch.sqrt(xr.var(1, unbiased=False, keepdim=True) + 1e-5)
     assert rel_err(o, refn.view(N, 128)) < 1e-5
+    # training criterion (float32 predictions, float64 labels) with its registered autograd formula
+    pred = torch.randn(N, 25, generator=g).to(dev).requires_grad_(True)
+    lab = torch.randn(N, 25, generator=g, dtype=torch.float64).to(dev)
+    s = torch.ops.msmp.sse(pred, lab)
+    torch.sqrt(s).backward()
+    d = pred.detach().double() - lab
+    sref = (d ** 2).sum()
+    assert s.dtype == torch.float64 and abs(float(s.detach()) - float(sref)) < 1e-13 * float(sref)
+    assert rel_err(pred.grad, d / torch.sqrt(sref)) < 1e-7
+    torch.library.opcheck(torch.ops.msmp.sse.default, (pred.detach(), lab), test_utils=("test_schema", "test_faketensor"))
