@@ -288,6 +288,16 @@ int msmp_lem_inputs(const msmp_lem_col* cols, int ncols, const double* clock, co
 int msmp_node_features(const float* u, int F_u, const float* pos_x, const float* variables, int V, int N, float* upad,
                        int ldu, float* side, cudaStream_t stream);
 
+/* ---- G^2 gate statistic (MP_PDE_Solver2DLEMLinG2, experiments/models_gnn2D.py:598-603) ------------------------------
+ * out[s] = inv[s] * sum over the out-edges e of node s, in CSC order, of (t[s] - t[dst[e]])^2 -- what
+ * torch_scatter.scatter((x_i - x_j)^2, edge_index[0], reduce='mean') computes, without the [E,128] intermediate and
+ * without atomics; rows of 128 floats; src / dst in CSR (destination-sorted) edge order, csc_perm = CSR edge ids sorted by
+ * source, colptr / rowptr the matching offsets, inv[s] = 1 / max(out-degree, 1).  msmp_g2_bwd: dt = d out / d t applied to g. */
+int msmp_g2_fwd(const float* t, const int* colptr, const int* csc_perm, const int* dst, const float* inv, float* out, int N,
+                cudaStream_t stream);
+int msmp_g2_bwd(const float* t, const float* g, const int* colptr, const int* csc_perm, const int* src, const int* dst,
+                const int* rowptr, const float* inv, float* dt, int N, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -82,6 +82,8 @@ _SIGS = {
     "msmp_loss_scalars": (I, [P, P, P, P]),
     "msmp_lem_inputs": (I, [P, I, P, P, I, I, P, P]),
     "msmp_node_features": (I, [P, I, P, P, I, I, P, I, P, P]),
+    "msmp_g2_fwd": (I, [P, P, P, P, P, P, I, P]),
+    "msmp_g2_bwd": (I, [P, P, P, P, P, P, P, P, P, I, P]),
     "msmp_sse_workspace": (S, [S]),
     "msmp_sse_fwd": (I, [P, P, S, P, S, P, P, P]),
     "msmp_sse_bwd": (I, [P, P, P, S, P, P]),

@@ -164,13 +164,31 @@ class _SourceMeanFn(torch.autograd.Function):
         return (g * ctx.inv[:, None])[topo.src.long()], None
 
 
+class _G2MeanFn(torch.autograd.Function):
+    """mean over a node's out-edges of (t[src] - t[dst])^2 in one launch per direction (msmp_g2_fwd / msmp_g2_bwd): no
+    [E,128] gathers, no atomics in the backward pass."""
+
+    @staticmethod
+    def forward(ctx, t, topo):
+        outdeg = (topo.colptr[1:] - topo.colptr[:-1]).clamp(min=1).float()
+        inv = (1.0 / outdeg).contiguous()
+        t = t.contiguous()
+        ctx.topo = topo
+        ctx.save_for_backward(t, inv)
+        return ops.g2_fwd(t, topo, inv)
+
+    @staticmethod
+    def backward(ctx, g):
+        t, inv = ctx.saved_tensors
+        return ops.g2_bwd(t, g, ctx.topo, inv), None
+
+
 def _g2_pair(gate_layer, main_layer, h, feat, topo):
     """models_gnn2D.py:598-603: tau = tanh(mean over out-edges of |t_src - t_dst|^2), t = swish(gate layer output)."""
     from .layers import instance_norm
     t = gate_layer.forward_prepared(h, feat, topo)
     t = t * torch.sigmoid(t)
-    src, dst = topo.src.long(), topo.dst.long()            # CSR (destination-sorted) edge order
-    tau = torch.tanh(_SourceMeanFn.apply((t[src] - t[dst]) ** 2, topo))
+    tau = torch.tanh(_G2MeanFn.apply(t, topo))
     m = main_layer.forward_prepared(h, feat, topo)
     return (1 - tau) * h + tau * (m * torch.sigmoid(m))
 

@@ -556,6 +556,29 @@ def lem_inputs(T, N, cols, clock=None, node_t=None):
     return inp
 
 
+# ---- G^2 gate statistic (models_gnn2D.py:598-603) ------------------------------------------------------
+def g2_fwd(t, topo, inv):
+    """out[s] = inv[s] * sum_{e: src e = s} (t[s] - t[dst e])^2 (CSC order), [N,128] fp32."""
+    if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.shape == (topo.N, H)):
+        raise ValueError("g2_fwd: contiguous float32 [N,128] CUDA tensor")
+    out = torch.empty_like(t)
+    check(lib.msmp_g2_fwd(t.data_ptr(), topo.colptr.data_ptr(), topo.csc_perm.data_ptr(), topo.dst.data_ptr(), inv.data_ptr(),
+                          out.data_ptr(), topo.N, _stream()), "msmp_g2_fwd")
+    _count(1 if topo.N else 0)
+    return out
+
+
+def g2_bwd(t, g, topo, inv):
+    """d/dt of g2_fwd applied to g (deterministic: one pass over a node's out-edges, one over its in-edges)."""
+    g = g.contiguous()
+    dt = torch.empty_like(t)
+    check(lib.msmp_g2_bwd(t.data_ptr(), g.data_ptr(), topo.colptr.data_ptr(), topo.csc_perm.data_ptr(), topo.src.data_ptr(),
+                          topo.dst.data_ptr(), topo.rowptr.data_ptr(), inv.data_ptr(), dt.data_ptr(), topo.N, _stream()),
+          "msmp_g2_bwd")
+    _count(1 if topo.N else 0)
+    return dt
+
+
 # ---- training criterion: summed squared error on float64 labels (train_helper.py:126) ----------------
 def sse_fwd(pred, y, sse_hi_lo=None):
     """sum((pred.double() - y) ** 2) as a float64 0-dim tensor; ``sse_hi_lo`` (2 floats) also receives it as a float pair."""

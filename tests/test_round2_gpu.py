@@ -450,3 +450,35 @@ def test_input_assembly_kernels_equal_framework_expressions(N, tw, nvar):
     ref1[:, :, 1] = u1.t()
     ref1[:, :, 2:3 + nvar] = variables
     assert torch.equal(inp1, ref1)
+
+
+def test_g2_gate_statistic_equals_framework_expression():
+    """msmp_g2_fwd / msmp_g2_bwd (the G^2 gate of MP_PDE_Solver2DLEMLinG2, models_gnn2D.py:598-603) on an irregular kNN graph
+    (out-degrees 0..many): forward and backward equal the float64 evaluation of the framework expression (gather, square,
+    scatter-mean by source) to 1e-6, the forward also the deterministic segmented mean of the gathered squares; bit-stable."""
+    from msmp_pde_b200 import synth
+    from msmp_pde_b200.graph import get_topology
+    from msmp_pde_b200.models_gnn2D import _G2MeanFn, _SourceMeanFn
+    dev = torch.device("cuda:0")
+    _, data, _ = synth.config_c3(B=5, nx=100, seed=2)
+    ei, batch = data.edge_index.to(dev), data.batch.to(dev)
+    N = data.x.shape[0]
+    topo = get_topology(ei, batch, N)
+    gen = torch.Generator(device=dev).manual_seed(3)
+    t = torch.randn(N, 128, device=dev, generator=gen).requires_grad_(True)
+    w = torch.randn(N, 128, device=dev, generator=gen)
+    out = _G2MeanFn.apply(t, topo)
+    (out * w).sum().backward()
+    src, dst = topo.src.long(), topo.dst.long()
+    ref = _SourceMeanFn.apply((t.detach()[src] - t.detach()[dst]) ** 2, topo)
+    assert rel_err(out, ref) < 1e-6, "forward vs segmented mean of the gathered squares"      # (the kernel fuses x * x into the add)
+    t64 = t.detach().double().requires_grad_(True)
+    cnt = torch.bincount(src, minlength=N).clamp(min=1).double()
+    ref64 = torch.zeros(N, 128, dtype=torch.float64, device=dev).index_add_(0, src, (t64[src] - t64[dst]) ** 2) / cnt[:, None]
+    (ref64 * w.double()).sum().backward()
+    assert rel_err(out, ref64) < 1e-6, "forward vs float64"
+    assert rel_err(t.grad, t64.grad) < 1e-6, "backward vs float64"
+    g1 = t.grad.clone()
+    t.grad = None
+    (_G2MeanFn.apply(t, topo) * w).sum().backward()
+    assert torch.equal(t.grad, g1)
