@@ -78,11 +78,12 @@ class _Solver2F(nn.Module):
     def _clock(self, device):
         """(cumsum(dt) in float64 [1, tw], the same rounded to float32): constants of the model, built once per device."""
         c = self.__dict__.get("_msmp_clock")
-        if c is None or c[0].device != device:
+        key = (device, float(self.pde.dt), self.time_window)
+        if c is None or c[0] != key:
             dt64 = torch.cumsum(torch.ones(1, self.time_window, dtype=torch.float64, device=device) * float(self.pde.dt), dim=1)
-            c = (dt64, dt64.float())
+            c = (key, dt64, dt64.float())
             self.__dict__["_msmp_clock"] = c
-        return c
+        return c[1], c[2]
 
     def forward(self, data) -> torch.Tensor:
         tw = self.time_window
