@@ -94,6 +94,28 @@ def test_topology_bit_exact_vs_numpy():
     assert small.one_chunk_per_graph and small.nchunks == small.B == 1
 
 
+def test_new_entry_points_host_side():
+    """Host-only checks of the round-2 additions: workspace query of the criterion kernel, argument validation of the
+    input-assembly / criterion / G^2 wrappers (CPU tensors are rejected: there is no CPU path behind them)."""
+    import torch
+    from msmp_pde_b200 import _lib, ops
+    assert _lib.lib.msmp_sse_workspace(0) == 8 and _lib.lib.msmp_sse_workspace(4096) == 16 and _lib.lib.msmp_sse_workspace(4097) == 24
+    u, px, v = torch.zeros(4, 50), torch.zeros(4, 1), torch.zeros(4, 2)
+    with pytest.raises(ValueError):
+        ops.node_features(u, px, v, 64)
+    with pytest.raises(ValueError):
+        ops.lem_inputs(25, 4, [("static", px, 0), ("time", u, 0)])
+    with pytest.raises(ValueError):
+        ops.lem_inputs(25, 4, [])
+    with pytest.raises(ValueError):
+        ops.sse_fwd(torch.zeros(4, 25), torch.zeros(4, 25, dtype=torch.float64))
+    # the C entry points validate their arguments before touching the device
+    assert _lib.lib.msmp_sse_fwd(0, 0, 0, 0, 0, 0, 0, 0) != 0
+    assert _lib.lib.msmp_lem_inputs(0, 0, 0, 0, 1, 1, 0, 0) != 0
+    assert _lib.lib.msmp_node_features(0, 0, 0, 0, 0, 1, 0, 0, 0, 0) != 0
+    assert _lib.lib.msmp_g2_fwd(0, 0, 0, 0, 0, 0, 1, 0) != 0
+
+
 def test_no_cpu_fallback():
     from msmp_pde_b200 import models_gnn, synth
     pde, data, meta = synth.config_c1(B=1, nx=20)
